@@ -1,0 +1,194 @@
+/*
+ * liblmc -- B200-native lattice Monte-Carlo engine: C ABI.
+ *
+ * This is the drop-in boundary for smol's per-flip hot path.  smol has no FFI of its own for
+ * this path: the native boundary in the reference is the set of Cython cpdef methods taking
+ * typed memoryviews.  Each entry point below names the reference interface it replaces
+ * (paths relative to the smol repository root):
+ *
+ *   lmc_model_create      <- ClusterExpansionProcessor.__init__ table build
+ *                            (smol/moca/processor/expansion.py:120-156, 344-392),
+ *                            OrbitContainer / IntArray2DContainer (smol/utils/cluster/container.pyx:21-341),
+ *                            EwaldProcessor tables (smol/moca/processor/ewald.py:76-101),
+ *                            ChemicalPotentialManager._build_table (smol/moca/ensemble.py:89-99),
+ *                            Sublattice (smol/moca/sublattice.py:23-110)
+ *   lmc_full_features     <- ClusterSpaceEvaluator.correlations_from_occupancy / interactions_from_occupancy
+ *                            (smol/utils/cluster/evaluator.pyx:121-209), EwaldProcessor.compute_feature_vector
+ *                            (smol/moca/processor/ewald.py:128-145), Ensemble.compute_feature_vector
+ *                            (smol/moca/ensemble.py:323-351) -- batched over walkers
+ *   lmc_delta_features    <- ClusterSpaceEvaluator.delta_correlations_from_occupancies /
+ *                            delta_interactions_from_occupancies (evaluator.pyx:211-317),
+ *                            delta_ewald_single_flip (smol/utils/cluster/ewald.pyx:9-59),
+ *                            Ensemble.compute_feature_vector_change (ensemble.py:353-376) -- batched
+ *   lmc_run               <- Sampler.sample inner loops (smol/moca/sampler/sampler.py:195-210, 436-440):
+ *                            MCKernel.single_step (smol/moca/kernel/base.py:145-166),
+ *                            Flip/Swap/TableFlip.propose_step (smol/moca/kernel/mcusher.py:154-200, 553-711),
+ *                            Metropolis / WangLandau accept (kernel/metropolis.py:31-49,
+ *                            kernel/wanglandau.py:186-266)
+ *   lmc_cast_*            <- the int32 occupancy dtype contract (sampler.py:406)
+ *
+ * Conventions: every function returns 0 on success, <0 on error (message via lmc_last_error);
+ * nothing throws across the ABI; no torch types.  Pointers named *_dev are DEVICE pointers owned
+ * by the caller (PyTorch tensors in the Python host); model tables are HOST pointers copied to
+ * device memory owned by the handle.  `stream` is a cudaStream_t passed as void*; launches are
+ * asynchronous on it.  A handle is bound to the device current at creation, one host thread per
+ * handle.
+ */
+#ifndef LMC_H_
+#define LMC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMC_ABI_VERSION 3
+#define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
+#define LMC_MAX_SUBLATTICES 8
+#define LMC_MAX_CODES 8       /* species codes per sublattice */
+#define LMC_MAX_FLIPS 4       /* changed sites per attempted step */
+#define LMC_MAX_DIMS 16       /* species counts tracked by the table-flip usher */
+#define LMC_MAX_TABLE_FLIPS 8
+
+typedef struct LmcModel LmcModel; /* opaque */
+
+/* All arrays are host pointers, C-contiguous. */
+typedef struct LmcModelDesc {
+  uint32_t abi_version;
+  int32_t num_sites;        /* N */
+  int32_t num_features;     /* F = len(natural_parameters) */
+  int32_t num_ce_features;  /* features produced by the cluster part (corr functions or orbits) */
+  int32_t supercell_size;   /* number of primitive cells (Processor.size) */
+  double feature0;          /* features[0]: size (CE) or offset*size (decomposition) */
+  const double* natural_parameters; /* [F] */
+
+  /* orbit tables */
+  int32_t num_orbits;            /* orbits with clusters (empty cluster excluded) */
+  const int32_t* orb_tab_off;    /* [num_orbits] offset of the orbit's K*T block in ftab */
+  const int32_t* orb_tab_len;    /* [num_orbits] T = flattened tensor length */
+  const int32_t* orb_nfunc;      /* [num_orbits] K = functions (bit combos); 1 for decomposition */
+  const int32_t* orb_fidx;       /* [num_orbits] first feature index (bit_id or orbit id) */
+  const int32_t* orb_csize;      /* [num_orbits] sites per cluster */
+  const int32_t* orb_stride;     /* [num_orbits][LMC_MAX_CLUSTER_SITES] flat tensor strides */
+  const double* orb_weight;      /* [num_orbits] size / (total cluster rows of the orbit) */
+  const double* ftab;            /* [ftab_len] feature tensors, orbit-major then function-major */
+  int64_t ftab_len;
+
+  /* full evaluation rows (clusterspace.get_orbit_indices layout, padded to 4 sites) */
+  const int64_t* orb_row_off;    /* [num_orbits+1] */
+  const uint16_t* full_rows;     /* [rows][4] site indices; unused slots repeat site 0 with stride 0 */
+
+  /* per-site local records (rows containing the site), sorted by orbit */
+  int32_t num_classes;
+  const int32_t* cls_orbit;      /* [num_classes] orbit index of the class */
+  const int32_t* cls_stride;     /* [num_classes][4]: strides of the 3 other sites, self stride */
+  const int64_t* site_rec_off;   /* [N+1] */
+  const uint16_t* site_rec;      /* [records][4]: 3 other site indices, class id */
+  const int64_t* site_seg_off;   /* [N+1] */
+  const int32_t* site_seg;       /* [segments][3]: first record (site relative), count, orbit */
+
+  /* Ewald (optional: ewald_size == 0 disables) */
+  int32_t ewald_size;            /* E */
+  int32_t ewald_width;           /* columns of ewald_inds */
+  const double* ewald_matrix;    /* [E][E] */
+  const int32_t* ewald_inds;     /* [N][ewald_width], -1 = vacancy */
+  int32_t ewald_feature;         /* feature index of the Ewald term */
+
+  /* chemical potentials (optional: mu_width == 0 disables) */
+  int32_t mu_width;
+  const double* mu_table;        /* [N][mu_width] */
+  int32_t mu_feature;            /* feature index of the chemical work (natural parameter -1) */
+
+  /* active sublattices */
+  int32_t num_sublattices;
+  const int32_t* sl_site_off;    /* [num_sublattices+1] offsets into sl_sites */
+  const int32_t* sl_sites;       /* active site indices, in Sublattice.active_sites order */
+  const int32_t* sl_ncodes;      /* [num_sublattices] */
+  const int32_t* sl_codes;       /* [num_sublattices][LMC_MAX_CODES] encoding */
+  const double* sl_prob;         /* [num_sublattices] proposal probabilities */
+
+  /* table-flip usher (optional: tf_num_flips == 0 disables) */
+  int32_t tf_num_dims;           /* d: one per (sublattice, species) over ALL sublattices */
+  int32_t tf_num_flips;          /* rows of the flip table */
+  const int32_t* tf_table;       /* [tf_num_flips][tf_num_dims] "counts" format */
+  const double* tf_weights;      /* [2*tf_num_flips] forward/backward weights */
+  const int32_t* tf_max_n;       /* [tf_num_dims] active sites of the dim's sublattice */
+  const int32_t* tf_dim_sl;      /* [tf_num_dims] ACTIVE sublattice index of the dim, -1 if inactive */
+  const int32_t* tf_dim_code;    /* [tf_num_dims] species code of the dim */
+  double tf_swap_weight;
+} LmcModelDesc;
+
+enum { LMC_USHER_FLIP = 0, LMC_USHER_SWAP = 1, LMC_USHER_TABLEFLIP = 2 };
+enum { LMC_KERNEL_METROPOLIS = 0, LMC_KERNEL_WANGLANDAU = 1 };
+
+typedef struct LmcWangLandau {
+  double min_enthalpy, max_enthalpy, bin_size, flatness, mod_update;
+  int32_t num_bins, check_period, update_period, reserved;
+  /* per-walker state, device pointers */
+  double* entropy_dev;        /* [W][num_bins] */
+  int64_t* histogram_dev;     /* [W][num_bins] */
+  int64_t* occurrences_dev;   /* [W][num_bins] */
+  double* mean_features_dev;  /* [W][num_bins][F] */
+  double* mod_factor_dev;     /* [W] */
+  int64_t* steps_counter_dev; /* [W] valid-state counter (wanglandau.py:230-232) */
+} LmcWangLandau;
+
+typedef struct LmcRunConfig {
+  int32_t num_walkers;        /* W walkers resident on this device */
+  int32_t walker_id_base;     /* global id of walker 0 (RNG counter word 3): rank sharding */
+  int32_t usher;              /* LMC_USHER_* */
+  int32_t kernel;             /* LMC_KERNEL_* */
+  int64_t num_samples;        /* S sampling intervals */
+  int32_t thin_by;            /* steps per interval */
+  int32_t group_size;         /* lanes cooperating on one walker: 0 = auto, else 1..32 (power of 2) */
+  int32_t block_threads;      /* 0 = auto */
+  int32_t reserved;
+  uint64_t step_begin;        /* global index of the first step (RNG counter words 0,1) */
+  const uint64_t* seeds_dev;  /* [W] Philox key per walker */
+  const double* beta_dev;     /* [W] 1/(kB T); ignored by Wang-Landau */
+  /* state, in/out */
+  int8_t* occ_dev;            /* [W][row_stride] int8 codes, row_stride = lmc_row_stride(N) */
+  double* features_dev;       /* [W][F] running features */
+  double* enthalpy_dev;       /* [W] running enthalpy */
+  /* per-sample traces, each may be NULL */
+  int8_t* trace_occ_dev;      /* [S][W][N] */
+  double* trace_features_dev; /* [S][W][F] */
+  double* trace_enthalpy_dev; /* [S][W] */
+  uint8_t* trace_accepted_dev;/* [S][W] flag of the LAST step of the interval (sampler.py:199-201) */
+  int32_t* trace_naccepted_dev;/* [S][W] accepted steps in the interval (engine extension) */
+  LmcWangLandau wl;           /* used when kernel == LMC_KERNEL_WANGLANDAU */
+} LmcRunConfig;
+
+int lmc_version(void);
+const char* lmc_last_error(void);
+int lmc_row_stride(int num_sites); /* bytes per walker row of occ_dev (16-byte multiple) */
+
+int lmc_model_create(const LmcModelDesc* desc, LmcModel** out);
+int lmc_model_destroy(LmcModel* model);
+int lmc_model_num_features(const LmcModel* model);
+
+/* int32 [W][N] <-> int8 [W][row_stride] */
+int lmc_cast_i32_to_i8(const int32_t* src_dev, int8_t* dst_dev, int num_walkers, int num_sites, void* stream);
+int lmc_cast_i8_to_i32(const int8_t* src_dev, int32_t* dst_dev, int64_t num_rows, int num_sites,
+                       int src_row_stride, void* stream);
+
+/* features_dev [W][F] <- full evaluation of every walker's occupancy; enthalpy_dev [W] may be NULL */
+int lmc_full_features(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* features_dev,
+                      double* enthalpy_dev, void* stream);
+
+/* out_dev [W][F] <- feature change of walker w for its k flips (sites/codes [W][k] int32, applied
+ * sequentially, chemical work against the pre-step occupancy) */
+int lmc_delta_features(const LmcModel* model, const int8_t* occ_dev, int num_walkers, const int32_t* sites_dev,
+                       const int32_t* codes_dev, int num_flips, double* out_dev, void* stream);
+
+/* advance every walker by num_samples*thin_by attempted steps */
+int lmc_run(const LmcModel* model, const LmcRunConfig* cfg, void* stream);
+
+/* number of kernel launches issued by this library since load (for bench accounting) */
+int64_t lmc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMC_H_ */

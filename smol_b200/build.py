@@ -1,0 +1,70 @@
+"""Build liblmc.so (sm_100a) in-tree with nvcc.  ``python -m smol_b200.build [--force]``."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "_lib")
+LIB = os.path.join(LIBDIR, "liblmc.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+GROUPS = (4, 8, 16, 32)
+
+
+def _sources():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
+        [os.path.join(HERE, "..", "include", "lmc.h")]
+    return deps
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(s) <= t for s in _sources())
+
+
+def _compile(args):
+    src, obj, extra = args
+    cmd = [NVCC, *FLAGS, *extra, "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return cmd, r
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if up_to_date() and not force:
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = [(os.path.join(CSRC, "lmc_api.cu"), os.path.join(objdir, "lmc_api.o"), [])]
+    for g in GROUPS:
+        jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"), os.path.join(objdir, f"lmc_run_g{g}.o"),
+                     [f"-DLMC_G={g}"]))
+    log = []
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        for cmd, r in ex.map(_compile, jobs):
+            log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(log[-1])
+                raise RuntimeError("nvcc failed")
+    with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    objs = [j[1] for j in jobs]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

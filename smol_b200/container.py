@@ -1,0 +1,168 @@
+"""SampleContainer: in-memory mirror of ``smol/moca/sampler/container.py`` (array part).
+
+Trace names, shapes ``[nsamples, nwalkers, ...]`` and dtypes follow
+``smol/moca/trace.py`` / ``sampler.py:123-128``: ``occupancy`` int32, ``features`` /
+``enthalpy`` / ``temperature`` float64, ``accepted`` bool (flag of the last step of each
+thinning interval, ``sampler.py:199-201``).  ``n_accepted`` (accepted steps per interval) is an
+engine extension.  HDF5 streaming (``container.py:420-512``) is not part of this build.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class SampleContainer:
+    def __init__(self, ensemble, nwalkers, trace_shapes, sampling_metadata=None):
+        self._ensemble = ensemble
+        self.metadata = dict(sampling_metadata or {})
+        self._nwalkers = nwalkers
+        self._shapes = dict(trace_shapes)      # name -> (shape tuple, dtype)
+        self._chunks = {name: [] for name in self._shapes}
+        self._cache = {}
+        self._thin = []
+        self.total_mc_steps = 0
+
+    # ---- bookkeeping ----------------------------------------------------------------------
+    @property
+    def ensemble(self):
+        return self._ensemble
+
+    @property
+    def sublattices(self):
+        return self._ensemble.sublattices
+
+    @property
+    def natural_parameters(self):
+        return self._ensemble.natural_parameters
+
+    @property
+    def num_samples(self):
+        ch = self._chunks["enthalpy"]
+        return int(sum(len(c) for c in ch))
+
+    def __len__(self):
+        return self.num_samples
+
+    @property
+    def shape(self):
+        return (self._nwalkers, self._shapes["occupancy"][0][0])
+
+    @property
+    def traced_values(self):
+        return list(self._shapes)
+
+    def append(self, traces: dict, thinned_by: int):
+        """container.py:384-397 for a whole block of samples at once."""
+        n = len(traces["enthalpy"])
+        for name in self._shapes:
+            self._chunks[name].append(traces[name])
+        self._cache.clear()
+        self.total_mc_steps += n * thinned_by
+        self._thin.append((n, thinned_by))
+
+    def clear(self):
+        for name in self._chunks:
+            self._chunks[name] = []
+        self._cache.clear()
+        self.total_mc_steps = 0
+        self._thin = []
+
+    def _full(self, name):
+        if name not in self._cache:
+            shape, dtype = self._shapes[name]
+            ch = self._chunks[name]
+            if not ch:
+                arr = np.empty((0, self._nwalkers, *shape), dtype=dtype)
+            else:
+                arr = np.concatenate(ch, axis=0) if len(ch) > 1 else ch[0]
+                if arr.dtype != dtype:
+                    arr = arr.astype(dtype)
+                self._chunks[name] = [arr]
+            self._cache[name] = arr
+        return self._cache[name]
+
+    @staticmethod
+    def _flatten(values):
+        s = values.shape
+        return values.reshape((s[0] * s[1], *s[2:]))
+
+    # ---- accessors (container.py:131-381) ---------------------------------------------------
+    def get_trace_value(self, name, discard=0, thin_by=1, flat=True):
+        value = self._full(name)[discard + thin_by - 1:: thin_by]
+        return self._flatten(value) if flat else value
+
+    def mean_trace_value(self, name, discard=0, thin_by=1, flat=True):
+        return self.get_trace_value(name, discard, thin_by, flat).mean(axis=0)
+
+    def trace_value_variance(self, name, discard=0, thin_by=1, flat=True):
+        return self.get_trace_value(name, discard, thin_by, flat).var(axis=0)
+
+    def sampling_efficiency(self, discard=0, flat=True):
+        total_accepted = self._full("accepted")[discard:].sum(axis=0)
+        eff = total_accepted / (self.num_samples - discard)
+        return eff.mean() if flat else eff
+
+    def step_efficiency(self, discard=0, flat=True):
+        """Exact accepted fraction over ALL attempted steps (engine extension)."""
+        nacc = self._full("n_accepted")[discard:].sum(axis=0).astype(np.float64)
+        steps = 0
+        seen = 0
+        for n, thin in self._thin:
+            lo = max(discard - seen, 0)
+            steps += max(n - lo, 0) * thin
+            seen += n
+        eff = nacc / max(steps, 1)
+        return eff.mean() if flat else eff
+
+    def get_occupancies(self, discard=0, thin_by=1, flat=True):
+        return self.get_trace_value("occupancy", discard, thin_by, flat)
+
+    def get_enthalpies(self, discard=0, thin_by=1, flat=True):
+        return self.get_trace_value("enthalpy", discard, thin_by, flat)
+
+    def get_feature_vectors(self, discard=0, thin_by=1, flat=True):
+        return self.get_trace_value("features", discard, thin_by, flat)
+
+    def get_energies(self, discard=0, thin_by=1, flat=True):
+        """container.py:208-229: energy = features[:n_energy] . coefs."""
+        feats = self.get_feature_vectors(discard, thin_by, flat)
+        n = self._ensemble.num_energy_coefs
+        return np.tensordot(feats[..., :n], self.natural_parameters[:n], axes=([-1], [0]))
+
+    def get_temperatures(self, discard=0, thin_by=1):
+        return self.get_trace_value("temperature", discard, thin_by, flat=False)[:, 0]
+
+    def mean_enthalpy(self, discard=0, thin_by=1, flat=True):
+        return self.get_enthalpies(discard, thin_by, flat).mean(axis=0)
+
+    def enthalpy_variance(self, discard=0, thin_by=1, flat=True):
+        return self.get_enthalpies(discard, thin_by, flat).var(axis=0)
+
+    def mean_energy(self, discard=0, thin_by=1, flat=True):
+        return self.get_energies(discard, thin_by, flat).mean(axis=0)
+
+    def energy_variance(self, discard=0, thin_by=1, flat=True):
+        return self.get_energies(discard, thin_by, flat).var(axis=0)
+
+    def mean_feature_vector(self, discard=0, thin_by=1, flat=True):
+        return self.get_feature_vectors(discard, thin_by, flat).mean(axis=0)
+
+    def feature_vector_variance(self, discard=0, thin_by=1, flat=True):
+        return self.get_feature_vectors(discard, thin_by, flat).var(axis=0)
+
+    def get_minimum_enthalpy(self, discard=0, thin_by=1, flat=True):
+        return self.get_enthalpies(discard, thin_by, flat).min(axis=0)
+
+    def get_minimum_enthalpy_occupancy(self, discard=0, thin_by=1, flat=True):
+        inds = self.get_enthalpies(discard, thin_by, flat).argmin(axis=0)
+        occus = self.get_occupancies(discard, thin_by, flat)
+        return occus[inds[0]] if flat else occus[inds, np.arange(self._nwalkers)][0]
+
+    def get_species_counts(self, discard=0, thin_by=1, flat=True):
+        """container.py:336-347: counts per species code on each sublattice."""
+        occus = self.get_occupancies(discard, thin_by, flat)
+        out = {}
+        for i, s in enumerate(self.sublattices):
+            for sp, code in zip(s.species, s.encoding):
+                out[(i, sp)] = np.count_nonzero(occus[..., s.sites] == code, axis=-1)
+        return out

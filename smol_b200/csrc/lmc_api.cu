@@ -1,0 +1,362 @@
+// C ABI of liblmc (see include/lmc.h): model upload, launch configuration, kernel dispatch.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#define LMC_API_TU
+#include "lmc_kernels.cuh"
+#include "lmc_launch.h"
+
+using namespace lmc;
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct LmcModel {
+  DevModel dm;
+  std::vector<void*> allocs;
+  OrbDev* orb_dev = nullptr;
+  double* nat_dev = nullptr;
+  int device = 0;
+  int smem_optin = 0;
+  int num_sms = 0;
+};
+
+template <typename T>
+static int upload(LmcModel* mdl, const T* host, size_t count, const T** out) {
+  void* p = nullptr;
+  const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
+  if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  mdl->allocs.push_back(p);
+  if (count) {
+    e = cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+  }
+  *out = reinterpret_cast<const T*>(p);
+  return 0;
+}
+
+extern "C" int lmc_version(void) { return LMC_ABI_VERSION; }
+extern "C" const char* lmc_last_error(void) { return g_err.c_str(); }
+extern "C" int lmc_row_stride(int n) { return (n + 15) & ~15; }
+extern "C" int64_t lmc_launch_count(void) { return g_launches.load(); }
+extern "C" int lmc_model_num_features(const LmcModel* m) { return m ? m->dm.F : -1; }
+
+extern "C" int lmc_model_destroy(LmcModel* m) {
+  if (!m) return 0;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return 0;
+}
+
+extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
+  if (!d || !out) return fail("null argument");
+  if (d->abi_version != LMC_ABI_VERSION) return fail("ABI version mismatch");
+  if (d->num_sites <= 0 || d->num_sites > 65535) return fail("num_sites must be in 1..65535 (u16 site indices)");
+  if (d->num_classes > 65535) return fail("too many record classes");
+  if (d->num_sublattices < 1 || d->num_sublattices > LMC_MAX_SUBLATTICES) return fail("1..8 active sublattices");
+  if (d->tf_num_dims > LMC_MAX_DIMS || d->tf_num_flips > LMC_MAX_TABLE_FLIPS) return fail("flip table too large");
+  LmcModel* mdl = new LmcModel();
+  DevModel& m = mdl->dm;
+  memset(&m, 0, sizeof(m));
+  cudaGetDevice(&mdl->device);
+  cudaDeviceGetAttribute(&mdl->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, mdl->device);
+  cudaDeviceGetAttribute(&mdl->num_sms, cudaDevAttrMultiProcessorCount, mdl->device);
+  m.N = d->num_sites;
+  m.Npad = lmc_row_stride(d->num_sites);
+  m.F = d->num_features;
+  m.Fce = d->num_ce_features;
+  m.nOrb = d->num_orbits;
+  m.nCls = d->num_classes;
+  m.nSl = d->num_sublattices;
+  m.size = d->supercell_size;
+  m.feature0 = d->feature0;
+  int rc = 0;
+#define UP(T, src, cnt, dst)                                         \
+  if ((rc = upload<T>(mdl, (const T*)(src), (size_t)(cnt), (const T**)&(dst)))) { \
+    lmc_model_destroy(mdl);                                          \
+    return rc;                                                       \
+  }
+  // orbit descriptors
+  std::vector<OrbDev> orbs(m.nOrb);
+  bool kone = true;
+  int tabA_len = 0;
+  for (int n = 0; n < m.nOrb; ++n) {
+    OrbDev& o = orbs[n];
+    o.ftab_off = d->orb_tab_off[n];
+    o.T = d->orb_tab_len[n];
+    o.K = d->orb_nfunc[n];
+    o.fidx = d->orb_fidx[n];
+    o.csize = d->orb_csize[n];
+    if (o.csize > LMC_MAX_CLUSTER_SITES) { lmc_model_destroy(mdl); return fail("clusters with more than 4 sites are not supported"); }
+    if (o.T > 65535) { lmc_model_destroy(mdl); return fail("flattened tensor longer than 65535"); }
+    o.row_off = (int)d->orb_row_off[n];
+    o.row_cnt = (int)(d->orb_row_off[n + 1] - d->orb_row_off[n]);
+    for (int i = 0; i < 4; ++i) o.stride[i] = d->orb_stride[n * LMC_MAX_CLUSTER_SITES + i];
+    o.w = d->orb_weight[n];
+    o.atab_off = tabA_len;
+    tabA_len += o.T;
+    if (o.K != 1) kone = false;
+  }
+  m.kone = kone ? 1 : 0;
+  m.tabA_len = tabA_len;
+  // phase-A table: raw tensors (K == 1 everywhere) or tensors contracted with nat * w
+  std::vector<double> tabA(tabA_len);
+  for (int n = 0; n < m.nOrb; ++n) {
+    const OrbDev& o = orbs[n];
+    for (int t = 0; t < o.T; ++t) {
+      if (kone) {
+        tabA[o.atab_off + t] = d->ftab[o.ftab_off + t];
+      } else {
+        double s = 0.0;
+        for (int k = 0; k < o.K; ++k) s += d->natural_parameters[o.fidx + k] * o.w * d->ftab[o.ftab_off + k * o.T + t];
+        tabA[o.atab_off + t] = s;
+      }
+    }
+  }
+  // blob: cls | coef | tabA | nat | orb
+  {
+    const int C = m.nCls;
+    size_t off = 0;
+    const size_t off_cls = off; off += (size_t)C * 16;
+    m.off_coef = (int)off; off += ((size_t)C * 8 + 15) & ~size_t(15);
+    m.off_tabA = (int)off; off += ((size_t)tabA_len * 8 + 15) & ~size_t(15);
+    m.off_nat = (int)off; off += ((size_t)m.F * 8 + 15) & ~size_t(15);
+    m.off_orb = (int)off; off += ((size_t)m.nOrb * sizeof(OrbDev) + 15) & ~size_t(15);
+    m.blob_bytes = (int)off;
+    std::vector<unsigned char> blob(off, 0);
+    uint32_t* cls = reinterpret_cast<uint32_t*>(blob.data() + off_cls);
+    double* coef = reinterpret_cast<double*>(blob.data() + m.off_coef);
+    for (int c = 0; c < C; ++c) {
+      const int orb = d->cls_orbit[c];
+      const int* st = d->cls_stride + c * 4;
+      for (int i = 0; i < 4; ++i)
+        if (st[i] < 0 || st[i] > 65535) { lmc_model_destroy(mdl); return fail("class stride out of range"); }
+      cls[c * 4 + 0] = (uint32_t)st[0] | ((uint32_t)st[1] << 16);
+      cls[c * 4 + 1] = (uint32_t)st[2] | ((uint32_t)st[3] << 16);
+      cls[c * 4 + 2] = (uint32_t)orbs[orb].atab_off;
+      cls[c * 4 + 3] = (uint32_t)orb;
+      coef[c] = kone ? d->natural_parameters[orbs[orb].fidx] * orbs[orb].w : 1.0;
+    }
+    memcpy(blob.data() + m.off_tabA, tabA.data(), (size_t)tabA_len * 8);
+    memcpy(blob.data() + m.off_nat, d->natural_parameters, (size_t)m.F * 8);
+    memcpy(blob.data() + m.off_orb, orbs.data(), (size_t)m.nOrb * sizeof(OrbDev));
+    UP(unsigned char, blob.data(), blob.size(), m.blob);
+  }
+  UP(OrbDev, orbs.data(), orbs.size(), mdl->orb_dev);
+  UP(double, d->natural_parameters, m.F, mdl->nat_dev);
+  UP(double, d->ftab, d->ftab_len, m.ftab);
+  // records
+  {
+    const int64_t nrec = d->site_rec_off[m.N];
+    std::vector<int> off32(m.N + 1);
+    int rmax = 0;
+    for (int i = 0; i <= m.N; ++i) off32[i] = (int)d->site_rec_off[i];
+    for (int i = 0; i < m.N; ++i) rmax = std::max(rmax, off32[i + 1] - off32[i]);
+    m.Rmax = (rmax + 1) & ~1;
+    UP(int, off32.data(), m.N + 1, m.site_rec_off);
+    UP(uint2, d->site_rec, nrec, m.site_rec);
+    const int64_t nseg = d->site_seg_off[m.N];
+    std::vector<int> soff(m.N + 1);
+    for (int i = 0; i <= m.N; ++i) soff[i] = (int)d->site_seg_off[i];
+    std::vector<int4> segs(nseg);
+    for (int64_t i = 0; i < nseg; ++i) segs[i] = make_int4(d->site_seg[i * 3], d->site_seg[i * 3 + 1], d->site_seg[i * 3 + 2], 0);
+    UP(int, soff.data(), m.N + 1, m.site_seg_off);
+    UP(int4, segs.data(), nseg, m.site_seg);
+    UP(uint2, d->full_rows, d->orb_row_off[m.nOrb], m.full_rows);
+  }
+  // Ewald: keep the TRANSPOSE so that column gathers of the reference become row gathers
+  m.E = d->ewald_size;
+  if (m.E > 0) {
+    m.ewW = d->ewald_width;
+    m.ewF = d->ewald_feature;
+    const size_t E = (size_t)m.E;
+    std::vector<double> mt(E * E);
+    for (size_t i = 0; i < E; ++i)
+      for (size_t j = 0; j < E; ++j) mt[j * E + i] = d->ewald_matrix[i * E + j];
+    UP(double, mt.data(), E * E, m.ewMt);
+    UP(int, d->ewald_inds, (size_t)m.N * m.ewW, m.ewInds);
+  }
+  m.muW = d->mu_width;
+  if (m.muW > 0) {
+    m.muF = d->mu_feature;
+    UP(double, d->mu_table, (size_t)m.N * m.muW, m.mu);
+  }
+  // sublattices
+  {
+    double cum = 0.0;
+    for (int s = 0; s < m.nSl; ++s) {
+      m.sl_off[s] = d->sl_site_off[s];
+      m.sl_ncodes[s] = d->sl_ncodes[s];
+      if (m.sl_ncodes[s] > LMC_MAX_CODES) { lmc_model_destroy(mdl); return fail("too many species on a sublattice"); }
+      for (int c = 0; c < LMC_MAX_CODES; ++c) {
+        m.sl_codes[s][c] = d->sl_codes[s * LMC_MAX_CODES + c];
+        if (c < m.sl_ncodes[s] && (m.sl_codes[s][c] < 0 || m.sl_codes[s][c] >= LMC_MAX_CODES)) {
+          lmc_model_destroy(mdl);
+          return fail("species codes must be < 8");
+        }
+      }
+      cum += d->sl_prob[s];
+      m.sl_cum[s] = (s == m.nSl - 1) ? 1.0 : cum;
+      const int a = d->sl_site_off[s], b = d->sl_site_off[s + 1];
+      bool contig = b > a;
+      for (int j = a + 1; j < b; ++j) contig = contig && d->sl_sites[j] == d->sl_sites[j - 1] + 1;
+      m.sl_first[s] = contig ? d->sl_sites[a] : -1;
+    }
+    m.sl_off[m.nSl] = d->sl_site_off[m.nSl];
+    UP(int, d->sl_sites, d->sl_site_off[m.nSl], m.sl_sites);
+  }
+  m.tfD = d->tf_num_flips > 0 ? d->tf_num_dims : 0;
+  m.tfNF = d->tf_num_flips;
+  for (int i = 0; i < m.tfNF; ++i)
+    for (int k = 0; k < m.tfD; ++k) m.tf_table[i][k] = d->tf_table[i * m.tfD + k];
+  for (int i = 0; i < 2 * m.tfNF; ++i) m.tf_w[i] = d->tf_weights[i];
+  for (int k = 0; k < m.tfD; ++k) {
+    m.tf_max_n[k] = d->tf_max_n[k];
+    m.tf_dim_sl[k] = d->tf_dim_sl[k];
+    m.tf_dim_code[k] = d->tf_dim_code[k];
+  }
+  m.tf_sw = d->tf_swap_weight;
+#undef UP
+  *out = mdl;
+  return 0;
+}
+
+extern "C" int lmc_cast_i32_to_i8(const int32_t* src, int8_t* dst, int W, int N, void* stream) {
+  const int Npad = lmc_row_stride(N);
+  const long long n = (long long)W * Npad;
+  if (n == 0) return 0;
+  lmc_cast_i32_i8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, W, N, Npad);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int lmc_cast_i8_to_i32(const int8_t* src, int32_t* dst, int64_t rows, int N, int stride, void* stream) {
+  const long long n = rows * N;
+  if (n == 0) return 0;
+  lmc_cast_i8_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, N, stride);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lmc_full_features(const LmcModel* mdl, const int8_t* occ, int W, double* feat, double* enth, void* stream) {
+  if (!mdl) return fail("null model");
+  if (W <= 0) return 0;
+  const DevModel& m = mdl->dm;
+  const size_t smem = (size_t)m.Npad + (m.E ? (size_t)m.N * 4 : 0) + 16;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(lmc_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lmc_full_kernel<<<W, 256, smem, (cudaStream_t)stream>>>(m, occ, feat, enth, mdl->orb_dev, mdl->nat_dev);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static size_t delta_walker_smem(const DevModel& m) {
+  return (((size_t)m.F * 8 + 15) & ~size_t(15)) + (((size_t)m.Rmax * 8 + 15) & ~size_t(15));
+}
+
+extern "C" int lmc_delta_features(const LmcModel* mdl, const int8_t* occ, int W, const int32_t* sites, const int32_t* codes,
+                                  int nflips, double* out, void* stream) {
+  if (!mdl) return fail("null model");
+  if (W <= 0) return 0;
+  const DevModel& m = mdl->dm;
+  const int G = 32, threads = 128, wpb = threads / G;
+  const size_t wsm = delta_walker_smem(m);
+  const size_t smem = (((size_t)m.blob_bytes + 15) & ~size_t(15)) + (size_t)wpb * (m.Npad + wsm);
+  if ((int)smem > mdl->smem_optin) return fail("model tables do not fit in shared memory");
+  const int grid = (W + wpb - 1) / wpb;
+  if (m.kone) {
+    CK(cudaFuncSetAttribute(lmc_delta_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lmc_delta_kernel<32, true><<<grid, threads, smem, (cudaStream_t)stream>>>(m, occ, W, sites, codes, nflips, out, wpb, (int)wsm);
+  } else {
+    CK(cudaFuncSetAttribute(lmc_delta_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lmc_delta_kernel<32, false><<<grid, threads, smem, (cudaStream_t)stream>>>(m, occ, W, sites, codes, nflips, out, wpb, (int)wsm);
+  }
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream) {
+  if (!mdl || !c) return fail("null argument");
+  const DevModel& m = mdl->dm;
+  if (c->num_walkers <= 0 || c->num_samples <= 0) return 0;
+  if (c->thin_by <= 0) return fail("thin_by must be positive");
+  if (c->usher == LMC_USHER_TABLEFLIP && m.tfNF == 0) return fail("model has no flip table");
+  if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins <= 1) return fail("Wang-Landau needs more than one bin");
+  const bool ewald = m.E > 0;
+  int G = c->group_size;
+  if (const char* e = getenv("LMC_GROUP_SIZE")) { if (G == 0) G = atoi(e); }
+  if (G == 0) {
+    if (ewald) G = 32;
+    else {
+      long long want = (long long)mdl->num_sms * 768 / c->num_walkers;
+      G = 4;
+      while (G < 32 && G * 2 <= want) G *= 2;
+    }
+  }
+  if (c->usher == LMC_USHER_TABLEFLIP) G = (G >= 16) ? 32 : 8;
+  if (G != 4 && G != 8 && G != 16 && G != 32) return fail("group_size must be 4, 8, 16 or 32");
+  int threads = c->block_threads;
+  if (const char* e = getenv("LMC_BLOCK_THREADS")) { if (threads == 0) threads = atoi(e); }
+  if (threads == 0) threads = 128;
+  if (threads % 32 || threads > 1024) return fail("block_threads must be a multiple of 32");
+
+  RunArgs a;
+  memset(&a, 0, sizeof(a));
+  a.W = c->num_walkers; a.walker_base = c->walker_id_base; a.usher = c->usher; a.kernel = c->kernel;
+  a.S = c->num_samples; a.thin = c->thin_by; a.step0 = c->step_begin;
+  a.seeds = reinterpret_cast<const unsigned long long*>(c->seeds_dev);
+  a.beta = c->beta_dev;
+  a.occ = c->occ_dev; a.features = c->features_dev; a.enthalpy = c->enthalpy_dev;
+  a.tr_occ = c->trace_occ_dev; a.tr_feat = c->trace_features_dev; a.tr_enth = c->trace_enthalpy_dev;
+  a.tr_acc = c->trace_accepted_dev; a.tr_nacc = c->trace_naccepted_dev;
+  a.wl = c->wl;
+  if (!a.seeds || !a.occ || !a.features || !a.enthalpy) return fail("state pointers must not be null");
+  if (c->kernel != LMC_KERNEL_WANGLANDAU && !a.beta) return fail("beta_dev must not be null");
+  // per-walker shared-memory slab: [features][stash x MAX_FLIPS][counts]
+  const size_t stash_el = m.kone ? 8 : 4;
+  a.off_feat = 0;
+  a.off_stash = (int)(((size_t)m.F * 8 + 15) & ~size_t(15));
+  a.off_cnt = a.off_stash + (int)(((size_t)LMC_MAX_FLIPS * m.Rmax * stash_el + 15) & ~size_t(15));
+  a.walker_smem = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
+  const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
+  size_t smem = 0;
+  for (;;) {
+    a.wpb = threads / G;
+    smem = blob + (size_t)a.wpb * (m.Npad + a.walker_smem);
+    if ((int)smem <= mdl->smem_optin - 1024 || threads <= 32) break;
+    threads -= 32;
+  }
+  if ((int)smem > mdl->smem_optin - 1024) return fail("model + walker state do not fit in shared memory");
+  const int grid = (a.W + a.wpb - 1) / a.wpb;
+  LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
+  int rc = -2;
+  switch (G) {
+    case 4: rc = launch_run_g4(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 8: rc = launch_run_g8(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 16: rc = launch_run_g16(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 32: rc = launch_run_g32(m, a, m.kone != 0, ewald, c->usher, lc); break;
+  }
+  if (rc == -2) return fail("no kernel instantiated for this group size / usher");
+  g_launches++;
+  if (rc != 0) return fail(std::string("launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}

@@ -1,0 +1,720 @@
+// Kernels of the lattice-MC engine (sm_100a).  See DESIGN.md for the data layout.
+#pragma once
+#include <math.h>
+#include "lmc_device.cuh"
+#include "lmc_model.cuh"
+
+namespace lmc {
+
+// shared-memory view of the staged tables
+struct SmemTables {
+  const uint4* cls;     // (s0 | s1<<16, s2 | self<<16, atab_off, orbit)
+  const double* coef;   // nat[fidx] * w of the class' orbit (K == 1 only)
+  const double* tabA;   // phase-A table
+  const double* nat;    // natural parameters
+  const OrbDev* orb;
+};
+
+__device__ __forceinline__ SmemTables smem_tables(const DevModel& m, const unsigned char* base) {
+  SmemTables t;
+  t.cls = reinterpret_cast<const uint4*>(base);
+  t.coef = reinterpret_cast<const double*>(base + m.off_coef);
+  t.tabA = reinterpret_cast<const double*>(base + m.off_tabA);
+  t.nat = reinterpret_cast<const double*>(base + m.off_nat);
+  t.orb = reinterpret_cast<const OrbDev*>(base + m.off_orb);
+  return t;
+}
+
+// Stage the table blob into shared memory with one TMA bulk copy (thread 0 issues, all wait).
+// `extra_*` lets the caller piggy-back a second bulk copy (the block's occupancy rows).
+__device__ __forceinline__ void stage_tables(const DevModel& m, unsigned char* smem, uint64_t* bar,
+                                             void* extra_dst, const void* extra_src, uint32_t extra_bytes) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)m.blob_bytes + extra_bytes);
+    tma_load_1d(smem, m.blob, (uint32_t)m.blob_bytes, bar);
+    if (extra_bytes) tma_load_1d(extra_dst, extra_src, extra_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase A: energy change of ONE flip (site: olda -> newb) against the current occupancy.
+// Lanes of the group stride over the site's local cluster records.  Restates
+// delta_interactions_from_occupancies / delta_correlations_from_occupancies
+// (smol/utils/cluster/evaluator.pyx:211-317) contracted with the natural parameters.
+// The per-record differences are stashed for phase B.
+// ------------------------------------------------------------------------------------------
+template <int G, bool KONE>
+__device__ __forceinline__ double flip_energy(const DevModel& m, const SmemTables& t, const uint8_t* occ, int site,
+                                              int olda, int newb, void* stash, int g) {
+  const int r0 = __ldg(m.site_rec_off + site), r1 = __ldg(m.site_rec_off + site + 1);
+  double acc = 0.0;
+  for (int r = r0 + g; r < r1; r += G) {
+    const uint2 rec = __ldg(m.site_rec + r);
+    const uint32_t c = rec.y >> 16;
+    const uint4 ci = t.cls[c];
+    const int o0 = occ[rec.x & 0xffffu], o1 = occ[rec.x >> 16], o2 = occ[rec.y & 0xffffu];
+    const int base = (int)(ci.x & 0xffffu) * o0 + (int)(ci.x >> 16) * o1 + (int)(ci.y & 0xffffu) * o2 + (int)ci.z;
+    const int self = (int)(ci.y >> 16);
+    const int ii = base + olda * self, ff = base + newb * self;
+    const double d = t.tabA[ff] - t.tabA[ii];
+    if (KONE) {
+      acc += t.coef[c] * d;
+      reinterpret_cast<double*>(stash)[r - r0] = d;
+    } else {
+      acc += d;
+      reinterpret_cast<uint32_t*>(stash)[r - r0] = (uint32_t)(ff - (int)ci.z) | ((uint32_t)(ii - (int)ci.z) << 16);
+    }
+  }
+  return acc;
+}
+
+// phase B: fold the stashed per-record differences of an ACCEPTED flip into the running feature
+// vector.  One lane owns one orbit segment and sums it in cluster order (the reference's order,
+// evaluator.pyx:253-263); feature += p * (size / J_total).
+template <int G, bool KONE>
+__device__ __forceinline__ void flip_features(const DevModel& m, const SmemTables& t, int site, const void* stash,
+                                              double* feat, int g) {
+  const int s0 = __ldg(m.site_seg_off + site), s1 = __ldg(m.site_seg_off + site + 1);
+  for (int s = s0 + g; s < s1; s += G) {
+    const int4 sg = __ldg(m.site_seg + s);
+    const OrbDev& o = t.orb[sg.z];
+    if (KONE) {
+      const double* d = reinterpret_cast<const double*>(stash) + sg.x;
+      double p = 0.0;
+      for (int j = 0; j < sg.y; ++j) p += d[j];
+      feat[o.fidx] += p * o.w;
+    } else {
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(stash) + sg.x;
+      for (int k = 0; k < o.K; ++k) {
+        const double* tk = m.ftab + o.ftab_off + k * o.T;
+        double p = 0.0;
+        for (int j = 0; j < sg.y; ++j) p += __ldg(tk + (u[j] & 0xffffu)) - __ldg(tk + (u[j] >> 16));
+        feat[o.fidx + k] += p * o.w;
+      }
+    }
+  }
+}
+
+// Ewald energy change of one flip: row gather over the (transposed) Ewald matrix.
+// Restates delta_ewald_single_flip (smol/utils/cluster/ewald.pyx:9-59); lanes stride over sites.
+template <int G>
+__device__ __forceinline__ double flip_ewald(const DevModel& m, const uint8_t* occ, int site, int olda, int newb,
+                                             int g) {
+  const int add = __ldg(m.ewInds + site * m.ewW + newb);
+  const int sub = __ldg(m.ewInds + site * m.ewW + olda);
+  const double* rowA = m.ewMt + (size_t)(add < 0 ? 0 : add) * m.E;
+  const double* rowS = m.ewMt + (size_t)(sub < 0 ? 0 : sub) * m.E;
+  double acc = 0.0;
+  for (int k = g; k < m.N; k += G) {
+    if (k == site) continue;
+    const int e = __ldg(m.ewInds + k * m.ewW + occ[k]);
+    if (e >= 0) {
+      double tk = 0.0;
+      if (add >= 0) tk += 2.0 * __ldg(rowA + e);
+      if (sub >= 0) tk -= 2.0 * __ldg(rowS + e);
+      acc += tk;
+    }
+  }
+  if (g == 0) {
+    double tk = 0.0;
+    if (add >= 0) tk += __ldg(rowA + add);
+    if (sub >= 0) tk -= __ldg(rowS + sub);
+    acc += tk;
+  }
+  return acc;
+}
+
+// k-th active site (in Sublattice.active_sites order) of sublattice `sl` whose code is != `code`
+// (ne) or == `code` (!ne).  Group-cooperative rank select: per-lane chunk counts, prefix, locate.
+// Restates `rng.choice(active_sites[occu[active_sites] != species1])` (mcusher.py:189-196) and the
+// species_list picks of TableFlip (mcusher.py:620-637).
+template <int G>
+__device__ __forceinline__ int select_site(const DevModel& m, const uint8_t* occ, int sl, int code, int k, bool ne,
+                                           int g, uint32_t mask) {
+  const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
+  const int first = m.sl_first[sl];
+  int chunk = (n_act + G - 1) / G;
+  const bool words = first >= 0 && (first & 3) == 0 && (n_act % (4 * G)) == 0;
+  int cnt = 0;
+  const int lo = g * chunk, hi = min(lo + chunk, n_act);
+  if (words) {
+    const uint32_t pat = (uint32_t)code * 0x01010101u;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(occ + first + lo);
+    for (int j = 0; j < chunk / 4; ++j) cnt += __popc(__vcmpeq4(w[j], pat)) >> 3;
+    if (ne) cnt = chunk - cnt;
+  } else {
+    for (int j = lo; j < hi; ++j) {
+      const int s = first >= 0 ? first + j : __ldg(m.sl_sites + off + j);
+      cnt += ne ? (occ[s] != code) : (occ[s] == code);
+    }
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) {
+    const int tt = __shfl_up_sync(mask, incl, o, G);
+    if (g >= o) incl += tt;
+  }
+  const int excl = incl - cnt;
+  const bool found = (k >= excl) && (k < incl);
+  int res = -1;
+  if (found) {
+    int rem = k - excl;
+    for (int j = lo; j < hi; ++j) {
+      const int s = first >= 0 ? first + j : __ldg(m.sl_sites + off + j);
+      const bool hit = ne ? (occ[s] != code) : (occ[s] == code);
+      if (hit) {
+        if (rem == 0) { res = s; break; }
+        --rem;
+      }
+    }
+  }
+  if (G > 1) {
+    const uint32_t b = __ballot_sync(mask, found);
+    const int src = b ? (__ffs(b) - 1) : (int)(threadIdx.x & 31);
+    res = __shfl_sync(mask, res, src);
+  }
+  return res;
+}
+
+__device__ __forceinline__ int choose_sublattice(const DevModel& m, uint32_t r0) {
+  if (m.nSl == 1) return 0;
+  const double u = u01(r0);
+  int s = 0;
+  while (s < m.nSl - 1 && !(m.sl_cum[s] > u)) ++s;
+  return s;
+}
+
+// feasibility mask * weights of the 2*nf flip directions (utils/math.py:832-867)
+__device__ __forceinline__ double tf_masked_weights(const DevModel& m, const int* n, double* wout) {
+  double sum = 0.0;
+  for (int i = 0; i < 2 * m.tfNF; ++i) {
+    const int sgn = (i & 1) ? -1 : 1;
+    bool ok = true;
+    for (int d = 0; d < m.tfD; ++d) {
+      const int v = n[d] + sgn * m.tf_table[i >> 1][d];
+      ok = ok && v >= 0 && v <= m.tf_max_n[d];
+    }
+    wout[i] = ok ? m.tf_w[i] : 0.0;
+    sum += wout[i];
+  }
+  return sum;
+}
+
+struct Step {
+  int n;                       // number of flips (0 = empty step)
+  int site[LMC_MAX_FLIPS], oldc[LMC_MAX_FLIPS], newc[LMC_MAX_FLIPS], sl[LMC_MAX_FLIPS];
+  double log_priori;
+};
+// append without dynamic indexing (keeps the arrays in registers)
+__device__ __forceinline__ void push_flip(Step& st, int site, int oldc, int newc, int sl) {
+#pragma unroll
+  for (int i = 0; i < LMC_MAX_FLIPS; ++i)
+    if (i == st.n) { st.site[i] = site; st.oldc[i] = oldc; st.newc[i] = newc; st.sl[i] = sl; }
+  if (st.n < LMC_MAX_FLIPS) ++st.n;
+}
+
+// Python float floor division `a // b` (CPython float_floor_div), used by WangLandau._get_bin_id
+__device__ __forceinline__ double py_floordiv(double a, double b) {
+  double mod = fmod(a, b);
+  double div = (a - mod) / b;
+  if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
+  if (div != 0.0) {
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+  }
+  return copysign(0.0, a / b);
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused MC kernel: propose -> delta features/energy (+Ewald, +mu) -> accept -> update,
+// num_samples * thin_by attempted steps per walker in ONE launch.
+// ------------------------------------------------------------------------------------------
+template <int G, bool KONE, bool EWALD, int USHER>
+__global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint64_t bar;
+  const int g = threadIdx.x % G;
+  const int wl_ = threadIdx.x / G;                  // walker slot in block
+  const int w = blockIdx.x * a.wpb + wl_;            // walker on this device
+  const int nw_blk = min(a.wpb, a.W - blockIdx.x * a.wpb);
+  const bool active = wl_ < a.wpb && w < a.W;
+  const uint32_t gmask = group_mask<G>();
+
+  unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
+  unsigned char* wslab = wbase + (size_t)wl_ * a.walker_smem;
+  // occupancy rows of the block are contiguous in global memory: slab layout keeps the rows of
+  // all walkers first ([wpb][Npad]) so that ONE bulk copy loads them.
+  uint8_t* occ_rows = wbase;
+  unsigned char* rest = wbase + (size_t)a.wpb * m.Npad;
+  uint8_t* occ = occ_rows + (size_t)wl_ * m.Npad;
+  unsigned char* priv = rest + (size_t)wl_ * a.walker_smem;
+  double* feat = reinterpret_cast<double*>(priv + a.off_feat);
+  unsigned char* stash0 = priv + a.off_stash;
+  int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
+  (void)wslab;
+
+  stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
+  const SmemTables t = smem_tables(m, smem);
+  if (!active) return;
+
+  const int stash_stride = m.Rmax * (KONE ? 8 : 4);
+  // running state
+  for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
+  double enth = a.enthalpy[w];
+  // species counts per (active sublattice, code)
+  for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
+  group_sync<G>(gmask);
+  if (g == 0) {
+    for (int s = 0; s < m.nSl; ++s)
+      for (int j = m.sl_off[s]; j < m.sl_off[s + 1]; ++j) {
+        const int site = m.sl_first[s] >= 0 ? m.sl_first[s] + (j - m.sl_off[s]) : m.sl_sites[j];
+        cnt[s * LMC_MAX_CODES + occ[site]]++;
+      }
+  }
+  group_sync<G>(gmask);
+
+  const unsigned long long seed = a.seeds[w];
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t wid = (uint32_t)(a.walker_base + w);
+  const bool wl_mode = a.kernel == LMC_KERNEL_WANGLANDAU;
+  const double beta = wl_mode ? 0.0 : a.beta[w];
+  const double nat_ew = EWALD ? t.nat[m.ewF] : 0.0;
+  const double nat_mu = m.muW ? t.nat[m.muF] : 0.0;
+
+  // Wang-Landau per-walker state
+  double* wlS = nullptr; long long* wlH = nullptr; long long* wlO = nullptr; double* wlM = nullptr;
+  double wl_m = 0.0; long long wl_cnt = 0;
+  const int nb = a.wl.num_bins;
+  if (wl_mode) {
+    wlS = a.wl.entropy_dev + (size_t)w * nb;
+    wlH = reinterpret_cast<long long*>(a.wl.histogram_dev) + (size_t)w * nb;
+    wlO = reinterpret_cast<long long*>(a.wl.occurrences_dev) + (size_t)w * nb;
+    wlM = a.wl.mean_features_dev + (size_t)w * nb * m.F;
+    wl_m = a.wl.mod_factor_dev[w];
+    wl_cnt = a.wl.steps_counter_dev[w];
+  }
+
+  unsigned long long step = a.step0;
+  for (long long s = 0; s < a.S; ++s) {
+    int nacc = 0;
+    bool accepted = true;
+    for (int it = 0; it < a.thin; ++it, ++step) {
+      const U4 r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1);
+      Step st;
+      st.n = 0;
+      st.log_priori = 0.0;
+#pragma unroll
+      for (int i = 0; i < LMC_MAX_FLIPS; ++i) { st.site[i] = 0; st.oldc[i] = 0; st.newc[i] = 0; st.sl[i] = 0; }
+
+      // ------------------------------ propose ------------------------------------------
+      int usher = USHER;
+      uint32_t q0 = r.x, q1 = r.y, q2 = r.z;   // words of the simple ushers
+      U4 r1blk{0, 0, 0, 0};
+      int tf_idx = -1;
+      double tfw[2 * LMC_MAX_TABLE_FLIPS];
+      double tfsum = 0.0;
+      int nd[LMC_MAX_DIMS];
+      if (USHER == LMC_USHER_TABLEFLIP) {
+        // TableFlip.propose_step, mcusher.py:553-639
+        r1blk = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 1u, wid, k0, k1);
+        for (int d = 0; d < m.tfD; ++d)
+          nd[d] = m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
+        bool do_swap = u01(r.x) < m.tf_sw;
+        if (!do_swap) {
+          tfsum = tf_masked_weights(m, nd, tfw);
+          if (!(tfsum > 0.0)) do_swap = true;
+        }
+        if (do_swap) {
+          usher = LMC_USHER_SWAP;
+          q0 = r1blk.x; q1 = r1blk.y; q2 = r1blk.z;
+        } else {
+          // choose_section_from_partition, utils/math.py:870-893
+          const double u = u01(r.y);
+          double cum = 0.0;
+          tf_idx = 2 * m.tfNF - 1;
+          for (int i = 0; i < 2 * m.tfNF; ++i) {
+            const double p = tfw[i] / tfsum;
+            cum += p;
+            if (cum > u && p > 0.0) { tf_idx = i; break; }
+          }
+        }
+      }
+      if (USHER == LMC_USHER_FLIP) {
+        // Flip.propose_step, mcusher.py:154-170
+        const int sl = choose_sublattice(m, q0);
+        const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
+        const int j = (int)mulhi32(q1, (uint32_t)n_act);
+        const int site = m.sl_first[sl] >= 0 ? m.sl_first[sl] + j : __ldg(m.sl_sites + off + j);
+        const int cur = occ[site];
+        const int nc = m.sl_ncodes[sl];
+        int ci = (int)mulhi32(q2, (uint32_t)(nc - 1));
+        int pos = nc;
+        for (int c = 0; c < nc; ++c) if (m.sl_codes[sl][c] == cur) { pos = c; break; }
+        if (ci >= pos) ++ci;
+        st.n = 1; st.site[0] = site; st.oldc[0] = cur; st.newc[0] = m.sl_codes[sl][ci]; st.sl[0] = sl;
+      } else if (USHER == LMC_USHER_SWAP || usher == LMC_USHER_SWAP) {
+        // Swap.propose_step, mcusher.py:176-200
+        const int sl = choose_sublattice(m, q0);
+        const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
+        const int j = (int)mulhi32(q1, (uint32_t)n_act);
+        const int site1 = m.sl_first[sl] >= 0 ? m.sl_first[sl] + j : __ldg(m.sl_sites + off + j);
+        const int s1 = occ[site1];
+        const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
+        if (ndiff > 0) {
+          const int k = (int)mulhi32(q2, (uint32_t)ndiff);
+          const int site2 = select_site<G>(m, occ, sl, s1, k, true, g, gmask);
+          const int s2 = occ[site2];
+          st.n = 2;
+          st.site[0] = site1; st.oldc[0] = s1; st.newc[0] = s2; st.sl[0] = sl;
+          st.site[1] = site2; st.oldc[1] = s2; st.newc[1] = s1; st.sl[1] = sl;
+        }
+      } else if (USHER == LMC_USHER_TABLEFLIP) {
+        // table flip: sequential picks, one random word each (words 4.. of the step)
+        const int sgn = (tf_idx & 1) ? -1 : 1;
+        const int* urow = m.tf_table[tf_idx >> 1];
+        int wi = 0;  // pick counter
+        U4 rb = r1blk;
+        int cur_blk = 1;
+        auto next_word = [&]() -> uint32_t {
+          const int b = 1 + (wi >> 2);
+          if (b != cur_blk) { rb = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)b, wid, k0, k1); cur_blk = b; }
+          const int l = wi & 3;
+          ++wi;
+          return l == 0 ? rb.x : l == 1 ? rb.y : l == 2 ? rb.z : rb.w;
+        };
+        int d0 = 0;
+        // dims of one sublattice are consecutive (occu_utils.py:20-25); walk sublattice by sublattice
+        while (d0 < m.tfD) {
+          const int sl = m.tf_dim_sl[d0];
+          int d1 = d0 + 1;
+          while (d1 < m.tfD && m.tf_dim_sl[d1] == sl) ++d1;
+          if (sl >= 0) {
+            int pool[LMC_MAX_FLIPS];
+            int npool = 0;
+            for (int d = d0; d < d1; ++d) {
+              const int ud = sgn * urow[d];
+              if (ud >= 0) continue;
+              int ranks[LMC_MAX_FLIPS];
+              int nr = 0;
+              for (int p = 0; p < -ud; ++p) {
+                int idx = (int)mulhi32(next_word(), (uint32_t)(nd[d] - p));
+                // index among the remaining sites -> rank in the original (ascending-site) list
+                for (int q = 0; q < nr; ++q) if (idx >= ranks[q]) ++idx;
+                int q = nr;
+                while (q > 0 && ranks[q - 1] > idx) { ranks[q] = ranks[q - 1]; --q; }
+                ranks[q] = idx; ++nr;
+                const int site = select_site<G>(m, occ, sl, m.tf_dim_code[d], idx, false, g, gmask);
+                if (npool < LMC_MAX_FLIPS) pool[npool++] = site;
+              }
+            }
+            for (int d = d0; d < d1; ++d) {
+              const int ud = sgn * urow[d];
+              if (ud <= 0) continue;
+              for (int p = 0; p < ud; ++p) {
+                const int idx = (int)mulhi32(next_word(), (uint32_t)npool);
+                const int site = pool[idx];
+                for (int q = idx; q + 1 < npool; ++q) pool[q] = pool[q + 1];
+                --npool;
+                push_flip(st, site, occ[site], m.tf_dim_code[d], sl);
+              }
+            }
+          }
+          d0 = d1;
+        }
+        // compute_log_priori_factor, mcusher.py:656-711
+        const double p_now = (1.0 - m.tf_sw) * tfw[tf_idx] / tfsum;
+        int nn[LMC_MAX_DIMS];
+        for (int d = 0; d < m.tfD; ++d) nn[d] = nd[d] + sgn * urow[d];
+        double tfw2[2 * LMC_MAX_TABLE_FLIPS];
+        const double sum2 = tf_masked_weights(m, nn, tfw2);
+        const double p_next = (1.0 - m.tf_sw) * tfw2[tf_idx ^ 1] / sum2;
+        double lf = log(p_next / p_now);
+        for (int d = 0; d < m.tfD; ++d)
+          if (urow[d] != 0) lf += lgamma((double)nd[d] + 1.0) - lgamma((double)nn[d] + 1.0);
+        st.log_priori = lf;
+      }
+
+      // ------------------------------ evaluate ------------------------------------------
+      double acc = 0.0, acc_ew = 0.0, dmu = 0.0;
+#pragma unroll
+      for (int f = 0; f < LMC_MAX_FLIPS; ++f) {
+        if (f < st.n) {
+          acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g);
+          if (EWALD) acc_ew += flip_ewald<G>(m, occ, st.site[f], st.oldc[f], st.newc[f], g);
+          if (m.muW)
+            dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
+          if (g == 0) occ[st.site[f]] = (uint8_t)st.newc[f];
+          group_sync<G>(gmask);
+        }
+      }
+      double dH = group_sum<G>(acc, gmask);
+      double dEw = 0.0;
+      if (EWALD) { dEw = group_sum<G>(acc_ew, gmask); dH += nat_ew * dEw; }
+      if (m.muW) dH += nat_mu * dmu;
+
+      // ------------------------------ accept --------------------------------------------
+      int new_bin = 0;
+      if (!wl_mode) {
+        // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
+        const double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
+        accepted = exponent >= 0.0 ? true : exponent > log(u01(r.w));
+      } else {
+        // WangLandau._accept_step, kernel/wanglandau.py:186-202
+        const double e_new = enth + dH;
+        if (e_new < a.wl.min_enthalpy || e_new >= a.wl.max_enthalpy) {
+          accepted = false;
+        } else {
+          const int bin = (int)py_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
+          new_bin = (int)py_floordiv(e_new - a.wl.min_enthalpy, a.wl.bin_size);
+          const double s_old = (bin >= 0 && bin < nb) ? __ldcg(wlS + bin) : 0.0;
+          const double s_new = (new_bin >= 0 && new_bin < nb) ? __ldcg(wlS + new_bin) : 0.0;
+          const double exponent = (s_old - s_new) + st.log_priori;
+          accepted = exponent >= 0.0 ? true : exponent > log(u01(r.w));
+        }
+      }
+
+      // ------------------------------ update --------------------------------------------
+      if (accepted) {
+        // MCKernel._do_accept_step (kernel/base.py:327-343) + trace accumulation (sampler.py:204-207)
+#pragma unroll
+        for (int f = 0; f < LMC_MAX_FLIPS; ++f)
+          if (f < st.n) flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g);
+        if (g == 0) {
+          if (EWALD) feat[m.ewF] += dEw;
+          if (m.muW) feat[m.muF] += dmu;
+#pragma unroll
+          for (int f = 0; f < LMC_MAX_FLIPS; ++f)
+            if (f < st.n) {
+              cnt[st.sl[f] * LMC_MAX_CODES + st.oldc[f]]--;
+              cnt[st.sl[f] * LMC_MAX_CODES + st.newc[f]]++;
+            }
+        }
+        enth += dH;
+        ++nacc;
+      } else if (st.n > 0) {
+        if (g == 0) {
+#pragma unroll
+          for (int f = LMC_MAX_FLIPS - 1; f >= 0; --f)
+            if (f < st.n) occ[st.site[f]] = (uint8_t)st.oldc[f];
+        }
+      }
+      group_sync<G>(gmask);
+
+      if (wl_mode) {
+        // WangLandau._do_post_step, kernel/wanglandau.py:222-266
+        const double fb = py_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
+        if (fb >= 0.0 && fb < (double)nb) {
+          const int bin = (int)fb;
+          ++wl_cnt;
+          const long long total = __ldcg(wlO + bin);
+          const double inv = 1.0 / (double)(total + 1);
+          for (int f = g; f < m.F; f += G) {
+            double* p = wlM + (size_t)bin * m.F + f;
+            __stcg(p, inv * (feat[f] + (double)total * __ldcg(p)));
+          }
+          if (wl_cnt % a.wl.update_period == 0 && g == 0) {
+            __stcg(wlS + bin, __ldcg(wlS + bin) + wl_m);
+            __stcg(wlH + bin, __ldcg(wlH + bin) + 1);
+            __stcg(wlO + bin, total + 1);
+          }
+          group_sync<G>(gmask);
+        }
+        if (wl_cnt % a.wl.check_period == 0) {
+          int nvis = 0;
+          double hsum = 0.0, hmin = 1e300;
+          for (int b = g; b < nb; b += G)
+            if (__ldcg(wlS + b) > 0.0) {
+              const double h = (double)__ldcg(wlH + b);
+              ++nvis; hsum += h; hmin = fmin(hmin, h);
+            }
+          nvis = group_sum_i<G>(nvis, gmask);
+          hsum = group_sum<G>(hsum, gmask);
+          hmin = group_min<G>(hmin, gmask);
+          if (nvis >= 2 && hmin > a.wl.flatness * (hsum / (double)nvis)) {
+            for (int b = g; b < nb; b += G) __stcg(wlH + b, 0ll);
+            wl_m = wl_m / a.wl.mod_update;
+            group_sync<G>(gmask);
+          }
+        }
+      }
+    }  // thin
+
+    // ------------------------------ sample trace ------------------------------------------
+    const size_t sw = (size_t)s * a.W + w;
+    if (a.tr_occ) {
+      int8_t* dst = a.tr_occ + sw * m.N;
+      if ((m.N & 15) == 0) {
+        if (g == 0) {
+          fence_proxy_async();
+          tma_store_1d(dst, occ, (uint32_t)m.N);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+      } else {
+        for (int i = g; i < m.N; i += G) dst[i] = (int8_t)occ[i];
+      }
+    }
+    if (a.tr_feat)
+      for (int f = g; f < m.F; f += G) a.tr_feat[sw * m.F + f] = feat[f];
+    if (g == 0) {
+      if (a.tr_enth) a.tr_enth[sw] = enth;
+      if (a.tr_acc) a.tr_acc[sw] = accepted ? 1 : 0;
+      if (a.tr_nacc) a.tr_nacc[sw] = nacc;
+    }
+    group_sync<G>(gmask);
+  }
+
+  // ------------------------------ final state ---------------------------------------------
+  for (int i = g; i < m.N; i += G) a.occ[(size_t)w * m.Npad + i] = (int8_t)occ[i];
+  for (int f = g; f < m.F; f += G) a.features[(size_t)w * m.F + f] = feat[f];
+  if (g == 0) {
+    a.enthalpy[w] = enth;
+    if (wl_mode) {
+      a.wl.mod_factor_dev[w] = wl_m;
+      a.wl.steps_counter_dev[w] = wl_cnt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// batched feature change for given flips (parity / Processor API): one group per walker
+// ------------------------------------------------------------------------------------------
+template <int G, bool KONE>
+__global__ void lmc_delta_kernel(const DevModel m, const int8_t* __restrict__ occ_g, int W, const int* __restrict__ sites,
+                                 const int* __restrict__ codes, int nflips, double* __restrict__ out, int wpb,
+                                 int walker_smem) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint64_t bar;
+  const int g = threadIdx.x % G, wl_ = threadIdx.x / G;
+  const int w = blockIdx.x * wpb + wl_;
+  const int nw_blk = min(wpb, W - blockIdx.x * wpb);
+  const uint32_t gmask = group_mask<G>();
+  unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
+  uint8_t* occ = wbase + (size_t)wl_ * m.Npad;
+  unsigned char* priv = wbase + (size_t)wpb * m.Npad + (size_t)wl_ * walker_smem;
+  double* feat = reinterpret_cast<double*>(priv);
+  unsigned char* stash = priv + ((m.F * 8 + 15) & ~15);
+  stage_tables(m, smem, &bar, wbase, occ_g + (size_t)blockIdx.x * wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
+  const SmemTables t = smem_tables(m, smem);
+  if (wl_ >= wpb || w >= W) return;
+  for (int f = g; f < m.F; f += G) feat[f] = 0.0;
+  group_sync<G>(gmask);
+  double dmu = 0.0, dew = 0.0;
+  for (int f = 0; f < nflips; ++f) {
+    const int site = sites[(size_t)w * nflips + f], newc = codes[(size_t)w * nflips + f];
+    const int oldc = occ[site];
+    // chemical work against the PRE-step occupancy (ensemble.py:369-373)
+    if (m.muW) dmu += m.mu[site * m.muW + newc] - m.mu[site * m.muW + (int)occ_g[(size_t)w * m.Npad + site]];
+    (void)flip_energy<G, KONE>(m, t, occ, site, oldc, newc, stash, g);
+    if (m.E) dew += flip_ewald<G>(m, occ, site, oldc, newc, g);
+    group_sync<G>(gmask);
+    flip_features<G, KONE>(m, t, site, stash, feat, g);
+    if (g == 0) occ[site] = (uint8_t)newc;
+    group_sync<G>(gmask);
+  }
+  if (m.E) dew = group_sum<G>(dew, gmask);
+  if (g == 0) {
+    if (m.E) feat[m.ewF] = dew;
+    if (m.muW) feat[m.muF] = dmu;
+  }
+  group_sync<G>(gmask);
+  for (int f = g; f < m.F; f += G) out[(size_t)w * m.F + f] = feat[f];
+}
+
+#ifdef LMC_API_TU  // non-template kernels live in the API translation unit only
+// ------------------------------------------------------------------------------------------
+// full feature vector: one block per walker (correlations_from_occupancy /
+// interactions_from_occupancy, evaluator.pyx:121-209; ewald.py:128-145; ensemble.py:344-349)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wp] = v;
+  __syncthreads();
+  double tot = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  return tot;
+}
+
+__global__ void lmc_full_kernel(const DevModel m, const int8_t* __restrict__ occ_g, double* __restrict__ features,
+                                double* __restrict__ enthalpy, const OrbDev* __restrict__ orbs,
+                                const double* __restrict__ nat) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red[32];
+  uint8_t* occ = smem;
+  int* eidx = reinterpret_cast<int*>(smem + m.Npad);
+  const int w = blockIdx.x;
+  for (int i = threadIdx.x; i < m.N; i += blockDim.x) occ[i] = (uint8_t)occ_g[(size_t)w * m.Npad + i];
+  __syncthreads();
+  double* out = features + (size_t)w * m.F;
+  double enth = 0.0;
+  if (threadIdx.x == 0) out[0] = m.feature0;
+  enth += nat[0] * m.feature0;
+  for (int n = 0; n < m.nOrb; ++n) {
+    const OrbDev o = orbs[n];
+    for (int k = 0; k < o.K; ++k) {
+      const double* tk = m.ftab + o.ftab_off + k * o.T;
+      double p = 0.0;
+      for (int r = threadIdx.x; r < o.row_cnt; r += blockDim.x) {
+        const uint2 row = __ldg(m.full_rows + o.row_off + r);
+        const int idx = o.stride[0] * occ[row.x & 0xffffu] + o.stride[1] * occ[row.x >> 16] +
+                        o.stride[2] * occ[row.y & 0xffffu] + o.stride[3] * occ[row.y >> 16];
+        p += __ldg(tk + idx);
+      }
+      p = block_sum(p, red);
+      const double v = p / (double)o.row_cnt * (double)m.size;
+      if (threadIdx.x == 0) out[o.fidx + k] = v;
+      enth += nat[o.fidx + k] * v;
+    }
+  }
+  if (m.E) {
+    for (int i = threadIdx.x; i < m.N; i += blockDim.x) eidx[i] = m.ewInds[i * m.ewW + occ[i]];
+    __syncthreads();
+    double p = 0.0;
+    const long long np = (long long)m.N * m.N;
+    for (long long q = threadIdx.x; q < np; q += blockDim.x) {
+      const int i = (int)(q / m.N), j = (int)(q % m.N);
+      const int a = eidx[i], b = eidx[j];
+      if (a >= 0 && b >= 0) p += __ldg(m.ewMt + (size_t)a * m.E + b);
+    }
+    p = block_sum(p, red);
+    if (threadIdx.x == 0) out[m.ewF] = p;
+    enth += nat[m.ewF] * p;
+  }
+  if (m.muW) {
+    double p = 0.0;
+    for (int i = threadIdx.x; i < m.N; i += blockDim.x) p += m.mu[i * m.muW + occ[i]];
+    p = block_sum(p, red);
+    if (threadIdx.x == 0) out[m.muF] = p;
+    enth += nat[m.muF] * p;
+  }
+  if (enthalpy && threadIdx.x == 0) enthalpy[w] = enth;
+}
+
+__global__ void lmc_cast_i32_i8_kernel(const int* __restrict__ src, int8_t* __restrict__ dst, int W, int N, int Npad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)W * Npad) return;
+  const int w = (int)(i / Npad), k = (int)(i % Npad);
+  dst[i] = k < N ? (int8_t)src[(size_t)w * N + k] : 0;
+}
+__global__ void lmc_cast_i8_i32_kernel(const int8_t* __restrict__ src, int* __restrict__ dst, long long rows, int N,
+                                       int stride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * N) return;
+  const long long w = i / N;
+  const int k = (int)(i % N);
+  dst[i] = (int)src[w * stride + k];
+}
+
+#endif  // LMC_API_TU
+
+}  // namespace lmc

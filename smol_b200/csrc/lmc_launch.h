@@ -1,0 +1,17 @@
+// Per-group-size launchers (each compiled in its own translation unit: lmc_run_inst.cu -DLMC_G=n).
+#pragma once
+#include <cuda_runtime.h>
+#include "lmc_model.cuh"
+
+namespace lmc {
+struct LaunchCfg {
+  int grid, threads;
+  size_t smem;
+  cudaStream_t stream;
+};
+// return 0 on success, a cudaError_t value on failure, -2 if the combination is not instantiated
+int launch_run_g4(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
+int launch_run_g8(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
+int launch_run_g16(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
+int launch_run_g32(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
+}  // namespace lmc

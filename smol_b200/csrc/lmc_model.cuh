@@ -1,0 +1,79 @@
+// Device-resident model description shared by all kernels (passed by value as a kernel parameter).
+#pragma once
+#include <stdint.h>
+#include "../../include/lmc.h"
+
+namespace lmc {
+
+// one orbit of clusters: where its tensors live and how to fold them into features
+struct OrbDev {
+  int ftab_off;    // offset of the K*T block in ftab (doubles)
+  int atab_off;    // offset of the T block in the phase-A table (raw tensor if K==1, else contracted)
+  int T, K, fidx;  // tensor length, functions, first feature index
+  int csize;       // sites per cluster
+  int row_off, row_cnt;  // rows in full_rows
+  int stride[4];
+  double w;        // size / total rows  (== 1 / multiplicity)
+};
+
+struct DevModel {
+  int N, Npad, F, Fce, nOrb, nCls, nSl, size, kone;
+  int Rmax;        // max local records of a site
+  int tabA_len;    // doubles in the phase-A table
+  double feature0;
+  // shared-memory blob (staged once per block by TMA): [cls uint4 x nCls][coef double x nCls]
+  // [tabA double x tabA_len][nat double x F][orb OrbDev x nOrb]
+  const unsigned char* blob;
+  int blob_bytes, off_coef, off_tabA, off_nat, off_orb;
+  const double* ftab;      // global copy of all feature tensors (phase B when K > 1, full evaluation)
+  const uint2* site_rec;   // [records] (idx0 | idx1<<16, idx2 | cls<<16)
+  const int* site_rec_off; // [N+1]
+  const int4* site_seg;    // [segments] (first, count, orbit, 0)
+  const int* site_seg_off; // [N+1]
+  const uint2* full_rows;  // [rows] 4 x u16 site indices
+  // Ewald
+  int E, ewW, ewF;
+  const double* ewMt;      // [E][E] TRANSPOSED matrix: ewMt[a*E + i] == M[i][a]
+  const int* ewInds;       // [N][ewW]
+  // chemical potentials
+  int muW, muF;
+  const double* mu;        // [N][muW]
+  // active sublattices
+  int sl_off[LMC_MAX_SUBLATTICES + 1];
+  int sl_ncodes[LMC_MAX_SUBLATTICES];
+  int sl_codes[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];
+  int sl_first[LMC_MAX_SUBLATTICES];   // first site if the active sites are one contiguous range, else -1
+  double sl_cum[LMC_MAX_SUBLATTICES];  // cumulative proposal probabilities
+  const int* sl_sites;
+  // table flips
+  int tfD, tfNF;
+  int tf_table[LMC_MAX_TABLE_FLIPS][LMC_MAX_DIMS];
+  double tf_w[2 * LMC_MAX_TABLE_FLIPS];
+  int tf_max_n[LMC_MAX_DIMS];
+  int tf_dim_sl[LMC_MAX_DIMS];
+  int tf_dim_code[LMC_MAX_DIMS];
+  double tf_sw;
+};
+
+struct RunArgs {
+  int W, walker_base, usher, kernel;
+  long long S;
+  int thin;
+  unsigned long long step0;
+  const unsigned long long* seeds;
+  const double* beta;
+  int8_t* occ;
+  double* features;
+  double* enthalpy;
+  int8_t* tr_occ;
+  double* tr_feat;
+  double* tr_enth;
+  uint8_t* tr_acc;
+  int* tr_nacc;
+  LmcWangLandau wl;
+  int wpb;            // walkers per block
+  int walker_smem;    // bytes of shared memory per walker
+  int off_feat, off_stash, off_cnt;  // offsets inside a walker's shared-memory slab
+};
+
+}  // namespace lmc

@@ -1,0 +1,98 @@
+"""Device engine: owns a ``liblmc`` model handle and the PyTorch device buffers.
+
+PyTorch is plumbing only (device memory, streams, pinned host copies); every kernel on the
+path is ours and is launched through the C ABI in ``include/lmc.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from .model import PackedModel
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class LmcEngine:
+    """One model resident on one CUDA device."""
+
+    def __init__(self, packed: PackedModel, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("smol_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = capi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.packed = packed
+        self.N = int(packed.desc.num_sites)
+        self.F = int(packed.desc.num_features)
+        self.row_stride = int(self.lib.lmc_row_stride(self.N))
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            capi.check(self.lib.lmc_model_create(C.byref(packed.desc), C.byref(handle)))
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.lmc_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def upload_occupancy(self, occ_host: np.ndarray):
+        """int32 ``[W, N]`` host array -> int8 ``[W, row_stride]`` device tensor."""
+        torch = _torch()
+        occ_host = np.ascontiguousarray(occ_host, dtype=np.int32)
+        W = occ_host.shape[0]
+        src = torch.from_numpy(occ_host)
+        try:
+            src = src.pin_memory()
+        except Exception:
+            pass
+        src = src.to(self.device, non_blocking=True)
+        dst = torch.empty((W, self.row_stride), dtype=torch.int8, device=self.device)
+        capi.check(self.lib.lmc_cast_i32_to_i8(src.data_ptr(), dst.data_ptr(), W, self.N,
+                                               self._stream()))
+        return dst
+
+    def occupancy_to_int32(self, occ_dev, rows: int, stride: int):
+        """int8 device rows -> int32 ``[rows, N]`` device tensor."""
+        torch = _torch()
+        out = torch.empty((rows, self.N), dtype=torch.int32, device=self.device)
+        capi.check(self.lib.lmc_cast_i8_to_i32(occ_dev.data_ptr(), out.data_ptr(), rows, self.N,
+                                               stride, self._stream()))
+        return out
+
+    def full_features(self, occ_dev):
+        torch = _torch()
+        W = occ_dev.shape[0]
+        feat = torch.empty((W, self.F), dtype=torch.float64, device=self.device)
+        enth = torch.empty((W,), dtype=torch.float64, device=self.device)
+        capi.check(self.lib.lmc_full_features(self.handle, occ_dev.data_ptr(), W, feat.data_ptr(),
+                                              enth.data_ptr(), self._stream()))
+        return feat, enth
+
+    def delta_features(self, occ_dev, sites, codes):
+        """sites/codes: int32 device tensors ``[W, k]``."""
+        torch = _torch()
+        W, k = sites.shape
+        out = torch.empty((W, self.F), dtype=torch.float64, device=self.device)
+        capi.check(self.lib.lmc_delta_features(self.handle, occ_dev.data_ptr(), W, sites.data_ptr(),
+                                               codes.data_ptr(), k, out.data_ptr(), self._stream()))
+        return out
+
+    def run(self, cfg: capi.LmcRunConfig):
+        capi.check(self.lib.lmc_run(self.handle, C.byref(cfg), self._stream()))
+
+    def launch_count(self) -> int:
+        return int(self.lib.lmc_launch_count())

@@ -256,7 +256,11 @@ class ClusterSubspace:
         self.num_orbits = oid
         self.num_corr_functions = bid
         self.num_clusters = ncl
+        self.external_terms = []   # EwaldTerm instances (clusterspace.py add_external_term)
         self._cache = {}
+
+    def add_external_term(self, term):
+        self.external_terms.append(term)
 
     # ---- reference-named properties ------------------------------------------------
     @property
@@ -487,6 +491,39 @@ def cluster_interaction_tensors(subspace: ClusterSubspace, coefs):
             for i, (m, tensor) in enumerate(zip(orb.bit_combo_multiplicities,
                                                 orb.correlation_tensors)))
         for orb in subspace.orbits)
+
+
+class ClusterExpansion:
+    """Minimal stand-in for ``smol.cofe.ClusterExpansion`` (cofe/expansion.py): subspace + coefs."""
+
+    def __init__(self, cluster_subspace, coefficients):
+        self.cluster_subspace = cluster_subspace
+        self.coefs = np.asarray(coefficients, dtype=np.float64)
+        n_ext = len(cluster_subspace.external_terms)
+        if len(self.coefs) != cluster_subspace.num_corr_functions + n_ext:
+            raise AttributeError("Feature matrix shape does not match the number of coefficients.")
+
+    @property
+    def eci(self):
+        n_ext = len(self.cluster_subspace.external_terms)
+        coefs = self.coefs[:-n_ext] if n_ext else self.coefs
+        return eci_from_coefs(self.cluster_subspace, coefs)
+
+    @property
+    def cluster_interaction_tensors(self):
+        n_ext = len(self.cluster_subspace.external_terms)
+        coefs = self.coefs[:-n_ext] if n_ext else self.coefs
+        return cluster_interaction_tensors(self.cluster_subspace, coefs)
+
+
+class EwaldTerm:
+    """Parameters of the Ewald external term (cofe/extern/ewald.py:25-63)."""
+
+    def __init__(self, eta=None, real_space_cut=None, recip_space_cut=None, use_term="total"):
+        if use_term != "total":
+            raise NotImplementedError("only the total Ewald matrix is generated here")
+        self.eta, self.real_space_cut, self.recip_space_cut = eta, real_space_cut, recip_space_cut
+        self.use_term = use_term
 
 
 # --------------------------------------------------------------------------------------

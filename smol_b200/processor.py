@@ -1,0 +1,282 @@
+"""Processors: the reference's ``smol.moca.processor`` interface evaluated on the GPU.
+
+Same class names, constructor arguments, attributes and error behaviour as
+``smol/moca/processor/{base,expansion,ewald,composite}.py``; the arithmetic runs in the
+CUDA kernels of ``liblmc`` (no CPU path).  Single-occupancy methods do a host round trip
+(they exist for API compatibility and tests); the batched ``*_batch`` variants are the
+efficient form.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import numpy as np
+
+from .model import ExpansionTables, PackedModel
+from .sublattice import Sublattice
+
+
+def _as_occu(occupancy):
+    """int32 conversion with the reference's error (expansion.py:176-189, 210-214)."""
+    try:
+        return np.array(occupancy, dtype=np.int32)
+    except (ValueError, TypeError):
+        types = {type(n) for n in occupancy}
+        raise ValueError(f"occupancy contains {types}, but should be integers!")
+
+
+class Processor(ABC):
+    """``smol/moca/processor/base.py:26-312``."""
+
+    def __init__(self, cluster_subspace, supercell_matrix, coefficients=None):
+        self._subspace = cluster_subspace
+        self._scmatrix = np.array(supercell_matrix)
+        self.size = int(round(abs(np.linalg.det(self._scmatrix))))          # base.py:66
+        self.coefs = None if coefficients is None else np.array(coefficients, dtype=np.float64)
+        self.allowed_species = list(cluster_subspace.allowed_species(self._scmatrix))
+        self.num_sites = len(self.allowed_species)
+        self._engine = None
+
+    @property
+    def cluster_subspace(self):
+        return self._subspace
+
+    @property
+    def supercell_matrix(self):
+        return self._scmatrix
+
+    # ---- encoding (base.py:192-243) ------------------------------------------------------
+    def encode_occupancy(self, occupancy):
+        return np.array([species.index(sp) for species, sp in zip(self.allowed_species, occupancy)],
+                        dtype=np.int32)
+
+    def decode_occupancy(self, encoded_occupancy):
+        return [species[i] for i, species in zip(encoded_occupancy, self.allowed_species)]
+
+    def get_sublattices(self):
+        """base.py:245-268: one sublattice per unique site space."""
+        spaces = []
+        for sp in self.allowed_species:
+            if sp not in spaces:
+                spaces.append(sp)
+        return [Sublattice(space, np.array([i for i, sp in enumerate(self.allowed_species)
+                                            if sp == space])) for space in spaces]
+
+    # ---- tables ----------------------------------------------------------------------------
+    @abstractmethod
+    def _tables(self):
+        """Return dict(expansion=ExpansionTables|None, ewald=(matrix, inds)|None)."""
+
+    def _get_engine(self):
+        if self._engine is None:
+            from .engine import LmcEngine
+            packed = PackedModel(self.num_sites, self.coefs, self.get_sublattices(), **self._tables())
+            self._engine = LmcEngine(packed)
+        return self._engine
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def compute_feature_vector_batch(self, occupancies):
+        """``[W, N]`` int occupancies -> ``[W, F]`` float64 feature vectors (GPU)."""
+        eng = self._get_engine()
+        occ = eng.upload_occupancy(_as_occu(occupancies).reshape(-1, self.num_sites))
+        feat, _ = eng.full_features(occ)
+        return feat.cpu().numpy()
+
+    def compute_feature_vector_change_batch(self, occupancies, sites, codes):
+        """Batched flips: ``sites``/``codes`` ``[W, k]`` applied sequentially per walker."""
+        import torch
+        eng = self._get_engine()
+        occ = eng.upload_occupancy(_as_occu(occupancies).reshape(-1, self.num_sites))
+        s = torch.as_tensor(np.ascontiguousarray(sites, dtype=np.int32)).to(eng.device)
+        c = torch.as_tensor(np.ascontiguousarray(codes, dtype=np.int32)).to(eng.device)
+        if s.ndim == 1:
+            s, c = s[:, None].contiguous(), c[:, None].contiguous()
+        return eng.delta_features(occ, s, c).cpu().numpy()
+
+    def compute_feature_vector(self, occupancy):
+        out = self.compute_feature_vector_batch(_as_occu(occupancy)[None, :])[0]
+        return out if out.size > 1 or not self._scalar_feature else float(out[0])
+
+    def compute_feature_vector_change(self, occupancy, flips):
+        occu = _as_occu(occupancy)
+        nfeat = len(self.coefs)
+        if len(flips) == 0:
+            out = np.zeros(nfeat)
+        else:
+            sites = np.array([[f[0] for f in flips]], dtype=np.int32)
+            codes = np.array([[f[1] for f in flips]], dtype=np.int32)
+            out = self.compute_feature_vector_change_batch(occu[None, :], sites, codes)[0]
+        return out if not self._scalar_feature else float(out[0])
+
+    _scalar_feature = False
+
+    def compute_property(self, occupancy):
+        """base.py:165-176."""
+        return np.dot(self.coefs, self.compute_feature_vector(occupancy))
+
+    def compute_property_change(self, occupancy, flips):
+        """base.py:178-190."""
+        return np.dot(self.coefs, self.compute_feature_vector_change(occupancy, flips))
+
+    def compute_average_drift(self, iterations=1000, seed=None):
+        """base.py:270-312 (delta vs full, forward and reverse), batched on the GPU."""
+        rng = np.random.default_rng(seed)
+        occu = np.array([rng.integers(len(sp)) for sp in self.allowed_species], dtype=np.int32)
+        active = [i for i, sp in enumerate(self.allowed_species) if len(sp) > 1]
+        occs, sites, codes = [], [], []
+        for _ in range(iterations):
+            site = int(rng.choice(active))
+            choices = [c for c in range(len(self.allowed_species[site])) if c != occu[site]]
+            new = int(rng.choice(choices))
+            occs.append(occu.copy())
+            sites.append(site)
+            codes.append(new)
+            occu[site] = new
+        occs.append(occu.copy())
+        occs = np.array(occs)
+        coefs = np.atleast_1d(self.coefs)
+        props = self.compute_feature_vector_batch(occs) @ coefs
+        sites_a, codes_a = np.array(sites)[:, None], np.array(codes)[:, None]
+        dfw = self.compute_feature_vector_change_batch(occs[:-1], sites_a, codes_a) @ coefs
+        back = occs[:-1][np.arange(iterations), sites][:, None]
+        drv = self.compute_feature_vector_change_batch(occs[1:], sites_a, back) @ coefs
+        forward = np.sum((props[1:] - props[:-1]) - dfw) / iterations
+        reverse = np.sum((props[:-1] - props[1:]) - drv) / iterations
+        return forward, reverse
+
+
+class ClusterExpansionProcessor(Processor):
+    """``smol/moca/processor/expansion.py:39-241``: features = correlation vector * size."""
+
+    def __init__(self, cluster_subspace, supercell_matrix, coefficients, use_concentration=False,
+                 num_threads=None, num_threads_full=None):
+        super().__init__(cluster_subspace, supercell_matrix, coefficients)
+        if len(coefficients) != cluster_subspace.num_corr_functions:
+            raise ValueError(
+                f"The provided coefficients are not the right length. Got {len(coefficients)} "
+                f"coefficients, the length must be {cluster_subspace.num_corr_functions} based on "
+                f"the provided cluster subspace.")
+        self.num_threads = num_threads            # kept for API compatibility (OpenMP knob)
+        self.num_threads_full = num_threads_full
+        self._exp = None
+
+    def _tables(self):
+        if self._exp is None:
+            self._exp = ExpansionTables(self._subspace, self._scmatrix, "correlation",
+                                        num_sites=self.num_sites)
+        return dict(expansion=self._exp)
+
+
+class ClusterDecompositionProcessor(Processor):
+    """``expansion.py:243-489``: features = mean cluster interactions * size."""
+
+    def __init__(self, cluster_subspace, supercell_matrix, interaction_tensors, coefficients=None,
+                 use_concentration=False, num_threads=None, num_threads_full=None):
+        if len(interaction_tensors) != cluster_subspace.num_orbits:
+            raise ValueError(
+                f"The number of cluster interaction tensors must match the number  of orbits in "
+                f"the subspace. Got {len(interaction_tensors)} interaction tensors, but need "
+                f"{cluster_subspace.num_orbits}  for the given cluster_subspace.")
+        coefficients = (cluster_subspace.orbit_multiplicities if coefficients is None
+                        else coefficients)                                   # expansion.py:311-316
+        super().__init__(cluster_subspace, supercell_matrix, coefficients)
+        self._interaction_tensors = interaction_tensors
+        self.num_threads = num_threads
+        self.num_threads_full = num_threads_full
+        self._exp = None
+
+    def _tables(self):
+        if self._exp is None:
+            self._exp = ExpansionTables(self._subspace, self._scmatrix, "interaction",
+                                        interaction_tensors=self._interaction_tensors,
+                                        num_sites=self.num_sites)
+        return dict(expansion=self._exp)
+
+
+class EwaldProcessor(Processor):
+    """``smol/moca/processor/ewald.py:26-208``.
+
+    The reference builds the matrix with pymatgen's ``EwaldSummation``; here it is either given
+    (``ewald_matrix`` + ``ewald_inds`` -- e.g. extracted from a live smol ``EwaldProcessor``) or
+    computed by ``smol_b200.lattice.ewald_matrix`` for the same overlaid-species structure.
+    """
+
+    _scalar_feature = True
+
+    def __init__(self, cluster_subspace, supercell_matrix, ewald_term=None, coefficient=1.0,
+                 ewald_matrix=None, ewald_inds=None):
+        super().__init__(cluster_subspace, supercell_matrix, np.array([coefficient]))
+        self._ewald_term = ewald_term
+        if ewald_matrix is None:
+            from .lattice import ewald_matrix as _ewm
+            kw = {}
+            if ewald_term is not None:
+                kw = dict(eta=getattr(ewald_term, "eta", None),
+                          real_cut=getattr(ewald_term, "real_space_cut", None),
+                          recip_cut=getattr(ewald_term, "recip_space_cut", None))
+            ewald_matrix, ewald_inds = _ewm(cluster_subspace, self._scmatrix, **kw)
+        self._matrix = np.ascontiguousarray(ewald_matrix, dtype=np.float64)
+        self._ewald_inds = np.ascontiguousarray(ewald_inds, dtype=np.int32)
+
+    @property
+    def ewald_matrix(self):
+        return self._matrix
+
+    def _tables(self):
+        return dict(ewald=(self._matrix, self._ewald_inds))
+
+    def compute_property(self, occupancy):
+        return self.coefs * self.compute_feature_vector(occupancy)            # ewald.py:103-113
+
+    def compute_property_change(self, occupancy, flips):
+        return self.coefs * self.compute_feature_vector_change(occupancy, flips)
+
+
+class CompositeProcessor(Processor):
+    """``smol/moca/processor/composite.py:26-180``: concatenated features of its members.
+
+    Supported composition (what the reference builds in ``Ensemble.from_cluster_expansion``,
+    ensemble.py:180-214): one expansion-type processor optionally followed by one
+    ``EwaldProcessor``.
+    """
+
+    def __init__(self, cluster_subspace, supercell_matrix, use_concentration=False):
+        super().__init__(cluster_subspace, supercell_matrix, None)
+        self._processors = []
+        self.coefs = np.empty(0)
+
+    @property
+    def processors(self):
+        return self._processors
+
+    def add_processor(self, processor):
+        if isinstance(processor, CompositeProcessor):
+            raise AttributeError("A CompositeProcessor can not be added into another "
+                                 "CompositeProcessor")
+        if self.cluster_subspace is not processor.cluster_subspace and \
+                self.cluster_subspace != processor.cluster_subspace:
+            raise ValueError("The cluster subspace of the processor to be added does not match "
+                             "the one of this CompositeProcessor.")
+        if not np.array_equal(self._scmatrix, processor.supercell_matrix):
+            raise ValueError("The supercell matrix of the processor to be added does not match "
+                             "the one of this CompositeProcessor.")
+        if isinstance(processor, EwaldProcessor):
+            if any(isinstance(p, EwaldProcessor) for p in self._processors):
+                raise NotImplementedError("only one EwaldProcessor per composite is supported")
+        elif self._processors:
+            raise NotImplementedError("the expansion-type processor must be added first and only once")
+        self._processors.append(processor)
+        self.coefs = np.append(self.coefs, processor.coefs)
+        self._engine = None
+
+    def _tables(self):
+        out = {}
+        for p in self._processors:
+            out.update(p._tables())
+        return out
+
+    def compute_property(self, occupancy):
+        return float(np.dot(self.coefs, self.compute_feature_vector(occupancy)))
+
+    def compute_property_change(self, occupancy, flips):
+        return float(np.dot(self.coefs, self.compute_feature_vector_change(occupancy, flips)))

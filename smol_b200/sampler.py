@@ -1,0 +1,333 @@
+"""Sampler: drop-in for ``smol.moca.Sampler`` whose step loop runs in one CUDA kernel.
+
+Mirrors ``smol/moca/sampler/sampler.py``: ``Sampler.from_ensemble(ensemble, *args,
+step_type, kernel_type, seeds, nwalkers, **kwargs)``, ``run``, ``anneal``, ``samples``,
+``efficiency``, ``clear_samples``, ``mckernels[i].temperature``.  The whole body of
+``Sampler.sample`` (sampler.py:195-210: steps x walkers x single_step) is ``lmc_run``.
+
+Randomness: counter-based Philox4x32-10 keyed by the walker's seed, counter = (global step,
+block, global walker id) -- independent of how walkers are sharded over GPUs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _capi as capi
+from .container import SampleContainer
+
+kB = 8.617333262145e-5  # smol/constants.py:4
+
+_USHERS = {"flip": capi.LMC_USHER_FLIP, "swap": capi.LMC_USHER_SWAP,
+           "tableflip": capi.LMC_USHER_TABLEFLIP, "table_flip": capi.LMC_USHER_TABLEFLIP}
+_KERNELS = {"metropolis": capi.LMC_KERNEL_METROPOLIS, "uniformlyrandom": capi.LMC_KERNEL_METROPOLIS,
+            "wanglandau": capi.LMC_KERNEL_WANGLANDAU, "wang-landau": capi.LMC_KERNEL_WANGLANDAU}
+
+
+class _KernelView:
+    """Per-walker handle standing in for the reference's MCKernel objects
+    (``sampler.mckernels[i].temperature = T`` is how ``anneal`` drives them, sampler.py:357-371)."""
+
+    def __init__(self, sampler, index):
+        self._s, self._i = sampler, index
+
+    @property
+    def temperature(self):
+        return float(self._s._temperature[self._i])
+
+    @temperature.setter
+    def temperature(self, value):
+        self._s._temperature[self._i] = float(value)
+
+    @property
+    def beta(self):
+        return 1.0 / (self._s.kB * self.temperature)
+
+    @property
+    def seed(self):
+        return int(self._s.seeds[self._i])
+
+    @property
+    def spec(self):
+        return {"kernel": self._s.kernel_type, "step": self._s.step_type, "seed": self.seed}
+
+
+def table_flip_tables(sublattices, flip_table, flip_weights=None, swap_weight=0.1):
+    """TableFlip.__init__ tables (mcusher.py:486-550): dims over ALL sublattices in order."""
+    flip_table = np.array(flip_table, dtype=np.int32)
+    active = [s for s in sublattices if len(s.active_sites) > 0]
+    dim_sl, dim_code, max_n = [], [], []
+    for s in sublattices:
+        a = next((i for i, t in enumerate(active) if t is s), -1)
+        for code in s.encoding:
+            dim_sl.append(a)
+            dim_code.append(int(code))
+            max_n.append(len(s.active_sites))
+    d = len(dim_sl)
+    if flip_table.ndim != 2 or flip_table.shape[1] != d:
+        raise ValueError(f"flip_table must have shape [n_flips, {d}]")
+    if flip_weights is None:
+        weights = np.ones(2 * len(flip_table))
+    elif len(flip_weights) == len(flip_table):
+        weights = np.repeat(np.asarray(flip_weights, dtype=np.float64), 2)
+    elif len(flip_weights) == 2 * len(flip_table):
+        weights = np.asarray(flip_weights, dtype=np.float64)
+    else:
+        raise ValueError(f"{len(flip_weights)} weights provided. You must provide either 1* or "
+                         f"2* weights given {len(flip_table)} flip vectors!")
+    changed = np.abs(flip_table).clip(min=0)
+    if (np.maximum(flip_table, 0).sum(axis=1) > capi.LMC_MAX_FLIPS).any() or \
+            (np.maximum(-flip_table, 0).sum(axis=1) > capi.LMC_MAX_FLIPS).any():
+        raise ValueError("flip vectors changing more than 4 sites are not supported")
+    del changed
+    return dict(num_dims=d, table=flip_table, weights=weights, max_n=max_n, dim_sl=dim_sl,
+                dim_code=dim_code, swap_weight=float(swap_weight))
+
+
+class Sampler:
+    """GPU Monte-Carlo sampler with the interface of ``smol.moca.Sampler``."""
+
+    def __init__(self, ensemble, kernel_type="Metropolis", step_type="swap", nwalkers=1, seeds=None,
+                 temperature=None, wl_params=None, usher_kwargs=None, walker_id_base=0,
+                 group_size=0, block_threads=0, record_occupancy=True, device=None, kB_=kB):
+        from .engine import LmcEngine
+        self.ensemble = ensemble
+        self.kernel_type = kernel_type
+        self.step_type = step_type
+        key = kernel_type.lower().replace("_", "")
+        if key not in _KERNELS:
+            raise ValueError(f"{kernel_type} is not a supported MCKernel "
+                             f"(available: Metropolis, UniformlyRandom, WangLandau)")
+        self._kernel = _KERNELS[key]
+        self._uniform = key == "uniformlyrandom"
+        ukey = step_type.lower().replace("-", "").replace("_", "") if step_type else "swap"
+        ukey = "tableflip" if ukey == "tableflip" else ukey
+        if ukey not in _USHERS:
+            raise ValueError(f"{step_type} is not a supported MCUsher (available: flip, swap, "
+                             f"table_flip)")
+        self._usher = _USHERS[ukey]
+        usher_kwargs = dict(usher_kwargs or {})
+        self.nwalkers = int(nwalkers)
+        if seeds is None:
+            ss = np.random.SeedSequence()
+            seeds = [int(x) for x in ss.generate_state(self.nwalkers, dtype=np.uint64)]
+        if len(seeds) != self.nwalkers:
+            raise ValueError("Number of seeds does not match number of kernels!")
+        self.seeds = np.array([int(s) & 0xFFFFFFFFFFFFFFFF for s in seeds], dtype=np.uint64)
+        self.kB = kB_
+        self._temperature = np.zeros(self.nwalkers)
+        if self._kernel == capi.LMC_KERNEL_METROPOLIS:
+            if self._uniform:
+                self._temperature[:] = np.inf
+            else:
+                if temperature is None:
+                    raise TypeError("Metropolis kernel needs a temperature")
+                self._temperature[:] = float(temperature)
+        self._wl = dict(wl_params or {})
+        table_flip = None
+        if self._usher == capi.LMC_USHER_TABLEFLIP:
+            if usher_kwargs.get("flip_table") is None:
+                raise NotImplementedError(
+                    "TableFlip needs an explicit flip_table (CompositionSpace generation of the "
+                    "table, smol/moca/composition/space.py, is outside the hot path)")
+            table_flip = table_flip_tables(ensemble.sublattices, usher_kwargs["flip_table"],
+                                           usher_kwargs.get("flip_weights"),
+                                           usher_kwargs.get("swap_weight", 0.1))
+        self._packed = ensemble.packed_model(
+            table_flip=table_flip,
+            sublattice_probabilities=usher_kwargs.get("sublattice_probabilities"))
+        self.engine = LmcEngine(self._packed, device=device)
+        self.walker_id_base = int(walker_id_base)
+        self.group_size, self.block_threads = int(group_size), int(block_threads)
+        self.record_occupancy = record_occupancy
+        self.mckernels = [_KernelView(self, i) for i in range(self.nwalkers)]
+        self._step_counter = 0
+        self._occ_dev = None
+        self._wl_state = None
+        N, F = ensemble.num_sites, len(ensemble.natural_parameters)
+        shapes = {"occupancy": ((N,), np.int32), "features": ((F,), np.float64),
+                  "enthalpy": ((1,), np.float64), "accepted": ((1,), bool),
+                  "n_accepted": ((), np.int32)}
+        if self._kernel == capi.LMC_KERNEL_METROPOLIS:
+            shapes["temperature"] = ((1,), np.float64)
+        self._container = SampleContainer(ensemble, self.nwalkers, shapes,
+                                          dict(ensemble.thermo_boundaries))
+
+    # ---- construction (sampler.py:52-139) ------------------------------------------------------
+    @classmethod
+    def from_ensemble(cls, ensemble, *args, step_type=None, kernel_type=None, seeds=None, nwalkers=1,
+                      **kwargs):
+        if step_type is None:
+            step_type = "flip" if getattr(ensemble, "chemical_potentials", None) is not None else "swap"
+        if kernel_type is None:
+            kernel_type = "Metropolis"
+        engine_kw = {k: kwargs.pop(k) for k in ("walker_id_base", "group_size", "block_threads",
+                                                "record_occupancy", "device") if k in kwargs}
+        key = kernel_type.lower().replace("_", "").replace("-", "")
+        temperature, wl = None, None
+        if key == "wanglandau":
+            names = ("min_enthalpy", "max_enthalpy", "bin_size")
+            vals = list(args)
+            wl = {}
+            for n in names:
+                wl[n] = kwargs.pop(n) if n in kwargs else vals.pop(0)
+            for n, dflt in (("flatness", 0.8), ("mod_factor", 1.0), ("check_period", 1000),
+                            ("update_period", 1), ("mod_update", None)):
+                wl[n] = kwargs.pop(n, dflt)
+        elif key == "metropolis":
+            temperature = kwargs.pop("temperature") if "temperature" in kwargs else args[0]
+        usher_kwargs = kwargs
+        return cls(ensemble, kernel_type=kernel_type, step_type=step_type, nwalkers=nwalkers,
+                   seeds=seeds, temperature=temperature, wl_params=wl, usher_kwargs=usher_kwargs,
+                   **engine_kw)
+
+    @property
+    def samples(self):
+        return self._container
+
+    def efficiency(self, discard=0, flat=True):
+        return self.samples.sampling_efficiency(discard=discard, flat=flat)
+
+    def clear_samples(self):
+        self.samples.clear()
+
+    # ---- Wang-Landau state ------------------------------------------------------------------------
+    def _init_wl(self):
+        import torch
+        p = self._wl
+        if p["min_enthalpy"] > p["max_enthalpy"]:
+            raise ValueError("min_enthalpy can not be larger than max_enthalpy.")
+        if (p["max_enthalpy"] - p["min_enthalpy"]) / p["bin_size"] <= 1:
+            raise ValueError("The values provided for min and max enthalpy and bin sizer result in "
+                             "a single bin!")
+        if p["mod_factor"] <= 0:
+            raise ValueError("mod_factor must be greater than 0.")
+        if callable(p.get("mod_update")):
+            raise NotImplementedError("callable mod_update is not supported on the GPU path")
+        levels = np.arange(p["min_enthalpy"], p["max_enthalpy"], p["bin_size"])  # wanglandau.py:107
+        nb, W, F = len(levels), self.nwalkers, self.engine.F
+        dev = self.engine.device
+        self._wl_state = dict(
+            levels=levels,
+            entropy=torch.zeros((W, nb), dtype=torch.float64, device=dev),
+            histogram=torch.zeros((W, nb), dtype=torch.int64, device=dev),
+            occurrences=torch.zeros((W, nb), dtype=torch.int64, device=dev),
+            mean_features=torch.zeros((W, nb, F), dtype=torch.float64, device=dev),
+            mod_factor=torch.full((W,), float(p["mod_factor"]), dtype=torch.float64, device=dev),
+            steps_counter=torch.zeros((W,), dtype=torch.int64, device=dev))
+
+    @property
+    def wang_landau_state(self):
+        """Per-walker arrays (entropy, histogram, occurrences, mean_features, mod_factor) on host."""
+        if self._wl_state is None:
+            return None
+        return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in self._wl_state.items()}
+
+    # ---- run (sampler.py:164-297, 386-434) ------------------------------------------------------------
+    def run(self, nsteps, initial_occupancies=None, thin_by=1, progress=False, stream_chunk=0,
+            stream_file=None, keep_last_chunk=False, swmr_mode=False, max_chunk_bytes=2 << 30):
+        import torch
+        eng = self.engine
+        if stream_chunk:
+            raise NotImplementedError("HDF5 streaming (container.py:420-512) is not part of this build")
+        if initial_occupancies is None:
+            if self._occ_dev is None:
+                raise RuntimeError("There are no saved samples to obtain the initial occupancies."
+                                   "These must be provided.")
+        else:
+            if self.samples.num_samples > 0:
+                warnings.warn("Initial occupancies where provided with a pre-existing set of samples."
+                              "\n Make real sure that is what you want. If not, reset the samples in "
+                              "the sampler.", RuntimeWarning)
+            occ = np.array(initial_occupancies)
+            if occ.ndim == 1 and self.nwalkers == 1:
+                occ = occ[None, :]
+            if occ.shape != (self.nwalkers, eng.N):
+                raise AttributeError("The given initial occcupancies have incompompatible dimensions. "
+                                     f"Shape should be {(self.nwalkers, eng.N)}.")
+            self._occ_dev = eng.upload_occupancy(occ.astype(np.int32))       # sampler.py:401-406
+        if nsteps % thin_by != 0:
+            warnings.warn(f"The number of steps {nsteps} is not a multiple of thin_by  {thin_by}. "
+                          f"The last {nsteps % thin_by} will be ignored.", category=RuntimeWarning)
+        S = nsteps // thin_by
+        W, N, F = self.nwalkers, eng.N, eng.F
+        dev = eng.device
+        # initial trace: full evaluation of the starting occupancies (base.py:345-365,
+        # wanglandau.py:290-300)
+        feat, enth = eng.full_features(self._occ_dev)
+        if self._kernel == capi.LMC_KERNEL_WANGLANDAU and self._wl_state is None:
+            self._init_wl()
+        seeds = torch.from_numpy(self.seeds.view(np.int64)).to(dev)
+        with np.errstate(divide="ignore"):
+            beta_h = np.where(np.isinf(self._temperature), 0.0, 1.0 / (self.kB * self._temperature))
+        beta = torch.from_numpy(np.ascontiguousarray(beta_h)).to(dev)
+        per_sample = W * ((N if self.record_occupancy else 0) + 8 * F + 8 + 1 + 4)
+        chunk = max(1, min(S, int(max_chunk_bytes // max(per_sample, 1)))) if S else 0
+        done = 0
+        while done < S:
+            n = min(chunk, S - done)
+            tr_occ = torch.empty((n, W, N), dtype=torch.int8, device=dev) if self.record_occupancy else None
+            tr_feat = torch.empty((n, W, F), dtype=torch.float64, device=dev)
+            tr_enth = torch.empty((n, W), dtype=torch.float64, device=dev)
+            tr_acc = torch.empty((n, W), dtype=torch.uint8, device=dev)
+            tr_nacc = torch.empty((n, W), dtype=torch.int32, device=dev)
+            cfg = capi.LmcRunConfig()
+            cfg.num_walkers, cfg.walker_id_base = W, self.walker_id_base
+            cfg.usher, cfg.kernel = self._usher, self._kernel
+            cfg.num_samples, cfg.thin_by = n, thin_by
+            cfg.group_size, cfg.block_threads = self.group_size, self.block_threads
+            cfg.step_begin = self._step_counter
+            cfg.seeds_dev, cfg.beta_dev = seeds.data_ptr(), beta.data_ptr()
+            cfg.occ_dev, cfg.features_dev, cfg.enthalpy_dev = \
+                self._occ_dev.data_ptr(), feat.data_ptr(), enth.data_ptr()
+            cfg.trace_occ_dev = tr_occ.data_ptr() if tr_occ is not None else None
+            cfg.trace_features_dev, cfg.trace_enthalpy_dev = tr_feat.data_ptr(), tr_enth.data_ptr()
+            cfg.trace_accepted_dev, cfg.trace_naccepted_dev = tr_acc.data_ptr(), tr_nacc.data_ptr()
+            if self._kernel == capi.LMC_KERNEL_WANGLANDAU:
+                p, st = self._wl, self._wl_state
+                wl = cfg.wl
+                wl.min_enthalpy, wl.max_enthalpy, wl.bin_size = p["min_enthalpy"], p["max_enthalpy"], p["bin_size"]
+                wl.flatness = p["flatness"]
+                wl.mod_update = float(p["mod_update"]) if p.get("mod_update") is not None else 2.0
+                wl.num_bins, wl.check_period, wl.update_period = len(st["levels"]), p["check_period"], p["update_period"]
+                wl.entropy_dev, wl.histogram_dev = st["entropy"].data_ptr(), st["histogram"].data_ptr()
+                wl.occurrences_dev, wl.mean_features_dev = st["occurrences"].data_ptr(), st["mean_features"].data_ptr()
+                wl.mod_factor_dev, wl.steps_counter_dev = st["mod_factor"].data_ptr(), st["steps_counter"].data_ptr()
+            eng.run(cfg)
+            self._step_counter += n * thin_by
+            traces = {
+                "features": tr_feat.cpu().numpy(),
+                "enthalpy": tr_enth.cpu().numpy()[:, :, None],
+                "accepted": tr_acc.cpu().numpy().astype(bool)[:, :, None],
+                "n_accepted": tr_nacc.cpu().numpy(),
+            }
+            if self.record_occupancy:
+                traces["occupancy"] = tr_occ.cpu().numpy()     # int8 on host; int32 on access
+            else:
+                traces["occupancy"] = np.zeros((n, W, 0), dtype=np.int8)
+            if "temperature" in self.samples._shapes:
+                traces["temperature"] = np.broadcast_to(self._temperature[None, :, None], (n, W, 1)).copy()
+            self.samples.append(traces, thin_by)
+            done += n
+        torch.cuda.synchronize(dev)
+
+    def anneal(self, temperatures, mcmc_steps, initial_occupancies=None, thin_by=1, progress=False,
+               stream_chunk=0, stream_file=None, swmr_mode=True):
+        """sampler.py:303-384."""
+        if temperatures[0] < temperatures[-1]:
+            raise ValueError("End temperature is greater than start "
+                             f"temperature {temperatures[-1]:.2f} > {temperatures[0]:.2f}.")
+        for k in self.mckernels:
+            k.temperature = temperatures[0]
+        self.run(mcmc_steps, initial_occupancies=initial_occupancies, thin_by=thin_by)
+        for t in temperatures[1:]:
+            for k in self.mckernels:
+                k.temperature = t
+            self.run(mcmc_steps, thin_by=thin_by)
+
+    def current_occupancies(self):
+        """int32 ``[W, N]`` host copy of the walkers' current occupancies."""
+        eng = self.engine
+        return eng.occupancy_to_int32(self._occ_dev, self.nwalkers, eng.row_stride).cpu().numpy()

@@ -1,0 +1,160 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+from tests import models as M
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10   # north-star float tolerance (relative); ATOL scales with the feature magnitude
+
+
+def _oracle():
+    from oracle import lmc_oracle as O
+    return O
+
+
+def _processors(kind, subspace, scm, coefs):
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    if kind == "expansion":
+        return (S.ClusterExpansionProcessor(subspace, scm, coefs),
+                O.ClusterExpansionProcessor(subspace, scm, coefs))
+    it = L.cluster_interaction_tensors(subspace, coefs)
+    return (S.ClusterDecompositionProcessor(subspace, scm, it),
+            O.ClusterDecompositionProcessor(subspace, scm, it))
+
+
+@pytest.mark.parametrize("kind", ["expansion", "decomposition"])
+@pytest.mark.parametrize("case", ["fcc2", "fcc4", "rs3"])
+def test_full_and_delta_features(cuda_device, kind, case):
+    if case.startswith("fcc"):
+        sub = M.fcc_subspace()
+        n = int(case[3:])
+    else:
+        sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+        n = 3
+    scm = np.eye(3, dtype=int) * n
+    rng = np.random.default_rng(5)
+    coefs = rng.normal(0, 0.05, sub.num_corr_functions)
+    gpu, ora = _processors(kind, sub, scm, coefs)
+    W = 24
+    occ = M.random_occupancies(sub, scm, W, seed=3)
+    full_g = gpu.compute_feature_vector_batch(occ)
+    full_o = np.array([ora.compute_feature_vector(o) for o in occ])
+    scale = np.abs(full_o).max()
+    np.testing.assert_allclose(full_g, full_o, rtol=RTOL, atol=RTOL * scale)
+    spaces = sub.allowed_species(scm)
+    active = [i for i, s in enumerate(spaces) if len(s) > 1]
+    for k in (1, 2, 3):
+        sites = rng.choice(active, size=(W, k))
+        codes = np.zeros((W, k), dtype=np.int32)
+        for w in range(W):
+            cur = occ[w].copy()
+            for j in range(k):
+                s = sites[w, j]
+                ch = [c for c in range(len(spaces[s])) if c != cur[s]]
+                codes[w, j] = rng.choice(ch)
+                cur[s] = codes[w, j]
+        d_g = gpu.compute_feature_vector_change_batch(occ, sites, codes)
+        d_o = np.array([ora.compute_feature_vector_change(occ[w], list(zip(sites[w], codes[w])))
+                        for w in range(W)])
+        np.testing.assert_allclose(d_g, d_o, rtol=RTOL, atol=RTOL * scale)
+
+
+def _run_both(ens_g, ens_o_factory, usher_name, W, nsteps, thin, occ0, seeds, T=None, wl=None,
+              usher_kwargs=None, group_size=0):
+    import smol_b200 as S
+    O = _oracle()
+    usher_kwargs = usher_kwargs or {}
+    if wl is None:
+        smp = S.Sampler.from_ensemble(ens_g, T, step_type=usher_name, nwalkers=W, seeds=list(seeds),
+                                      group_size=group_size, **usher_kwargs)
+    else:
+        smp = S.Sampler.from_ensemble(ens_g, wl["min"], wl["max"], wl["bin"], step_type=usher_name,
+                                      kernel_type="WangLandau", nwalkers=W, seeds=list(seeds),
+                                      check_period=wl["check"], flatness=wl["flatness"],
+                                      group_size=group_size, **usher_kwargs)
+    smp.run(nsteps, occ0, thin_by=thin)
+    kernels = []
+    for w in range(W):
+        ens_o = ens_o_factory()
+        subl = ens_o.sublattices
+        if usher_name == "swap":
+            ush = O.Swap(subl, usher_kwargs.get("sublattice_probabilities"))
+        elif usher_name == "flip":
+            ush = O.Flip(subl, usher_kwargs.get("sublattice_probabilities"))
+        else:
+            ush = O.TableFlip(subl, usher_kwargs["flip_table"],
+                              swap_weight=usher_kwargs.get("swap_weight", 0.1))
+        if wl is None:
+            kernels.append(O.Metropolis(ens_o, ush, T, seed=int(seeds[w]), walker=w))
+        else:
+            kernels.append(O.WangLandau(ens_o, ush, wl["min"], wl["max"], wl["bin"],
+                                        flatness=wl["flatness"], check_period=wl["check"],
+                                        seed=int(seeds[w]), walker=w))
+    ref = O.run_sampler(kernels, occ0, nsteps, thin)
+    return smp, ref, kernels
+
+
+def _compare_traces(smp, ref):
+    s = smp.samples
+    np.testing.assert_array_equal(s.get_occupancies(flat=False), ref["occupancy"])   # bit exact
+    np.testing.assert_array_equal(s.get_trace_value("accepted", flat=False), ref["accepted"])
+    np.testing.assert_array_equal(s.get_trace_value("n_accepted", flat=False), ref["n_accepted"])
+    scale = np.abs(ref["features"]).max()
+    np.testing.assert_allclose(s.get_feature_vectors(flat=False), ref["features"], rtol=RTOL,
+                               atol=RTOL * scale)
+    np.testing.assert_allclose(s.get_enthalpies(flat=False), ref["enthalpy"], rtol=RTOL,
+                               atol=RTOL * np.abs(ref["enthalpy"]).max())
+
+
+@pytest.mark.parametrize("kind", ["decomposition", "expansion"])
+@pytest.mark.parametrize("n,group", [(2, 0), (4, 8), (4, 32)])
+def test_canonical_swap_trajectory(cuda_device, kind, n, group):
+    import smol_b200 as S
+    O = _oracle()
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * n
+    coefs = M.fcc_coefs(sub)
+    gpu_p, ora_p = _processors(kind, sub, scm, coefs)
+    ens_g = S.Ensemble(gpu_p)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices))
+
+    W = 6
+    occ0 = M.random_occupancies(sub, scm, W, seed=1, balanced=True)
+    seeds = np.arange(100, 100 + W)
+    smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, 400, 20, occ0, seeds, T=1000.0, group_size=group)
+    _compare_traces(smp, ref)
+    assert 0 < smp.samples.step_efficiency() <= 1
+
+
+def test_semigrand_ewald_flip_trajectory(cuda_device):
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    sub = M.rocksalt_subspace()
+    scm = np.eye(3, dtype=int) * 2
+    rng = np.random.default_rng(11)
+    coefs = rng.normal(0, 0.05, sub.num_corr_functions)
+    it = L.cluster_interaction_tensors(sub, coefs)
+    ewm, ewi = L.ewald_matrix(sub, scm)
+    comp = S.CompositeProcessor(sub, scm)
+    comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
+    comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.1, ewald_matrix=ewm, ewald_inds=ewi))
+    mus = {"Li+": 0.0, "Mn3+": 0.3, "Ti4+": -0.2}
+    ens_g = S.Ensemble(comp, chemical_potentials=mus)
+    ora_p = O.CompositeProcessor([O.ClusterDecompositionProcessor(sub, scm, it),
+                                  O.EwaldProcessor(ewm, ewi, 0.1)])
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices), chemical_potentials=mus)
+
+    W = 4
+    occ0 = M.random_occupancies(sub, scm, W, seed=2)
+    seeds = np.arange(7, 7 + W)
+    smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 300, 10, occ0, seeds, T=1500.0)
+    _compare_traces(smp, ref)
