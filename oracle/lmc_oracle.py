@@ -217,7 +217,11 @@ class _ExpansionBase:
         self.coefs = np.asarray(coefficients, dtype=np.float64)
         self._orbit_data = get_orbit_data(cluster_subspace.orbits)
         self._indices = tuple(cluster_subspace.get_orbit_indices(supercell_matrix).arrays)
-        self.num_sites = 1 + max(int(a.max()) for a in self._indices)
+        # Processor.num_sites = len(supercell structure) (processor/base.py:88-91), which also counts
+        # sites without configurational freedom that appear in no cluster
+        nss = getattr(cluster_subspace, "num_supercell_sites", None)
+        self.num_sites = (int(nss(self.supercell_matrix)) if nss is not None
+                          else 1 + max(int(a.max()) for a in self._indices))
         self._ref = load_ref() if use_ref else None
         if use_ref and self._ref is None:
             raise RuntimeError("oracle/_ref is not built; run python oracle/build_ref.py")

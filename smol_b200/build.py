@@ -44,10 +44,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     jobs = [(os.path.join(CSRC, "lmc_api.cu"), os.path.join(objdir, "lmc_api.o"), [])]
     for g in GROUPS:
-        jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"), os.path.join(objdir, f"lmc_run_g{g}.o"),
-                     [f"-DLMC_G={g}"]))
+        for wl in (0, 1):
+            jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"),
+                         os.path.join(objdir, f"lmc_run_g{g}_wl{wl}.o"), [f"-DLMC_G={g}", f"-DLMC_WL={wl}"]))
     log = []
-    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:
         for cmd, r in ex.map(_compile, jobs):
             log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             if r.returncode != 0:

@@ -130,29 +130,30 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       }
     }
   }
-  // blob: cls | coef | tabA | nat | orb
+  // blob: cls (nCls + 1 entries, the last is the all-zero padding class) | tabA | nat | orb
   {
-    const int C = m.nCls;
+    const int C = m.nCls + 1;
     size_t off = 0;
     const size_t off_cls = off; off += (size_t)C * 16;
-    m.off_coef = (int)off; off += ((size_t)C * 8 + 15) & ~size_t(15);
+    m.off_coef = (int)off;
     m.off_tabA = (int)off; off += ((size_t)tabA_len * 8 + 15) & ~size_t(15);
     m.off_nat = (int)off; off += ((size_t)m.F * 8 + 15) & ~size_t(15);
     m.off_orb = (int)off; off += ((size_t)m.nOrb * sizeof(OrbDev) + 15) & ~size_t(15);
     m.blob_bytes = (int)off;
     std::vector<unsigned char> blob(off, 0);
     uint32_t* cls = reinterpret_cast<uint32_t*>(blob.data() + off_cls);
-    double* coef = reinterpret_cast<double*>(blob.data() + m.off_coef);
-    for (int c = 0; c < C; ++c) {
+    for (int c = 0; c < m.nCls; ++c) {
       const int orb = d->cls_orbit[c];
       const int* st = d->cls_stride + c * 4;
       for (int i = 0; i < 4; ++i)
-        if (st[i] < 0 || st[i] > 65535) { lmc_model_destroy(mdl); return fail("class stride out of range"); }
-      cls[c * 4 + 0] = (uint32_t)st[0] | ((uint32_t)st[1] << 16);
-      cls[c * 4 + 1] = (uint32_t)st[2] | ((uint32_t)st[3] << 16);
-      cls[c * 4 + 2] = (uint32_t)orbs[orb].atab_off;
-      cls[c * 4 + 3] = (uint32_t)orb;
-      coef[c] = kone ? d->natural_parameters[orbs[orb].fidx] * orbs[orb].w : 1.0;
+        if (st[i] < 0 || st[i] > 255) {
+          lmc_model_destroy(mdl);
+          return fail("flat tensor strides above 255 are not supported (u8 strides for dp4a)");
+        }
+      cls[c * 4 + 0] = (uint32_t)st[0] | ((uint32_t)st[1] << 8) | ((uint32_t)st[2] << 16) | ((uint32_t)st[3] << 24);
+      cls[c * 4 + 1] = (uint32_t)orbs[orb].atab_off;
+      const double coef = kone ? d->natural_parameters[orbs[orb].fidx] * orbs[orb].w : 1.0;
+      memcpy(&cls[c * 4 + 2], &coef, 8);
     }
     memcpy(blob.data() + m.off_tabA, tabA.data(), (size_t)tabA_len * 8);
     memcpy(blob.data() + m.off_nat, d->natural_parameters, (size_t)m.F * 8);
@@ -164,14 +165,19 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
   UP(double, d->ftab, d->ftab_len, m.ftab);
   // records
   {
-    const int64_t nrec = d->site_rec_off[m.N];
-    std::vector<int> off32(m.N + 1);
     int rmax = 0;
-    for (int i = 0; i <= m.N; ++i) off32[i] = (int)d->site_rec_off[i];
-    for (int i = 0; i < m.N; ++i) rmax = std::max(rmax, off32[i + 1] - off32[i]);
-    m.Rmax = (rmax + 1) & ~1;
-    UP(int, off32.data(), m.N + 1, m.site_rec_off);
-    UP(uint2, d->site_rec, nrec, m.site_rec);
+    for (int i = 0; i < m.N; ++i) rmax = std::max(rmax, (int)(d->site_rec_off[i + 1] - d->site_rec_off[i]));
+    m.Rstride = std::max(32, (rmax + 31) & ~31);  // multiple of every group size
+    // fixed-stride table: site s owns records [s*Rstride, (s+1)*Rstride); pads point at site 0
+    // with the zero class so that they contribute exactly 0
+    std::vector<uint16_t> rec((size_t)m.N * m.Rstride * 4, 0);
+    for (int i = 0; i < m.N; ++i) {
+      const int64_t a = d->site_rec_off[i], b = d->site_rec_off[i + 1];
+      uint16_t* dst = rec.data() + (size_t)i * m.Rstride * 4;
+      memcpy(dst, d->site_rec + a * 4, (size_t)(b - a) * 8);
+      for (int r = (int)(b - a); r < m.Rstride; ++r) dst[r * 4 + 3] = (uint16_t)m.nCls;
+    }
+    UP(uint2, rec.data(), (size_t)m.N * m.Rstride, m.site_rec);
     const int64_t nseg = d->site_seg_off[m.N];
     std::vector<int> soff(m.N + 1);
     for (int i = 0; i <= m.N; ++i) soff[i] = (int)d->site_seg_off[i];
@@ -220,6 +226,15 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       m.sl_first[s] = contig ? d->sl_sites[a] : -1;
     }
     m.sl_off[m.nSl] = d->sl_site_off[m.nSl];
+    int pw = 0;
+    for (int s = 0; s < m.nSl; ++s) {
+      int maxcode = 0;
+      for (int c = 0; c < m.sl_ncodes[s]; ++c) maxcode = std::max(maxcode, m.sl_codes[s][c]);
+      m.sl_nwords[s] = (m.sl_off[s + 1] - m.sl_off[s] + 31) / 32;
+      m.sl_plane_off[s] = pw;
+      pw += (maxcode + 1) * m.sl_nwords[s];
+    }
+    m.plane_words = pw;
     UP(int, d->sl_sites, d->sl_site_off[m.nSl], m.sl_sites);
   }
   m.tfD = d->tf_num_flips > 0 ? d->tf_num_dims : 0;
@@ -269,7 +284,7 @@ extern "C" int lmc_full_features(const LmcModel* mdl, const int8_t* occ, int W, 
 }
 
 static size_t delta_walker_smem(const DevModel& m) {
-  return (((size_t)m.F * 8 + 15) & ~size_t(15)) + (((size_t)m.Rmax * 8 + 15) & ~size_t(15));
+  return (((size_t)m.F * 8 + 15) & ~size_t(15)) + (((size_t)m.Rstride * 8 + 15) & ~size_t(15));
 }
 
 extern "C" int lmc_delta_features(const LmcModel* mdl, const int8_t* occ, int W, const int32_t* sites, const int32_t* codes,
@@ -335,8 +350,17 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const size_t stash_el = m.kone ? 8 : 4;
   a.off_feat = 0;
   a.off_stash = (int)(((size_t)m.F * 8 + 15) & ~size_t(15));
-  a.off_cnt = a.off_stash + (int)(((size_t)LMC_MAX_FLIPS * m.Rmax * stash_el + 15) & ~size_t(15));
-  a.walker_smem = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
+  a.max_flips = c->usher == LMC_USHER_FLIP ? 1 : 2;
+  if (c->usher == LMC_USHER_TABLEFLIP)
+    for (int i = 0; i < m.tfNF; ++i) {
+      int up = 0, dn = 0;
+      for (int k = 0; k < m.tfD; ++k) { up += std::max(m.tf_table[i][k], 0); dn += std::max(-m.tf_table[i][k], 0); }
+      a.max_flips = std::max(a.max_flips, std::max(up, dn));
+    }
+  if (a.max_flips > LMC_MAX_FLIPS) return fail("flip table changes more than 4 sites per step");
+  a.off_cnt = a.off_stash + (int)(((size_t)a.max_flips * m.Rstride * stash_el + 15) & ~size_t(15));
+  a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
+  a.walker_smem = a.off_plane + ((m.plane_words * 4 + 15) & ~15);
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
   for (;;) {
@@ -349,11 +373,12 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const int grid = (a.W + a.wpb - 1) / a.wpb;
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
   int rc = -2;
+  const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
   switch (G) {
-    case 4: rc = launch_run_g4(m, a, m.kone != 0, ewald, c->usher, lc); break;
-    case 8: rc = launch_run_g8(m, a, m.kone != 0, ewald, c->usher, lc); break;
-    case 16: rc = launch_run_g16(m, a, m.kone != 0, ewald, c->usher, lc); break;
-    case 32: rc = launch_run_g32(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 16: rc = (wl ? launch_run_wl_g16 : launch_run_g16)(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 32: rc = (wl ? launch_run_wl_g32 : launch_run_g32)(m, a, m.kone != 0, ewald, c->usher, lc); break;
   }
   if (rc == -2) return fail("no kernel instantiated for this group size / usher");
   g_launches++;

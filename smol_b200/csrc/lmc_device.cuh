@@ -15,25 +15,28 @@ namespace lmc {
 // ------------------------------------------------------------------------------------------
 struct U4 { uint32_t x, y, z, w; };
 
-__host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                     uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ void mulwide(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+  uint64_t p;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
-    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
-    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    uint32_t hi0, lo0, hi1, lo1;
+    mulwide(0xD2511F53u, c0, hi0, lo0);
+    mulwide(0xCD9E8D57u, c2, hi1, lo1);
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   return U4{c0, c1, c2, c3};
 }
 
-__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t r, uint32_t n) {
-  return (uint32_t)(((uint64_t)r * (uint64_t)n) >> 32);
-}
-__host__ __device__ __forceinline__ double u01(uint32_t r) { return ((double)r + 0.5) * 2.3283064365386963e-10; }
+__device__ __forceinline__ uint32_t mulhi32(uint32_t r, uint32_t n) { return __umulhi(r, n); }
+__device__ __forceinline__ double u01(uint32_t r) { return ((double)r + 0.5) * 2.3283064365386963e-10; }
 
 // ------------------------------------------------------------------------------------------
 // TMA bulk copy + mbarrier helpers (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS)

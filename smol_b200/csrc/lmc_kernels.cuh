@@ -8,8 +8,8 @@ namespace lmc {
 
 // shared-memory view of the staged tables
 struct SmemTables {
-  const uint4* cls;     // (s0 | s1<<16, s2 | self<<16, atab_off, orbit)
-  const double* coef;   // nat[fidx] * w of the class' orbit (K == 1 only)
+  const uint4* cls;     // (strides u8x4 [other0, other1, other2, self], atab_off, coef lo, coef hi)
+  const double* coef;   // unused (kept for layout compatibility)
   const double* tabA;   // phase-A table
   const double* nat;    // natural parameters
   const OrbDev* orb;
@@ -18,7 +18,7 @@ struct SmemTables {
 __device__ __forceinline__ SmemTables smem_tables(const DevModel& m, const unsigned char* base) {
   SmemTables t;
   t.cls = reinterpret_cast<const uint4*>(base);
-  t.coef = reinterpret_cast<const double*>(base + m.off_coef);
+  t.coef = nullptr;
   t.tabA = reinterpret_cast<const double*>(base + m.off_tabA);
   t.nat = reinterpret_cast<const double*>(base + m.off_nat);
   t.orb = reinterpret_cast<const OrbDev*>(base + m.off_orb);
@@ -49,26 +49,65 @@ __device__ __forceinline__ void stage_tables(const DevModel& m, unsigned char* s
 // (smol/utils/cluster/evaluator.pyx:211-317) contracted with the natural parameters.
 // The per-record differences are stashed for phase B.
 // ------------------------------------------------------------------------------------------
+struct RecChunk { uint2 r[4]; };  // the first 4*G records of a site, one lane's share
+
+template <int G>
+__device__ __forceinline__ RecChunk load_records(const DevModel& m, int site, int g) {
+  const uint2* rp = m.site_rec + (size_t)site * m.Rstride;
+  RecChunk c;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = g + u * G;
+    c.r[u] = r < m.Rstride ? __ldg(rp + r) : make_uint2(0u, (uint32_t)m.nCls << 16);
+  }
+  return c;
+}
+
+template <bool KONE>
+__device__ __forceinline__ void eval_record(const SmemTables& t, const uint8_t* occ, const uint2 rec, uint32_t oldsh,
+                                            uint32_t xmask, void* stash, int r, double& acc) {
+  const uint4 ci = t.cls[rec.y >> 16];
+  // occupancy bytes of the three other sites + the old code in the self slot; one dp4a each gives
+  // the flat tensor index before / after the flip
+  const uint32_t o = (uint32_t)occ[rec.x & 0xffffu] | ((uint32_t)occ[rec.x >> 16] << 8) |
+                     ((uint32_t)occ[rec.y & 0xffffu] << 16) | oldsh;
+  const uint32_t ii = __dp4a(o, ci.x, ci.y);
+  const uint32_t ff = __dp4a(o ^ xmask, ci.x, ci.y);
+  const double d = t.tabA[ff] - t.tabA[ii];
+  if (KONE) {
+    acc += __hiloint2double((int)ci.w, (int)ci.z) * d;
+    reinterpret_cast<double*>(stash)[r] = d;
+  } else {
+    acc += d;
+    reinterpret_cast<uint32_t*>(stash)[r] = (ff - ci.y) | ((ii - ci.y) << 16);
+  }
+}
+
 template <int G, bool KONE>
 __device__ __forceinline__ double flip_energy(const DevModel& m, const SmemTables& t, const uint8_t* occ, int site,
-                                              int olda, int newb, void* stash, int g) {
-  const int r0 = __ldg(m.site_rec_off + site), r1 = __ldg(m.site_rec_off + site + 1);
+                                              int olda, int newb, void* stash, int g, const RecChunk& pre) {
+  const uint32_t oldsh = (uint32_t)olda << 24;
+  const uint32_t xmask = (uint32_t)(olda ^ newb) << 24;
   double acc = 0.0;
-  for (int r = r0 + g; r < r1; r += G) {
-    const uint2 rec = __ldg(m.site_rec + r);
-    const uint32_t c = rec.y >> 16;
-    const uint4 ci = t.cls[c];
-    const int o0 = occ[rec.x & 0xffffu], o1 = occ[rec.x >> 16], o2 = occ[rec.y & 0xffffu];
-    const int base = (int)(ci.x & 0xffffu) * o0 + (int)(ci.x >> 16) * o1 + (int)(ci.y & 0xffffu) * o2 + (int)ci.z;
-    const int self = (int)(ci.y >> 16);
-    const int ii = base + olda * self, ff = base + newb * self;
-    const double d = t.tabA[ff] - t.tabA[ii];
-    if (KONE) {
-      acc += t.coef[c] * d;
-      reinterpret_cast<double*>(stash)[r - r0] = d;
-    } else {
-      acc += d;
-      reinterpret_cast<uint32_t*>(stash)[r - r0] = (uint32_t)(ff - (int)ci.z) | ((uint32_t)(ii - (int)ci.z) << 16);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = g + u * G;
+    if (r < m.Rstride) eval_record<KONE>(t, occ, pre.r[u], oldsh, xmask, stash, r, acc);
+  }
+  if (m.Rstride > 4 * G) {
+    const uint2* rp = m.site_rec + (size_t)site * m.Rstride;
+    for (int base = 4 * G; base < m.Rstride; base += 4 * G) {
+      uint2 rec[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = base + g + u * G;
+        rec[u] = r < m.Rstride ? __ldg(rp + r) : make_uint2(0u, (uint32_t)m.nCls << 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = base + g + u * G;
+        if (r < m.Rstride) eval_record<KONE>(t, occ, rec[u], oldsh, xmask, stash, r, acc);
+      }
     }
   }
   return acc;
@@ -130,29 +169,26 @@ __device__ __forceinline__ double flip_ewald(const DevModel& m, const uint8_t* o
   return acc;
 }
 
-// k-th active site (in Sublattice.active_sites order) of sublattice `sl` whose code is != `code`
-// (ne) or == `code` (!ne).  Group-cooperative rank select: per-lane chunk counts, prefix, locate.
+// Position (in Sublattice.active_sites order) of the k-th active site of sublattice `sl` whose
+// code is != `code` (ne) or == `code` (!ne).  The walker keeps one bit-plane per species code
+// (bit j of plane[code] <=> active site j holds `code`); lanes popcount contiguous word chunks,
+// a group prefix sum locates the owning lane, a 5-step binary search locates the bit.
 // Restates `rng.choice(active_sites[occu[active_sites] != species1])` (mcusher.py:189-196) and the
 // species_list picks of TableFlip (mcusher.py:620-637).
 template <int G>
-__device__ __forceinline__ int select_site(const DevModel& m, const uint8_t* occ, int sl, int code, int k, bool ne,
-                                           int g, uint32_t mask) {
-  const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
-  const int first = m.sl_first[sl];
-  int chunk = (n_act + G - 1) / G;
-  const bool words = first >= 0 && (first & 3) == 0 && (n_act % (4 * G)) == 0;
+__device__ __forceinline__ int select_pos(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
+                                          int g, uint32_t mask) {
+  const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+  const int nw = m.sl_nwords[sl];
+  const uint32_t* pl = planes + m.sl_plane_off[sl] + code * nw;
+  const int cw = (nw + G - 1) / G;
+  const int lo = g * cw, hi = min(lo + cw, nw);
   int cnt = 0;
-  const int lo = g * chunk, hi = min(lo + chunk, n_act);
-  if (words) {
-    const uint32_t pat = (uint32_t)code * 0x01010101u;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(occ + first + lo);
-    for (int j = 0; j < chunk / 4; ++j) cnt += __popc(__vcmpeq4(w[j], pat)) >> 3;
-    if (ne) cnt = chunk - cnt;
-  } else {
-    for (int j = lo; j < hi; ++j) {
-      const int s = first >= 0 ? first + j : __ldg(m.sl_sites + off + j);
-      cnt += ne ? (occ[s] != code) : (occ[s] == code);
-    }
+  const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
+  for (int wd = lo; wd < hi; ++wd) {
+    uint32_t b = pl[wd];
+    if (ne) b = ~b & (wd == nw - 1 ? tail : 0xffffffffu);
+    cnt += __popc(b);
   }
   int incl = cnt;
 #pragma unroll
@@ -165,13 +201,25 @@ __device__ __forceinline__ int select_site(const DevModel& m, const uint8_t* occ
   int res = -1;
   if (found) {
     int rem = k - excl;
-    for (int j = lo; j < hi; ++j) {
-      const int s = first >= 0 ? first + j : __ldg(m.sl_sites + off + j);
-      const bool hit = ne ? (occ[s] != code) : (occ[s] == code);
-      if (hit) {
-        if (rem == 0) { res = s; break; }
-        --rem;
+    for (int wd = lo; wd < hi; ++wd) {
+      uint32_t b = pl[wd];
+      if (ne) b = ~b & (wd == nw - 1 ? tail : 0xffffffffu);
+      const int c = __popc(b);
+      if (rem < c) {
+        int pos = 0;
+        int c16 = __popc(b & 0xffffu);
+        if (rem >= c16) { rem -= c16; pos += 16; b >>= 16; }
+        int c8 = __popc(b & 0xffu);
+        if (rem >= c8) { rem -= c8; pos += 8; b >>= 8; }
+        int c4 = __popc(b & 0xfu);
+        if (rem >= c4) { rem -= c4; pos += 4; b >>= 4; }
+        int c2 = __popc(b & 0x3u);
+        if (rem >= c2) { rem -= c2; pos += 2; b >>= 2; }
+        if (rem >= (int)(b & 1u)) pos += 1;
+        res = wd * 32 + pos;
+        break;
       }
+      rem -= c;
     }
   }
   if (G > 1) {
@@ -180,6 +228,24 @@ __device__ __forceinline__ int select_site(const DevModel& m, const uint8_t* occ
     res = __shfl_sync(mask, res, src);
   }
   return res;
+}
+
+__device__ __forceinline__ int site_of_pos(const DevModel& m, int sl, int pos) {
+  return m.sl_first[sl] >= 0 ? m.sl_first[sl] + pos : __ldg(m.sl_sites + m.sl_off[sl] + pos);
+}
+
+// Metropolis test `exponent >= 0 or exponent > log(u)` (kernel/metropolis.py:46-48).  A float
+// logarithm with a guard band decides almost every case; inside the band the exact double log is
+// evaluated, so the decision is always the one of the double-precision test.
+__device__ __forceinline__ bool accept_test(double exponent, uint32_t r) {
+  if (exponent >= 0.0) return true;
+  const double u = u01(r);
+  const float lf = __logf((float)u);
+  const float ex = (float)exponent;
+  const float eps = 1e-5f * (1.0f + fabsf(lf)) + 1e-6f * fabsf(ex);
+  if (ex < lf - eps) return false;
+  if (ex > lf + eps) return true;
+  return exponent > log(u);
 }
 
 __device__ __forceinline__ int choose_sublattice(const DevModel& m, uint32_t r0) {
@@ -208,14 +274,14 @@ __device__ __forceinline__ double tf_masked_weights(const DevModel& m, const int
 
 struct Step {
   int n;                       // number of flips (0 = empty step)
-  int site[LMC_MAX_FLIPS], oldc[LMC_MAX_FLIPS], newc[LMC_MAX_FLIPS], sl[LMC_MAX_FLIPS];
+  int site[LMC_MAX_FLIPS], oldc[LMC_MAX_FLIPS], newc[LMC_MAX_FLIPS], sl[LMC_MAX_FLIPS], pos[LMC_MAX_FLIPS];
   double log_priori;
 };
 // append without dynamic indexing (keeps the arrays in registers)
-__device__ __forceinline__ void push_flip(Step& st, int site, int oldc, int newc, int sl) {
+__device__ __forceinline__ void push_flip(Step& st, int site, int oldc, int newc, int sl, int pos) {
 #pragma unroll
   for (int i = 0; i < LMC_MAX_FLIPS; ++i)
-    if (i == st.n) { st.site[i] = site; st.oldc[i] = oldc; st.newc[i] = newc; st.sl[i] = sl; }
+    if (i == st.n) { st.site[i] = site; st.oldc[i] = oldc; st.newc[i] = newc; st.sl[i] = sl; st.pos[i] = pos; }
   if (st.n < LMC_MAX_FLIPS) ++st.n;
 }
 
@@ -236,7 +302,7 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // the fused MC kernel: propose -> delta features/energy (+Ewald, +mu) -> accept -> update,
 // num_samples * thin_by attempted steps per walker in ONE launch.
 // ------------------------------------------------------------------------------------------
-template <int G, bool KONE, bool EWALD, int USHER>
+template <int G, bool KONE, bool EWALD, int USHER, bool WLMODE>
 __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -258,32 +324,38 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
   double* feat = reinterpret_cast<double*>(priv + a.off_feat);
   unsigned char* stash0 = priv + a.off_stash;
   int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
   (void)wslab;
 
   stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
   const SmemTables t = smem_tables(m, smem);
   if (!active) return;
 
-  const int stash_stride = m.Rmax * (KONE ? 8 : 4);
+  const int stash_stride = m.Rstride * (KONE ? 8 : 4);
   // running state
   for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
   double enth = a.enthalpy[w];
-  // species counts per (active sublattice, code)
+  // species counts per (active sublattice, code) and one bit-plane per code
   for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
+  for (int i = g; i < m.plane_words; i += G) planes[i] = 0u;
   group_sync<G>(gmask);
-  if (g == 0) {
-    for (int s = 0; s < m.nSl; ++s)
-      for (int j = m.sl_off[s]; j < m.sl_off[s + 1]; ++j) {
-        const int site = m.sl_first[s] >= 0 ? m.sl_first[s] + (j - m.sl_off[s]) : m.sl_sites[j];
-        cnt[s * LMC_MAX_CODES + occ[site]]++;
+  for (int sl = 0; sl < m.nSl; ++sl) {
+    const int n_act = m.sl_off[sl + 1] - m.sl_off[sl], nw = m.sl_nwords[sl];
+    for (int wd = g; wd < nw; wd += G) {
+      const int jn = min(32, n_act - 32 * wd);
+      for (int b = 0; b < jn; ++b) {
+        const int code = occ[site_of_pos(m, sl, wd * 32 + b)];
+        planes[m.sl_plane_off[sl] + code * nw + wd] |= 1u << b;
+        atomicAdd(&cnt[sl * LMC_MAX_CODES + code], 1);
       }
+    }
   }
   group_sync<G>(gmask);
 
   const unsigned long long seed = a.seeds[w];
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint32_t wid = (uint32_t)(a.walker_base + w);
-  const bool wl_mode = a.kernel == LMC_KERNEL_WANGLANDAU;
+  constexpr bool wl_mode = WLMODE;
   const double beta = wl_mode ? 0.0 : a.beta[w];
   const double nat_ew = EWALD ? t.nat[m.ewF] : 0.0;
   const double nat_mu = m.muW ? t.nat[m.muF] : 0.0;
@@ -311,7 +383,7 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
       st.n = 0;
       st.log_priori = 0.0;
 #pragma unroll
-      for (int i = 0; i < LMC_MAX_FLIPS; ++i) { st.site[i] = 0; st.oldc[i] = 0; st.newc[i] = 0; st.sl[i] = 0; }
+      for (int i = 0; i < LMC_MAX_FLIPS; ++i) { st.site[i] = 0; st.oldc[i] = 0; st.newc[i] = 0; st.sl[i] = 0; st.pos[i] = 0; }
 
       // ------------------------------ propose ------------------------------------------
       int usher = USHER;
@@ -351,29 +423,30 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
         const int sl = choose_sublattice(m, q0);
         const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
         const int j = (int)mulhi32(q1, (uint32_t)n_act);
-        const int site = m.sl_first[sl] >= 0 ? m.sl_first[sl] + j : __ldg(m.sl_sites + off + j);
+        const int site = site_of_pos(m, sl, j);
         const int cur = occ[site];
         const int nc = m.sl_ncodes[sl];
         int ci = (int)mulhi32(q2, (uint32_t)(nc - 1));
         int pos = nc;
         for (int c = 0; c < nc; ++c) if (m.sl_codes[sl][c] == cur) { pos = c; break; }
         if (ci >= pos) ++ci;
-        st.n = 1; st.site[0] = site; st.oldc[0] = cur; st.newc[0] = m.sl_codes[sl][ci]; st.sl[0] = sl;
+        st.n = 1; st.site[0] = site; st.oldc[0] = cur; st.newc[0] = m.sl_codes[sl][ci]; st.sl[0] = sl; st.pos[0] = j;
       } else if (USHER == LMC_USHER_SWAP || usher == LMC_USHER_SWAP) {
         // Swap.propose_step, mcusher.py:176-200
         const int sl = choose_sublattice(m, q0);
         const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
         const int j = (int)mulhi32(q1, (uint32_t)n_act);
-        const int site1 = m.sl_first[sl] >= 0 ? m.sl_first[sl] + j : __ldg(m.sl_sites + off + j);
+        const int site1 = site_of_pos(m, sl, j);
         const int s1 = occ[site1];
         const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
         if (ndiff > 0) {
           const int k = (int)mulhi32(q2, (uint32_t)ndiff);
-          const int site2 = select_site<G>(m, occ, sl, s1, k, true, g, gmask);
+          const int p2 = select_pos<G>(m, planes, sl, s1, k, true, g, gmask);
+          const int site2 = site_of_pos(m, sl, p2);
           const int s2 = occ[site2];
           st.n = 2;
-          st.site[0] = site1; st.oldc[0] = s1; st.newc[0] = s2; st.sl[0] = sl;
-          st.site[1] = site2; st.oldc[1] = s2; st.newc[1] = s1; st.sl[1] = sl;
+          st.site[0] = site1; st.oldc[0] = s1; st.newc[0] = s2; st.sl[0] = sl; st.pos[0] = j;
+          st.site[1] = site2; st.oldc[1] = s2; st.newc[1] = s1; st.sl[1] = sl; st.pos[1] = p2;
         }
       } else if (USHER == LMC_USHER_TABLEFLIP) {
         // table flip: sequential picks, one random word each (words 4.. of the step)
@@ -396,7 +469,7 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
           int d1 = d0 + 1;
           while (d1 < m.tfD && m.tf_dim_sl[d1] == sl) ++d1;
           if (sl >= 0) {
-            int pool[LMC_MAX_FLIPS];
+            int pool[LMC_MAX_FLIPS], ppos[LMC_MAX_FLIPS];
             int npool = 0;
             for (int d = d0; d < d1; ++d) {
               const int ud = sgn * urow[d];
@@ -410,8 +483,8 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
                 int q = nr;
                 while (q > 0 && ranks[q - 1] > idx) { ranks[q] = ranks[q - 1]; --q; }
                 ranks[q] = idx; ++nr;
-                const int site = select_site<G>(m, occ, sl, m.tf_dim_code[d], idx, false, g, gmask);
-                if (npool < LMC_MAX_FLIPS) pool[npool++] = site;
+                const int pp = select_pos<G>(m, planes, sl, m.tf_dim_code[d], idx, false, g, gmask);
+                if (npool < LMC_MAX_FLIPS) { pool[npool] = site_of_pos(m, sl, pp); ppos[npool] = pp; ++npool; }
               }
             }
             for (int d = d0; d < d1; ++d) {
@@ -419,10 +492,10 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
               if (ud <= 0) continue;
               for (int p = 0; p < ud; ++p) {
                 const int idx = (int)mulhi32(next_word(), (uint32_t)npool);
-                const int site = pool[idx];
-                for (int q = idx; q + 1 < npool; ++q) pool[q] = pool[q + 1];
+                const int site = pool[idx], pp = ppos[idx];
+                for (int q = idx; q + 1 < npool; ++q) { pool[q] = pool[q + 1]; ppos[q] = ppos[q + 1]; }
                 --npool;
-                push_flip(st, site, occ[site], m.tf_dim_code[d], sl);
+                push_flip(st, site, occ[site], m.tf_dim_code[d], sl, pp);
               }
             }
           }
@@ -443,10 +516,17 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
 
       // ------------------------------ evaluate ------------------------------------------
       double acc = 0.0, acc_ew = 0.0, dmu = 0.0;
+      // the cluster records depend on the sites only: fetch the first two flips' records up front so
+      // that their L2 latency overlaps (swap = 2 flips)
+      RecChunk pre0, pre1;
+      if (st.n > 0) pre0 = load_records<G>(m, st.site[0], g);
+      if (st.n > 1) pre1 = load_records<G>(m, st.site[1], g);
 #pragma unroll
       for (int f = 0; f < LMC_MAX_FLIPS; ++f) {
         if (f < st.n) {
-          acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g);
+          if (f >= 2) pre0 = load_records<G>(m, st.site[f], g);
+          acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g,
+                                      f == 1 ? pre1 : pre0);
           if (EWALD) acc_ew += flip_ewald<G>(m, occ, st.site[f], st.oldc[f], st.newc[f], g);
           if (m.muW)
             dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
@@ -464,7 +544,7 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
       if (!wl_mode) {
         // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
         const double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
-        accepted = exponent >= 0.0 ? true : exponent > log(u01(r.w));
+        accepted = accept_test(exponent, r.w);
       } else {
         // WangLandau._accept_step, kernel/wanglandau.py:186-202
         const double e_new = enth + dH;
@@ -476,7 +556,7 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
           const double s_old = (bin >= 0 && bin < nb) ? __ldcg(wlS + bin) : 0.0;
           const double s_new = (new_bin >= 0 && new_bin < nb) ? __ldcg(wlS + new_bin) : 0.0;
           const double exponent = (s_old - s_new) + st.log_priori;
-          accepted = exponent >= 0.0 ? true : exponent > log(u01(r.w));
+          accepted = accept_test(exponent, r.w);
         }
       }
 
@@ -494,6 +574,11 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
             if (f < st.n) {
               cnt[st.sl[f] * LMC_MAX_CODES + st.oldc[f]]--;
               cnt[st.sl[f] * LMC_MAX_CODES + st.newc[f]]++;
+              const int nw = m.sl_nwords[st.sl[f]];
+              uint32_t* pl = planes + m.sl_plane_off[st.sl[f]] + (st.pos[f] >> 5);
+              const uint32_t bit = 1u << (st.pos[f] & 31);
+              pl[st.oldc[f] * nw] ^= bit;
+              pl[st.newc[f] * nw] ^= bit;
             }
         }
         enth += dH;
@@ -612,7 +697,7 @@ __global__ void lmc_delta_kernel(const DevModel m, const int8_t* __restrict__ oc
     const int oldc = occ[site];
     // chemical work against the PRE-step occupancy (ensemble.py:369-373)
     if (m.muW) dmu += m.mu[site * m.muW + newc] - m.mu[site * m.muW + (int)occ_g[(size_t)w * m.Npad + site]];
-    (void)flip_energy<G, KONE>(m, t, occ, site, oldc, newc, stash, g);
+    (void)flip_energy<G, KONE>(m, t, occ, site, oldc, newc, stash, g, load_records<G>(m, site, g));
     if (m.E) dew += flip_ewald<G>(m, occ, site, oldc, newc, g);
     group_sync<G>(gmask);
     flip_features<G, KONE>(m, t, site, stash, feat, g);

@@ -18,7 +18,7 @@ struct OrbDev {
 
 struct DevModel {
   int N, Npad, F, Fce, nOrb, nCls, nSl, size, kone;
-  int Rmax;        // max local records of a site
+  int Rstride;     // records per site in the padded table (multiple of 4; pads use class nCls)
   int tabA_len;    // doubles in the phase-A table
   double feature0;
   // shared-memory blob (staged once per block by TMA): [cls uint4 x nCls][coef double x nCls]
@@ -26,8 +26,7 @@ struct DevModel {
   const unsigned char* blob;
   int blob_bytes, off_coef, off_tabA, off_nat, off_orb;
   const double* ftab;      // global copy of all feature tensors (phase B when K > 1, full evaluation)
-  const uint2* site_rec;   // [records] (idx0 | idx1<<16, idx2 | cls<<16)
-  const int* site_rec_off; // [N+1]
+  const uint2* site_rec;   // [N][Rstride] (idx0 | idx1<<16, idx2 | cls<<16), padded per site
   const int4* site_seg;    // [segments] (first, count, orbit, 0)
   const int* site_seg_off; // [N+1]
   const uint2* full_rows;  // [rows] 4 x u16 site indices
@@ -44,6 +43,9 @@ struct DevModel {
   int sl_codes[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];
   int sl_first[LMC_MAX_SUBLATTICES];   // first site if the active sites are one contiguous range, else -1
   double sl_cum[LMC_MAX_SUBLATTICES];  // cumulative proposal probabilities
+  int sl_nwords[LMC_MAX_SUBLATTICES];  // 32-bit words of one species bit-plane (ceil(n_active/32))
+  int sl_plane_off[LMC_MAX_SUBLATTICES];  // word offset of the sublattice's planes [code][word]
+  int plane_words;                     // total words of all planes of one walker
   const int* sl_sites;
   // table flips
   int tfD, tfNF;
@@ -73,7 +75,8 @@ struct RunArgs {
   LmcWangLandau wl;
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
-  int off_feat, off_stash, off_cnt;  // offsets inside a walker's shared-memory slab
+  int off_feat, off_stash, off_cnt, off_plane;  // offsets inside a walker's shared-memory slab
+  int max_flips;      // flips per step of the selected usher (stash slots)
 };
 
 }  // namespace lmc

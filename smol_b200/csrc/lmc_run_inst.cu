@@ -2,8 +2,8 @@
 #include "lmc_kernels.cuh"
 #include "lmc_launch.h"
 
-#ifndef LMC_G
-#error "compile with -DLMC_G=<group size>"
+#if !defined(LMC_G) || !defined(LMC_WL)
+#error "compile with -DLMC_G=<group size> -DLMC_WL=<0|1>"
 #endif
 #define LMC_CAT2(a, b) a##b
 #define LMC_CAT(a, b) LMC_CAT2(a, b)
@@ -12,7 +12,7 @@ namespace lmc {
 
 template <bool KONE, bool EWALD, int USHER>
 static int launch_one(const DevModel& m, const RunArgs& a, const LaunchCfg& lc) {
-  auto kern = lmc_run_kernel<LMC_G, KONE, EWALD, USHER>;
+  auto kern = lmc_run_kernel<LMC_G, KONE, EWALD, USHER, (LMC_WL != 0)>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<lc.grid, lc.threads, lc.smem, lc.stream>>>(m, a);
@@ -31,7 +31,12 @@ static int launch_usher(const DevModel& m, const RunArgs& a, int usher, const La
   }
 }
 
-int LMC_CAT(launch_run_g, LMC_G)(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher,
+#if LMC_WL
+#define LMC_FN LMC_CAT(launch_run_wl_g, LMC_G)
+#else
+#define LMC_FN LMC_CAT(launch_run_g, LMC_G)
+#endif
+int LMC_FN(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher,
                                  const LaunchCfg& lc) {
   if (kone) return ewald ? launch_usher<true, true>(m, a, usher, lc) : launch_usher<true, false>(m, a, usher, lc);
   return ewald ? launch_usher<false, true>(m, a, usher, lc) : launch_usher<false, false>(m, a, usher, lc);

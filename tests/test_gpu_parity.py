@@ -158,3 +158,79 @@ def test_semigrand_ewald_flip_trajectory(cuda_device):
     seeds = np.arange(7, 7 + W)
     smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 300, 10, occ0, seeds, T=1500.0)
     _compare_traces(smp, ref)
+
+
+def test_wang_landau_flip_trajectory(cuda_device):
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 3
+    coefs = M.fcc_coefs(sub, seed=7)
+    it = L.cluster_interaction_tensors(sub, coefs)
+    gpu_p = S.ClusterDecompositionProcessor(sub, scm, it)
+    ora_p = O.ClusterDecompositionProcessor(sub, scm, it)
+    ens_g = S.Ensemble(gpu_p)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices))
+
+    W = 5
+    occ0 = M.random_occupancies(sub, scm, W, seed=4)
+    e0 = np.array([ora_p.compute_property(o) for o in occ0])
+    lo, hi = e0.min() - 2.0, e0.max() + 2.0
+    wl = dict(min=lo, max=hi, bin=(hi - lo) / 37.3, check=50, flatness=0.3)
+    seeds = np.arange(40, 40 + W)
+    smp, ref, kernels = _run_both(ens_g, ens_o, "flip", W, 1500, 50, occ0, seeds, wl=wl)
+    _compare_traces(smp, ref)
+    st = smp.wang_landau_state
+    for w, k in enumerate(kernels):
+        np.testing.assert_array_equal(st["histogram"][w], k._histogram)
+        np.testing.assert_array_equal(st["occurrences"][w], k._occurrences)
+        np.testing.assert_allclose(st["entropy"][w], k._entropy, rtol=1e-13, atol=0)
+        assert st["mod_factor"][w] == k._m
+        np.testing.assert_allclose(st["mean_features"][w], k._mean_features, rtol=RTOL,
+                                   atol=RTOL * np.abs(k._mean_features).max())
+    assert (st["mod_factor"] < 1.0).any(), "flatness was never reached; weak test"
+
+
+@pytest.mark.parametrize("group", [8, 32])
+def test_table_flip_ewald_semigrand_trajectory(cuda_device, group):
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * 3
+    rng = np.random.default_rng(21)
+    coefs = rng.normal(0, 0.03, sub.num_corr_functions)
+    it = L.cluster_interaction_tensors(sub, coefs)
+    ewm, ewi = L.ewald_matrix(sub, scm)
+    comp = S.CompositeProcessor(sub, scm)
+    comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
+    comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.05, ewald_matrix=ewm, ewald_inds=ewi))
+    mus = {"Li+": 0.0, "Mn3+": 0.4, "Ti4+": -0.3, "O2-": 0.1, "F-": 0.0}
+    ens_g = S.Ensemble(comp, chemical_potentials=mus)
+    ora_p = O.CompositeProcessor([O.ClusterDecompositionProcessor(sub, scm, it),
+                                  O.EwaldProcessor(ewm, ewi, 0.05)])
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices), chemical_potentials=mus)
+
+    table = [[-1, 1, 0, 2, -2], [0, -1, 1, 1, -1]]
+    W, ncell = 3, 27
+    occ0 = np.zeros((W, 2 * ncell), dtype=np.int32)
+    for w in range(W):
+        cat = np.array([0] * 20 + [1] * 4 + [2] * 3)   # 20 Li+, 4 Mn3+, 3 Ti4+  (+44)
+        ani = np.array([0] * 17 + [1] * 10)            # 17 O2-, 10 F-          (-44)
+        occ0[w, :ncell] = rng.permutation(cat)
+        occ0[w, ncell:] = rng.permutation(ani)
+    seeds = np.arange(900, 900 + W)
+    smp, ref, _ = _run_both(ens_g, ens_o, "table_flip", W, 400, 20, occ0, seeds, T=2000.0,
+                            usher_kwargs=dict(flip_table=table, swap_weight=0.2), group_size=group)
+    _compare_traces(smp, ref)
+    # charge neutrality is conserved by construction of the table
+    occ = smp.samples.get_occupancies(flat=True)
+    q_cat = np.array([1, 3, 4])[occ[:, :ncell]].sum(axis=1)
+    q_ani = np.array([-2, -1])[occ[:, ncell:]].sum(axis=1)
+    assert np.all(q_cat + q_ani == 0)
+    assert smp.samples.step_efficiency() > 0
