@@ -19,7 +19,7 @@ def main():
     occ0 = M.random_occupancies(sub, scm, W, seed=0, balanced=True)
     N = occ0.shape[1]
     for G in [int(x) for x in os.environ.get("GS", "4,8,16,32").split(",")]:
-        for bt in [int(x) for x in os.environ.get("BTS", "128,256").split(",")]:
+        for bt in [int(x) for x in os.environ.get("BTS", "128").split(",")]:
             smp = S.Sampler.from_ensemble(ens, 1000.0, step_type="swap", nwalkers=W, seeds=list(range(W)),
                                           group_size=G, block_threads=bt)
             smp.run(N * 2, occ0, thin_by=N)
@@ -29,6 +29,7 @@ def main():
             t0.record(); smp.run(N * sweeps, thin_by=N); t1.record(); torch.cuda.synchronize()
             ms = t0.elapsed_time(t1)
             acc = smp.samples.step_efficiency()
-            print(f"G={G:2d} threads={bt:4d} W={W} N={N}: {W*N*sweeps/ms*1e3:.3e} steps/s  ({ms:.1f} ms, acc={acc:.3f})", flush=True)
+            kms = smp.last_kernel_ms
+            print(f"G={G:2d} threads={bt:4d} W={W} N={N}: kernel {W*N*sweeps/kms*1e3:.3e} steps/s ({kms:.1f} ms) | run() {W*N*sweeps/ms*1e3:.3e} ({ms:.1f} ms) acc={acc:.3f}", flush=True)
 
 main()

@@ -332,7 +332,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   int threads = c->block_threads;
   if (const char* e = getenv("LMC_BLOCK_THREADS")) { if (threads == 0) threads = atoi(e); }
   if (threads == 0) threads = 128;
-  if (threads % 32 || threads > 1024) return fail("block_threads must be a multiple of 32");
+  if (threads % 32 || threads > 128) return fail("block_threads must be 32, 64, 96 or 128");
 
   RunArgs a;
   memset(&a, 0, sizeof(a));
@@ -357,6 +357,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
       for (int k = 0; k < m.tfD; ++k) { up += std::max(m.tf_table[i][k], 0); dn += std::max(-m.tf_table[i][k], 0); }
       a.max_flips = std::max(a.max_flips, std::max(up, dn));
     }
+  if (const char* e = getenv("LMC_SEQUENTIAL_FLIPS")) a.seq_flips = atoi(e);
   if (a.max_flips > LMC_MAX_FLIPS) return fail("flip table changes more than 4 sites per step");
   a.off_cnt = a.off_stash + (int)(((size_t)a.max_flips * m.Rstride * stash_el + 15) & ~size_t(15));
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;

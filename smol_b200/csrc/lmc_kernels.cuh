@@ -83,34 +83,97 @@ __device__ __forceinline__ void eval_record(const SmemTables& t, const uint8_t* 
   }
 }
 
+// NU records of ONE flip per lane, fully unrolled (no per-record branches: the record table is
+// padded to a multiple of the group size with zero-class records)
+template <int G, bool KONE, int NU>
+__device__ __forceinline__ void eval_chunk1(const SmemTables& t, const uint8_t* occ, const uint2* rec, uint32_t oldsh,
+                                            uint32_t xmask, void* stash, int r0, double& acc) {
+#pragma unroll
+  for (int u = 0; u < NU; ++u) eval_record<KONE>(t, occ, rec[u], oldsh, xmask, stash, r0 + u * G, acc);
+}
+// the same for TWO flips interleaved (independent dependency chains -> twice the ILP)
+template <int G, bool KONE, int NU>
+__device__ __forceinline__ void eval_chunk2(const SmemTables& t, const uint8_t* occ, const uint2* ra, const uint2* rb,
+                                            uint32_t sha, uint32_t xa, uint32_t shb, uint32_t xb, void* stasha,
+                                            void* stashb, int r0, double& acca, double& accb) {
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    eval_record<KONE>(t, occ, ra[u], sha, xa, stasha, r0 + u * G, acca);
+    eval_record<KONE>(t, occ, rb[u], shb, xb, stashb, r0 + u * G, accb);
+  }
+}
+
+template <int G>
+__device__ __forceinline__ void load_chunk(const DevModel& m, const uint2* rp, int r0, uint2* rec) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = r0 + u * G;
+    rec[u] = r < m.Rstride ? __ldg(rp + r) : make_uint2(0u, (uint32_t)m.nCls << 16);
+  }
+}
+
+template <int G, bool KONE>
+__device__ __forceinline__ void eval_n1(int nu, const SmemTables& t, const uint8_t* occ, const uint2* rec, uint32_t oldsh,
+                                        uint32_t xmask, void* stash, int r0, double& acc) {
+  switch (nu) {   // warp-uniform
+    case 1: eval_chunk1<G, KONE, 1>(t, occ, rec, oldsh, xmask, stash, r0, acc); break;
+    case 2: eval_chunk1<G, KONE, 2>(t, occ, rec, oldsh, xmask, stash, r0, acc); break;
+    case 3: eval_chunk1<G, KONE, 3>(t, occ, rec, oldsh, xmask, stash, r0, acc); break;
+    default: eval_chunk1<G, KONE, 4>(t, occ, rec, oldsh, xmask, stash, r0, acc); break;
+  }
+}
+template <int G, bool KONE>
+__device__ __forceinline__ void eval_n2(int nu, const SmemTables& t, const uint8_t* occ, const uint2* ra, const uint2* rb,
+                                        uint32_t sha, uint32_t xa, uint32_t shb, uint32_t xb, void* stasha, void* stashb,
+                                        int r0, double& acca, double& accb) {
+  switch (nu) {
+    case 1: eval_chunk2<G, KONE, 1>(t, occ, ra, rb, sha, xa, shb, xb, stasha, stashb, r0, acca, accb); break;
+    case 2: eval_chunk2<G, KONE, 2>(t, occ, ra, rb, sha, xa, shb, xb, stasha, stashb, r0, acca, accb); break;
+    case 3: eval_chunk2<G, KONE, 3>(t, occ, ra, rb, sha, xa, shb, xb, stasha, stashb, r0, acca, accb); break;
+    default: eval_chunk2<G, KONE, 4>(t, occ, ra, rb, sha, xa, shb, xb, stasha, stashb, r0, acca, accb); break;
+  }
+}
+
+// energy change of one flip; `pre` holds the lane's first four records
 template <int G, bool KONE>
 __device__ __forceinline__ double flip_energy(const DevModel& m, const SmemTables& t, const uint8_t* occ, int site,
                                               int olda, int newb, void* stash, int g, const RecChunk& pre) {
   const uint32_t oldsh = (uint32_t)olda << 24;
   const uint32_t xmask = (uint32_t)(olda ^ newb) << 24;
+  const int nper = m.Rstride / G;   // records per lane (uniform: Rstride is a multiple of 32)
   double acc = 0.0;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int r = g + u * G;
-    if (r < m.Rstride) eval_record<KONE>(t, occ, pre.r[u], oldsh, xmask, stash, r, acc);
-  }
-  if (m.Rstride > 4 * G) {
-    const uint2* rp = m.site_rec + (size_t)site * m.Rstride;
-    for (int base = 4 * G; base < m.Rstride; base += 4 * G) {
-      uint2 rec[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = base + g + u * G;
-        rec[u] = r < m.Rstride ? __ldg(rp + r) : make_uint2(0u, (uint32_t)m.nCls << 16);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = base + g + u * G;
-        if (r < m.Rstride) eval_record<KONE>(t, occ, rec[u], oldsh, xmask, stash, r, acc);
-      }
-    }
+  eval_n1<G, KONE>(min(nper, 4), t, occ, pre.r, oldsh, xmask, stash, g, acc);
+  const uint2* rp = m.site_rec + (size_t)site * m.Rstride;
+  for (int base = 4; base < nper; base += 4) {
+    uint2 rec[4];
+    load_chunk<G>(m, rp, g + base * G, rec);
+    eval_n1<G, KONE>(min(nper - base, 4), t, occ, rec, oldsh, xmask, stash, g + base * G, acc);
   }
   return acc;
+}
+
+// energy change of a two-flip step (swap).  The caller has already written flip a's new code to
+// the occupancy: flip a's records never contain its own site, flip b's records must see flip a
+// applied (sequential semantics of expansion.py:217-229), so both can be evaluated interleaved.
+template <int G, bool KONE>
+__device__ __forceinline__ double flip_energy_pair(const DevModel& m, const SmemTables& t, const uint8_t* occ,
+                                                   int sitea, int olda, int newa, int siteb, int oldb, int newb,
+                                                   void* stasha, void* stashb, int g, const RecChunk& prea,
+                                                   const RecChunk& preb) {
+  const uint32_t sha = (uint32_t)olda << 24, xa = (uint32_t)(olda ^ newa) << 24;
+  const uint32_t shb = (uint32_t)oldb << 24, xb = (uint32_t)(oldb ^ newb) << 24;
+  const int nper = m.Rstride / G;
+  double acca = 0.0, accb = 0.0;
+  eval_n2<G, KONE>(min(nper, 4), t, occ, prea.r, preb.r, sha, xa, shb, xb, stasha, stashb, g, acca, accb);
+  const uint2* rpa = m.site_rec + (size_t)sitea * m.Rstride;
+  const uint2* rpb = m.site_rec + (size_t)siteb * m.Rstride;
+  for (int base = 4; base < nper; base += 4) {
+    uint2 ra[4], rb[4];
+    load_chunk<G>(m, rpa, g + base * G, ra);
+    load_chunk<G>(m, rpb, g + base * G, rb);
+    eval_n2<G, KONE>(min(nper - base, 4), t, occ, ra, rb, sha, xa, shb, xb, stasha, stashb, g + base * G, acca, accb);
+  }
+  return acca + accb;
 }
 
 // phase B: fold the stashed per-record differences of an ACCEPTED flip into the running feature
@@ -181,6 +244,38 @@ __device__ __forceinline__ int select_pos(const DevModel& m, const uint32_t* pla
   const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
   const int nw = m.sl_nwords[sl];
   const uint32_t* pl = planes + m.sl_plane_off[sl] + code * nw;
+  if (G > 1 && nw <= G) {
+    // one word per lane: prefix over the popcounts, then every lane tests bits of the owning word
+    const uint32_t tl = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
+    uint32_t b = 0u;
+    if (g < nw) {
+      b = pl[g];
+      if (ne) b = ~b & (g == nw - 1 ? tl : 0xffffffffu);
+    }
+    const int c = __popc(b);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      const int tt = __shfl_up_sync(mask, incl, o, G);
+      if (g >= o) incl += tt;
+    }
+    const int excl = incl - c;
+    const uint32_t own = __ballot_sync(mask, (k >= excl) && (k < incl));
+    const int src = own ? (__ffs(own) - 1) : (int)(threadIdx.x & 31);
+    const uint32_t word = __shfl_sync(mask, b, src);
+    const int rem = k - __shfl_sync(mask, excl, src);
+    const int wd = src & (G - 1);
+    int hit = -1;
+#pragma unroll
+    for (int bit = 0; bit < 32; bit += G) {
+      const int q = bit + g;
+      if (((word >> q) & 1u) && __popc(word & ((1u << q) - 1u)) == rem) hit = q;
+    }
+    const uint32_t hb = __ballot_sync(mask, hit >= 0);
+    const int hl = hb ? (__ffs(hb) - 1) : (int)(threadIdx.x & 31);
+    hit = __shfl_sync(mask, hit, hl);
+    return wd * 32 + hit;
+  }
   const int cw = (nw + G - 1) / G;
   const int lo = g * cw, hi = min(lo + cw, nw);
   int cnt = 0;
@@ -234,18 +329,19 @@ __device__ __forceinline__ int site_of_pos(const DevModel& m, int sl, int pos) {
   return m.sl_first[sl] >= 0 ? m.sl_first[sl] + pos : __ldg(m.sl_sites + m.sl_off[sl] + pos);
 }
 
-// Metropolis test `exponent >= 0 or exponent > log(u)` (kernel/metropolis.py:46-48).  A float
-// logarithm with a guard band decides almost every case; inside the band the exact double log is
-// evaluated, so the decision is always the one of the double-precision test.
-__device__ __forceinline__ bool accept_test(double exponent, uint32_t r) {
+// Metropolis test `exponent >= 0 or exponent > log(u)` (kernel/metropolis.py:46-48).  `lf` is a
+// float logarithm of u (computed ahead of time); with a guard band it decides almost every case,
+// inside the band the exact double log is evaluated, so the decision is always the one of the
+// double-precision test.
+__device__ __forceinline__ float log_u_float(uint32_t r) { return __logf((float)u01(r)); }
+
+__device__ __forceinline__ bool accept_test(double exponent, float lf, uint32_t r_exact) {
   if (exponent >= 0.0) return true;
-  const double u = u01(r);
-  const float lf = __logf((float)u);
   const float ex = (float)exponent;
   const float eps = 1e-5f * (1.0f + fabsf(lf)) + 1e-6f * fabsf(ex);
   if (ex < lf - eps) return false;
   if (ex > lf + eps) return true;
-  return exponent > log(u);
+  return exponent > log(u01(r_exact));
 }
 
 __device__ __forceinline__ int choose_sublattice(const DevModel& m, uint32_t r0) {
@@ -303,7 +399,8 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // num_samples * thin_by attempted steps per walker in ONE launch.
 // ------------------------------------------------------------------------------------------
 template <int G, bool KONE, bool EWALD, int USHER, bool WLMODE>
-__global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
+__global__ void __launch_bounds__(128, (EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 4 : 7)
+lmc_run_kernel(const DevModel m, const RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint64_t bar;
   const int g = threadIdx.x % G;
@@ -374,11 +471,43 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
   }
 
   unsigned long long step = a.step0;
+  // State-independent part of the next G steps, one step per lane (counter-based RNG): random
+  // words, sublattice, first site and the float log of the acceptance uniform.  Every step then
+  // costs a few shuffles instead of a redundant Philox evaluation in all lanes.
+  U4 bq{0, 0, 0, 0};
+  int b_slj = 0, b_site = 0;
+  float b_lf = 0.f;
+  int bphase = 0;
   for (long long s = 0; s < a.S; ++s) {
     int nacc = 0;
     bool accepted = true;
     for (int it = 0; it < a.thin; ++it, ++step) {
-      const U4 r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1);
+      U4 r;
+      float lf;
+      int pre_sl = 0, pre_j = 0, pre_site = 0;
+      if (USHER == LMC_USHER_TABLEFLIP) {
+        r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1);
+        lf = log_u_float(r.w);
+      } else {
+        if (bphase == 0) {
+          const unsigned long long st_ = step + (unsigned long long)g;
+          bq = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
+          const int sl_ = choose_sublattice(m, bq.x);
+          const int j_ = (int)mulhi32(bq.y, (uint32_t)(m.sl_off[sl_ + 1] - m.sl_off[sl_]));
+          b_slj = (sl_ << 24) | j_;
+          b_site = site_of_pos(m, sl_, j_);
+          b_lf = log_u_float(bq.w);
+        }
+        const int src = (int)((threadIdx.x & 31u) & ~(uint32_t)(G - 1)) + bphase;
+        const int slj = __shfl_sync(gmask, b_slj, src);
+        pre_sl = slj >> 24; pre_j = slj & 0xffffff;
+        pre_site = __shfl_sync(gmask, b_site, src);
+        r.x = 0u; r.y = 0u;
+        r.z = __shfl_sync(gmask, bq.z, src);
+        r.w = __shfl_sync(gmask, bq.w, src);
+        lf = __shfl_sync(gmask, b_lf, src);
+        bphase = (bphase + 1) & (G - 1);
+      }
       Step st;
       st.n = 0;
       st.log_priori = 0.0;
@@ -420,10 +549,7 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
       }
       if (USHER == LMC_USHER_FLIP) {
         // Flip.propose_step, mcusher.py:154-170
-        const int sl = choose_sublattice(m, q0);
-        const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
-        const int j = (int)mulhi32(q1, (uint32_t)n_act);
-        const int site = site_of_pos(m, sl, j);
+        const int sl = pre_sl, j = pre_j, site = pre_site;
         const int cur = occ[site];
         const int nc = m.sl_ncodes[sl];
         int ci = (int)mulhi32(q2, (uint32_t)(nc - 1));
@@ -433,10 +559,13 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
         st.n = 1; st.site[0] = site; st.oldc[0] = cur; st.newc[0] = m.sl_codes[sl][ci]; st.sl[0] = sl; st.pos[0] = j;
       } else if (USHER == LMC_USHER_SWAP || usher == LMC_USHER_SWAP) {
         // Swap.propose_step, mcusher.py:176-200
-        const int sl = choose_sublattice(m, q0);
-        const int off = m.sl_off[sl], n_act = m.sl_off[sl + 1] - off;
-        const int j = (int)mulhi32(q1, (uint32_t)n_act);
-        const int site1 = site_of_pos(m, sl, j);
+        int sl = pre_sl, j = pre_j, site1 = pre_site;
+        if (USHER == LMC_USHER_TABLEFLIP) {  // fallback swap of the table-flip usher: words 4,5,6
+          sl = choose_sublattice(m, q0);
+          j = (int)mulhi32(q1, (uint32_t)(m.sl_off[sl + 1] - m.sl_off[sl]));
+          site1 = site_of_pos(m, sl, j);
+        }
+        const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
         const int s1 = occ[site1];
         const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
         if (ndiff > 0) {
@@ -516,35 +645,65 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
 
       // ------------------------------ evaluate ------------------------------------------
       double acc = 0.0, acc_ew = 0.0, dmu = 0.0;
+      constexpr bool MU_POSSIBLE = USHER != LMC_USHER_SWAP;  // a swap leaves the chemical work unchanged
       // the cluster records depend on the sites only: fetch the first two flips' records up front so
-      // that their L2 latency overlaps (swap = 2 flips)
+      // that their L2 latency overlaps with the rest of the proposal
       RecChunk pre0, pre1;
+      bool deferred1 = false;
       if (st.n > 0) pre0 = load_records<G>(m, st.site[0], g);
       if (st.n > 1) pre1 = load_records<G>(m, st.site[1], g);
-#pragma unroll
-      for (int f = 0; f < LMC_MAX_FLIPS; ++f) {
-        if (f < st.n) {
-          if (f >= 2) pre0 = load_records<G>(m, st.site[f], g);
-          acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g,
-                                      f == 1 ? pre1 : pre0);
-          if (EWALD) acc_ew += flip_ewald<G>(m, occ, st.site[f], st.oldc[f], st.newc[f], g);
-          if (m.muW)
-            dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
-          if (g == 0) occ[st.site[f]] = (uint8_t)st.newc[f];
-          group_sync<G>(gmask);
+      if (st.n >= 2 && !a.seq_flips) {
+        if (g == 0) occ[st.site[0]] = (uint8_t)st.newc[0];
+        group_sync<G>(gmask);
+        acc = flip_energy_pair<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], st.site[1], st.oldc[1],
+                                        st.newc[1], stash0, stash0 + stash_stride, g, pre0, pre1);
+        if (EWALD) {
+          acc_ew = flip_ewald<G>(m, occ, st.site[0], st.oldc[0], st.newc[0], g);
+          acc_ew += flip_ewald<G>(m, occ, st.site[1], st.oldc[1], st.newc[1], g);
         }
+        // flip 0's records read site 1 (old value): lanes are not guaranteed to run in lockstep, so
+        // site 1 may only be written once every lane is done -- after a sync (more flips follow) or
+        // after the group reduction below (two-flip step: written on accept only)
+        if (st.n > 2) {
+          group_sync<G>(gmask);
+          if (g == 0) occ[st.site[1]] = (uint8_t)st.newc[1];
+          group_sync<G>(gmask);
+        } else {
+          deferred1 = true;
+        }
+      } else if (st.n >= 1) {
+        acc = flip_energy<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], stash0, g, pre0);
+        if (EWALD) acc_ew = flip_ewald<G>(m, occ, st.site[0], st.oldc[0], st.newc[0], g);
+        if (g == 0) occ[st.site[0]] = (uint8_t)st.newc[0];
+        if (st.n > 1) group_sync<G>(gmask);
+      }
+#pragma unroll
+      for (int f = 1; f < LMC_MAX_FLIPS; ++f) {
+        if (f < st.n && (f >= 2 || a.seq_flips)) {
+          pre0 = load_records<G>(m, st.site[f], g);
+          acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g, pre0);
+          if (EWALD) acc_ew += flip_ewald<G>(m, occ, st.site[f], st.oldc[f], st.newc[f], g);
+          if (g == 0) occ[st.site[f]] = (uint8_t)st.newc[f];
+          if (f + 1 < st.n) group_sync<G>(gmask);
+        }
+      }
+      if (MU_POSSIBLE && m.muW) {
+#pragma unroll
+        for (int f = 0; f < LMC_MAX_FLIPS; ++f)
+          if (f < st.n)
+            dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
       }
       double dH = group_sum<G>(acc, gmask);
       double dEw = 0.0;
       if (EWALD) { dEw = group_sum<G>(acc_ew, gmask); dH += nat_ew * dEw; }
-      if (m.muW) dH += nat_mu * dmu;
+      if (MU_POSSIBLE && m.muW) dH += nat_mu * dmu;
 
       // ------------------------------ accept --------------------------------------------
       int new_bin = 0;
       if (!wl_mode) {
         // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
         const double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
-        accepted = accept_test(exponent, r.w);
+        accepted = accept_test(exponent, lf, r.w);
       } else {
         // WangLandau._accept_step, kernel/wanglandau.py:186-202
         const double e_new = enth + dH;
@@ -556,7 +715,7 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
           const double s_old = (bin >= 0 && bin < nb) ? __ldcg(wlS + bin) : 0.0;
           const double s_new = (new_bin >= 0 && new_bin < nb) ? __ldcg(wlS + new_bin) : 0.0;
           const double exponent = (s_old - s_new) + st.log_priori;
-          accepted = accept_test(exponent, r.w);
+          accepted = accept_test(exponent, lf, r.w);
         }
       }
 
@@ -567,8 +726,9 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
         for (int f = 0; f < LMC_MAX_FLIPS; ++f)
           if (f < st.n) flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g);
         if (g == 0) {
+          if (deferred1) occ[st.site[1]] = (uint8_t)st.newc[1];
           if (EWALD) feat[m.ewF] += dEw;
-          if (m.muW) feat[m.muF] += dmu;
+          if (MU_POSSIBLE && m.muW) feat[m.muF] += dmu;
 #pragma unroll
           for (int f = 0; f < LMC_MAX_FLIPS; ++f)
             if (f < st.n) {
@@ -587,7 +747,7 @@ __global__ void lmc_run_kernel(const DevModel m, const RunArgs a) {
         if (g == 0) {
 #pragma unroll
           for (int f = LMC_MAX_FLIPS - 1; f >= 0; --f)
-            if (f < st.n) occ[st.site[f]] = (uint8_t)st.oldc[f];
+            if (f < st.n && !(f == 1 && deferred1)) occ[st.site[f]] = (uint8_t)st.oldc[f];
         }
       }
       group_sync<G>(gmask);

@@ -77,6 +77,7 @@ struct RunArgs {
   int walker_smem;    // bytes of shared memory per walker
   int off_feat, off_stash, off_cnt, off_plane;  // offsets inside a walker's shared-memory slab
   int max_flips;      // flips per step of the selected usher (stash slots)
+  int seq_flips;      // debug: evaluate the flips of a step strictly one after another
 };
 
 }  // namespace lmc

@@ -266,6 +266,7 @@ class Sampler:
         per_sample = W * ((N if self.record_occupancy else 0) + 8 * F + 8 + 1 + 4)
         chunk = max(1, min(S, int(max_chunk_bytes // max(per_sample, 1)))) if S else 0
         done = 0
+        self._kernel_events = []
         while done < S:
             n = min(chunk, S - done)
             tr_occ = torch.empty((n, W, N), dtype=torch.int8, device=dev) if self.record_occupancy else None
@@ -295,7 +296,11 @@ class Sampler:
                 wl.entropy_dev, wl.histogram_dev = st["entropy"].data_ptr(), st["histogram"].data_ptr()
                 wl.occurrences_dev, wl.mean_features_dev = st["occurrences"].data_ptr(), st["mean_features"].data_ptr()
                 wl.mod_factor_dev, wl.steps_counter_dev = st["mod_factor"].data_ptr(), st["steps_counter"].data_ptr()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
             eng.run(cfg)
+            ev1.record()
+            self._kernel_events.append((ev0, ev1))
             self._step_counter += n * thin_by
             traces = {
                 "features": tr_feat.cpu().numpy(),
@@ -312,6 +317,9 @@ class Sampler:
             self.samples.append(traces, thin_by)
             done += n
         torch.cuda.synchronize(dev)
+        # device time of the lmc_run launches of this call (CUDA events on the launching stream)
+        self.last_kernel_ms = float(sum(a.elapsed_time(b) for a, b in self._kernel_events))
+        self._kernel_events = []
 
     def anneal(self, temperatures, mcmc_steps, initial_occupancies=None, thin_by=1, progress=False,
                stream_chunk=0, stream_file=None, swmr_mode=True):
