@@ -320,12 +320,11 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   int G = c->group_size;
   if (const char* e = getenv("LMC_GROUP_SIZE")) { if (G == 0) G = atoi(e); }
   if (G == 0) {
-    if (ewald) G = 32;
-    else {
-      long long want = (long long)mdl->num_sms * 768 / c->num_walkers;
-      G = 4;
-      while (G < 32 && G * 2 <= want) G *= 2;
-    }
+    // measured on B200 (profiles/): a full warp per walker wins while all walkers fit in one wave
+    // (W <= 32 per SM); beyond that half warps amortise the per-step scalar work better
+    if (ewald || c->num_walkers <= mdl->num_sms * 32) G = 32;
+    else if (c->num_walkers <= mdl->num_sms * 1024) G = 16;
+    else G = 8;
   }
   if (c->usher == LMC_USHER_TABLEFLIP) G = (G >= 16) ? 32 : 8;
   if (G != 4 && G != 8 && G != 16 && G != 32) return fail("group_size must be 4, 8, 16 or 32");

@@ -187,6 +187,17 @@ class Sampler:
     def samples(self):
         return self._container
 
+    def _staging(self, name, dev_tensor):
+        """Cached pinned host buffer matching ``dev_tensor`` (page-locked D2H staging)."""
+        import torch
+        cache = self.__dict__.setdefault("_pinned", {})
+        key = (name, tuple(dev_tensor.shape), dev_tensor.dtype)
+        if key not in cache:
+            for k in [k for k in cache if k[0] == name]:
+                del cache[k]
+            cache[key] = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+        return cache[key]
+
     def efficiency(self, discard=0, flat=True):
         return self.samples.sampling_efficiency(discard=discard, flat=flat)
 
@@ -302,14 +313,22 @@ class Sampler:
             ev1.record()
             self._kernel_events.append((ev0, ev1))
             self._step_counter += n * thin_by
+            # device -> pinned host staging (async on the launching stream), one sync, then numpy
+            dev_tr = {"features": tr_feat, "enthalpy": tr_enth, "accepted": tr_acc, "n_accepted": tr_nacc}
+            if self.record_occupancy:
+                dev_tr["occupancy"] = tr_occ
+            host = {k: self._staging(k, v) for k, v in dev_tr.items()}
+            for k, v in dev_tr.items():
+                host[k].copy_(v, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
             traces = {
-                "features": tr_feat.cpu().numpy(),
-                "enthalpy": tr_enth.cpu().numpy()[:, :, None],
-                "accepted": tr_acc.cpu().numpy().astype(bool)[:, :, None],
-                "n_accepted": tr_nacc.cpu().numpy(),
+                "features": host["features"].numpy().copy(),
+                "enthalpy": host["enthalpy"].numpy().copy()[:, :, None],
+                "accepted": host["accepted"].numpy().astype(bool)[:, :, None],
+                "n_accepted": host["n_accepted"].numpy().copy(),
             }
             if self.record_occupancy:
-                traces["occupancy"] = tr_occ.cpu().numpy()     # int8 on host; int32 on access
+                traces["occupancy"] = host["occupancy"].numpy().copy()   # int8 on host; int32 on access
             else:
                 traces["occupancy"] = np.zeros((n, W, 0), dtype=np.int8)
             if "temperature" in self.samples._shapes:
