@@ -1,0 +1,65 @@
+"""CUDA path vs golden vectors produced by the reference's own compiled Cython evaluators."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import models as M
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+CASES = {"fcc2": (lambda: M.fcc_subspace(), 2), "fcc3": (lambda: M.fcc_subspace(), 3),
+         "rs2": (lambda: M.rocksalt_subspace(anions=("O2-", "F-")), 2)}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_matches_reference_golden_vectors(cuda_device, name):
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    mk, n = CASES[name]
+    sub = mk()
+    scm = np.eye(3, dtype=int) * n
+    coefs = GOLD[f"{name}_coefs"]
+    occ, sites, codes = GOLD[f"{name}_occ"], GOLD[f"{name}_sites"], GOLD[f"{name}_codes"]
+    ce = S.ClusterExpansionProcessor(sub, scm, coefs)
+    cd = S.ClusterDecompositionProcessor(sub, scm, L.cluster_interaction_tensors(sub, coefs))
+    for proc, key in ((ce, "corr"), (cd, "inter")):
+        full = GOLD[f"{name}_full_{key}"]
+        scale = np.abs(full).max()
+        np.testing.assert_allclose(proc.compute_feature_vector_batch(occ), full, rtol=1e-10, atol=1e-10 * scale)
+        np.testing.assert_allclose(proc.compute_feature_vector_change_batch(occ, sites, codes),
+                                   GOLD[f"{name}_delta_{key}"], rtol=1e-10, atol=1e-10 * scale)
+    if name == "rs2":
+        ew = S.EwaldProcessor(sub, scm, ewald_matrix=GOLD["rs2_ewald_matrix"], ewald_inds=GOLD["rs2_ewald_inds"])
+        scale = np.abs(GOLD["rs2_full_ewald"]).max()
+        np.testing.assert_allclose(ew.compute_feature_vector_batch(occ)[:, 0], GOLD["rs2_full_ewald"], rtol=1e-10)
+        np.testing.assert_allclose(ew.compute_feature_vector_change_batch(occ, sites, codes)[:, 0],
+                                   GOLD["rs2_delta_ewald"], rtol=1e-10, atol=1e-10 * scale)
+
+
+def test_processor_api_single_calls_and_errors(cuda_device):
+    """Reference-style single calls (tests/test_moca/test_processor.py:175-231)."""
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 3
+    coefs = M.fcc_coefs(sub)
+    proc = S.ClusterDecompositionProcessor(sub, scm, L.cluster_interaction_tensors(sub, coefs))
+    occ = M.random_occupancies(sub, scm, 1, seed=1)[0]
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        s = int(rng.integers(27))
+        new = 1 - occ[s]
+        occ2 = occ.copy()
+        occ2[s] = new
+        dprop = proc.compute_property_change(occ, [(s, new)])
+        assert dprop == pytest.approx(proc.compute_property(occ2) - proc.compute_property(occ), rel=1e-10, abs=1e-11)
+        assert proc.compute_property_change(occ2, [(s, occ[s])]) == pytest.approx(-dprop, rel=1e-10, abs=1e-12)
+        occ = occ2
+    with pytest.raises(ValueError):
+        proc.compute_feature_vector(["a"] * 27)
+    fwd, rev = proc.compute_average_drift(iterations=200, seed=1)
+    assert abs(fwd) < 1e-12 and abs(rev) < 1e-12
+    assert np.array_equal(proc.compute_feature_vector_change(occ, []), np.zeros(8))
+    with pytest.raises(ValueError):
+        S.ClusterExpansionProcessor(sub, scm, coefs[:-1])
