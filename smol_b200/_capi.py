@@ -107,7 +107,8 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liblmc.so")
+    return os.environ.get("LMC_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                         "_lib", "liblmc.so")
 
 
 def load():

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
-LIB = os.path.join(LIBDIR, "liblmc.so")
+LIB = os.path.join(LIBDIR, os.environ.get("LMC_LIB_NAME", "liblmc.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -31,7 +31,7 @@ def up_to_date() -> bool:
 
 def _compile(args):
     src, obj, extra = args
-    cmd = [NVCC, *FLAGS, *extra, "-c", src, "-o", obj]
+    cmd = [NVCC, *FLAGS, *extra, *os.environ.get("LMC_EXTRA_DEFS", "").split(), "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return cmd, r
 
@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if up_to_date() and not force:
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" + os.environ.get("LMC_LIB_NAME", "").replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
     jobs = [(os.path.join(CSRC, "lmc_api.cu"), os.path.join(objdir, "lmc_api.o"), [])]
     for g in GROUPS:

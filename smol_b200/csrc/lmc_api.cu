@@ -360,7 +360,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (a.max_flips > LMC_MAX_FLIPS) return fail("flip table changes more than 4 sites per step");
   a.off_cnt = a.off_stash + (int)(((size_t)a.max_flips * m.Rstride * stash_el + 15) & ~size_t(15));
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
-  a.walker_smem = a.off_plane + ((m.plane_words * 4 + 15) & ~15);
+  a.off_ring = a.off_plane + ((2 * m.plane_words * 4 + 15) & ~15);  // planes + prefix popcounts
+  a.walker_smem = a.off_ring + G * 16;                                // per-lane precomputed proposals
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
   for (;;) {

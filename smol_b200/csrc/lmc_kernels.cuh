@@ -52,7 +52,7 @@ __device__ __forceinline__ void stage_tables(const DevModel& m, unsigned char* s
 struct RecChunk { uint2 r[4]; };  // the first 4*G records of a site, one lane's share
 
 template <int G>
-__device__ __forceinline__ RecChunk load_records(const DevModel& m, int site, int g) {
+__device__ __forceinline__ RecChunk load_records_pred(const DevModel& m, int site, int g) {
   const uint2* rp = m.site_rec + (size_t)site * m.Rstride;
   RecChunk c;
 #pragma unroll
@@ -60,6 +60,25 @@ __device__ __forceinline__ RecChunk load_records(const DevModel& m, int site, in
     const int r = g + u * G;
     c.r[u] = r < m.Rstride ? __ldg(rp + r) : make_uint2(0u, (uint32_t)m.nCls << 16);
   }
+  return c;
+}
+
+// A/B measured on B200 (profiles/r01_variants.md): the branchy uniform loads raise register pressure
+#ifndef LMC_OPT_LOADSW
+#define LMC_OPT_LOADSW 0
+#endif
+template <int G>
+__device__ __forceinline__ RecChunk load_records(const DevModel& m, int site, int g) {
+#if !LMC_OPT_LOADSW
+  return load_records_pred<G>(m, site, g);
+#endif
+  const uint2* rp = m.site_rec + (size_t)site * m.Rstride + g;
+  RecChunk c;
+  const int nper = m.Rstride / G;   // uniform (Rstride is a multiple of 32)
+  c.r[0] = __ldg(rp);
+  if (nper > 1) c.r[1] = __ldg(rp + G);
+  if (nper > 2) c.r[2] = __ldg(rp + 2 * G);
+  if (nper > 3) c.r[3] = __ldg(rp + 3 * G);
   return c;
 }
 
@@ -239,7 +258,7 @@ __device__ __forceinline__ double flip_ewald(const DevModel& m, const uint8_t* o
 // Restates `rng.choice(active_sites[occu[active_sites] != species1])` (mcusher.py:189-196) and the
 // species_list picks of TableFlip (mcusher.py:620-637).
 template <int G>
-__device__ __forceinline__ int select_pos(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
+__device__ __forceinline__ int select_pos_scan(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
                                           int g, uint32_t mask) {
   const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
   const int nw = m.sl_nwords[sl];
@@ -325,6 +344,78 @@ __device__ __forceinline__ int select_pos(const DevModel& m, const uint32_t* pla
   return res;
 }
 
+template <int G>
+__device__ __forceinline__ int select_pos_pfx(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
+                                          int g, uint32_t mask) {
+  // planes: [plane words | exclusive prefix popcounts], both [code][word] per sublattice
+  const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+  const int nw = m.sl_nwords[sl];
+  const uint32_t* pl = planes + m.sl_plane_off[sl] + code * nw;
+  const uint32_t* px = pl + m.plane_words;
+  const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
+  const int cw = (nw + G - 1) / G;            // words per lane (1 when the plane fits the group)
+  const int lo = g * cw, hi = min(lo + cw, nw);
+  // candidates before this lane's chunk (all words before the last one are full)
+  int excl = 0x7fffffff, cnt = 0;
+  uint32_t b = 0u;
+  if (lo < nw) {
+    const int pe = (int)px[lo];
+    excl = ne ? 32 * lo - pe : pe;
+    for (int wd = lo; wd < hi; ++wd) {
+      b = pl[wd];
+      if (ne) b = ~b & (wd == nw - 1 ? tail : 0xffffffffu);
+      cnt += __popc(b);
+    }
+  }
+  const bool found = (k >= excl) && (k < excl + cnt);
+  int wsel = lo;
+  int rem = k - excl;
+  if (cw > 1 && found) {   // locate the word inside the chunk
+    for (int wd = lo; wd < hi; ++wd) {
+      b = pl[wd];
+      if (ne) b = ~b & (wd == nw - 1 ? tail : 0xffffffffu);
+      const int c = __popc(b);
+      if (rem < c) { wsel = wd; break; }
+      rem -= c;
+    }
+  }
+  if (G == 1) {
+    int pos = 0;
+    for (int q = 0; q < 32; ++q)
+      if (((b >> q) & 1u) && __popc(b & ((1u << q) - 1u)) == rem) pos = q;
+    return wsel * 32 + pos;
+  }
+  const uint32_t own = __ballot_sync(mask, found);
+  const int src = own ? (__ffs(own) - 1) : (int)(threadIdx.x & 31);
+  const uint32_t word = __shfl_sync(mask, b, src);
+  rem = __shfl_sync(mask, rem, src);
+  wsel = __shfl_sync(mask, wsel, src);
+  int hit = -1;
+#pragma unroll
+  for (int bit = 0; bit < 32; bit += G) {   // every lane tests bit(s) of the owning word
+    const int q = bit + g;
+    if (((word >> q) & 1u) && __popc(word & ((1u << q) - 1u)) == rem) hit = q;
+  }
+  const uint32_t hb = __ballot_sync(mask, hit >= 0);
+  if (G == 32) return wsel * 32 + (hb ? __ffs(hb) - 1 : 0);
+  const int hl = hb ? (__ffs(hb) - 1) : (int)(threadIdx.x & 31);
+  return wsel * 32 + __shfl_sync(mask, hit, hl);
+}
+
+// cached prefix popcounts measured neutral vs the shuffle scan (profiles/r01_variants.md): off
+#ifndef LMC_OPT_PFX
+#define LMC_OPT_PFX 0
+#endif
+template <int G>
+__device__ __forceinline__ int select_pos(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
+                                          int g, uint32_t mask) {
+#if LMC_OPT_PFX
+  return select_pos_pfx<G>(m, planes, sl, code, k, ne, g, mask);
+#else
+  return select_pos_scan<G>(m, planes, sl, code, k, ne, g, mask);
+#endif
+}
+
 __device__ __forceinline__ int site_of_pos(const DevModel& m, int sl, int pos) {
   return m.sl_first[sl] >= 0 ? m.sl_first[sl] + pos : __ldg(m.sl_sites + m.sl_off[sl] + pos);
 }
@@ -335,13 +426,14 @@ __device__ __forceinline__ int site_of_pos(const DevModel& m, int sl, int pos) {
 // double-precision test.
 __device__ __forceinline__ float log_u_float(uint32_t r) { return __logf((float)u01(r)); }
 
-__device__ __forceinline__ bool accept_test(double exponent, float lf, uint32_t r_exact) {
-  if (exponent >= 0.0) return true;
+// returns 1 accept, 0 reject, -1 undecided (inside the guard band: evaluate the exact double test)
+__device__ __forceinline__ int accept_fast(double exponent, float lf) {
+  if (exponent >= 0.0) return 1;
   const float ex = (float)exponent;
   const float eps = 1e-5f * (1.0f + fabsf(lf)) + 1e-6f * fabsf(ex);
-  if (ex < lf - eps) return false;
-  if (ex > lf + eps) return true;
-  return exponent > log(u01(r_exact));
+  if (ex < lf - eps) return 0;
+  if (ex > lf + eps) return 1;
+  return -1;
 }
 
 __device__ __forceinline__ int choose_sublattice(const DevModel& m, uint32_t r0) {
@@ -368,17 +460,19 @@ __device__ __forceinline__ double tf_masked_weights(const DevModel& m, const int
   return sum;
 }
 
+template <int MF>
 struct Step {
   int n;                       // number of flips (0 = empty step)
-  int site[LMC_MAX_FLIPS], oldc[LMC_MAX_FLIPS], newc[LMC_MAX_FLIPS], sl[LMC_MAX_FLIPS], pos[LMC_MAX_FLIPS];
+  int site[MF], oldc[MF], newc[MF], sl[MF], pos[MF];
   double log_priori;
 };
 // append without dynamic indexing (keeps the arrays in registers)
-__device__ __forceinline__ void push_flip(Step& st, int site, int oldc, int newc, int sl, int pos) {
+template <int MF>
+__device__ __forceinline__ void push_flip(Step<MF>& st, int site, int oldc, int newc, int sl, int pos) {
 #pragma unroll
-  for (int i = 0; i < LMC_MAX_FLIPS; ++i)
+  for (int i = 0; i < MF; ++i)
     if (i == st.n) { st.site[i] = site; st.oldc[i] = oldc; st.newc[i] = newc; st.sl[i] = sl; st.pos[i] = pos; }
-  if (st.n < LMC_MAX_FLIPS) ++st.n;
+  if (st.n < MF) ++st.n;
 }
 
 // Python float floor division `a // b` (CPython float_floor_div), used by WangLandau._get_bin_id
@@ -399,8 +493,10 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // num_samples * thin_by attempted steps per walker in ONE launch.
 // ------------------------------------------------------------------------------------------
 template <int G, bool KONE, bool EWALD, int USHER, bool WLMODE>
-__global__ void __launch_bounds__(128, (EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 4 : 7)
+__global__ void __launch_bounds__(128, (EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 4 : (G < 32 ? 5 : 7))
 lmc_run_kernel(const DevModel m, const RunArgs a) {
+  constexpr int MF = USHER == LMC_USHER_FLIP ? 1 : (USHER == LMC_USHER_SWAP ? 2 : LMC_MAX_FLIPS);
+  constexpr int I1 = MF > 1 ? 1 : 0;   // index of the second flip (dead code when MF == 1)
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint64_t bar;
   const int g = threadIdx.x % G;
@@ -434,7 +530,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   double enth = a.enthalpy[w];
   // species counts per (active sublattice, code) and one bit-plane per code
   for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
-  for (int i = g; i < m.plane_words; i += G) planes[i] = 0u;
+  for (int i = g; i < 2 * m.plane_words; i += G) planes[i] = 0u;
   group_sync<G>(gmask);
   for (int sl = 0; sl < m.nSl; ++sl) {
     const int n_act = m.sl_off[sl + 1] - m.sl_off[sl], nw = m.sl_nwords[sl];
@@ -445,6 +541,18 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         planes[m.sl_plane_off[sl] + code * nw + wd] |= 1u << b;
         atomicAdd(&cnt[sl * LMC_MAX_CODES + code], 1);
       }
+    }
+  }
+  group_sync<G>(gmask);
+  // exclusive prefix popcounts per (sublattice, code): px[w] = set bits of the plane in words < w
+  for (int sl = 0; LMC_OPT_PFX && sl < m.nSl; ++sl) {
+    const int nw = m.sl_nwords[sl];
+    int maxcode = 0;
+    for (int c = 0; c < m.sl_ncodes[sl]; ++c) maxcode = max(maxcode, m.sl_codes[sl][c]);
+    for (int code = g; code <= maxcode; code += G) {
+      uint32_t* pl = planes + m.sl_plane_off[sl] + code * nw;
+      uint32_t run = 0;
+      for (int wd = 0; wd < nw; ++wd) { pl[m.plane_words + wd] = run; run += __popc(pl[wd]); }
     }
   }
   group_sync<G>(gmask);
@@ -474,9 +582,16 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // State-independent part of the next G steps, one step per lane (counter-based RNG): random
   // words, sublattice, first site and the float log of the acceptance uniform.  Every step then
   // costs a few shuffles instead of a redundant Philox evaluation in all lanes.
+#ifndef LMC_OPT_RING
+#define LMC_OPT_RING 1
+#endif
+#if LMC_OPT_RING
+  uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [G] x (sl<<24 | pos, site, word z, float log u)
+#else
   U4 bq{0, 0, 0, 0};
   int b_slj = 0, b_site = 0;
   float b_lf = 0.f;
+#endif
   int bphase = 0;
   for (long long s = 0; s < a.S; ++s) {
     int nacc = 0;
@@ -489,6 +604,24 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1);
         lf = log_u_float(r.w);
       } else {
+#if LMC_OPT_RING
+        if (bphase == 0) {
+          const unsigned long long st_ = step + (unsigned long long)g;
+          const U4 bq = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
+          const int sl_ = choose_sublattice(m, bq.x);
+          const int j_ = (int)mulhi32(bq.y, (uint32_t)(m.sl_off[sl_ + 1] - m.sl_off[sl_]));
+          group_sync<G>(gmask);   // every lane has consumed the previous batch
+          ring[g] = make_uint4((uint32_t)((sl_ << 24) | j_), (uint32_t)site_of_pos(m, sl_, j_), bq.z,
+                               __float_as_uint(log_u_float(bq.w)));
+          group_sync<G>(gmask);
+        }
+        const uint4 rq = ring[bphase];   // same address in all lanes: one broadcast load
+        pre_sl = (int)(rq.x >> 24); pre_j = (int)(rq.x & 0xffffffu);
+        pre_site = (int)rq.y;
+        r.x = 0u; r.y = 0u; r.w = 0u;
+        r.z = rq.z;
+        lf = __uint_as_float(rq.w);
+#else
         if (bphase == 0) {
           const unsigned long long st_ = step + (unsigned long long)g;
           bq = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
@@ -502,17 +635,17 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         const int slj = __shfl_sync(gmask, b_slj, src);
         pre_sl = slj >> 24; pre_j = slj & 0xffffff;
         pre_site = __shfl_sync(gmask, b_site, src);
-        r.x = 0u; r.y = 0u;
+        r.x = 0u; r.y = 0u; r.w = 0u;
         r.z = __shfl_sync(gmask, bq.z, src);
-        r.w = __shfl_sync(gmask, bq.w, src);
         lf = __shfl_sync(gmask, b_lf, src);
+#endif
         bphase = (bphase + 1) & (G - 1);
       }
-      Step st;
+      Step<MF> st;
       st.n = 0;
       st.log_priori = 0.0;
 #pragma unroll
-      for (int i = 0; i < LMC_MAX_FLIPS; ++i) { st.site[i] = 0; st.oldc[i] = 0; st.newc[i] = 0; st.sl[i] = 0; st.pos[i] = 0; }
+      for (int i = 0; i < MF; ++i) { st.site[i] = 0; st.oldc[i] = 0; st.newc[i] = 0; st.sl[i] = 0; st.pos[i] = 0; }
 
       // ------------------------------ propose ------------------------------------------
       int usher = USHER;
@@ -575,7 +708,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           const int s2 = occ[site2];
           st.n = 2;
           st.site[0] = site1; st.oldc[0] = s1; st.newc[0] = s2; st.sl[0] = sl; st.pos[0] = j;
-          st.site[1] = site2; st.oldc[1] = s2; st.newc[1] = s1; st.sl[1] = sl; st.pos[1] = p2;
+          st.site[I1] = site2; st.oldc[I1] = s2; st.newc[I1] = s1; st.sl[I1] = sl; st.pos[I1] = p2;
         }
       } else if (USHER == LMC_USHER_TABLEFLIP) {
         // table flip: sequential picks, one random word each (words 4.. of the step)
@@ -651,22 +784,22 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       RecChunk pre0, pre1;
       bool deferred1 = false;
       if (st.n > 0) pre0 = load_records<G>(m, st.site[0], g);
-      if (st.n > 1) pre1 = load_records<G>(m, st.site[1], g);
+      if (st.n > 1) pre1 = load_records<G>(m, st.site[I1], g);
       if (st.n >= 2 && !a.seq_flips) {
         if (g == 0) occ[st.site[0]] = (uint8_t)st.newc[0];
         group_sync<G>(gmask);
-        acc = flip_energy_pair<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], st.site[1], st.oldc[1],
-                                        st.newc[1], stash0, stash0 + stash_stride, g, pre0, pre1);
+        acc = flip_energy_pair<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], st.site[I1], st.oldc[I1],
+                                        st.newc[I1], stash0, stash0 + stash_stride, g, pre0, pre1);
         if (EWALD) {
           acc_ew = flip_ewald<G>(m, occ, st.site[0], st.oldc[0], st.newc[0], g);
-          acc_ew += flip_ewald<G>(m, occ, st.site[1], st.oldc[1], st.newc[1], g);
+          acc_ew += flip_ewald<G>(m, occ, st.site[I1], st.oldc[I1], st.newc[I1], g);
         }
         // flip 0's records read site 1 (old value): lanes are not guaranteed to run in lockstep, so
         // site 1 may only be written once every lane is done -- after a sync (more flips follow) or
         // after the group reduction below (two-flip step: written on accept only)
         if (st.n > 2) {
           group_sync<G>(gmask);
-          if (g == 0) occ[st.site[1]] = (uint8_t)st.newc[1];
+          if (g == 0) occ[st.site[I1]] = (uint8_t)st.newc[I1];
           group_sync<G>(gmask);
         } else {
           deferred1 = true;
@@ -678,7 +811,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         if (st.n > 1) group_sync<G>(gmask);
       }
 #pragma unroll
-      for (int f = 1; f < LMC_MAX_FLIPS; ++f) {
+      for (int f = 1; f < MF; ++f) {
         if (f < st.n && (f >= 2 || a.seq_flips)) {
           pre0 = load_records<G>(m, st.site[f], g);
           acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g, pre0);
@@ -689,7 +822,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       }
       if (MU_POSSIBLE && m.muW) {
 #pragma unroll
-        for (int f = 0; f < LMC_MAX_FLIPS; ++f)
+        for (int f = 0; f < MF; ++f)
           if (f < st.n)
             dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
       }
@@ -703,7 +836,11 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       if (!wl_mode) {
         // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
         const double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
-        accepted = accept_test(exponent, lf, r.w);
+        {
+          const int af = accept_fast(exponent, lf);
+          accepted = af >= 0 ? (af != 0)
+                             : exponent > log(u01(philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1).w));
+        }
       } else {
         // WangLandau._accept_step, kernel/wanglandau.py:186-202
         const double e_new = enth + dH;
@@ -715,7 +852,11 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           const double s_old = (bin >= 0 && bin < nb) ? __ldcg(wlS + bin) : 0.0;
           const double s_new = (new_bin >= 0 && new_bin < nb) ? __ldcg(wlS + new_bin) : 0.0;
           const double exponent = (s_old - s_new) + st.log_priori;
-          accepted = accept_test(exponent, lf, r.w);
+          {
+          const int af = accept_fast(exponent, lf);
+          accepted = af >= 0 ? (af != 0)
+                             : exponent > log(u01(philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1).w));
+        }
         }
       }
 
@@ -723,14 +864,14 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       if (accepted) {
         // MCKernel._do_accept_step (kernel/base.py:327-343) + trace accumulation (sampler.py:204-207)
 #pragma unroll
-        for (int f = 0; f < LMC_MAX_FLIPS; ++f)
+        for (int f = 0; f < MF; ++f)
           if (f < st.n) flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g);
         if (g == 0) {
-          if (deferred1) occ[st.site[1]] = (uint8_t)st.newc[1];
+          if (deferred1) occ[st.site[I1]] = (uint8_t)st.newc[I1];
           if (EWALD) feat[m.ewF] += dEw;
           if (MU_POSSIBLE && m.muW) feat[m.muF] += dmu;
 #pragma unroll
-          for (int f = 0; f < LMC_MAX_FLIPS; ++f)
+          for (int f = 0; f < MF; ++f)
             if (f < st.n) {
               cnt[st.sl[f] * LMC_MAX_CODES + st.oldc[f]]--;
               cnt[st.sl[f] * LMC_MAX_CODES + st.newc[f]]++;
@@ -741,12 +882,23 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
               pl[st.newc[f] * nw] ^= bit;
             }
         }
+        // prefix popcounts of the touched planes: words after the flipped position shift by one
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          if (LMC_OPT_PFX && f < st.n) {
+            const int nw = m.sl_nwords[st.sl[f]];
+            uint32_t* px = planes + m.plane_words + m.sl_plane_off[st.sl[f]];
+            for (int wd = (st.pos[f] >> 5) + 1 + g; wd < nw; wd += G) {
+              px[st.oldc[f] * nw + wd] -= 1u;
+              px[st.newc[f] * nw + wd] += 1u;
+            }
+          }
         enth += dH;
         ++nacc;
       } else if (st.n > 0) {
         if (g == 0) {
 #pragma unroll
-          for (int f = LMC_MAX_FLIPS - 1; f >= 0; --f)
+          for (int f = MF - 1; f >= 0; --f)
             if (f < st.n && !(f == 1 && deferred1)) occ[st.site[f]] = (uint8_t)st.oldc[f];
         }
       }

@@ -75,7 +75,7 @@ struct RunArgs {
   LmcWangLandau wl;
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
-  int off_feat, off_stash, off_cnt, off_plane;  // offsets inside a walker's shared-memory slab
+  int off_feat, off_stash, off_cnt, off_plane, off_ring;  // offsets inside a walker's shared-memory slab
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another
 };
