@@ -124,7 +124,8 @@ enum { LMC_KERNEL_METROPOLIS = 0, LMC_KERNEL_WANGLANDAU = 1 };
 
 typedef struct LmcWangLandau {
   double min_enthalpy, max_enthalpy, bin_size, flatness, mod_update;
-  int32_t num_bins, check_period, update_period, reserved;
+  int32_t num_bins, check_period, update_period;
+  int32_t reserved; /* 1: mean_features_dev holds per-bin SUMS (valid when update_period == 1) */
   /* per-walker state, device pointers */
   double* entropy_dev;        /* [W][num_bins] */
   int64_t* histogram_dev;     /* [W][num_bins] */

@@ -178,17 +178,20 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       for (int r = (int)(b - a); r < m.Rstride; ++r) dst[r * 4 + 3] = (uint16_t)m.nCls;
     }
     UP(uint2, rec.data(), (size_t)m.N * m.Rstride, m.site_rec);
-    const int64_t nseg = d->site_seg_off[m.N];
-    std::vector<int> soff(m.N + 1);
-    for (int i = 0; i <= m.N; ++i) soff[i] = (int)d->site_seg_off[i];
-    std::vector<int4> segs(nseg);
-    for (int64_t i = 0; i < nseg; ++i) segs[i] = make_int4(d->site_seg[i * 3], d->site_seg[i * 3 + 1], d->site_seg[i * 3 + 2], 0);
-    UP(int, soff.data(), m.N + 1, m.site_seg_off);
-    UP(int4, segs.data(), nseg, m.site_seg);
+    int smax = 1;
+    for (int i = 0; i < m.N; ++i) smax = std::max(smax, (int)(d->site_seg_off[i + 1] - d->site_seg_off[i]));
+    m.Sstride = smax;
+    std::vector<int4> segs((size_t)m.N * smax, make_int4(0, 0, 0, 0));
+    for (int i = 0; i < m.N; ++i)
+      for (int64_t q = d->site_seg_off[i]; q < d->site_seg_off[i + 1]; ++q)
+        segs[(size_t)i * smax + (q - d->site_seg_off[i])] =
+            make_int4(d->site_seg[q * 3], d->site_seg[q * 3 + 1], d->site_seg[q * 3 + 2], 0);
+    UP(int4, segs.data(), segs.size(), m.site_seg);
     UP(uint2, d->full_rows, d->orb_row_off[m.nOrb], m.full_rows);
   }
   // Ewald: keep the TRANSPOSE so that column gathers of the reference become row gathers
   m.E = d->ewald_size;
+  if (m.E >= 65535) { lmc_model_destroy(mdl); return fail("Ewald matrices with 65535 or more rows are not supported (u16 row cache)"); }
   if (m.E > 0) {
     m.ewW = d->ewald_width;
     m.ewF = d->ewald_feature;
@@ -284,7 +287,8 @@ extern "C" int lmc_full_features(const LmcModel* mdl, const int8_t* occ, int W, 
 }
 
 static size_t delta_walker_smem(const DevModel& m) {
-  return (((size_t)m.F * 8 + 15) & ~size_t(15)) + (((size_t)m.Rstride * 8 + 15) & ~size_t(15));
+  return (((size_t)m.F * 8 + 15) & ~size_t(15)) + (((size_t)m.Rstride * 8 + 15) & ~size_t(15)) +
+         (m.E ? (((size_t)m.N * 2 + 15) & ~size_t(15)) : 0);
 }
 
 extern "C" int lmc_delta_features(const LmcModel* mdl, const int8_t* occ, int W, const int32_t* sites, const int32_t* codes,
@@ -361,7 +365,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_cnt = a.off_stash + (int)(((size_t)a.max_flips * m.Rstride * stash_el + 15) & ~size_t(15));
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
   a.off_ring = a.off_plane + ((2 * m.plane_words * 4 + 15) & ~15);  // planes + prefix popcounts
-  a.walker_smem = a.off_ring + G * 16;                                // per-lane precomputed proposals
+  a.off_eidx = a.off_ring + G * 16;                                   // per-lane precomputed proposals
+  a.walker_smem = a.off_eidx + (ewald ? ((2 * m.N + 15) & ~15) : 0);  // cached Ewald row index per site
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
   for (;;) {

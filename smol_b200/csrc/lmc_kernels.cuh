@@ -198,49 +198,61 @@ __device__ __forceinline__ double flip_energy_pair(const DevModel& m, const Smem
 // phase B: fold the stashed per-record differences of an ACCEPTED flip into the running feature
 // vector.  One lane owns one orbit segment and sums it in cluster order (the reference's order,
 // evaluator.pyx:253-263); feature += p * (size / J_total).
-template <int G, bool KONE>
-__device__ __forceinline__ void flip_features(const DevModel& m, const SmemTables& t, int site, const void* stash,
-                                              double* feat, int g) {
-  const int s0 = __ldg(m.site_seg_off + site), s1 = __ldg(m.site_seg_off + site + 1);
-  for (int s = s0 + g; s < s1; s += G) {
-    const int4 sg = __ldg(m.site_seg + s);
-    const OrbDev& o = t.orb[sg.z];
-    if (KONE) {
-      const double* d = reinterpret_cast<const double*>(stash) + sg.x;
+template <bool KONE>
+__device__ __forceinline__ void fold_segment(const DevModel& m, const SmemTables& t, const int4 sg, const void* stash,
+                                             double* feat) {
+  if (sg.y <= 0) return;   // padding entry
+  const OrbDev& o = t.orb[sg.z];
+  if (KONE) {
+    const double* d = reinterpret_cast<const double*>(stash) + sg.x;
+    double p = 0.0;
+    for (int j = 0; j < sg.y; ++j) p += d[j];
+    feat[o.fidx] += p * o.w;
+  } else {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(stash) + sg.x;
+    for (int k = 0; k < o.K; ++k) {
+      const double* tk = m.ftab + o.ftab_off + k * o.T;
       double p = 0.0;
-      for (int j = 0; j < sg.y; ++j) p += d[j];
-      feat[o.fidx] += p * o.w;
-    } else {
-      const uint32_t* u = reinterpret_cast<const uint32_t*>(stash) + sg.x;
-      for (int k = 0; k < o.K; ++k) {
-        const double* tk = m.ftab + o.ftab_off + k * o.T;
-        double p = 0.0;
-        for (int j = 0; j < sg.y; ++j) p += __ldg(tk + (u[j] & 0xffffu)) - __ldg(tk + (u[j] >> 16));
-        feat[o.fidx + k] += p * o.w;
-      }
+      for (int j = 0; j < sg.y; ++j) p += __ldg(tk + (u[j] & 0xffffu)) - __ldg(tk + (u[j] >> 16));
+      feat[o.fidx + k] += p * o.w;
     }
   }
+}
+// the lane's first orbit segment of a site (fixed-stride table, count 0 = padding); state independent,
+// so it can be fetched together with the records
+template <int G>
+__device__ __forceinline__ int4 load_segment(const DevModel& m, int site, int g) {
+  return g < m.Sstride ? __ldg(m.site_seg + (size_t)site * m.Sstride + g) : make_int4(0, 0, 0, 0);
+}
+template <int G, bool KONE>
+__device__ __forceinline__ void flip_features(const DevModel& m, const SmemTables& t, int site, const void* stash,
+                                              double* feat, int g, const int4 seg0) {
+  fold_segment<KONE>(m, t, seg0, stash, feat);
+  for (int sidx = g + G; sidx < m.Sstride; sidx += G)
+    fold_segment<KONE>(m, t, __ldg(m.site_seg + (size_t)site * m.Sstride + sidx), stash, feat);
 }
 
 // Ewald energy change of one flip: row gather over the (transposed) Ewald matrix.
 // Restates delta_ewald_single_flip (smol/utils/cluster/ewald.pyx:9-59); lanes stride over sites.
+// `eidx[k]` caches ewald_inds[k, occ[k]] per walker (0xFFFF = vacancy, no matrix row) so that the
+// inner loop is one shared-memory load and two independent matrix gathers, unrolled for
+// memory-level parallelism (the two rows are 2 x 8 x E bytes of HBM/L2 traffic per flip).
 template <int G>
-__device__ __forceinline__ double flip_ewald(const DevModel& m, const uint8_t* occ, int site, int olda, int newb,
+__device__ __forceinline__ double flip_ewald(const DevModel& m, const uint16_t* eidx, int site, int olda, int newb,
                                              int g) {
   const int add = __ldg(m.ewInds + site * m.ewW + newb);
   const int sub = __ldg(m.ewInds + site * m.ewW + olda);
   const double* rowA = m.ewMt + (size_t)(add < 0 ? 0 : add) * m.E;
   const double* rowS = m.ewMt + (size_t)(sub < 0 ? 0 : sub) * m.E;
+  const double ca = add >= 0 ? 2.0 : 0.0, cs = sub >= 0 ? 2.0 : 0.0;
   double acc = 0.0;
+#pragma unroll 8
   for (int k = g; k < m.N; k += G) {
-    if (k == site) continue;
-    const int e = __ldg(m.ewInds + k * m.ewW + occ[k]);
-    if (e >= 0) {
-      double tk = 0.0;
-      if (add >= 0) tk += 2.0 * __ldg(rowA + e);
-      if (sub >= 0) tk -= 2.0 * __ldg(rowS + e);
-      acc += tk;
-    }
+    const uint32_t e = eidx[k];
+    const bool skip = (e == 0xffffu) || (k == site);
+    const uint32_t ev = skip ? 0u : e;
+    const double tk = ca * __ldg(rowA + ev) - cs * __ldg(rowS + ev);   // (2 M[i,add]) - (2 M[j,sub])
+    acc += skip ? 0.0 : tk;
   }
   if (g == 0) {
     double tk = 0.0;
@@ -250,13 +262,11 @@ __device__ __forceinline__ double flip_ewald(const DevModel& m, const uint8_t* o
   }
   return acc;
 }
+__device__ __forceinline__ uint16_t ewald_index(const DevModel& m, int site, int code) {
+  const int e = __ldg(m.ewInds + site * m.ewW + code);
+  return e < 0 ? (uint16_t)0xffffu : (uint16_t)e;
+}
 
-// Position (in Sublattice.active_sites order) of the k-th active site of sublattice `sl` whose
-// code is != `code` (ne) or == `code` (!ne).  The walker keeps one bit-plane per species code
-// (bit j of plane[code] <=> active site j holds `code`); lanes popcount contiguous word chunks,
-// a group prefix sum locates the owning lane, a 5-step binary search locates the bit.
-// Restates `rng.choice(active_sites[occu[active_sites] != species1])` (mcusher.py:189-196) and the
-// species_list picks of TableFlip (mcusher.py:620-637).
 template <int G>
 __device__ __forceinline__ int select_pos_scan(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
                                           int g, uint32_t mask) {
@@ -475,6 +485,16 @@ __device__ __forceinline__ void push_flip(Step<MF>& st, int site, int oldc, int 
   if (st.n < MF) ++st.n;
 }
 
+// floor(a / b) of the EXACT quotient for b > 0: candidate from the rounded division, corrected with the
+// exact FMA remainder.  CPython's float `//` (fmod based, used by WangLandau._get_bin_id) returns the
+// same value; this form needs no iterative fmod.
+__device__ __forceinline__ double exact_floordiv(double a, double b) {
+  double q = floor(a / b);
+  const double r = fma(-q, b, a);
+  if (r < 0.0) q -= 1.0;
+  else if (r >= b) q += 1.0;
+  return q;
+}
 // Python float floor division `a // b` (CPython float_floor_div), used by WangLandau._get_bin_id
 __device__ __forceinline__ double py_floordiv(double a, double b) {
   double mod = fmod(a, b);
@@ -518,6 +538,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   unsigned char* stash0 = priv + a.off_stash;
   int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
   uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
+  uint16_t* eidx = reinterpret_cast<uint16_t*>(priv + a.off_eidx);
   (void)wslab;
 
   stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
@@ -528,6 +549,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // running state
   for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
   double enth = a.enthalpy[w];
+  if (EWALD) {
+    for (int i = g; i < m.N; i += G) eidx[i] = ewald_index(m, i, occ[i]);
+  }
   // species counts per (active sublattice, code) and one bit-plane per code
   for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
   for (int i = g; i < 2 * m.plane_words; i += G) planes[i] = 0u;
@@ -568,6 +592,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // Wang-Landau per-walker state
   double* wlS = nullptr; long long* wlH = nullptr; long long* wlO = nullptr; double* wlM = nullptr;
   double wl_m = 0.0; long long wl_cnt = 0;
+  double cur_fb = -1.0, s_cur = 0.0;   // current bin (floor value) and its entropy, kept in registers
+  const bool wl_sum = a.wl.reserved != 0;  // mean_features buffer holds per-bin SUMS (update_period == 1)
   const int nb = a.wl.num_bins;
   if (wl_mode) {
     wlS = a.wl.entropy_dev + (size_t)w * nb;
@@ -576,6 +602,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     wlM = a.wl.mean_features_dev + (size_t)w * nb * m.F;
     wl_m = a.wl.mod_factor_dev[w];
     wl_cnt = a.wl.steps_counter_dev[w];
+    cur_fb = exact_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
+    s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? __ldcg(wlS + (int)cur_fb) : 0.0;
   }
 
   unsigned long long step = a.step0;
@@ -783,31 +811,36 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       // that their L2 latency overlaps with the rest of the proposal
       RecChunk pre0, pre1;
       bool deferred1 = false;
-      if (st.n > 0) pre0 = load_records<G>(m, st.site[0], g);
-      if (st.n > 1) pre1 = load_records<G>(m, st.site[I1], g);
+      // orbit segments for phase B: prefetched only by the variants that are not register-capped
+      // (high-acceptance workloads: Wang-Landau, Ewald, table flips); the 72-register swap/flip
+      // kernel fetches them on accept
+      constexpr bool SEGPRE = EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP || G < 32;
+      int4 seg0 = make_int4(0, 0, 0, 0), seg1 = make_int4(0, 0, 0, 0);
+      if (st.n > 0) { pre0 = load_records<G>(m, st.site[0], g); if (SEGPRE) seg0 = load_segment<G>(m, st.site[0], g); }
+      if (st.n > 1) { pre1 = load_records<G>(m, st.site[I1], g); if (SEGPRE) seg1 = load_segment<G>(m, st.site[I1], g); }
       if (st.n >= 2 && !a.seq_flips) {
-        if (g == 0) occ[st.site[0]] = (uint8_t)st.newc[0];
+        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) eidx[st.site[0]] = ewald_index(m, st.site[0], st.newc[0]); }
         group_sync<G>(gmask);
         acc = flip_energy_pair<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], st.site[I1], st.oldc[I1],
                                         st.newc[I1], stash0, stash0 + stash_stride, g, pre0, pre1);
         if (EWALD) {
-          acc_ew = flip_ewald<G>(m, occ, st.site[0], st.oldc[0], st.newc[0], g);
-          acc_ew += flip_ewald<G>(m, occ, st.site[I1], st.oldc[I1], st.newc[I1], g);
+          acc_ew = flip_ewald<G>(m, eidx, st.site[0], st.oldc[0], st.newc[0], g);
+          acc_ew += flip_ewald<G>(m, eidx, st.site[I1], st.oldc[I1], st.newc[I1], g);
         }
         // flip 0's records read site 1 (old value): lanes are not guaranteed to run in lockstep, so
         // site 1 may only be written once every lane is done -- after a sync (more flips follow) or
         // after the group reduction below (two-flip step: written on accept only)
         if (st.n > 2) {
           group_sync<G>(gmask);
-          if (g == 0) occ[st.site[I1]] = (uint8_t)st.newc[I1];
+          if (g == 0) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) eidx[st.site[I1]] = ewald_index(m, st.site[I1], st.newc[I1]); }
           group_sync<G>(gmask);
         } else {
           deferred1 = true;
         }
       } else if (st.n >= 1) {
         acc = flip_energy<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], stash0, g, pre0);
-        if (EWALD) acc_ew = flip_ewald<G>(m, occ, st.site[0], st.oldc[0], st.newc[0], g);
-        if (g == 0) occ[st.site[0]] = (uint8_t)st.newc[0];
+        if (EWALD) acc_ew = flip_ewald<G>(m, eidx, st.site[0], st.oldc[0], st.newc[0], g);
+        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) eidx[st.site[0]] = ewald_index(m, st.site[0], st.newc[0]); }
         if (st.n > 1) group_sync<G>(gmask);
       }
 #pragma unroll
@@ -815,8 +848,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         if (f < st.n && (f >= 2 || a.seq_flips)) {
           pre0 = load_records<G>(m, st.site[f], g);
           acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g, pre0);
-          if (EWALD) acc_ew += flip_ewald<G>(m, occ, st.site[f], st.oldc[f], st.newc[f], g);
-          if (g == 0) occ[st.site[f]] = (uint8_t)st.newc[f];
+          if (EWALD) acc_ew += flip_ewald<G>(m, eidx, st.site[f], st.oldc[f], st.newc[f], g);
+          if (g == 0) { occ[st.site[f]] = (uint8_t)st.newc[f]; if (EWALD) eidx[st.site[f]] = ewald_index(m, st.site[f], st.newc[f]); }
           if (f + 1 < st.n) group_sync<G>(gmask);
         }
       }
@@ -832,7 +865,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       if (MU_POSSIBLE && m.muW) dH += nat_mu * dmu;
 
       // ------------------------------ accept --------------------------------------------
-      int new_bin = 0;
+      double new_fb = cur_fb, s_new = s_cur;
       if (!wl_mode) {
         // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
         const double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
@@ -842,21 +875,20 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
                              : exponent > log(u01(philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1).w));
         }
       } else {
-        // WangLandau._accept_step, kernel/wanglandau.py:186-202
+        // WangLandau._accept_step, kernel/wanglandau.py:186-202.  The current bin and its entropy live
+        // in registers (the post-step bin of step t is the pre-step bin of step t+1), so only the
+        // entropy of the NEW bin is loaded.
         const double e_new = enth + dH;
         if (e_new < a.wl.min_enthalpy || e_new >= a.wl.max_enthalpy) {
           accepted = false;
         } else {
-          const int bin = (int)py_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
-          new_bin = (int)py_floordiv(e_new - a.wl.min_enthalpy, a.wl.bin_size);
-          const double s_old = (bin >= 0 && bin < nb) ? __ldcg(wlS + bin) : 0.0;
-          const double s_new = (new_bin >= 0 && new_bin < nb) ? __ldcg(wlS + new_bin) : 0.0;
-          const double exponent = (s_old - s_new) + st.log_priori;
-          {
+          new_fb = exact_floordiv(e_new - a.wl.min_enthalpy, a.wl.bin_size);
+          s_new = new_fb == cur_fb ? s_cur
+                                   : ((new_fb >= 0.0 && new_fb < (double)nb) ? __ldcg(wlS + (int)new_fb) : 0.0);
+          const double exponent = (s_cur - s_new) + st.log_priori;
           const int af = accept_fast(exponent, lf);
           accepted = af >= 0 ? (af != 0)
                              : exponent > log(u01(philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1).w));
-        }
         }
       }
 
@@ -865,9 +897,11 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         // MCKernel._do_accept_step (kernel/base.py:327-343) + trace accumulation (sampler.py:204-207)
 #pragma unroll
         for (int f = 0; f < MF; ++f)
-          if (f < st.n) flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g);
+          if (f < st.n)
+            flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g,
+                                   (SEGPRE && f == 0) ? seg0 : ((SEGPRE && f == 1) ? seg1 : load_segment<G>(m, st.site[f], g)));
         if (g == 0) {
-          if (deferred1) occ[st.site[I1]] = (uint8_t)st.newc[I1];
+          if (deferred1) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) eidx[st.site[I1]] = ewald_index(m, st.site[I1], st.newc[I1]); }
           if (EWALD) feat[m.ewF] += dEw;
           if (MU_POSSIBLE && m.muW) feat[m.muF] += dmu;
 #pragma unroll
@@ -894,36 +928,51 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
             }
           }
         enth += dH;
+        if (wl_mode) { cur_fb = new_fb; s_cur = s_new; }
         ++nacc;
       } else if (st.n > 0) {
         if (g == 0) {
 #pragma unroll
           for (int f = MF - 1; f >= 0; --f)
-            if (f < st.n && !(f == 1 && deferred1)) occ[st.site[f]] = (uint8_t)st.oldc[f];
+            if (f < st.n && !(f == 1 && deferred1)) {
+              occ[st.site[f]] = (uint8_t)st.oldc[f];
+              if (EWALD) eidx[st.site[f]] = ewald_index(m, st.site[f], st.oldc[f]);
+            }
         }
       }
       group_sync<G>(gmask);
 
       if (wl_mode) {
         // WangLandau._do_post_step, kernel/wanglandau.py:222-266
-        const double fb = py_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
-        if (fb >= 0.0 && fb < (double)nb) {
-          const int bin = (int)fb;
+        if (cur_fb >= 0.0 && cur_fb < (double)nb) {
+          const int bin = (int)cur_fb;
           ++wl_cnt;
-          const long long total = __ldcg(wlO + bin);
-          const double inv = 1.0 / (double)(total + 1);
-          for (int f = g; f < m.F; f += G) {
-            double* p = wlM + (size_t)bin * m.F + f;
-            __stcg(p, inv * (feat[f] + (double)total * __ldcg(p)));
+          const bool upd = wl_cnt % a.wl.update_period == 0;
+          if (wl_sum) {
+            // update_period == 1: the running mean (x_n + (n-1) M)/n is sum/n -- accumulate the sum with
+            // fire-and-forget reductions, the host divides by `occurrences`
+            for (int f = g; f < m.F; f += G) atomicAdd(wlM + (size_t)bin * m.F + f, feat[f]);
+            if (g == 0) atomicAdd(reinterpret_cast<unsigned long long*>(wlO + bin), 1ull);
+          } else {
+            const long long total = __ldcg(wlO + bin);
+            const double inv = 1.0 / (double)(total + 1);
+            for (int f = g; f < m.F; f += G) {
+              double* p = wlM + (size_t)bin * m.F + f;
+              __stcg(p, inv * (feat[f] + (double)total * __ldcg(p)));
+            }
+            if (upd && g == 0) __stcg(wlO + bin, total + 1);
           }
-          if (wl_cnt % a.wl.update_period == 0 && g == 0) {
-            __stcg(wlS + bin, __ldcg(wlS + bin) + wl_m);
-            __stcg(wlH + bin, __ldcg(wlH + bin) + 1);
-            __stcg(wlO + bin, total + 1);
+          if (upd) {
+            s_cur += wl_m;
+            if (g == 0) {
+              __stcg(wlS + bin, s_cur);
+              atomicAdd(reinterpret_cast<unsigned long long*>(wlH + bin), 1ull);
+            }
           }
-          group_sync<G>(gmask);
         }
         if (wl_cnt % a.wl.check_period == 0) {
+          __threadfence_block();
+          group_sync<G>(gmask);   // lane 0's entropy/histogram updates are visible to the group
           int nvis = 0;
           double hsum = 0.0, hmin = 1e300;
           for (int b = g; b < nb; b += G)
@@ -1002,6 +1051,9 @@ __global__ void lmc_delta_kernel(const DevModel m, const int8_t* __restrict__ oc
   const SmemTables t = smem_tables(m, smem);
   if (wl_ >= wpb || w >= W) return;
   for (int f = g; f < m.F; f += G) feat[f] = 0.0;
+  uint16_t* eidx = reinterpret_cast<uint16_t*>(stash + ((m.Rstride * 8 + 15) & ~15));
+  if (m.E)
+    for (int i = g; i < m.N; i += G) eidx[i] = ewald_index(m, i, occ[i]);
   group_sync<G>(gmask);
   double dmu = 0.0, dew = 0.0;
   for (int f = 0; f < nflips; ++f) {
@@ -1010,10 +1062,10 @@ __global__ void lmc_delta_kernel(const DevModel m, const int8_t* __restrict__ oc
     // chemical work against the PRE-step occupancy (ensemble.py:369-373)
     if (m.muW) dmu += m.mu[site * m.muW + newc] - m.mu[site * m.muW + (int)occ_g[(size_t)w * m.Npad + site]];
     (void)flip_energy<G, KONE>(m, t, occ, site, oldc, newc, stash, g, load_records<G>(m, site, g));
-    if (m.E) dew += flip_ewald<G>(m, occ, site, oldc, newc, g);
+    if (m.E) dew += flip_ewald<G>(m, eidx, site, oldc, newc, g);
     group_sync<G>(gmask);
-    flip_features<G, KONE>(m, t, site, stash, feat, g);
-    if (g == 0) occ[site] = (uint8_t)newc;
+    flip_features<G, KONE>(m, t, site, stash, feat, g, load_segment<G>(m, site, g));
+    if (g == 0) { occ[site] = (uint8_t)newc; if (m.E) eidx[site] = ewald_index(m, site, newc); }
     group_sync<G>(gmask);
   }
   if (m.E) dew = group_sum<G>(dew, gmask);

@@ -27,8 +27,8 @@ struct DevModel {
   int blob_bytes, off_coef, off_tabA, off_nat, off_orb;
   const double* ftab;      // global copy of all feature tensors (phase B when K > 1, full evaluation)
   const uint2* site_rec;   // [N][Rstride] (idx0 | idx1<<16, idx2 | cls<<16), padded per site
-  const int4* site_seg;    // [segments] (first, count, orbit, 0)
-  const int* site_seg_off; // [N+1]
+  const int4* site_seg;    // [N][Sstride] (first, count, orbit, 0); count 0 = padding
+  int Sstride;             // orbit segments per site (max over sites)
   const uint2* full_rows;  // [rows] 4 x u16 site indices
   // Ewald
   int E, ewW, ewF;
@@ -75,7 +75,7 @@ struct RunArgs {
   LmcWangLandau wl;
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
-  int off_feat, off_stash, off_cnt, off_plane, off_ring;  // offsets inside a walker's shared-memory slab
+  int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx;  // offsets inside a walker's shared-memory slab
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another
 };

@@ -234,7 +234,14 @@ class Sampler:
         """Per-walker arrays (entropy, histogram, occurrences, mean_features, mod_factor) on host."""
         if self._wl_state is None:
             return None
-        return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in self._wl_state.items()}
+        out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in self._wl_state.items()}
+        if int(self._wl["update_period"]) == 1:
+            # the device accumulates per-bin feature SUMS; with update_period == 1 the reference's running
+            # mean (wanglandau.py:234-238) equals sum / occurrences
+            occ = out["occurrences"].astype(np.float64)[:, :, None]
+            out["mean_features"] = np.divide(out["mean_features"], occ, out=np.zeros_like(out["mean_features"]),
+                                             where=occ > 0)
+        return out
 
     # ---- run (sampler.py:164-297, 386-434) ------------------------------------------------------------
     def run(self, nsteps, initial_occupancies=None, thin_by=1, progress=False, stream_chunk=0,
@@ -304,6 +311,7 @@ class Sampler:
                 wl.flatness = p["flatness"]
                 wl.mod_update = float(p["mod_update"]) if p.get("mod_update") is not None else 2.0
                 wl.num_bins, wl.check_period, wl.update_period = len(st["levels"]), p["check_period"], p["update_period"]
+                wl.reserved = 1 if int(p["update_period"]) == 1 else 0   # mean_features buffer holds sums
                 wl.entropy_dev, wl.histogram_dev = st["entropy"].data_ptr(), st["histogram"].data_ptr()
                 wl.occurrences_dev, wl.mean_features_dev = st["occurrences"].data_ptr(), st["mean_features"].data_ptr()
                 wl.mod_factor_dev, wl.steps_counter_dev = st["mod_factor"].data_ptr(), st["steps_counter"].data_ptr()
