@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
 #include <atomic>
@@ -11,6 +12,7 @@
 #define LMC_API_TU
 #include "lmc_kernels.cuh"
 #include "lmc_launch.h"
+#define LMC_PLANE_COPIES (LMC_OPT_PFX ? 2 : 1)
 
 using namespace lmc;
 
@@ -130,6 +132,85 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       }
     }
   }
+  std::vector<double> qtab;
+  // Ewald.  Generic form: keep the TRANSPOSE so that the reference's column gathers become row
+  // gathers.  Ewald matrices are charge products times a geometric site kernel,
+  // M[i,j] = q_i q_j K[site_i, site_j] (pymatgen EwaldSummation), which turns the two strided E-long
+  // row gathers of a flip into ONE contiguous N-long row; detected here, verified entry by entry.
+  m.E = d->ewald_size;
+  if (m.E >= 65535) { lmc_model_destroy(mdl); return fail("Ewald matrices with 65535 or more rows are not supported (u16 row cache)"); }
+  if (m.E > 0) {
+    m.ewW = d->ewald_width;
+    m.ewF = d->ewald_feature;
+    const size_t E = (size_t)m.E, N = (size_t)m.N;
+    const double* M = d->ewald_matrix;
+    bool fact = true;
+    if (const char* e = getenv("LMC_EWALD_FACTORIZE")) fact = atoi(e) != 0;
+    std::vector<int> row_site(E, -1), site_ref(N, -1);
+    for (size_t k = 0; k < N && fact; ++k)
+      for (int c = 0; c < m.ewW; ++c) {
+        const int e = d->ewald_inds[k * m.ewW + c];
+        if (e < 0) continue;
+        if ((size_t)e >= E || row_site[e] >= 0) { fact = false; break; }
+        row_site[e] = (int)k;
+        if (site_ref[k] < 0) site_ref[k] = e;
+      }
+    for (size_t e = 0; e < E && fact; ++e) fact = row_site[e] >= 0;
+    std::vector<double> q(E, 0.0), dg(E, 0.0), K;
+    double mmax = 0.0;
+    if (fact) {
+      for (size_t i = 0; i < E * E; ++i) mmax = std::max(mmax, fabs(M[i]));
+      // relative charge of row i w.r.t. the reference row of its site, from the column where the
+      // reference row is largest (on another site)
+      for (size_t i = 0; i < E && fact; ++i) {
+        const int ref = site_ref[row_site[i]];
+        size_t jbest = 0; double best = -1.0;
+        for (size_t j = 0; j < E; ++j)
+          if (row_site[j] != row_site[i] && fabs(M[(size_t)ref * E + j]) > best) { best = fabs(M[(size_t)ref * E + j]); jbest = j; }
+        if (!(best > 1e-12 * mmax)) { fact = false; break; }
+        q[i] = M[i * E + jbest] / M[(size_t)ref * E + jbest];
+        dg[i] = M[i * E + i];
+      }
+    }
+    if (fact) {
+      K.assign(N * N, 0.0);
+      for (size_t s = 0; s < N; ++s)
+        for (size_t t = 0; t < N; ++t)
+          if (s != t && site_ref[s] >= 0 && site_ref[t] >= 0) K[s * N + t] = M[(size_t)site_ref[s] * E + site_ref[t]];
+      const double tol = 1e-12 * mmax;
+      for (size_t i = 0; i < E && fact; ++i)
+        for (size_t j = 0; j < E; ++j) {
+          if (row_site[i] == row_site[j]) continue;
+          if (fabs(M[i * E + j] - q[i] * q[j] * K[(size_t)row_site[i] * N + row_site[j]]) > tol ||
+              fabs(M[i * E + j] - M[j * E + i]) > tol) { fact = false; break; }
+        }
+    }
+    std::vector<uint8_t> qidx(E, 0);
+    if (fact) {   // distinct charge values -> byte index (shared-memory table), else stay generic
+      for (size_t i = 0; i < E && fact; ++i) {
+        size_t f = 0;
+        while (f < qtab.size() && qtab[f] != q[i]) ++f;
+        if (f == qtab.size()) { if (qtab.size() >= 255) { fact = false; break; } qtab.push_back(q[i]); }
+        qidx[i] = (uint8_t)f;
+      }
+    }
+    if (fact) {
+      m.ewNQ = (int)qtab.size();
+      qtab.push_back(0.0);   // vacancy
+      UP(double, K.data(), N * N, m.ewK);
+      UP(double, q.data(), E, m.ewQ);
+      UP(double, dg.data(), E, m.ewD);
+      UP(uint8_t, qidx.data(), E, m.ewQidx);
+      m.ewMt = nullptr;
+    } else {
+      qtab.clear();
+      std::vector<double> mt(E * E);
+      for (size_t i = 0; i < E; ++i)
+        for (size_t j = 0; j < E; ++j) mt[j * E + i] = M[i * E + j];
+      UP(double, mt.data(), E * E, m.ewMt);
+    }
+    UP(int, d->ewald_inds, (size_t)m.N * m.ewW, m.ewInds);
+  }
   // blob: cls (nCls + 1 entries, the last is the all-zero padding class) | tabA | nat | orb
   {
     const int C = m.nCls + 1;
@@ -139,6 +220,7 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     m.off_tabA = (int)off; off += ((size_t)tabA_len * 8 + 15) & ~size_t(15);
     m.off_nat = (int)off; off += ((size_t)m.F * 8 + 15) & ~size_t(15);
     m.off_orb = (int)off; off += ((size_t)m.nOrb * sizeof(OrbDev) + 15) & ~size_t(15);
+    m.off_qtab = (int)off; off += ((size_t)std::max<size_t>(qtab.size(), 2) * 8 + 15) & ~size_t(15);
     m.blob_bytes = (int)off;
     std::vector<unsigned char> blob(off, 0);
     uint32_t* cls = reinterpret_cast<uint32_t*>(blob.data() + off_cls);
@@ -158,6 +240,7 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     memcpy(blob.data() + m.off_tabA, tabA.data(), (size_t)tabA_len * 8);
     memcpy(blob.data() + m.off_nat, d->natural_parameters, (size_t)m.F * 8);
     memcpy(blob.data() + m.off_orb, orbs.data(), (size_t)m.nOrb * sizeof(OrbDev));
+    if (!qtab.empty()) memcpy(blob.data() + m.off_qtab, qtab.data(), qtab.size() * 8);
     UP(unsigned char, blob.data(), blob.size(), m.blob);
   }
   UP(OrbDev, orbs.data(), orbs.size(), mdl->orb_dev);
@@ -188,19 +271,6 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
             make_int4(d->site_seg[q * 3], d->site_seg[q * 3 + 1], d->site_seg[q * 3 + 2], 0);
     UP(int4, segs.data(), segs.size(), m.site_seg);
     UP(uint2, d->full_rows, d->orb_row_off[m.nOrb], m.full_rows);
-  }
-  // Ewald: keep the TRANSPOSE so that column gathers of the reference become row gathers
-  m.E = d->ewald_size;
-  if (m.E >= 65535) { lmc_model_destroy(mdl); return fail("Ewald matrices with 65535 or more rows are not supported (u16 row cache)"); }
-  if (m.E > 0) {
-    m.ewW = d->ewald_width;
-    m.ewF = d->ewald_feature;
-    const size_t E = (size_t)m.E;
-    std::vector<double> mt(E * E);
-    for (size_t i = 0; i < E; ++i)
-      for (size_t j = 0; j < E; ++j) mt[j * E + i] = d->ewald_matrix[i * E + j];
-    UP(double, mt.data(), E * E, m.ewMt);
-    UP(int, d->ewald_inds, (size_t)m.N * m.ewW, m.ewInds);
   }
   m.muW = d->mu_width;
   if (m.muW > 0) {
@@ -251,6 +321,13 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     m.tf_dim_code[k] = d->tf_dim_code[k];
   }
   m.tf_sw = d->tf_swap_weight;
+  {
+    int maxn = 1;
+    for (int k = 0; k < m.tfD; ++k) maxn = std::max(maxn, m.tf_max_n[k]);
+    std::vector<double> lg(maxn + 2);
+    for (int n = 0; n < maxn + 2; ++n) lg[n] = lgamma((double)n + 1.0);   // gammaln(n + 1), mcusher.py:705-709
+    UP(double, lg.data(), lg.size(), m.lgam);
+  }
 #undef UP
   *out = mdl;
   return 0;
@@ -334,8 +411,11 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (G != 4 && G != 8 && G != 16 && G != 32) return fail("group_size must be 4, 8, 16 or 32");
   int threads = c->block_threads;
   if (const char* e = getenv("LMC_BLOCK_THREADS")) { if (threads == 0) threads = atoi(e); }
+  const bool relaxed = ewald || c->kernel == LMC_KERNEL_WANGLANDAU || c->usher == LMC_USHER_TABLEFLIP;
+  const int max_threads = relaxed ? 256 : 128;
+  const bool auto_threads = threads == 0;
   if (threads == 0) threads = 128;
-  if (threads % 32 || threads > 128) return fail("block_threads must be 32, 64, 96 or 128");
+  if (threads % 32 || threads > max_threads) return fail("block_threads must be a multiple of 32 (<= 128, or <= 256 for Ewald / Wang-Landau / table-flip kernels)");
 
   RunArgs a;
   memset(&a, 0, sizeof(a));
@@ -364,11 +444,27 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (a.max_flips > LMC_MAX_FLIPS) return fail("flip table changes more than 4 sites per step");
   a.off_cnt = a.off_stash + (int)(((size_t)a.max_flips * m.Rstride * stash_el + 15) & ~size_t(15));
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
-  a.off_ring = a.off_plane + ((2 * m.plane_words * 4 + 15) & ~15);  // planes + prefix popcounts
+  a.off_ring = a.off_plane + ((LMC_PLANE_COPIES * m.plane_words * 4 + 15) & ~15);  // planes (+ prefix popcounts)
   a.off_eidx = a.off_ring + G * 16;                                   // per-lane precomputed proposals
-  a.walker_smem = a.off_eidx + (ewald ? ((2 * m.N + 15) & ~15) : 0);  // cached Ewald row index per site
+  a.walker_smem = a.off_eidx + (ewald ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
+  if (auto_threads && relaxed) {
+    // shared memory limits residency here: take the block size with the most resident walkers per SM
+    // (fewest waves); 16 warps/SM is the register ceiling of these variants
+    const size_t sm_smem = 227 * 1024;
+    int best_t = 0; long best_w = -1;
+    for (int t = G; t <= max_threads; t += G) {
+      if (t % 32) continue;
+      const size_t bs = blob + (size_t)(t / G) * (m.Npad + a.walker_smem);
+      if ((int)bs > mdl->smem_optin - 1024) break;
+      long blocks = (long)(sm_smem / (bs + 1024));
+      blocks = std::min(blocks, (long)(512 / t));
+      const long wsm = blocks * (t / G);
+      if (wsm > best_w) { best_w = wsm; best_t = t; }
+    }
+    if (best_t) threads = best_t;
+  }
   for (;;) {
     a.wpb = threads / G;
     smem = blob + (size_t)a.wpb * (m.Npad + a.walker_smem);

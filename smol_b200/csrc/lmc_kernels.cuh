@@ -13,6 +13,7 @@ struct SmemTables {
   const double* tabA;   // phase-A table
   const double* nat;    // natural parameters
   const OrbDev* orb;
+  const double* qtab;   // distinct charge values of the factorised Ewald matrix (+ 0.0 for vacancies)
 };
 
 __device__ __forceinline__ SmemTables smem_tables(const DevModel& m, const unsigned char* base) {
@@ -22,6 +23,7 @@ __device__ __forceinline__ SmemTables smem_tables(const DevModel& m, const unsig
   t.tabA = reinterpret_cast<const double*>(base + m.off_tabA);
   t.nat = reinterpret_cast<const double*>(base + m.off_nat);
   t.orb = reinterpret_cast<const OrbDev*>(base + m.off_orb);
+  t.qtab = reinterpret_cast<const double*>(base + m.off_qtab);
   return t;
 }
 
@@ -232,16 +234,32 @@ __device__ __forceinline__ void flip_features(const DevModel& m, const SmemTable
     fold_segment<KONE>(m, t, __ldg(m.site_seg + (size_t)site * m.Sstride + sidx), stash, feat);
 }
 
-// Ewald energy change of one flip: row gather over the (transposed) Ewald matrix.
-// Restates delta_ewald_single_flip (smol/utils/cluster/ewald.pyx:9-59); lanes stride over sites.
-// `eidx[k]` caches ewald_inds[k, occ[k]] per walker (0xFFFF = vacancy, no matrix row) so that the
-// inner loop is one shared-memory load and two independent matrix gathers, unrolled for
-// memory-level parallelism (the two rows are 2 x 8 x E bytes of HBM/L2 traffic per flip).
+// Ewald energy change of one flip (delta_ewald_single_flip, smol/utils/cluster/ewald.pyx:9-59); lanes
+// stride over sites.  Two forms:
+//  * factorised matrix M[i,j] = q_i q_j K[site_i, site_j] (what an Ewald summation produces; detected
+//    and verified entry by entry at model creation):
+//        dE = 2 (q_add - q_sub) sum_k q_k K[site, k] + M[add,add] - M[sub,sub]        (K[s,s] = 0)
+//    `ecache` holds one byte per site: the index of the site's current charge in a small table
+//    (shared memory); the inner loop is LDS.U8 + LDS.64 + one fully coalesced LDG + DFMA;
+//  * generic symmetric matrix: `ecache` holds the u16 matrix row of each site's current species
+//    (0xFFFF = vacancy) and the loop gathers the two (transposed) rows `add` and `sub`.
 template <int G>
-__device__ __forceinline__ double flip_ewald(const DevModel& m, const uint16_t* eidx, int site, int olda, int newb,
-                                             int g) {
+__device__ __forceinline__ double flip_ewald(const DevModel& m, const SmemTables& t, const void* ecache, int site,
+                                             int olda, int newb, int g) {
   const int add = __ldg(m.ewInds + site * m.ewW + newb);
   const int sub = __ldg(m.ewInds + site * m.ewW + olda);
+  if (m.ewK) {
+    const uint8_t* qi = reinterpret_cast<const uint8_t*>(ecache);
+    const double qa = add >= 0 ? __ldg(m.ewQ + add) : 0.0, qs = sub >= 0 ? __ldg(m.ewQ + sub) : 0.0;
+    const double* krow = m.ewK + (size_t)site * m.N;
+    double accf = 0.0;
+#pragma unroll 8
+    for (int k = g; k < m.N; k += G) accf += t.qtab[qi[k]] * __ldg(krow + k);
+    accf *= 2.0 * (qa - qs);
+    if (g == 0) accf += (add >= 0 ? __ldg(m.ewD + add) : 0.0) - (sub >= 0 ? __ldg(m.ewD + sub) : 0.0);
+    return accf;
+  }
+  const uint16_t* eidx = reinterpret_cast<const uint16_t*>(ecache);
   const double* rowA = m.ewMt + (size_t)(add < 0 ? 0 : add) * m.E;
   const double* rowS = m.ewMt + (size_t)(sub < 0 ? 0 : sub) * m.E;
   const double ca = add >= 0 ? 2.0 : 0.0, cs = sub >= 0 ? 2.0 : 0.0;
@@ -262,9 +280,11 @@ __device__ __forceinline__ double flip_ewald(const DevModel& m, const uint16_t* 
   }
   return acc;
 }
-__device__ __forceinline__ uint16_t ewald_index(const DevModel& m, int site, int code) {
+// refresh the per-walker Ewald cache entry of `site` after its code changed
+__device__ __forceinline__ void ewald_cache_set(const DevModel& m, void* ecache, int site, int code) {
   const int e = __ldg(m.ewInds + site * m.ewW + code);
-  return e < 0 ? (uint16_t)0xffffu : (uint16_t)e;
+  if (m.ewK) reinterpret_cast<uint8_t*>(ecache)[site] = e < 0 ? (uint8_t)m.ewNQ : __ldg(m.ewQidx + e);
+  else reinterpret_cast<uint16_t*>(ecache)[site] = e < 0 ? (uint16_t)0xffffu : (uint16_t)e;
 }
 
 template <int G>
@@ -513,7 +533,8 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // num_samples * thin_by attempted steps per walker in ONE launch.
 // ------------------------------------------------------------------------------------------
 template <int G, bool KONE, bool EWALD, int USHER, bool WLMODE>
-__global__ void __launch_bounds__(128, (EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 4 : (G < 32 ? 5 : 7))
+__global__ void __launch_bounds__((EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 256 : 128,
+                                  (EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7))
 lmc_run_kernel(const DevModel m, const RunArgs a) {
   constexpr int MF = USHER == LMC_USHER_FLIP ? 1 : (USHER == LMC_USHER_SWAP ? 2 : LMC_MAX_FLIPS);
   constexpr int I1 = MF > 1 ? 1 : 0;   // index of the second flip (dead code when MF == 1)
@@ -538,7 +559,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   unsigned char* stash0 = priv + a.off_stash;
   int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
   uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
-  uint16_t* eidx = reinterpret_cast<uint16_t*>(priv + a.off_eidx);
+  void* eidx = priv + a.off_eidx;   // per-walker Ewald cache (see flip_ewald)
   (void)wslab;
 
   stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
@@ -550,11 +571,11 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
   double enth = a.enthalpy[w];
   if (EWALD) {
-    for (int i = g; i < m.N; i += G) eidx[i] = ewald_index(m, i, occ[i]);
+    for (int i = g; i < m.N; i += G) ewald_cache_set(m, eidx, i, occ[i]);
   }
   // species counts per (active sublattice, code) and one bit-plane per code
   for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
-  for (int i = g; i < 2 * m.plane_words; i += G) planes[i] = 0u;
+  for (int i = g; i < (LMC_OPT_PFX ? 2 : 1) * m.plane_words; i += G) planes[i] = 0u;
   group_sync<G>(gmask);
   for (int sl = 0; sl < m.nSl; ++sl) {
     const int n_act = m.sl_off[sl + 1] - m.sl_off[sl], nw = m.sl_nwords[sl];
@@ -800,7 +821,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         const double p_next = (1.0 - m.tf_sw) * tfw2[tf_idx ^ 1] / sum2;
         double lf = log(p_next / p_now);
         for (int d = 0; d < m.tfD; ++d)
-          if (urow[d] != 0) lf += lgamma((double)nd[d] + 1.0) - lgamma((double)nn[d] + 1.0);
+          if (urow[d] != 0) lf += __ldg(m.lgam + nd[d]) - __ldg(m.lgam + nn[d]);   // ln n! table (gammaln(n+1))
         st.log_priori = lf;
       }
 
@@ -819,28 +840,28 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       if (st.n > 0) { pre0 = load_records<G>(m, st.site[0], g); if (SEGPRE) seg0 = load_segment<G>(m, st.site[0], g); }
       if (st.n > 1) { pre1 = load_records<G>(m, st.site[I1], g); if (SEGPRE) seg1 = load_segment<G>(m, st.site[I1], g); }
       if (st.n >= 2 && !a.seq_flips) {
-        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) eidx[st.site[0]] = ewald_index(m, st.site[0], st.newc[0]); }
+        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) ewald_cache_set(m, eidx, st.site[0], st.newc[0]); }
         group_sync<G>(gmask);
         acc = flip_energy_pair<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], st.site[I1], st.oldc[I1],
                                         st.newc[I1], stash0, stash0 + stash_stride, g, pre0, pre1);
         if (EWALD) {
-          acc_ew = flip_ewald<G>(m, eidx, st.site[0], st.oldc[0], st.newc[0], g);
-          acc_ew += flip_ewald<G>(m, eidx, st.site[I1], st.oldc[I1], st.newc[I1], g);
+          acc_ew = flip_ewald<G>(m, t, eidx, st.site[0], st.oldc[0], st.newc[0], g);
+          acc_ew += flip_ewald<G>(m, t, eidx, st.site[I1], st.oldc[I1], st.newc[I1], g);
         }
         // flip 0's records read site 1 (old value): lanes are not guaranteed to run in lockstep, so
         // site 1 may only be written once every lane is done -- after a sync (more flips follow) or
         // after the group reduction below (two-flip step: written on accept only)
         if (st.n > 2) {
           group_sync<G>(gmask);
-          if (g == 0) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) eidx[st.site[I1]] = ewald_index(m, st.site[I1], st.newc[I1]); }
+          if (g == 0) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) ewald_cache_set(m, eidx, st.site[I1], st.newc[I1]); }
           group_sync<G>(gmask);
         } else {
           deferred1 = true;
         }
       } else if (st.n >= 1) {
         acc = flip_energy<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], stash0, g, pre0);
-        if (EWALD) acc_ew = flip_ewald<G>(m, eidx, st.site[0], st.oldc[0], st.newc[0], g);
-        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) eidx[st.site[0]] = ewald_index(m, st.site[0], st.newc[0]); }
+        if (EWALD) acc_ew = flip_ewald<G>(m, t, eidx, st.site[0], st.oldc[0], st.newc[0], g);
+        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) ewald_cache_set(m, eidx, st.site[0], st.newc[0]); }
         if (st.n > 1) group_sync<G>(gmask);
       }
 #pragma unroll
@@ -848,8 +869,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         if (f < st.n && (f >= 2 || a.seq_flips)) {
           pre0 = load_records<G>(m, st.site[f], g);
           acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g, pre0);
-          if (EWALD) acc_ew += flip_ewald<G>(m, eidx, st.site[f], st.oldc[f], st.newc[f], g);
-          if (g == 0) { occ[st.site[f]] = (uint8_t)st.newc[f]; if (EWALD) eidx[st.site[f]] = ewald_index(m, st.site[f], st.newc[f]); }
+          if (EWALD) acc_ew += flip_ewald<G>(m, t, eidx, st.site[f], st.oldc[f], st.newc[f], g);
+          if (g == 0) { occ[st.site[f]] = (uint8_t)st.newc[f]; if (EWALD) ewald_cache_set(m, eidx, st.site[f], st.newc[f]); }
           if (f + 1 < st.n) group_sync<G>(gmask);
         }
       }
@@ -901,7 +922,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
             flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g,
                                    (SEGPRE && f == 0) ? seg0 : ((SEGPRE && f == 1) ? seg1 : load_segment<G>(m, st.site[f], g)));
         if (g == 0) {
-          if (deferred1) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) eidx[st.site[I1]] = ewald_index(m, st.site[I1], st.newc[I1]); }
+          if (deferred1) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) ewald_cache_set(m, eidx, st.site[I1], st.newc[I1]); }
           if (EWALD) feat[m.ewF] += dEw;
           if (MU_POSSIBLE && m.muW) feat[m.muF] += dmu;
 #pragma unroll
@@ -936,7 +957,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           for (int f = MF - 1; f >= 0; --f)
             if (f < st.n && !(f == 1 && deferred1)) {
               occ[st.site[f]] = (uint8_t)st.oldc[f];
-              if (EWALD) eidx[st.site[f]] = ewald_index(m, st.site[f], st.oldc[f]);
+              if (EWALD) ewald_cache_set(m, eidx, st.site[f], st.oldc[f]);
             }
         }
       }
@@ -1051,9 +1072,9 @@ __global__ void lmc_delta_kernel(const DevModel m, const int8_t* __restrict__ oc
   const SmemTables t = smem_tables(m, smem);
   if (wl_ >= wpb || w >= W) return;
   for (int f = g; f < m.F; f += G) feat[f] = 0.0;
-  uint16_t* eidx = reinterpret_cast<uint16_t*>(stash + ((m.Rstride * 8 + 15) & ~15));
+  void* eidx = stash + ((m.Rstride * 8 + 15) & ~15);
   if (m.E)
-    for (int i = g; i < m.N; i += G) eidx[i] = ewald_index(m, i, occ[i]);
+    for (int i = g; i < m.N; i += G) ewald_cache_set(m, eidx, i, occ[i]);
   group_sync<G>(gmask);
   double dmu = 0.0, dew = 0.0;
   for (int f = 0; f < nflips; ++f) {
@@ -1062,10 +1083,10 @@ __global__ void lmc_delta_kernel(const DevModel m, const int8_t* __restrict__ oc
     // chemical work against the PRE-step occupancy (ensemble.py:369-373)
     if (m.muW) dmu += m.mu[site * m.muW + newc] - m.mu[site * m.muW + (int)occ_g[(size_t)w * m.Npad + site]];
     (void)flip_energy<G, KONE>(m, t, occ, site, oldc, newc, stash, g, load_records<G>(m, site, g));
-    if (m.E) dew += flip_ewald<G>(m, eidx, site, oldc, newc, g);
+    if (m.E) dew += flip_ewald<G>(m, t, eidx, site, oldc, newc, g);
     group_sync<G>(gmask);
     flip_features<G, KONE>(m, t, site, stash, feat, g, load_segment<G>(m, site, g));
-    if (g == 0) { occ[site] = (uint8_t)newc; if (m.E) eidx[site] = ewald_index(m, site, newc); }
+    if (g == 0) { occ[site] = (uint8_t)newc; if (m.E) ewald_cache_set(m, eidx, site, newc); }
     group_sync<G>(gmask);
   }
   if (m.E) dew = group_sum<G>(dew, gmask);
@@ -1133,7 +1154,10 @@ __global__ void lmc_full_kernel(const DevModel m, const int8_t* __restrict__ occ
     for (long long q = threadIdx.x; q < np; q += blockDim.x) {
       const int i = (int)(q / m.N), j = (int)(q % m.N);
       const int a = eidx[i], b = eidx[j];
-      if (a >= 0 && b >= 0) p += __ldg(m.ewMt + (size_t)a * m.E + b);
+      if (a >= 0 && b >= 0) {
+        if (m.ewK) p += i == j ? __ldg(m.ewD + a) : __ldg(m.ewQ + a) * __ldg(m.ewQ + b) * __ldg(m.ewK + q);
+        else p += __ldg(m.ewMt + (size_t)a * m.E + b);
+      }
     }
     p = block_sum(p, red);
     if (threadIdx.x == 0) out[m.ewF] = p;

@@ -24,7 +24,7 @@ struct DevModel {
   // shared-memory blob (staged once per block by TMA): [cls uint4 x nCls][coef double x nCls]
   // [tabA double x tabA_len][nat double x F][orb OrbDev x nOrb]
   const unsigned char* blob;
-  int blob_bytes, off_coef, off_tabA, off_nat, off_orb;
+  int blob_bytes, off_coef, off_tabA, off_nat, off_orb, off_qtab;
   const double* ftab;      // global copy of all feature tensors (phase B when K > 1, full evaluation)
   const uint2* site_rec;   // [N][Rstride] (idx0 | idx1<<16, idx2 | cls<<16), padded per site
   const int4* site_seg;    // [N][Sstride] (first, count, orbit, 0); count 0 = padding
@@ -34,6 +34,12 @@ struct DevModel {
   int E, ewW, ewF;
   const double* ewMt;      // [E][E] TRANSPOSED matrix: ewMt[a*E + i] == M[i][a]
   const int* ewInds;       // [N][ewW]
+  // factorised form (when M[i,j] == q_i q_j K[site_i, site_j] off the site-diagonal blocks):
+  const double* ewK;       // [N][N] site kernel, nullptr when the matrix does not factorise
+  const double* ewQ;       // [E] relative charge of a matrix row
+  const double* ewD;       // [E] diagonal M[i,i]
+  const uint8_t* ewQidx;   // [E] index of the row's charge in the shared-memory charge table
+  int ewNQ;                // number of distinct charges; index ewNQ is the 0.0 used for vacancies
   // chemical potentials
   int muW, muF;
   const double* mu;        // [N][muW]
@@ -55,6 +61,7 @@ struct DevModel {
   int tf_dim_sl[LMC_MAX_DIMS];
   int tf_dim_code[LMC_MAX_DIMS];
   double tf_sw;
+  const double* lgam;      // [max_n + 2] ln(n!) table for the table-flip a-priori factor
 };
 
 struct RunArgs {

@@ -132,7 +132,11 @@ def test_canonical_swap_trajectory(cuda_device, kind, n, group):
     assert 0 < smp.samples.step_efficiency() <= 1
 
 
-def test_semigrand_ewald_flip_trajectory(cuda_device):
+@pytest.mark.parametrize("factorize", ["1", "0", "random"])
+def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
+    """factorize=1: M = q q^T x K fast path; 0: generic transposed-row gather; random: a symmetric matrix
+    that does NOT factorise (the library must detect that and fall back)."""
+    monkeypatch.setenv("LMC_EWALD_FACTORIZE", "0" if factorize == "0" else "1")
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
@@ -142,6 +146,9 @@ def test_semigrand_ewald_flip_trajectory(cuda_device):
     coefs = rng.normal(0, 0.05, sub.num_corr_functions)
     it = L.cluster_interaction_tensors(sub, coefs)
     ewm, ewi = L.ewald_matrix(sub, scm)
+    if factorize == "random":
+        r = np.random.default_rng(0).normal(0, 1.0, ewm.shape)
+        ewm = 0.5 * (r + r.T)
     comp = S.CompositeProcessor(sub, scm)
     comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
     comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.1, ewald_matrix=ewm, ewald_inds=ewi))
@@ -194,8 +201,9 @@ def test_wang_landau_flip_trajectory(cuda_device):
     assert (st["mod_factor"] < 1.0).any(), "flatness was never reached; weak test"
 
 
-@pytest.mark.parametrize("group", [8, 32])
-def test_table_flip_ewald_semigrand_trajectory(cuda_device, group):
+@pytest.mark.parametrize("group,factorize", [(8, "1"), (32, "1"), (32, "0")])
+def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, monkeypatch):
+    monkeypatch.setenv("LMC_EWALD_FACTORIZE", factorize)
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
