@@ -826,6 +826,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       }
 
       // ------------------------------ evaluate ------------------------------------------
+      // lanes of a group are not assumed to run in lockstep: all reads of the proposal phase are
+      // complete before lane 0 starts writing flips into the occupancy
+      group_sync<G>(gmask);
       double acc = 0.0, acc_ew = 0.0, dmu = 0.0;
       constexpr bool MU_POSSIBLE = USHER != LMC_USHER_SWAP;  // a swap leaves the chemical work unchanged
       // the cluster records depend on the sites only: fetch the first two flips' records up front so
@@ -914,6 +917,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       }
 
       // ------------------------------ update --------------------------------------------
+      group_sync<G>(gmask);   // every lane has finished reading the occupancy / caches of this step
       if (accepted) {
         // MCKernel._do_accept_step (kernel/base.py:327-343) + trace accumulation (sampler.py:204-207)
 #pragma unroll
