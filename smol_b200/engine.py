@@ -52,7 +52,9 @@ class LmcEngine:
     def upload_occupancy(self, occ_host: np.ndarray):
         """int32 ``[W, N]`` host array -> int8 ``[W, row_stride]`` device tensor."""
         torch = _torch()
-        occ_host = np.ascontiguousarray(occ_host, dtype=np.int32)
+        occ_host = np.asarray(occ_host)
+        if occ_host.dtype.kind not in "iu":
+            occ_host = occ_host.astype(np.int32)      # raises for non-numeric input like the reference
         W = occ_host.shape[0]
         key = tuple(occ_host.shape)
         if getattr(self, "_pin_key", None) != key:   # cached page-locked H2D staging buffer
@@ -60,7 +62,7 @@ class LmcEngine:
             self._pin_key = key
         if getattr(self, "_pin_evt", None) is not None:
             self._pin_evt.synchronize()          # the previous async copy has consumed the buffer
-        self._pin_buf.numpy()[...] = occ_host
+        np.copyto(self._pin_buf.numpy(), occ_host, casting="unsafe")   # one pass: copy + int32 conversion
         src = self._pin_buf.to(self.device, non_blocking=True)
         self._pin_evt = torch.cuda.Event()
         self._pin_evt.record(torch.cuda.current_stream(self.device))

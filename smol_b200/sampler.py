@@ -20,6 +20,25 @@ from .container import SampleContainer
 
 kB = 8.617333262145e-5  # smol/constants.py:4
 
+_POOL = None
+
+
+def _fast_copy(src: np.ndarray) -> np.ndarray:
+    """Copy out of the page-locked staging buffer; large arrays are split over a few threads
+    (numpy releases the GIL in copyto, and the page faults of the fresh destination parallelise)."""
+    global _POOL
+    dst = np.empty_like(src)
+    if src.nbytes < (4 << 20) or src.shape[0] < 2:
+        np.copyto(dst, src)
+        return dst
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4)
+    parts = min(4, src.shape[0])
+    bounds = np.linspace(0, src.shape[0], parts + 1).astype(int)
+    list(_POOL.map(lambda ab: np.copyto(dst[ab[0]:ab[1]], src[ab[0]:ab[1]]), zip(bounds[:-1], bounds[1:])))
+    return dst
+
 _USHERS = {"flip": capi.LMC_USHER_FLIP, "swap": capi.LMC_USHER_SWAP,
            "tableflip": capi.LMC_USHER_TABLEFLIP, "table_flip": capi.LMC_USHER_TABLEFLIP}
 _KERNELS = {"metropolis": capi.LMC_KERNEL_METROPOLIS, "uniformlyrandom": capi.LMC_KERNEL_METROPOLIS,
@@ -187,16 +206,19 @@ class Sampler:
     def samples(self):
         return self._container
 
-    def _staging(self, name, dev_tensor):
-        """Cached pinned host buffer matching ``dev_tensor`` (page-locked D2H staging)."""
+    def _trace_slot(self, index, nmax, W, N, F, dev):
+        """Cached trace slot ``index``: device buffers + page-locked host staging for ``nmax`` samples."""
         import torch
-        cache = self.__dict__.setdefault("_pinned", {})
-        key = (name, tuple(dev_tensor.shape), dev_tensor.dtype)
-        if key not in cache:
-            for k in [k for k in cache if k[0] == name]:
-                del cache[k]
-            cache[key] = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
-        return cache[key]
+        cache = self.__dict__.setdefault("_slots", {})
+        key = (index, nmax, W, N, F, self.record_occupancy)
+        if cache.get(index, {}).get("key") != key:
+            shapes = {"features": ((nmax, W, F), torch.float64), "enthalpy": ((nmax, W), torch.float64),
+                      "accepted": ((nmax, W), torch.uint8), "n_accepted": ((nmax, W), torch.int32),
+                      "occupancy": ((nmax, W, N if self.record_occupancy else 0), torch.int8)}
+            cache[index] = {"key": key,
+                            "dev": {k: torch.empty(sh, dtype=dt, device=dev) for k, (sh, dt) in shapes.items()},
+                            "host": {k: torch.empty(sh, dtype=dt, pin_memory=True) for k, (sh, dt) in shapes.items()}}
+        return cache[index]
 
     def efficiency(self, discard=0, flat=True):
         return self.samples.sampling_efficiency(discard=discard, flat=flat)
@@ -245,7 +267,8 @@ class Sampler:
 
     # ---- run (sampler.py:164-297, 386-434) ------------------------------------------------------------
     def run(self, nsteps, initial_occupancies=None, thin_by=1, progress=False, stream_chunk=0,
-            stream_file=None, keep_last_chunk=False, swmr_mode=False, max_chunk_bytes=2 << 30):
+            stream_file=None, keep_last_chunk=False, swmr_mode=False, max_chunk_bytes=2 << 30,
+            pipeline_chunks=4):
         import torch
         eng = self.engine
         if stream_chunk:
@@ -259,13 +282,15 @@ class Sampler:
                 warnings.warn("Initial occupancies where provided with a pre-existing set of samples."
                               "\n Make real sure that is what you want. If not, reset the samples in "
                               "the sampler.", RuntimeWarning)
-            occ = np.array(initial_occupancies)
+            occ = np.asarray(initial_occupancies)
             if occ.ndim == 1 and self.nwalkers == 1:
                 occ = occ[None, :]
             if occ.shape != (self.nwalkers, eng.N):
                 raise AttributeError("The given initial occcupancies have incompompatible dimensions. "
                                      f"Shape should be {(self.nwalkers, eng.N)}.")
-            self._occ_dev = eng.upload_occupancy(occ.astype(np.int32))       # sampler.py:401-406
+            # copied (sampler.py:401) and converted to int32 (sampler.py:406) on the way into the
+            # page-locked staging buffer; the caller's array is never modified
+            self._occ_dev = eng.upload_occupancy(occ)
         if nsteps % thin_by != 0:
             warnings.warn(f"The number of steps {nsteps} is not a multiple of thin_by  {thin_by}. "
                           f"The last {nsteps % thin_by} will be ignored.", category=RuntimeWarning)
@@ -282,16 +307,43 @@ class Sampler:
             beta_h = np.where(np.isinf(self._temperature), 0.0, 1.0 / (self.kB * self._temperature))
         beta = torch.from_numpy(np.ascontiguousarray(beta_h)).to(dev)
         per_sample = W * ((N if self.record_occupancy else 0) + 8 * F + 8 + 1 + 4)
-        chunk = max(1, min(S, int(max_chunk_bytes // max(per_sample, 1)))) if S else 0
-        done = 0
+        # The run is cut into a few launches so that the device->host copy and the host-side
+        # bookkeeping of chunk i overlap the kernel of chunk i+1 (double-buffered trace slots, copies
+        # on a side stream).  The chains are unaffected: the RNG is counter based.
+        nmax = max(1, min(S, int(max_chunk_bytes // max(per_sample, 1)))) if S else 0
+        if S >= 2 * pipeline_chunks:
+            nmax = min(nmax, -(-S // pipeline_chunks))
+        elif S >= 2:
+            nmax = min(nmax, -(-S // 2))
         self._kernel_events = []
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        slots = [self._trace_slot(i, nmax, W, N, F, dev) for i in range(2)]
+
+        def finalize(slot, n, ev_copy):
+            ev_copy.synchronize()
+            host = slot["host"]
+            traces = {
+                "features": _fast_copy(host["features"][:n].numpy()),
+                "enthalpy": host["enthalpy"][:n].numpy().copy()[:, :, None],
+                "accepted": host["accepted"][:n].numpy().astype(bool)[:, :, None],
+                "n_accepted": host["n_accepted"][:n].numpy().copy(),
+            }
+            if self.record_occupancy:
+                o = host["occupancy"][:n].numpy()
+                traces["occupancy"] = _fast_copy(o.reshape(n * W, N)).reshape(n, W, N)   # int8; int32 on access
+            else:
+                traces["occupancy"] = np.zeros((n, W, 0), dtype=np.int8)
+            if "temperature" in self.samples._shapes:
+                traces["temperature"] = np.broadcast_to(self._temperature[None, :, None], (n, W, 1)).copy()
+            self.samples.append(traces, thin_by)
+
+        done, ci, pending = 0, 0, None
         while done < S:
-            n = min(chunk, S - done)
-            tr_occ = torch.empty((n, W, N), dtype=torch.int8, device=dev) if self.record_occupancy else None
-            tr_feat = torch.empty((n, W, F), dtype=torch.float64, device=dev)
-            tr_enth = torch.empty((n, W), dtype=torch.float64, device=dev)
-            tr_acc = torch.empty((n, W), dtype=torch.uint8, device=dev)
-            tr_nacc = torch.empty((n, W), dtype=torch.int32, device=dev)
+            n = min(nmax, S - done)
+            slot = slots[ci % 2]
+            d = slot["dev"]
             cfg = capi.LmcRunConfig()
             cfg.num_walkers, cfg.walker_id_base = W, self.walker_id_base
             cfg.usher, cfg.kernel = self._usher, self._kernel
@@ -301,9 +353,9 @@ class Sampler:
             cfg.seeds_dev, cfg.beta_dev = seeds.data_ptr(), beta.data_ptr()
             cfg.occ_dev, cfg.features_dev, cfg.enthalpy_dev = \
                 self._occ_dev.data_ptr(), feat.data_ptr(), enth.data_ptr()
-            cfg.trace_occ_dev = tr_occ.data_ptr() if tr_occ is not None else None
-            cfg.trace_features_dev, cfg.trace_enthalpy_dev = tr_feat.data_ptr(), tr_enth.data_ptr()
-            cfg.trace_accepted_dev, cfg.trace_naccepted_dev = tr_acc.data_ptr(), tr_nacc.data_ptr()
+            cfg.trace_occ_dev = d["occupancy"].data_ptr() if self.record_occupancy else None
+            cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
+            cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
             if self._kernel == capi.LMC_KERNEL_WANGLANDAU:
                 p, st = self._wl, self._wl_state
                 wl = cfg.wl
@@ -316,33 +368,27 @@ class Sampler:
                 wl.occurrences_dev, wl.mean_features_dev = st["occurrences"].data_ptr(), st["mean_features"].data_ptr()
                 wl.mod_factor_dev, wl.steps_counter_dev = st["mod_factor"].data_ptr(), st["steps_counter"].data_ptr()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
+            ev0.record(main)
             eng.run(cfg)
-            ev1.record()
+            ev1.record(main)
             self._kernel_events.append((ev0, ev1))
             self._step_counter += n * thin_by
-            # device -> pinned host staging (async on the launching stream), one sync, then numpy
-            dev_tr = {"features": tr_feat, "enthalpy": tr_enth, "accepted": tr_acc, "n_accepted": tr_nacc}
-            if self.record_occupancy:
-                dev_tr["occupancy"] = tr_occ
-            host = {k: self._staging(k, v) for k, v in dev_tr.items()}
-            for k, v in dev_tr.items():
-                host[k].copy_(v, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
-            traces = {
-                "features": host["features"].numpy().copy(),
-                "enthalpy": host["enthalpy"].numpy().copy()[:, :, None],
-                "accepted": host["accepted"].numpy().astype(bool)[:, :, None],
-                "n_accepted": host["n_accepted"].numpy().copy(),
-            }
-            if self.record_occupancy:
-                traces["occupancy"] = host["occupancy"].numpy().copy()   # int8 on host; int32 on access
-            else:
-                traces["occupancy"] = np.zeros((n, W, 0), dtype=np.int8)
-            if "temperature" in self.samples._shapes:
-                traces["temperature"] = np.broadcast_to(self._temperature[None, :, None], (n, W, 1)).copy()
-            self.samples.append(traces, thin_by)
+            # device -> pinned host staging on the copy stream, behind this chunk's kernel
+            ev_copy = torch.cuda.Event()
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ev1)
+                for k, v in d.items():
+                    if k == "occupancy" and not self.record_occupancy:
+                        continue
+                    slot["host"][k][:n].copy_(v[:n], non_blocking=True)
+                ev_copy.record(self._copy_stream)
+            if pending is not None:
+                finalize(*pending)        # overlaps the kernel just launched
+            pending = (slot, n, ev_copy)
             done += n
+            ci += 1
+        if pending is not None:
+            finalize(*pending)
         torch.cuda.synchronize(dev)
         # device time of the lmc_run launches of this call (CUDA events on the launching stream)
         self.last_kernel_ms = float(sum(a.elapsed_time(b) for a, b in self._kernel_events))
