@@ -515,6 +515,15 @@ __device__ __forceinline__ double exact_floordiv(double a, double b) {
   else if (r >= b) q += 1.0;
   return q;
 }
+// st.<field>[f] for a RUNTIME f without dynamic indexing (keeps the arrays in registers)
+template <int MF>
+__device__ __forceinline__ int pick(const int (&arr)[MF], int f) {
+  int v = arr[0];
+#pragma unroll
+  for (int i = 1; i < MF; ++i) v = (f == i) ? arr[i] : v;
+  return v;
+}
+
 // Python float floor division `a // b` (CPython float_floor_div), used by WangLandau._get_bin_id
 __device__ __forceinline__ double py_floordiv(double a, double b) {
   double mod = fmod(a, b);
@@ -842,38 +851,54 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       int4 seg0 = make_int4(0, 0, 0, 0), seg1 = make_int4(0, 0, 0, 0);
       if (st.n > 0) { pre0 = load_records<G>(m, st.site[0], g); if (SEGPRE) seg0 = load_segment<G>(m, st.site[0], g); }
       if (st.n > 1) { pre1 = load_records<G>(m, st.site[I1], g); if (SEGPRE) seg1 = load_segment<G>(m, st.site[I1], g); }
-      if (st.n >= 2 && !a.seq_flips) {
-        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) ewald_cache_set(m, eidx, st.site[0], st.newc[0]); }
+      // Ewald part first: it only touches the per-walker Ewald cache, never the occupancy.  Flip f is
+      // evaluated with flips < f applied to the cache (sequential semantics, ewald.py:168-181); the
+      // last flip is applied on accept only.  One loop, not unrolled: one copy of the row-gather code.
+      if (EWALD) {
+#pragma unroll 1
+        for (int f = 0; f < st.n; ++f) {
+          const int sf = pick<MF>(st.site, f), of = pick<MF>(st.oldc, f), nf = pick<MF>(st.newc, f);
+          acc_ew += flip_ewald<G>(m, t, eidx, sf, of, nf, g);
+          if (f + 1 < st.n) {
+            group_sync<G>(gmask);
+            if (g == 0) ewald_cache_set(m, eidx, sf, nf);
+            group_sync<G>(gmask);
+          }
+        }
+      }
+      constexpr bool SEQ_ONLY = USHER == LMC_USHER_TABLEFLIP;   // compact code for the big variant
+      if (!SEQ_ONLY && st.n >= 2 && !a.seq_flips) {
+        if (g == 0) occ[st.site[0]] = (uint8_t)st.newc[0];
         group_sync<G>(gmask);
         acc = flip_energy_pair<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], st.site[I1], st.oldc[I1],
                                         st.newc[I1], stash0, stash0 + stash_stride, g, pre0, pre1);
-        if (EWALD) {
-          acc_ew = flip_ewald<G>(m, t, eidx, st.site[0], st.oldc[0], st.newc[0], g);
-          acc_ew += flip_ewald<G>(m, t, eidx, st.site[I1], st.oldc[I1], st.newc[I1], g);
-        }
         // flip 0's records read site 1 (old value): lanes are not guaranteed to run in lockstep, so
         // site 1 may only be written once every lane is done -- after a sync (more flips follow) or
         // after the group reduction below (two-flip step: written on accept only)
         if (st.n > 2) {
           group_sync<G>(gmask);
-          if (g == 0) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) ewald_cache_set(m, eidx, st.site[I1], st.newc[I1]); }
+          if (g == 0) occ[st.site[I1]] = (uint8_t)st.newc[I1];
           group_sync<G>(gmask);
         } else {
           deferred1 = true;
         }
-      } else if (st.n >= 1) {
-        acc = flip_energy<G, KONE>(m, t, occ, st.site[0], st.oldc[0], st.newc[0], stash0, g, pre0);
-        if (EWALD) acc_ew = flip_ewald<G>(m, t, eidx, st.site[0], st.oldc[0], st.newc[0], g);
-        if (g == 0) { occ[st.site[0]] = (uint8_t)st.newc[0]; if (EWALD) ewald_cache_set(m, eidx, st.site[0], st.newc[0]); }
-        if (st.n > 1) group_sync<G>(gmask);
-      }
 #pragma unroll
-      for (int f = 1; f < MF; ++f) {
-        if (f < st.n && (f >= 2 || a.seq_flips)) {
-          pre0 = load_records<G>(m, st.site[f], g);
-          acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g, pre0);
-          if (EWALD) acc_ew += flip_ewald<G>(m, t, eidx, st.site[f], st.oldc[f], st.newc[f], g);
-          if (g == 0) { occ[st.site[f]] = (uint8_t)st.newc[f]; if (EWALD) ewald_cache_set(m, eidx, st.site[f], st.newc[f]); }
+        for (int f = 2; f < MF; ++f) {
+          if (f < st.n) {
+            pre0 = load_records<G>(m, st.site[f], g);
+            acc += flip_energy<G, KONE>(m, t, occ, st.site[f], st.oldc[f], st.newc[f], stash0 + f * stash_stride, g, pre0);
+            if (g == 0) occ[st.site[f]] = (uint8_t)st.newc[f];
+            if (f + 1 < st.n) group_sync<G>(gmask);
+          }
+        }
+      } else {
+        // strictly sequential evaluation (single flips, the table-flip variant, debug switch)
+#pragma unroll 1
+        for (int f = 0; f < st.n; ++f) {
+          const int sf = pick<MF>(st.site, f), of = pick<MF>(st.oldc, f), nf = pick<MF>(st.newc, f);
+          if (f > 0) pre0 = (f == 1 && !SEQ_ONLY) ? pre1 : load_records<G>(m, sf, g);
+          acc += flip_energy<G, KONE>(m, t, occ, sf, of, nf, stash0 + f * stash_stride, g, pre0);
+          if (g == 0) occ[sf] = (uint8_t)nf;
           if (f + 1 < st.n) group_sync<G>(gmask);
         }
       }
@@ -926,7 +951,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
             flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g,
                                    (SEGPRE && f == 0) ? seg0 : ((SEGPRE && f == 1) ? seg1 : load_segment<G>(m, st.site[f], g)));
         if (g == 0) {
-          if (deferred1) { occ[st.site[I1]] = (uint8_t)st.newc[I1]; if (EWALD) ewald_cache_set(m, eidx, st.site[I1], st.newc[I1]); }
+          if (deferred1) occ[st.site[I1]] = (uint8_t)st.newc[I1];
+          if (EWALD && st.n > 0)   // the last flip enters the Ewald cache on accept only
+            ewald_cache_set(m, eidx, pick<MF>(st.site, st.n - 1), pick<MF>(st.newc, st.n - 1));
           if (EWALD) feat[m.ewF] += dEw;
           if (MU_POSSIBLE && m.muW) feat[m.muF] += dmu;
 #pragma unroll
@@ -959,9 +986,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         if (g == 0) {
 #pragma unroll
           for (int f = MF - 1; f >= 0; --f)
-            if (f < st.n && !(f == 1 && deferred1)) {
-              occ[st.site[f]] = (uint8_t)st.oldc[f];
-              if (EWALD) ewald_cache_set(m, eidx, st.site[f], st.oldc[f]);
+            if (f < st.n) {
+              if (!(f == 1 && deferred1)) occ[st.site[f]] = (uint8_t)st.oldc[f];
+              if (EWALD && f + 1 < st.n) ewald_cache_set(m, eidx, st.site[f], st.oldc[f]);
             }
         }
       }
