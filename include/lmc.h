@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 3
+#define LMC_ABI_VERSION 4
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -144,7 +144,8 @@ typedef struct LmcRunConfig {
   int32_t thin_by;            /* steps per interval */
   int32_t group_size;         /* lanes cooperating on one walker: 0 = auto, else 1..32 (power of 2) */
   int32_t block_threads;      /* 0 = auto */
-  int32_t reserved;
+  int32_t spec_mode;          /* Metropolis flip/swap kernel: 0 = auto (by measured acceptance), 1 = classic
+                                 (one step per warp), 2 = speculative batch (8 steps per warp, first accept wins) */
   uint64_t step_begin;        /* global index of the first step (RNG counter words 0,1) */
   const uint64_t* seeds_dev;  /* [W] Philox key per walker */
   const double* beta_dev;     /* [W] 1/(kB T); ignored by Wang-Landau */

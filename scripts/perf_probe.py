@@ -18,10 +18,12 @@ def main():
     ens = S.Ensemble(proc)
     occ0 = M.random_occupancies(sub, scm, W, seed=0, balanced=True)
     N = occ0.shape[1]
+    T = float(os.environ.get("TEMP", 1000.0))
     for G in [int(x) for x in os.environ.get("GS", "4,8,16,32").split(",")]:
         for bt in [int(x) for x in os.environ.get("BTS", "128").split(",")]:
-            smp = S.Sampler.from_ensemble(ens, 1000.0, step_type="swap", nwalkers=W, seeds=list(range(W)),
-                                          group_size=G, block_threads=bt)
+            # GS=-1: speculative-batch kernel, GS=0: auto
+            smp = S.Sampler.from_ensemble(ens, T, step_type="swap", nwalkers=W, seeds=list(range(W)),
+                                          group_size=max(G, 0), block_threads=bt, spec_mode=2 if G < 0 else (1 if G > 0 else 0))
             smp.run(N * 2, occ0, thin_by=N)
             torch.cuda.synchronize()
             t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)

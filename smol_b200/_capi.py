@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 3
+LMC_ABI_VERSION = 4
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -88,7 +88,7 @@ class LmcRunConfig(C.Structure):
     _fields_ = [
         ("num_walkers", C.c_int32), ("walker_id_base", C.c_int32), ("usher", C.c_int32),
         ("kernel", C.c_int32), ("num_samples", C.c_int64), ("thin_by", C.c_int32),
-        ("group_size", C.c_int32), ("block_threads", C.c_int32), ("reserved", C.c_int32),
+        ("group_size", C.c_int32), ("block_threads", C.c_int32), ("spec_mode", C.c_int32),
         ("step_begin", C.c_uint64), ("seeds_dev", _P), ("beta_dev", _P),
         ("occ_dev", _P), ("features_dev", _P), ("enthalpy_dev", _P),
         ("trace_occ_dev", _P), ("trace_features_dev", _P), ("trace_enthalpy_dev", _P),

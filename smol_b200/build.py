@@ -47,6 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for wl in (0, 1):
             jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"),
                          os.path.join(objdir, f"lmc_run_g{g}_wl{wl}.o"), [f"-DLMC_G={g}", f"-DLMC_WL={wl}"]))
+    jobs.append((os.path.join(CSRC, "lmc_spec_inst.cu"), os.path.join(objdir, "lmc_spec.o"), []))
     log = []
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:
         for cmd, r in ex.map(_compile, jobs):

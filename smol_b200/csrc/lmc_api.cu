@@ -37,6 +37,13 @@ struct LmcModel {
   int device = 0;
   int smem_optin = 0;
   int num_sms = 0;
+  // acceptance feedback for the kernel selection: the kernels add their accepted / attempted step
+  // totals to device counters; an async copy after each launch brings them to page-locked host
+  // memory and lmc_run reads whatever has arrived (no synchronisation)
+  unsigned long long* stats_host = nullptr;
+  unsigned long long* stats_dev = nullptr;
+  unsigned long long snap[2] = {0, 0};
+  double acc_rate = -1.0;   // acceptance ratio of the most recent completed launches, < 0: unknown
 };
 
 template <typename T>
@@ -63,6 +70,7 @@ extern "C" int lmc_model_num_features(const LmcModel* m) { return m ? m->dm.F : 
 extern "C" int lmc_model_destroy(LmcModel* m) {
   if (!m) return 0;
   for (void* p : m->allocs) cudaFree(p);
+  if (m->stats_host) cudaFreeHost(m->stats_host);
   delete m;
   return 0;
 }
@@ -80,6 +88,17 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
   cudaGetDevice(&mdl->device);
   cudaDeviceGetAttribute(&mdl->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, mdl->device);
   cudaDeviceGetAttribute(&mdl->num_sms, cudaDevAttrMultiProcessorCount, mdl->device);
+  if (cudaHostAlloc((void**)&mdl->stats_host, 2 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess &&
+      cudaMalloc((void**)&mdl->stats_dev, 2 * sizeof(unsigned long long)) == cudaSuccess) {
+    mdl->stats_host[0] = mdl->stats_host[1] = 0;
+    cudaMemset(mdl->stats_dev, 0, 2 * sizeof(unsigned long long));
+    mdl->allocs.push_back(mdl->stats_dev);
+  } else {
+    if (mdl->stats_host) cudaFreeHost(mdl->stats_host);
+    mdl->stats_host = nullptr;
+    mdl->stats_dev = nullptr;
+    (void)cudaGetLastError();
+  }
   m.N = d->num_sites;
   m.Npad = lmc_row_stride(d->num_sites);
   m.F = d->num_features;
@@ -211,6 +230,99 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     }
     UP(int, d->ewald_inds, (size_t)m.N * m.ewW, m.ewInds);
   }
+  // speculative-batch kernel tables (lmc_spec.cuh).  Records are regrouped by the number of OTHER
+  // sites (1 incl. point terms, 2, 3) and carry the base of their class in a difference table
+  //   D[new][tbase + c0 + NC c1 + NC^2 c2 + NC^n old] = coef * (T[idx after] - T[idx before])
+  // so that one record costs one occupancy gather per other site and ONE table lookup.
+  std::vector<double> dtab;
+  std::vector<unsigned char> sprec;
+  {
+    int NC = 2;
+    for (int n = 0; n < m.nOrb; ++n)
+      for (int i = 0; i < orbs[n].csize; ++i) {
+        const int hi = i == 0 ? orbs[n].T : orbs[n].stride[i - 1];
+        if (orbs[n].stride[i] > 0) NC = std::max(NC, hi / orbs[n].stride[i]);
+      }
+    bool ok = NC <= LMC_MAX_CODES && m.nCls > 0;
+    const long Z = (long)NC * NC * NC * NC;   // zero block hit by the padding records
+    std::vector<int> noth(m.nCls, 0), tbase(m.nCls, 0);
+    // per-class difference blocks [new][entry]; identical blocks (symmetric tensors: every position of
+    // the flipped site in the cluster gives the same block) are stored once
+    std::vector<std::vector<double>> blocks;
+    std::vector<long> block_base, block_len;
+    long L = Z;
+    for (int c = 0; c < m.nCls && ok; ++c) {
+      const int* st = d->cls_stride + c * 4;
+      int n = 0;
+      while (n < 3 && st[n] > 0) ++n;
+      for (int i = n; i < 3; ++i) ok = ok && st[i] == 0;   // other sites are compacted to the first slots
+      if (!ok) break;
+      n = std::max(n, 1);
+      noth[c] = n;
+      const OrbDev& o = orbs[d->cls_orbit[c]];
+      const double coef = kone ? d->natural_parameters[o.fidx] * o.w : 1.0;
+      long combos = 1;
+      for (int i = 0; i < n; ++i) combos *= NC;
+      const long len = combos * NC;
+      std::vector<double> blk((size_t)len * NC, 0.0);
+      for (long q = 0; q < combos; ++q) {
+        long ii0 = 0, r = q;
+        for (int i = 0; i < n; ++i) { ii0 += (long)st[i] * (r % NC); r /= NC; }   // st[i] == 0 for the dummy slot of point terms
+        for (int oldc = 0; oldc < NC; ++oldc)
+          for (int newc = 0; newc < NC; ++newc) {
+            const long ii = ii0 + (long)st[3] * oldc, ff = ii0 + (long)st[3] * newc;
+            if (ii >= o.T || ff >= o.T || newc == oldc) continue;
+            blk[(size_t)newc * len + q + combos * oldc] = coef * (tabA[o.atab_off + ff] - tabA[o.atab_off + ii]);
+          }
+      }
+      size_t hit = blocks.size();
+      for (size_t b = 0; b < blocks.size(); ++b)
+        if (block_len[b] == len && memcmp(blocks[b].data(), blk.data(), blk.size() * 8) == 0) { hit = b; break; }
+      if (hit == blocks.size()) {
+        blocks.push_back(std::move(blk));
+        block_base.push_back(L);
+        block_len.push_back(len);
+        L += len;
+      }
+      tbase[c] = (int)block_base[hit];
+    }
+    ok = ok && L <= 65535 && (size_t)L * NC * 8 <= 64 * 1024;
+    if (const char* e = getenv("LMC_SPEC_TABLES")) ok = ok && atoi(e) != 0;
+    if (ok) {
+      dtab.assign((size_t)L * NC, 0.0);
+      for (size_t b = 0; b < blocks.size(); ++b)
+        for (int newc = 0; newc < NC; ++newc)
+          memcpy(&dtab[(size_t)newc * L + block_base[b]], &blocks[b][(size_t)newc * block_len[b]], (size_t)block_len[b] * 8);
+      // per-site record lists by number of other sites
+      int n1 = 0, n2 = 0, n3 = 0;
+      for (int i = 0; i < m.N; ++i) {
+        int k1 = 0, k2 = 0, k3 = 0;
+        for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) {
+          const int n = noth[d->site_rec[r * 4 + 3]];
+          (n == 1 ? k1 : n == 2 ? k2 : k3)++;
+        }
+        n1 = std::max(n1, k1); n2 = std::max(n2, k2); n3 = std::max(n3, k3);
+      }
+      m.spN1 = (n1 + 15) & ~15; m.spN2 = (n2 + 7) & ~7; m.spN3 = (n3 + 7) & ~7;
+      m.spSb = m.spN1 * 4 + (m.spN2 + m.spN3) * 8;
+      sprec.assign((size_t)std::max(m.N * m.spSb, 16), 0);   // zero records: site 0, tbase 0 (zero block)
+      for (int i = 0; i < m.N; ++i) {
+        uint32_t* p1 = reinterpret_cast<uint32_t*>(sprec.data() + (size_t)i * m.spSb);
+        uint32_t* p2 = p1 + m.spN1;
+        uint32_t* p3 = p2 + 2 * m.spN2;
+        int k1 = 0, k2 = 0, k3 = 0;
+        for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) {
+          const uint16_t* rc = d->site_rec + r * 4;
+          const int c = rc[3], n = noth[c];
+          const uint32_t tb = (uint32_t)tbase[c];
+          if (n == 1) p1[k1++] = (uint32_t)rc[0] | (tb << 16);
+          else if (n == 2) { p2[2 * k2] = (uint32_t)rc[0] | ((uint32_t)rc[1] << 16); p2[2 * k2 + 1] = tb << 16; ++k2; }
+          else { p3[2 * k3] = (uint32_t)rc[0] | ((uint32_t)rc[1] << 16); p3[2 * k3 + 1] = (uint32_t)rc[2] | (tb << 16); ++k3; }
+        }
+      }
+      m.spOK = 1; m.spNC = NC; m.spL = (int)L;
+    }
+  }
   // blob: cls (nCls + 1 entries, the last is the all-zero padding class) | tabA | nat | orb
   {
     const int C = m.nCls + 1;
@@ -221,6 +333,7 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     m.off_nat = (int)off; off += ((size_t)m.F * 8 + 15) & ~size_t(15);
     m.off_orb = (int)off; off += ((size_t)m.nOrb * sizeof(OrbDev) + 15) & ~size_t(15);
     m.off_qtab = (int)off; off += ((size_t)std::max<size_t>(qtab.size(), 2) * 8 + 15) & ~size_t(15);
+    m.off_dtab = (int)off; off += (dtab.size() * 8 + 15) & ~size_t(15);
     m.blob_bytes = (int)off;
     std::vector<unsigned char> blob(off, 0);
     uint32_t* cls = reinterpret_cast<uint32_t*>(blob.data() + off_cls);
@@ -241,7 +354,9 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     memcpy(blob.data() + m.off_nat, d->natural_parameters, (size_t)m.F * 8);
     memcpy(blob.data() + m.off_orb, orbs.data(), (size_t)m.nOrb * sizeof(OrbDev));
     if (!qtab.empty()) memcpy(blob.data() + m.off_qtab, qtab.data(), qtab.size() * 8);
+    if (!dtab.empty()) memcpy(blob.data() + m.off_dtab, dtab.data(), dtab.size() * 8);
     UP(unsigned char, blob.data(), blob.size(), m.blob);
+    if (m.spOK) UP(unsigned char, sprec.data(), sprec.size(), m.sp_rec);
   }
   UP(OrbDev, orbs.data(), orbs.size(), mdl->orb_dev);
   UP(double, d->natural_parameters, m.F, mdl->nat_dev);
@@ -400,6 +515,24 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const bool ewald = m.E > 0;
   int G = c->group_size;
   if (const char* e = getenv("LMC_GROUP_SIZE")) { if (G == 0) G = atoi(e); }
+  // kernel selection: the speculative-batch kernel (lmc_spec.cuh) wins while fewer than ~1/3 of the
+  // steps are accepted; the acceptance ratio comes from the totals of the launches that have completed
+  LmcModel* mm = const_cast<LmcModel*>(mdl);
+  if (mm->stats_host) {
+    const unsigned long long acc = ((volatile unsigned long long*)mm->stats_host)[0];
+    const unsigned long long att = ((volatile unsigned long long*)mm->stats_host)[1];
+    if (att >= mm->snap[1] + 65536ull && acc >= mm->snap[0]) {
+      mm->acc_rate = (double)(acc - mm->snap[0]) / (double)(att - mm->snap[1]);
+      mm->snap[0] = acc; mm->snap[1] = att;
+    }
+  }
+  int spec_mode = c->spec_mode;
+  if (const char* e = getenv("LMC_SPEC")) { if (spec_mode == 0) spec_mode = atoi(e) ? 2 : 1; }
+  const bool spec_ok = m.spOK && !ewald && c->kernel == LMC_KERNEL_METROPOLIS &&
+                       (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
+  if (spec_mode == 2 && !spec_ok) return fail("the speculative kernel supports Metropolis flip/swap steps without Ewald term only");
+  const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35));
+  if (use_spec) G = 32;
   if (G == 0) {
     // measured on B200 (profiles/): a full warp per walker wins while all walkers fit in one wave
     // (W <= 32 per SM); beyond that half warps amortise the per-step scalar work better
@@ -411,7 +544,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (G != 4 && G != 8 && G != 16 && G != 32) return fail("group_size must be 4, 8, 16 or 32");
   int threads = c->block_threads;
   if (const char* e = getenv("LMC_BLOCK_THREADS")) { if (threads == 0) threads = atoi(e); }
-  const bool relaxed = ewald || c->kernel == LMC_KERNEL_WANGLANDAU || c->usher == LMC_USHER_TABLEFLIP;
+  const bool relaxed = !use_spec && (ewald || c->kernel == LMC_KERNEL_WANGLANDAU || c->usher == LMC_USHER_TABLEFLIP);
   const int max_threads = relaxed ? 256 : 128;
   const bool auto_threads = threads == 0;
   if (threads == 0) threads = 128;
@@ -427,6 +560,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.tr_occ = c->trace_occ_dev; a.tr_feat = c->trace_features_dev; a.tr_enth = c->trace_enthalpy_dev;
   a.tr_acc = c->trace_accepted_dev; a.tr_nacc = c->trace_naccepted_dev;
   a.wl = c->wl;
+  a.stats = mm->stats_dev;
   if (!a.seeds || !a.occ || !a.features || !a.enthalpy) return fail("state pointers must not be null");
   if (c->kernel != LMC_KERNEL_WANGLANDAU && !a.beta) return fail("beta_dev must not be null");
   // per-walker shared-memory slab: [features][stash x MAX_FLIPS][counts]
@@ -476,7 +610,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
   int rc = -2;
   const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
-  switch (G) {
+  if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, lc);
+  else switch (G) {
     case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewald, c->usher, lc); break;
     case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewald, c->usher, lc); break;
     case 16: rc = (wl ? launch_run_wl_g16 : launch_run_g16)(m, a, m.kone != 0, ewald, c->usher, lc); break;
@@ -485,5 +620,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (rc == -2) return fail("no kernel instantiated for this group size / usher");
   g_launches++;
   if (rc != 0) return fail(std::string("launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  // acceptance totals follow the launch in stream order; the host looks at them at the next call
+  if (mm->stats_host && c->kernel == LMC_KERNEL_METROPOLIS)
+    cudaMemcpyAsync(mm->stats_host, mm->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   return 0;
 }

@@ -651,6 +651,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   float b_lf = 0.f;
 #endif
   int bphase = 0;
+  long long nacc_total = 0;
   for (long long s = 0; s < a.S; ++s) {
     int nacc = 0;
     bool accepted = true;
@@ -1045,6 +1046,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     }  // thin
 
     // ------------------------------ sample trace ------------------------------------------
+    nacc_total += nacc;
     const size_t sw = (size_t)s * a.W + w;
     if (a.tr_occ) {
       int8_t* dst = a.tr_occ + sw * m.N;
@@ -1077,6 +1079,10 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     if (wl_mode) {
       a.wl.mod_factor_dev[w] = wl_m;
       a.wl.steps_counter_dev[w] = wl_cnt;
+    }
+    if (a.stats && !wl_mode) {   // acceptance feedback for the kernel selection of the next launches
+      atomicAdd(a.stats, (unsigned long long)nacc_total);
+      atomicAdd(a.stats + 1, (unsigned long long)(a.S * (long long)a.thin));
     }
   }
 }

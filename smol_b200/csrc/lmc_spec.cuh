@@ -1,0 +1,399 @@
+// Speculative-batch Metropolis kernel (sm_100a).
+//
+// The classic kernel (lmc_kernels.cuh) spends all 32 lanes of a warp on ONE attempted step: the
+// per-step scalar work (proposal, rank select, reduction, accept test) is replicated 32 wide and
+// dominates the instruction count.  Here a warp still owns one walker, but each group of
+// SPEC_SG = 4 lanes evaluates a DIFFERENT upcoming step (SPEC_B = 8 consecutive steps per batch)
+// against the current occupancy.  The RNG is counter based (Philox keyed by step index), so step
+// t + j is fully defined before step t has been decided.  Rejected steps leave the state
+// untouched, hence every step of the batch up to and including the FIRST accepted one has been
+// evaluated against exactly the state the sequential chain would have seen: that prefix is
+// committed, the rest of the batch is discarded and proposed again from the new state.  The chain
+// is the sequential Metropolis chain of smol (kernel/base.py:145-166, metropolis.py:31-49), step
+// for step; only the amount of wasted work depends on the acceptance ratio.
+//
+// Evaluation uses the size-sorted compact records and the pre-differenced table built at model
+// creation (lmc_api.cu): one occupancy gather per other site and one table lookup per record.
+// The accepted step is re-evaluated by the whole warp with the classic record path, which leaves
+// the per-record differences in the stash for the feature update (cluster order of
+// evaluator.pyx:253-263).
+#pragma once
+#include "lmc_kernels.cuh"
+
+namespace lmc {
+
+constexpr int SPEC_SG = 4;
+constexpr int SPEC_B = 32 / SPEC_SG;
+
+// k-th (0-based) active position of sublattice `sl` whose code differs from `code`; the four lanes
+// of a subgroup split the plane words.  Called by all 32 lanes (full-mask shuffles of width 4).
+__device__ __forceinline__ int spec_select_ne(const DevModel& m, const uint32_t* planes, int sl, int code, int k, int l) {
+  const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+  const int nw = m.sl_nwords[sl];
+  const uint32_t* pl = planes + m.sl_plane_off[sl] + code * nw;
+  const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
+  const int cw = (nw + SPEC_SG - 1) / SPEC_SG;
+  const int lo = l * cw;
+  int cnt = 0;
+  for (int i = 0; i < cw; ++i) {
+    const int wd = lo + i;
+    uint32_t b = 0u;
+    if (wd < nw) b = ~pl[wd] & (wd == nw - 1 ? tail : 0xffffffffu);
+    cnt += __popc(b);
+  }
+  int incl = cnt;
+  int tt = __shfl_up_sync(0xffffffffu, incl, 1, SPEC_SG);
+  if (l >= 1) incl += tt;
+  tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
+  if (l >= 2) incl += tt;
+  int rem = k - (incl - cnt);
+  const bool found = rem >= 0 && rem < cnt;
+  int res = 0;
+  if (found) {
+    for (int i = 0; i < cw; ++i) {
+      const int wd = lo + i;
+      uint32_t b = 0u;
+      if (wd < nw) b = ~pl[wd] & (wd == nw - 1 ? tail : 0xffffffffu);
+      const int c = __popc(b);
+      if (rem < c) {
+        int pos = 0;
+        const int c16 = __popc(b & 0xffffu);
+        if (rem >= c16) { rem -= c16; pos += 16; b >>= 16; }
+        const int c8 = __popc(b & 0xffu);
+        if (rem >= c8) { rem -= c8; pos += 8; b >>= 8; }
+        const int c4 = __popc(b & 0xfu);
+        if (rem >= c4) { rem -= c4; pos += 4; b >>= 4; }
+        const int c2 = __popc(b & 0x3u);
+        if (rem >= c2) { rem -= c2; pos += 2; b >>= 2; }
+        if (rem >= (int)(b & 1u)) pos += 1;
+        res = wd * 32 + pos;
+        break;
+      }
+      rem -= c;
+    }
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, found);
+  const uint32_t mine = (bal >> (threadIdx.x & 28u)) & 0xfu;
+  const int own = mine ? (__ffs(mine) - 1) : 0;
+  return __shfl_sync(0xffffffffu, res, own, SPEC_SG);
+}
+
+// occupancy code of site s; PATCH: site `ps` reads as `pc` (the first flip of a swap applied)
+template <bool PATCH>
+__device__ __forceinline__ uint32_t spec_code(const uint8_t* occ, uint32_t s, uint32_t ps, uint32_t pc) {
+  uint32_t c = occ[s];
+  if (PATCH) c = (s == ps) ? pc : c;
+  return c;
+}
+
+template <bool PATCH>
+__device__ __forceinline__ void spec_pairs4(const uint8_t* occ, const double* Dn, const uint4 v, uint32_t old1, uint32_t ps,
+                                            uint32_t pc, double& a0, double& a1) {
+  a0 += Dn[(v.x >> 16) + spec_code<PATCH>(occ, v.x & 0xffffu, ps, pc) + old1];
+  a1 += Dn[(v.y >> 16) + spec_code<PATCH>(occ, v.y & 0xffffu, ps, pc) + old1];
+  a0 += Dn[(v.z >> 16) + spec_code<PATCH>(occ, v.z & 0xffffu, ps, pc) + old1];
+  a1 += Dn[(v.w >> 16) + spec_code<PATCH>(occ, v.w & 0xffffu, ps, pc) + old1];
+}
+template <bool PATCH>
+__device__ __forceinline__ void spec_trip2(const uint8_t* occ, const double* Dn, const uint4 v, uint32_t NC, uint32_t old2,
+                                           uint32_t ps, uint32_t pc, double& a0, double& a1) {
+  a0 += Dn[(v.y >> 16) + spec_code<PATCH>(occ, v.x & 0xffffu, ps, pc) + NC * spec_code<PATCH>(occ, v.x >> 16, ps, pc) + old2];
+  a1 += Dn[(v.w >> 16) + spec_code<PATCH>(occ, v.z & 0xffffu, ps, pc) + NC * spec_code<PATCH>(occ, v.z >> 16, ps, pc) + old2];
+}
+template <bool PATCH>
+__device__ __forceinline__ void spec_quad2(const uint8_t* occ, const double* Dn, const uint4 v, uint32_t NC, uint32_t old3,
+                                           uint32_t ps, uint32_t pc, double& a0, double& a1) {
+  a0 += Dn[(v.y >> 16) + spec_code<PATCH>(occ, v.x & 0xffffu, ps, pc) +
+           NC * (spec_code<PATCH>(occ, v.x >> 16, ps, pc) + NC * spec_code<PATCH>(occ, v.y & 0xffffu, ps, pc)) + old3];
+  a1 += Dn[(v.w >> 16) + spec_code<PATCH>(occ, v.z & 0xffffu, ps, pc) +
+           NC * (spec_code<PATCH>(occ, v.z >> 16, ps, pc) + NC * spec_code<PATCH>(occ, v.w & 0xffffu, ps, pc)) + old3];
+}
+
+// scaled energy change of one flip (lane l of 4 takes every fourth 16-byte chunk of the record lists)
+template <bool PATCH>
+__device__ __forceinline__ double spec_flip_energy(const DevModel& m, const uint8_t* occ, const double* dtab, int site,
+                                                   int oldc, int newc, uint32_t ps, uint32_t pc, int l) {
+  const uint4* rp = reinterpret_cast<const uint4*>(m.sp_rec + (size_t)site * m.spSb) + l;
+  const double* Dn = dtab + newc * m.spL;
+  const uint32_t NC = (uint32_t)m.spNC;
+  const uint32_t old1 = NC * (uint32_t)oldc, old2 = NC * old1, old3 = NC * old2;
+  double a0 = 0.0, a1 = 0.0;
+  const int c1 = m.spN1 >> 4, c2 = m.spN2 >> 3, c3 = m.spN3 >> 3;
+#pragma unroll 2
+  for (int q = 0; q < c1; ++q) spec_pairs4<PATCH>(occ, Dn, __ldg(rp + q * SPEC_SG), old1, ps, pc, a0, a1);
+  rp += c1 * SPEC_SG;
+#pragma unroll 2
+  for (int q = 0; q < c2; ++q) spec_trip2<PATCH>(occ, Dn, __ldg(rp + q * SPEC_SG), NC, old2, ps, pc, a0, a1);
+  rp += c2 * SPEC_SG;
+  for (int q = 0; q < c3; ++q) spec_quad2<PATCH>(occ, Dn, __ldg(rp + q * SPEC_SG), NC, old3, ps, pc, a0, a1);
+  return a0 + a1;
+}
+
+// both flips of a swap in the same loops (independent chains: twice the ILP); flip b sees flip a
+// applied through the PATCH of its gathers (sequential semantics of expansion.py:217-229)
+__device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint8_t* occ, const double* dtab, int sitea,
+                                                   int olda, int newa, int siteb, int oldb, int newb, int l) {
+  const uint4* ra = reinterpret_cast<const uint4*>(m.sp_rec + (size_t)sitea * m.spSb) + l;
+  const uint4* rb = reinterpret_cast<const uint4*>(m.sp_rec + (size_t)siteb * m.spSb) + l;
+  const double* Da = dtab + newa * m.spL;
+  const double* Db = dtab + newb * m.spL;
+  const uint32_t NC = (uint32_t)m.spNC;
+  const uint32_t oa1 = NC * (uint32_t)olda, oa2 = NC * oa1, oa3 = NC * oa2;
+  const uint32_t ob1 = NC * (uint32_t)oldb, ob2 = NC * ob1, ob3 = NC * ob2;
+  const uint32_t ps = (uint32_t)sitea, pc = (uint32_t)newa;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  const int c1 = m.spN1 >> 4, c2 = m.spN2 >> 3, c3 = m.spN3 >> 3;
+#pragma unroll 2
+  for (int q = 0; q < c1; ++q) {
+    const uint4 va = __ldg(ra + q * SPEC_SG), vb = __ldg(rb + q * SPEC_SG);
+    spec_pairs4<false>(occ, Da, va, oa1, 0u, 0u, a0, a1);
+    spec_pairs4<true>(occ, Db, vb, ob1, ps, pc, b0, b1);
+  }
+  ra += c1 * SPEC_SG; rb += c1 * SPEC_SG;
+#pragma unroll 2
+  for (int q = 0; q < c2; ++q) {
+    const uint4 va = __ldg(ra + q * SPEC_SG), vb = __ldg(rb + q * SPEC_SG);
+    spec_trip2<false>(occ, Da, va, NC, oa2, 0u, 0u, a0, a1);
+    spec_trip2<true>(occ, Db, vb, NC, ob2, ps, pc, b0, b1);
+  }
+  ra += c2 * SPEC_SG; rb += c2 * SPEC_SG;
+  for (int q = 0; q < c3; ++q) {
+    const uint4 va = __ldg(ra + q * SPEC_SG), vb = __ldg(rb + q * SPEC_SG);
+    spec_quad2<false>(occ, Da, va, NC, oa3, 0u, 0u, a0, a1);
+    spec_quad2<true>(occ, Db, vb, NC, ob3, ps, pc, b0, b1);
+  }
+  return (a0 + a1) + (b0 + b1);
+}
+
+template <bool KONE, int USHER>
+__global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, const RunArgs a) {
+  static_assert(USHER == LMC_USHER_FLIP || USHER == LMC_USHER_SWAP, "flip / swap only");
+  constexpr int G = 32;
+  constexpr uint32_t FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint64_t bar;
+  const int g = threadIdx.x & 31;
+  const int wl_ = threadIdx.x >> 5;                 // walker slot in block
+  const int w = blockIdx.x * a.wpb + wl_;
+  const int nw_blk = min(a.wpb, a.W - blockIdx.x * a.wpb);
+  const bool active = wl_ < a.wpb && w < a.W;
+  const int sg = g >> 2, l = g & 3;
+
+  unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
+  uint8_t* occ_rows = wbase;
+  unsigned char* rest = wbase + (size_t)a.wpb * m.Npad;
+  uint8_t* occ = occ_rows + (size_t)wl_ * m.Npad;
+  unsigned char* priv = rest + (size_t)wl_ * a.walker_smem;
+  double* feat = reinterpret_cast<double*>(priv + a.off_feat);
+  unsigned char* stash0 = priv + a.off_stash;
+  int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
+  uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [32] x (sl<<24 | pos, site, word z, float log u)
+
+  stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
+  const SmemTables t = smem_tables(m, smem);
+  const double* dtab = reinterpret_cast<const double*>(smem + m.off_dtab);
+  if (!active) return;
+
+  const int stash_stride = m.Rstride * (KONE ? 8 : 4);
+  for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
+  double enth = a.enthalpy[w];
+  for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
+  for (int i = g; i < m.plane_words; i += G) planes[i] = 0u;
+  __syncwarp();
+  for (int sl = 0; sl < m.nSl; ++sl) {
+    const int n_act = m.sl_off[sl + 1] - m.sl_off[sl], nw = m.sl_nwords[sl];
+    for (int wd = g; wd < nw; wd += G) {
+      const int jn = min(32, n_act - 32 * wd);
+      for (int b = 0; b < jn; ++b) {
+        const int code = occ[site_of_pos(m, sl, wd * 32 + b)];
+        planes[m.sl_plane_off[sl] + code * nw + wd] |= 1u << b;
+        atomicAdd(&cnt[sl * LMC_MAX_CODES + code], 1);
+      }
+    }
+  }
+  __syncwarp();
+
+  const unsigned long long seed = a.seeds[w];
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t wid = (uint32_t)(a.walker_base + w);
+  const double beta = a.beta[w];
+  constexpr bool MU_POSSIBLE = USHER != LMC_USHER_SWAP;
+  const double nat_mu = (MU_POSSIBLE && m.muW) ? t.nat[m.muF] : 0.0;
+
+  unsigned long long step = a.step0;
+  unsigned long long rbase = step;
+  bool ring_valid = false;
+  long long nacc_total = 0;
+  for (long long s = 0; s < a.S; ++s) {
+    int nacc = 0;
+    bool accepted = true;
+    int it = 0;
+    while (it < a.thin) {
+      const int nb = min(SPEC_B, a.thin - it);
+      if (!ring_valid || step + (unsigned long long)nb > rbase + 32ull) {
+        // state-independent part of the next 32 steps, one step per lane
+        rbase = step;
+        const unsigned long long st_ = step + (unsigned long long)g;
+        const U4 bq = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
+        const int sl_ = choose_sublattice(m, bq.x);
+        const int j_ = (int)mulhi32(bq.y, (uint32_t)(m.sl_off[sl_ + 1] - m.sl_off[sl_]));
+        __syncwarp();
+        ring[g] = make_uint4((uint32_t)((sl_ << 24) | j_), (uint32_t)site_of_pos(m, sl_, j_), bq.z,
+                             __float_as_uint(log_u_float(bq.w)));
+        __syncwarp();
+        ring_valid = true;
+      }
+      const bool live = sg < nb;
+      const uint4 rq = ring[min((int)(step - rbase) + sg, 31)];
+      const int sl = (int)(rq.x >> 24), pos1 = (int)(rq.x & 0xffffffu), site1 = (int)rq.y;
+      const float lf = __uint_as_float(rq.w);
+
+      // ------------------------------ propose (one step per subgroup) -------------------------
+      int n = 0, s1, site2 = 0, s2 = 0, pos2 = 0;
+      s1 = occ[site1];
+      if (USHER == LMC_USHER_FLIP) {
+        // Flip.propose_step, mcusher.py:154-170
+        const int nc = m.sl_ncodes[sl];
+        int ci = (int)mulhi32(rq.z, (uint32_t)(nc - 1));
+        int p = nc;
+        for (int c = 0; c < nc; ++c) if (m.sl_codes[sl][c] == s1) { p = c; break; }
+        if (ci >= p) ++ci;
+        s2 = m.sl_codes[sl][ci];
+        n = 1;
+      } else {
+        // Swap.propose_step, mcusher.py:176-200
+        const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+        const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
+        const int k = ndiff > 0 ? (int)mulhi32(rq.z, (uint32_t)ndiff) : 0;
+        pos2 = spec_select_ne(m, planes, sl, s1, k, l);
+        if (ndiff > 0) {
+          site2 = site_of_pos(m, sl, pos2);
+          s2 = occ[site2];
+          n = 2;
+        }
+      }
+
+      // ------------------------------ evaluate ------------------------------------------------
+      double acc = 0.0, dmu = 0.0;
+      if (live && n > 0) {
+        if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy<false>(m, occ, dtab, site1, s1, s2, 0u, 0u, l);
+        else acc = spec_swap_energy(m, occ, dtab, site1, s1, s2, site2, s2, s1, l);
+      }
+      acc += __shfl_xor_sync(FULL, acc, 1);
+      acc += __shfl_xor_sync(FULL, acc, 2);
+      double dH = acc;
+      if (MU_POSSIBLE && m.muW) {
+        dmu = __ldg(m.mu + site1 * m.muW + s2) - __ldg(m.mu + site1 * m.muW + s1);
+        dH += nat_mu * dmu;
+      }
+
+      // ------------------------------ accept (metropolis.py:31-49) ----------------------------
+      const double exponent = __dmul_rn(-beta, dH);
+      const int af = accept_fast(exponent, lf);
+      bool acc_ = af != 0;
+      if (af < 0) {
+        const unsigned long long st_ = step + (unsigned long long)sg;
+        acc_ = exponent > log(u01(philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1).w));
+      }
+      const uint32_t bal = __ballot_sync(FULL, acc_ && live);
+      if (bal == 0u) {
+        step += (unsigned long long)nb;
+        it += nb;
+        accepted = false;
+        continue;
+      }
+
+      // ------------------------------ commit the first accepted step --------------------------
+      const int src = __ffs(bal) - 1;
+      const int j = src >> 2;
+      const int c_n = __shfl_sync(FULL, n, src);
+      const int c_sl = __shfl_sync(FULL, sl, src);
+      const int c_site1 = __shfl_sync(FULL, site1, src), c_s1 = __shfl_sync(FULL, s1, src), c_pos1 = __shfl_sync(FULL, pos1, src);
+      const int c_site2 = __shfl_sync(FULL, site2, src), c_s2 = __shfl_sync(FULL, s2, src), c_pos2 = __shfl_sync(FULL, pos2, src);
+      const double c_dH = __shfl_sync(FULL, dH, src);
+      const double c_dmu = __shfl_sync(FULL, dmu, src);
+      if (c_n == 2) {
+        if (g == 0) occ[c_site1] = (uint8_t)c_s2;
+        __syncwarp();
+        const RecChunk pre0 = load_records<G>(m, c_site1, g), pre1 = load_records<G>(m, c_site2, g);
+        (void)flip_energy_pair<G, KONE>(m, t, occ, c_site1, c_s1, c_s2, c_site2, c_s2, c_s1, stash0, stash0 + stash_stride,
+                                        g, pre0, pre1);
+        __syncwarp();
+        flip_features<G, KONE>(m, t, c_site1, stash0, feat, g, load_segment<G>(m, c_site1, g));
+        __syncwarp();
+        flip_features<G, KONE>(m, t, c_site2, stash0 + stash_stride, feat, g, load_segment<G>(m, c_site2, g));
+        if (g == 0) {
+          occ[c_site2] = (uint8_t)c_s1;
+          const int nw = m.sl_nwords[c_sl];
+          uint32_t* pl = planes + m.sl_plane_off[c_sl];
+          const uint32_t bit1 = 1u << (c_pos1 & 31), bit2 = 1u << (c_pos2 & 31);
+          pl[c_s1 * nw + (c_pos1 >> 5)] ^= bit1;
+          pl[c_s2 * nw + (c_pos1 >> 5)] ^= bit1;
+          pl[c_s2 * nw + (c_pos2 >> 5)] ^= bit2;
+          pl[c_s1 * nw + (c_pos2 >> 5)] ^= bit2;
+        }
+      } else if (c_n == 1) {
+        const RecChunk pre0 = load_records<G>(m, c_site1, g);
+        (void)flip_energy<G, KONE>(m, t, occ, c_site1, c_s1, c_s2, stash0, g, pre0);
+        __syncwarp();
+        flip_features<G, KONE>(m, t, c_site1, stash0, feat, g, load_segment<G>(m, c_site1, g));
+        if (g == 0) {
+          occ[c_site1] = (uint8_t)c_s2;
+          if (MU_POSSIBLE && m.muW) feat[m.muF] += c_dmu;
+          cnt[c_sl * LMC_MAX_CODES + c_s1]--;
+          cnt[c_sl * LMC_MAX_CODES + c_s2]++;
+          const int nw = m.sl_nwords[c_sl];
+          uint32_t* pl = planes + m.sl_plane_off[c_sl] + (c_pos1 >> 5);
+          const uint32_t bit = 1u << (c_pos1 & 31);
+          pl[c_s1 * nw] ^= bit;
+          pl[c_s2 * nw] ^= bit;
+        }
+      }
+      __syncwarp();
+      enth += c_dH;
+      ++nacc;
+      accepted = true;
+      step += (unsigned long long)(j + 1);
+      it += j + 1;
+    }  // thin
+
+    // ------------------------------ sample trace ------------------------------------------
+    nacc_total += nacc;
+    const size_t sw = (size_t)s * a.W + w;
+    if (a.tr_occ) {
+      int8_t* dst = a.tr_occ + sw * m.N;
+      if ((m.N & 15) == 0) {
+        if (g == 0) {
+          fence_proxy_async();
+          tma_store_1d(dst, occ, (uint32_t)m.N);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+      } else {
+        for (int i = g; i < m.N; i += G) dst[i] = (int8_t)occ[i];
+      }
+    }
+    if (a.tr_feat)
+      for (int f = g; f < m.F; f += G) a.tr_feat[sw * m.F + f] = feat[f];
+    if (g == 0) {
+      if (a.tr_enth) a.tr_enth[sw] = enth;
+      if (a.tr_acc) a.tr_acc[sw] = accepted ? 1 : 0;
+      if (a.tr_nacc) a.tr_nacc[sw] = nacc;
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------ final state ---------------------------------------------
+  for (int i = g; i < m.N; i += G) a.occ[(size_t)w * m.Npad + i] = (int8_t)occ[i];
+  for (int f = g; f < m.F; f += G) a.features[(size_t)w * m.F + f] = feat[f];
+  if (g == 0) {
+    a.enthalpy[w] = enth;
+    if (a.stats) {
+      atomicAdd(a.stats, (unsigned long long)nacc_total);
+      atomicAdd(a.stats + 1, (unsigned long long)(a.S * (long long)a.thin));
+    }
+  }
+}
+
+}  // namespace lmc

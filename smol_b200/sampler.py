@@ -110,7 +110,8 @@ class Sampler:
 
     def __init__(self, ensemble, kernel_type="Metropolis", step_type="swap", nwalkers=1, seeds=None,
                  temperature=None, wl_params=None, usher_kwargs=None, walker_id_base=0,
-                 group_size=0, block_threads=0, record_occupancy=True, device=None, kB_=kB):
+                 group_size=0, block_threads=0, record_occupancy=True, device=None, kB_=kB,
+                 spec_mode=0):
         from .engine import LmcEngine
         self.ensemble = ensemble
         self.kernel_type = kernel_type
@@ -160,6 +161,8 @@ class Sampler:
         self.engine = LmcEngine(self._packed, device=device)
         self.walker_id_base = int(walker_id_base)
         self.group_size, self.block_threads = int(group_size), int(block_threads)
+        # Metropolis flip/swap kernel: 0 auto (by measured acceptance), 1 classic, 2 speculative batch
+        self.spec_mode = int(spec_mode)
         self.record_occupancy = record_occupancy
         self.mckernels = [_KernelView(self, i) for i in range(self.nwalkers)]
         self._step_counter = 0
@@ -182,7 +185,7 @@ class Sampler:
             step_type = "flip" if getattr(ensemble, "chemical_potentials", None) is not None else "swap"
         if kernel_type is None:
             kernel_type = "Metropolis"
-        engine_kw = {k: kwargs.pop(k) for k in ("walker_id_base", "group_size", "block_threads",
+        engine_kw = {k: kwargs.pop(k) for k in ("walker_id_base", "group_size", "block_threads", "spec_mode",
                                                 "record_occupancy", "device") if k in kwargs}
         key = kernel_type.lower().replace("_", "").replace("-", "")
         temperature, wl = None, None
@@ -349,6 +352,7 @@ class Sampler:
             cfg.usher, cfg.kernel = self._usher, self._kernel
             cfg.num_samples, cfg.thin_by = n, thin_by
             cfg.group_size, cfg.block_threads = self.group_size, self.block_threads
+            cfg.spec_mode = self.spec_mode
             cfg.step_begin = self._step_counter
             cfg.seeds_dev, cfg.beta_dev = seeds.data_ptr(), beta.data_ptr()
             cfg.occ_dev, cfg.features_dev, cfg.enthalpy_dev = \

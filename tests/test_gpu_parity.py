@@ -242,3 +242,99 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
     q_ani = np.array([-2, -1])[occ[:, ncell:]].sum(axis=1)
     assert np.all(q_cat + q_ani == 0)
     assert smp.samples.step_efficiency() > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# speculative-batch kernel (csrc/lmc_spec.cuh): same chain as the classic kernel and the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["decomposition", "expansion"])
+@pytest.mark.parametrize("n,T,thin", [(2, 1000.0, 20), (4, 300.0, 7), (4, 1000.0, 64), (3, 1e5, 13)])
+def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin):
+    """low / medium / near-infinite temperature (acceptance ~0 .. ~1), sampling intervals that are not
+    multiples of the batch, aliased 2x2x2 cell; spec_mode=2 forces the speculative kernel, 1 the classic
+    one: both must reproduce the oracle chain bit for bit."""
+    import smol_b200 as S
+    O = _oracle()
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * n
+    coefs = M.fcc_coefs(sub)
+    gpu_p, ora_p = _processors(kind, sub, scm, coefs)
+    ens_g = S.Ensemble(gpu_p)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices))
+
+    W = 5
+    occ0 = M.random_occupancies(sub, scm, W, seed=3, balanced=True)
+    seeds = np.arange(500, 500 + W)
+    nsteps = thin * 30
+    smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, nsteps, thin, occ0, seeds, T=T,
+                            usher_kwargs=dict(spec_mode=2))
+    _compare_traces(smp, ref)
+    smp1 = S.Sampler.from_ensemble(ens_g, T, step_type="swap", nwalkers=W, seeds=list(seeds), spec_mode=1)
+    smp1.run(nsteps, occ0, thin_by=thin)
+    np.testing.assert_array_equal(smp1.samples.get_occupancies(flat=False),
+                                  smp.samples.get_occupancies(flat=False))
+    np.testing.assert_allclose(smp1.samples.get_enthalpies(flat=False), smp.samples.get_enthalpies(flat=False),
+                               rtol=1e-12, atol=1e-12 * np.abs(ref["enthalpy"]).max())
+
+
+@pytest.mark.parametrize("T", [400.0, 3000.0])
+def test_speculative_semigrand_flip_trajectory(cuda_device, T):
+    """ternary rocksalt cations, chemical potentials, single flips (no Ewald term): speculative kernel"""
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    sub = M.rocksalt_subspace()
+    scm = np.eye(3, dtype=int) * 3
+    rng = np.random.default_rng(5)
+    coefs = rng.normal(0, 0.05, sub.num_corr_functions)
+    it = L.cluster_interaction_tensors(sub, coefs)
+    mus = {"Li+": 0.0, "Mn3+": 0.3, "Ti4+": -0.2}
+    ens_g = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, it), chemical_potentials=mus)
+    ora_p = O.ClusterDecompositionProcessor(sub, scm, it)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices), chemical_potentials=mus)
+
+    W = 4
+    occ0 = M.random_occupancies(sub, scm, W, seed=8)
+    seeds = np.arange(70, 70 + W)
+    smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 330, 11, occ0, seeds, T=T, usher_kwargs=dict(spec_mode=2))
+    _compare_traces(smp, ref)
+
+
+def test_speculative_two_sublattice_swap(cuda_device):
+    """cation AND anion sublattices active (different record counts per site class), correlation basis"""
+    import smol_b200 as S
+    O = _oracle()
+    sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * 3
+    rng = np.random.default_rng(9)
+    coefs = rng.normal(0, 0.03, sub.num_corr_functions)
+    gpu_p, ora_p = _processors("expansion", sub, scm, coefs)
+    ens_g = S.Ensemble(gpu_p)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices))
+
+    W = 4
+    occ0 = M.random_occupancies(sub, scm, W, seed=12)
+    seeds = np.arange(33, 33 + W)
+    smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, 600, 25, occ0, seeds, T=1200.0, usher_kwargs=dict(spec_mode=2))
+    _compare_traces(smp, ref)
+
+
+def test_speculative_rejects_unsupported(cuda_device):
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 3
+    it = L.cluster_interaction_tensors(sub, M.fcc_coefs(sub))
+    ens = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, it))
+    occ0 = M.random_occupancies(sub, scm, 2, seed=4)
+    e0 = 0.0
+    smp = S.Sampler.from_ensemble(ens, e0 - 50.0, e0 + 50.0, 1.0, step_type="flip", kernel_type="WangLandau",
+                                  nwalkers=2, seeds=[1, 2], spec_mode=2)
+    with pytest.raises(RuntimeError, match="speculative"):
+        smp.run(100, occ0, thin_by=10)
