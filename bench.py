@@ -239,8 +239,12 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 20))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        smp.run(N * S_, occ_host, thin_by=N)          # warm-up (allocations, pinned staging)
-        smp.clear_samples()
+        # every timed step uploads the same EQUILIBRATED host occupancies (int32): the walkers' state at
+        # the end of the device-resident arm, so that both arms are timed in the same regime
+        occ_host = np.ascontiguousarray(eng.occupancy_to_int32(occ_dev, W, eng.row_stride).cpu().numpy(), dtype=np.int32)
+        for _ in range(2):
+            smp.run(N * S_, occ_host, thin_by=N)      # warm-up (allocations, pinned staging)
+            smp.clear_samples()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

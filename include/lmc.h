@@ -164,7 +164,7 @@ typedef struct LmcRunConfig {
 
 int lmc_version(void);
 const char* lmc_last_error(void);
-int lmc_row_stride(int num_sites); /* bytes per walker row of occ_dev (16-byte multiple) */
+int lmc_row_stride(int num_sites); /* bytes per walker row of occ_dev (16-byte multiple, at least one zero pad byte) */
 
 int lmc_model_create(const LmcModelDesc* desc, LmcModel** out);
 int lmc_model_destroy(LmcModel* model);
@@ -186,6 +186,12 @@ int lmc_delta_features(const LmcModel* model, const int8_t* occ_dev, int num_wal
 
 /* advance every walker by num_samples*thin_by attempted steps */
 int lmc_run(const LmcModel* model, const LmcRunConfig* cfg, void* stream);
+
+/* host-only (no device needed): tables of the speculative-batch kernel for a model description.
+ * info[8] = {built, code radix NC, entries per new-code plane, records per site, blocks, merged, table bytes,
+ * record bytes}; dtab_out [NC][L] doubles and rec_out [N][records] x 8 bytes are filled when large enough */
+int lmc_spec_tables_host(const LmcModelDesc* desc, int32_t* info, double* dtab_out, int64_t dtab_cap,
+                         uint8_t* rec_out, int64_t rec_cap);
 
 /* number of kernel launches issued by this library since load (for bench accounting) */
 int64_t lmc_launch_count(void);

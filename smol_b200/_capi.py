@@ -100,7 +100,7 @@ class LmcRunConfig(C.Structure):
 EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
-    "lmc_delta_features", "lmc_run", "lmc_launch_count",
+    "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host",
 )
 
 _LIB = None
@@ -134,6 +134,7 @@ def load():
     lib.lmc_delta_features.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P]
     lib.lmc_run.argtypes = [_P, C.POINTER(LmcRunConfig), _P]
     lib.lmc_launch_count.restype = C.c_int64
+    lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:
         raise RuntimeError("liblmc.so ABI version mismatch; rebuild with python -m smol_b200.build")
     _LIB = lib

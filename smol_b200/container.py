@@ -20,6 +20,7 @@ class SampleContainer:
         self._chunks = {name: [] for name in self._shapes}
         self._cache = {}
         self._thin = []
+        self._owned = []          # (release callback, base ndarray) of page-locked blocks the chunks view
         self.total_mc_steps = 0
 
     # ---- bookkeeping ----------------------------------------------------------------------
@@ -51,21 +52,36 @@ class SampleContainer:
     def traced_values(self):
         return list(self._shapes)
 
-    def append(self, traces: dict, thinned_by: int):
-        """container.py:384-397 for a whole block of samples at once."""
+    def append(self, traces: dict, thinned_by: int, owned=None):
+        """container.py:384-397 for a whole block of samples at once.
+
+        ``owned``: ``(release, base)`` pairs for trace arrays that are views of page-locked blocks
+        written directly by the device->host copy (no staging copy).  ``clear`` hands a block back
+        through ``release`` only when nothing outside this container still refers to it."""
         n = len(traces["enthalpy"])
         for name in self._shapes:
             self._chunks[name].append(traces[name])
+        if owned:
+            self._owned.extend(owned)
         self._cache.clear()
         self.total_mc_steps += n * thinned_by
         self._thin.append((n, thinned_by))
 
     def clear(self):
+        import sys
         for name in self._chunks:
             self._chunks[name] = []
         self._cache.clear()
         self.total_mc_steps = 0
         self._thin = []
+        owned, self._owned = self._owned, []
+        for i in range(len(owned)):
+            release, base = owned[i]
+            owned[i] = None
+            # references left: the local name and getrefcount's argument; anything more is a view
+            # the caller still holds, and its memory must not be recycled under it
+            if sys.getrefcount(base) <= 2:
+                release()
 
     def _full(self, name):
         if name not in self._cache:

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <array>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -63,7 +64,7 @@ static int upload(LmcModel* mdl, const T* host, size_t count, const T** out) {
 
 extern "C" int lmc_version(void) { return LMC_ABI_VERSION; }
 extern "C" const char* lmc_last_error(void) { return g_err.c_str(); }
-extern "C" int lmc_row_stride(int n) { return (n + 15) & ~15; }
+extern "C" int lmc_row_stride(int n) { return (n + 16) & ~15; }   // always at least one zero pad byte behind the row
 extern "C" int64_t lmc_launch_count(void) { return g_launches.load(); }
 extern "C" int lmc_model_num_features(const LmcModel* m) { return m ? m->dm.F : -1; }
 
@@ -72,6 +73,232 @@ extern "C" int lmc_model_destroy(LmcModel* m) {
   for (void* p : m->allocs) cudaFree(p);
   if (m->stats_host) cudaFreeHost(m->stats_host);
   delete m;
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// host-only table construction (no CUDA calls: also reachable through lmc_spec_tables_host for tests)
+// ------------------------------------------------------------------------------------------------
+static int host_orbits(const LmcModelDesc* d, std::vector<OrbDev>& orbs, std::vector<double>& tabA, bool& kone) {
+  const int nOrb = d->num_orbits;
+  orbs.assign(nOrb, OrbDev());
+  kone = true;
+  int tabA_len = 0;
+  for (int n = 0; n < nOrb; ++n) {
+    OrbDev& o = orbs[n];
+    o.ftab_off = d->orb_tab_off[n];
+    o.T = d->orb_tab_len[n];
+    o.K = d->orb_nfunc[n];
+    o.fidx = d->orb_fidx[n];
+    o.csize = d->orb_csize[n];
+    if (o.csize > LMC_MAX_CLUSTER_SITES) return fail("clusters with more than 4 sites are not supported");
+    if (o.T > 65535) return fail("flattened tensor longer than 65535");
+    o.row_off = (int)d->orb_row_off[n];
+    o.row_cnt = (int)(d->orb_row_off[n + 1] - d->orb_row_off[n]);
+    for (int i = 0; i < 4; ++i) o.stride[i] = d->orb_stride[n * LMC_MAX_CLUSTER_SITES + i];
+    o.w = d->orb_weight[n];
+    o.atab_off = tabA_len;
+    tabA_len += o.T;
+    if (o.K != 1) kone = false;
+  }
+  // phase-A table: raw tensors (K == 1 everywhere) or tensors contracted with nat * w
+  tabA.assign(tabA_len, 0.0);
+  for (int n = 0; n < nOrb; ++n) {
+    const OrbDev& o = orbs[n];
+    for (int t = 0; t < o.T; ++t) {
+      if (kone) {
+        tabA[o.atab_off + t] = d->ftab[o.ftab_off + t];
+      } else {
+        double s = 0.0;
+        for (int k = 0; k < o.K; ++k) s += d->natural_parameters[o.fidx + k] * o.w * d->ftab[o.ftab_off + k * o.T + t];
+        tabA[o.atab_off + t] = s;
+      }
+    }
+  }
+  return 0;
+}
+
+// Tables of the speculative-batch kernel (lmc_spec.cuh).  The local cluster records of a site are
+// MERGED into records with three gathered sites and ONE lookup in a pre-differenced table
+//   D[new][tbase + old + NC (c0 + NC (c1 + NC c2))] = sum over the merged terms of
+//                                                     coef * (T[idx after] - T[idx before])
+// (a 4-site cluster fills a record; a 3-site cluster takes a pair term along; pair / point terms go
+// three to a record), so a flip costs about half the table lookups of one lookup per cluster.
+// Unused gather slots point at the zero pad byte behind the occupancy row (site index N), so a
+// block with k used slots needs NC^(k+1) entries only.
+struct SpecTables {
+  int ok = 0, NC = 0, L = 0, NQ = 0, nblocks = 0, merged = 0;
+  std::vector<double> dtab;          // [NC][L]
+  std::vector<unsigned char> rec;    // [N][NQ] x uint2 (s0 | s1<<16, s2 | tbase<<16)
+};
+
+static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& orbs, const std::vector<double>& tabA,
+                              bool kone, SpecTables& sp) {
+  const int N = d->num_sites, nCls = d->num_classes, nOrb = d->num_orbits;
+  sp = SpecTables();
+  int NC = 2;
+  for (int n = 0; n < nOrb; ++n)
+    for (int i = 0; i < orbs[n].csize; ++i) {
+      const int hi = i == 0 ? orbs[n].T : orbs[n].stride[i - 1];
+      if (orbs[n].stride[i] > 0) NC = std::max(NC, hi / orbs[n].stride[i]);
+    }
+  if (NC > LMC_MAX_CODES || nCls <= 0 || N >= 65535) return;
+  if (const char* e = getenv("LMC_SPEC_TABLES")) { if (atoi(e) == 0) return; }
+  std::vector<int> noth(nCls, 0);
+  for (int c = 0; c < nCls; ++c) {
+    const int* st = d->cls_stride + c * 4;
+    int n = 0;
+    while (n < 3 && st[n] > 0) ++n;
+    for (int i = n; i < 3; ++i) if (st[i] != 0) return;   // other sites must be compacted to the first slots
+    noth[c] = std::max(n, 1);                              // point terms take a (dummy) slot
+  }
+  // contribution of a class-c record for other-site codes oc[0..], old -> new
+  auto term = [&](int c, const int* oc, int oldc, int newc) -> double {
+    const OrbDev& o = orbs[d->cls_orbit[c]];
+    const int* st = d->cls_stride + c * 4;
+    const double coef = kone ? d->natural_parameters[o.fidx] * o.w : 1.0;
+    long ii = (long)st[3] * oldc, ff = (long)st[3] * newc;
+    for (int i = 0; i < 3 && st[i] > 0; ++i) { ii += (long)st[i] * oc[i]; ff += (long)st[i] * oc[i]; }
+    if (ii >= o.T || ff >= o.T || newc == oldc) return 0.0;
+    return coef * (tabA[o.atab_off + ff] - tabA[o.atab_off + ii]);
+  };
+  struct Merged { int cls[3]; uint16_t site[3]; };
+  const uint16_t DUMMY = (uint16_t)N;   // zero pad byte of the occupancy row
+  int max_level = 2;
+  if (const char* e = getenv("LMC_SPEC_MERGE")) max_level = atoi(e) ? 2 : 1;
+  size_t budget = 64 * 1024;   // bytes of shared memory the difference table may take
+  if (const char* e = getenv("LMC_SPEC_TABLE_KB")) budget = (size_t)atoi(e) * 1024;
+  for (int level = max_level; level >= 1 && !sp.ok; --level) {   // 2: merged records, 1: one cluster per record
+    // deduplicated [new][entry] blocks; block 0 = zeros (padding records)
+    std::vector<std::vector<double>> store;
+    std::vector<long> store_base;
+    std::vector<std::array<int, 4>> keys;   // (cls0, cls1, cls2, store index)
+    long L = (long)NC * NC * NC * NC;
+    store.emplace_back((size_t)L * NC, 0.0);
+    store_base.push_back(0);
+    auto block_of = [&](const int* cls) -> int {
+      for (const auto& k : keys)
+        if (k[0] == cls[0] && k[1] == cls[1] && k[2] == cls[2]) return k[3];
+      int used = 0;
+      for (int k = 0; k < 3 && cls[k] >= 0; ++k) used += noth[cls[k]];
+      long combos = 1;
+      for (int i = 0; i < used; ++i) combos *= NC;
+      const long len = combos * NC;
+      std::vector<double> blk((size_t)len * NC, 0.0);
+      for (long q = 0; q < combos; ++q) {
+        const int code[3] = {(int)(q % NC), (int)((q / NC) % NC), (int)(q / ((long)NC * NC))};
+        for (int oldc = 0; oldc < NC; ++oldc)
+          for (int newc = 0; newc < NC; ++newc) {
+            double v = 0.0;
+            int slot = 0;
+            for (int k = 0; k < 3 && cls[k] >= 0; ++k) { v += term(cls[k], code + slot, oldc, newc); slot += noth[cls[k]]; }
+            blk[(size_t)newc * len + oldc + NC * q] = v;
+          }
+      }
+      int idx = -1;
+      for (size_t b = 1; b < store.size() && idx < 0; ++b)
+        if (store[b].size() == blk.size() && memcmp(store[b].data(), blk.data(), blk.size() * 8) == 0) idx = (int)b;
+      if (idx < 0) {
+        store.push_back(std::move(blk));
+        store_base.push_back(L);
+        L += len;
+        idx = (int)store.size() - 1;
+      }
+      keys.push_back({cls[0], cls[1], cls[2], idx});
+      return idx;
+    };
+    std::vector<std::vector<Merged>> merged(N);
+    size_t nq = 0;
+    auto psite = [&](int c, const uint16_t* rc) { return d->cls_stride[c * 4] > 0 ? rc[0] : DUMMY; };   // point terms gather nothing
+    for (int i = 0; i < N; ++i) {
+      std::vector<std::vector<const uint16_t*>> P(nCls);   // pair / point records by class
+      std::vector<const uint16_t*> T;
+      std::vector<Merged>& out = merged[i];
+      for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) {
+        const uint16_t* rc = d->site_rec + r * 4;
+        const int c = rc[3], n = noth[c];
+        if (n == 3) out.push_back(Merged{{c, -1, -1}, {rc[0], rc[1], rc[2]}});
+        else if (n == 2 && level == 1) out.push_back(Merged{{c, -1, -1}, {rc[0], rc[1], DUMMY}});
+        else if (n == 2) T.push_back(rc);
+        else if (level == 1) out.push_back(Merged{{c, -1, -1}, {psite(c, rc), DUMMY, DUMMY}});
+        else P[c].push_back(rc);
+      }
+      std::vector<size_t> head(nCls, 0);
+      auto remaining = [&](int c) { return P[c].size() - head[c]; };
+      for (const uint16_t* t : T) {   // a 3-site cluster takes a pair term of the fullest class along
+        int best = -1;
+        for (int c = 0; c < nCls; ++c)
+          if (remaining(c) > 0 && (best < 0 || remaining(c) > remaining(best))) best = c;
+        if (best >= 0) {
+          const uint16_t* pr = P[best][head[best]++];
+          out.push_back(Merged{{(int)t[3], best, -1}, {t[0], t[1], psite(best, pr)}});
+        } else {
+          out.push_back(Merged{{(int)t[3], -1, -1}, {t[0], t[1], DUMMY}});
+        }
+      }
+      for (int c = 0; c < nCls; ++c)
+        while (remaining(c) >= 3) {
+          const uint16_t *a = P[c][head[c]], *b = P[c][head[c] + 1], *e = P[c][head[c] + 2];
+          head[c] += 3;
+          out.push_back(Merged{{c, c, c}, {psite(c, a), psite(c, b), psite(c, e)}});
+        }
+      Merged cur{{-1, -1, -1}, {DUMMY, DUMMY, DUMMY}};
+      int fill = 0;
+      for (int c = 0; c < nCls; ++c)
+        while (remaining(c) > 0) {
+          const uint16_t* pr = P[c][head[c]++];
+          cur.cls[fill] = c; cur.site[fill] = psite(c, pr);
+          if (++fill == 3) { out.push_back(cur); cur = Merged{{-1, -1, -1}, {DUMMY, DUMMY, DUMMY}}; fill = 0; }
+        }
+      if (fill) out.push_back(cur);
+      nq = std::max(nq, out.size());
+    }
+    const int NQ = (int)((nq + 7) & ~size_t(7));
+    std::vector<unsigned char> rec((size_t)std::max(N * NQ * 8, 16), 0);
+    bool ok = true;
+    for (int i = 0; i < N && ok; ++i) {
+      uint32_t* p = reinterpret_cast<uint32_t*>(rec.data() + (size_t)i * NQ * 8);
+      for (int k = 0; k < NQ; ++k) {
+        if (k < (int)merged[i].size()) {
+          const Merged& mr = merged[i][k];
+          const long tb = store_base[block_of(mr.cls)];
+          if (L > 65535 || (size_t)L * NC * 8 > budget) { ok = false; break; }
+          p[2 * k] = (uint32_t)mr.site[0] | ((uint32_t)mr.site[1] << 16);
+          p[2 * k + 1] = (uint32_t)mr.site[2] | ((uint32_t)tb << 16);
+        } else {   // padding: three zero bytes, zero block
+          p[2 * k] = (uint32_t)DUMMY | ((uint32_t)DUMMY << 16);
+          p[2 * k + 1] = (uint32_t)DUMMY;
+        }
+      }
+    }
+    if (!ok) continue;
+    sp.dtab.assign((size_t)L * NC, 0.0);
+    for (size_t b = 0; b < store.size(); ++b) {
+      const size_t len = store[b].size() / NC;
+      for (int newc = 0; newc < NC; ++newc)
+        memcpy(&sp.dtab[(size_t)newc * L + store_base[b]], &store[b][(size_t)newc * len], len * 8);
+    }
+    sp.rec = std::move(rec);
+    sp.ok = 1; sp.NC = NC; sp.L = (int)L; sp.NQ = NQ; sp.nblocks = (int)store.size(); sp.merged = level == 2;
+  }
+}
+
+// host-only: build the tables of the speculative kernel for a model description (tests / diagnostics)
+// info = {ok, NC, L, NQ, nblocks, merged, table bytes, record bytes}
+extern "C" int lmc_spec_tables_host(const LmcModelDesc* d, int32_t* info, double* dtab_out, int64_t dtab_cap,
+                                    uint8_t* rec_out, int64_t rec_cap) {
+  if (!d || !info) return fail("null argument");
+  std::vector<OrbDev> orbs;
+  std::vector<double> tabA;
+  bool kone = true;
+  if (host_orbits(d, orbs, tabA, kone)) return -1;
+  SpecTables sp;
+  build_spec_tables(d, orbs, tabA, kone, sp);
+  info[0] = sp.ok; info[1] = sp.NC; info[2] = sp.L; info[3] = sp.NQ; info[4] = sp.nblocks; info[5] = sp.merged;
+  info[6] = (int32_t)(sp.dtab.size() * 8); info[7] = (int32_t)sp.rec.size();
+  if (dtab_out && (int64_t)sp.dtab.size() <= dtab_cap) memcpy(dtab_out, sp.dtab.data(), sp.dtab.size() * 8);
+  if (rec_out && (int64_t)sp.rec.size() <= rec_cap) memcpy(rec_out, sp.rec.data(), sp.rec.size());
   return 0;
 }
 
@@ -114,43 +341,14 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     lmc_model_destroy(mdl);                                          \
     return rc;                                                       \
   }
-  // orbit descriptors
-  std::vector<OrbDev> orbs(m.nOrb);
+  // orbit descriptors + phase-A table
+  std::vector<OrbDev> orbs;
+  std::vector<double> tabA;
   bool kone = true;
-  int tabA_len = 0;
-  for (int n = 0; n < m.nOrb; ++n) {
-    OrbDev& o = orbs[n];
-    o.ftab_off = d->orb_tab_off[n];
-    o.T = d->orb_tab_len[n];
-    o.K = d->orb_nfunc[n];
-    o.fidx = d->orb_fidx[n];
-    o.csize = d->orb_csize[n];
-    if (o.csize > LMC_MAX_CLUSTER_SITES) { lmc_model_destroy(mdl); return fail("clusters with more than 4 sites are not supported"); }
-    if (o.T > 65535) { lmc_model_destroy(mdl); return fail("flattened tensor longer than 65535"); }
-    o.row_off = (int)d->orb_row_off[n];
-    o.row_cnt = (int)(d->orb_row_off[n + 1] - d->orb_row_off[n]);
-    for (int i = 0; i < 4; ++i) o.stride[i] = d->orb_stride[n * LMC_MAX_CLUSTER_SITES + i];
-    o.w = d->orb_weight[n];
-    o.atab_off = tabA_len;
-    tabA_len += o.T;
-    if (o.K != 1) kone = false;
-  }
+  if (host_orbits(d, orbs, tabA, kone)) { lmc_model_destroy(mdl); return -1; }
   m.kone = kone ? 1 : 0;
+  const int tabA_len = (int)tabA.size();
   m.tabA_len = tabA_len;
-  // phase-A table: raw tensors (K == 1 everywhere) or tensors contracted with nat * w
-  std::vector<double> tabA(tabA_len);
-  for (int n = 0; n < m.nOrb; ++n) {
-    const OrbDev& o = orbs[n];
-    for (int t = 0; t < o.T; ++t) {
-      if (kone) {
-        tabA[o.atab_off + t] = d->ftab[o.ftab_off + t];
-      } else {
-        double s = 0.0;
-        for (int k = 0; k < o.K; ++k) s += d->natural_parameters[o.fidx + k] * o.w * d->ftab[o.ftab_off + k * o.T + t];
-        tabA[o.atab_off + t] = s;
-      }
-    }
-  }
   std::vector<double> qtab;
   // Ewald.  Generic form: keep the TRANSPOSE so that the reference's column gathers become row
   // gathers.  Ewald matrices are charge products times a geometric site kernel,
@@ -230,99 +428,12 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     }
     UP(int, d->ewald_inds, (size_t)m.N * m.ewW, m.ewInds);
   }
-  // speculative-batch kernel tables (lmc_spec.cuh).  Records are regrouped by the number of OTHER
-  // sites (1 incl. point terms, 2, 3) and carry the base of their class in a difference table
-  //   D[new][tbase + c0 + NC c1 + NC^2 c2 + NC^n old] = coef * (T[idx after] - T[idx before])
-  // so that one record costs one occupancy gather per other site and ONE table lookup.
-  std::vector<double> dtab;
-  std::vector<unsigned char> sprec;
-  {
-    int NC = 2;
-    for (int n = 0; n < m.nOrb; ++n)
-      for (int i = 0; i < orbs[n].csize; ++i) {
-        const int hi = i == 0 ? orbs[n].T : orbs[n].stride[i - 1];
-        if (orbs[n].stride[i] > 0) NC = std::max(NC, hi / orbs[n].stride[i]);
-      }
-    bool ok = NC <= LMC_MAX_CODES && m.nCls > 0;
-    const long Z = (long)NC * NC * NC * NC;   // zero block hit by the padding records
-    std::vector<int> noth(m.nCls, 0), tbase(m.nCls, 0);
-    // per-class difference blocks [new][entry]; identical blocks (symmetric tensors: every position of
-    // the flipped site in the cluster gives the same block) are stored once
-    std::vector<std::vector<double>> blocks;
-    std::vector<long> block_base, block_len;
-    long L = Z;
-    for (int c = 0; c < m.nCls && ok; ++c) {
-      const int* st = d->cls_stride + c * 4;
-      int n = 0;
-      while (n < 3 && st[n] > 0) ++n;
-      for (int i = n; i < 3; ++i) ok = ok && st[i] == 0;   // other sites are compacted to the first slots
-      if (!ok) break;
-      n = std::max(n, 1);
-      noth[c] = n;
-      const OrbDev& o = orbs[d->cls_orbit[c]];
-      const double coef = kone ? d->natural_parameters[o.fidx] * o.w : 1.0;
-      long combos = 1;
-      for (int i = 0; i < n; ++i) combos *= NC;
-      const long len = combos * NC;
-      std::vector<double> blk((size_t)len * NC, 0.0);
-      for (long q = 0; q < combos; ++q) {
-        long ii0 = 0, r = q;
-        for (int i = 0; i < n; ++i) { ii0 += (long)st[i] * (r % NC); r /= NC; }   // st[i] == 0 for the dummy slot of point terms
-        for (int oldc = 0; oldc < NC; ++oldc)
-          for (int newc = 0; newc < NC; ++newc) {
-            const long ii = ii0 + (long)st[3] * oldc, ff = ii0 + (long)st[3] * newc;
-            if (ii >= o.T || ff >= o.T || newc == oldc) continue;
-            blk[(size_t)newc * len + q + combos * oldc] = coef * (tabA[o.atab_off + ff] - tabA[o.atab_off + ii]);
-          }
-      }
-      size_t hit = blocks.size();
-      for (size_t b = 0; b < blocks.size(); ++b)
-        if (block_len[b] == len && memcmp(blocks[b].data(), blk.data(), blk.size() * 8) == 0) { hit = b; break; }
-      if (hit == blocks.size()) {
-        blocks.push_back(std::move(blk));
-        block_base.push_back(L);
-        block_len.push_back(len);
-        L += len;
-      }
-      tbase[c] = (int)block_base[hit];
-    }
-    ok = ok && L <= 65535 && (size_t)L * NC * 8 <= 64 * 1024;
-    if (const char* e = getenv("LMC_SPEC_TABLES")) ok = ok && atoi(e) != 0;
-    if (ok) {
-      dtab.assign((size_t)L * NC, 0.0);
-      for (size_t b = 0; b < blocks.size(); ++b)
-        for (int newc = 0; newc < NC; ++newc)
-          memcpy(&dtab[(size_t)newc * L + block_base[b]], &blocks[b][(size_t)newc * block_len[b]], (size_t)block_len[b] * 8);
-      // per-site record lists by number of other sites
-      int n1 = 0, n2 = 0, n3 = 0;
-      for (int i = 0; i < m.N; ++i) {
-        int k1 = 0, k2 = 0, k3 = 0;
-        for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) {
-          const int n = noth[d->site_rec[r * 4 + 3]];
-          (n == 1 ? k1 : n == 2 ? k2 : k3)++;
-        }
-        n1 = std::max(n1, k1); n2 = std::max(n2, k2); n3 = std::max(n3, k3);
-      }
-      m.spN1 = (n1 + 15) & ~15; m.spN2 = (n2 + 7) & ~7; m.spN3 = (n3 + 7) & ~7;
-      m.spSb = m.spN1 * 4 + (m.spN2 + m.spN3) * 8;
-      sprec.assign((size_t)std::max(m.N * m.spSb, 16), 0);   // zero records: site 0, tbase 0 (zero block)
-      for (int i = 0; i < m.N; ++i) {
-        uint32_t* p1 = reinterpret_cast<uint32_t*>(sprec.data() + (size_t)i * m.spSb);
-        uint32_t* p2 = p1 + m.spN1;
-        uint32_t* p3 = p2 + 2 * m.spN2;
-        int k1 = 0, k2 = 0, k3 = 0;
-        for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) {
-          const uint16_t* rc = d->site_rec + r * 4;
-          const int c = rc[3], n = noth[c];
-          const uint32_t tb = (uint32_t)tbase[c];
-          if (n == 1) p1[k1++] = (uint32_t)rc[0] | (tb << 16);
-          else if (n == 2) { p2[2 * k2] = (uint32_t)rc[0] | ((uint32_t)rc[1] << 16); p2[2 * k2 + 1] = tb << 16; ++k2; }
-          else { p3[2 * k3] = (uint32_t)rc[0] | ((uint32_t)rc[1] << 16); p3[2 * k3 + 1] = (uint32_t)rc[2] | (tb << 16); ++k3; }
-        }
-      }
-      m.spOK = 1; m.spNC = NC; m.spL = (int)L;
-    }
-  }
+  // speculative-batch kernel tables (merged records + pre-differenced table), see build_spec_tables
+  SpecTables sp;
+  build_spec_tables(d, orbs, tabA, kone, sp);
+  const std::vector<double>& dtab = sp.dtab;
+  const std::vector<unsigned char>& sprec = sp.rec;
+  m.spOK = sp.ok; m.spNC = sp.NC; m.spL = sp.L; m.spNQ = sp.NQ; m.spSb = sp.NQ * 8;
   // blob: cls (nCls + 1 entries, the last is the all-zero padding class) | tabA | nat | orb
   {
     const int C = m.nCls + 1;
@@ -531,7 +642,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const bool spec_ok = m.spOK && !ewald && c->kernel == LMC_KERNEL_METROPOLIS &&
                        (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
   if (spec_mode == 2 && !spec_ok) return fail("the speculative kernel supports Metropolis flip/swap steps without Ewald term only");
-  const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35));
+  // auto: only while the staged tables leave room for a full complement of resident walkers per SM
+  const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35 && m.blob_bytes <= 24 * 1024));
   if (use_spec) G = 32;
   if (G == 0) {
     // measured on B200 (profiles/): a full warp per walker wins while all walkers fit in one wave

@@ -62,14 +62,14 @@ struct DevModel {
   int tf_dim_code[LMC_MAX_DIMS];
   double tf_sw;
   const double* lgam;      // [max_n + 2] ln(n!) table for the table-flip a-priori factor
-  // speculative-batch kernel (lmc_spec.cuh): size-sorted compact records + pre-differenced tables
+  // speculative-batch kernel (lmc_spec.cuh): merged three-gather records + pre-differenced tables
   int spOK;                // tables built (0: model outside the limits of the speculative kernel)
   int spNC;                // code radix of the difference-table index (max species per site)
   int spL;                 // doubles per new-code plane of the difference table
-  int spN1, spN2, spN3;    // padded records per site with 1 / 2 / 3 other sites (multiples of 16 / 8 / 8)
-  int spSb;                // bytes per site of sp_rec
+  int spNQ;                // merged records per site (padded to a multiple of 8 with zero records)
+  int spSb;                // bytes per site of sp_rec (8 spNQ)
   int off_dtab;            // offset of the difference table [spNC][spL] in the blob
-  const unsigned char* sp_rec;  // [N][spSb]: [spN1 x u32 (site | tbase<<16)][(spN2+spN3) x uint2 (s0 | s1<<16, s2 | tbase<<16)]
+  const unsigned char* sp_rec;  // [N][spNQ] x uint2 (s0 | s1<<16, s2 | tbase<<16)
 };
 
 struct RunArgs {

@@ -12,8 +12,9 @@
 // is the sequential Metropolis chain of smol (kernel/base.py:145-166, metropolis.py:31-49), step
 // for step; only the amount of wasted work depends on the acceptance ratio.
 //
-// Evaluation uses the size-sorted compact records and the pre-differenced table built at model
-// creation (lmc_api.cu): one occupancy gather per other site and one table lookup per record.
+// Evaluation uses the merged records and the pre-differenced table built at model creation
+// (lmc_api.cu): three occupancy byte gathers and ONE table lookup per record, where a record
+// carries a 4-site cluster, a 3-site cluster plus a pair term, or three pair/point terms.
 // The accepted step is re-evaluated by the whole warp with the classic record path, which leaves
 // the per-record differences in the stash for the feature update (cluster order of
 // evaluator.pyx:253-263).
@@ -25,6 +26,21 @@ namespace lmc {
 constexpr int SPEC_SG = 4;
 constexpr int SPEC_B = 32 / SPEC_SG;
 
+// position of the (rem+1)-th set bit of b (rem < popc(b))
+__device__ __forceinline__ int spec_nth_bit(uint32_t b, int rem) {
+  int pos = 0;
+  const int c16 = __popc(b & 0xffffu);
+  if (rem >= c16) { rem -= c16; pos += 16; b >>= 16; }
+  const int c8 = __popc(b & 0xffu);
+  if (rem >= c8) { rem -= c8; pos += 8; b >>= 8; }
+  const int c4 = __popc(b & 0xfu);
+  if (rem >= c4) { rem -= c4; pos += 4; b >>= 4; }
+  const int c2 = __popc(b & 0x3u);
+  if (rem >= c2) { rem -= c2; pos += 2; b >>= 2; }
+  if (rem >= (int)(b & 1u)) pos += 1;
+  return pos;
+}
+
 // k-th (0-based) active position of sublattice `sl` whose code differs from `code`; the four lanes
 // of a subgroup split the plane words.  Called by all 32 lanes (full-mask shuffles of width 4).
 __device__ __forceinline__ int spec_select_ne(const DevModel& m, const uint32_t* planes, int sl, int code, int k, int l) {
@@ -34,42 +50,51 @@ __device__ __forceinline__ int spec_select_ne(const DevModel& m, const uint32_t*
   const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
   const int cw = (nw + SPEC_SG - 1) / SPEC_SG;
   const int lo = l * cw;
-  int cnt = 0;
-  for (int i = 0; i < cw; ++i) {
-    const int wd = lo + i;
-    uint32_t b = 0u;
-    if (wd < nw) b = ~pl[wd] & (wd == nw - 1 ? tail : 0xffffffffu);
-    cnt += __popc(b);
-  }
-  int incl = cnt;
-  int tt = __shfl_up_sync(0xffffffffu, incl, 1, SPEC_SG);
-  if (l >= 1) incl += tt;
-  tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
-  if (l >= 2) incl += tt;
-  int rem = k - (incl - cnt);
-  const bool found = rem >= 0 && rem < cnt;
   int res = 0;
-  if (found) {
+  bool found;
+  if (cw <= 4) {
+    // up to four words per lane (<= 512 active sites): straight-line, no divergence
+    uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+    if (lo < nw) w0 = ~pl[lo] & (lo == nw - 1 ? tail : 0xffffffffu);
+    if (cw > 1 && lo + 1 < nw) w1 = ~pl[lo + 1] & (lo + 1 == nw - 1 ? tail : 0xffffffffu);
+    if (cw > 2 && lo + 2 < nw) w2 = ~pl[lo + 2] & (lo + 2 == nw - 1 ? tail : 0xffffffffu);
+    if (cw > 3 && lo + 3 < nw) w3 = ~pl[lo + 3] & (lo + 3 == nw - 1 ? tail : 0xffffffffu);
+    const int p1 = __popc(w0), p2 = p1 + __popc(w1), p3 = p2 + __popc(w2), cnt = p3 + __popc(w3);
+    int incl = cnt;
+    int tt = __shfl_up_sync(0xffffffffu, incl, 1, SPEC_SG);
+    if (l >= 1) incl += tt;
+    tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
+    if (l >= 2) incl += tt;
+    int rem = k - (incl - cnt);
+    found = rem >= 0 && rem < cnt;
+    const int wi = (rem >= p1) + (rem >= p2) + (rem >= p3);
+    const uint32_t word = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
+    rem -= wi == 0 ? 0 : wi == 1 ? p1 : wi == 2 ? p2 : p3;
+    res = (lo + wi) * 32 + spec_nth_bit(word, found ? rem : 0);
+  } else {
+    int cnt = 0;
     for (int i = 0; i < cw; ++i) {
       const int wd = lo + i;
       uint32_t b = 0u;
       if (wd < nw) b = ~pl[wd] & (wd == nw - 1 ? tail : 0xffffffffu);
-      const int c = __popc(b);
-      if (rem < c) {
-        int pos = 0;
-        const int c16 = __popc(b & 0xffffu);
-        if (rem >= c16) { rem -= c16; pos += 16; b >>= 16; }
-        const int c8 = __popc(b & 0xffu);
-        if (rem >= c8) { rem -= c8; pos += 8; b >>= 8; }
-        const int c4 = __popc(b & 0xfu);
-        if (rem >= c4) { rem -= c4; pos += 4; b >>= 4; }
-        const int c2 = __popc(b & 0x3u);
-        if (rem >= c2) { rem -= c2; pos += 2; b >>= 2; }
-        if (rem >= (int)(b & 1u)) pos += 1;
-        res = wd * 32 + pos;
-        break;
+      cnt += __popc(b);
+    }
+    int incl = cnt;
+    int tt = __shfl_up_sync(0xffffffffu, incl, 1, SPEC_SG);
+    if (l >= 1) incl += tt;
+    tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
+    if (l >= 2) incl += tt;
+    int rem = k - (incl - cnt);
+    found = rem >= 0 && rem < cnt;
+    if (found) {
+      for (int i = 0; i < cw; ++i) {
+        const int wd = lo + i;
+        uint32_t b = 0u;
+        if (wd < nw) b = ~pl[wd] & (wd == nw - 1 ? tail : 0xffffffffu);
+        const int c = __popc(b);
+        if (rem < c) { res = wd * 32 + spec_nth_bit(b, rem); break; }
+        rem -= c;
       }
-      rem -= c;
     }
   }
   const uint32_t bal = __ballot_sync(0xffffffffu, found);
@@ -86,50 +111,33 @@ __device__ __forceinline__ uint32_t spec_code(const uint8_t* occ, uint32_t s, ui
   return c;
 }
 
+// two merged records (one 16-byte chunk): three gathers + one table lookup each
 template <bool PATCH>
-__device__ __forceinline__ void spec_pairs4(const uint8_t* occ, const double* Dn, const uint4 v, uint32_t old1, uint32_t ps,
-                                            uint32_t pc, double& a0, double& a1) {
-  a0 += Dn[(v.x >> 16) + spec_code<PATCH>(occ, v.x & 0xffffu, ps, pc) + old1];
-  a1 += Dn[(v.y >> 16) + spec_code<PATCH>(occ, v.y & 0xffffu, ps, pc) + old1];
-  a0 += Dn[(v.z >> 16) + spec_code<PATCH>(occ, v.z & 0xffffu, ps, pc) + old1];
-  a1 += Dn[(v.w >> 16) + spec_code<PATCH>(occ, v.w & 0xffffu, ps, pc) + old1];
-}
-template <bool PATCH>
-__device__ __forceinline__ void spec_trip2(const uint8_t* occ, const double* Dn, const uint4 v, uint32_t NC, uint32_t old2,
-                                           uint32_t ps, uint32_t pc, double& a0, double& a1) {
-  a0 += Dn[(v.y >> 16) + spec_code<PATCH>(occ, v.x & 0xffffu, ps, pc) + NC * spec_code<PATCH>(occ, v.x >> 16, ps, pc) + old2];
-  a1 += Dn[(v.w >> 16) + spec_code<PATCH>(occ, v.z & 0xffffu, ps, pc) + NC * spec_code<PATCH>(occ, v.z >> 16, ps, pc) + old2];
-}
-template <bool PATCH>
-__device__ __forceinline__ void spec_quad2(const uint8_t* occ, const double* Dn, const uint4 v, uint32_t NC, uint32_t old3,
-                                           uint32_t ps, uint32_t pc, double& a0, double& a1) {
-  a0 += Dn[(v.y >> 16) + spec_code<PATCH>(occ, v.x & 0xffffu, ps, pc) +
-           NC * (spec_code<PATCH>(occ, v.x >> 16, ps, pc) + NC * spec_code<PATCH>(occ, v.y & 0xffffu, ps, pc)) + old3];
-  a1 += Dn[(v.w >> 16) + spec_code<PATCH>(occ, v.z & 0xffffu, ps, pc) +
-           NC * (spec_code<PATCH>(occ, v.z >> 16, ps, pc) + NC * spec_code<PATCH>(occ, v.w & 0xffffu, ps, pc)) + old3];
+__device__ __forceinline__ void spec_rec2(const uint8_t* occ, const double* Dn, const uint4 v, uint32_t NC, uint32_t old3,
+                                          uint32_t ps, uint32_t pc, double& a0, double& a1) {
+  a0 += Dn[(v.y >> 16) + old3 +
+           NC * (spec_code<PATCH>(occ, v.x & 0xffffu, ps, pc) +
+                 NC * (spec_code<PATCH>(occ, v.x >> 16, ps, pc) + NC * spec_code<PATCH>(occ, v.y & 0xffffu, ps, pc)))];
+  a1 += Dn[(v.w >> 16) + old3 +
+           NC * (spec_code<PATCH>(occ, v.z & 0xffffu, ps, pc) +
+                 NC * (spec_code<PATCH>(occ, v.z >> 16, ps, pc) + NC * spec_code<PATCH>(occ, v.w & 0xffffu, ps, pc)))];
 }
 
-// scaled energy change of one flip (lane l of 4 takes every fourth 16-byte chunk of the record lists)
-template <bool PATCH>
+// scaled energy change of one flip (lane l of 4 takes every fourth 16-byte chunk of the record list)
 __device__ __forceinline__ double spec_flip_energy(const DevModel& m, const uint8_t* occ, const double* dtab, int site,
-                                                   int oldc, int newc, uint32_t ps, uint32_t pc, int l) {
+                                                   int oldc, int newc, int l) {
   const uint4* rp = reinterpret_cast<const uint4*>(m.sp_rec + (size_t)site * m.spSb) + l;
   const double* Dn = dtab + newc * m.spL;
   const uint32_t NC = (uint32_t)m.spNC;
-  const uint32_t old1 = NC * (uint32_t)oldc, old2 = NC * old1, old3 = NC * old2;
+  const uint32_t old3 = (uint32_t)oldc;   // the old code is the fastest index of a block
   double a0 = 0.0, a1 = 0.0;
-  const int c1 = m.spN1 >> 4, c2 = m.spN2 >> 3, c3 = m.spN3 >> 3;
-#pragma unroll 2
-  for (int q = 0; q < c1; ++q) spec_pairs4<PATCH>(occ, Dn, __ldg(rp + q * SPEC_SG), old1, ps, pc, a0, a1);
-  rp += c1 * SPEC_SG;
-#pragma unroll 2
-  for (int q = 0; q < c2; ++q) spec_trip2<PATCH>(occ, Dn, __ldg(rp + q * SPEC_SG), NC, old2, ps, pc, a0, a1);
-  rp += c2 * SPEC_SG;
-  for (int q = 0; q < c3; ++q) spec_quad2<PATCH>(occ, Dn, __ldg(rp + q * SPEC_SG), NC, old3, ps, pc, a0, a1);
+  const int nchunk = m.spNQ >> 3;
+#pragma unroll 3
+  for (int q = 0; q < nchunk; ++q) spec_rec2<false>(occ, Dn, __ldg(rp + q * SPEC_SG), NC, old3, 0u, 0u, a0, a1);
   return a0 + a1;
 }
 
-// both flips of a swap in the same loops (independent chains: twice the ILP); flip b sees flip a
+// both flips of a swap in the same loop (independent chains: twice the ILP); flip b sees flip a
 // applied through the PATCH of its gathers (sequential semantics of expansion.py:217-229)
 __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint8_t* occ, const double* dtab, int sitea,
                                                    int olda, int newa, int siteb, int oldb, int newb, int l) {
@@ -138,29 +146,15 @@ __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint
   const double* Da = dtab + newa * m.spL;
   const double* Db = dtab + newb * m.spL;
   const uint32_t NC = (uint32_t)m.spNC;
-  const uint32_t oa1 = NC * (uint32_t)olda, oa2 = NC * oa1, oa3 = NC * oa2;
-  const uint32_t ob1 = NC * (uint32_t)oldb, ob2 = NC * ob1, ob3 = NC * ob2;
+  const uint32_t oa3 = (uint32_t)olda, ob3 = (uint32_t)oldb;   // the old code is the fastest index of a block
   const uint32_t ps = (uint32_t)sitea, pc = (uint32_t)newa;
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-  const int c1 = m.spN1 >> 4, c2 = m.spN2 >> 3, c3 = m.spN3 >> 3;
-#pragma unroll 2
-  for (int q = 0; q < c1; ++q) {
+  const int nchunk = m.spNQ >> 3;
+#pragma unroll 3
+  for (int q = 0; q < nchunk; ++q) {
     const uint4 va = __ldg(ra + q * SPEC_SG), vb = __ldg(rb + q * SPEC_SG);
-    spec_pairs4<false>(occ, Da, va, oa1, 0u, 0u, a0, a1);
-    spec_pairs4<true>(occ, Db, vb, ob1, ps, pc, b0, b1);
-  }
-  ra += c1 * SPEC_SG; rb += c1 * SPEC_SG;
-#pragma unroll 2
-  for (int q = 0; q < c2; ++q) {
-    const uint4 va = __ldg(ra + q * SPEC_SG), vb = __ldg(rb + q * SPEC_SG);
-    spec_trip2<false>(occ, Da, va, NC, oa2, 0u, 0u, a0, a1);
-    spec_trip2<true>(occ, Db, vb, NC, ob2, ps, pc, b0, b1);
-  }
-  ra += c2 * SPEC_SG; rb += c2 * SPEC_SG;
-  for (int q = 0; q < c3; ++q) {
-    const uint4 va = __ldg(ra + q * SPEC_SG), vb = __ldg(rb + q * SPEC_SG);
-    spec_quad2<false>(occ, Da, va, NC, oa3, 0u, 0u, a0, a1);
-    spec_quad2<true>(occ, Db, vb, NC, ob3, ps, pc, b0, b1);
+    spec_rec2<false>(occ, Da, va, NC, oa3, 0u, 0u, a0, a1);
+    spec_rec2<true>(occ, Db, vb, NC, ob3, ps, pc, b0, b1);
   }
   return (a0 + a1) + (b0 + b1);
 }
@@ -194,6 +188,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
   const SmemTables t = smem_tables(m, smem);
   const double* dtab = reinterpret_cast<const double*>(smem + m.off_dtab);
   if (!active) return;
+  if (g == 0) occ[m.N] = 0;   // pad byte behind the row: the zero code gathered by unused record slots
 
   const int stash_stride = m.Rstride * (KONE ? 8 : 4);
   for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
@@ -277,7 +272,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
       // ------------------------------ evaluate ------------------------------------------------
       double acc = 0.0, dmu = 0.0;
       if (live && n > 0) {
-        if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy<false>(m, occ, dtab, site1, s1, s2, 0u, 0u, l);
+        if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy(m, occ, dtab, site1, s1, s2, l);
         else acc = spec_swap_energy(m, occ, dtab, site1, s1, s2, site2, s2, s1, l);
       }
       acc += __shfl_xor_sync(FULL, acc, 1);

@@ -18,6 +18,24 @@ def _torch():
     return torch
 
 
+_POOL = None
+
+
+def _copy_into(dst: np.ndarray, src: np.ndarray):
+    """dst[...] = src with dtype conversion; large arrays are split over a few threads (numpy releases
+    the GIL inside copyto)."""
+    global _POOL
+    if src.nbytes < (4 << 20) or src.shape[0] < 4:
+        np.copyto(dst, src, casting="unsafe")
+        return
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4)
+    bounds = np.linspace(0, src.shape[0], 5).astype(int)
+    list(_POOL.map(lambda ab: np.copyto(dst[ab[0]:ab[1]], src[ab[0]:ab[1]], casting="unsafe"),
+                   zip(bounds[:-1], bounds[1:])))
+
+
 class LmcEngine:
     """One model resident on one CUDA device."""
 
@@ -62,7 +80,7 @@ class LmcEngine:
             self._pin_key = key
         if getattr(self, "_pin_evt", None) is not None:
             self._pin_evt.synchronize()          # the previous async copy has consumed the buffer
-        np.copyto(self._pin_buf.numpy(), occ_host, casting="unsafe")   # one pass: copy + int32 conversion
+        _copy_into(self._pin_buf.numpy(), occ_host)   # one pass: copy + int32 conversion
         src = self._pin_buf.to(self.device, non_blocking=True)
         self._pin_evt = torch.cuda.Event()
         self._pin_evt.record(torch.cuda.current_stream(self.device))

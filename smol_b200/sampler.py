@@ -11,6 +11,7 @@ block, global walker id) -- independent of how walkers are sharded over GPUs.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import warnings
 
 import numpy as np
@@ -38,6 +39,44 @@ def _fast_copy(src: np.ndarray) -> np.ndarray:
     bounds = np.linspace(0, src.shape[0], parts + 1).astype(int)
     list(_POOL.map(lambda ab: np.copyto(dst[ab[0]:ab[1]], src[ab[0]:ab[1]]), zip(bounds[:-1], bounds[1:])))
     return dst
+
+
+
+class _PinnedPool:
+    """Recycles page-locked host blocks that receive the per-chunk trace copies.
+
+    The trace arrays handed to the SampleContainer are views of these blocks (no staging copy on
+    the way out); ``SampleContainer.clear`` returns a block once no outside view refers to it.
+    ``LMC_PINNED_POOL_MB`` caps the page-locked memory in flight (default 4096); beyond the cap the
+    sampler falls back to a fixed staging slot plus a host copy."""
+
+    def __init__(self):
+        self.free = {}
+        self.outstanding = 0
+        self.cap = int(os.environ.get("LMC_PINNED_POOL_MB", "4096")) << 20
+
+    def acquire(self, shape, dtype):
+        import torch
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            t = lst.pop()
+        else:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            if self.outstanding + nbytes > self.cap:
+                return None
+            t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        self.outstanding += t.numel() * t.element_size()
+        return t
+
+    def release(self, t):
+        self.outstanding -= t.numel() * t.element_size()
+        lst = self.free.setdefault((tuple(t.shape), t.dtype), [])
+        if len(lst) < 8:
+            lst.append(t)
+
+
+_PINNED = _PinnedPool()
 
 _USHERS = {"flip": capi.LMC_USHER_FLIP, "swap": capi.LMC_USHER_SWAP,
            "tableflip": capi.LMC_USHER_TABLEFLIP, "table_flip": capi.LMC_USHER_TABLEFLIP}
@@ -218,10 +257,18 @@ class Sampler:
             shapes = {"features": ((nmax, W, F), torch.float64), "enthalpy": ((nmax, W), torch.float64),
                       "accepted": ((nmax, W), torch.uint8), "n_accepted": ((nmax, W), torch.int32),
                       "occupancy": ((nmax, W, N if self.record_occupancy else 0), torch.int8)}
-            cache[index] = {"key": key,
+            cache[index] = {"key": key, "shapes": shapes,
                             "dev": {k: torch.empty(sh, dtype=dt, device=dev) for k, (sh, dt) in shapes.items()},
-                            "host": {k: torch.empty(sh, dtype=dt, pin_memory=True) for k, (sh, dt) in shapes.items()}}
+                            "host": None}
         return cache[index]
+
+    @staticmethod
+    def _slot_staging(slot):
+        """fixed page-locked staging of a slot (fallback when the pinned pool is exhausted)"""
+        import torch
+        if slot["host"] is None:
+            slot["host"] = {k: torch.empty(sh, dtype=dt, pin_memory=True) for k, (sh, dt) in slot["shapes"].items()}
+        return slot["host"]
 
     def efficiency(self, discard=0, flat=True):
         return self.samples.sampling_efficiency(discard=discard, flat=flat)
@@ -305,10 +352,16 @@ class Sampler:
         feat, enth = eng.full_features(self._occ_dev)
         if self._kernel == capi.LMC_KERNEL_WANGLANDAU and self._wl_state is None:
             self._init_wl()
-        seeds = torch.from_numpy(self.seeds.view(np.int64)).to(dev)
+        if getattr(self, "_seeds_dev", None) is None:
+            self._seeds_dev = torch.from_numpy(self.seeds.view(np.int64)).to(dev)
+        seeds = self._seeds_dev
         with np.errstate(divide="ignore"):
             beta_h = np.where(np.isinf(self._temperature), 0.0, 1.0 / (self.kB * self._temperature))
-        beta = torch.from_numpy(np.ascontiguousarray(beta_h)).to(dev)
+        bkey = beta_h.tobytes()
+        if getattr(self, "_beta_key", None) != bkey:     # re-uploaded only when a temperature changed
+            self._beta_dev = torch.from_numpy(np.ascontiguousarray(beta_h)).to(dev)
+            self._beta_key = bkey
+        beta = self._beta_dev
         per_sample = W * ((N if self.record_occupancy else 0) + 8 * F + 8 + 1 + 4)
         # The run is cut into a few launches so that the device->host copy and the host-side
         # bookkeeping of chunk i overlap the kernel of chunk i+1 (double-buffered trace slots, copies
@@ -324,23 +377,35 @@ class Sampler:
             self._copy_stream = torch.cuda.Stream(device=dev)
         slots = [self._trace_slot(i, nmax, W, N, F, dev) for i in range(2)]
 
-        def finalize(slot, n, ev_copy):
+        def finalize(host, pooled, n, ev_copy):
             ev_copy.synchronize()
-            host = slot["host"]
-            traces = {
-                "features": _fast_copy(host["features"][:n].numpy()),
-                "enthalpy": host["enthalpy"][:n].numpy().copy()[:, :, None],
-                "accepted": host["accepted"][:n].numpy().astype(bool)[:, :, None],
-                "n_accepted": host["n_accepted"][:n].numpy().copy(),
-            }
-            if self.record_occupancy:
-                o = host["occupancy"][:n].numpy()
-                traces["occupancy"] = _fast_copy(o.reshape(n * W, N)).reshape(n, W, N)   # int8; int32 on access
+            owned = []
+            if pooled:
+                # the trace arrays ARE the page-locked blocks the copy engine wrote: no host copy
+                arrs = {k: v.numpy() for k, v in host.items()}
+                for k, v in host.items():
+                    owned.append(((lambda t=v: _PINNED.release(t)), arrs[k]))
+                traces = {"features": arrs["features"][:n], "enthalpy": arrs["enthalpy"][:n][:, :, None],
+                          "accepted": arrs["accepted"][:n].view(np.bool_)[:, :, None],
+                          "n_accepted": arrs["n_accepted"][:n]}
+                if self.record_occupancy:
+                    traces["occupancy"] = arrs["occupancy"][:n]          # int8; int32 on access
+                del arrs
             else:
+                traces = {
+                    "features": _fast_copy(host["features"][:n].numpy()),
+                    "enthalpy": host["enthalpy"][:n].numpy().copy()[:, :, None],
+                    "accepted": host["accepted"][:n].numpy().astype(bool)[:, :, None],
+                    "n_accepted": host["n_accepted"][:n].numpy().copy(),
+                }
+                if self.record_occupancy:
+                    o = host["occupancy"][:n].numpy()
+                    traces["occupancy"] = _fast_copy(o.reshape(n * W, N)).reshape(n, W, N)   # int8; int32 on access
+            if not self.record_occupancy:
                 traces["occupancy"] = np.zeros((n, W, 0), dtype=np.int8)
             if "temperature" in self.samples._shapes:
                 traces["temperature"] = np.broadcast_to(self._temperature[None, :, None], (n, W, 1)).copy()
-            self.samples.append(traces, thin_by)
+            self.samples.append(traces, thin_by, owned=owned)
 
         done, ci, pending = 0, 0, None
         while done < S:
@@ -378,17 +443,23 @@ class Sampler:
             self._kernel_events.append((ev0, ev1))
             self._step_counter += n * thin_by
             # device -> pinned host staging on the copy stream, behind this chunk's kernel
+            names = [k for k in d if not (k == "occupancy" and not self.record_occupancy)]
+            host = {k: _PINNED.acquire((n, *d[k].shape[1:]), d[k].dtype) for k in names}
+            pooled = all(v is not None for v in host.values())
+            if not pooled:
+                for v in host.values():
+                    if v is not None:
+                        _PINNED.release(v)
+                host = self._slot_staging(slot)
             ev_copy = torch.cuda.Event()
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(ev1)
-                for k, v in d.items():
-                    if k == "occupancy" and not self.record_occupancy:
-                        continue
-                    slot["host"][k][:n].copy_(v[:n], non_blocking=True)
+                for k in names:
+                    host[k][:n].copy_(d[k][:n], non_blocking=True)
                 ev_copy.record(self._copy_stream)
             if pending is not None:
                 finalize(*pending)        # overlaps the kernel just launched
-            pending = (slot, n, ev_copy)
+            pending = (host, pooled, n, ev_copy)
             done += n
             ci += 1
         if pending is not None:

@@ -33,7 +33,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     lib.lmc_version.restype = ctypes.c_int
     assert lib.lmc_version() == capi.LMC_ABI_VERSION
-    assert lib.lmc_row_stride(512) == 512 and lib.lmc_row_stride(27) == 32
+    assert lib.lmc_row_stride(512) == 528 and lib.lmc_row_stride(27) == 32   # >= 1 zero pad byte
 
 
 def test_ctypes_struct_matches_header_field_order():
