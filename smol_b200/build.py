@@ -29,8 +29,19 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(s) <= t for s in _sources())
 
 
+def _deps(src):
+    """files an object depends on: its source, every header, and (for the API unit only) nothing else"""
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    if not src.endswith("lmc_spec_inst.cu"):
+        hdrs = [h for h in hdrs if not h.endswith("lmc_spec.cuh")]
+    return [src, os.path.join(HERE, "..", "include", "lmc.h"), *hdrs]
+
+
 def _compile(args):
-    src, obj, extra = args
+    src, obj, extra, force = args
+    if (not force and not os.environ.get("LMC_EXTRA_DEFS") and os.path.exists(obj)
+            and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in _deps(src))):
+        return ["(up to date)", obj], subprocess.CompletedProcess([], 0, "", "")
     cmd = [NVCC, *FLAGS, *extra, *os.environ.get("LMC_EXTRA_DEFS", "").split(), "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return cmd, r
@@ -42,12 +53,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(LIBDIR, "obj" + os.environ.get("LMC_LIB_NAME", "").replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
-    jobs = [(os.path.join(CSRC, "lmc_api.cu"), os.path.join(objdir, "lmc_api.o"), [])]
+    jobs = [(os.path.join(CSRC, "lmc_api.cu"), os.path.join(objdir, "lmc_api.o"), [], force)]
     for g in GROUPS:
         for wl in (0, 1):
             jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"),
-                         os.path.join(objdir, f"lmc_run_g{g}_wl{wl}.o"), [f"-DLMC_G={g}", f"-DLMC_WL={wl}"]))
-    jobs.append((os.path.join(CSRC, "lmc_spec_inst.cu"), os.path.join(objdir, "lmc_spec.o"), []))
+                         os.path.join(objdir, f"lmc_run_g{g}_wl{wl}.o"), [f"-DLMC_G={g}", f"-DLMC_WL={wl}"], force))
+    jobs.append((os.path.join(CSRC, "lmc_spec_inst.cu"), os.path.join(objdir, "lmc_spec.o"), [], force))
     log = []
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:
         for cmd, r in ex.map(_compile, jobs):

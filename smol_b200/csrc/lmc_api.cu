@@ -6,7 +6,9 @@
 #include <string.h>
 
 #include <array>
+#include <algorithm>
 #include <atomic>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -163,27 +165,38 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
     if (ii >= o.T || ff >= o.T || newc == oldc) return 0.0;
     return coef * (tabA[o.atab_off + ff] - tabA[o.atab_off + ii]);
   };
-  struct Merged { int cls[3]; uint16_t site[3]; };
+  // a merged record: up to three gathered sites and the cluster terms folded into its table block;
+  // slot[i] = which gathered site feeds the i-th other site of the term's cluster
+  struct Term { int cls; int slot[3]; };
+  struct MRec { uint16_t site[3]; int ns; std::vector<Term> terms; };
   const uint16_t DUMMY = (uint16_t)N;   // zero pad byte of the occupancy row
-  int max_level = 2;
-  if (const char* e = getenv("LMC_SPEC_MERGE")) max_level = atoi(e) ? 2 : 1;
+  // merge level 3: site-set cover (a record takes every cluster whose other sites are among its three
+  // gathered sites: an FCC tetrahedron record also carries its three triangles and nearest-neighbour
+  // pairs), 2: one cluster + pair terms per record, 1: one cluster per record
+  int max_level = 3;
+  if (const char* e = getenv("LMC_SPEC_MERGE")) max_level = std::min(3, std::max(1, atoi(e) + 1));
   size_t budget = 64 * 1024;   // bytes of shared memory the difference table may take
   if (const char* e = getenv("LMC_SPEC_TABLE_KB")) budget = (size_t)atoi(e) * 1024;
-  for (int level = max_level; level >= 1 && !sp.ok; --level) {   // 2: merged records, 1: one cluster per record
+  for (int level = max_level; level >= 1 && !sp.ok; --level) {
     // deduplicated [new][entry] blocks; block 0 = zeros (padding records)
     std::vector<std::vector<double>> store;
     std::vector<long> store_base;
-    std::vector<std::array<int, 4>> keys;   // (cls0, cls1, cls2, store index)
+    std::map<std::vector<int>, int> keys;   // (ns, cls, slots ...) -> store index
     long L = (long)NC * NC * NC * NC;
     store.emplace_back((size_t)L * NC, 0.0);
     store_base.push_back(0);
-    auto block_of = [&](const int* cls) -> int {
-      for (const auto& k : keys)
-        if (k[0] == cls[0] && k[1] == cls[1] && k[2] == cls[2]) return k[3];
-      int used = 0;
-      for (int k = 0; k < 3 && cls[k] >= 0; ++k) used += noth[cls[k]];
+    auto block_of = [&](MRec& r) -> int {
+      std::sort(r.terms.begin(), r.terms.end(), [](const Term& a, const Term& b) {
+        if (a.cls != b.cls) return a.cls < b.cls;
+        for (int i = 0; i < 3; ++i) if (a.slot[i] != b.slot[i]) return a.slot[i] < b.slot[i];
+        return false;
+      });
+      std::vector<int> key{r.ns};
+      for (const Term& t : r.terms) { key.push_back(t.cls); key.push_back(t.slot[0]); key.push_back(t.slot[1]); key.push_back(t.slot[2]); }
+      auto it = keys.find(key);
+      if (it != keys.end()) return it->second;
       long combos = 1;
-      for (int i = 0; i < used; ++i) combos *= NC;
+      for (int i = 0; i < r.ns; ++i) combos *= NC;
       const long len = combos * NC;
       std::vector<double> blk((size_t)len * NC, 0.0);
       for (long q = 0; q < combos; ++q) {
@@ -191,8 +204,10 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
         for (int oldc = 0; oldc < NC; ++oldc)
           for (int newc = 0; newc < NC; ++newc) {
             double v = 0.0;
-            int slot = 0;
-            for (int k = 0; k < 3 && cls[k] >= 0; ++k) { v += term(cls[k], code + slot, oldc, newc); slot += noth[cls[k]]; }
+            for (const Term& t : r.terms) {
+              const int oc[3] = {code[t.slot[0]], code[t.slot[1]], code[t.slot[2]]};
+              v += term(t.cls, oc, oldc, newc);
+            }
             blk[(size_t)newc * len + oldc + NC * q] = v;
           }
       }
@@ -205,53 +220,91 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
         L += len;
         idx = (int)store.size() - 1;
       }
-      keys.push_back({cls[0], cls[1], cls[2], idx});
+      keys.emplace(std::move(key), idx);
       return idx;
     };
-    std::vector<std::vector<Merged>> merged(N);
+    std::vector<std::vector<MRec>> merged(N);
     size_t nq = 0;
-    auto psite = [&](int c, const uint16_t* rc) { return d->cls_stride[c * 4] > 0 ? rc[0] : DUMMY; };   // point terms gather nothing
+    auto nreal = [&](int c) { return d->cls_stride[c * 4] > 0 ? noth[c] : 0; };   // point terms gather nothing
+    // record with consecutive slots for the given clusters (levels 1 and 2)
+    auto packed_rec = [&](std::initializer_list<const uint16_t*> rcs) {
+      MRec r{{DUMMY, DUMMY, DUMMY}, 0, {}};
+      for (const uint16_t* rc : rcs) {
+        const int c = rc[3];
+        Term t{c, {0, 0, 0}};
+        for (int i = 0; i < nreal(c); ++i) { t.slot[i] = r.ns; r.site[r.ns++] = rc[i]; }
+        if (nreal(c) == 0 && r.ns < 3) ++r.ns;   // a point term keeps its (dummy) slot
+        r.terms.push_back(t);
+      }
+      return r;
+    };
     for (int i = 0; i < N; ++i) {
-      std::vector<std::vector<const uint16_t*>> P(nCls);   // pair / point records by class
-      std::vector<const uint16_t*> T;
-      std::vector<Merged>& out = merged[i];
-      for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) {
-        const uint16_t* rc = d->site_rec + r * 4;
-        const int c = rc[3], n = noth[c];
-        if (n == 3) out.push_back(Merged{{c, -1, -1}, {rc[0], rc[1], rc[2]}});
-        else if (n == 2 && level == 1) out.push_back(Merged{{c, -1, -1}, {rc[0], rc[1], DUMMY}});
-        else if (n == 2) T.push_back(rc);
-        else if (level == 1) out.push_back(Merged{{c, -1, -1}, {psite(c, rc), DUMMY, DUMMY}});
-        else P[c].push_back(rc);
-      }
-      std::vector<size_t> head(nCls, 0);
-      auto remaining = [&](int c) { return P[c].size() - head[c]; };
-      for (const uint16_t* t : T) {   // a 3-site cluster takes a pair term of the fullest class along
-        int best = -1;
+      std::vector<MRec>& out = merged[i];
+      if (level == 3) {
+        std::vector<const uint16_t*> recs;
+        for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) recs.push_back(d->site_rec + r * 4);
+        std::stable_sort(recs.begin(), recs.end(), [&](const uint16_t* a, const uint16_t* b) { return nreal(a[3]) > nreal(b[3]); });
+        for (const uint16_t* rc : recs) {
+          const int c = rc[3], n = nreal(c);
+          int best = -1, best_score = -1;
+          for (size_t k = 0; k < out.size(); ++k) {
+            MRec& r = out[k];
+            int missing = 0;
+            for (int a = 0; a < n; ++a) {
+              bool have = false;
+              for (int b = 0; b < r.ns; ++b) have = have || r.site[b] == rc[a];
+              for (int b = 0; b < a; ++b) have = have || rc[b] == rc[a];   // repeated site of an aliased cluster
+              if (!have) ++missing;
+            }
+            if (r.ns + missing > 3) continue;
+            // prefer records that already hold the sites, then the fullest one
+            const int score = (n - missing) * 16 + (missing == 0 ? 8 : 0) + r.ns;
+            if (score > best_score) { best_score = score; best = (int)k; }
+          }
+          if (best < 0) { out.push_back(MRec{{DUMMY, DUMMY, DUMMY}, 0, {}}); best = (int)out.size() - 1; }
+          MRec& r = out[best];
+          Term t{c, {0, 0, 0}};
+          for (int a = 0; a < n; ++a) {
+            int at = -1;
+            for (int b = 0; b < r.ns; ++b) if (r.site[b] == rc[a]) at = b;
+            if (at < 0) { at = r.ns; r.site[r.ns++] = rc[a]; }
+            t.slot[a] = at;
+          }
+          r.terms.push_back(t);
+        }
+      } else {
+        std::vector<std::vector<const uint16_t*>> P(nCls);   // pair / point records by class
+        std::vector<const uint16_t*> T;
+        for (int64_t r = d->site_rec_off[i]; r < d->site_rec_off[i + 1]; ++r) {
+          const uint16_t* rc = d->site_rec + r * 4;
+          const int c = rc[3], n = noth[c];
+          if (n == 3 || level == 1) out.push_back(packed_rec({rc}));
+          else if (n == 2) T.push_back(rc);
+          else P[c].push_back(rc);
+        }
+        std::vector<size_t> head(nCls, 0);
+        auto remaining = [&](int c) { return P[c].size() - head[c]; };
+        for (const uint16_t* t : T) {   // a 3-site cluster takes a pair term of the fullest class along
+          int best = -1;
+          for (int c = 0; c < nCls; ++c)
+            if (remaining(c) > 0 && (best < 0 || remaining(c) > remaining(best))) best = c;
+          if (best >= 0) out.push_back(packed_rec({t, P[best][head[best]++]}));
+          else out.push_back(packed_rec({t}));
+        }
         for (int c = 0; c < nCls; ++c)
-          if (remaining(c) > 0 && (best < 0 || remaining(c) > remaining(best))) best = c;
-        if (best >= 0) {
-          const uint16_t* pr = P[best][head[best]++];
-          out.push_back(Merged{{(int)t[3], best, -1}, {t[0], t[1], psite(best, pr)}});
-        } else {
-          out.push_back(Merged{{(int)t[3], -1, -1}, {t[0], t[1], DUMMY}});
+          while (remaining(c) >= 3) {
+            out.push_back(packed_rec({P[c][head[c]], P[c][head[c] + 1], P[c][head[c] + 2]}));
+            head[c] += 3;
+          }
+        std::vector<const uint16_t*> rest;
+        for (int c = 0; c < nCls; ++c)
+          while (remaining(c) > 0) rest.push_back(P[c][head[c]++]);
+        for (size_t k = 0; k < rest.size(); k += 3) {
+          if (k + 2 < rest.size()) out.push_back(packed_rec({rest[k], rest[k + 1], rest[k + 2]}));
+          else if (k + 1 < rest.size()) out.push_back(packed_rec({rest[k], rest[k + 1]}));
+          else out.push_back(packed_rec({rest[k]}));
         }
       }
-      for (int c = 0; c < nCls; ++c)
-        while (remaining(c) >= 3) {
-          const uint16_t *a = P[c][head[c]], *b = P[c][head[c] + 1], *e = P[c][head[c] + 2];
-          head[c] += 3;
-          out.push_back(Merged{{c, c, c}, {psite(c, a), psite(c, b), psite(c, e)}});
-        }
-      Merged cur{{-1, -1, -1}, {DUMMY, DUMMY, DUMMY}};
-      int fill = 0;
-      for (int c = 0; c < nCls; ++c)
-        while (remaining(c) > 0) {
-          const uint16_t* pr = P[c][head[c]++];
-          cur.cls[fill] = c; cur.site[fill] = psite(c, pr);
-          if (++fill == 3) { out.push_back(cur); cur = Merged{{-1, -1, -1}, {DUMMY, DUMMY, DUMMY}}; fill = 0; }
-        }
-      if (fill) out.push_back(cur);
       nq = std::max(nq, out.size());
     }
     const int NQ = (int)((nq + 7) & ~size_t(7));
@@ -261,8 +314,8 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
       uint32_t* p = reinterpret_cast<uint32_t*>(rec.data() + (size_t)i * NQ * 8);
       for (int k = 0; k < NQ; ++k) {
         if (k < (int)merged[i].size()) {
-          const Merged& mr = merged[i][k];
-          const long tb = store_base[block_of(mr.cls)];
+          MRec& mr = merged[i][k];
+          const long tb = store_base[block_of(mr)];
           if (L > 65535 || (size_t)L * NC * 8 > budget) { ok = false; break; }
           p[2 * k] = (uint32_t)mr.site[0] | ((uint32_t)mr.site[1] << 16);
           p[2 * k + 1] = (uint32_t)mr.site[2] | ((uint32_t)tb << 16);
@@ -280,7 +333,7 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
         memcpy(&sp.dtab[(size_t)newc * L + store_base[b]], &store[b][(size_t)newc * len], len * 8);
     }
     sp.rec = std::move(rec);
-    sp.ok = 1; sp.NC = NC; sp.L = (int)L; sp.NQ = NQ; sp.nblocks = (int)store.size(); sp.merged = level == 2;
+    sp.ok = 1; sp.NC = NC; sp.L = (int)L; sp.NQ = NQ; sp.nblocks = (int)store.size(); sp.merged = level - 1;
   }
 }
 
@@ -722,7 +775,12 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
   int rc = -2;
   const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
-  if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, lc);
+  if (use_spec) {
+    // lanes per speculated step: 2 once the measured acceptance is below 3 % (see lmc_spec.cuh)
+    int sg = (mm->acc_rate >= 0.0 && mm->acc_rate < 0.03) ? 2 : 4;
+    if (const char* e = getenv("LMC_SPEC_SG")) sg = atoi(e) == 2 ? 2 : 4;
+    rc = launch_spec(m, a, m.kone != 0, c->usher, sg, lc);
+  }
   else switch (G) {
     case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewald, c->usher, lc); break;
     case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewald, c->usher, lc); break;

@@ -15,7 +15,8 @@ int launch_run_g8(const DevModel& m, const RunArgs& a, bool kone, bool ewald, in
 int launch_run_g16(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
 int launch_run_g32(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
 // speculative-batch Metropolis kernel (flip / swap)
-int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, const LaunchCfg& lc);
+// sg = lanes per speculated step (2 or 4)
+int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int sg, const LaunchCfg& lc);
 // Wang-Landau variants
 int launch_run_wl_g4(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
 int launch_run_wl_g8(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);

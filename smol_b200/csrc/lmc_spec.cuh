@@ -23,8 +23,9 @@
 
 namespace lmc {
 
-constexpr int SPEC_SG = 4;
-constexpr int SPEC_B = 32 / SPEC_SG;
+// SG lanes evaluate one upcoming step, 32 / SG steps per batch: SG = 4 by default, SG = 2 once fewer
+// than a few percent of the steps are accepted (the per-step scalar work -- proposal, rank select,
+// accept test -- is replicated over the SG lanes, so it halves; a discarded batch tail costs more)
 
 // position of the (rem+1)-th set bit of b (rem < popc(b))
 __device__ __forceinline__ int spec_nth_bit(uint32_t b, int rem) {
@@ -41,8 +42,9 @@ __device__ __forceinline__ int spec_nth_bit(uint32_t b, int rem) {
   return pos;
 }
 
-// k-th (0-based) active position of sublattice `sl` whose code differs from `code`; the four lanes
-// of a subgroup split the plane words.  Called by all 32 lanes (full-mask shuffles of width 4).
+// k-th (0-based) active position of sublattice `sl` whose code differs from `code`; the SG lanes
+// of a subgroup split the plane words.  Called by all 32 lanes (full-mask shuffles of width SG).
+template <int SPEC_SG>
 __device__ __forceinline__ int spec_select_ne(const DevModel& m, const uint32_t* planes, int sl, int code, int k, int l) {
   const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
   const int nw = m.sl_nwords[sl];
@@ -63,8 +65,10 @@ __device__ __forceinline__ int spec_select_ne(const DevModel& m, const uint32_t*
     int incl = cnt;
     int tt = __shfl_up_sync(0xffffffffu, incl, 1, SPEC_SG);
     if (l >= 1) incl += tt;
-    tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
-    if (l >= 2) incl += tt;
+    if (SPEC_SG > 2) {
+      tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
+      if (l >= 2) incl += tt;
+    }
     int rem = k - (incl - cnt);
     found = rem >= 0 && rem < cnt;
     const int wi = (rem >= p1) + (rem >= p2) + (rem >= p3);
@@ -82,8 +86,10 @@ __device__ __forceinline__ int spec_select_ne(const DevModel& m, const uint32_t*
     int incl = cnt;
     int tt = __shfl_up_sync(0xffffffffu, incl, 1, SPEC_SG);
     if (l >= 1) incl += tt;
-    tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
-    if (l >= 2) incl += tt;
+    if (SPEC_SG > 2) {
+      tt = __shfl_up_sync(0xffffffffu, incl, 2, SPEC_SG);
+      if (l >= 2) incl += tt;
+    }
     int rem = k - (incl - cnt);
     found = rem >= 0 && rem < cnt;
     if (found) {
@@ -98,7 +104,7 @@ __device__ __forceinline__ int spec_select_ne(const DevModel& m, const uint32_t*
     }
   }
   const uint32_t bal = __ballot_sync(0xffffffffu, found);
-  const uint32_t mine = (bal >> (threadIdx.x & 28u)) & 0xfu;
+  const uint32_t mine = (bal >> (threadIdx.x & 31u & ~(uint32_t)(SPEC_SG - 1))) & ((1u << SPEC_SG) - 1u);
   const int own = mine ? (__ffs(mine) - 1) : 0;
   return __shfl_sync(0xffffffffu, res, own, SPEC_SG);
 }
@@ -123,7 +129,8 @@ __device__ __forceinline__ void spec_rec2(const uint8_t* occ, const double* Dn, 
                  NC * (spec_code<PATCH>(occ, v.z >> 16, ps, pc) + NC * spec_code<PATCH>(occ, v.w & 0xffffu, ps, pc)))];
 }
 
-// scaled energy change of one flip (lane l of 4 takes every fourth 16-byte chunk of the record list)
+// scaled energy change of one flip (lane l of SG takes every SG-th 16-byte chunk of the record list)
+template <int SPEC_SG>
 __device__ __forceinline__ double spec_flip_energy(const DevModel& m, const uint8_t* occ, const double* dtab, int site,
                                                    int oldc, int newc, int l) {
   const uint4* rp = reinterpret_cast<const uint4*>(m.sp_rec + (size_t)site * m.spSb) + l;
@@ -131,7 +138,7 @@ __device__ __forceinline__ double spec_flip_energy(const DevModel& m, const uint
   const uint32_t NC = (uint32_t)m.spNC;
   const uint32_t old3 = (uint32_t)oldc;   // the old code is the fastest index of a block
   double a0 = 0.0, a1 = 0.0;
-  const int nchunk = m.spNQ >> 3;
+  const int nchunk = m.spNQ / (2 * SPEC_SG);   // spNQ is a multiple of 8
 #pragma unroll 3
   for (int q = 0; q < nchunk; ++q) spec_rec2<false>(occ, Dn, __ldg(rp + q * SPEC_SG), NC, old3, 0u, 0u, a0, a1);
   return a0 + a1;
@@ -139,6 +146,7 @@ __device__ __forceinline__ double spec_flip_energy(const DevModel& m, const uint
 
 // both flips of a swap in the same loop (independent chains: twice the ILP); flip b sees flip a
 // applied through the PATCH of its gathers (sequential semantics of expansion.py:217-229)
+template <int SPEC_SG>
 __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint8_t* occ, const double* dtab, int sitea,
                                                    int olda, int newa, int siteb, int oldb, int newb, int l) {
   const uint4* ra = reinterpret_cast<const uint4*>(m.sp_rec + (size_t)sitea * m.spSb) + l;
@@ -149,7 +157,7 @@ __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint
   const uint32_t oa3 = (uint32_t)olda, ob3 = (uint32_t)oldb;   // the old code is the fastest index of a block
   const uint32_t ps = (uint32_t)sitea, pc = (uint32_t)newa;
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-  const int nchunk = m.spNQ >> 3;
+  const int nchunk = m.spNQ / (2 * SPEC_SG);
 #pragma unroll 3
   for (int q = 0; q < nchunk; ++q) {
     const uint4 va = __ldg(ra + q * SPEC_SG), vb = __ldg(rb + q * SPEC_SG);
@@ -159,9 +167,11 @@ __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint
   return (a0 + a1) + (b0 + b1);
 }
 
-template <bool KONE, int USHER>
+template <bool KONE, int USHER, int SPEC_SG>
 __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, const RunArgs a) {
   static_assert(USHER == LMC_USHER_FLIP || USHER == LMC_USHER_SWAP, "flip / swap only");
+  static_assert(SPEC_SG == 2 || SPEC_SG == 4, "2 or 4 lanes per speculated step");
+  constexpr int SPEC_B = 32 / SPEC_SG;
   constexpr int G = 32;
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
   const int w = blockIdx.x * a.wpb + wl_;
   const int nw_blk = min(a.wpb, a.W - blockIdx.x * a.wpb);
   const bool active = wl_ < a.wpb && w < a.W;
-  const int sg = g >> 2, l = g & 3;
+  const int sg = g / SPEC_SG, l = g % SPEC_SG;
 
   unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
   uint8_t* occ_rows = wbase;
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
         const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
         const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
         const int k = ndiff > 0 ? (int)mulhi32(rq.z, (uint32_t)ndiff) : 0;
-        pos2 = spec_select_ne(m, planes, sl, s1, k, l);
+        pos2 = spec_select_ne<SPEC_SG>(m, planes, sl, s1, k, l);
         if (ndiff > 0) {
           site2 = site_of_pos(m, sl, pos2);
           s2 = occ[site2];
@@ -272,11 +282,11 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
       // ------------------------------ evaluate ------------------------------------------------
       double acc = 0.0, dmu = 0.0;
       if (live && n > 0) {
-        if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy(m, occ, dtab, site1, s1, s2, l);
-        else acc = spec_swap_energy(m, occ, dtab, site1, s1, s2, site2, s2, s1, l);
+        if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, l);
+        else acc = spec_swap_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, site2, s2, s1, l);
       }
       acc += __shfl_xor_sync(FULL, acc, 1);
-      acc += __shfl_xor_sync(FULL, acc, 2);
+      if (SPEC_SG > 2) acc += __shfl_xor_sync(FULL, acc, 2);
       double dH = acc;
       if (MU_POSSIBLE && m.muW) {
         dmu = __ldg(m.mu + site1 * m.muW + s2) - __ldg(m.mu + site1 * m.muW + s1);
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
 
       // ------------------------------ commit the first accepted step --------------------------
       const int src = __ffs(bal) - 1;
-      const int j = src >> 2;
+      const int j = src / SPEC_SG;
       const int c_n = __shfl_sync(FULL, n, src);
       const int c_sl = __shfl_sync(FULL, sl, src);
       const int c_site1 = __shfl_sync(FULL, site1, src), c_s1 = __shfl_sync(FULL, s1, src), c_pos1 = __shfl_sync(FULL, pos1, src);

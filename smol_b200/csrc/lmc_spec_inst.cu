@@ -4,20 +4,25 @@
 
 namespace lmc {
 
-template <bool KONE, int USHER>
-static int launch_spec_one(const DevModel& m, const RunArgs& a, const LaunchCfg& lc) {
-  auto kern = lmc_spec_kernel<KONE, USHER>;
+template <bool KONE, int USHER, int SG>
+static int launch_spec_sg(const DevModel& m, const RunArgs& a, const LaunchCfg& lc) {
+  auto kern = lmc_spec_kernel<KONE, USHER, SG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<lc.grid, lc.threads, lc.smem, lc.stream>>>(m, a);
   return (int)cudaGetLastError();
 }
 
-int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, const LaunchCfg& lc) {
+template <bool KONE, int USHER>
+static int launch_spec_one(const DevModel& m, const RunArgs& a, int sg, const LaunchCfg& lc) {
+  return sg == 2 ? launch_spec_sg<KONE, USHER, 2>(m, a, lc) : launch_spec_sg<KONE, USHER, 4>(m, a, lc);
+}
+
+int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int sg, const LaunchCfg& lc) {
   if (usher == LMC_USHER_FLIP)
-    return kone ? launch_spec_one<true, LMC_USHER_FLIP>(m, a, lc) : launch_spec_one<false, LMC_USHER_FLIP>(m, a, lc);
+    return kone ? launch_spec_one<true, LMC_USHER_FLIP>(m, a, sg, lc) : launch_spec_one<false, LMC_USHER_FLIP>(m, a, sg, lc);
   if (usher == LMC_USHER_SWAP)
-    return kone ? launch_spec_one<true, LMC_USHER_SWAP>(m, a, lc) : launch_spec_one<false, LMC_USHER_SWAP>(m, a, lc);
+    return kone ? launch_spec_one<true, LMC_USHER_SWAP>(m, a, sg, lc) : launch_spec_one<false, LMC_USHER_SWAP>(m, a, sg, lc);
   return -2;
 }
 

@@ -249,11 +249,13 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["decomposition", "expansion"])
 @pytest.mark.parametrize("n,T,thin", [(2, 1000.0, 20), (4, 300.0, 7), (4, 1000.0, 64), (3, 1e5, 13)])
-def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin):
+@pytest.mark.parametrize("sg", ["4", "2"])
+def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypatch):
     """low / medium / near-infinite temperature (acceptance ~0 .. ~1), sampling intervals that are not
     multiples of the batch, aliased 2x2x2 cell; spec_mode=2 forces the speculative kernel, 1 the classic
-    one: both must reproduce the oracle chain bit for bit."""
+    one: both must reproduce the oracle chain bit for bit.  sg = lanes per speculated step."""
     import smol_b200 as S
+    monkeypatch.setenv("LMC_SPEC_SG", sg)
     O = _oracle()
     sub = M.fcc_subspace()
     scm = np.eye(3, dtype=int) * n
@@ -280,9 +282,11 @@ def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin):
 
 
 @pytest.mark.parametrize("T", [400.0, 3000.0])
-def test_speculative_semigrand_flip_trajectory(cuda_device, T):
+@pytest.mark.parametrize("sg", ["4", "2"])
+def test_speculative_semigrand_flip_trajectory(cuda_device, T, sg, monkeypatch):
     """ternary rocksalt cations, chemical potentials, single flips (no Ewald term): speculative kernel"""
     import smol_b200 as S
+    monkeypatch.setenv("LMC_SPEC_SG", sg)
     from smol_b200 import lattice as L
     O = _oracle()
     sub = M.rocksalt_subspace()

@@ -54,7 +54,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("merge", ["1", "0"])
+@pytest.mark.parametrize("merge", ["2", "1", "0"])
 def test_spec_tables_reproduce_oracle_flip_energies(name, make, merge, monkeypatch):
     import smol_b200 as S
     monkeypatch.setenv("LMC_SPEC_MERGE", merge)
@@ -74,7 +74,7 @@ def test_spec_tables_reproduce_oracle_flip_energies(name, make, merge, monkeypat
     packed = ens.packed_model()
     info, dtab, rec = _tables(packed)
     assert info[0] == 1, info
-    assert info[5] == int(merge == "1") or info[5] == 0
+    assert info[5] <= int(merge)
     NC = info[1]
     occ = M.random_occupancies(sub, scm, 1, seed=5)[0]
     spaces = sub.allowed_species(scm)
@@ -110,13 +110,15 @@ def ens_change(ora, occ, flips):
     return ora.compute_feature_vector_change(occ, flips)
 
 
-def test_merged_records_halve_the_lookups():
+def test_cover_merge_quarters_the_lookups():
     import smol_b200 as S
     sub = M.fcc_subspace()
     scm = np.eye(3, dtype=int) * 8
     it = L.cluster_interaction_tensors(sub, M.fcc_coefs(sub))
     packed = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, it)).packed_model()
     info, dtab, rec = _tables(packed)
-    assert info[0] == 1 and info[5] == 1
-    assert info[3] == 48          # 87 local clusters of config 2 -> 43 merged records, padded to 48
+    assert info[0] == 1 and info[5] == 2
+    # 87 local clusters of config 2 -> 22 records: 8 nearest-neighbour triangles of sites (each carries a
+    # tetrahedron, its three triangles and nearest-neighbour pairs) + 14 records of three farther pairs
+    assert info[3] == 24
     assert info[6] <= 8 * 1024    # the difference table stays a few KB of shared memory
