@@ -578,15 +578,19 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       m.sl_first[s] = contig ? d->sl_sites[a] : -1;
     }
     m.sl_off[m.nSl] = d->sl_site_off[m.nSl];
-    int pw = 0;
+    int pw = 0, le = 0;
     for (int s = 0; s < m.nSl; ++s) {
       int maxcode = 0;
       for (int c = 0; c < m.sl_ncodes[s]; ++c) maxcode = std::max(maxcode, m.sl_codes[s][c]);
       m.sl_nwords[s] = (m.sl_off[s + 1] - m.sl_off[s] + 31) / 32;
       m.sl_plane_off[s] = pw;
       pw += (maxcode + 1) * m.sl_nwords[s];
+      m.sl_nplanes[s] = maxcode + 1;
+      m.sl_list_off[s] = le;
+      le += (maxcode + 1) * (m.sl_off[s + 1] - m.sl_off[s]);
     }
     m.plane_words = pw;
+    m.list_entries = le;
     UP(int, d->sl_sites, d->sl_site_off[m.nSl], m.sl_sites);
   }
   m.tfD = d->tf_num_flips > 0 ? d->tf_num_dims : 0;
@@ -698,6 +702,13 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   // auto: only while the staged tables leave room for a full complement of resident walkers per SM
   const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35 && m.blob_bytes <= 24 * 1024));
   if (use_spec) G = 32;
+  // lanes per speculated step (lmc_spec.cuh).  Four everywhere: with two or one lane per step (one uses
+  // sorted position lists for the swap partner) the scalar work per step shrinks, but 16 / 32 unrelated
+  // flip sites per warp instruction multiply the L1 / shared-memory wavefronts of the record loads and
+  // occupancy gathers, which is the pipe that bounds this kernel (measured, profiles/r01_variants.md)
+  int spec_sg = 4;
+  if (const char* e = getenv("LMC_SPEC_SG")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) spec_sg = v; }
+  const bool spec_lists = use_spec && spec_sg == 1 && c->usher == LMC_USHER_SWAP;
   if (G == 0) {
     // measured on B200 (profiles/): a full warp per walker wins while all walkers fit in one wave
     // (W <= 32 per SM); beyond that half warps amortise the per-step scalar work better
@@ -745,7 +756,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
   a.off_ring = a.off_plane + ((LMC_PLANE_COPIES * m.plane_words * 4 + 15) & ~15);  // planes (+ prefix popcounts)
   a.off_eidx = a.off_ring + G * 16;                                   // per-lane precomputed proposals
-  a.walker_smem = a.off_eidx + (ewald ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
+  a.off_lists = a.off_eidx + (ewald ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
+  a.walker_smem = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
   if (auto_threads && relaxed) {
@@ -775,12 +787,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
   int rc = -2;
   const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
-  if (use_spec) {
-    // lanes per speculated step: 2 once the measured acceptance is below 3 % (see lmc_spec.cuh)
-    int sg = (mm->acc_rate >= 0.0 && mm->acc_rate < 0.03) ? 2 : 4;
-    if (const char* e = getenv("LMC_SPEC_SG")) sg = atoi(e) == 2 ? 2 : 4;
-    rc = launch_spec(m, a, m.kone != 0, c->usher, sg, lc);
-  }
+  if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, lc);
   else switch (G) {
     case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewald, c->usher, lc); break;
     case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewald, c->usher, lc); break;

@@ -15,7 +15,7 @@ int launch_run_g8(const DevModel& m, const RunArgs& a, bool kone, bool ewald, in
 int launch_run_g16(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
 int launch_run_g32(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
 // speculative-batch Metropolis kernel (flip / swap)
-// sg = lanes per speculated step (2 or 4)
+// sg = lanes per speculated step (1, 2 or 4; 1 uses sorted position lists for swaps)
 int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int sg, const LaunchCfg& lc);
 // Wang-Landau variants
 int launch_run_wl_g4(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);

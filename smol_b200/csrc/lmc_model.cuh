@@ -52,6 +52,9 @@ struct DevModel {
   int sl_nwords[LMC_MAX_SUBLATTICES];  // 32-bit words of one species bit-plane (ceil(n_active/32))
   int sl_plane_off[LMC_MAX_SUBLATTICES];  // word offset of the sublattice's planes [code][word]
   int plane_words;                     // total words of all planes of one walker
+  int sl_nplanes[LMC_MAX_SUBLATTICES];    // planes of the sublattice (max code + 1)
+  int sl_list_off[LMC_MAX_SUBLATTICES];   // u16 offset of the sublattice's position lists [code][n_active] (lmc_spec.cuh)
+  int list_entries;                    // u16 entries of all position lists of one walker
   const int* sl_sites;
   // table flips
   int tfD, tfNF;
@@ -90,7 +93,7 @@ struct RunArgs {
   LmcWangLandau wl;
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
-  int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx;  // offsets inside a walker's shared-memory slab
+  int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx, off_lists;  // offsets inside a walker's shared-memory slab
   unsigned long long* stats;  // [2] accepted / attempted step totals (device counters; kernel selection feedback)
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another

@@ -3,7 +3,7 @@
 // The classic kernel (lmc_kernels.cuh) spends all 32 lanes of a warp on ONE attempted step: the
 // per-step scalar work (proposal, rank select, reduction, accept test) is replicated 32 wide and
 // dominates the instruction count.  Here a warp still owns one walker, but each group of
-// SPEC_SG = 4 lanes evaluates a DIFFERENT upcoming step (SPEC_B = 8 consecutive steps per batch)
+// SPEC_SG = 4 lanes evaluates a DIFFERENT upcoming step (SPEC_B = 32 / SPEC_SG = 8 consecutive steps per batch)
 // against the current occupancy.  The RNG is counter based (Philox keyed by step index), so step
 // t + j is fully defined before step t has been decided.  Rejected steps leave the state
 // untouched, hence every step of the batch up to and including the FIRST accepted one has been
@@ -23,9 +23,37 @@
 
 namespace lmc {
 
-// SG lanes evaluate one upcoming step, 32 / SG steps per batch: SG = 4 by default, SG = 2 once fewer
-// than a few percent of the steps are accepted (the per-step scalar work -- proposal, rank select,
-// accept test -- is replicated over the SG lanes, so it halves; a discarded batch tail costs more)
+// SG lanes evaluate one upcoming step, 32 / SG steps per batch.  SG = 4 is what lmc_run launches; SG = 2
+// and SG = 1 (LMC_SPEC_SG) replicate less scalar work per step but measured slower on B200: the record
+// loads and occupancy gathers of 16 / 32 unrelated flip sites per instruction cost more L1 / shared-
+// memory wavefronts than the saved instructions (profiles/r01_variants.md).
+//
+// LISTS (swap usher): instead of the rank select over species bit-planes, every (sublattice, code c)
+// keeps the ASCENDING list of active positions whose code differs from c, so the k-th swap partner of
+// Swap.propose_step (mcusher.py:190-196) is one shared-memory load.  An accepted swap a <-> b replaces
+// one entry in the lists of a and b (warp-wide shift), which pays off while accepts are rare.
+
+// sorted list of n u16 positions: remove X, insert Y (X in the list, Y not).  Whole warp.
+__device__ __forceinline__ void spec_list_replace(uint16_t* list, int n, int X, int Y, int g) {
+  if (Y > X) {   // entries in (X, Y) move one slot down
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + g;
+      const int v = i < n ? (int)list[i] : 0xffff;
+      const int nx = i + 1 < n ? (int)list[i + 1] : 0xffff;
+      __syncwarp();
+      if (v >= X && v < Y) list[i] = (uint16_t)(nx < Y ? nx : Y);
+    }
+  } else {       // entries in (Y, X) move one slot up
+    for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
+      const int i = base + g;
+      const int v = i < n ? (int)list[i] : 0xffff;
+      const int pv = (i > 0 && i - 1 < n) ? (int)list[i - 1] : -1;
+      __syncwarp();
+      if (v > Y && v <= X) list[i] = (uint16_t)(pv > Y ? pv : Y);
+    }
+  }
+  __syncwarp();
+}
 
 // position of the (rem+1)-th set bit of b (rem < popc(b))
 __device__ __forceinline__ int spec_nth_bit(uint32_t b, int rem) {
@@ -167,10 +195,11 @@ __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint
   return (a0 + a1) + (b0 + b1);
 }
 
-template <bool KONE, int USHER, int SPEC_SG>
+template <bool KONE, int USHER, int SPEC_SG, bool LISTS>
 __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, const RunArgs a) {
   static_assert(USHER == LMC_USHER_FLIP || USHER == LMC_USHER_SWAP, "flip / swap only");
-  static_assert(SPEC_SG == 2 || SPEC_SG == 4, "2 or 4 lanes per speculated step");
+  static_assert(SPEC_SG == 1 || SPEC_SG == 2 || SPEC_SG == 4, "1, 2 or 4 lanes per speculated step");
+  static_assert(!LISTS || USHER == LMC_USHER_SWAP, "position lists serve the swap usher");
   constexpr int SPEC_B = 32 / SPEC_SG;
   constexpr int G = 32;
   constexpr uint32_t FULL = 0xffffffffu;
@@ -193,6 +222,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
   int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
   uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
   uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [32] x (sl<<24 | pos, site, word z, float log u)
+  uint16_t* lists = reinterpret_cast<uint16_t*>(priv + a.off_lists);   // LISTS: [sublattice][code][n_active]
 
   stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
   const SmemTables t = smem_tables(m, smem);
@@ -218,6 +248,35 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
     }
   }
   __syncwarp();
+  if (LISTS) {
+    // lists[sl][c] = ascending active positions with code != c, expanded from the complement of plane c
+    for (int sl = 0; sl < m.nSl; ++sl) {
+      const int n_act = m.sl_off[sl + 1] - m.sl_off[sl], nw = m.sl_nwords[sl];
+      const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
+      for (int c = 0; c < m.sl_nplanes[sl]; ++c) {
+        uint16_t* lst = lists + m.sl_list_off[sl] + c * n_act;
+        int carry = 0;
+        for (int w0 = 0; w0 < nw; w0 += 32) {
+          const int wd = w0 + g;
+          uint32_t b = wd < nw ? (~planes[m.sl_plane_off[sl] + c * nw + wd] & (wd == nw - 1 ? tail : 0xffffffffu)) : 0u;
+          const int pc = __popc(b);
+          int incl = pc;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int tt = __shfl_up_sync(FULL, incl, o);
+            if (g >= o) incl += tt;
+          }
+          int at = carry + incl - pc;
+          while (b) {
+            lst[at++] = (uint16_t)(wd * 32 + __ffs(b) - 1);
+            b &= b - 1u;
+          }
+          carry += __shfl_sync(FULL, incl, 31);
+        }
+      }
+    }
+    __syncwarp();
+  }
 
   const unsigned long long seed = a.seeds[w];
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -236,7 +295,16 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
     int it = 0;
     while (it < a.thin) {
       const int nb = min(SPEC_B, a.thin - it);
-      if (!ring_valid || step + (unsigned long long)nb > rbase + 32ull) {
+      uint4 rq;
+      if (SPEC_SG == 1) {
+        // one step per lane: the lane's own Philox block, no staging
+        const unsigned long long st_ = step + (unsigned long long)g;
+        const U4 bq = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
+        const int sl_ = choose_sublattice(m, bq.x);
+        const int j_ = (int)mulhi32(bq.y, (uint32_t)(m.sl_off[sl_ + 1] - m.sl_off[sl_]));
+        rq = make_uint4((uint32_t)((sl_ << 24) | j_), (uint32_t)site_of_pos(m, sl_, j_), bq.z,
+                        __float_as_uint(log_u_float(bq.w)));
+      } else if (!ring_valid || step + (unsigned long long)nb > rbase + 32ull) {
         // state-independent part of the next 32 steps, one step per lane
         rbase = step;
         const unsigned long long st_ = step + (unsigned long long)g;
@@ -250,7 +318,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
         ring_valid = true;
       }
       const bool live = sg < nb;
-      const uint4 rq = ring[min((int)(step - rbase) + sg, 31)];
+      if (SPEC_SG > 1) rq = ring[min((int)(step - rbase) + sg, 31)];
       const int sl = (int)(rq.x >> 24), pos1 = (int)(rq.x & 0xffffffu), site1 = (int)rq.y;
       const float lf = __uint_as_float(rq.w);
 
@@ -271,7 +339,8 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
         const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
         const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
         const int k = ndiff > 0 ? (int)mulhi32(rq.z, (uint32_t)ndiff) : 0;
-        pos2 = spec_select_ne<SPEC_SG>(m, planes, sl, s1, k, l);
+        if (LISTS) pos2 = ndiff > 0 ? (int)lists[m.sl_list_off[sl] + s1 * n_act + k] : 0;
+        else pos2 = spec_select_ne<SPEC_SG == 1 ? 2 : SPEC_SG>(m, planes, sl, s1, k, l);
         if (ndiff > 0) {
           site2 = site_of_pos(m, sl, pos2);
           s2 = occ[site2];
@@ -285,7 +354,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
         if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, l);
         else acc = spec_swap_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, site2, s2, s1, l);
       }
-      acc += __shfl_xor_sync(FULL, acc, 1);
+      if (SPEC_SG > 1) acc += __shfl_xor_sync(FULL, acc, 1);
       if (SPEC_SG > 2) acc += __shfl_xor_sync(FULL, acc, 2);
       double dH = acc;
       if (MU_POSSIBLE && m.muW) {
@@ -337,6 +406,13 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
           pl[c_s2 * nw + (c_pos1 >> 5)] ^= bit1;
           pl[c_s2 * nw + (c_pos2 >> 5)] ^= bit2;
           pl[c_s1 * nw + (c_pos2 >> 5)] ^= bit2;
+        }
+        if (LISTS) {
+          // position 1 now differs from code s1 and position 2 no longer does; the reverse for code s2
+          const int n_act = m.sl_off[c_sl + 1] - m.sl_off[c_sl];
+          uint16_t* lb = lists + m.sl_list_off[c_sl];
+          spec_list_replace(lb + c_s1 * n_act, n_act - cnt[c_sl * LMC_MAX_CODES + c_s1], c_pos2, c_pos1, g);
+          spec_list_replace(lb + c_s2 * n_act, n_act - cnt[c_sl * LMC_MAX_CODES + c_s2], c_pos1, c_pos2, g);
         }
       } else if (c_n == 1) {
         const RecChunk pre0 = load_records<G>(m, c_site1, g);

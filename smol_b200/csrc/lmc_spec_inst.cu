@@ -6,7 +6,7 @@ namespace lmc {
 
 template <bool KONE, int USHER, int SG>
 static int launch_spec_sg(const DevModel& m, const RunArgs& a, const LaunchCfg& lc) {
-  auto kern = lmc_spec_kernel<KONE, USHER, SG>;
+  auto kern = lmc_spec_kernel<KONE, USHER, SG, (SG == 1 && USHER == LMC_USHER_SWAP)>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<lc.grid, lc.threads, lc.smem, lc.stream>>>(m, a);
@@ -15,6 +15,7 @@ static int launch_spec_sg(const DevModel& m, const RunArgs& a, const LaunchCfg& 
 
 template <bool KONE, int USHER>
 static int launch_spec_one(const DevModel& m, const RunArgs& a, int sg, const LaunchCfg& lc) {
+  if (sg == 1) return launch_spec_sg<KONE, USHER, 1>(m, a, lc);
   return sg == 2 ? launch_spec_sg<KONE, USHER, 2>(m, a, lc) : launch_spec_sg<KONE, USHER, 4>(m, a, lc);
 }
 

@@ -249,7 +249,7 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["decomposition", "expansion"])
 @pytest.mark.parametrize("n,T,thin", [(2, 1000.0, 20), (4, 300.0, 7), (4, 1000.0, 64), (3, 1e5, 13)])
-@pytest.mark.parametrize("sg", ["4", "2"])
+@pytest.mark.parametrize("sg", ["4", "2", "1"])
 def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypatch):
     """low / medium / near-infinite temperature (acceptance ~0 .. ~1), sampling intervals that are not
     multiples of the batch, aliased 2x2x2 cell; spec_mode=2 forces the speculative kernel, 1 the classic
@@ -282,7 +282,7 @@ def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypa
 
 
 @pytest.mark.parametrize("T", [400.0, 3000.0])
-@pytest.mark.parametrize("sg", ["4", "2"])
+@pytest.mark.parametrize("sg", ["4", "2", "1"])
 def test_speculative_semigrand_flip_trajectory(cuda_device, T, sg, monkeypatch):
     """ternary rocksalt cations, chemical potentials, single flips (no Ewald term): speculative kernel"""
     import smol_b200 as S
