@@ -25,6 +25,8 @@
  *                            Flip/Swap/TableFlip.propose_step (smol/moca/kernel/mcusher.py:154-200, 553-711),
  *                            Metropolis / WangLandau accept (kernel/metropolis.py:31-49,
  *                            kernel/wanglandau.py:186-266)
+ *   lmc_ewald_field       <- the site sums of delta_ewald_single_flip (smol/utils/cluster/ewald.pyx:43-58),
+ *                            evaluated once per walker and then kept current by lmc_run (potential cache)
  *   lmc_cast_*            <- the int32 occupancy dtype contract (sampler.py:406)
  *
  * Conventions: every function returns 0 on success, <0 on error (message via lmc_last_error);
@@ -43,7 +45,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 4
+#define LMC_ABI_VERSION 5
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -159,6 +161,10 @@ typedef struct LmcRunConfig {
   double* trace_enthalpy_dev; /* [S][W] */
   uint8_t* trace_accepted_dev;/* [S][W] flag of the LAST step of the interval (sampler.py:199-201) */
   int32_t* trace_naccepted_dev;/* [S][W] accepted steps in the interval (engine extension) */
+  /* optional Ewald potential cache, in/out: field[w][k] = sum_j q_j K[k][j] of walker w's CURRENT occupancy
+     (lmc_ewald_field).  Non-NULL: a flip costs O(1) reads of it and every accepted step updates it;
+     NULL: every flip gathers its Ewald matrix rows.  Needs a factorisable Ewald matrix (lmc_model_info). */
+  double* ewald_field_dev;    /* [W][N] */
   LmcWangLandau wl;           /* used when kernel == LMC_KERNEL_WANGLANDAU */
 } LmcRunConfig;
 
@@ -169,6 +175,10 @@ int lmc_row_stride(int num_sites); /* bytes per walker row of occ_dev (16-byte m
 int lmc_model_create(const LmcModelDesc* desc, LmcModel** out);
 int lmc_model_destroy(LmcModel* model);
 int lmc_model_num_features(const LmcModel* model);
+/* info[0] = 1 if the Ewald matrix factorises as M[i,j] = q_i q_j K[site_i, site_j] (potential cache usable),
+ * info[1] = speculative-kernel tables built, info[2] = bytes of the staged table blob, info[3] = records per site
+ * of the speculative kernel; entries beyond `n` are not written */
+int lmc_model_info(const LmcModel* model, int32_t* info, int n);
 
 /* int32 [W][N] <-> int8 [W][row_stride] */
 int lmc_cast_i32_to_i8(const int32_t* src_dev, int8_t* dst_dev, int num_walkers, int num_sites, void* stream);
@@ -178,6 +188,9 @@ int lmc_cast_i8_to_i32(const int8_t* src_dev, int32_t* dst_dev, int64_t num_rows
 /* features_dev [W][F] <- full evaluation of every walker's occupancy; enthalpy_dev [W] may be NULL */
 int lmc_full_features(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* features_dev,
                       double* enthalpy_dev, void* stream);
+
+/* field_dev [W][N] <- Ewald potential cache of every walker's occupancy (see LmcRunConfig.ewald_field_dev) */
+int lmc_ewald_field(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* field_dev, void* stream);
 
 /* out_dev [W][F] <- feature change of walker w for its k flips (sites/codes [W][k] int32, applied
  * sequentially, chemical work against the pre-step occupancy) */

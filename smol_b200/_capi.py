@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 4
+LMC_ABI_VERSION = 5
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -92,7 +92,7 @@ class LmcRunConfig(C.Structure):
         ("step_begin", C.c_uint64), ("seeds_dev", _P), ("beta_dev", _P),
         ("occ_dev", _P), ("features_dev", _P), ("enthalpy_dev", _P),
         ("trace_occ_dev", _P), ("trace_features_dev", _P), ("trace_enthalpy_dev", _P),
-        ("trace_accepted_dev", _P), ("trace_naccepted_dev", _P),
+        ("trace_accepted_dev", _P), ("trace_naccepted_dev", _P), ("ewald_field_dev", _P),
         ("wl", LmcWangLandau),
     ]
 
@@ -100,7 +100,8 @@ class LmcRunConfig(C.Structure):
 EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
-    "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host",
+    "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host", "lmc_model_info",
+    "lmc_ewald_field",
 )
 
 _LIB = None
@@ -133,6 +134,8 @@ def load():
     lib.lmc_full_features.argtypes = [_P, _P, C.c_int, _P, _P, _P]
     lib.lmc_delta_features.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P]
     lib.lmc_run.argtypes = [_P, C.POINTER(LmcRunConfig), _P]
+    lib.lmc_model_info.argtypes = [_P, C.POINTER(C.c_int32), C.c_int]
+    lib.lmc_ewald_field.argtypes = [_P, _P, C.c_int, _P, _P]
     lib.lmc_launch_count.restype = C.c_int64
     lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:

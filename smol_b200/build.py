@@ -32,7 +32,7 @@ def up_to_date() -> bool:
 def _deps(src):
     """files an object depends on: its source, every header, and (for the API unit only) nothing else"""
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    if not src.endswith("lmc_spec_inst.cu"):
+    if "lmc_spec_inst" not in src:
         hdrs = [h for h in hdrs if not h.endswith("lmc_spec.cuh")]
     return [src, os.path.join(HERE, "..", "include", "lmc.h"), *hdrs]
 
@@ -59,6 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"),
                          os.path.join(objdir, f"lmc_run_g{g}_wl{wl}.o"), [f"-DLMC_G={g}", f"-DLMC_WL={wl}"], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst.cu"), os.path.join(objdir, "lmc_spec.o"), [], force))
+    jobs.append((os.path.join(CSRC, "lmc_spec_inst2.cu"), os.path.join(objdir, "lmc_spec2.o"), [], force))
     log = []
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:
         for cmd, r in ex.map(_compile, jobs):

@@ -467,6 +467,17 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     if (fact) {
       m.ewNQ = (int)qtab.size();
       qtab.push_back(0.0);   // vacancy
+      // exactly symmetric site kernel (the check above bounds the asymmetry by 1e-12 max|M|): the potential
+      // cache reads rows where the definition has columns
+      for (size_t s = 0; s < N; ++s)
+        for (size_t t = s + 1; t < N; ++t) K[s * N + t] = K[t * N + s] = 0.5 * (K[s * N + t] + K[t * N + s]);
+      std::vector<double2> qd(N * (size_t)m.ewW, make_double2(0.0, 0.0));
+      for (size_t k = 0; k < N; ++k)
+        for (int c = 0; c < m.ewW; ++c) {
+          const int e = d->ewald_inds[k * m.ewW + c];
+          if (e >= 0) qd[k * m.ewW + c] = make_double2(q[e], dg[e]);
+        }
+      UP(double2, qd.data(), qd.size(), m.ewQD);
       UP(double, K.data(), N * N, m.ewK);
       UP(double, q.data(), E, m.ewQ);
       UP(double, dg.data(), E, m.ewD);
@@ -616,6 +627,28 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
   return 0;
 }
 
+extern "C" int lmc_model_info(const LmcModel* mdl, int32_t* info, int n) {
+  if (!mdl || !info) return fail("null argument");
+  const DevModel& m = mdl->dm;
+  const int32_t v[4] = {m.E > 0 && m.ewK != nullptr, m.spOK, m.blob_bytes, m.spNQ};
+  for (int i = 0; i < n && i < 4; ++i) info[i] = v[i];
+  return 0;
+}
+
+extern "C" int lmc_ewald_field(const LmcModel* mdl, const int8_t* occ, int W, double* field, void* stream) {
+  if (!mdl || !occ || !field) return fail("null argument");
+  if (W <= 0) return 0;
+  const DevModel& m = mdl->dm;
+  if (m.E <= 0 || !m.ewK) return fail("the Ewald potential cache needs an Ewald matrix of the form q_i q_j K[site_i, site_j]");
+  const size_t smem = (size_t)FIELD_WPB * m.N * sizeof(double);
+  if ((int)smem > mdl->smem_optin) return fail("too many sites for the Ewald potential cache kernel");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(lmc_ewald_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lmc_ewald_field_kernel<<<(W + FIELD_WPB - 1) / FIELD_WPB, 256, smem, (cudaStream_t)stream>>>(m, occ, W, field);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int lmc_cast_i32_to_i8(const int32_t* src, int8_t* dst, int W, int N, void* stream) {
   const int Npad = lmc_row_stride(N);
   const long long n = (long long)W * Npad;
@@ -681,6 +714,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (c->usher == LMC_USHER_TABLEFLIP && m.tfNF == 0) return fail("model has no flip table");
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins <= 1) return fail("Wang-Landau needs more than one bin");
   const bool ewald = m.E > 0;
+  const bool field = ewald && c->ewald_field_dev != nullptr;   // Ewald through the potential cache
+  if (field && !m.ewK) return fail("ewald_field_dev needs an Ewald matrix of the form q_i q_j K[site_i, site_j]");
   int G = c->group_size;
   if (const char* e = getenv("LMC_GROUP_SIZE")) { if (G == 0) G = atoi(e); }
   // kernel selection: the speculative-batch kernel (lmc_spec.cuh) wins while fewer than ~1/3 of the
@@ -696,11 +731,12 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   }
   int spec_mode = c->spec_mode;
   if (const char* e = getenv("LMC_SPEC")) { if (spec_mode == 0) spec_mode = atoi(e) ? 2 : 1; }
-  const bool spec_ok = m.spOK && !ewald && c->kernel == LMC_KERNEL_METROPOLIS &&
+  const bool spec_ok = m.spOK && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
                        (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
-  if (spec_mode == 2 && !spec_ok) return fail("the speculative kernel supports Metropolis flip/swap steps without Ewald term only");
+  if (spec_mode == 2 && !spec_ok)
+    return fail("the speculative kernel supports Metropolis flip/swap steps (an Ewald term through ewald_field_dev only)");
   // auto: only while the staged tables leave room for a full complement of resident walkers per SM
-  const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35 && m.blob_bytes <= 24 * 1024));
+  const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35 && m.blob_bytes <= 40 * 1024));
   if (use_spec) G = 32;
   // lanes per speculated step (lmc_spec.cuh).  Four everywhere: with two or one lane per step (one uses
   // sorted position lists for the swap partner) the scalar work per step shrinks, but 16 / 32 unrelated
@@ -756,7 +792,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
   a.off_ring = a.off_plane + ((LMC_PLANE_COPIES * m.plane_words * 4 + 15) & ~15);  // planes (+ prefix popcounts)
   a.off_eidx = a.off_ring + G * 16;                                   // per-lane precomputed proposals
-  a.off_lists = a.off_eidx + (ewald ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
+  a.ew_field = field ? c->ewald_field_dev : nullptr;
+  a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
   a.walker_smem = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
@@ -776,6 +813,14 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     }
     if (best_t) threads = best_t;
   }
+  bool spec_wide = false;
+  if (use_spec && auto_threads) {
+    // seven blocks of four walkers per SM while they fit; with a larger table blob two blocks of fourteen
+    // walkers (448 threads) keep the same 28 walkers resident
+    const size_t b4 = blob + 4 * (size_t)(m.Npad + a.walker_smem) + 1024, b14 = blob + 14 * (size_t)(m.Npad + a.walker_smem) + 1024;
+    if (7 * b4 > 227 * 1024 && 2 * b14 <= 227 * 1024 && (int)b14 <= mdl->smem_optin) { spec_wide = true; threads = 448; }
+  }
+  if (const char* e = getenv("LMC_SPEC_WIDE")) { if (use_spec) { spec_wide = atoi(e) != 0; threads = spec_wide ? 448 : 128; } }
   for (;;) {
     a.wpb = threads / G;
     smem = blob + (size_t)a.wpb * (m.Npad + a.walker_smem);
@@ -787,12 +832,14 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
   int rc = -2;
   const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
-  if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, lc);
+  spec_wide = spec_wide && threads == 448;
+  if (use_spec && (field || spec_wide)) rc = launch_spec_x(m, a, m.kone != 0, c->usher, field, spec_wide, lc);
+  else if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, lc);
   else switch (G) {
-    case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewald, c->usher, lc); break;
-    case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewald, c->usher, lc); break;
-    case 16: rc = (wl ? launch_run_wl_g16 : launch_run_g16)(m, a, m.kone != 0, ewald, c->usher, lc); break;
-    case 32: rc = (wl ? launch_run_wl_g32 : launch_run_g32)(m, a, m.kone != 0, ewald, c->usher, lc); break;
+    case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewmode, c->usher, lc); break;
+    case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewmode, c->usher, lc); break;
+    case 16: rc = (wl ? launch_run_wl_g16 : launch_run_g16)(m, a, m.kone != 0, ewmode, c->usher, lc); break;
+    case 32: rc = (wl ? launch_run_wl_g32 : launch_run_g32)(m, a, m.kone != 0, ewmode, c->usher, lc); break;
   }
   if (rc == -2) return fail("no kernel instantiated for this group size / usher");
   g_launches++;

@@ -287,6 +287,14 @@ __device__ __forceinline__ void ewald_cache_set(const DevModel& m, void* ecache,
   else reinterpret_cast<uint16_t*>(ecache)[site] = e < 0 ? (uint16_t)0xffffu : (uint16_t)e;
 }
 
+// Ewald through the potential cache fld[k] = sum_j q_j K[k][j] of the walker's current occupancy:
+//   dE(flip k: a -> b) = 2 (q_b - q_a) fld[k] + M[bb] - M[aa]          (K[k][k] = 0)
+// and an accepted flip adds (q_b - q_a) K[k][:] to the cache.  Flips of one step are sequential
+// (ewald.py:168-181): flip f sees the cache shifted by the earlier flips, dq_h K[site_h][site_f].
+__device__ __forceinline__ double2 ewald_qd(const DevModel& m, int site, int code) {
+  return __ldg(m.ewQD + site * m.ewW + code);
+}
+
 template <int G>
 __device__ __forceinline__ int select_pos_scan(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
                                           int g, uint32_t mask) {
@@ -541,10 +549,14 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // the fused MC kernel: propose -> delta features/energy (+Ewald, +mu) -> accept -> update,
 // num_samples * thin_by attempted steps per walker in ONE launch.
 // ------------------------------------------------------------------------------------------
-template <int G, bool KONE, bool EWALD, int USHER, bool WLMODE>
-__global__ void __launch_bounds__((EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 256 : 128,
-                                  (EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7))
+// EWMODE: 0 no Ewald term, 1 matrix rows gathered at every flip (flip_ewald), 2 potential cache (ewald_qd).
+// A template parameter, not a run-time switch: the table-flip variants are instruction-fetch bound and
+// carry one Ewald path each.
+template <int G, bool KONE, int EWMODE, int USHER, bool WLMODE>
+__global__ void __launch_bounds__((EWMODE || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 256 : 128,
+                                  (EWMODE || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7))
 lmc_run_kernel(const DevModel m, const RunArgs a) {
+  constexpr bool EWALD = EWMODE != 0, EWGATHER = EWMODE == 1, EWFIELD = EWMODE == 2;
   constexpr int MF = USHER == LMC_USHER_FLIP ? 1 : (USHER == LMC_USHER_SWAP ? 2 : LMC_MAX_FLIPS);
   constexpr int I1 = MF > 1 ? 1 : 0;   // index of the second flip (dead code when MF == 1)
   extern __shared__ __align__(16) unsigned char smem[];
@@ -569,6 +581,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
   uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
   void* eidx = priv + a.off_eidx;   // per-walker Ewald cache (see flip_ewald)
+  double* fld = EWFIELD ? a.ew_field + (size_t)w * m.N : nullptr;   // potential cache (global / L2)
   (void)wslab;
 
   stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
@@ -579,7 +592,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // running state
   for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
   double enth = a.enthalpy[w];
-  if (EWALD) {
+  if (EWGATHER) {
     for (int i = g; i < m.N; i += G) ewald_cache_set(m, eidx, i, occ[i]);
   }
   // species counts per (active sublattice, code) and one bit-plane per code
@@ -855,7 +868,23 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       // Ewald part first: it only touches the per-walker Ewald cache, never the occupancy.  Flip f is
       // evaluated with flips < f applied to the cache (sequential semantics, ewald.py:168-181); the
       // last flip is applied on accept only.  One loop, not unrolled: one copy of the row-gather code.
-      if (EWALD) {
+      double dq[MF];
+#pragma unroll
+      for (int f = 0; f < MF; ++f) dq[f] = 0.0;
+      if (EWFIELD) {
+        double e = 0.0;
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          if (f < st.n) {
+            const double2 qn = ewald_qd(m, st.site[f], st.newc[f]), qo = ewald_qd(m, st.site[f], st.oldc[f]);
+            dq[f] = qn.x - qo.x;
+            double phi = fld[st.site[f]];
+#pragma unroll
+            for (int h = 0; h < f; ++h) phi += dq[h] * __ldg(m.ewK + (size_t)st.site[h] * m.N + st.site[f]);
+            e += 2.0 * dq[f] * phi + (qn.y - qo.y);
+          }
+        acc_ew = g == 0 ? e : 0.0;   // every lane holds the same value; the group sum below counts it once
+      } else if (EWGATHER) {
 #pragma unroll 1
         for (int f = 0; f < st.n; ++f) {
           const int sf = pick<MF>(st.site, f), of = pick<MF>(st.oldc, f), nf = pick<MF>(st.newc, f);
@@ -953,7 +982,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
                                    (SEGPRE && f == 0) ? seg0 : ((SEGPRE && f == 1) ? seg1 : load_segment<G>(m, st.site[f], g)));
         if (g == 0) {
           if (deferred1) occ[st.site[I1]] = (uint8_t)st.newc[I1];
-          if (EWALD && st.n > 0)   // the last flip enters the Ewald cache on accept only
+          if (EWGATHER && st.n > 0)   // the last flip enters the Ewald cache on accept only
             ewald_cache_set(m, eidx, pick<MF>(st.site, st.n - 1), pick<MF>(st.newc, st.n - 1));
           if (EWALD) feat[m.ewF] += dEw;
           if (MU_POSSIBLE && m.muW) feat[m.muF] += dmu;
@@ -980,6 +1009,15 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
               px[st.newc[f] * nw + wd] += 1u;
             }
           }
+        if (EWFIELD) {   // accepted: shift the potential cache by the changed charges
+          for (int k = g; k < m.N; k += G) {
+            double v = fld[k];
+#pragma unroll
+            for (int f = 0; f < MF; ++f)
+              if (f < st.n) v += dq[f] * __ldg(m.ewK + (size_t)st.site[f] * m.N + k);
+            fld[k] = v;
+          }
+        }
         enth += dH;
         if (wl_mode) { cur_fb = new_fb; s_cur = s_new; }
         ++nacc;
@@ -989,7 +1027,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           for (int f = MF - 1; f >= 0; --f)
             if (f < st.n) {
               if (!(f == 1 && deferred1)) occ[st.site[f]] = (uint8_t)st.oldc[f];
-              if (EWALD && f + 1 < st.n) ewald_cache_set(m, eidx, st.site[f], st.oldc[f]);
+              if (EWGATHER && f + 1 < st.n) ewald_cache_set(m, eidx, st.site[f], st.oldc[f]);
             }
         }
       }
@@ -1208,6 +1246,44 @@ __global__ void lmc_full_kernel(const DevModel m, const int8_t* __restrict__ occ
     enth += nat[m.muF] * p;
   }
   if (enthalpy && threadIdx.x == 0) enthalpy[w] = enth;
+}
+
+// Ewald potential cache of every walker: field[w][s] = sum_k q_k(w) K[s][k].  Four walkers per block share
+// each row of K (read once from L2, coalesced); one warp per row.
+constexpr int FIELD_WPB = 4;
+__global__ void lmc_ewald_field_kernel(const DevModel m, const int8_t* __restrict__ occ_g, int W, double* __restrict__ field) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* qs = reinterpret_cast<double*>(smem);   // [FIELD_WPB][N] charges of the walkers' current species
+  const int w0 = blockIdx.x * FIELD_WPB;
+  for (int i = threadIdx.x; i < FIELD_WPB * m.N; i += blockDim.x) {
+    const int ww = i / m.N, k = i - ww * m.N;
+    double q = 0.0;
+    if (w0 + ww < W) {
+      const int e = m.ewInds[k * m.ewW + occ_g[(size_t)(w0 + ww) * m.Npad + k]];
+      if (e >= 0) q = m.ewQ[e];
+    }
+    qs[i] = q;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nwp = blockDim.x >> 5;
+  for (int s = wp; s < m.N; s += nwp) {
+    const double* krow = m.ewK + (size_t)s * m.N;
+    double acc[FIELD_WPB];
+#pragma unroll
+    for (int ww = 0; ww < FIELD_WPB; ++ww) acc[ww] = 0.0;
+    for (int k = lane; k < m.N; k += 32) {
+      const double kv = __ldg(krow + k);
+#pragma unroll
+      for (int ww = 0; ww < FIELD_WPB; ++ww) acc[ww] += qs[ww * m.N + k] * kv;
+    }
+#pragma unroll
+    for (int ww = 0; ww < FIELD_WPB; ++ww) {
+      double v = acc[ww];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && w0 + ww < W) field[(size_t)(w0 + ww) * m.N + s] = v;
+    }
+  }
 }
 
 __global__ void lmc_cast_i32_i8_kernel(const int* __restrict__ src, int8_t* __restrict__ dst, int W, int N, int Npad) {

@@ -9,17 +9,20 @@ struct LaunchCfg {
   size_t smem;
   cudaStream_t stream;
 };
+// ewald: 0 none, 1 gathered matrix rows, 2 potential cache
 // return 0 on success, a cudaError_t value on failure, -2 if the combination is not instantiated
-int launch_run_g4(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
-int launch_run_g8(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
-int launch_run_g16(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
-int launch_run_g32(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
+int launch_run_g4(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
+int launch_run_g8(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
+int launch_run_g16(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
+int launch_run_g32(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
 // speculative-batch Metropolis kernel (flip / swap)
 // sg = lanes per speculated step (1, 2 or 4; 1 uses sorted position lists for swaps)
 int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int sg, const LaunchCfg& lc);
+// Ewald potential cache (ewf) and / or 448-thread blocks (wide), four lanes per step
+int launch_spec_x(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
 // Wang-Landau variants
-int launch_run_wl_g4(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
-int launch_run_wl_g8(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
-int launch_run_wl_g16(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
-int launch_run_wl_g32(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher, const LaunchCfg& lc);
+int launch_run_wl_g4(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
+int launch_run_wl_g8(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
+int launch_run_wl_g16(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
+int launch_run_wl_g32(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
 }  // namespace lmc

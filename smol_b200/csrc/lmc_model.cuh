@@ -40,6 +40,7 @@ struct DevModel {
   const double* ewD;       // [E] diagonal M[i,i]
   const uint8_t* ewQidx;   // [E] index of the row's charge in the shared-memory charge table
   int ewNQ;                // number of distinct charges; index ewNQ is the 0.0 used for vacancies
+  const double2* ewQD;     // [N][ewW] (charge, diagonal M[e,e]) of species code c on site k; (0, 0) for vacancies
   // chemical potentials
   int muW, muF;
   const double* mu;        // [N][muW]
@@ -90,6 +91,7 @@ struct RunArgs {
   double* tr_enth;
   uint8_t* tr_acc;
   int* tr_nacc;
+  double* ew_field;   // [W][N] Ewald potential cache (nullptr: gather the matrix rows), see lmc.h
   LmcWangLandau wl;
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker

@@ -10,7 +10,7 @@
 
 namespace lmc {
 
-template <bool KONE, bool EWALD, int USHER>
+template <bool KONE, int EWALD, int USHER>
 static int launch_one(const DevModel& m, const RunArgs& a, const LaunchCfg& lc) {
   auto kern = lmc_run_kernel<LMC_G, KONE, EWALD, USHER, (LMC_WL != 0)>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
@@ -19,7 +19,7 @@ static int launch_one(const DevModel& m, const RunArgs& a, const LaunchCfg& lc) 
   return (int)cudaGetLastError();
 }
 
-template <bool KONE, bool EWALD>
+template <bool KONE, int EWALD>
 static int launch_usher(const DevModel& m, const RunArgs& a, int usher, const LaunchCfg& lc) {
   switch (usher) {
     case LMC_USHER_FLIP: return launch_one<KONE, EWALD, LMC_USHER_FLIP>(m, a, lc);
@@ -36,10 +36,13 @@ static int launch_usher(const DevModel& m, const RunArgs& a, int usher, const La
 #else
 #define LMC_FN LMC_CAT(launch_run_g, LMC_G)
 #endif
-int LMC_FN(const DevModel& m, const RunArgs& a, bool kone, bool ewald, int usher,
+// ewald: 0 none, 1 gathered matrix rows, 2 potential cache (RunArgs::ew_field)
+int LMC_FN(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher,
                                  const LaunchCfg& lc) {
-  if (kone) return ewald ? launch_usher<true, true>(m, a, usher, lc) : launch_usher<true, false>(m, a, usher, lc);
-  return ewald ? launch_usher<false, true>(m, a, usher, lc) : launch_usher<false, false>(m, a, usher, lc);
+  if (kone) return ewald == 2 ? launch_usher<true, 2>(m, a, usher, lc)
+                              : (ewald ? launch_usher<true, 1>(m, a, usher, lc) : launch_usher<true, 0>(m, a, usher, lc));
+  return ewald == 2 ? launch_usher<false, 2>(m, a, usher, lc)
+                    : (ewald ? launch_usher<false, 1>(m, a, usher, lc) : launch_usher<false, 0>(m, a, usher, lc));
 }
 
 }  // namespace lmc

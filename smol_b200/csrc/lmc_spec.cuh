@@ -195,8 +195,13 @@ __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint
   return (a0 + a1) + (b0 + b1);
 }
 
-template <bool KONE, int USHER, int SPEC_SG, bool LISTS>
-__global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, const RunArgs a) {
+// EWF: Ewald term through the potential cache (a.ew_field, see lmc_kernels.cuh): two cached doubles and
+// a charge table lookup per flip, one row of the site kernel per ACCEPTED flip.
+// MAXT / MINB: launch bounds.  (128, 7) while seven blocks of four walkers fit an SM's shared memory;
+// (448, 2) -- fourteen walkers share one copy of a larger table blob -- otherwise: both keep 28 walkers
+// resident per SM (4096 walkers = one wave on 148 SMs) at 72 registers.
+template <bool KONE, int USHER, int SPEC_SG, bool LISTS, bool EWF, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, const RunArgs a) {
   static_assert(USHER == LMC_USHER_FLIP || USHER == LMC_USHER_SWAP, "flip / swap only");
   static_assert(SPEC_SG == 1 || SPEC_SG == 2 || SPEC_SG == 4, "1, 2 or 4 lanes per speculated step");
   static_assert(!LISTS || USHER == LMC_USHER_SWAP, "position lists serve the swap usher");
@@ -284,6 +289,8 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
   const double beta = a.beta[w];
   constexpr bool MU_POSSIBLE = USHER != LMC_USHER_SWAP;
   const double nat_mu = (MU_POSSIBLE && m.muW) ? t.nat[m.muF] : 0.0;
+  const double nat_ew = EWF ? t.nat[m.ewF] : 0.0;
+  double* fld = EWF ? a.ew_field + (size_t)w * m.N : nullptr;
 
   unsigned long long step = a.step0;
   unsigned long long rbase = step;
@@ -349,6 +356,17 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
       }
 
       // ------------------------------ evaluate ------------------------------------------------
+      // Ewald term first: its (L2) loads are in flight while the cluster records are evaluated
+      double dEw = 0.0;
+      if (EWF && n > 0) {
+        const double2 qn = ewald_qd(m, site1, s2), qo = ewald_qd(m, site1, s1);
+        const double dq1 = qn.x - qo.x;
+        dEw = 2.0 * dq1 * fld[site1] + (qn.y - qo.y);
+        if (USHER == LMC_USHER_SWAP) {   // site 2 takes s1; it sees the cache shifted by flip 1
+          const double2 qn2 = ewald_qd(m, site2, s1), qo2 = ewald_qd(m, site2, s2);
+          dEw += 2.0 * (qn2.x - qo2.x) * (fld[site2] + dq1 * __ldg(m.ewK + (size_t)site1 * m.N + site2)) + (qn2.y - qo2.y);
+        }
+      }
       double acc = 0.0, dmu = 0.0;
       if (live && n > 0) {
         if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, l);
@@ -357,6 +375,7 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
       if (SPEC_SG > 1) acc += __shfl_xor_sync(FULL, acc, 1);
       if (SPEC_SG > 2) acc += __shfl_xor_sync(FULL, acc, 2);
       double dH = acc;
+      if (EWF) dH += nat_ew * dEw;
       if (MU_POSSIBLE && m.muW) {
         dmu = __ldg(m.mu + site1 * m.muW + s2) - __ldg(m.mu + site1 * m.muW + s1);
         dH += nat_mu * dmu;
@@ -387,6 +406,17 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_kernel(const DevModel m, cons
       const int c_site2 = __shfl_sync(FULL, site2, src), c_s2 = __shfl_sync(FULL, s2, src), c_pos2 = __shfl_sync(FULL, pos2, src);
       const double c_dH = __shfl_sync(FULL, dH, src);
       const double c_dmu = __shfl_sync(FULL, dmu, src);
+      if (EWF) {
+        // accepted: the changed charges shift the potential cache (read again by the next batch: the
+        // __syncwarp at the end of the commit orders these stores before those loads)
+        const double c_dEw = __shfl_sync(FULL, dEw, src);
+        const double dq1 = ewald_qd(m, c_site1, c_s2).x - ewald_qd(m, c_site1, c_s1).x;
+        const double dq2 = c_n == 2 ? ewald_qd(m, c_site2, c_s1).x - ewald_qd(m, c_site2, c_s2).x : 0.0;
+        const double* k1 = m.ewK + (size_t)c_site1 * m.N;
+        const double* k2 = m.ewK + (size_t)(c_n == 2 ? c_site2 : c_site1) * m.N;
+        for (int k = g; k < m.N; k += G) fld[k] += dq1 * __ldg(k1 + k) + dq2 * __ldg(k2 + k);
+        if (g == 0) feat[m.ewF] += c_dEw;
+      }
       if (c_n == 2) {
         if (g == 0) occ[c_site1] = (uint8_t)c_s2;
         __syncwarp();

@@ -115,6 +115,21 @@ class LmcEngine:
                                                codes.data_ptr(), k, out.data_ptr(), self._stream()))
         return out
 
+    def model_info(self):
+        """(Ewald matrix factorises, speculative tables built, table blob bytes, speculative records per site)"""
+        info = (C.c_int32 * 4)()
+        capi.check(self.lib.lmc_model_info(self.handle, info, 4))
+        return tuple(int(x) for x in info)
+
+    def ewald_field(self, occ_dev, out=None):
+        """Ewald potential cache ``[W, N]`` (float64) of the walkers' occupancies, see ``lmc.h``."""
+        torch = _torch()
+        W = occ_dev.shape[0]
+        if out is None:
+            out = torch.empty((W, self.N), dtype=torch.float64, device=self.device)
+        capi.check(self.lib.lmc_ewald_field(self.handle, occ_dev.data_ptr(), W, out.data_ptr(), self._stream()))
+        return out
+
     def run(self, cfg: capi.LmcRunConfig):
         capi.check(self.lib.lmc_run(self.handle, C.byref(cfg), self._stream()))
 

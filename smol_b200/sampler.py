@@ -150,7 +150,7 @@ class Sampler:
     def __init__(self, ensemble, kernel_type="Metropolis", step_type="swap", nwalkers=1, seeds=None,
                  temperature=None, wl_params=None, usher_kwargs=None, walker_id_base=0,
                  group_size=0, block_threads=0, record_occupancy=True, device=None, kB_=kB,
-                 spec_mode=0):
+                 spec_mode=0, ewald_field="auto"):
         from .engine import LmcEngine
         self.ensemble = ensemble
         self.kernel_type = kernel_type
@@ -202,6 +202,16 @@ class Sampler:
         self.group_size, self.block_threads = int(group_size), int(block_threads)
         # Metropolis flip/swap kernel: 0 auto (by measured acceptance), 1 classic, 2 speculative batch
         self.spec_mode = int(spec_mode)
+        # Ewald term through the per-walker potential cache (O(1) per flip, one row of the site kernel per
+        # accepted flip) instead of gathering matrix rows at every flip: "auto" = while fewer than a quarter
+        # of the steps are accepted (needs an Ewald matrix of the form q_i q_j K[site_i, site_j])
+        if ewald_field == "auto" and os.environ.get("LMC_EWALD_FIELD") in ("0", "1"):   # A/B switch
+            ewald_field = os.environ["LMC_EWALD_FIELD"] == "1"
+        if ewald_field not in ("auto", True, False):
+            raise ValueError("ewald_field must be 'auto', True or False")
+        self.ewald_field = ewald_field
+        self._ew_field = None
+        self._acc_est = None
         self.record_occupancy = record_occupancy
         self.mckernels = [_KernelView(self, i) for i in range(self.nwalkers)]
         self._step_counter = 0
@@ -225,7 +235,7 @@ class Sampler:
         if kernel_type is None:
             kernel_type = "Metropolis"
         engine_kw = {k: kwargs.pop(k) for k in ("walker_id_base", "group_size", "block_threads", "spec_mode",
-                                                "record_occupancy", "device") if k in kwargs}
+                                                "record_occupancy", "device", "ewald_field") if k in kwargs}
         key = kernel_type.lower().replace("_", "").replace("-", "")
         temperature, wl = None, None
         if key == "wanglandau":
@@ -350,6 +360,15 @@ class Sampler:
         # initial trace: full evaluation of the starting occupancies (base.py:345-365,
         # wanglandau.py:290-300)
         feat, enth = eng.full_features(self._occ_dev)
+        # Ewald potential cache: rebuilt from the occupancies at every run (bounds its rounding drift to one
+        # run), kept current by the kernels in between
+        use_field = False
+        if self.ewald_field is not False and eng.model_info()[0]:
+            use_field = self.ewald_field is True or self._acc_est is None or self._acc_est < 0.25
+        elif self.ewald_field is True:
+            raise RuntimeError("ewald_field=True needs an Ewald term whose matrix factorises as q_i q_j K[site_i, site_j]")
+        if use_field:
+            self._ew_field = eng.ewald_field(self._occ_dev, out=self._ew_field)
         if self._kernel == capi.LMC_KERNEL_WANGLANDAU and self._wl_state is None:
             self._init_wl()
         if getattr(self, "_seeds_dev", None) is None:
@@ -405,6 +424,8 @@ class Sampler:
                 traces["occupancy"] = np.zeros((n, W, 0), dtype=np.int8)
             if "temperature" in self.samples._shapes:
                 traces["temperature"] = np.broadcast_to(self._temperature[None, :, None], (n, W, 1)).copy()
+            if n and W:   # acceptance of the chunk: steers the Ewald path of the next run
+                self._acc_est = float(traces["n_accepted"][-1].mean()) / thin_by
             self.samples.append(traces, thin_by, owned=owned)
 
         done, ci, pending = 0, 0, None
@@ -425,6 +446,7 @@ class Sampler:
             cfg.trace_occ_dev = d["occupancy"].data_ptr() if self.record_occupancy else None
             cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
             cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
+            cfg.ewald_field_dev = self._ew_field.data_ptr() if use_field else None
             if self._kernel == capi.LMC_KERNEL_WANGLANDAU:
                 p, st = self._wl, self._wl_state
                 wl = cfg.wl

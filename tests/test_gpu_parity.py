@@ -132,11 +132,21 @@ def test_canonical_swap_trajectory(cuda_device, kind, n, group):
     assert 0 < smp.samples.step_efficiency() <= 1
 
 
-@pytest.mark.parametrize("factorize", ["1", "0", "random"])
+@pytest.mark.parametrize("factorize", ["1", "gather", "spec", "spec-wide", "0", "random"])
 def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
-    """factorize=1: M = q q^T x K fast path; 0: generic transposed-row gather; random: a symmetric matrix
-    that does NOT factorise (the library must detect that and fall back)."""
+    """factorize=1: M = q q^T x K, Ewald through the per-walker potential cache (the default); gather: the
+    same matrix with one row of K gathered per flip; spec / spec-wide: potential cache inside the speculative
+    kernel (128- and 448-thread blocks); 0: generic transposed-row gather; random: a symmetric matrix that
+    does NOT factorise (the library must detect that and fall back)."""
     monkeypatch.setenv("LMC_EWALD_FACTORIZE", "0" if factorize == "0" else "1")
+    kw = {}
+    if factorize == "gather":
+        kw = dict(ewald_field=False)
+    elif factorize.startswith("spec"):
+        kw = dict(spec_mode=2, ewald_field=True)
+        monkeypatch.setenv("LMC_SPEC_WIDE", "1" if factorize == "spec-wide" else "0")
+    else:
+        kw = dict(spec_mode=1)
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
@@ -163,8 +173,43 @@ def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
     W = 4
     occ0 = M.random_occupancies(sub, scm, W, seed=2)
     seeds = np.arange(7, 7 + W)
-    smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 300, 10, occ0, seeds, T=1500.0)
+    smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 300, 10, occ0, seeds, T=1500.0, usher_kwargs=kw)
     _compare_traces(smp, ref)
+    assert (smp._ew_field is not None) == (factorize in ("1", "spec", "spec-wide"))
+    # a second run continues the chains (potential cache rebuilt from the occupancies, then kept current)
+    smp.run(100, thin_by=10)
+    assert smp.samples.num_samples == 40
+
+
+@pytest.mark.parametrize("mode", ["classic", "spec"])
+def test_canonical_ewald_swap_trajectory(cuda_device, mode):
+    """canonical swaps with an Ewald term through the potential cache: flip 2 of a swap sees the cache
+    shifted by flip 1 (one element of the site kernel); classic and speculative kernels"""
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    sub = M.rocksalt_subspace()
+    scm = np.eye(3, dtype=int) * 3
+    rng = np.random.default_rng(17)
+    coefs = rng.normal(0, 0.05, sub.num_corr_functions)
+    it = L.cluster_interaction_tensors(sub, coefs)
+    ewm, ewi = L.ewald_matrix(sub, scm)
+    comp = S.CompositeProcessor(sub, scm)
+    comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
+    comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.1, ewald_matrix=ewm, ewald_inds=ewi))
+    ens_g = S.Ensemble(comp)
+    ora_p = O.CompositeProcessor([O.ClusterDecompositionProcessor(sub, scm, it), O.EwaldProcessor(ewm, ewi, 0.1)])
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices))
+
+    W = 4
+    occ0 = M.random_occupancies(sub, scm, W, seed=6)
+    seeds = np.arange(40, 40 + W)
+    smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, 520, 13, occ0, seeds, T=2500.0,
+                            usher_kwargs=dict(spec_mode=2 if mode == "spec" else 1))
+    _compare_traces(smp, ref)
+    assert smp._ew_field is not None and 0 < smp.samples.step_efficiency() < 1
 
 
 def test_wang_landau_flip_trajectory(cuda_device):
@@ -201,9 +246,11 @@ def test_wang_landau_flip_trajectory(cuda_device):
     assert (st["mod_factor"] < 1.0).any(), "flatness was never reached; weak test"
 
 
-@pytest.mark.parametrize("group,factorize", [(8, "1"), (32, "1"), (32, "0")])
+@pytest.mark.parametrize("group,factorize", [(8, "1"), (32, "1"), (32, "gather"), (32, "0")])
 def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, monkeypatch):
-    monkeypatch.setenv("LMC_EWALD_FACTORIZE", factorize)
+    """factorize=1: potential cache (flips of one step chained through elements of the site kernel);
+    gather: one row of K per flip; 0: generic matrix rows"""
+    monkeypatch.setenv("LMC_EWALD_FACTORIZE", "0" if factorize == "0" else "1")
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
@@ -234,7 +281,8 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
         occ0[w, ncell:] = rng.permutation(ani)
     seeds = np.arange(900, 900 + W)
     smp, ref, _ = _run_both(ens_g, ens_o, "table_flip", W, 400, 20, occ0, seeds, T=2000.0,
-                            usher_kwargs=dict(flip_table=table, swap_weight=0.2), group_size=group)
+                            usher_kwargs=dict(flip_table=table, swap_weight=0.2, ewald_field=factorize != "gather"
+                                              if factorize != "0" else "auto"), group_size=group)
     _compare_traces(smp, ref)
     # charge neutrality is conserved by construction of the table
     occ = smp.samples.get_occupancies(flat=True)
