@@ -279,7 +279,9 @@ def run_ours(args):
     achieved = per_gpu_rate * ALGO_BYTES_PER_STEP / 1e9
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_summary.json")))
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel this bench runs, from the
+        # committed ncu --set full capture (profiles/r01c_lmc_spec_cfg2.md)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01c_summary.json")))
         traffic = prof.get("dram_bytes_per_launch_at_bench_size")
     except Exception:
         pass
