@@ -153,6 +153,10 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
+    # libraries (NCCL's version banner) write to fd 1: keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import smol_b200 as S
@@ -317,7 +321,8 @@ def run_ours(args):
                      "sample": "C restatement oracle/lmc_oracle.c, one process per core"},
         "wall_s_timed_region": t_wall,
     }
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 def run_reference(args):
