@@ -23,10 +23,14 @@
  *   lmc_run               <- Sampler.sample inner loops (smol/moca/sampler/sampler.py:195-210, 436-440):
  *                            MCKernel.single_step (smol/moca/kernel/base.py:145-166),
  *                            Flip/Swap/TableFlip.propose_step (smol/moca/kernel/mcusher.py:154-200, 553-711),
+ *                            Composite.propose_step over Flip / Swap sub-ushers (mcusher.py:307-394),
  *                            Metropolis / WangLandau accept (kernel/metropolis.py:31-49,
  *                            kernel/wanglandau.py:186-266)
  *   lmc_ewald_field       <- the site sums of delta_ewald_single_flip (smol/utils/cluster/ewald.pyx:43-58),
  *                            evaluated once per walker and then kept current by lmc_run (potential cache)
+ *   lmc_bias_init, LmcRunConfig.bias_* <- MCBias.compute_bias / compute_bias_change of FugacityBias and
+ *                            SquareChargeBias (smol/moca/kernel/bias.py:79-287) and the bias term of the
+ *                            Metropolis exponent (kernel/metropolis.py:43-44)
  *   lmc_cast_*            <- the int32 occupancy dtype contract (sampler.py:406)
  *
  * Conventions: every function returns 0 on success, <0 on error (message via lmc_last_error);
@@ -45,13 +49,14 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 5
+#define LMC_ABI_VERSION 7
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
 #define LMC_MAX_FLIPS 4       /* changed sites per attempted step */
 #define LMC_MAX_DIMS 16       /* species counts tracked by the table-flip usher */
 #define LMC_MAX_TABLE_FLIPS 8
+#define LMC_MAX_COMPOSITE 4   /* sub-ushers of a composite usher */
 
 typedef struct LmcModel LmcModel; /* opaque */
 
@@ -121,8 +126,12 @@ typedef struct LmcModelDesc {
   double tf_swap_weight;
 } LmcModelDesc;
 
-enum { LMC_USHER_FLIP = 0, LMC_USHER_SWAP = 1, LMC_USHER_TABLEFLIP = 2 };
+enum { LMC_USHER_FLIP = 0, LMC_USHER_SWAP = 1, LMC_USHER_TABLEFLIP = 2, LMC_USHER_COMPOSITE = 3 };
 enum { LMC_KERNEL_METROPOLIS = 0, LMC_KERNEL_WANGLANDAU = 1 };
+/* bias terms of the Metropolis kernel: value = sum_k table[k][occ[k]] (LMC_BIAS_TABLE_SUM; FugacityBias with
+ * table = log fugacity fractions) or -penalty * (sum_k table[k][occ[k]])^2 (LMC_BIAS_SQUARE_SUM; SquareChargeBias
+ * with table = oxidation states) */
+enum { LMC_BIAS_NONE = 0, LMC_BIAS_TABLE_SUM = 1, LMC_BIAS_SQUARE_SUM = 2 };
 
 typedef struct LmcWangLandau {
   double min_enthalpy, max_enthalpy, bin_size, flatness, mod_update;
@@ -165,6 +174,20 @@ typedef struct LmcRunConfig {
      (lmc_ewald_field).  Non-NULL: a flip costs O(1) reads of it and every accepted step updates it;
      NULL: every flip gathers its Ewald matrix rows.  Needs a factorisable Ewald matrix (lmc_model_info). */
   double* ewald_field_dev;    /* [W][N] */
+  /* optional bias term (Metropolis only), see LMC_BIAS_*; state from lmc_bias_init, kept current by lmc_run */
+  int32_t bias_mode;
+  int32_t bias_width;            /* columns of bias_table_dev */
+  double bias_penalty;
+  const double* bias_table_dev;  /* [N][bias_width] */
+  double* bias_dev;              /* [W] running bias value, in/out */
+  double* bias_sum_dev;          /* [W] running table sum, in/out */
+  double* trace_bias_dev;        /* [S][W], may be NULL */
+  /* LMC_USHER_COMPOSITE (mcusher.py:307-394): every step picks one sub-usher by weight (random word 4 of the
+     step), which proposes with its OWN sublattice probabilities (0 = sublattice not served by it) */
+  int32_t comp_num;                                              /* 1..LMC_MAX_COMPOSITE */
+  int32_t comp_usher[LMC_MAX_COMPOSITE];                         /* LMC_USHER_FLIP or LMC_USHER_SWAP */
+  double comp_cum[LMC_MAX_COMPOSITE];                            /* cumulative pick probabilities */
+  double comp_sl_cum[LMC_MAX_COMPOSITE][LMC_MAX_SUBLATTICES];    /* cumulative sublattice probabilities */
   LmcWangLandau wl;           /* used when kernel == LMC_KERNEL_WANGLANDAU */
 } LmcRunConfig;
 
@@ -191,6 +214,10 @@ int lmc_full_features(const LmcModel* model, const int8_t* occ_dev, int num_walk
 
 /* field_dev [W][N] <- Ewald potential cache of every walker's occupancy (see LmcRunConfig.ewald_field_dev) */
 int lmc_ewald_field(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* field_dev, void* stream);
+
+/* bias_dev [W], sum_dev [W] <- bias value and table sum of every walker's occupancy (MCBias.compute_bias) */
+int lmc_bias_init(const int8_t* occ_dev, int num_walkers, int num_sites, int bias_mode, int bias_width,
+                  double bias_penalty, const double* bias_table_dev, double* bias_dev, double* sum_dev, void* stream);
 
 /* out_dev [W][F] <- feature change of walker w for its k flips (sites/codes [W][k] int32, applied
  * sequentially, chemical work against the pre-step occupancy) */

@@ -562,6 +562,29 @@ class Swap(_Usher):
         return []
 
 
+class Composite(_Usher):
+    """mcusher.py:307-394: one of the sub-ushers, picked by weight with random word 4 of the step (the
+    reference draws ``rng.choice(mcushers, p=p)``), proposes with its own sublattices / probabilities."""
+
+    def __init__(self, sublattices, mcushers, mcusher_weights=None):
+        super().__init__(sublattices)
+        self.mcushers = list(mcushers)
+        weights = [1] * len(self.mcushers) if mcusher_weights is None else list(mcusher_weights)
+        total = sum(weights)                                           # mcusher.py:382-390
+        self._p = [w / total for w in weights]
+        self._pcum = np.cumsum(self._p)
+        self._pcum[-1] = 1.0
+
+    def propose_step(self, occupancy, rnd: StepRandom, word0=0):
+        u = u01(rnd.word(4))
+        pick = len(self.mcushers) - 1
+        for i, c in enumerate(self._pcum):
+            if c > u:
+                pick = i
+                break
+        return self.mcushers[pick].propose_step(occupancy, rnd, word0)
+
+
 def flip_weights_mask(flip_vectors, n, max_n):
     """utils/math.py:832-867."""
     fv = np.array(flip_vectors, dtype=int)
@@ -703,6 +726,78 @@ class TableFlip(_Usher):
 # ======================================================================================
 # L4: kernels (smol/moca/kernel/base.py, metropolis.py, random.py, wanglandau.py)
 # ======================================================================================
+# ------------------------------------------------------------------------------------------------
+# bias terms (smol/moca/kernel/bias.py)
+# ------------------------------------------------------------------------------------------------
+def _oxi_state(label) -> float:
+    """get_oxi_state (smol/moca/composition/space.py) for species labels such as 'Mn3+', 'O2-', 'A'."""
+    import re
+    m = re.search(r"(\d*\.?\d*)([+-])$", str(label))
+    if not m:
+        return 0.0
+    mag = float(m.group(1)) if m.group(1) else 1.0
+    return mag if m.group(2) == "+" else -mag
+
+
+class _Bias:
+    def __init__(self, sublattices):
+        self.sublattices = list(sublattices)
+        self.active_sublattices = [s for s in self.sublattices if s.is_active]
+
+    def _table(self, fill):
+        num_cols = max(int(max(sl.encoding)) for sl in self.sublattices) + 1     # bias.py:226-229
+        num_rows = sum(len(sl.sites) for sl in self.sublattices)
+        return np.full((num_rows, num_cols), fill, dtype=np.float64)
+
+    def compute_bias_change(self, occupancy, step):
+        """MCBias.compute_bias_change, bias.py:79-93."""
+        occu_next = np.array(occupancy).copy()
+        for site, code in step:
+            occu_next[site] = code
+        return self.compute_bias(occu_next) - self.compute_bias(occupancy)
+
+
+class FugacityBias(_Bias):
+    """bias.py:96-233."""
+
+    def __init__(self, sublattices, fugacity_fractions):
+        super().__init__(sublattices)
+        table = self._table(1.0)
+        for fus, sl in zip(fugacity_fractions, self.active_sublattices):           # bias.py:230-233
+            ordered = np.array([fus[sp] for sp in sl.species], dtype=np.float64)
+            table[np.asarray(sl.sites)[:, None], np.asarray(sl.encoding)] = ordered[None, :]
+        self._fu_table = table
+
+    def compute_bias(self, occupancy):
+        """bias.py:180-191."""
+        return sum(math.log(self._fu_table[site, sp]) for site, sp in enumerate(occupancy))
+
+    def compute_bias_change(self, occupancy, step):
+        """bias.py:193-214: only the last flip of a site counts."""
+        steps = {site: code for site, code in step}
+        return sum(math.log(self._fu_table[site, code] / self._fu_table[site, occupancy[site]])
+                   for site, code in steps.items())
+
+
+class SquareChargeBias(_Bias):
+    """bias.py:236-287."""
+
+    def __init__(self, sublattices, penalty=0.5):
+        super().__init__(sublattices)
+        self.penalty = penalty
+        table = self._table(0.0)
+        for sl in self.sublattices:                                                # bias.py:267-270
+            cs = np.array([_oxi_state(sp) for sp in sl.species], dtype=np.float64)
+            table[np.asarray(sl.sites)[:, None], np.asarray(sl.encoding)] = cs[None, :]
+        self._c_table = table
+
+    def compute_bias(self, occupancy):
+        """bias.py:276-287."""
+        occupancy = np.asarray(occupancy)
+        c = np.sum(self._c_table[np.arange(len(occupancy), dtype=int), occupancy])
+        return -self.penalty * c ** 2
+
+
 def _dot_seq(a, b) -> float:
     """Sequential dot product (the engine's order; np.dot's BLAS order is unspecified)."""
     p = 0.0
@@ -714,9 +809,10 @@ def _dot_seq(a, b) -> float:
 class Metropolis:
     """kernel/metropolis.py:31-60 + kernel/base.py:145-166, 291-343, 368-436."""
 
-    def __init__(self, ensemble, usher, temperature, seed=0, walker=0, kB_=kB):
+    def __init__(self, ensemble, usher, temperature, seed=0, walker=0, kB_=kB, bias=None):
         self.ensemble = ensemble
         self.usher = usher
+        self.bias = bias
         self.natural_params = ensemble.natural_parameters
         self.seed, self.walker = int(seed), int(walker)
         self.kB = kB_
@@ -729,10 +825,13 @@ class Metropolis:
 
     def compute_initial_trace(self, occupancy):
         feats = np.array(self.ensemble.compute_feature_vector(occupancy), dtype=np.float64)
-        return SimpleNamespace(occupancy=np.array(occupancy), features=feats,
-                               enthalpy=np.array([_dot_seq(self.natural_params, feats)]),
-                               accepted=np.array([True]),
-                               temperature=np.array([self.temperature], dtype=np.float64))
+        tr = SimpleNamespace(occupancy=np.array(occupancy), features=feats,
+                             enthalpy=np.array([_dot_seq(self.natural_params, feats)]),
+                             accepted=np.array([True]),
+                             temperature=np.array([self.temperature], dtype=np.float64))
+        if self.bias is not None:                                    # base.py:362-363
+            tr.bias = np.array([self.bias.compute_bias(occupancy)], dtype=np.float64)
+        return tr
 
     def set_aux_state(self, occupancy):
         return
@@ -747,13 +846,17 @@ class Metropolis:
         dH = _dot_seq(self.natural_params, dfeat)
         log_factor = self.usher.compute_log_priori_factor(occupancy, step)
         exponent = -self.beta * dH + log_factor                      # metropolis.py:41
+        dbias = 0.0
+        if self.bias is not None:                                     # base.py:307-311, metropolis.py:43-44
+            dbias = float(self.bias.compute_bias_change(occupancy, step))
+            exponent += dbias
         # metropolis.py:46-48 (the uniform of this step is word 3 of block 0, drawn or not)
         accepted = True if exponent >= 0 else exponent > math.log(u01(rnd.word(3)))
         if accepted:
             for site, sp in step:                                     # base.py:339-340
                 occupancy[site] = sp
         return SimpleNamespace(accepted=accepted, dfeatures=dfeat, denthalpy=dH, step=step,
-                               exponent=exponent)
+                               exponent=exponent, dbias=dbias)
 
 
 class UniformlyRandom(Metropolis):
@@ -873,6 +976,10 @@ def run_sampler(kernels, initial_occupancies, nsteps, thin_by=1):
                features=np.zeros((S, W, feats.shape[1])), enthalpy=np.zeros((S, W, 1)),
                accepted=np.zeros((S, W, 1), dtype=bool),
                n_accepted=np.zeros((S, W), dtype=np.int64))
+    has_bias = all(hasattr(t, "bias") for t in traces)
+    bias = np.stack([t.bias for t in traces]) if has_bias else None
+    if has_bias:
+        out["bias"] = np.zeros((S, W, 1))
     acc = np.ones(W, dtype=bool)
     for s in range(S):
         nacc = np.zeros(W, dtype=np.int64)
@@ -884,9 +991,13 @@ def run_sampler(kernels, initial_occupancies, nsteps, thin_by=1):
                     feats[i] += st.dfeatures
                     enth[i] += st.denthalpy
                     nacc[i] += 1
+                    if has_bias:
+                        bias[i] += st.dbias
         out["occupancy"][s] = occus
         out["features"][s] = feats
         out["enthalpy"][s] = enth
         out["accepted"][s, :, 0] = acc
         out["n_accepted"][s] = nacc
+        if has_bias:
+            out["bias"][s] = bias
     return out

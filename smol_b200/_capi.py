@@ -7,15 +7,17 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 5
+LMC_ABI_VERSION = 7
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
 LMC_MAX_FLIPS = 4
 LMC_MAX_DIMS = 16
 LMC_MAX_TABLE_FLIPS = 8
-LMC_USHER_FLIP, LMC_USHER_SWAP, LMC_USHER_TABLEFLIP = 0, 1, 2
+LMC_MAX_COMPOSITE = 4
+LMC_USHER_FLIP, LMC_USHER_SWAP, LMC_USHER_TABLEFLIP, LMC_USHER_COMPOSITE = 0, 1, 2, 3
 LMC_KERNEL_METROPOLIS, LMC_KERNEL_WANGLANDAU = 0, 1
+LMC_BIAS_NONE, LMC_BIAS_TABLE_SUM, LMC_BIAS_SQUARE_SUM = 0, 1, 2
 
 _P = C.c_void_p
 
@@ -93,6 +95,11 @@ class LmcRunConfig(C.Structure):
         ("occ_dev", _P), ("features_dev", _P), ("enthalpy_dev", _P),
         ("trace_occ_dev", _P), ("trace_features_dev", _P), ("trace_enthalpy_dev", _P),
         ("trace_accepted_dev", _P), ("trace_naccepted_dev", _P), ("ewald_field_dev", _P),
+        ("bias_mode", C.c_int32), ("bias_width", C.c_int32), ("bias_penalty", C.c_double),
+        ("bias_table_dev", _P), ("bias_dev", _P), ("bias_sum_dev", _P), ("trace_bias_dev", _P),
+        ("comp_num", C.c_int32), ("comp_usher", C.c_int32 * LMC_MAX_COMPOSITE),
+        ("comp_cum", C.c_double * LMC_MAX_COMPOSITE),
+        ("comp_sl_cum", (C.c_double * LMC_MAX_SUBLATTICES) * LMC_MAX_COMPOSITE),
         ("wl", LmcWangLandau),
     ]
 
@@ -101,7 +108,7 @@ EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
     "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host", "lmc_model_info",
-    "lmc_ewald_field",
+    "lmc_ewald_field", "lmc_bias_init",
 )
 
 _LIB = None
@@ -136,6 +143,7 @@ def load():
     lib.lmc_run.argtypes = [_P, C.POINTER(LmcRunConfig), _P]
     lib.lmc_model_info.argtypes = [_P, C.POINTER(C.c_int32), C.c_int]
     lib.lmc_ewald_field.argtypes = [_P, _P, C.c_int, _P, _P]
+    lib.lmc_bias_init.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]
     lib.lmc_launch_count.restype = C.c_int64
     lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:

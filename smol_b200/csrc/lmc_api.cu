@@ -649,6 +649,17 @@ extern "C" int lmc_ewald_field(const LmcModel* mdl, const int8_t* occ, int W, do
   return 0;
 }
 
+extern "C" int lmc_bias_init(const int8_t* occ, int W, int N, int mode, int bw, double pen, const double* tab, double* bias,
+                             double* sum, void* stream) {
+  if (!occ || !tab || !bias || !sum) return fail("null argument");
+  if (mode != LMC_BIAS_TABLE_SUM && mode != LMC_BIAS_SQUARE_SUM) return fail("unknown bias mode");
+  if (W <= 0) return 0;
+  lmc_bias_init_kernel<<<(W + 3) / 4, 128, 0, (cudaStream_t)stream>>>(occ, W, N, lmc_row_stride(N), mode, bw, pen, tab, bias, sum);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int lmc_cast_i32_to_i8(const int32_t* src, int8_t* dst, int W, int N, void* stream) {
   const int Npad = lmc_row_stride(N);
   const long long n = (long long)W * Npad;
@@ -712,6 +723,14 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (c->num_walkers <= 0 || c->num_samples <= 0) return 0;
   if (c->thin_by <= 0) return fail("thin_by must be positive");
   if (c->usher == LMC_USHER_TABLEFLIP && m.tfNF == 0) return fail("model has no flip table");
+  if (c->usher == LMC_USHER_COMPOSITE) {
+    if (c->comp_num < 1 || c->comp_num > LMC_MAX_COMPOSITE) return fail("a composite usher takes 1..4 sub-ushers");
+    for (int i = 0; i < c->comp_num; ++i)
+      if (c->comp_usher[i] != LMC_USHER_FLIP && c->comp_usher[i] != LMC_USHER_SWAP)
+        return fail("composite sub-ushers must be Flip or Swap");
+    if (c->kernel == LMC_KERNEL_WANGLANDAU) return fail("the composite usher is built for the Metropolis kernel only");
+  }
+  if (c->usher < 0 || c->usher > LMC_USHER_COMPOSITE) return fail("unknown usher");
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins <= 1) return fail("Wang-Landau needs more than one bin");
   const bool ewald = m.E > 0;
   const bool field = ewald && c->ewald_field_dev != nullptr;   // Ewald through the potential cache
@@ -731,10 +750,15 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   }
   int spec_mode = c->spec_mode;
   if (const char* e = getenv("LMC_SPEC")) { if (spec_mode == 0) spec_mode = atoi(e) ? 2 : 1; }
-  const bool spec_ok = m.spOK && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
+  if (c->bias_mode != LMC_BIAS_NONE) {
+    if (c->kernel != LMC_KERNEL_METROPOLIS) return fail("bias terms are defined for the Metropolis kernel only (wanglandau.py:24)");
+    if (c->bias_mode != LMC_BIAS_TABLE_SUM && c->bias_mode != LMC_BIAS_SQUARE_SUM) return fail("unknown bias mode");
+    if (!c->bias_table_dev || !c->bias_dev || !c->bias_sum_dev || c->bias_width <= 0) return fail("bias pointers must not be null");
+  }
+  const bool spec_ok = m.spOK && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
                        (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
   if (spec_mode == 2 && !spec_ok)
-    return fail("the speculative kernel supports Metropolis flip/swap steps (an Ewald term through ewald_field_dev only)");
+    return fail("the speculative kernel supports unbiased Metropolis flip/swap steps (an Ewald term through ewald_field_dev only)");
   // auto: only while the staged tables leave room for a full complement of resident walkers per SM
   const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35 && m.blob_bytes <= 40 * 1024));
   if (use_spec) G = 32;
@@ -753,10 +777,11 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     else G = 8;
   }
   if (c->usher == LMC_USHER_TABLEFLIP) G = (G >= 16) ? 32 : 8;
+  if (c->usher == LMC_USHER_COMPOSITE) G = 32;
   if (G != 4 && G != 8 && G != 16 && G != 32) return fail("group_size must be 4, 8, 16 or 32");
   int threads = c->block_threads;
   if (const char* e = getenv("LMC_BLOCK_THREADS")) { if (threads == 0) threads = atoi(e); }
-  const bool relaxed = !use_spec && (ewald || c->kernel == LMC_KERNEL_WANGLANDAU || c->usher == LMC_USHER_TABLEFLIP);
+  const bool relaxed = !use_spec && (ewald || c->kernel == LMC_KERNEL_WANGLANDAU || c->usher >= LMC_USHER_TABLEFLIP);
   const int max_threads = relaxed ? 256 : 128;
   const bool auto_threads = threads == 0;
   if (threads == 0) threads = 128;
@@ -772,6 +797,14 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.tr_occ = c->trace_occ_dev; a.tr_feat = c->trace_features_dev; a.tr_enth = c->trace_enthalpy_dev;
   a.tr_acc = c->trace_accepted_dev; a.tr_nacc = c->trace_naccepted_dev;
   a.wl = c->wl;
+  a.bias_mode = c->bias_mode; a.bias_w = c->bias_width; a.bias_pen = c->bias_penalty;
+  a.bias_tab = c->bias_table_dev; a.bias = c->bias_dev; a.bias_sum = c->bias_sum_dev; a.tr_bias = c->trace_bias_dev;
+  a.comp_num = c->usher == LMC_USHER_COMPOSITE ? c->comp_num : 0;
+  for (int i = 0; i < LMC_MAX_COMPOSITE; ++i) {
+    a.comp_usher[i] = c->comp_usher[i];
+    a.comp_cum[i] = c->comp_cum[i];
+    for (int k = 0; k < LMC_MAX_SUBLATTICES; ++k) a.comp_sl_cum[i][k] = c->comp_sl_cum[i][k];
+  }
   a.stats = mm->stats_dev;
   if (!a.seeds || !a.occ || !a.features || !a.enthalpy) return fail("state pointers must not be null");
   if (c->kernel != LMC_KERNEL_WANGLANDAU && !a.beta) return fail("beta_dev must not be null");
@@ -794,7 +827,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_eidx = a.off_ring + G * 16;                                   // per-lane precomputed proposals
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
-  a.walker_smem = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
+  a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
+  a.walker_smem = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 : 0);              // running bias value and table sum
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
   if (auto_threads && relaxed) {
@@ -832,6 +866,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
   int rc = -2;
   const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
+  const int ewmode = !ewald ? 0 : (field ? 2 : 1);   // Ewald path of the classic kernels
   spec_wide = spec_wide && threads == 448;
   if (use_spec && (field || spec_wide)) rc = launch_spec_x(m, a, m.kone != 0, c->usher, field, spec_wide, lc);
   else if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, lc);

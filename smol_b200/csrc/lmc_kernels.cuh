@@ -553,11 +553,12 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // A template parameter, not a run-time switch: the table-flip variants are instruction-fetch bound and
 // carry one Ewald path each.
 template <int G, bool KONE, int EWMODE, int USHER, bool WLMODE>
-__global__ void __launch_bounds__((EWMODE || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 256 : 128,
-                                  (EWMODE || WLMODE || USHER == LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7))
+__global__ void __launch_bounds__((EWMODE || WLMODE || USHER >= LMC_USHER_TABLEFLIP) ? 256 : 128,
+                                  (EWMODE || WLMODE || USHER >= LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7))
 lmc_run_kernel(const DevModel m, const RunArgs a) {
   constexpr bool EWALD = EWMODE != 0, EWGATHER = EWMODE == 1, EWFIELD = EWMODE == 2;
-  constexpr int MF = USHER == LMC_USHER_FLIP ? 1 : (USHER == LMC_USHER_SWAP ? 2 : LMC_MAX_FLIPS);
+  constexpr bool COMP = USHER == LMC_USHER_COMPOSITE;   // flip / swap sub-ushers picked per step
+  constexpr int MF = USHER == LMC_USHER_FLIP ? 1 : ((USHER == LMC_USHER_SWAP || COMP) ? 2 : LMC_MAX_FLIPS);
   constexpr int I1 = MF > 1 ? 1 : 0;   // index of the second flip (dead code when MF == 1)
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -649,6 +650,14 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? __ldcg(wlS + (int)cur_fb) : 0.0;
   }
 
+  // bias term of the exponent (bias.py; Metropolis only): running value and table sum, all lanes alike
+  // (kept in the walker's shared-memory slab, not in registers: the swap / flip variants are register capped)
+  double* bstate = reinterpret_cast<double*>(priv + a.off_bias);
+  if (!WLMODE && a.bias_mode) {
+    if (g == 0) { bstate[0] = a.bias[w]; bstate[1] = a.bias_sum[w]; }
+    group_sync<G>(gmask);
+  }
+
   unsigned long long step = a.step0;
   // State-independent part of the next G steps, one step per lane (counter-based RNG): random
   // words, sublattice, first site and the float log of the acceptance uniform.  Every step then
@@ -672,7 +681,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       U4 r;
       float lf;
       int pre_sl = 0, pre_j = 0, pre_site = 0;
-      if (USHER == LMC_USHER_TABLEFLIP) {
+      if (USHER == LMC_USHER_TABLEFLIP || COMP) {
         r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1);
         lf = log_u_float(r.w);
       } else {
@@ -752,7 +761,22 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           }
         }
       }
-      if (USHER == LMC_USHER_FLIP) {
+      if (COMP) {
+        // Composite.propose_step, mcusher.py:392-394: word 4 of the step picks the sub-usher, which then draws
+        // the sublattice by its own probabilities and the site (words 0, 1)
+        r1blk = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 1u, wid, k0, k1);
+        const double uc = u01(r1blk.x);
+        int ci = 0;
+        while (ci < a.comp_num - 1 && !(a.comp_cum[ci] > uc)) ++ci;
+        usher = a.comp_usher[ci];
+        const double us = u01(r.x);
+        int s = 0;
+        while (s < m.nSl - 1 && !(a.comp_sl_cum[ci][s] > us)) ++s;
+        pre_sl = s;
+        pre_j = (int)mulhi32(r.y, (uint32_t)(m.sl_off[s + 1] - m.sl_off[s]));
+        pre_site = site_of_pos(m, s, pre_j);
+      }
+      if (USHER == LMC_USHER_FLIP || (COMP && usher == LMC_USHER_FLIP)) {
         // Flip.propose_step, mcusher.py:154-170
         const int sl = pre_sl, j = pre_j, site = pre_site;
         const int cur = occ[site];
@@ -945,9 +969,24 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
 
       // ------------------------------ accept --------------------------------------------
       double new_fb = cur_fb, s_new = s_cur;
+      double dbias = 0.0, dbc = 0.0;
       if (!wl_mode) {
         // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
-        const double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
+        double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
+        if (a.bias_mode) {
+          // MCBias.compute_bias_change (bias.py:79-95, 193-214): table differences of the changed sites;
+          // SquareChargeBias: bias(after) - bias(before) with bias = -penalty * charge^2 (bias.py:276-287)
+#pragma unroll
+          for (int f = 0; f < MF; ++f)
+            if (f < st.n)
+              dbc += __ldg(a.bias_tab + st.site[f] * a.bias_w + st.newc[f]) - __ldg(a.bias_tab + st.site[f] * a.bias_w + st.oldc[f]);
+          if (a.bias_mode == LMC_BIAS_TABLE_SUM) dbias = dbc;
+          else {
+            const double c0 = bstate[1], c1 = c0 + dbc;
+            dbias = __dsub_rn(-__dmul_rn(a.bias_pen, __dmul_rn(c1, c1)), -__dmul_rn(a.bias_pen, __dmul_rn(c0, c0)));
+          }
+          exponent = __dadd_rn(exponent, dbias);   // metropolis.py:43-44
+        }
         {
           const int af = accept_fast(exponent, lf);
           accepted = af >= 0 ? (af != 0)
@@ -1019,6 +1058,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           }
         }
         enth += dH;
+        if (!WLMODE && a.bias_mode && g == 0) { bstate[0] += dbias; bstate[1] += dbc; }   // read again after the step's final sync
         if (wl_mode) { cur_fb = new_fb; s_cur = s_new; }
         ++nacc;
       } else if (st.n > 0) {
@@ -1105,6 +1145,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       if (a.tr_enth) a.tr_enth[sw] = enth;
       if (a.tr_acc) a.tr_acc[sw] = accepted ? 1 : 0;
       if (a.tr_nacc) a.tr_nacc[sw] = nacc;
+      if (!WLMODE && a.bias_mode && a.tr_bias) a.tr_bias[sw] = bstate[0];
     }
     group_sync<G>(gmask);
   }
@@ -1114,6 +1155,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   for (int f = g; f < m.F; f += G) a.features[(size_t)w * m.F + f] = feat[f];
   if (g == 0) {
     a.enthalpy[w] = enth;
+    if (!WLMODE && a.bias_mode) { a.bias[w] = bstate[0]; a.bias_sum[w] = bstate[1]; }
     if (wl_mode) {
       a.wl.mod_factor_dev[w] = wl_m;
       a.wl.steps_counter_dev[w] = wl_cnt;
@@ -1283,6 +1325,21 @@ __global__ void lmc_ewald_field_kernel(const DevModel m, const int8_t* __restric
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && w0 + ww < W) field[(size_t)(w0 + ww) * m.N + s] = v;
     }
+  }
+}
+
+// MCBias.compute_bias for every walker (bias.py:180-191, 276-287): one warp per walker
+__global__ void lmc_bias_init_kernel(const int8_t* __restrict__ occ_g, int W, int N, int Npad, int mode, int bw, double pen,
+                                     const double* __restrict__ tab, double* __restrict__ bias, double* __restrict__ sum) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= W) return;
+  double c = 0.0;
+  for (int k = lane; k < N; k += 32) c += tab[k * bw + occ_g[(size_t)w * Npad + k]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) {
+    sum[w] = c;
+    bias[w] = mode == LMC_BIAS_SQUARE_SUM ? -(pen * (c * c)) : c;
   }
 }
 

@@ -92,10 +92,19 @@ struct RunArgs {
   uint8_t* tr_acc;
   int* tr_nacc;
   double* ew_field;   // [W][N] Ewald potential cache (nullptr: gather the matrix rows), see lmc.h
+  int bias_mode, bias_w;       // LMC_BIAS_*, columns of bias_tab
+  double bias_pen;
+  const double* bias_tab;      // [N][bias_w]
+  double* bias;                // [W] running bias value
+  double* bias_sum;            // [W] running table sum
+  double* tr_bias;             // [S][W]
+  int comp_num, comp_usher[LMC_MAX_COMPOSITE];                   // composite usher, see lmc.h
+  double comp_cum[LMC_MAX_COMPOSITE];
+  double comp_sl_cum[LMC_MAX_COMPOSITE][LMC_MAX_SUBLATTICES];
   LmcWangLandau wl;
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
-  int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx, off_lists;  // offsets inside a walker's shared-memory slab
+  int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx, off_lists, off_bias;  // offsets inside a walker's shared-memory slab
   unsigned long long* stats;  // [2] accepted / attempted step totals (device counters; kernel selection feedback)
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another

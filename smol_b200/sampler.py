@@ -79,7 +79,8 @@ class _PinnedPool:
 _PINNED = _PinnedPool()
 
 _USHERS = {"flip": capi.LMC_USHER_FLIP, "swap": capi.LMC_USHER_SWAP,
-           "tableflip": capi.LMC_USHER_TABLEFLIP, "table_flip": capi.LMC_USHER_TABLEFLIP}
+           "tableflip": capi.LMC_USHER_TABLEFLIP, "table_flip": capi.LMC_USHER_TABLEFLIP,
+           "composite": capi.LMC_USHER_COMPOSITE}
 _KERNELS = {"metropolis": capi.LMC_KERNEL_METROPOLIS, "uniformlyrandom": capi.LMC_KERNEL_METROPOLIS,
             "wanglandau": capi.LMC_KERNEL_WANGLANDAU, "wang-landau": capi.LMC_KERNEL_WANGLANDAU}
 
@@ -150,7 +151,7 @@ class Sampler:
     def __init__(self, ensemble, kernel_type="Metropolis", step_type="swap", nwalkers=1, seeds=None,
                  temperature=None, wl_params=None, usher_kwargs=None, walker_id_base=0,
                  group_size=0, block_threads=0, record_occupancy=True, device=None, kB_=kB,
-                 spec_mode=0, ewald_field="auto"):
+                 spec_mode=0, ewald_field="auto", bias_type=None, bias_kwargs=None):
         from .engine import LmcEngine
         self.ensemble = ensemble
         self.kernel_type = kernel_type
@@ -165,9 +166,21 @@ class Sampler:
         ukey = "tableflip" if ukey == "tableflip" else ukey
         if ukey not in _USHERS:
             raise ValueError(f"{step_type} is not a supported MCUsher (available: flip, swap, "
-                             f"table_flip)")
+                             f"table_flip, composite)")
         self._usher = _USHERS[ukey]
         usher_kwargs = dict(usher_kwargs or {})
+        self._composite = None
+        if self._usher == capi.LMC_USHER_COMPOSITE:
+            # Composite(sublattices, mcushers, mcusher_weights), mcusher.py:314-350
+            from .usher import Composite
+            if self._kernel != capi.LMC_KERNEL_METROPOLIS:
+                raise NotImplementedError("the composite usher is built for the Metropolis kernel only")
+            comp = Composite(ensemble.sublattices, usher_kwargs.pop("mcushers", None),
+                             usher_kwargs.pop("mcusher_weights", None))
+            if not comp.mcushers:
+                raise ValueError("a composite usher needs at least one mcusher")
+            self._composite = comp.device_tables(ensemble.sublattices)
+            self.mcusher = comp
         self.nwalkers = int(nwalkers)
         if seeds is None:
             ss = np.random.SeedSequence()
@@ -213,6 +226,17 @@ class Sampler:
         self._ew_field = None
         self._acc_est = None
         self.record_occupancy = record_occupancy
+        # bias term of the Metropolis exponent (kernel/base.py:229-235, metropolis.py:43-44)
+        self.bias = None
+        if bias_type is not None:
+            if self._kernel != capi.LMC_KERNEL_METROPOLIS:
+                raise ValueError(f"{bias_type} is not a valid MCBias for this kernel.")   # wanglandau.py:24
+            from .bias import MCBias, mcbias_factory
+            self.bias = bias_type if isinstance(bias_type, MCBias) else \
+                mcbias_factory(bias_type, ensemble.sublattices, **(bias_kwargs or {}))
+            if self.bias.table.shape[0] != ensemble.num_sites:
+                raise ValueError("the bias table does not cover all sites of the ensemble")
+        self._bias_dev = None
         self.mckernels = [_KernelView(self, i) for i in range(self.nwalkers)]
         self._step_counter = 0
         self._occ_dev = None
@@ -223,6 +247,8 @@ class Sampler:
                   "n_accepted": ((), np.int32)}
         if self._kernel == capi.LMC_KERNEL_METROPOLIS:
             shapes["temperature"] = ((1,), np.float64)
+        if self.bias is not None:
+            shapes["bias"] = ((1,), np.float64)
         self._container = SampleContainer(ensemble, self.nwalkers, shapes,
                                           dict(ensemble.thermo_boundaries))
 
@@ -235,7 +261,7 @@ class Sampler:
         if kernel_type is None:
             kernel_type = "Metropolis"
         engine_kw = {k: kwargs.pop(k) for k in ("walker_id_base", "group_size", "block_threads", "spec_mode",
-                                                "record_occupancy", "device", "ewald_field") if k in kwargs}
+                                                "record_occupancy", "device", "ewald_field", "bias_type", "bias_kwargs") if k in kwargs}
         key = kernel_type.lower().replace("_", "").replace("-", "")
         temperature, wl = None, None
         if key == "wanglandau":
@@ -262,11 +288,13 @@ class Sampler:
         """Cached trace slot ``index``: device buffers + page-locked host staging for ``nmax`` samples."""
         import torch
         cache = self.__dict__.setdefault("_slots", {})
-        key = (index, nmax, W, N, F, self.record_occupancy)
+        key = (index, nmax, W, N, F, self.record_occupancy, self.bias is not None)
         if cache.get(index, {}).get("key") != key:
             shapes = {"features": ((nmax, W, F), torch.float64), "enthalpy": ((nmax, W), torch.float64),
                       "accepted": ((nmax, W), torch.uint8), "n_accepted": ((nmax, W), torch.int32),
                       "occupancy": ((nmax, W, N if self.record_occupancy else 0), torch.int8)}
+            if self.bias is not None:
+                shapes["bias"] = ((nmax, W), torch.float64)
             cache[index] = {"key": key, "shapes": shapes,
                             "dev": {k: torch.empty(sh, dtype=dt, device=dev) for k, (sh, dt) in shapes.items()},
                             "host": None}
@@ -369,6 +397,17 @@ class Sampler:
             raise RuntimeError("ewald_field=True needs an Ewald term whose matrix factorises as q_i q_j K[site_i, site_j]")
         if use_field:
             self._ew_field = eng.ewald_field(self._occ_dev, out=self._ew_field)
+        if self.bias is not None:
+            # initial bias of the starting occupancies (base.py:362-363), then kept current by the kernel
+            if self._bias_dev is None:
+                self._bias_dev = dict(
+                    table=torch.from_numpy(np.ascontiguousarray(self.bias.table, dtype=np.float64)).to(dev),
+                    value=torch.empty((W,), dtype=torch.float64, device=dev),
+                    tsum=torch.empty((W,), dtype=torch.float64, device=dev))
+            b = self._bias_dev
+            capi.check(eng.lib.lmc_bias_init(self._occ_dev.data_ptr(), W, N, self.bias.mode, self.bias.table.shape[1],
+                                             float(self.bias.penalty), b["table"].data_ptr(), b["value"].data_ptr(),
+                                             b["tsum"].data_ptr(), eng._stream()))
         if self._kernel == capi.LMC_KERNEL_WANGLANDAU and self._wl_state is None:
             self._init_wl()
         if getattr(self, "_seeds_dev", None) is None:
@@ -407,6 +446,8 @@ class Sampler:
                 traces = {"features": arrs["features"][:n], "enthalpy": arrs["enthalpy"][:n][:, :, None],
                           "accepted": arrs["accepted"][:n].view(np.bool_)[:, :, None],
                           "n_accepted": arrs["n_accepted"][:n]}
+                if self.bias is not None:
+                    traces["bias"] = arrs["bias"][:n][:, :, None]
                 if self.record_occupancy:
                     traces["occupancy"] = arrs["occupancy"][:n]          # int8; int32 on access
                 del arrs
@@ -417,6 +458,8 @@ class Sampler:
                     "accepted": host["accepted"][:n].numpy().astype(bool)[:, :, None],
                     "n_accepted": host["n_accepted"][:n].numpy().copy(),
                 }
+                if self.bias is not None:
+                    traces["bias"] = host["bias"][:n].numpy().copy()[:, :, None]
                 if self.record_occupancy:
                     o = host["occupancy"][:n].numpy()
                     traces["occupancy"] = _fast_copy(o.reshape(n * W, N)).reshape(n, W, N)   # int8; int32 on access
@@ -447,6 +490,20 @@ class Sampler:
             cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
             cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
             cfg.ewald_field_dev = self._ew_field.data_ptr() if use_field else None
+            if self._composite is not None:
+                codes, cum, sl_cum = self._composite
+                cfg.comp_num = len(codes)
+                for i, code in enumerate(codes):
+                    cfg.comp_usher[i] = code
+                    cfg.comp_cum[i] = float(cum[i])
+                    for k in range(capi.LMC_MAX_SUBLATTICES):
+                        cfg.comp_sl_cum[i][k] = float(sl_cum[i, k])
+            if self.bias is not None:
+                b = self._bias_dev
+                cfg.bias_mode, cfg.bias_width = self.bias.mode, self.bias.table.shape[1]
+                cfg.bias_penalty = float(self.bias.penalty)
+                cfg.bias_table_dev, cfg.bias_dev, cfg.bias_sum_dev = b["table"].data_ptr(), b["value"].data_ptr(), b["tsum"].data_ptr()
+                cfg.trace_bias_dev = d["bias"].data_ptr()
             if self._kernel == capi.LMC_KERNEL_WANGLANDAU:
                 p, st = self._wl, self._wl_state
                 wl = cfg.wl

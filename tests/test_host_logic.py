@@ -42,8 +42,10 @@ def test_ctypes_struct_matches_header_field_order():
     fields = re.findall(r"\b([a-z_0-9]+);", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
     assert fields == [f[0] for f in capi.LmcModelDesc._fields_]
     body = hdr[hdr.index("typedef struct LmcRunConfig {"):hdr.index("} LmcRunConfig;")]
-    fields = re.findall(r"\b([a-z_0-9]+);", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    fields = re.findall(r"\b([a-z_0-9]+)(?:\[[A-Za-z_0-9]+\])*;", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
     assert fields == [f[0] for f in capi.LmcRunConfig._fields_]
+    # array members keep their extents
+    assert ctypes.sizeof(capi.LmcRunConfig().comp_sl_cum) == 8 * capi.LMC_MAX_COMPOSITE * capi.LMC_MAX_SUBLATTICES
 
 
 @pytest.mark.parametrize("n", [2, 4])
@@ -137,3 +139,49 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(capi, "lib_path", lambda: str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         capi.load()
+
+
+def test_bias_tables_follow_the_reference_layout():
+    """bias.py:216-233, 259-272: per-site tables indexed [site, code]; oracle restatement of the bias change
+    equals the difference of full bias values"""
+    from smol_b200 import bias as B
+    from oracle import lmc_oracle as O
+    sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * 2
+    import smol_b200 as S
+    proc = S.ClusterExpansionProcessor(sub, scm, np.zeros(sub.num_corr_functions))
+    sls = proc.get_sublattices()
+    assert [B.get_oxi_state(x) for x in ("Li+", "Mn3+", "Ti4+", "O2-", "F-", "A")] == [1, 3, 4, -2, -1, 0]
+    sq = B.SquareChargeBias(sls, penalty=0.5)
+    N = proc.num_sites
+    assert sq.table.shape == (N, 3) and sq.mode == capi.LMC_BIAS_SQUARE_SUM
+    cat = next(s for s in sls if "Li+" in s.species)
+    ani = next(s for s in sls if "F-" in s.species)
+    np.testing.assert_array_equal(sq.table[cat.sites[0]], [1, 3, 4])
+    np.testing.assert_array_equal(sq.table[ani.sites[0]], [-2, -1, 0])
+    fr = [{"Li+": 0.5, "Mn3+": 0.25, "Ti4+": 0.25}, {"O2-": 0.75, "F-": 0.25}]
+    if "Li+" not in sls[0].species:
+        fr = fr[::-1]
+    fu = B.FugacityBias(sls, fugacity_fractions=fr)
+    np.testing.assert_allclose(fu.table[cat.sites[3]], np.log([0.5, 0.25, 0.25]))
+    np.testing.assert_allclose(fu.table[ani.sites[3]], [np.log(0.75), np.log(0.25), 0.0])
+    assert B.FugacityBias(sls).fugacity_fractions[0] is not None          # default: equal fractions
+    with pytest.raises(ValueError):
+        B.SquareChargeBias(sls, penalty=-1.0)
+    with pytest.raises(ValueError):
+        B.FugacityBias(sls, fugacity_fractions=[{"Li+": 1.0}, {"O2-": 0.5, "F-": 0.5}])
+    with pytest.raises(ValueError):
+        B.mcbias_factory("no-such-bias", sls)
+    # oracle: change == difference of totals (the reference's generic compute_bias_change)
+    osl = M.oracle_sublattices(O, sls)
+    rng = np.random.default_rng(0)
+    occ = M.random_occupancies(sub, scm, 1, seed=3)[0]
+    for ob in (O.SquareChargeBias(osl, 0.3), O.FugacityBias(osl, fr)):
+        for _ in range(10):
+            s1, s2 = int(rng.choice(cat.sites)), int(rng.choice(ani.sites))
+            step = [(s1, int((occ[s1] + 1) % 3)), (s2, int((occ[s2] + 1) % 2))]
+            nxt = occ.copy()
+            for site, code in step:
+                nxt[site] = code
+            np.testing.assert_allclose(ob.compute_bias_change(occ, step), ob.compute_bias(nxt) - ob.compute_bias(occ),
+                                       rtol=1e-12, atol=1e-12)
