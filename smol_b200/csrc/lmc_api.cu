@@ -768,7 +768,15 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   // occupancy gathers, which is the pipe that bounds this kernel (measured, profiles/r01_variants.md)
   int spec_sg = 4;
   if (const char* e = getenv("LMC_SPEC_SG")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) spec_sg = v; }
-  const bool spec_lists = use_spec && spec_sg == 1 && c->usher == LMC_USHER_SWAP;
+  // swap partner from sorted position lists instead of the rank select: measured neutral with four lanes per
+  // step (the kernel is bound by the L1 / shared-memory data pipe, not by issue slots; profiles/r01_variants.md),
+  // so only the one-lane variant and LMC_SPEC_LISTS=1 use them
+  bool spec_lists = use_spec && c->usher == LMC_USHER_SWAP && !field && spec_sg == 1;
+  if (const char* e = getenv("LMC_SPEC_LISTS")) spec_lists = use_spec && c->usher == LMC_USHER_SWAP && !field && spec_sg != 2 && (atoi(e) != 0 || spec_sg == 1);
+  {
+    const size_t per_walker = (size_t)m.Npad + 4096 + (size_t)m.list_entries * 2;   // generous bound of the slab
+    if (spec_lists && spec_sg == 4 && 7 * ((((size_t)m.blob_bytes + 15) & ~size_t(15)) + 4 * per_walker + 1024) > 227 * 1024) spec_lists = false;
+  }
   if (G == 0) {
     // measured on B200 (profiles/): a full warp per walker wins while all walkers fit in one wave
     // (W <= 32 per SM); beyond that half warps amortise the per-step scalar work better
@@ -852,9 +860,9 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     // seven blocks of four walkers per SM while they fit; with a larger table blob two blocks of fourteen
     // walkers (448 threads) keep the same 28 walkers resident
     const size_t b4 = blob + 4 * (size_t)(m.Npad + a.walker_smem) + 1024, b14 = blob + 14 * (size_t)(m.Npad + a.walker_smem) + 1024;
-    if (7 * b4 > 227 * 1024 && 2 * b14 <= 227 * 1024 && (int)b14 <= mdl->smem_optin) { spec_wide = true; threads = 448; }
+    if (!spec_lists && 7 * b4 > 227 * 1024 && 2 * b14 <= 227 * 1024 && (int)b14 <= mdl->smem_optin) { spec_wide = true; threads = 448; }
   }
-  if (const char* e = getenv("LMC_SPEC_WIDE")) { if (use_spec) { spec_wide = atoi(e) != 0; threads = spec_wide ? 448 : 128; } }
+  if (const char* e = getenv("LMC_SPEC_WIDE")) { if (use_spec && !spec_lists) { spec_wide = atoi(e) != 0; threads = spec_wide ? 448 : 128; } }
   for (;;) {
     a.wpb = threads / G;
     smem = blob + (size_t)a.wpb * (m.Npad + a.walker_smem);
@@ -869,7 +877,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const int ewmode = !ewald ? 0 : (field ? 2 : 1);   // Ewald path of the classic kernels
   spec_wide = spec_wide && threads == 448;
   if (use_spec && (field || spec_wide)) rc = launch_spec_x(m, a, m.kone != 0, c->usher, field, spec_wide, lc);
-  else if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, lc);
+  else if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, spec_lists, lc);
   else switch (G) {
     case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewmode, c->usher, lc); break;
     case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewmode, c->usher, lc); break;

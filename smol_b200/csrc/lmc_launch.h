@@ -17,7 +17,7 @@ int launch_run_g16(const DevModel& m, const RunArgs& a, bool kone, int ewald, in
 int launch_run_g32(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
 // speculative-batch Metropolis kernel (flip / swap)
 // sg = lanes per speculated step (1, 2 or 4; 1 uses sorted position lists for swaps)
-int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int sg, const LaunchCfg& lc);
+int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int sg, bool lists, const LaunchCfg& lc);
 // Ewald potential cache (ewf) and / or 448-thread blocks (wide), four lanes per step
 int launch_spec_x(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
 // Wang-Landau variants

@@ -6,7 +6,7 @@ namespace lmc {
 
 template <bool KONE, int USHER, int SG, bool EWF, int MAXT, int MINB>
 static int launch_spec_k(const DevModel& m, const RunArgs& a, const LaunchCfg& lc) {
-  auto kern = lmc_spec_kernel<KONE, USHER, SG, (SG == 1 && USHER == LMC_USHER_SWAP), EWF, MAXT, MINB>;
+  auto kern = lmc_spec_kernel<KONE, USHER, SG, false, EWF, MAXT, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<lc.grid, lc.threads, lc.smem, lc.stream>>>(m, a);

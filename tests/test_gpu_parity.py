@@ -429,13 +429,15 @@ def test_bias_rejected_where_the_reference_rejects_it(cuda_device):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["decomposition", "expansion"])
 @pytest.mark.parametrize("n,T,thin", [(2, 1000.0, 20), (4, 300.0, 7), (4, 1000.0, 64), (3, 1e5, 13)])
-@pytest.mark.parametrize("sg", ["4", "2", "1"])
+@pytest.mark.parametrize("sg", ["4", "4L", "2", "1"])
 def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypatch):
     """low / medium / near-infinite temperature (acceptance ~0 .. ~1), sampling intervals that are not
     multiples of the batch, aliased 2x2x2 cell; spec_mode=2 forces the speculative kernel, 1 the classic
-    one: both must reproduce the oracle chain bit for bit.  sg = lanes per speculated step."""
+    one: both must reproduce the oracle chain bit for bit.  sg = lanes per speculated step, L = swap partner
+    from sorted position lists instead of the rank select."""
     import smol_b200 as S
-    monkeypatch.setenv("LMC_SPEC_SG", sg)
+    monkeypatch.setenv("LMC_SPEC_SG", sg[0])
+    monkeypatch.setenv("LMC_SPEC_LISTS", "1" if sg.endswith("L") else "0")
     O = _oracle()
     sub = M.fcc_subspace()
     scm = np.eye(3, dtype=int) * n
