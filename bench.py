@@ -313,8 +313,9 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                      "algorithmic_bytes_per_attempted_step": ALGO_BYTES_PER_STEP,
-                     "note": "sparse integer gather-reduce on an L2/SMEM-resident working set: the "
-                             "kernel is issue/latency bound, DRAM traffic is far below algorithmic bytes"},
+                     "note": "sparse integer gather-reduce on an L2/SMEM-resident working set: DRAM traffic is far "
+                             "below the algorithmic bytes; the kernel is bound by the L1/shared-memory data pipe "
+                             "(l1tex__data_pipe_lsu_wavefronts 86.5 % of peak, profiles/r01c_lmc_spec_cfg2.md)"},
         "cpu_baseline": {"value": cpu_rate, "unit": "steps/s", "cores": cores, "kind": kind,
                          "sample": sample},
         "cpu_port": {"value": port_rate, "unit": "steps/s", "cores": cores, "kind": "port",

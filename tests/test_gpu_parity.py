@@ -198,6 +198,37 @@ def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
     assert smp.samples.num_samples == 40
 
 
+def test_ewald_potential_cache_stays_consistent(cuda_device):
+    """after thousands of accepted flips the incrementally updated cache equals the one rebuilt from the
+    occupancies, and the running Ewald feature equals the full evaluation (drift check in the spirit of
+    Processor.compute_average_drift, processor/base.py:208-243)"""
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    sub = M.rocksalt_subspace()
+    scm = np.eye(3, dtype=int) * 4
+    rng = np.random.default_rng(23)
+    it = L.cluster_interaction_tensors(sub, rng.normal(0, 0.02, sub.num_corr_functions))
+    ewm, ewi = L.ewald_matrix(sub, scm)
+    comp = S.CompositeProcessor(sub, scm)
+    comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
+    comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.05, ewald_matrix=ewm, ewald_inds=ewi))
+    ens = S.Ensemble(comp, chemical_potentials={"Li+": 0.0, "Mn3+": 0.3, "Ti4+": -0.2})
+    W = 64
+    occ0 = M.random_occupancies(sub, scm, W, seed=3)
+    for spec in (1, 2):
+        smp = S.Sampler.from_ensemble(ens, 8000.0, step_type="flip", nwalkers=W, seeds=list(range(W)),
+                                      spec_mode=spec, ewald_field=True)
+        smp.run(20000, occ0, thin_by=2000)
+        assert smp.samples.step_efficiency() > 0.2          # thousands of cache updates per walker
+        eng = smp.engine
+        fresh = eng.ewald_field(smp._occ_dev).cpu().numpy()
+        kept = smp._ew_field.cpu().numpy()
+        np.testing.assert_allclose(kept, fresh, rtol=0, atol=1e-10 * np.abs(fresh).max())
+        feat, enth = eng.full_features(smp._occ_dev)
+        last = smp.samples.get_feature_vectors(flat=False)[-1]
+        np.testing.assert_allclose(last, feat.cpu().numpy(), rtol=1e-10, atol=1e-10 * np.abs(last).max())
+
+
 @pytest.mark.parametrize("mode", ["classic", "spec"])
 def test_canonical_ewald_swap_trajectory(cuda_device, mode):
     """canonical swaps with an Ewald term through the potential cache: flip 2 of a swap sees the cache
