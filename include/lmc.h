@@ -24,6 +24,7 @@
  *                            MCKernel.single_step (smol/moca/kernel/base.py:145-166),
  *                            Flip/Swap/TableFlip.propose_step (smol/moca/kernel/mcusher.py:154-200, 553-711),
  *                            Composite.propose_step over Flip / Swap sub-ushers (mcusher.py:307-394),
+ *                            MultiStep.propose_step over a Flip / Swap sub-usher (mcusher.py:203-304),
  *                            Metropolis / WangLandau accept (kernel/metropolis.py:31-49,
  *                            kernel/wanglandau.py:186-266)
  *   lmc_ewald_field       <- the site sums of delta_ewald_single_flip (smol/utils/cluster/ewald.pyx:43-58),
@@ -49,7 +50,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 7
+#define LMC_ABI_VERSION 8
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -126,7 +127,7 @@ typedef struct LmcModelDesc {
   double tf_swap_weight;
 } LmcModelDesc;
 
-enum { LMC_USHER_FLIP = 0, LMC_USHER_SWAP = 1, LMC_USHER_TABLEFLIP = 2, LMC_USHER_COMPOSITE = 3 };
+enum { LMC_USHER_FLIP = 0, LMC_USHER_SWAP = 1, LMC_USHER_TABLEFLIP = 2, LMC_USHER_COMPOSITE = 3, LMC_USHER_MULTISTEP = 4 };
 enum { LMC_KERNEL_METROPOLIS = 0, LMC_KERNEL_WANGLANDAU = 1 };
 /* bias terms of the Metropolis kernel: value = sum_k table[k][occ[k]] (LMC_BIAS_TABLE_SUM; FugacityBias with
  * table = log fugacity fractions) or -penalty * (sum_k table[k][occ[k]])^2 (LMC_BIAS_SQUARE_SUM; SquareChargeBias
@@ -188,6 +189,14 @@ typedef struct LmcRunConfig {
   int32_t comp_usher[LMC_MAX_COMPOSITE];                         /* LMC_USHER_FLIP or LMC_USHER_SWAP */
   double comp_cum[LMC_MAX_COMPOSITE];                            /* cumulative pick probabilities */
   double comp_sl_cum[LMC_MAX_COMPOSITE][LMC_MAX_SUBLATTICES];    /* cumulative sublattice probabilities */
+  /* LMC_USHER_MULTISTEP (mcusher.py:203-304): a step chains step_length proposals of one sub-usher, each against
+     the occupancy with the earlier ones applied; a proposal touching an already changed site is dropped.  The
+     length is picked with random word 4 of the step, proposal j draws from block 2 + j.  At most LMC_MAX_FLIPS
+     changed sites: lengths <= 4 (Flip) or <= 2 (Swap) */
+  int32_t ms_usher;                                              /* LMC_USHER_FLIP or LMC_USHER_SWAP */
+  int32_t ms_num;                                                /* 1..LMC_MAX_COMPOSITE step lengths */
+  int32_t ms_len[LMC_MAX_COMPOSITE];
+  double ms_cum[LMC_MAX_COMPOSITE];                              /* cumulative probabilities of the lengths */
   LmcWangLandau wl;           /* used when kernel == LMC_KERNEL_WANGLANDAU */
 } LmcRunConfig;
 

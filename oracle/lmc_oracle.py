@@ -585,6 +585,40 @@ class Composite(_Usher):
         return self.mcushers[pick].propose_step(occupancy, rnd, word0)
 
 
+class MultiStep(_Usher):
+    """mcusher.py:203-304.  The length comes from random word 4 of the step (the reference draws
+    ``rng.choice(step_lens, p=step_p)``); proposal j of the chain draws from words 8 + 4 j .. (block 2 + j)."""
+
+    def __init__(self, sublattices, mcusher, step_lengths, step_probabilities=None):
+        super().__init__(sublattices)
+        self._mcusher = mcusher
+        self._step_lens = [step_lengths] if isinstance(step_lengths, int) else list(step_lengths)
+        p = ([1.0 / len(self._step_lens)] * len(self._step_lens) if step_probabilities is None
+             else list(step_probabilities))                              # mcusher.py:244-247
+        self._pcum = np.cumsum(p)
+        self._pcum[-1] = 1.0
+
+    def propose_step(self, occupancy, rnd: StepRandom, word0=0):
+        u = u01(rnd.word(4))
+        pick = len(self._step_lens) - 1
+        for i, c in enumerate(self._pcum):
+            if c > u:
+                pick = i
+                break
+        step_length = self._step_lens[pick]
+        occu = np.array(occupancy).copy()                                # mcusher.py:287
+        steps = [self._mcusher.propose_step(occu, rnd, 8)]
+        for f in steps[-1]:
+            occu[f[0]] = f[1]
+        for j in range(1, step_length):                                  # mcusher.py:293-301
+            step = self._mcusher.propose_step(occu, rnd, 8 + 4 * j)
+            if all(s not in (s for st in steps for s, _ in st) for s, _ in step):
+                steps.append(step)
+                for f in steps[-1]:
+                    occu[f[0]] = f[1]
+        return [flip for step in steps for flip in step]
+
+
 def flip_weights_mask(flip_vectors, n, max_n):
     """utils/math.py:832-867."""
     fv = np.array(flip_vectors, dtype=int)

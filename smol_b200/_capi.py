@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 7
+LMC_ABI_VERSION = 8
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -15,7 +15,7 @@ LMC_MAX_FLIPS = 4
 LMC_MAX_DIMS = 16
 LMC_MAX_TABLE_FLIPS = 8
 LMC_MAX_COMPOSITE = 4
-LMC_USHER_FLIP, LMC_USHER_SWAP, LMC_USHER_TABLEFLIP, LMC_USHER_COMPOSITE = 0, 1, 2, 3
+LMC_USHER_FLIP, LMC_USHER_SWAP, LMC_USHER_TABLEFLIP, LMC_USHER_COMPOSITE, LMC_USHER_MULTISTEP = 0, 1, 2, 3, 4
 LMC_KERNEL_METROPOLIS, LMC_KERNEL_WANGLANDAU = 0, 1
 LMC_BIAS_NONE, LMC_BIAS_TABLE_SUM, LMC_BIAS_SQUARE_SUM = 0, 1, 2
 
@@ -100,6 +100,8 @@ class LmcRunConfig(C.Structure):
         ("comp_num", C.c_int32), ("comp_usher", C.c_int32 * LMC_MAX_COMPOSITE),
         ("comp_cum", C.c_double * LMC_MAX_COMPOSITE),
         ("comp_sl_cum", (C.c_double * LMC_MAX_SUBLATTICES) * LMC_MAX_COMPOSITE),
+        ("ms_usher", C.c_int32), ("ms_num", C.c_int32), ("ms_len", C.c_int32 * LMC_MAX_COMPOSITE),
+        ("ms_cum", C.c_double * LMC_MAX_COMPOSITE),
         ("wl", LmcWangLandau),
     ]
 

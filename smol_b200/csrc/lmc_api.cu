@@ -730,7 +730,15 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
         return fail("composite sub-ushers must be Flip or Swap");
     if (c->kernel == LMC_KERNEL_WANGLANDAU) return fail("the composite usher is built for the Metropolis kernel only");
   }
-  if (c->usher < 0 || c->usher > LMC_USHER_COMPOSITE) return fail("unknown usher");
+  if (c->usher == LMC_USHER_MULTISTEP) {
+    if (c->ms_usher != LMC_USHER_FLIP && c->ms_usher != LMC_USHER_SWAP) return fail("the multi-step sub-usher must be Flip or Swap");
+    if (c->ms_num < 1 || c->ms_num > LMC_MAX_COMPOSITE) return fail("a multi-step usher takes 1..4 step lengths");
+    for (int i = 0; i < c->ms_num; ++i)
+      if (c->ms_len[i] < 1 || c->ms_len[i] * (c->ms_usher == LMC_USHER_SWAP ? 2 : 1) > LMC_MAX_FLIPS)
+        return fail("multi-step lengths must change at most 4 sites per step (<= 4 flips or <= 2 swaps)");
+    if (c->kernel == LMC_KERNEL_WANGLANDAU) return fail("the multi-step usher is built for the Metropolis kernel only");
+  }
+  if (c->usher < 0 || c->usher > LMC_USHER_MULTISTEP) return fail("unknown usher");
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins <= 1) return fail("Wang-Landau needs more than one bin");
   const bool ewald = m.E > 0;
   const bool field = ewald && c->ewald_field_dev != nullptr;   // Ewald through the potential cache
@@ -785,7 +793,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     else G = 8;
   }
   if (c->usher == LMC_USHER_TABLEFLIP) G = (G >= 16) ? 32 : 8;
-  if (c->usher == LMC_USHER_COMPOSITE) G = 32;
+  if (c->usher == LMC_USHER_COMPOSITE || c->usher == LMC_USHER_MULTISTEP) G = 32;
   if (G != 4 && G != 8 && G != 16 && G != 32) return fail("group_size must be 4, 8, 16 or 32");
   int threads = c->block_threads;
   if (const char* e = getenv("LMC_BLOCK_THREADS")) { if (threads == 0) threads = atoi(e); }
@@ -813,6 +821,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     a.comp_cum[i] = c->comp_cum[i];
     for (int k = 0; k < LMC_MAX_SUBLATTICES; ++k) a.comp_sl_cum[i][k] = c->comp_sl_cum[i][k];
   }
+  a.ms_usher = c->ms_usher; a.ms_num = c->usher == LMC_USHER_MULTISTEP ? c->ms_num : 0;
+  for (int i = 0; i < LMC_MAX_COMPOSITE; ++i) { a.ms_len[i] = c->ms_len[i]; a.ms_cum[i] = c->ms_cum[i]; }
   a.stats = mm->stats_dev;
   if (!a.seeds || !a.occ || !a.features || !a.enthalpy) return fail("state pointers must not be null");
   if (c->kernel != LMC_KERNEL_WANGLANDAU && !a.beta) return fail("beta_dev must not be null");
@@ -820,7 +830,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const size_t stash_el = m.kone ? 8 : 4;
   a.off_feat = 0;
   a.off_stash = (int)(((size_t)m.F * 8 + 15) & ~size_t(15));
-  a.max_flips = c->usher == LMC_USHER_FLIP ? 1 : 2;
+  a.max_flips = c->usher == LMC_USHER_FLIP ? 1 : (c->usher == LMC_USHER_MULTISTEP ? LMC_MAX_FLIPS : 2);
   if (c->usher == LMC_USHER_TABLEFLIP)
     for (int i = 0; i < m.tfNF; ++i) {
       int up = 0, dn = 0;

@@ -558,6 +558,7 @@ __global__ void __launch_bounds__((EWMODE || WLMODE || USHER >= LMC_USHER_TABLEF
 lmc_run_kernel(const DevModel m, const RunArgs a) {
   constexpr bool EWALD = EWMODE != 0, EWGATHER = EWMODE == 1, EWFIELD = EWMODE == 2;
   constexpr bool COMP = USHER == LMC_USHER_COMPOSITE;   // flip / swap sub-ushers picked per step
+  constexpr bool MULTI = USHER == LMC_USHER_MULTISTEP;  // chained proposals of one flip / swap sub-usher
   constexpr int MF = USHER == LMC_USHER_FLIP ? 1 : ((USHER == LMC_USHER_SWAP || COMP) ? 2 : LMC_MAX_FLIPS);
   constexpr int I1 = MF > 1 ? 1 : 0;   // index of the second flip (dead code when MF == 1)
   extern __shared__ __align__(16) unsigned char smem[];
@@ -681,7 +682,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       U4 r;
       float lf;
       int pre_sl = 0, pre_j = 0, pre_site = 0;
-      if (USHER == LMC_USHER_TABLEFLIP || COMP) {
+      if (USHER == LMC_USHER_TABLEFLIP || COMP || MULTI) {
         r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1);
         lf = log_u_float(r.w);
       } else {
@@ -732,6 +733,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       int usher = USHER;
       uint32_t q0 = r.x, q1 = r.y, q2 = r.z;   // words of the simple ushers
       U4 r1blk{0, 0, 0, 0};
+      int ms_toggled = 0;   // flips of chained swaps whose plane bits are temporarily toggled
       int tf_idx = -1;
       double tfw[2 * LMC_MAX_TABLE_FLIPS];
       double tfsum = 0.0;
@@ -775,6 +777,75 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         pre_sl = s;
         pre_j = (int)mulhi32(r.y, (uint32_t)(m.sl_off[s + 1] - m.sl_off[s]));
         pre_site = site_of_pos(m, s, pre_j);
+      }
+      if (MULTI) {
+        // MultiStep.propose_step, mcusher.py:284-304.  Proposal j sees proposals < j applied: they only ever
+        // touch other sites (a colliding proposal is dropped), so the occupancy bytes can be read as they are;
+        // the species bit-planes that serve a swap's partner choice are toggled for the chained swaps and
+        // restored before the evaluation.
+        r1blk = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 1u, wid, k0, k1);
+        const double ul = u01(r1blk.x);
+        int li = 0;
+        while (li < a.ms_num - 1 && !(a.ms_cum[li] > ul)) ++li;
+        const int len = a.ms_len[li];
+        for (int j = 0; j < len; ++j) {
+          const U4 rj = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(2 + j), wid, k0, k1);
+          const int sl = choose_sublattice(m, rj.x);
+          const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+          const int pos1 = (int)mulhi32(rj.y, (uint32_t)n_act);
+          const int site1 = site_of_pos(m, sl, pos1);
+          const int s1 = occ[site1];
+          bool clash = false;
+#pragma unroll
+          for (int f = 0; f < MF; ++f) clash = clash || (f < st.n && st.site[f] == site1);
+          if (a.ms_usher == LMC_USHER_FLIP) {
+            const int nc = m.sl_ncodes[sl];
+            int ci = (int)mulhi32(rj.z, (uint32_t)(nc - 1));
+            int cp = nc;
+            for (int c = 0; c < nc; ++c) if (m.sl_codes[sl][c] == s1) { cp = c; break; }
+            if (ci >= cp) ++ci;
+            if (!clash) push_flip(st, site1, s1, m.sl_codes[sl][ci], sl, pos1);
+          } else {
+            const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
+            if (!clash && ndiff > 0) {   // uniform over the group (a clash makes the proposal void whatever it picks)
+              const int k = (int)mulhi32(rj.z, (uint32_t)ndiff);
+              const int pos2 = select_pos<G>(m, planes, sl, s1, k, true, g, gmask);
+              const int site2 = site_of_pos(m, sl, pos2);
+              const int s2 = occ[site2];
+#pragma unroll
+              for (int f = 0; f < MF; ++f) clash = clash || (f < st.n && st.site[f] == site2);
+              if (!clash) {
+                push_flip(st, site1, s1, s2, sl, pos1);
+                push_flip(st, site2, s2, s1, sl, pos2);
+                if (j + 1 < len) {   // later proposals pick partners in the swapped configuration
+                  group_sync<G>(gmask);
+                  if (g == 0) {
+                    const int nw = m.sl_nwords[sl];
+                    uint32_t* pl = planes + m.sl_plane_off[sl];
+                    pl[s1 * nw + (pos1 >> 5)] ^= 1u << (pos1 & 31); pl[s2 * nw + (pos1 >> 5)] ^= 1u << (pos1 & 31);
+                    pl[s2 * nw + (pos2 >> 5)] ^= 1u << (pos2 & 31); pl[s1 * nw + (pos2 >> 5)] ^= 1u << (pos2 & 31);
+                  }
+                  group_sync<G>(gmask);
+                  ms_toggled += 2;
+                }
+              }
+            }
+          }
+        }
+        if (ms_toggled) {   // restore the planes of the current occupancy
+          group_sync<G>(gmask);
+          if (g == 0) {
+#pragma unroll
+            for (int f = 0; f < MF; ++f)
+              if (f < ms_toggled) {
+                const int nw = m.sl_nwords[st.sl[f]];
+                uint32_t* pl = planes + m.sl_plane_off[st.sl[f]] + (st.pos[f] >> 5);
+                pl[st.oldc[f] * nw] ^= 1u << (st.pos[f] & 31);
+                pl[st.newc[f] * nw] ^= 1u << (st.pos[f] & 31);
+              }
+          }
+          group_sync<G>(gmask);
+        }
       }
       if (USHER == LMC_USHER_FLIP || (COMP && usher == LMC_USHER_FLIP)) {
         // Flip.propose_step, mcusher.py:154-170

@@ -101,6 +101,8 @@ struct RunArgs {
   int comp_num, comp_usher[LMC_MAX_COMPOSITE];                   // composite usher, see lmc.h
   double comp_cum[LMC_MAX_COMPOSITE];
   double comp_sl_cum[LMC_MAX_COMPOSITE][LMC_MAX_SUBLATTICES];
+  int ms_usher, ms_num, ms_len[LMC_MAX_COMPOSITE];               // multi-step usher, see lmc.h
+  double ms_cum[LMC_MAX_COMPOSITE];
   LmcWangLandau wl;
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker

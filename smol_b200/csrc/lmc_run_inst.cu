@@ -29,6 +29,7 @@ static int launch_usher(const DevModel& m, const RunArgs& a, int usher, const La
 #endif
 #if LMC_G == 32 && !LMC_WL
     case LMC_USHER_COMPOSITE: return launch_one<KONE, EWALD, LMC_USHER_COMPOSITE>(m, a, lc);
+    case LMC_USHER_MULTISTEP: return launch_one<KONE, EWALD, LMC_USHER_MULTISTEP>(m, a, lc);
 #endif
     default: return -2;
   }

@@ -80,7 +80,7 @@ _PINNED = _PinnedPool()
 
 _USHERS = {"flip": capi.LMC_USHER_FLIP, "swap": capi.LMC_USHER_SWAP,
            "tableflip": capi.LMC_USHER_TABLEFLIP, "table_flip": capi.LMC_USHER_TABLEFLIP,
-           "composite": capi.LMC_USHER_COMPOSITE}
+           "composite": capi.LMC_USHER_COMPOSITE, "multistep": capi.LMC_USHER_MULTISTEP}
 _KERNELS = {"metropolis": capi.LMC_KERNEL_METROPOLIS, "uniformlyrandom": capi.LMC_KERNEL_METROPOLIS,
             "wanglandau": capi.LMC_KERNEL_WANGLANDAU, "wang-landau": capi.LMC_KERNEL_WANGLANDAU}
 
@@ -166,7 +166,7 @@ class Sampler:
         ukey = "tableflip" if ukey == "tableflip" else ukey
         if ukey not in _USHERS:
             raise ValueError(f"{step_type} is not a supported MCUsher (available: flip, swap, "
-                             f"table_flip, composite)")
+                             f"table_flip, composite, multi_step)")
         self._usher = _USHERS[ukey]
         usher_kwargs = dict(usher_kwargs or {})
         self._composite = None
@@ -181,6 +181,20 @@ class Sampler:
                 raise ValueError("a composite usher needs at least one mcusher")
             self._composite = comp.device_tables(ensemble.sublattices)
             self.mcusher = comp
+        self._multistep = None
+        if self._usher == capi.LMC_USHER_MULTISTEP:
+            # MultiStep(sublattices, mcusher, step_lengths, step_probabilities), mcusher.py:206-272
+            from .usher import MultiStep
+            if self._kernel != capi.LMC_KERNEL_METROPOLIS:
+                raise NotImplementedError("the multi-step usher is built for the Metropolis kernel only")
+            if "mcusher" not in usher_kwargs or "step_lengths" not in usher_kwargs:
+                raise TypeError("MultiStep needs mcusher and step_lengths")
+            ms = MultiStep(ensemble.sublattices, usher_kwargs.pop("mcusher"), usher_kwargs.pop("step_lengths"),
+                           usher_kwargs.pop("step_probabilities", None))
+            self._multistep = ms.device_tables()
+            usher_kwargs.setdefault("sublattice_probabilities", ms.sublattice_probabilities
+                                    if len(ms.sublattice_probabilities) == len(ensemble.active_sublattices) else None)
+            self.mcusher = ms
         self.nwalkers = int(nwalkers)
         if seeds is None:
             ss = np.random.SeedSequence()
@@ -490,6 +504,12 @@ class Sampler:
             cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
             cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
             cfg.ewald_field_dev = self._ew_field.data_ptr() if use_field else None
+            if self._multistep is not None:
+                code, lens, cum = self._multistep
+                cfg.ms_usher, cfg.ms_num = code, len(lens)
+                for i, ln in enumerate(lens):
+                    cfg.ms_len[i] = ln
+                    cfg.ms_cum[i] = float(cum[i])
             if self._composite is not None:
                 codes, cum, sl_cum = self._composite
                 cfg.comp_num = len(codes)

@@ -100,12 +100,47 @@ class Composite(MCUsher):
         return [u.code for u in self._mcushers], cum, sl_cum
 
 
-_USHER_CLASSES = {"flip": Flip, "swap": Swap, "composite": Composite}
+class MultiStep(MCUsher):
+    """``mcusher.py:203-304``: a step chains ``step_length`` proposals of one sub-usher; a proposal that touches
+    an already changed site is dropped.  (With ``step_probabilities`` the reference stores them in a misspelt
+    attribute, ``mcusher.py:243``, and then fails in ``propose_step``; here they are used as documented.)"""
+
+    code = capi.LMC_USHER_MULTISTEP
+
+    def __init__(self, sublattices, mcusher, step_lengths, step_probabilities=None, rng=None):
+        super().__init__(sublattices)
+        lens = np.array([step_lengths] if isinstance(step_lengths, (int, np.integer)) else step_lengths, dtype=int)
+        if step_probabilities is not None:
+            if sum(step_probabilities) != 1.0:                                   # mcusher.py:237-238
+                raise ValueError("The step_probabilities do not sum to 1.")
+            if len(step_probabilities) != len(lens):                             # mcusher.py:239-242
+                raise ValueError("The length of step_lengths and step_probabilities does not match.")
+            probs = np.array(step_probabilities, dtype=np.float64)
+        else:
+            probs = np.full(len(lens), 1.0 / len(lens))
+        if isinstance(mcusher, str):
+            mcusher = mcusher_factory(mcusher, self.sublattices)
+        if not isinstance(mcusher, (Flip, Swap)):
+            raise NotImplementedError("the multi-step sub-usher must be Flip or Swap on the GPU path")
+        per = 2 if isinstance(mcusher, Swap) else 1
+        if len(lens) < 1 or len(lens) > capi.LMC_MAX_COMPOSITE or (lens < 1).any() or (lens * per > capi.LMC_MAX_FLIPS).any():
+            raise ValueError("step lengths must change at most 4 sites per step (<= 4 flips or <= 2 swaps), "
+                             "at most 4 different lengths")
+        self._mcusher, self._step_lens, self._step_p = mcusher, lens, probs
+        self.sublattice_probabilities = mcusher.sublattice_probabilities
+
+    def device_tables(self):
+        cum = np.cumsum(self._step_p)
+        cum[-1] = 1.0
+        return self._mcusher.code, [int(x) for x in self._step_lens], cum
+
+
+_USHER_CLASSES = {"flip": Flip, "swap": Swap, "composite": Composite, "multistep": MultiStep}
 
 
 def mcusher_factory(usher_type, sublattices, *args, **kwargs):
     """``mcusher.py`` ``mcusher_factory``."""
     key = str(usher_type).lower().replace("-", "").replace("_", "")
     if key not in _USHER_CLASSES:
-        raise ValueError(f"{usher_type} is not a supported MCUsher here (Flip, Swap, Composite)")
+        raise ValueError(f"{usher_type} is not a supported MCUsher here (Flip, Swap, Composite, MultiStep)")
     return _USHER_CLASSES[key](sublattices, *args, **kwargs)

