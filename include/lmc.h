@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 8
+#define LMC_ABI_VERSION 9
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -58,6 +58,7 @@ extern "C" {
 #define LMC_MAX_DIMS 16       /* species counts tracked by the table-flip usher */
 #define LMC_MAX_TABLE_FLIPS 8
 #define LMC_MAX_COMPOSITE 4   /* sub-ushers of a composite usher */
+#define LMC_MAX_BIAS_ROWS 4   /* hyperplanes of a SquareHyperplaneBias */
 
 typedef struct LmcModel LmcModel; /* opaque */
 
@@ -130,8 +131,9 @@ typedef struct LmcModelDesc {
 enum { LMC_USHER_FLIP = 0, LMC_USHER_SWAP = 1, LMC_USHER_TABLEFLIP = 2, LMC_USHER_COMPOSITE = 3, LMC_USHER_MULTISTEP = 4 };
 enum { LMC_KERNEL_METROPOLIS = 0, LMC_KERNEL_WANGLANDAU = 1 };
 /* bias terms of the Metropolis kernel: value = sum_k table[k][occ[k]] (LMC_BIAS_TABLE_SUM; FugacityBias with
- * table = log fugacity fractions) or -penalty * (sum_k table[k][occ[k]])^2 (LMC_BIAS_SQUARE_SUM; SquareChargeBias
- * with table = oxidation states) */
+ * table = log fugacity fractions) or -penalty * sum_r (sum_k table[k][occ[k]][r] - intercept[r])^2
+ * (LMC_BIAS_SQUARE_SUM; SquareChargeBias: one row of oxidation states, intercept 0; SquareHyperplaneBias: row r =
+ * column A[r][dim(k, code)] of the hyperplane normals, intercept b[r]) */
 enum { LMC_BIAS_NONE = 0, LMC_BIAS_TABLE_SUM = 1, LMC_BIAS_SQUARE_SUM = 2 };
 
 typedef struct LmcWangLandau {
@@ -177,11 +179,12 @@ typedef struct LmcRunConfig {
   double* ewald_field_dev;    /* [W][N] */
   /* optional bias term (Metropolis only), see LMC_BIAS_*; state from lmc_bias_init, kept current by lmc_run */
   int32_t bias_mode;
-  int32_t bias_width;            /* columns of bias_table_dev */
+  int32_t bias_width;            /* species codes per site of bias_table_dev */
+  int32_t bias_rows;             /* rows per (site, code): 1, or the number of hyperplanes (<= LMC_MAX_BIAS_ROWS) */
   double bias_penalty;
-  const double* bias_table_dev;  /* [N][bias_width] */
+  const double* bias_table_dev;  /* [N][bias_width][bias_rows] */
   double* bias_dev;              /* [W] running bias value, in/out */
-  double* bias_sum_dev;          /* [W] running table sum, in/out */
+  double* bias_sum_dev;          /* [W][bias_rows] running table sums minus intercepts, in/out */
   double* trace_bias_dev;        /* [S][W], may be NULL */
   /* LMC_USHER_COMPOSITE (mcusher.py:307-394): every step picks one sub-usher by weight (random word 4 of the
      step), which proposes with its OWN sublattice probabilities (0 = sublattice not served by it) */
@@ -224,9 +227,11 @@ int lmc_full_features(const LmcModel* model, const int8_t* occ_dev, int num_walk
 /* field_dev [W][N] <- Ewald potential cache of every walker's occupancy (see LmcRunConfig.ewald_field_dev) */
 int lmc_ewald_field(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* field_dev, void* stream);
 
-/* bias_dev [W], sum_dev [W] <- bias value and table sum of every walker's occupancy (MCBias.compute_bias) */
-int lmc_bias_init(const int8_t* occ_dev, int num_walkers, int num_sites, int bias_mode, int bias_width,
-                  double bias_penalty, const double* bias_table_dev, double* bias_dev, double* sum_dev, void* stream);
+/* bias_dev [W], sum_dev [W][bias_rows] <- bias value and table sums (minus the host array intercepts[bias_rows],
+ * NULL = zeros) of every walker's occupancy (MCBias.compute_bias) */
+int lmc_bias_init(const int8_t* occ_dev, int num_walkers, int num_sites, int bias_mode, int bias_width, int bias_rows,
+                  double bias_penalty, const double* intercepts, const double* bias_table_dev, double* bias_dev,
+                  double* sum_dev, void* stream);
 
 /* out_dev [W][F] <- feature change of walker w for its k flips (sites/codes [W][k] int32, applied
  * sequentially, chemical work against the pre-step occupancy) */

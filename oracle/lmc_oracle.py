@@ -832,6 +832,26 @@ class SquareChargeBias(_Bias):
         return -self.penalty * c ** 2
 
 
+class SquareHyperplaneBias(_Bias):
+    """bias.py:290-353 with get_dim_ids_table / occu_to_counts (occu_utils.py:27-57, 96-130)."""
+
+    def __init__(self, sublattices, hyperplane_normals, hyperplane_intercepts, penalty=0.5):
+        super().__init__(sublattices)
+        self.penalty = penalty
+        self._A = np.array(hyperplane_normals, dtype=int)
+        self._b = np.array(hyperplane_intercepts, dtype=int)
+        self._dim_ids_table = get_dim_ids_table(self.sublattices)
+        self.d = sum(len(sl.species) for sl in self.sublattices)
+
+    def compute_bias(self, occupancy):
+        occu = np.array(occupancy, dtype=int)
+        dim_ids = self._dim_ids_table[np.arange(len(occu), dtype=int), occu]     # occu_to_counts
+        n = np.zeros(self.d, dtype=int)
+        ids, cnt = np.unique(dim_ids[dim_ids >= 0], return_counts=True)
+        n[ids] = cnt
+        return -self.penalty * np.sum((self._A @ n - self._b) ** 2)
+
+
 def _dot_seq(a, b) -> float:
     """Sequential dot product (the engine's order; np.dot's BLAS order is unspecified)."""
     p = 0.0

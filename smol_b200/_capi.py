@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 8
+LMC_ABI_VERSION = 9
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -15,6 +15,7 @@ LMC_MAX_FLIPS = 4
 LMC_MAX_DIMS = 16
 LMC_MAX_TABLE_FLIPS = 8
 LMC_MAX_COMPOSITE = 4
+LMC_MAX_BIAS_ROWS = 4
 LMC_USHER_FLIP, LMC_USHER_SWAP, LMC_USHER_TABLEFLIP, LMC_USHER_COMPOSITE, LMC_USHER_MULTISTEP = 0, 1, 2, 3, 4
 LMC_KERNEL_METROPOLIS, LMC_KERNEL_WANGLANDAU = 0, 1
 LMC_BIAS_NONE, LMC_BIAS_TABLE_SUM, LMC_BIAS_SQUARE_SUM = 0, 1, 2
@@ -95,7 +96,7 @@ class LmcRunConfig(C.Structure):
         ("occ_dev", _P), ("features_dev", _P), ("enthalpy_dev", _P),
         ("trace_occ_dev", _P), ("trace_features_dev", _P), ("trace_enthalpy_dev", _P),
         ("trace_accepted_dev", _P), ("trace_naccepted_dev", _P), ("ewald_field_dev", _P),
-        ("bias_mode", C.c_int32), ("bias_width", C.c_int32), ("bias_penalty", C.c_double),
+        ("bias_mode", C.c_int32), ("bias_width", C.c_int32), ("bias_rows", C.c_int32), ("bias_penalty", C.c_double),
         ("bias_table_dev", _P), ("bias_dev", _P), ("bias_sum_dev", _P), ("trace_bias_dev", _P),
         ("comp_num", C.c_int32), ("comp_usher", C.c_int32 * LMC_MAX_COMPOSITE),
         ("comp_cum", C.c_double * LMC_MAX_COMPOSITE),
@@ -145,7 +146,7 @@ def load():
     lib.lmc_run.argtypes = [_P, C.POINTER(LmcRunConfig), _P]
     lib.lmc_model_info.argtypes = [_P, C.POINTER(C.c_int32), C.c_int]
     lib.lmc_ewald_field.argtypes = [_P, _P, C.c_int, _P, _P]
-    lib.lmc_bias_init.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]
+    lib.lmc_bias_init.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P, _P]
     lib.lmc_launch_count.restype = C.c_int64
     lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:

@@ -5,7 +5,8 @@ On the device both supported terms are a per-site table and a running table sum 
 (``LMC_BIAS_*`` in ``include/lmc.h``):
 
 * ``FugacityBias`` (``bias.py:96-233``): ``sum_k log(fugacity_fraction[k][occ[k]])`` -> table of log fractions;
-* ``SquareChargeBias`` (``bias.py:236-287``): ``-penalty * (sum_k oxidation_state[k][occ[k]])**2``.
+* ``SquareChargeBias`` (``bias.py:236-287``): ``-penalty * (sum_k oxidation_state[k][occ[k]])**2``;
+* ``SquareHyperplaneBias`` (``bias.py:290-353``): ``-penalty * ||A n - b||**2``, one table row per hyperplane.
 
 ``compute_bias`` / ``compute_bias_change`` run the same device kernel as the sampler.
 """
@@ -37,6 +38,7 @@ class MCBias:
 
     mode = capi.LMC_BIAS_NONE
     penalty = 0.0
+    intercepts = None      # per-row constants subtracted from the table sums (SquareHyperplaneBias: b)
 
     def __init__(self, sublattices, rng=None, **kwargs):
         self.sublattices = list(sublattices)
@@ -45,8 +47,19 @@ class MCBias:
 
     @property
     def table(self) -> np.ndarray:
-        """float64 ``[num_sites, max_code + 1]`` table summed over the occupancy on the device."""
+        """float64 ``[num_sites, max_code + 1]`` (``[..., rows]`` for several hyperplanes) table summed over the
+        occupancy on the device."""
         return self._table
+
+    @property
+    def rows(self) -> int:
+        return 1 if self._table.ndim == 2 else int(self._table.shape[2])
+
+    def _intercept_array(self):
+        ic = np.zeros(capi.LMC_MAX_BIAS_ROWS, dtype=np.float64)
+        if self.intercepts is not None:
+            ic[:self.rows] = np.asarray(self.intercepts, dtype=np.float64)
+        return ic
 
     def _blank_table(self, fill):
         num_cols = max(int(max(sl.encoding)) for sl in self.sublattices) + 1
@@ -67,10 +80,11 @@ class MCBias:
         occ_d = torch.from_numpy(rows).to(dev)
         tab_d = torch.from_numpy(np.ascontiguousarray(self.table)).to(dev)
         bias = torch.empty(W, dtype=torch.float64, device=dev)
-        tsum = torch.empty(W, dtype=torch.float64, device=dev)
-        capi.check(lib.lmc_bias_init(occ_d.data_ptr(), W, N, self.mode, self.table.shape[1], float(self.penalty),
-                                     tab_d.data_ptr(), bias.data_ptr(), tsum.data_ptr(),
-                                     torch.cuda.current_stream(dev).cuda_stream))
+        tsum = torch.empty((W, self.rows), dtype=torch.float64, device=dev)
+        ic = self._intercept_array()
+        capi.check(lib.lmc_bias_init(occ_d.data_ptr(), W, N, self.mode, self.table.shape[1], self.rows,
+                                     float(self.penalty), ic.ctypes.data, tab_d.data_ptr(), bias.data_ptr(),
+                                     tsum.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
         return bias.cpu().numpy()
 
     def compute_bias(self, occupancy):
@@ -142,13 +156,49 @@ class SquareChargeBias(MCBias):
         self._table = table
 
 
+class SquareHyperplaneBias(MCBias):
+    """``bias.py:290-353``: ``-penalty * ||A n - b||^2`` with ``n`` the species counts in "counts" format
+    (one entry per (sublattice, species), ``occu_utils.py:27-57``)."""
+
+    mode = capi.LMC_BIAS_SQUARE_SUM
+
+    def __init__(self, sublattices, hyperplane_normals, hyperplane_intercepts, penalty=0.5, **kwargs):
+        super().__init__(sublattices, **kwargs)
+        if penalty <= 0:
+            raise ValueError("Penalty factor should be > 0!")
+        self.penalty = float(penalty)
+        self._A = np.atleast_2d(np.array(hyperplane_normals, dtype=int))
+        self._b = np.atleast_1d(np.array(hyperplane_intercepts, dtype=int))
+        self.d = sum(len(sl.species) for sl in self.sublattices)
+        if self._A.shape != (len(self._b), self.d):
+            raise ValueError(f"hyperplane_normals must have shape [{len(self._b)}, {self.d}]")
+        if len(self._b) > capi.LMC_MAX_BIAS_ROWS:
+            raise ValueError(f"at most {capi.LMC_MAX_BIAS_ROWS} hyperplanes")
+        # get_dim_ids_table (occu_utils.py:27-57), then column A[:, dim] per (site, code)
+        num_cols = max(int(max(sl.encoding)) for sl in self.sublattices) + 1
+        num_rows = sum(len(sl.sites) for sl in self.sublattices)
+        dim_ids = np.full((num_rows, num_cols), -1, dtype=int)
+        dim = 0
+        for sl in self.sublattices:
+            for code in sl.encoding:
+                dim_ids[np.asarray(sl.sites, dtype=int), int(code)] = dim
+                dim += 1
+        self._dim_ids_table = dim_ids
+        table = np.zeros((num_rows, num_cols, len(self._b)), dtype=np.float64)
+        ok = dim_ids >= 0
+        table[ok] = self._A.T[dim_ids[ok]]
+        self._table = table
+        self.intercepts = self._b.astype(np.float64)
+
+
 _BIAS = {"fugacitybias": FugacityBias, "fugacity": FugacityBias,
-         "squarechargebias": SquareChargeBias, "squarecharge": SquareChargeBias}
+         "squarechargebias": SquareChargeBias, "squarecharge": SquareChargeBias,
+         "squarehyperplanebias": SquareHyperplaneBias, "squarehyperplane": SquareHyperplaneBias}
 
 
 def mcbias_factory(bias_type, sublattices, *args, **kwargs):
     """``bias.py:355-372``."""
     key = str(bias_type).lower().replace("-", "").replace("_", "").replace(" ", "")
     if key not in _BIAS:
-        raise ValueError(f"{bias_type} is not a supported MCBias (available: FugacityBias, SquareChargeBias)")
+        raise ValueError(f"{bias_type} is not a supported MCBias (available: FugacityBias, SquareChargeBias, SquareHyperplaneBias)")
     return _BIAS[key](sublattices, *args, **kwargs)

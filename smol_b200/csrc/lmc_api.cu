@@ -649,12 +649,16 @@ extern "C" int lmc_ewald_field(const LmcModel* mdl, const int8_t* occ, int W, do
   return 0;
 }
 
-extern "C" int lmc_bias_init(const int8_t* occ, int W, int N, int mode, int bw, double pen, const double* tab, double* bias,
-                             double* sum, void* stream) {
+extern "C" int lmc_bias_init(const int8_t* occ, int W, int N, int mode, int bw, int rows, double pen, const double* icpt,
+                             const double* tab, double* bias, double* sum, void* stream) {
   if (!occ || !tab || !bias || !sum) return fail("null argument");
   if (mode != LMC_BIAS_TABLE_SUM && mode != LMC_BIAS_SQUARE_SUM) return fail("unknown bias mode");
+  if (rows < 1 || rows > LMC_MAX_BIAS_ROWS || (mode == LMC_BIAS_TABLE_SUM && rows != 1)) return fail("bias_rows out of range");
   if (W <= 0) return 0;
-  lmc_bias_init_kernel<<<(W + 3) / 4, 128, 0, (cudaStream_t)stream>>>(occ, W, N, lmc_row_stride(N), mode, bw, pen, tab, bias, sum);
+  BiasIcpt ic;
+  for (int r = 0; r < LMC_MAX_BIAS_ROWS; ++r) ic.v[r] = (icpt && r < rows) ? icpt[r] : 0.0;
+  lmc_bias_init_kernel<<<(W + 3) / 4, 128, 0, (cudaStream_t)stream>>>(occ, W, N, lmc_row_stride(N), mode, bw, rows, pen, ic, tab,
+                                                                    bias, sum);
   g_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -762,6 +766,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     if (c->kernel != LMC_KERNEL_METROPOLIS) return fail("bias terms are defined for the Metropolis kernel only (wanglandau.py:24)");
     if (c->bias_mode != LMC_BIAS_TABLE_SUM && c->bias_mode != LMC_BIAS_SQUARE_SUM) return fail("unknown bias mode");
     if (!c->bias_table_dev || !c->bias_dev || !c->bias_sum_dev || c->bias_width <= 0) return fail("bias pointers must not be null");
+    if (c->bias_rows < 1 || c->bias_rows > LMC_MAX_BIAS_ROWS || (c->bias_mode == LMC_BIAS_TABLE_SUM && c->bias_rows != 1))
+      return fail("bias_rows out of range");
   }
   const bool spec_ok = m.spOK && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
                        (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
@@ -813,7 +819,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.tr_occ = c->trace_occ_dev; a.tr_feat = c->trace_features_dev; a.tr_enth = c->trace_enthalpy_dev;
   a.tr_acc = c->trace_accepted_dev; a.tr_nacc = c->trace_naccepted_dev;
   a.wl = c->wl;
-  a.bias_mode = c->bias_mode; a.bias_w = c->bias_width; a.bias_pen = c->bias_penalty;
+  a.bias_mode = c->bias_mode; a.bias_w = c->bias_width; a.bias_rows = c->bias_rows; a.bias_pen = c->bias_penalty;
   a.bias_tab = c->bias_table_dev; a.bias = c->bias_dev; a.bias_sum = c->bias_sum_dev; a.tr_bias = c->trace_bias_dev;
   a.comp_num = c->usher == LMC_USHER_COMPOSITE ? c->comp_num : 0;
   for (int i = 0; i < LMC_MAX_COMPOSITE; ++i) {
@@ -846,7 +852,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
-  a.walker_smem = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 : 0);              // running bias value and table sum
+  a.walker_smem = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
   const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
   size_t smem = 0;
   if (auto_threads && relaxed) {

@@ -655,7 +655,10 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // (kept in the walker's shared-memory slab, not in registers: the swap / flip variants are register capped)
   double* bstate = reinterpret_cast<double*>(priv + a.off_bias);
   if (!WLMODE && a.bias_mode) {
-    if (g == 0) { bstate[0] = a.bias[w]; bstate[1] = a.bias_sum[w]; }
+    if (g == 0) {
+      bstate[0] = a.bias[w];
+      for (int r = 0; r < a.bias_rows; ++r) bstate[1 + r] = a.bias_sum[(size_t)w * a.bias_rows + r];
+    }
     group_sync<G>(gmask);
   }
 
@@ -1040,22 +1043,28 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
 
       // ------------------------------ accept --------------------------------------------
       double new_fb = cur_fb, s_new = s_cur;
-      double dbias = 0.0, dbc = 0.0;
+      double dbias = 0.0, dbc = 0.0;   // dbc: table difference of the last row (the only one for a table-sum bias)
       if (!wl_mode) {
         // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
         double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
         if (a.bias_mode) {
-          // MCBias.compute_bias_change (bias.py:79-95, 193-214): table differences of the changed sites;
-          // SquareChargeBias: bias(after) - bias(before) with bias = -penalty * charge^2 (bias.py:276-287)
+          // MCBias.compute_bias_change (bias.py:79-95, 193-214): table differences of the changed sites.
+          // Square biases: bias(after) - bias(before) with bias = -penalty * sum_r c_r^2 (bias.py:276-287, 342-353);
+          // the c_r are integer valued (charges, hyperplane residuals A n - b), so the sums are exact
+          double q0 = 0.0, q1 = 0.0;
+          for (int r = 0; r < a.bias_rows; ++r) {
+            double d = 0.0;
 #pragma unroll
-          for (int f = 0; f < MF; ++f)
-            if (f < st.n)
-              dbc += __ldg(a.bias_tab + st.site[f] * a.bias_w + st.newc[f]) - __ldg(a.bias_tab + st.site[f] * a.bias_w + st.oldc[f]);
-          if (a.bias_mode == LMC_BIAS_TABLE_SUM) dbias = dbc;
-          else {
-            const double c0 = bstate[1], c1 = c0 + dbc;
-            dbias = __dsub_rn(-__dmul_rn(a.bias_pen, __dmul_rn(c1, c1)), -__dmul_rn(a.bias_pen, __dmul_rn(c0, c0)));
+            for (int f = 0; f < MF; ++f)
+              if (f < st.n)
+                d += __ldg(a.bias_tab + (st.site[f] * a.bias_w + st.newc[f]) * a.bias_rows + r) -
+                     __ldg(a.bias_tab + (st.site[f] * a.bias_w + st.oldc[f]) * a.bias_rows + r);
+            const double c0 = bstate[1 + r], c1 = c0 + d;
+            q0 += __dmul_rn(c0, c0); q1 += __dmul_rn(c1, c1);
+            dbc = d;
           }
+          if (a.bias_mode == LMC_BIAS_TABLE_SUM) dbias = dbc;
+          else dbias = __dsub_rn(-__dmul_rn(a.bias_pen, q1), -__dmul_rn(a.bias_pen, q0));
           exponent = __dadd_rn(exponent, dbias);   // metropolis.py:43-44
         }
         {
@@ -1129,7 +1138,18 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           }
         }
         enth += dH;
-        if (!WLMODE && a.bias_mode && g == 0) { bstate[0] += dbias; bstate[1] += dbc; }   // read again after the step's final sync
+        if (!WLMODE && a.bias_mode && g == 0) {   // read again after the step's final sync
+          bstate[0] += dbias;
+          for (int r = 0; r < a.bias_rows; ++r) {
+            double d = 0.0;
+#pragma unroll
+            for (int f = 0; f < MF; ++f)
+              if (f < st.n)
+                d += __ldg(a.bias_tab + (st.site[f] * a.bias_w + st.newc[f]) * a.bias_rows + r) -
+                     __ldg(a.bias_tab + (st.site[f] * a.bias_w + st.oldc[f]) * a.bias_rows + r);
+            bstate[1 + r] += d;
+          }
+        }
         if (wl_mode) { cur_fb = new_fb; s_cur = s_new; }
         ++nacc;
       } else if (st.n > 0) {
@@ -1226,7 +1246,10 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   for (int f = g; f < m.F; f += G) a.features[(size_t)w * m.F + f] = feat[f];
   if (g == 0) {
     a.enthalpy[w] = enth;
-    if (!WLMODE && a.bias_mode) { a.bias[w] = bstate[0]; a.bias_sum[w] = bstate[1]; }
+    if (!WLMODE && a.bias_mode) {
+      a.bias[w] = bstate[0];
+      for (int r = 0; r < a.bias_rows; ++r) a.bias_sum[(size_t)w * a.bias_rows + r] = bstate[1 + r];
+    }
     if (wl_mode) {
       a.wl.mod_factor_dev[w] = wl_m;
       a.wl.steps_counter_dev[w] = wl_cnt;
@@ -1399,19 +1422,26 @@ __global__ void lmc_ewald_field_kernel(const DevModel m, const int8_t* __restric
   }
 }
 
-// MCBias.compute_bias for every walker (bias.py:180-191, 276-287): one warp per walker
-__global__ void lmc_bias_init_kernel(const int8_t* __restrict__ occ_g, int W, int N, int Npad, int mode, int bw, double pen,
-                                     const double* __restrict__ tab, double* __restrict__ bias, double* __restrict__ sum) {
+// MCBias.compute_bias for every walker (bias.py:180-191, 276-287, 342-353): one warp per walker.
+// sum[w][r] = sum_k tab[k][occ_k][r] - icpt[r]; bias = sum[w][0] (table sum) or -penalty * sum_r sum[w][r]^2
+struct BiasIcpt { double v[LMC_MAX_BIAS_ROWS]; };
+__global__ void lmc_bias_init_kernel(const int8_t* __restrict__ occ_g, int W, int N, int Npad, int mode, int bw, int rows,
+                                     double pen, BiasIcpt icpt, const double* __restrict__ tab, double* __restrict__ bias,
+                                     double* __restrict__ sum) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (w >= W) return;
-  double c = 0.0;
-  for (int k = lane; k < N; k += 32) c += tab[k * bw + occ_g[(size_t)w * Npad + k]];
+  double q = 0.0, first = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    double c = 0.0;
+    for (int k = lane; k < N; k += 32) c += tab[((size_t)k * bw + occ_g[(size_t)w * Npad + k]) * rows + r];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if (lane == 0) {
-    sum[w] = c;
-    bias[w] = mode == LMC_BIAS_SQUARE_SUM ? -(pen * (c * c)) : c;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    c -= icpt.v[r];
+    if (lane == 0) sum[(size_t)w * rows + r] = c;
+    q += c * c;
+    if (r == 0) first = c;
   }
+  if (lane == 0) bias[w] = mode == LMC_BIAS_SQUARE_SUM ? -(pen * q) : first;
 }
 
 __global__ void lmc_cast_i32_i8_kernel(const int* __restrict__ src, int8_t* __restrict__ dst, int W, int N, int Npad) {

@@ -92,11 +92,11 @@ struct RunArgs {
   uint8_t* tr_acc;
   int* tr_nacc;
   double* ew_field;   // [W][N] Ewald potential cache (nullptr: gather the matrix rows), see lmc.h
-  int bias_mode, bias_w;       // LMC_BIAS_*, columns of bias_tab
+  int bias_mode, bias_w, bias_rows;   // LMC_BIAS_*, codes and rows per code of bias_tab
   double bias_pen;
-  const double* bias_tab;      // [N][bias_w]
+  const double* bias_tab;      // [N][bias_w][bias_rows]
   double* bias;                // [W] running bias value
-  double* bias_sum;            // [W] running table sum
+  double* bias_sum;            // [W][bias_rows] running table sums
   double* tr_bias;             // [S][W]
   int comp_num, comp_usher[LMC_MAX_COMPOSITE];                   // composite usher, see lmc.h
   double comp_cum[LMC_MAX_COMPOSITE];

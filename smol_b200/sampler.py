@@ -417,11 +417,13 @@ class Sampler:
                 self._bias_dev = dict(
                     table=torch.from_numpy(np.ascontiguousarray(self.bias.table, dtype=np.float64)).to(dev),
                     value=torch.empty((W,), dtype=torch.float64, device=dev),
-                    tsum=torch.empty((W,), dtype=torch.float64, device=dev))
+                    tsum=torch.empty((W, self.bias.rows), dtype=torch.float64, device=dev))
             b = self._bias_dev
+            icpt = self.bias._intercept_array()
             capi.check(eng.lib.lmc_bias_init(self._occ_dev.data_ptr(), W, N, self.bias.mode, self.bias.table.shape[1],
-                                             float(self.bias.penalty), b["table"].data_ptr(), b["value"].data_ptr(),
-                                             b["tsum"].data_ptr(), eng._stream()))
+                                             self.bias.rows, float(self.bias.penalty), icpt.ctypes.data,
+                                             b["table"].data_ptr(), b["value"].data_ptr(), b["tsum"].data_ptr(),
+                                             eng._stream()))
         if self._kernel == capi.LMC_KERNEL_WANGLANDAU and self._wl_state is None:
             self._init_wl()
         if getattr(self, "_seeds_dev", None) is None:
@@ -520,7 +522,7 @@ class Sampler:
                         cfg.comp_sl_cum[i][k] = float(sl_cum[i, k])
             if self.bias is not None:
                 b = self._bias_dev
-                cfg.bias_mode, cfg.bias_width = self.bias.mode, self.bias.table.shape[1]
+                cfg.bias_mode, cfg.bias_width, cfg.bias_rows = self.bias.mode, self.bias.table.shape[1], self.bias.rows
                 cfg.bias_penalty = float(self.bias.penalty)
                 cfg.bias_table_dev, cfg.bias_dev, cfg.bias_sum_dev = b["table"].data_ptr(), b["value"].data_ptr(), b["tsum"].data_ptr()
                 cfg.trace_bias_dev = d["bias"].data_ptr()

@@ -111,6 +111,7 @@ def _run_both(ens_g, ens_o_factory, usher_name, W, nsteps, thin, occ0, seeds, T=
             ob = None
             if bias is not None:
                 ob = (O.FugacityBias(subl, bias[1]["fugacity_fractions"]) if "fugacity" in bias[0].lower()
+                      else O.SquareHyperplaneBias(subl, **bias[1]) if "hyperplane" in bias[0].lower()
                       else O.SquareChargeBias(subl, **bias[1]))
             kernels.append(O.Metropolis(ens_o, ush, T, seed=int(seeds[w]), walker=w, bias=ob))
         else:
@@ -435,7 +436,10 @@ def test_multistep_trajectory(cuda_device, sub_usher, lens, probs):
 # bias terms (smol/moca/kernel/bias.py) in the Metropolis exponent
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("bias", [("square-charge", dict(penalty=0.5)), ("SquareChargeBias", dict(penalty=0.02)),
-                                  ("fugacity", None)], ids=["charge0.5", "charge0.02", "fugacity"])
+                                  ("fugacity", None),
+                                  ("square-hyperplane", dict(hyperplane_normals=[[1, 3, 4, -2, -1], [1, -2, 0, 0, 0]],
+                                                             hyperplane_intercepts=[0, 3], penalty=0.05))],
+                         ids=["charge0.5", "charge0.02", "fugacity", "hyperplanes"])
 @pytest.mark.parametrize("group", [0, 8])
 def test_biased_semigrand_flip_trajectory(cuda_device, bias, group):
     """single flips on cation AND anion sublattices with a charge penalty / fugacity fractions: the bias
@@ -468,6 +472,7 @@ def test_biased_semigrand_flip_trajectory(cuda_device, bias, group):
     assert np.abs(np.diff(ref["bias"][:, 0, 0])).max() > 0, "bias never changed; weak test"
     # single-call API against the oracle's restatement
     ob = ref_bias = (O.FugacityBias(ens_o().sublattices, kw["fugacity_fractions"]) if "fug" in name
+                     else O.SquareHyperplaneBias(ens_o().sublattices, **kw) if "hyper" in name
                      else O.SquareChargeBias(ens_o().sublattices, **kw))
     step = [(0, int((occ0[0, 0] + 1) % 3)), (30, int((occ0[0, 30] + 1) % 2))]
     np.testing.assert_allclose(smp.bias.compute_bias(occ0[0]), ob.compute_bias(occ0[0]), rtol=1e-12, atol=1e-12)

@@ -172,11 +172,23 @@ def test_bias_tables_follow_the_reference_layout():
         B.FugacityBias(sls, fugacity_fractions=[{"Li+": 1.0}, {"O2-": 0.5, "F-": 0.5}])
     with pytest.raises(ValueError):
         B.mcbias_factory("no-such-bias", sls)
+    # hyperplanes: row r of the table = A[r][dim(site, code)], dims counted sublattice by sublattice
+    A = [[1, 3, 4, -2, -1], [1, -2, 0, 0, 0]] if "Li+" in sls[0].species else [[-2, -1, 1, 3, 4], [0, 0, 1, -2, 0]]
+    hp = B.SquareHyperplaneBias(sls, A, [0, 3], penalty=0.1)
+    assert hp.table.shape == (N, 3, 2) and hp.rows == 2 and list(hp.intercepts) == [0, 3]
+    np.testing.assert_array_equal(hp.table[cat.sites[0], :, 0], [1, 3, 4])
+    np.testing.assert_array_equal(hp.table[cat.sites[0], :, 1], [1, -2, 0])
+    np.testing.assert_array_equal(hp.table[ani.sites[0], :2, 0], [-2, -1])
+    with pytest.raises(ValueError):
+        B.SquareHyperplaneBias(sls, [[1, 2, 3]], [0])
     # oracle: change == difference of totals (the reference's generic compute_bias_change)
     osl = M.oracle_sublattices(O, sls)
     rng = np.random.default_rng(0)
     occ = M.random_occupancies(sub, scm, 1, seed=3)[0]
-    for ob in (O.SquareChargeBias(osl, 0.3), O.FugacityBias(osl, fr)):
+    # with A = the charges and b = 0 the hyperplane bias is the charge bias
+    occ_t = M.random_occupancies(sub, scm, 1, seed=8)[0]
+    assert O.SquareHyperplaneBias(osl, [A[0]], [0], 0.3).compute_bias(occ_t) == O.SquareChargeBias(osl, 0.3).compute_bias(occ_t)
+    for ob in (O.SquareChargeBias(osl, 0.3), O.FugacityBias(osl, fr), O.SquareHyperplaneBias(osl, A, [0, 3], 0.2)):
         for _ in range(10):
             s1, s2 = int(rng.choice(cat.sites)), int(rng.choice(ani.sites))
             step = [(s1, int((occ[s1] + 1) % 3)), (s2, int((occ[s2] + 1) % 2))]
