@@ -7,7 +7,7 @@ from tests import models as M
 sub, scm, coefs, it = bench.build_model()
 W, N = 4096, 512
 ens = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, it))
-occ = M.random_occupancies(sub, scm, W, seed=0, balanced=True)
+occ = torch.from_numpy(M.random_occupancies(sub, scm, W, seed=0, balanced=True).astype(np.int32)).pin_memory()
 smp = S.Sampler.from_ensemble(ens, 1000.0, step_type="swap", nwalkers=W, seeds=list(range(W)))
 warnings.simplefilter("ignore")
 for _ in range(3):

@@ -70,6 +70,16 @@ class LmcEngine:
     def upload_occupancy(self, occ_host: np.ndarray):
         """int32 ``[W, N]`` host array -> int8 ``[W, row_stride]`` device tensor."""
         torch = _torch()
+        if isinstance(occ_host, torch.Tensor) and occ_host.device.type == "cpu" and occ_host.is_pinned() \
+                and occ_host.dtype == torch.int32 and occ_host.is_contiguous():
+            # the caller's buffer is already page-locked int32: copy straight from it (no staging pass)
+            W = occ_host.shape[0]
+            src = occ_host.to(self.device, non_blocking=True)
+            dst = torch.empty((W, self.row_stride), dtype=torch.int8, device=self.device)
+            capi.check(self.lib.lmc_cast_i32_to_i8(src.data_ptr(), dst.data_ptr(), W, self.N, self._stream()))
+            return dst
+        if isinstance(occ_host, torch.Tensor):
+            occ_host = occ_host.cpu().numpy()
         occ_host = np.asarray(occ_host)
         if occ_host.dtype.kind not in "iu":
             occ_host = occ_host.astype(np.int32)      # raises for non-numeric input like the reference

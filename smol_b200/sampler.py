@@ -384,10 +384,10 @@ class Sampler:
                 warnings.warn("Initial occupancies where provided with a pre-existing set of samples."
                               "\n Make real sure that is what you want. If not, reset the samples in "
                               "the sampler.", RuntimeWarning)
-            occ = np.asarray(initial_occupancies)
+            occ = initial_occupancies if isinstance(initial_occupancies, torch.Tensor) else np.asarray(initial_occupancies)
             if occ.ndim == 1 and self.nwalkers == 1:
                 occ = occ[None, :]
-            if occ.shape != (self.nwalkers, eng.N):
+            if tuple(occ.shape) != (self.nwalkers, eng.N):
                 raise AttributeError("The given initial occcupancies have incompompatible dimensions. "
                                      f"Shape should be {(self.nwalkers, eng.N)}.")
             # copied (sampler.py:401) and converted to int32 (sampler.py:406) on the way into the

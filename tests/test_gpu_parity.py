@@ -347,6 +347,29 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
     assert smp.samples.step_efficiency() > 0
 
 
+def test_page_locked_tensor_input_equals_array_input(cuda_device):
+    """initial occupancies given as a page-locked int32 torch tensor are copied straight from the caller's
+    buffer; the chains are those of the ndarray path and the caller's data is left untouched (sampler.py:401)"""
+    import torch
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 4
+    it = L.cluster_interaction_tensors(sub, M.fcc_coefs(sub))
+    ens = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, it))
+    W = 6
+    occ0 = M.random_occupancies(sub, scm, W, seed=2, balanced=True)
+    pinned = torch.from_numpy(occ0.astype(np.int32)).pin_memory()
+    out = []
+    for src in (occ0, pinned):
+        smp = S.Sampler.from_ensemble(ens, 1500.0, step_type="swap", nwalkers=W, seeds=list(range(W)))
+        smp.run(640, src, thin_by=64)
+        out.append((smp.samples.get_occupancies(flat=False), smp.samples.get_enthalpies(flat=False)))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(pinned.numpy(), occ0)
+
+
 # ---------------------------------------------------------------------------------------------
 # composite usher (mcusher.py:307-394)
 # ---------------------------------------------------------------------------------------------
