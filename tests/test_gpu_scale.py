@@ -95,6 +95,96 @@ def test_config3_semigrand_ewald_full_size(cuda_device):
         np.testing.assert_allclose(out["features"][:, 0], feats[:, w], rtol=RTOL, atol=RTOL * scale)
 
 
+def test_config4_wang_landau_full_size(cuda_device):
+    """binary FCC 8x8x8 Wang-Landau (AFM Ising coefficients of the wang-landau notebook), 1024 independent
+    walkers: walkers checked bit-exact against the C oracle incl. their entropy / histogram; ALL walkers:
+    occurrences count every step inside the window, histogram <= occurrences, enthalpy == full re-evaluation,
+    visited levels inside the window."""
+    import smol_b200 as S
+    from oracle import lmc_oracle as O
+    from smol_b200 import lattice as L
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 8
+    coefs = np.zeros(sub.num_corr_functions)
+    mult = sub.function_total_multiplicities
+    coefs[1], coefs[2] = 2.0 * mult[1], 1.0 * mult[2]
+    it = L.cluster_interaction_tensors(sub, coefs)
+    proc = S.ClusterDecompositionProcessor(sub, scm, it)
+    ens = S.Ensemble(proc)
+    W, N = 1024, 512
+    occ0 = M.random_occupancies(sub, scm, W, seed=2)
+    e0 = ens.compute_feature_vector_batch(occ0[:64]) @ ens.natural_parameters
+    lo = float(np.floor((e0.mean() - 5 * e0.std() - 200) / 4.0) * 4.0 - 2.0)
+    hi = float(e0.mean() + 5 * e0.std() + 200)
+    seeds = np.arange(W) * 31 + 5
+    nsteps, thin = 4096, 1024
+    smp = S.Sampler.from_ensemble(ens, lo, hi, 4.0, step_type="flip", kernel_type="WangLandau", nwalkers=W,
+                                  seeds=list(seeds), flatness=0.8, check_period=1000)
+    smp.run(nsteps, occ0, thin_by=thin)
+    st = smp.wang_landau_state
+    enth = smp.samples.get_enthalpies(flat=False)[:, :, 0]
+    assert (enth >= lo).all() and (enth < hi).all()
+    assert (st["occurrences"].sum(axis=1) == nsteps).all()                   # every step ends inside the window
+    assert (st["histogram"] <= st["occurrences"]).all() and (st["entropy"] >= 0).all()
+    assert ((st["entropy"] > 0) == (st["occurrences"] > 0)).all()
+    occ_last = smp.samples.get_occupancies(flat=False)[-1]
+    full = ens.compute_feature_vector_batch(occ_last) @ ens.natural_parameters
+    np.testing.assert_allclose(enth[-1], full, rtol=RTOL, atol=1e-9)
+    co = _c_oracle(ens, O.ClusterDecompositionProcessor(sub, scm, it))
+    for w in (0, 333, 1023):
+        out, state = co.run(occ0[w:w + 1], nsteps, thin, seeds[w:w + 1], usher="flip", walker_base=w,
+                            wl=dict(min=lo, max=hi, bin=4.0, flatness=0.8, check=1000))
+        np.testing.assert_array_equal(out["occupancy"][:, 0], smp.samples.get_occupancies(flat=False)[:, w])
+        np.testing.assert_array_equal(state["histogram"][0], st["histogram"][w])
+        np.testing.assert_array_equal(state["occurrences"][0], st["occurrences"][w])
+        np.testing.assert_allclose(state["entropy"][0], st["entropy"][w], rtol=1e-12, atol=0)
+        assert state["mod_factor"][0] == st["mod_factor"][w]
+
+
+def test_config5_table_flip_ewald_full_cell(cuda_device):
+    """5-species rocksalt 12x12x12 (N = 3456, Ewald E = 8640) + charge-neutral table flips: properties that do
+    not depend on the size -- charge neutrality and site conservation of every sample, running features ==
+    full re-evaluation (Ewald row-gather AND potential-cache paths give the same chains), 64 walkers."""
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    n = 12
+    sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * n
+    rng = np.random.default_rng(21)
+    it = L.cluster_interaction_tensors(sub, rng.normal(0, 0.01, sub.num_corr_functions))
+    ewm, ewi = L.ewald_matrix(sub, scm)
+    comp = S.CompositeProcessor(sub, scm)
+    comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
+    comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.1, ewald_matrix=ewm, ewald_inds=ewi))
+    mus = {"Li+": 0.0, "Mn3+": 0.4, "Ti4+": -0.3, "O2-": 0.1, "F-": 0.0}
+    ens = S.Ensemble(comp, chemical_potentials=mus)
+    nc, W = n ** 3, 64
+    nMn, nTi = nc // 6, nc // 8
+    nLi = nc - nMn - nTi
+    nO = nLi + 3 * nMn + 4 * nTi - nc
+    cat = np.array([0] * nLi + [1] * nMn + [2] * nTi)
+    ani = np.array([0] * nO + [1] * (nc - nO))
+    occ0 = np.zeros((W, 2 * nc), dtype=np.int32)
+    for w in range(W):
+        occ0[w, :nc], occ0[w, nc:] = rng.permutation(cat), rng.permutation(ani)
+    table = [[-1, 1, 0, 2, -2], [0, -1, 1, 1, -1]]
+    res = []
+    for field in (False, True):
+        smp = S.Sampler.from_ensemble(ens, 1500.0, step_type="table_flip", nwalkers=W, seeds=list(range(W)),
+                                      flip_table=table, swap_weight=0.1, ewald_field=field)
+        smp.run(600, occ0, thin_by=200)
+        occ = smp.samples.get_occupancies(flat=False)
+        q = np.array([1, 3, 4])[occ[:, :, :nc]].sum(axis=2) + np.array([-2, -1])[occ[:, :, nc:]].sum(axis=2)
+        assert (q == 0).all()                                               # charge neutral at every sample
+        assert smp.samples.step_efficiency() > 0.1
+        feats = smp.samples.get_feature_vectors(flat=False)
+        full = ens.compute_feature_vector_batch(occ[-1])
+        np.testing.assert_allclose(feats[-1], full, rtol=RTOL, atol=RTOL * np.abs(full).max())
+        res.append(occ)
+    np.testing.assert_array_equal(res[0], res[1])
+    assert (res[0][-1] != occ0).any()
+
+
 def test_edge_cases(cuda_device):
     """empty swap (mcusher.py:194-199), restricted sites, sublattice probabilities, single walker,
     thin_by remainder warning (sampler.py:183-188), wrong shapes, anneal."""
