@@ -706,7 +706,7 @@ extern "C" int lmc_delta_features(const LmcModel* mdl, const int8_t* occ, int W,
   const DevModel& m = mdl->dm;
   const int G = 32, threads = 128, wpb = threads / G;
   const size_t wsm = delta_walker_smem(m);
-  const size_t smem = (((size_t)m.blob_bytes + 15) & ~size_t(15)) + (size_t)wpb * (m.Npad + wsm);
+  const size_t smem = (((size_t)m.off_dtab + 15) & ~size_t(15)) + (size_t)wpb * (m.Npad + wsm);
   if ((int)smem > mdl->smem_optin) return fail("model tables do not fit in shared memory");
   const int grid = (W + wpb - 1) / wpb;
   if (m.kone) {
@@ -853,7 +853,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   a.walker_smem = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
-  const size_t blob = ((size_t)m.blob_bytes + 15) & ~size_t(15);
+  // staged tables: the speculative kernel takes the whole blob, the classic kernels stop before its difference table
+  const size_t blob = ((size_t)(use_spec ? m.blob_bytes : m.off_dtab) + 15) & ~size_t(15);
   size_t smem = 0;
   if (auto_threads && relaxed) {
     // shared memory limits residency here: take the block size with the most resident walkers per SM

@@ -28,17 +28,20 @@ __device__ __forceinline__ SmemTables smem_tables(const DevModel& m, const unsig
 }
 
 // Stage the table blob into shared memory with one TMA bulk copy (thread 0 issues, all wait).
-// `extra_*` lets the caller piggy-back a second bulk copy (the block's occupancy rows).
+// `extra_*` lets the caller piggy-back a second bulk copy (the block's occupancy rows).  `blob_bytes`: the
+// classic kernels stage the blob up to the difference table of the speculative kernel (m.off_dtab), which
+// they never read -- for multi-species models that table is tens of KB of shared memory per block.
 __device__ __forceinline__ void stage_tables(const DevModel& m, unsigned char* smem, uint64_t* bar,
-                                             void* extra_dst, const void* extra_src, uint32_t extra_bytes) {
+                                             void* extra_dst, const void* extra_src, uint32_t extra_bytes,
+                                             uint32_t blob_bytes) {
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)m.blob_bytes + extra_bytes);
-    tma_load_1d(smem, m.blob, (uint32_t)m.blob_bytes, bar);
+    mbar_expect_tx(bar, blob_bytes + extra_bytes);
+    tma_load_1d(smem, m.blob, blob_bytes, bar);
     if (extra_bytes) tma_load_1d(extra_dst, extra_src, extra_bytes, bar);
   }
   mbar_wait(bar, 0);
@@ -570,7 +573,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   const bool active = wl_ < a.wpb && w < a.W;
   const uint32_t gmask = group_mask<G>();
 
-  unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
+  unsigned char* wbase = smem + ((m.off_dtab + 15) & ~15);
   unsigned char* wslab = wbase + (size_t)wl_ * a.walker_smem;
   // occupancy rows of the block are contiguous in global memory: slab layout keeps the rows of
   // all walkers first ([wpb][Npad]) so that ONE bulk copy loads them.
@@ -586,7 +589,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   double* fld = EWFIELD ? a.ew_field + (size_t)w * m.N : nullptr;   // potential cache (global / L2)
   (void)wslab;
 
-  stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
+  stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad),
+               (uint32_t)m.off_dtab);
   const SmemTables t = smem_tables(m, smem);
   if (!active) return;
 
@@ -1274,12 +1278,13 @@ __global__ void lmc_delta_kernel(const DevModel m, const int8_t* __restrict__ oc
   const int w = blockIdx.x * wpb + wl_;
   const int nw_blk = min(wpb, W - blockIdx.x * wpb);
   const uint32_t gmask = group_mask<G>();
-  unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
+  unsigned char* wbase = smem + ((m.off_dtab + 15) & ~15);
   uint8_t* occ = wbase + (size_t)wl_ * m.Npad;
   unsigned char* priv = wbase + (size_t)wpb * m.Npad + (size_t)wl_ * walker_smem;
   double* feat = reinterpret_cast<double*>(priv);
   unsigned char* stash = priv + ((m.F * 8 + 15) & ~15);
-  stage_tables(m, smem, &bar, wbase, occ_g + (size_t)blockIdx.x * wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
+  stage_tables(m, smem, &bar, wbase, occ_g + (size_t)blockIdx.x * wpb * m.Npad, (uint32_t)(nw_blk * m.Npad),
+               (uint32_t)m.off_dtab);
   const SmemTables t = smem_tables(m, smem);
   if (wl_ >= wpb || w >= W) return;
   for (int f = g; f < m.F; f += G) feat[f] = 0.0;

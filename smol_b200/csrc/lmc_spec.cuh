@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
   uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [32] x (sl<<24 | pos, site, word z, float log u)
   uint16_t* lists = reinterpret_cast<uint16_t*>(priv + a.off_lists);   // LISTS: [sublattice][code][n_active]
 
-  stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad));
+  stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad),
+               (uint32_t)m.blob_bytes);
   const SmemTables t = smem_tables(m, smem);
   const double* dtab = reinterpret_cast<const double*>(smem + m.off_dtab);
   if (!active) return;
