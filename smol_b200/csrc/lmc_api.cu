@@ -15,7 +15,6 @@
 #define LMC_API_TU
 #include "lmc_kernels.cuh"
 #include "lmc_launch.h"
-#define LMC_PLANE_COPIES (LMC_OPT_PFX ? 2 : 1)
 
 using namespace lmc;
 
@@ -503,7 +502,6 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     const int C = m.nCls + 1;
     size_t off = 0;
     const size_t off_cls = off; off += (size_t)C * 16;
-    m.off_coef = (int)off;
     m.off_tabA = (int)off; off += ((size_t)tabA_len * 8 + 15) & ~size_t(15);
     m.off_nat = (int)off; off += ((size_t)m.F * 8 + 15) & ~size_t(15);
     m.off_orb = (int)off; off += ((size_t)m.nOrb * sizeof(OrbDev) + 15) & ~size_t(15);
@@ -847,7 +845,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (a.max_flips > LMC_MAX_FLIPS) return fail("flip table changes more than 4 sites per step");
   a.off_cnt = a.off_stash + (int)(((size_t)a.max_flips * m.Rstride * stash_el + 15) & ~size_t(15));
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
-  a.off_ring = a.off_plane + ((LMC_PLANE_COPIES * m.plane_words * 4 + 15) & ~15);  // planes (+ prefix popcounts)
+  a.off_ring = a.off_plane + ((m.plane_words * 4 + 15) & ~15);   // species bit-planes
   a.off_eidx = a.off_ring + G * 16;                                   // per-lane precomputed proposals
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)

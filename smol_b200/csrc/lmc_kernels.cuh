@@ -9,7 +9,6 @@ namespace lmc {
 // shared-memory view of the staged tables
 struct SmemTables {
   const uint4* cls;     // (strides u8x4 [other0, other1, other2, self], atab_off, coef lo, coef hi)
-  const double* coef;   // unused (kept for layout compatibility)
   const double* tabA;   // phase-A table
   const double* nat;    // natural parameters
   const OrbDev* orb;
@@ -19,7 +18,6 @@ struct SmemTables {
 __device__ __forceinline__ SmemTables smem_tables(const DevModel& m, const unsigned char* base) {
   SmemTables t;
   t.cls = reinterpret_cast<const uint4*>(base);
-  t.coef = nullptr;
   t.tabA = reinterpret_cast<const double*>(base + m.off_tabA);
   t.nat = reinterpret_cast<const double*>(base + m.off_nat);
   t.orb = reinterpret_cast<const OrbDev*>(base + m.off_orb);
@@ -68,23 +66,11 @@ __device__ __forceinline__ RecChunk load_records_pred(const DevModel& m, int sit
   return c;
 }
 
-// A/B measured on B200 (profiles/r01_variants.md): the branchy uniform loads raise register pressure
-#ifndef LMC_OPT_LOADSW
-#define LMC_OPT_LOADSW 0
-#endif
+// (uniform-branch loads instead of predicated ones were measured slower: they raise the register pressure of
+// the 72-register variants, profiles/r01_variants.md)
 template <int G>
 __device__ __forceinline__ RecChunk load_records(const DevModel& m, int site, int g) {
-#if !LMC_OPT_LOADSW
   return load_records_pred<G>(m, site, g);
-#endif
-  const uint2* rp = m.site_rec + (size_t)site * m.Rstride + g;
-  RecChunk c;
-  const int nper = m.Rstride / G;   // uniform (Rstride is a multiple of 32)
-  c.r[0] = __ldg(rp);
-  if (nper > 1) c.r[1] = __ldg(rp + G);
-  if (nper > 2) c.r[2] = __ldg(rp + 2 * G);
-  if (nper > 3) c.r[3] = __ldg(rp + 3 * G);
-  return c;
 }
 
 template <bool KONE>
@@ -385,76 +371,11 @@ __device__ __forceinline__ int select_pos_scan(const DevModel& m, const uint32_t
   return res;
 }
 
-template <int G>
-__device__ __forceinline__ int select_pos_pfx(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
-                                          int g, uint32_t mask) {
-  // planes: [plane words | exclusive prefix popcounts], both [code][word] per sublattice
-  const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
-  const int nw = m.sl_nwords[sl];
-  const uint32_t* pl = planes + m.sl_plane_off[sl] + code * nw;
-  const uint32_t* px = pl + m.plane_words;
-  const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
-  const int cw = (nw + G - 1) / G;            // words per lane (1 when the plane fits the group)
-  const int lo = g * cw, hi = min(lo + cw, nw);
-  // candidates before this lane's chunk (all words before the last one are full)
-  int excl = 0x7fffffff, cnt = 0;
-  uint32_t b = 0u;
-  if (lo < nw) {
-    const int pe = (int)px[lo];
-    excl = ne ? 32 * lo - pe : pe;
-    for (int wd = lo; wd < hi; ++wd) {
-      b = pl[wd];
-      if (ne) b = ~b & (wd == nw - 1 ? tail : 0xffffffffu);
-      cnt += __popc(b);
-    }
-  }
-  const bool found = (k >= excl) && (k < excl + cnt);
-  int wsel = lo;
-  int rem = k - excl;
-  if (cw > 1 && found) {   // locate the word inside the chunk
-    for (int wd = lo; wd < hi; ++wd) {
-      b = pl[wd];
-      if (ne) b = ~b & (wd == nw - 1 ? tail : 0xffffffffu);
-      const int c = __popc(b);
-      if (rem < c) { wsel = wd; break; }
-      rem -= c;
-    }
-  }
-  if (G == 1) {
-    int pos = 0;
-    for (int q = 0; q < 32; ++q)
-      if (((b >> q) & 1u) && __popc(b & ((1u << q) - 1u)) == rem) pos = q;
-    return wsel * 32 + pos;
-  }
-  const uint32_t own = __ballot_sync(mask, found);
-  const int src = own ? (__ffs(own) - 1) : (int)(threadIdx.x & 31);
-  const uint32_t word = __shfl_sync(mask, b, src);
-  rem = __shfl_sync(mask, rem, src);
-  wsel = __shfl_sync(mask, wsel, src);
-  int hit = -1;
-#pragma unroll
-  for (int bit = 0; bit < 32; bit += G) {   // every lane tests bit(s) of the owning word
-    const int q = bit + g;
-    if (((word >> q) & 1u) && __popc(word & ((1u << q) - 1u)) == rem) hit = q;
-  }
-  const uint32_t hb = __ballot_sync(mask, hit >= 0);
-  if (G == 32) return wsel * 32 + (hb ? __ffs(hb) - 1 : 0);
-  const int hl = hb ? (__ffs(hb) - 1) : (int)(threadIdx.x & 31);
-  return wsel * 32 + __shfl_sync(mask, hit, hl);
-}
-
-// cached prefix popcounts measured neutral vs the shuffle scan (profiles/r01_variants.md): off
-#ifndef LMC_OPT_PFX
-#define LMC_OPT_PFX 0
-#endif
+// (cached prefix popcounts per plane word were measured neutral against the shuffle scan, profiles/r01_variants.md)
 template <int G>
 __device__ __forceinline__ int select_pos(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
                                           int g, uint32_t mask) {
-#if LMC_OPT_PFX
-  return select_pos_pfx<G>(m, planes, sl, code, k, ne, g, mask);
-#else
   return select_pos_scan<G>(m, planes, sl, code, k, ne, g, mask);
-#endif
 }
 
 __device__ __forceinline__ int site_of_pos(const DevModel& m, int sl, int pos) {
@@ -574,7 +495,6 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   const uint32_t gmask = group_mask<G>();
 
   unsigned char* wbase = smem + ((m.off_dtab + 15) & ~15);
-  unsigned char* wslab = wbase + (size_t)wl_ * a.walker_smem;
   // occupancy rows of the block are contiguous in global memory: slab layout keeps the rows of
   // all walkers first ([wpb][Npad]) so that ONE bulk copy loads them.
   uint8_t* occ_rows = wbase;
@@ -587,7 +507,6 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
   void* eidx = priv + a.off_eidx;   // per-walker Ewald cache (see flip_ewald)
   double* fld = EWFIELD ? a.ew_field + (size_t)w * m.N : nullptr;   // potential cache (global / L2)
-  (void)wslab;
 
   stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad),
                (uint32_t)m.off_dtab);
@@ -603,7 +522,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   }
   // species counts per (active sublattice, code) and one bit-plane per code
   for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
-  for (int i = g; i < (LMC_OPT_PFX ? 2 : 1) * m.plane_words; i += G) planes[i] = 0u;
+  for (int i = g; i < m.plane_words; i += G) planes[i] = 0u;
   group_sync<G>(gmask);
   for (int sl = 0; sl < m.nSl; ++sl) {
     const int n_act = m.sl_off[sl + 1] - m.sl_off[sl], nw = m.sl_nwords[sl];
@@ -617,19 +536,6 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     }
   }
   group_sync<G>(gmask);
-  // exclusive prefix popcounts per (sublattice, code): px[w] = set bits of the plane in words < w
-  for (int sl = 0; LMC_OPT_PFX && sl < m.nSl; ++sl) {
-    const int nw = m.sl_nwords[sl];
-    int maxcode = 0;
-    for (int c = 0; c < m.sl_ncodes[sl]; ++c) maxcode = max(maxcode, m.sl_codes[sl][c]);
-    for (int code = g; code <= maxcode; code += G) {
-      uint32_t* pl = planes + m.sl_plane_off[sl] + code * nw;
-      uint32_t run = 0;
-      for (int wd = 0; wd < nw; ++wd) { pl[m.plane_words + wd] = run; run += __popc(pl[wd]); }
-    }
-  }
-  group_sync<G>(gmask);
-
   const unsigned long long seed = a.seeds[w];
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint32_t wid = (uint32_t)(a.walker_base + w);
@@ -670,16 +576,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // State-independent part of the next G steps, one step per lane (counter-based RNG): random
   // words, sublattice, first site and the float log of the acceptance uniform.  Every step then
   // costs a few shuffles instead of a redundant Philox evaluation in all lanes.
-#ifndef LMC_OPT_RING
-#define LMC_OPT_RING 1
-#endif
-#if LMC_OPT_RING
   uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [G] x (sl<<24 | pos, site, word z, float log u)
-#else
-  U4 bq{0, 0, 0, 0};
-  int b_slj = 0, b_site = 0;
-  float b_lf = 0.f;
-#endif
   int bphase = 0;
   long long nacc_total = 0;
   for (long long s = 0; s < a.S; ++s) {
@@ -693,7 +590,6 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         r = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 0u, wid, k0, k1);
         lf = log_u_float(r.w);
       } else {
-#if LMC_OPT_RING
         if (bphase == 0) {
           const unsigned long long st_ = step + (unsigned long long)g;
           const U4 bq = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
@@ -710,24 +606,6 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         r.x = 0u; r.y = 0u; r.w = 0u;
         r.z = rq.z;
         lf = __uint_as_float(rq.w);
-#else
-        if (bphase == 0) {
-          const unsigned long long st_ = step + (unsigned long long)g;
-          bq = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
-          const int sl_ = choose_sublattice(m, bq.x);
-          const int j_ = (int)mulhi32(bq.y, (uint32_t)(m.sl_off[sl_ + 1] - m.sl_off[sl_]));
-          b_slj = (sl_ << 24) | j_;
-          b_site = site_of_pos(m, sl_, j_);
-          b_lf = log_u_float(bq.w);
-        }
-        const int src = (int)((threadIdx.x & 31u) & ~(uint32_t)(G - 1)) + bphase;
-        const int slj = __shfl_sync(gmask, b_slj, src);
-        pre_sl = slj >> 24; pre_j = slj & 0xffffff;
-        pre_site = __shfl_sync(gmask, b_site, src);
-        r.x = 0u; r.y = 0u; r.w = 0u;
-        r.z = __shfl_sync(gmask, bq.z, src);
-        lf = __shfl_sync(gmask, b_lf, src);
-#endif
         bphase = (bphase + 1) & (G - 1);
       }
       Step<MF> st;
@@ -1121,17 +999,6 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
               pl[st.newc[f] * nw] ^= bit;
             }
         }
-        // prefix popcounts of the touched planes: words after the flipped position shift by one
-#pragma unroll
-        for (int f = 0; f < MF; ++f)
-          if (LMC_OPT_PFX && f < st.n) {
-            const int nw = m.sl_nwords[st.sl[f]];
-            uint32_t* px = planes + m.plane_words + m.sl_plane_off[st.sl[f]];
-            for (int wd = (st.pos[f] >> 5) + 1 + g; wd < nw; wd += G) {
-              px[st.oldc[f] * nw + wd] -= 1u;
-              px[st.newc[f] * nw + wd] += 1u;
-            }
-          }
         if (EWFIELD) {   // accepted: shift the potential cache by the changed charges
           for (int k = g; k < m.N; k += G) {
             double v = fld[k];

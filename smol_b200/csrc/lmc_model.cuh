@@ -21,10 +21,10 @@ struct DevModel {
   int Rstride;     // records per site in the padded table (multiple of 4; pads use class nCls)
   int tabA_len;    // doubles in the phase-A table
   double feature0;
-  // shared-memory blob (staged once per block by TMA): [cls uint4 x nCls][coef double x nCls]
-  // [tabA double x tabA_len][nat double x F][orb OrbDev x nOrb]
+  // shared-memory blob (staged once per block by TMA): [cls uint4 x (nCls + 1)][tabA double x tabA_len]
+  // [nat double x F][orb OrbDev x nOrb][qtab][dtab: speculative kernel only]
   const unsigned char* blob;
-  int blob_bytes, off_coef, off_tabA, off_nat, off_orb, off_qtab;
+  int blob_bytes, off_tabA, off_nat, off_orb, off_qtab;
   const double* ftab;      // global copy of all feature tensors (phase B when K > 1, full evaluation)
   const uint2* site_rec;   // [N][Rstride] (idx0 | idx1<<16, idx2 | cls<<16), padded per site
   const int4* site_seg;    // [N][Sstride] (first, count, orbit, 0); count 0 = padding
