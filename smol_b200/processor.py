@@ -33,6 +33,10 @@ class Processor(ABC):
         self._scmatrix = np.array(supercell_matrix)
         self.size = int(round(abs(np.linalg.det(self._scmatrix))))          # base.py:66
         self.coefs = None if coefficients is None else np.array(coefficients, dtype=np.float64)
+        # species allowed on every supercell site, in the order that defines the occupancy codes.  The reference
+        # reads them off the supercell structure (base.py:68-72, get_allowed_species); a subspace from
+        # smol_b200.lattice provides them directly, and smol_b200.interop hands over a live smol processor's list
+        # through the attribute ``_allowed_species_override`` of the subspace wrapper.
         self.allowed_species = list(cluster_subspace.allowed_species(self._scmatrix))
         self.num_sites = len(self.allowed_species)
         self._engine = None

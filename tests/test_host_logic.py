@@ -197,3 +197,58 @@ def test_bias_tables_follow_the_reference_layout():
                 nxt[site] = code
             np.testing.assert_allclose(ob.compute_bias_change(occ, step), ob.compute_bias(nxt) - ob.compute_bias(occ),
                                        rtol=1e-12, atol=1e-12)
+
+
+def test_interop_extracts_a_smol_like_ensemble():
+    """smol_b200.interop reads only attribute names of the reference interface (processor/base.py:59-107,
+    expansion.py:324, ewald.py:78-101, composite.py:56-59, ensemble.py:219-321).  smol itself cannot be imported
+    here, so stand-ins with exactly those names are used; the packed device tables must equal the ones of the
+    natively built ensemble."""
+    from types import SimpleNamespace
+    import smol_b200 as S
+    from smol_b200 import interop
+
+    sub = M.rocksalt_subspace()
+    scm = np.eye(3, dtype=int) * 2
+    rng = np.random.default_rng(5)
+    it = L.cluster_interaction_tensors(sub, rng.normal(0, 0.05, sub.num_corr_functions))
+    ewm, ewi = L.ewald_matrix(sub, scm)
+    mus = {"Li+": 0.0, "Mn3+": 0.3, "Ti4+": -0.2}
+    native_p = S.CompositeProcessor(sub, scm)
+    native_p.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
+    native_p.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.1, ewald_matrix=ewm, ewald_inds=ewi))
+    native = S.Ensemble(native_p, chemical_potentials=mus)
+
+    # what a live smol ensemble exposes (no allowed_species() on the subspace: the processor carries the list)
+    ref_names = ("orbits", "num_orbits", "num_corr_functions", "orbit_multiplicities", "get_orbit_indices",
+                 "function_total_multiplicities")
+    smol_subspace = SimpleNamespace(**{n: getattr(sub, n) for n in ref_names})
+    allowed = [tuple(sp) for sp in sub.allowed_species(scm)]
+
+    class ClusterDecompositionProcessor:      # names as in smol.moca.processor
+        cluster_subspace, supercell_matrix, allowed_species = smol_subspace, scm, allowed
+        coefs, _interaction_tensors = np.array(sub.orbit_multiplicities, dtype=float), it
+
+    class EwaldProcessor:
+        cluster_subspace, supercell_matrix, allowed_species = smol_subspace, scm, allowed
+        coefs, ewald_matrix, _ewald_inds, _ewald_term = np.array(0.1), ewm, ewi, None
+
+    class CompositeProcessor:
+        cluster_subspace, supercell_matrix, allowed_species = smol_subspace, scm, allowed
+        processors = [ClusterDecompositionProcessor(), EwaldProcessor()]
+
+    subl = [SimpleNamespace(site_space={sp: 1.0 / len(s.species) for sp in s.species}, sites=s.sites,
+                            active_sites=s.active_sites, encoding=s.encoding) for s in native.sublattices]
+    smol_ens = SimpleNamespace(processor=CompositeProcessor(), sublattices=subl, chemical_potentials=mus)
+    got = interop.from_smol_ensemble(smol_ens)
+    np.testing.assert_array_equal(got.natural_parameters, native.natural_parameters)
+    a, b = got.packed_model(), native.packed_model()
+    assert len(a.keep) == len(b.keep)
+    for x, y in zip(a.keep, b.keep):
+        np.testing.assert_array_equal(x, y)
+    for f, ctype in capi.LmcModelDesc._fields_:
+        if ctype is not ctypes.c_void_p:          # scalars; the arrays behind the pointers were compared above
+            assert getattr(a.desc, f) == getattr(b.desc, f), f
+    with pytest.raises(NotImplementedError):
+        interop.from_smol_processor(SimpleNamespace(cluster_subspace=smol_subspace, supercell_matrix=scm,
+                                                    allowed_species=allowed))
