@@ -16,3 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lmc_spec_kernel -s 3 -c 1 \
   -f -o $OUT/${TAG}_spec_cfg2 python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT
+# other BASELINE configs (kernel-only) and their ncu captures:
+#   python scripts/config_bench.py 3 4 5 > gpurun_out/configs.jsonl
+#   ncu --set full --clock-control none --import-source on -k regex:lmc_run_kernel -s 2 -c 1 -f -o gpurun_out/cfg5 python scripts/config_bench.py 5
