@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 9
+#define LMC_ABI_VERSION 10
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -147,6 +147,12 @@ typedef struct LmcWangLandau {
   double* mean_features_dev;  /* [W][num_bins][F] */
   double* mod_factor_dev;     /* [W] */
   int64_t* steps_counter_dev; /* [W] valid-state counter (wanglandau.py:230-232) */
+  /* per-sample traces of the state above (wanglandau.py:247-251), each may be NULL */
+  double* trace_entropy_dev;        /* [S][W][num_bins] */
+  int64_t* trace_histogram_dev;     /* [S][W][num_bins] */
+  int64_t* trace_occurrences_dev;   /* [S][W][num_bins] */
+  double* trace_mean_features_dev;  /* [S][W][num_bins][F] cumulative MEAN features (sums / occurrences if reserved == 1) */
+  double* trace_mod_factor_dev;     /* [S][W] modification factor before the flatness check of the sampled step */
 } LmcWangLandau;
 
 typedef struct LmcRunConfig {

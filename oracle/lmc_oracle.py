@@ -999,6 +999,9 @@ class WangLandau:
                 self._entropy[bin_id] += self._m
                 self._histogram[bin_id] += 1
                 self._occurrences[bin_id] += 1
+        # trace (wanglandau.py:247-251): the arrays themselves -- a reset below shows in the sample -- but a COPY
+        # of the modification factor taken before the flatness check
+        self.trace_mod_factor = self._m
         if self._steps_counter % self.check_period == 0:
             histogram = self._histogram[self._entropy > 0]
             if len(histogram) >= 2 and (histogram > self.flatness * histogram.mean()).all():
@@ -1030,6 +1033,12 @@ def run_sampler(kernels, initial_occupancies, nsteps, thin_by=1):
                features=np.zeros((S, W, feats.shape[1])), enthalpy=np.zeros((S, W, 1)),
                accepted=np.zeros((S, W, 1), dtype=bool),
                n_accepted=np.zeros((S, W), dtype=np.int64))
+    is_wl = all(hasattr(k, "_entropy") for k in kernels)
+    if is_wl:
+        nb, nf = kernels[0]._mean_features.shape
+        out.update(entropy=np.zeros((S, W, nb)), histogram=np.zeros((S, W, nb), dtype=np.int64),
+                   occurrences=np.zeros((S, W, nb), dtype=np.int64), mod_factor=np.zeros((S, W, 1)),
+                   cumulative_mean_features=np.zeros((S, W, nb, nf)))
     has_bias = all(hasattr(t, "bias") for t in traces)
     bias = np.stack([t.bias for t in traces]) if has_bias else None
     if has_bias:
@@ -1052,6 +1061,11 @@ def run_sampler(kernels, initial_occupancies, nsteps, thin_by=1):
         out["enthalpy"][s] = enth
         out["accepted"][s, :, 0] = acc
         out["n_accepted"][s] = nacc
+        if is_wl:
+            for i, k in enumerate(kernels):
+                out["entropy"][s, i], out["histogram"][s, i] = k._entropy, k._histogram
+                out["occurrences"][s, i], out["mod_factor"][s, i, 0] = k._occurrences, k.trace_mod_factor
+                out["cumulative_mean_features"][s, i] = k._mean_features
         if has_bias:
             out["bias"][s] = bias
     return out

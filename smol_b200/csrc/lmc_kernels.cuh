@@ -546,7 +546,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
 
   // Wang-Landau per-walker state
   double* wlS = nullptr; long long* wlH = nullptr; long long* wlO = nullptr; double* wlM = nullptr;
-  double wl_m = 0.0; long long wl_cnt = 0;
+  double wl_m = 0.0, wl_m_traced = 0.0; long long wl_cnt = 0;
   double cur_fb = -1.0, s_cur = 0.0;   // current bin (floor value) and its entropy, kept in registers
   const bool wl_sum = a.wl.reserved != 0;  // mean_features buffer holds per-bin SUMS (update_period == 1)
   const int nb = a.wl.num_bins;
@@ -1063,6 +1063,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
             }
           }
         }
+        wl_m_traced = wl_m;   // trace.mod_factor is copied before the flatness check (wanglandau.py:251)
         if (wl_cnt % a.wl.check_period == 0) {
           __threadfence_block();
           group_sync<G>(gmask);   // lane 0's entropy/histogram updates are visible to the group
@@ -1108,6 +1109,27 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       if (a.tr_acc) a.tr_acc[sw] = accepted ? 1 : 0;
       if (a.tr_nacc) a.tr_nacc[sw] = nacc;
       if (!WLMODE && a.bias_mode && a.tr_bias) a.tr_bias[sw] = bstate[0];
+      if (WLMODE && a.wl.trace_mod_factor_dev) a.wl.trace_mod_factor_dev[sw] = wl_m_traced;
+    }
+    if (WLMODE && (a.wl.trace_entropy_dev || a.wl.trace_histogram_dev || a.wl.trace_occurrences_dev ||
+                   a.wl.trace_mean_features_dev)) {
+      // the walker's Wang-Landau arrays as they stand after the sampled step (wanglandau.py:247-250: the trace
+      // holds the arrays themselves, so a histogram reset of that very step shows)
+      __threadfence_block();
+      group_sync<G>(gmask);
+      for (int b = g; b < nb; b += G) {
+        const long long oc = __ldcg(wlO + b);
+        if (a.wl.trace_entropy_dev) __stcs(a.wl.trace_entropy_dev + sw * nb + b, __ldcg(wlS + b));
+        if (a.wl.trace_histogram_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_histogram_dev) + sw * nb + b, __ldcg(wlH + b));
+        if (a.wl.trace_occurrences_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_occurrences_dev) + sw * nb + b, oc);
+      }
+      if (a.wl.trace_mean_features_dev) {
+        for (int i = g; i < nb * m.F; i += G) {
+          double v = __ldcg(wlM + i);
+          if (wl_sum) { const long long oc = __ldcg(wlO + i / m.F); v = oc > 0 ? v / (double)oc : 0.0; }
+          __stcs(a.wl.trace_mean_features_dev + (sw * nb) * m.F + i, v);
+        }
+      }
     }
     group_sync<G>(gmask);
   }

@@ -151,7 +151,7 @@ class Sampler:
     def __init__(self, ensemble, kernel_type="Metropolis", step_type="swap", nwalkers=1, seeds=None,
                  temperature=None, wl_params=None, usher_kwargs=None, walker_id_base=0,
                  group_size=0, block_threads=0, record_occupancy=True, device=None, kB_=kB,
-                 spec_mode=0, ewald_field="auto", bias_type=None, bias_kwargs=None):
+                 spec_mode=0, ewald_field="auto", bias_type=None, bias_kwargs=None, wl_trace="full"):
         from .engine import LmcEngine
         self.ensemble = ensemble
         self.kernel_type = kernel_type
@@ -263,6 +263,20 @@ class Sampler:
             shapes["temperature"] = ((1,), np.float64)
         if self.bias is not None:
             shapes["bias"] = ((1,), np.float64)
+        # Wang-Landau: the kernel's arrays are part of every sample (wanglandau.py:247-251).  "full" as the
+        # reference, "no_means" without cumulative_mean_features ([bins, F] per walker and sample), "none"
+        if wl_trace not in ("full", "no_means", "none"):
+            raise ValueError("wl_trace must be 'full', 'no_means' or 'none'")
+        self._wl_trace = []
+        if self._kernel == capi.LMC_KERNEL_WANGLANDAU and wl_trace != "none":
+            p = self._wl
+            nb = len(np.arange(p["min_enthalpy"], p["max_enthalpy"], p["bin_size"]))
+            self._wl_trace = [("entropy", (nb,), np.float64), ("histogram", (nb,), np.int64),
+                              ("occurrences", (nb,), np.int64), ("mod_factor", (1,), np.float64)]
+            if wl_trace == "full":
+                self._wl_trace.append(("cumulative_mean_features", (nb, F), np.float64))
+            for name, shape, dtype in self._wl_trace:
+                shapes[name] = (shape, dtype)
         self._container = SampleContainer(ensemble, self.nwalkers, shapes,
                                           dict(ensemble.thermo_boundaries))
 
@@ -275,7 +289,7 @@ class Sampler:
         if kernel_type is None:
             kernel_type = "Metropolis"
         engine_kw = {k: kwargs.pop(k) for k in ("walker_id_base", "group_size", "block_threads", "spec_mode",
-                                                "record_occupancy", "device", "ewald_field", "bias_type", "bias_kwargs") if k in kwargs}
+                                                "record_occupancy", "device", "ewald_field", "bias_type", "bias_kwargs", "wl_trace") if k in kwargs}
         key = kernel_type.lower().replace("_", "").replace("-", "")
         temperature, wl = None, None
         if key == "wanglandau":
@@ -302,13 +316,16 @@ class Sampler:
         """Cached trace slot ``index``: device buffers + page-locked host staging for ``nmax`` samples."""
         import torch
         cache = self.__dict__.setdefault("_slots", {})
-        key = (index, nmax, W, N, F, self.record_occupancy, self.bias is not None)
+        key = (index, nmax, W, N, F, self.record_occupancy, self.bias is not None, len(self._wl_trace))
         if cache.get(index, {}).get("key") != key:
             shapes = {"features": ((nmax, W, F), torch.float64), "enthalpy": ((nmax, W), torch.float64),
                       "accepted": ((nmax, W), torch.uint8), "n_accepted": ((nmax, W), torch.int32),
                       "occupancy": ((nmax, W, N if self.record_occupancy else 0), torch.int8)}
             if self.bias is not None:
                 shapes["bias"] = ((nmax, W), torch.float64)
+            for name, shape, dtype in self._wl_trace:
+                tail = () if name == "mod_factor" else shape
+                shapes[name] = ((nmax, W, *tail), torch.float64 if dtype == np.float64 else torch.int64)
             cache[index] = {"key": key, "shapes": shapes,
                             "dev": {k: torch.empty(sh, dtype=dt, device=dev) for k, (sh, dt) in shapes.items()},
                             "host": None}
@@ -464,6 +481,8 @@ class Sampler:
                           "n_accepted": arrs["n_accepted"][:n]}
                 if self.bias is not None:
                     traces["bias"] = arrs["bias"][:n][:, :, None]
+                for name, _, _ in self._wl_trace:
+                    traces[name] = arrs[name][:n][:, :, None] if name == "mod_factor" else arrs[name][:n]
                 if self.record_occupancy:
                     traces["occupancy"] = arrs["occupancy"][:n]          # int8; int32 on access
                 del arrs
@@ -476,6 +495,9 @@ class Sampler:
                 }
                 if self.bias is not None:
                     traces["bias"] = host["bias"][:n].numpy().copy()[:, :, None]
+                for name, _, _ in self._wl_trace:
+                    v = host[name][:n].numpy().copy()
+                    traces[name] = v[:, :, None] if name == "mod_factor" else v
                 if self.record_occupancy:
                     o = host["occupancy"][:n].numpy()
                     traces["occupancy"] = _fast_copy(o.reshape(n * W, N)).reshape(n, W, N)   # int8; int32 on access
@@ -537,6 +559,11 @@ class Sampler:
                 wl.entropy_dev, wl.histogram_dev = st["entropy"].data_ptr(), st["histogram"].data_ptr()
                 wl.occurrences_dev, wl.mean_features_dev = st["occurrences"].data_ptr(), st["mean_features"].data_ptr()
                 wl.mod_factor_dev, wl.steps_counter_dev = st["mod_factor"].data_ptr(), st["steps_counter"].data_ptr()
+                for name, _, _ in self._wl_trace:
+                    field = {"entropy": "trace_entropy_dev", "histogram": "trace_histogram_dev",
+                             "occurrences": "trace_occurrences_dev", "mod_factor": "trace_mod_factor_dev",
+                             "cumulative_mean_features": "trace_mean_features_dev"}[name]
+                    setattr(wl, field, d[name].data_ptr())
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(main)
             eng.run(cfg)

@@ -299,6 +299,22 @@ def test_wang_landau_flip_trajectory(cuda_device):
         np.testing.assert_allclose(st["mean_features"][w], k._mean_features, rtol=RTOL,
                                    atol=RTOL * np.abs(k._mean_features).max())
     assert (st["mod_factor"] < 1.0).any(), "flatness was never reached; weak test"
+    # per-sample Wang-Landau traces (wanglandau.py:247-251): the arrays after the sampled step, the
+    # modification factor as it was before that step's flatness check
+    g = smp.samples.get_trace_value
+    np.testing.assert_array_equal(g("histogram", flat=False), ref["histogram"])
+    np.testing.assert_array_equal(g("occurrences", flat=False), ref["occurrences"])
+    np.testing.assert_allclose(g("entropy", flat=False), ref["entropy"], rtol=1e-13, atol=0)
+    np.testing.assert_array_equal(g("mod_factor", flat=False), ref["mod_factor"])
+    np.testing.assert_allclose(g("cumulative_mean_features", flat=False), ref["cumulative_mean_features"], rtol=RTOL,
+                               atol=RTOL * np.abs(ref["cumulative_mean_features"]).max())
+    assert len(np.unique(ref["mod_factor"][:, 0, 0])) > 1 and ref["histogram"].shape == (30, W, len(kernels[0]._levels))
+    # the light variants keep the container free of the big arrays
+    smp2 = S.Sampler.from_ensemble(ens_g, wl["min"], wl["max"], wl["bin"], step_type="flip", kernel_type="WangLandau",
+                                   nwalkers=W, seeds=list(seeds), check_period=50, flatness=0.3, wl_trace="no_means")
+    smp2.run(500, occ0, thin_by=50)
+    assert "cumulative_mean_features" not in smp2.samples.traced_values and "entropy" in smp2.samples.traced_values
+    np.testing.assert_array_equal(smp2.samples.get_trace_value("histogram", flat=False), ref["histogram"][:10])
 
 
 @pytest.mark.parametrize("group,factorize", [(8, "1"), (32, "1"), (32, "gather"), (32, "0")])
