@@ -32,6 +32,10 @@
  *   lmc_bias_init, LmcRunConfig.bias_* <- MCBias.compute_bias / compute_bias_change of FugacityBias and
  *                            SquareChargeBias (smol/moca/kernel/bias.py:79-287) and the bias term of the
  *                            Metropolis exponent (kernel/metropolis.py:43-44)
+ *   lmc_ewald_site_kernel <- the reciprocal + real space sums of pymatgen's EwaldSummation behind
+ *                            EwaldTerm.get_ewald_matrix (smol/cofe/extern/ewald.py:102-177): pair kernel between
+ *                            a few origin sites and every site of the supercell (the matrix follows by
+ *                            translation and by the charge products)
  *   lmc_cast_*            <- the int32 occupancy dtype contract (sampler.py:406)
  *
  * Conventions: every function returns 0 on success, <0 on error (message via lmc_last_error);
@@ -50,7 +54,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 10
+#define LMC_ABI_VERSION 11
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -252,6 +256,15 @@ int lmc_run(const LmcModel* model, const LmcRunConfig* cfg, void* stream);
  * record bytes}; dtab_out [NC][L] doubles and rec_out [N][records] x 8 bytes are filled when large enough */
 int lmc_spec_tables_host(const LmcModelDesc* desc, int32_t* info, double* dtab_out, int64_t dtab_cap,
                          uint8_t* rec_out, int64_t rec_cap);
+
+/* Ewald pair kernel (no charges, no self term):
+ *   out_dev[o][k] = (2 pi / V) sum_G coef[G] cos(G . (r_k - r_origin[o])) + 1/2 sum_T' erfc(sqrt(eta) |d + T|) / |d + T|
+ * with d = r_k - r_origin[o], the second sum over the lattice translations T with 1e-8 < |d + T| <= real_cut.
+ * cart_dev [num_sites][3], origins_dev [num_origins] (site indices), gvec_dev [num_g][3], gcoef_dev [num_g]
+ * (= exp(-G^2 / 4 eta) / G^2), tvec_dev [num_t][3]; all device pointers, doubles. */
+int lmc_ewald_site_kernel(const double* cart_dev, int num_sites, const int32_t* origins_dev, int num_origins,
+                          const double* gvec_dev, const double* gcoef_dev, int num_g, const double* tvec_dev, int num_t,
+                          double eta, double real_cut, double volume, double* out_dev, void* stream);
 
 /* number of kernel launches issued by this library since load (for bench accounting) */
 int64_t lmc_launch_count(void);

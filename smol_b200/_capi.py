@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 10
+LMC_ABI_VERSION = 11
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -113,7 +113,7 @@ EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
     "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host", "lmc_model_info",
-    "lmc_ewald_field", "lmc_bias_init",
+    "lmc_ewald_field", "lmc_bias_init", "lmc_ewald_site_kernel",
 )
 
 _LIB = None
@@ -149,6 +149,8 @@ def load():
     lib.lmc_model_info.argtypes = [_P, C.POINTER(C.c_int32), C.c_int]
     lib.lmc_ewald_field.argtypes = [_P, _P, C.c_int, _P, _P]
     lib.lmc_bias_init.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P, _P]
+    lib.lmc_ewald_site_kernel.argtypes = [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_double,
+                                          C.c_double, C.c_double, _P, _P]
     lib.lmc_launch_count.restype = C.c_int64
     lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:

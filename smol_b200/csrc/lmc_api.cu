@@ -662,6 +662,19 @@ extern "C" int lmc_bias_init(const int8_t* occ, int W, int N, int mode, int bw, 
   return 0;
 }
 
+extern "C" int lmc_ewald_site_kernel(const double* cart, int nsites, const int32_t* origins, int norig, const double* gv,
+                                     const double* gc, int ng, const double* tv, int nt, double eta, double rcut, double vol,
+                                     double* out, void* stream) {
+  if (!cart || !origins || !gv || !gc || !tv || !out) return fail("null argument");
+  if (nsites <= 0 || norig <= 0) return 0;
+  if (norig > 65535) return fail("too many origin sites");
+  lmc_ewald_site_kernel_k<<<dim3((unsigned)nsites, (unsigned)norig), 256, 0, (cudaStream_t)stream>>>(
+      cart, origins, gv, gc, ng, tv, nt, eta, rcut, vol, nsites, out);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int lmc_cast_i32_to_i8(const int32_t* src, int8_t* dst, int W, int N, void* stream) {
   const int Npad = lmc_row_stride(N);
   const long long n = (long long)W * Npad;

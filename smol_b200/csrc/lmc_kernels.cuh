@@ -1338,6 +1338,29 @@ __global__ void lmc_bias_init_kernel(const int8_t* __restrict__ occ_g, int W, in
   if (lane == 0) bias[w] = mode == LMC_BIAS_SQUARE_SUM ? -(pen * q) : first;
 }
 
+// Ewald pair kernel between origin site o (blockIdx.y) and site k (blockIdx.x): one block per pair, threads
+// stride over the reciprocal vectors and the real-space translations (cofe/extern/ewald.py:102-177 evaluates
+// the same sums through pymatgen's EwaldSummation).
+__global__ void lmc_ewald_site_kernel_k(const double* __restrict__ cart, const int* __restrict__ origins,
+                                        const double* __restrict__ gv, const double* __restrict__ gc, int ng,
+                                        const double* __restrict__ tv, int nt, double eta, double rcut, double vol,
+                                        int nsites, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int k = blockIdx.x, o = blockIdx.y, r0 = origins[o];
+  const double dx = cart[3 * k] - cart[3 * r0], dy = cart[3 * k + 1] - cart[3 * r0 + 1], dz = cart[3 * k + 2] - cart[3 * r0 + 2];
+  double rec = 0.0, real = 0.0;
+  for (int i = threadIdx.x; i < ng; i += blockDim.x)
+    rec += gc[i] * cos(gv[3 * i] * dx + gv[3 * i + 1] * dy + gv[3 * i + 2] * dz);
+  const double rse = sqrt(eta);
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+    const double x = dx + tv[3 * i], y = dy + tv[3 * i + 1], z = dz + tv[3 * i + 2];
+    const double r = sqrt(x * x + y * y + z * z);
+    if (r > 1e-8 && r <= rcut) real += erfc(rse * r) / r;
+  }
+  const double v = block_sum((2.0 * 3.14159265358979323846 / vol) * rec + 0.5 * real, red);
+  if (threadIdx.x == 0) out[(size_t)o * nsites + k] = v;
+}
+
 __global__ void lmc_cast_i32_i8_kernel(const int* __restrict__ src, int8_t* __restrict__ dst, int W, int N, int Npad) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)W * Npad) return;

@@ -549,16 +549,53 @@ def ewald_indices(subspace: ClusterSubspace, scmatrix):
     return inds, np.array(site_of_row), np.array(charge)
 
 
+def _ewald_rows_numpy(cart, rows, gv, coef, tv, eta, real_cut, vol):
+    """Pair kernel between the origin sites ``rows`` and every site: reciprocal + real space sums."""
+    from scipy.special import erfc
+    k_rows = np.zeros((len(rows), len(cart)))
+    for bi, r0 in enumerate(rows):
+        d = cart - cart[r0]
+        for lo in range(0, len(gv), 4096):
+            ph = d @ gv[lo:lo + 4096].T
+            k_rows[bi] += (2 * math.pi / vol) * (np.cos(ph) @ coef[lo:lo + 4096])
+    rse = math.sqrt(eta)
+    for bi, r0 in enumerate(rows):
+        d = (cart - cart[r0])[:, None, :] + tv[None, :, :]
+        r = np.sqrt(np.sum(d * d, axis=2))
+        mask = (r > 1e-8) & (r <= real_cut)
+        rr = np.where(mask, r, 1.0)
+        k_rows[bi] += 0.5 * np.sum(np.where(mask, erfc(rse * rr) / rr, 0.0), axis=1)
+    return k_rows
+
+
+def _ewald_rows_gpu(cart, rows, gv, coef, tv, eta, real_cut, vol):
+    """The same sums on the GPU (``lmc_ewald_site_kernel``, one block per site pair)."""
+    import torch
+    from . import _capi as capi
+    lib = capi.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def up(a, dt):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    cart_d, rows_d = up(cart, np.float64), up(rows, np.int32)
+    gv_d, gc_d, tv_d = up(gv, np.float64), up(coef, np.float64), up(tv, np.float64)
+    out = torch.empty((len(rows), len(cart)), dtype=torch.float64, device=dev)
+    capi.check(lib.lmc_ewald_site_kernel(cart_d.data_ptr(), len(cart), rows_d.data_ptr(), len(rows), gv_d.data_ptr(),
+                                         gc_d.data_ptr(), len(gv), tv_d.data_ptr(), len(tv), float(eta),
+                                         float(real_cut), float(vol), out.data_ptr(),
+                                         torch.cuda.current_stream(dev).cuda_stream))
+    return out.cpu().numpy()
+
+
 def ewald_matrix(subspace: ClusterSubspace, scmatrix, eta=None, real_cut=None, recip_cut=None,
-                 acc=12.0):
+                 acc=12.0, backend="auto"):
     """Total Ewald pair matrix M (eV) with ``E_total = sum(M[occupied][:, occupied])``.
 
     Same decomposition as pymatgen's ``EwaldSummation.total_energy_matrix`` used by
     ``cofe/extern/ewald.py:159-177``: reciprocal + real (+ point/self term on the diagonal),
     no charged-cell correction.  Units eV with e^2/(4 pi eps0) = 14.399645 eV*A.
+    ``backend``: "gpu" (``lmc_ewald_site_kernel``), "numpy", or "auto" = the GPU when one is present.
     """
-    from scipy.special import erfc
-
     conv = 14.39964547842567
     S = np.asarray(scmatrix, dtype=np.int64).reshape(3, 3)
     L = S @ subspace.prim.lattice
@@ -588,33 +625,38 @@ def ewald_matrix(subspace: ClusterSubspace, scmatrix, eta=None, real_cut=None, r
     keep = (g2 > 1e-12) & (g2 <= recip_cut ** 2)
     gv, g2 = gv[keep], g2[keep]
     coef = np.exp(-g2 / (4 * eta)) / g2
-    k_rows = np.zeros((nb, nsite))
-    for bi, r0 in enumerate(rows):
-        d = cart - cart[r0]
-        for lo in range(0, len(gv), 4096):
-            ph = d @ gv[lo:lo + 4096].T
-            k_rows[bi] += (2 * math.pi / vol) * (np.cos(ph) @ coef[lo:lo + 4096])
     # real-space sum (pairs at zero distance -- the site itself or an overlaid species -- skipped)
     heights = 1.0 / np.linalg.norm(Linv, axis=0)
     mm = np.ceil(real_cut / heights).astype(int) + 1
     ti = np.array(list(itertools.product(*[range(-m_, m_ + 1) for m_ in mm])))
     tv = ti @ L
-    rse = math.sqrt(eta)
-    for bi, r0 in enumerate(rows):
-        d = (cart - cart[r0])[:, None, :] + tv[None, :, :]
-        r = np.sqrt(np.sum(d * d, axis=2))
-        mask = (r > 1e-8) & (r <= real_cut)
-        rr = np.where(mask, r, 1.0)
-        k_rows[bi] += 0.5 * np.sum(np.where(mask, erfc(rse * rr) / rr, 0.0), axis=1)
+    if backend == "auto":
+        try:
+            import torch
+            backend = "gpu" if torch.cuda.is_available() else "numpy"
+        except ImportError:
+            backend = "numpy"
+    if backend not in ("gpu", "numpy"):
+        raise ValueError("backend must be 'auto', 'gpu' or 'numpy'")
+    k_rows = (_ewald_rows_gpu if backend == "gpu" else _ewald_rows_numpy)(cart, rows, gv, coef, tv, eta, real_cut, vol)
     # expand by translation invariance: K[(b,c),(b2,c2)] = k_rows[b][(b2, c2 - c)]
     Sinv = np.linalg.inv(S)
-    table = {tuple(p_): i_ for i_, p_ in enumerate(pts)}
-    cellsub = np.empty((ncell, ncell), dtype=np.int64)  # [c, c2] -> index of pts[c2]-pts[c]
-    for c in range(ncell):
-        fr = (pts - pts[c]) @ Sinv
-        fr = fr - np.floor(fr + 1e-9)
-        wrapped = np.rint(fr @ S).astype(np.int64)
-        cellsub[c] = [table[tuple(w)] for w in wrapped]
+    # [c, c2] -> index of the supercell lattice point pts[c2] - pts[c] (wrapped into the supercell)
+    diff = (pts[None, :, :] - pts[:, None, :]).reshape(-1, 3)
+    fr = diff @ Sinv
+    fr = fr - np.floor(fr + 1e-9)
+    wrapped = np.rint(fr @ S).astype(np.int64)
+    lo_, span = pts.min(axis=0), pts.max(axis=0) - pts.min(axis=0) + 1
+
+    def key(v):
+        v = v - lo_
+        return (v[:, 0] * span[1] + v[:, 1]) * span[2] + v[:, 2]
+    pkeys = key(pts)
+    order = np.argsort(pkeys)
+    pos = np.searchsorted(pkeys[order], key(wrapped))
+    if (pos >= ncell).any() or (pkeys[order][np.minimum(pos, ncell - 1)] != key(wrapped)).any():
+        raise RuntimeError("wrapped lattice point outside the supercell point set")
+    cellsub = order[pos].reshape(ncell, ncell)
     k_full = np.empty((nsite, nsite))
     for b in range(nb):
         for b2 in range(nb):

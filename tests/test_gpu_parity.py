@@ -363,6 +363,20 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
     assert smp.samples.step_efficiency() > 0
 
 
+def test_ewald_matrix_gpu_backend_equals_numpy(cuda_device):
+    """lmc_ewald_site_kernel (reciprocal + real space sums per site pair) against the numpy evaluation of the
+    same sums (cofe/extern/ewald.py:102-177 gets them from pymatgen); a skewed supercell and two sublattices"""
+    from smol_b200 import lattice as L
+    for anions, scm in ((("O2-",), np.eye(3, dtype=int) * 3),
+                        (("O2-", "F-"), np.array([[2, 1, 0], [0, 2, 0], [0, 0, 3]]))):
+        sub = M.rocksalt_subspace(anions=anions)
+        a, ia = L.ewald_matrix(sub, scm, backend="numpy")
+        b, ib = L.ewald_matrix(sub, scm, backend="gpu")
+        np.testing.assert_array_equal(ia, ib)
+        np.testing.assert_allclose(b, a, rtol=0, atol=1e-12 * np.abs(a).max())
+        assert np.abs(b - b.T).max() == 0.0
+
+
 def test_page_locked_tensor_input_equals_array_input(cuda_device):
     """initial occupancies given as a page-locked int32 torch tensor are copied straight from the caller's
     buffer; the chains are those of the ndarray path and the caller's data is left untouched (sampler.py:401)"""
