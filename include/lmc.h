@@ -36,6 +36,10 @@
  *                            EwaldTerm.get_ewald_matrix (smol/cofe/extern/ewald.py:102-177): pair kernel between
  *                            a few origin sites and every site of the supercell (the matrix follows by
  *                            translation and by the charge products)
+ *   lmc_distance_init, LmcRunConfig.dist_* <- DistanceProcessor.compute_feature_vector[_change]
+ *                            (smol/moca/processor/distance.py:133-180, 281-331, 424-472) over
+ *                            ClusterSpaceEvaluator.corr_distances / interaction_distances_from_occupancies
+ *                            (smol/utils/cluster/evaluator.pyx:319-435)
  *   lmc_cast_*            <- the int32 occupancy dtype contract (sampler.py:406)
  *
  * Conventions: every function returns 0 on success, <0 on error (message via lmc_last_error);
@@ -54,7 +58,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 11
+#define LMC_ABI_VERSION 12
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -196,6 +200,18 @@ typedef struct LmcRunConfig {
   double* bias_dev;              /* [W] running bias value, in/out */
   double* bias_sum_dev;          /* [W][bias_rows] running table sums minus intercepts, in/out */
   double* trace_bias_dev;        /* [S][W], may be NULL */
+  /* optional distance processor (processor/distance.py): the features are [L, |f_i - target_i| ...] with f the
+     correlation / cluster-interaction vector per supercell and L the largest orbit diameter up to which all
+     features match the target within dist_tol; natural parameters [-w, W ...].  Metropolis flip / swap steps
+     without Ewald term.  State from lmc_distance_init, kept current by lmc_run. */
+  int32_t dist_mode;             /* 0 off, 1 on */
+  int32_t dist_num_groups;       /* orbit groups of equal diameter, ascending (clusterspace.py:367-381) */
+  double dist_tol;
+  const double* dist_target_dev; /* [F] */
+  const int32_t* dist_group_off_dev;  /* [dist_num_groups + 1] offsets into dist_group_idx_dev */
+  const int32_t* dist_group_idx_dev;  /* feature indices of the groups' orbits */
+  const double* dist_group_diam_dev;  /* [dist_num_groups] */
+  double* dist_vector_dev;       /* [W][F] running correlation / interaction vector per supercell, in/out */
   /* LMC_USHER_COMPOSITE (mcusher.py:307-394): every step picks one sub-usher by weight (random word 4 of the
      step), which proposes with its OWN sublattice probabilities (0 = sublattice not served by it) */
   int32_t comp_num;                                              /* 1..LMC_MAX_COMPOSITE */
@@ -256,6 +272,14 @@ int lmc_run(const LmcModel* model, const LmcRunConfig* cfg, void* stream);
  * record bytes}; dtab_out [NC][L] doubles and rec_out [N][records] x 8 bytes are filled when large enough */
 int lmc_spec_tables_host(const LmcModelDesc* desc, int32_t* info, double* dtab_out, int64_t dtab_cap,
                          uint8_t* rec_out, int64_t rec_cap);
+
+/* Distance processor state of every walker: features_dev [W][F] holds the EXTENSIVE features on entry
+ * (lmc_full_features) and the distance vector on return; vector_dev [W][F] <- features / supercell size;
+ * enthalpy_dev [W] <- natural_parameters . distance vector */
+int lmc_distance_init(const LmcModel* model, int num_walkers, double* features_dev, double* vector_dev,
+                      double* enthalpy_dev, const double* target_dev, double tol, int num_groups,
+                      const int32_t* group_off_dev, const int32_t* group_idx_dev, const double* group_diam_dev,
+                      void* stream);
 
 /* Ewald pair kernel (no charges, no self term):
  *   out_dev[o][k] = (2 pi / V) sum_G coef[G] cos(G . (r_k - r_origin[o])) + 1/2 sum_T' erfc(sqrt(eta) |d + T|) / |d + T|

@@ -174,6 +174,32 @@ def delta_interactions_from_occupancies(orbit_data, num_orbits, inter_tensors, o
     return out
 
 
+def corr_distances_from_occupancies(orbit_data, num_corr, occu_f, occu_i, ref_corr_vector, indices):
+    """evaluator.pyx:319-372: |corr - ref| of the two occupancies, rows [before, after]; column 0 stays 0."""
+    out = np.zeros((2, num_corr))
+    for (oid, bit_id, tensors, strides), idx in zip(orbit_data, indices):
+        J = idx.shape[0]
+        ind_i = (occu_i[idx] * strides[None, :]).sum(axis=1)
+        ind_f = (occu_f[idx] * strides[None, :]).sum(axis=1)
+        for k in range(tensors.shape[0]):
+            out[1, bit_id + k] = abs(_seq_sum(tensors[k, ind_f]) / J - ref_corr_vector[bit_id + k])
+            out[0, bit_id + k] = abs(_seq_sum(tensors[k, ind_i]) / J - ref_corr_vector[bit_id + k])
+    return out
+
+
+def interaction_distances_from_occupancies(orbit_data, num_orbits, inter_tensors, occu_f, occu_i,
+                                           ref_interaction_vector, indices):
+    """evaluator.pyx:374-435."""
+    out = np.zeros((2, num_orbits))
+    for (oid, bit_id, tensors, strides), idx, inter in zip(orbit_data, indices, inter_tensors):
+        J = idx.shape[0]
+        ind_i = (occu_i[idx] * strides[None, :]).sum(axis=1)
+        ind_f = (occu_f[idx] * strides[None, :]).sum(axis=1)
+        out[1, oid] = abs(_seq_sum(inter[ind_f]) / J - ref_interaction_vector[oid])
+        out[0, oid] = abs(_seq_sum(inter[ind_i]) / J - ref_interaction_vector[oid])
+    return out
+
+
 def delta_ewald_single_flip(occu_f, occu_i, ewald_matrix, ewald_indices, site_ind):
     """ewald.pyx:9-59 (sequential k loop, per-k partial ``out_k`` then ``out += out_k``)."""
     add = ewald_indices[site_ind, occu_f[site_ind]]
@@ -355,6 +381,132 @@ class ClusterDecompositionProcessor(_ExpansionBase):
                     ld.orbit_data, self.num_orbits, flat, occu_f, occu_i, ld.ratio, ld.indices)
             occu_i = occu_f
         return delta * self.size
+
+    def compute_property(self, occupancy):
+        return np.dot(self.coefs, self.compute_feature_vector(occupancy))
+
+    def compute_property_change(self, occupancy, flips):
+        return np.dot(self.coefs, self.compute_feature_vector_change(occupancy, flips))
+
+
+def orbits_by_diameter(cluster_subspace):
+    """clusterspace.py:367-381: {diameter rounded to 6 decimals: orbits}, ascending."""
+    from itertools import groupby
+
+    def diam(orb):
+        base = getattr(orb, "base_cluster", None)
+        d = getattr(base, "diameter", None)
+        return float(np.round(orb.diameter if d is None else d, 6))
+    return {size: tuple(orbs) for size, orbs in groupby(sorted(cluster_subspace.orbits, key=diam), key=diam)}
+
+
+class _DistanceMixin:
+    """processor/distance.py:20-200: d = -w L + |W (f - f_T)|_1 as features [L, |f_i - f_T,i| ...] with
+    coefficients [-w, W...]; features are per supercell (NOT multiplied by the size)."""
+
+    def _init_distance(self, target_vector, match_weight, match_tol, target_weights):
+        if match_weight < 0:
+            raise ValueError("The match weight must be a positive number.")          # distance.py:80-81
+        if len(target_weights) != len(target_vector) - 1:
+            raise ValueError("The length of target_weights must be equal to the length of"
+                             f"the target vector minus one {len(target_vector) - 1}.")
+        self.target_vector = np.array(target_vector, dtype=np.float64)
+        self.match_tol = match_tol
+        self.coefs = np.concatenate([[-match_weight], np.asarray(target_weights, dtype=np.float64)])
+        self._by_diameter = orbits_by_diameter(self.cluster_subspace)
+
+    def exact_match_max_diameter(self, distance_vector):
+        """distance.py:309-331 / 452-472."""
+        max_matched_diameter = 0.0
+        for diameter, orbits in self._by_diameter.items():
+            indices = self._orbit_feature_indices(orbits)
+            if np.all(distance_vector[indices] <= self.match_tol):
+                max_matched_diameter = diameter
+            else:
+                break
+        return max_matched_diameter
+
+    def compute_feature_vector(self, occupancy):
+        """distance.py:133-154."""
+        occupancy = np.array(occupancy, dtype=np.int32)
+        fv = self._base_feature_vector(occupancy) / self.size
+        fv[:] = np.abs(fv - self.target_vector)
+        fv[0] = self.exact_match_max_diameter(fv) if self.coefs[0] != 0 else 0.0
+        return fv
+
+    def compute_feature_vector_change(self, occupancy, flips):
+        """distance.py:156-180."""
+        occupancy = np.array(occupancy, dtype=np.int32)
+        dv = self.compute_feature_vector_distances(occupancy, flips)
+        if self.coefs[0] != 0:
+            dv[0, 0] = self.exact_match_max_diameter(dv[0])
+            dv[1, 0] = self.exact_match_max_diameter(dv[1])
+        return dv[1] - dv[0]
+
+
+class CorrelationDistanceProcessor(_DistanceMixin, ClusterExpansionProcessor):
+    """processor/distance.py:209-331."""
+
+    def __init__(self, cluster_subspace, supercell_matrix, target_vector=None, match_weight=1.0,
+                 match_tol=1e-8, target_weights=None, use_ref=False):
+        n = cluster_subspace.num_corr_functions
+        target_vector = np.zeros(n) if target_vector is None else target_vector
+        target_weights = np.ones(n - 1) if target_weights is None else target_weights
+        ClusterExpansionProcessor.__init__(self, cluster_subspace, supercell_matrix, np.zeros(n), use_ref)
+        self._init_distance(target_vector, match_weight, match_tol, target_weights)
+
+    def _base_feature_vector(self, occupancy):
+        return ClusterExpansionProcessor.compute_feature_vector(self, occupancy)
+
+    def _orbit_feature_indices(self, orbits):
+        return [i for orb in orbits for i in range(orb.bit_id, orb.bit_id + len(orb))]
+
+    def compute_feature_vector_distances(self, occupancy, flips):
+        """distance.py:281-307."""
+        occu_f = occupancy.copy()
+        for f in flips:
+            occu_f[f[0]] = f[1]
+        if self._ref is not None:
+            return np.array(self._evaluator.corr_distances_from_occupancies(
+                occu_f, occupancy, np.ascontiguousarray(self.target_vector), self._container))
+        return corr_distances_from_occupancies(self._orbit_data, self.num_corr, occu_f, occupancy,
+                                               self.target_vector, self._indices)
+
+    def compute_property(self, occupancy):
+        return np.dot(self.coefs, self.compute_feature_vector(occupancy))
+
+    def compute_property_change(self, occupancy, flips):
+        return np.dot(self.coefs, self.compute_feature_vector_change(occupancy, flips))
+
+
+class ClusterInteractionDistanceProcessor(_DistanceMixin, ClusterDecompositionProcessor):
+    """processor/distance.py:334-472."""
+
+    def __init__(self, cluster_subspace, supercell_matrix, interaction_tensors, target_vector=None,
+                 match_weight=1.0, match_tol=1e-8, target_weights=None, use_ref=False):
+        n = cluster_subspace.num_orbits
+        target_vector = np.zeros(n) if target_vector is None else target_vector
+        target_weights = np.ones(n - 1) if target_weights is None else target_weights
+        ClusterDecompositionProcessor.__init__(self, cluster_subspace, supercell_matrix, interaction_tensors,
+                                               None, use_ref)
+        self._init_distance(target_vector, match_weight, match_tol, target_weights)
+
+    def _base_feature_vector(self, occupancy):
+        return ClusterDecompositionProcessor.compute_feature_vector(self, occupancy)
+
+    def _orbit_feature_indices(self, orbits):
+        return [orb.id for orb in orbits]
+
+    def compute_feature_vector_distances(self, occupancy, flips):
+        """distance.py:424-450."""
+        occu_f = occupancy.copy()
+        for f in flips:
+            occu_f[f[0]] = f[1]
+        if self._ref is not None:
+            return np.array(self._evaluator.interaction_distances_from_occupancies(
+                occu_f, occupancy, np.ascontiguousarray(self.target_vector), self._container))
+        return interaction_distances_from_occupancies(self._orbit_data, self.num_orbits, self._flat, occu_f,
+                                                      occupancy, self.target_vector, self._indices)
 
     def compute_property(self, occupancy):
         return np.dot(self.coefs, self.compute_feature_vector(occupancy))

@@ -6,10 +6,11 @@ the C ABI of ``include/lmc.h``; this package is the Python host side mirroring
 ``smol.moca``'s Processor / Ensemble / Sampler interface.
 """
 from .ensemble import Ensemble
-from .processor import (ClusterDecompositionProcessor, ClusterExpansionProcessor,
-                        CompositeProcessor, EwaldProcessor)
+from .processor import (ClusterDecompositionProcessor, ClusterExpansionProcessor, ClusterInteractionDistanceProcessor,
+                        CompositeProcessor, CorrelationDistanceProcessor, EwaldProcessor)
 from .sampler import Sampler
 from .sublattice import Sublattice
 
 __all__ = ["Ensemble", "Sampler", "Sublattice", "ClusterExpansionProcessor",
-           "ClusterDecompositionProcessor", "EwaldProcessor", "CompositeProcessor"]
+           "ClusterDecompositionProcessor", "EwaldProcessor", "CompositeProcessor",
+           "CorrelationDistanceProcessor", "ClusterInteractionDistanceProcessor"]

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 11
+LMC_ABI_VERSION = 12
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -100,6 +100,9 @@ class LmcRunConfig(C.Structure):
         ("trace_accepted_dev", _P), ("trace_naccepted_dev", _P), ("ewald_field_dev", _P),
         ("bias_mode", C.c_int32), ("bias_width", C.c_int32), ("bias_rows", C.c_int32), ("bias_penalty", C.c_double),
         ("bias_table_dev", _P), ("bias_dev", _P), ("bias_sum_dev", _P), ("trace_bias_dev", _P),
+        ("dist_mode", C.c_int32), ("dist_num_groups", C.c_int32), ("dist_tol", C.c_double),
+        ("dist_target_dev", _P), ("dist_group_off_dev", _P), ("dist_group_idx_dev", _P),
+        ("dist_group_diam_dev", _P), ("dist_vector_dev", _P),
         ("comp_num", C.c_int32), ("comp_usher", C.c_int32 * LMC_MAX_COMPOSITE),
         ("comp_cum", C.c_double * LMC_MAX_COMPOSITE),
         ("comp_sl_cum", (C.c_double * LMC_MAX_SUBLATTICES) * LMC_MAX_COMPOSITE),
@@ -113,7 +116,7 @@ EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
     "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host", "lmc_model_info",
-    "lmc_ewald_field", "lmc_bias_init", "lmc_ewald_site_kernel",
+    "lmc_ewald_field", "lmc_bias_init", "lmc_ewald_site_kernel", "lmc_distance_init",
 )
 
 _LIB = None
@@ -151,6 +154,7 @@ def load():
     lib.lmc_bias_init.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P, _P]
     lib.lmc_ewald_site_kernel.argtypes = [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_double,
                                           C.c_double, C.c_double, _P, _P]
+    lib.lmc_distance_init.argtypes = [_P, C.c_int, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P]
     lib.lmc_launch_count.restype = C.c_int64
     lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:

@@ -58,6 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for wl in (0, 1):
             jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"),
                          os.path.join(objdir, f"lmc_run_g{g}_wl{wl}.o"), [f"-DLMC_G={g}", f"-DLMC_WL={wl}"], force))
+    jobs.append((os.path.join(CSRC, "lmc_run_dist_inst.cu"), os.path.join(objdir, "lmc_run_dist.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst.cu"), os.path.join(objdir, "lmc_spec.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst2.cu"), os.path.join(objdir, "lmc_spec2.o"), [], force))
     log = []

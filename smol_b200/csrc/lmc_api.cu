@@ -662,6 +662,19 @@ extern "C" int lmc_bias_init(const int8_t* occ, int W, int N, int mode, int bw, 
   return 0;
 }
 
+extern "C" int lmc_distance_init(const LmcModel* mdl, int W, double* feat, double* vec, double* enth, const double* target,
+                                 double tol, int ngrp, const int32_t* goff, const int32_t* gidx, const double* gdiam,
+                                 void* stream) {
+  if (!mdl || !feat || !vec || !target || !goff || !gidx || !gdiam) return fail("null argument");
+  if (W <= 0) return 0;
+  const DevModel& m = mdl->dm;
+  lmc_distance_init_kernel<<<(W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(W, m.F, m.size, mdl->nat_dev, feat, vec, enth, target,
+                                                                              tol, ngrp, goff, gidx, gdiam);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int lmc_ewald_site_kernel(const double* cart, int nsites, const int32_t* origins, int norig, const double* gv,
                                      const double* gc, int ng, const double* tv, int nt, double eta, double rcut, double vol,
                                      double* out, void* stream) {
@@ -780,7 +793,15 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     if (c->bias_rows < 1 || c->bias_rows > LMC_MAX_BIAS_ROWS || (c->bias_mode == LMC_BIAS_TABLE_SUM && c->bias_rows != 1))
       return fail("bias_rows out of range");
   }
-  const bool spec_ok = m.spOK && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
+  const bool dist = c->dist_mode != 0;
+  if (dist) {
+    if (c->kernel != LMC_KERNEL_METROPOLIS || (c->usher != LMC_USHER_FLIP && c->usher != LMC_USHER_SWAP) || ewald || m.muW)
+      return fail("distance processors run Metropolis flip / swap steps without Ewald or chemical-potential terms");
+    if (!c->dist_target_dev || !c->dist_group_off_dev || !c->dist_group_idx_dev || !c->dist_group_diam_dev || !c->dist_vector_dev)
+      return fail("distance processor pointers must not be null");
+    if (c->bias_mode != LMC_BIAS_NONE) return fail("bias terms are not combined with distance processors");
+  }
+  const bool spec_ok = m.spOK && !dist && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
                        (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
   if (spec_mode == 2 && !spec_ok)
     return fail("the speculative kernel supports unbiased Metropolis flip/swap steps (an Ewald term through ewald_field_dev only)");
@@ -810,7 +831,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     else G = 8;
   }
   if (c->usher == LMC_USHER_TABLEFLIP) G = (G >= 16) ? 32 : 8;
-  if (c->usher == LMC_USHER_COMPOSITE || c->usher == LMC_USHER_MULTISTEP) G = 32;
+  if (c->usher == LMC_USHER_COMPOSITE || c->usher == LMC_USHER_MULTISTEP || dist) G = 32;
   if (G != 4 && G != 8 && G != 16 && G != 32) return fail("group_size must be 4, 8, 16 or 32");
   int threads = c->block_threads;
   if (const char* e = getenv("LMC_BLOCK_THREADS")) { if (threads == 0) threads = atoi(e); }
@@ -863,7 +884,11 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
-  a.walker_smem = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
+  a.off_dist = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
+  a.walker_smem = a.off_dist + (dist ? ((3 * m.F * 8 + 15) & ~15) : 0);   // distance processor: vector, delta, new distances
+  a.dist_ngrp = c->dist_num_groups; a.dist_tol = c->dist_tol; a.dist_target = c->dist_target_dev;
+  a.dist_grp_off = c->dist_group_off_dev; a.dist_grp_idx = c->dist_group_idx_dev; a.dist_grp_diam = c->dist_group_diam_dev;
+  a.dist_vec = c->dist_vector_dev;
   // staged tables: the speculative kernel takes the whole blob, the classic kernels stop before its difference table
   const size_t blob = ((size_t)(use_spec ? m.blob_bytes : m.off_dtab) + 15) & ~size_t(15);
   size_t smem = 0;
@@ -906,6 +931,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   spec_wide = spec_wide && threads == 448;
   if (use_spec && (field || spec_wide)) rc = launch_spec_x(m, a, m.kone != 0, c->usher, field, spec_wide, lc);
   else if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, spec_lists, lc);
+  else if (dist) rc = launch_run_dist(m, a, m.kone != 0, c->usher, lc);
   else switch (G) {
     case 4: rc = (wl ? launch_run_wl_g4 : launch_run_g4)(m, a, m.kone != 0, ewmode, c->usher, lc); break;
     case 8: rc = (wl ? launch_run_wl_g8 : launch_run_g8)(m, a, m.kone != 0, ewmode, c->usher, lc); break;

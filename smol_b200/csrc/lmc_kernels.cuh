@@ -476,7 +476,10 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // EWMODE: 0 no Ewald term, 1 matrix rows gathered at every flip (flip_ewald), 2 potential cache (ewald_qd).
 // A template parameter, not a run-time switch: the table-flip variants are instruction-fetch bound and
 // carry one Ewald path each.
-template <int G, bool KONE, int EWMODE, int USHER, bool WLMODE>
+// DIST: distance processor (processor/distance.py): the running features are the distance vector
+// [L, |f_i - target_i| ...]; every proposal folds its per-record differences into the change of the
+// correlation / interaction vector f (phase B for each proposal, not only on accept) to get the new distances.
+template <int G, bool KONE, int EWMODE, int USHER, bool WLMODE, bool DIST = false>
 __global__ void __launch_bounds__((EWMODE || WLMODE || USHER >= LMC_USHER_TABLEFLIP) ? 256 : 128,
                                   (EWMODE || WLMODE || USHER >= LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7))
 lmc_run_kernel(const DevModel m, const RunArgs a) {
@@ -561,6 +564,11 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? __ldcg(wlS + (int)cur_fb) : 0.0;
   }
 
+  double* dvec = reinterpret_cast<double*>(priv + a.off_dist);   // DIST: [vector F][delta F][new distances F]
+  if (DIST) {
+    for (int f = g; f < m.F; f += G) dvec[f] = a.dist_vec[(size_t)w * m.F + f];
+    group_sync<G>(gmask);
+  }
   // bias term of the exponent (bias.py; Metropolis only): running value and table sum, all lanes alike
   // (kept in the walker's shared-memory slab, not in registers: the swap / flip variants are register capped)
   double* bstate = reinterpret_cast<double*>(priv + a.off_bias);
@@ -922,6 +930,40 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       double dEw = 0.0;
       if (EWALD) { dEw = group_sum<G>(acc_ew, gmask); dH += nat_ew * dEw; }
       if (MU_POSSIBLE && m.muW) dH += nat_mu * dmu;
+      double dist_L = 0.0;
+      if (DIST) {
+        // DistanceProcessor.compute_feature_vector_change (distance.py:156-180): distances of the vector with
+        // the flips applied minus the current ones; the vector is per supercell (not times the size)
+        double* dd = dvec + m.F;
+        double* dn = dvec + 2 * m.F;
+        for (int f = g; f < m.F; f += G) dd[f] = 0.0;
+        group_sync<G>(gmask);   // stash of this proposal complete, delta zeroed
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          if (f < st.n) {
+            flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, dd, g, load_segment<G>(m, st.site[f], g));
+            group_sync<G>(gmask);
+          }
+        double part = 0.0;
+        const double inv_size = 1.0 / (double)m.size;
+        for (int f = g; f < m.F; f += G)
+          if (f > 0) {
+            const double v = fabs(dvec[f] + dd[f] * inv_size - __ldg(a.dist_target + f));
+            dn[f] = v;
+            part += t.nat[f] * (v - feat[f]);
+          }
+        group_sync<G>(gmask);
+        if (t.nat[0] != 0.0) {   // exact_match_max_diameter, distance.py:309-331, 452-472
+          for (int q = 0; q < a.dist_ngrp; ++q) {
+            bool ok = true;
+            for (int i = __ldg(a.dist_grp_off + q); i < __ldg(a.dist_grp_off + q + 1); ++i)
+              ok = ok && dn[__ldg(a.dist_grp_idx + i)] <= a.dist_tol;
+            if (!ok) break;
+            dist_L = __ldg(a.dist_grp_diam + q);
+          }
+        }
+        dH = group_sum<G>(part, gmask) + t.nat[0] * (dist_L - feat[0]);
+      }
 
       // ------------------------------ accept --------------------------------------------
       double new_fb = cur_fb, s_new = s_cur;
@@ -976,11 +1018,22 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       group_sync<G>(gmask);   // every lane has finished reading the occupancy / caches of this step
       if (accepted) {
         // MCKernel._do_accept_step (kernel/base.py:327-343) + trace accumulation (sampler.py:204-207)
+        if (DIST) {
+          const double inv_size = 1.0 / (double)m.size;
+          for (int f = g; f < m.F; f += G) {
+            dvec[f] += dvec[m.F + f] * inv_size;
+            feat[f] = f > 0 ? dvec[2 * m.F + f] : dist_L;
+          }
+        } else {
 #pragma unroll
-        for (int f = 0; f < MF; ++f)
-          if (f < st.n)
-            flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g,
-                                   (SEGPRE && f == 0) ? seg0 : ((SEGPRE && f == 1) ? seg1 : load_segment<G>(m, st.site[f], g)));
+          for (int f = 0; f < MF; ++f)
+            if (f < st.n) {
+              // (lanes of different flips may own the same feature: one flip after the other)
+              if (f > 0) group_sync<G>(gmask);
+              flip_features<G, KONE>(m, t, st.site[f], stash0 + f * stash_stride, feat, g,
+                                     (SEGPRE && f == 0) ? seg0 : ((SEGPRE && f == 1) ? seg1 : load_segment<G>(m, st.site[f], g)));
+            }
+        }
         if (g == 0) {
           if (deferred1) occ[st.site[I1]] = (uint8_t)st.newc[I1];
           if (EWGATHER && st.n > 0)   // the last flip enters the Ewald cache on accept only
@@ -1137,6 +1190,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // ------------------------------ final state ---------------------------------------------
   for (int i = g; i < m.N; i += G) a.occ[(size_t)w * m.Npad + i] = (int8_t)occ[i];
   for (int f = g; f < m.F; f += G) a.features[(size_t)w * m.F + f] = feat[f];
+  if (DIST)
+    for (int f = g; f < m.F; f += G) a.dist_vec[(size_t)w * m.F + f] = dvec[f];
   if (g == 0) {
     a.enthalpy[w] = enth;
     if (!WLMODE && a.bias_mode) {
@@ -1336,6 +1391,35 @@ __global__ void lmc_bias_init_kernel(const int8_t* __restrict__ occ_g, int W, in
     if (r == 0) first = c;
   }
   if (lane == 0) bias[w] = mode == LMC_BIAS_SQUARE_SUM ? -(pen * q) : first;
+}
+
+// DistanceProcessor.compute_feature_vector (distance.py:133-154) from the extensive features of
+// lmc_full_kernel: one thread per walker (F is a few tens)
+__global__ void lmc_distance_init_kernel(int W, int F, int size, const double* __restrict__ nat, double* __restrict__ feat,
+                                         double* __restrict__ vec, double* __restrict__ enth, const double* __restrict__ target,
+                                         double tol, int ngrp, const int* __restrict__ goff, const int* __restrict__ gidx,
+                                         const double* __restrict__ gdiam) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  double* fw = feat + (size_t)w * F;
+  double* vw = vec + (size_t)w * F;
+  double e = 0.0;
+  for (int f = 0; f < F; ++f) {
+    const double v = fw[f] / (double)size;
+    vw[f] = v;
+    fw[f] = fabs(v - target[f]);
+    if (f > 0) e += nat[f] * fw[f];
+  }
+  double L = 0.0;
+  if (nat[0] != 0.0)
+    for (int q = 0; q < ngrp; ++q) {
+      bool ok = true;
+      for (int i = goff[q]; i < goff[q + 1]; ++i) ok = ok && fw[gidx[i]] <= tol;
+      if (!ok) break;
+      L = gdiam[q];
+    }
+  fw[0] = L;
+  if (enth) enth[w] = e + nat[0] * L;
 }
 
 // Ewald pair kernel between origin site o (blockIdx.y) and site k (blockIdx.x): one block per pair, threads

@@ -98,6 +98,15 @@ struct RunArgs {
   double* bias;                // [W] running bias value
   double* bias_sum;            // [W][bias_rows] running table sums
   double* tr_bias;             // [S][W]
+  // distance processor (lmc.h): target vector, match tolerance, orbit groups by diameter, running vector
+  int dist_ngrp;
+  double dist_tol;
+  const double* dist_target;
+  const int* dist_grp_off;
+  const int* dist_grp_idx;
+  const double* dist_grp_diam;
+  double* dist_vec;            // [W][F]
+  int off_dist;                // shared memory: [vector F][delta F][new distances F] doubles
   int comp_num, comp_usher[LMC_MAX_COMPOSITE];                   // composite usher, see lmc.h
   double comp_cum[LMC_MAX_COMPOSITE];
   double comp_sl_cum[LMC_MAX_COMPOSITE][LMC_MAX_SUBLATTICES];

@@ -140,6 +140,30 @@ class LmcEngine:
         capi.check(self.lib.lmc_ewald_field(self.handle, occ_dev.data_ptr(), W, out.data_ptr(), self._stream()))
         return out
 
+    def distance_tables(self, processor):
+        """device copies of a DistanceProcessor's target vector and orbit groups (cached per engine)"""
+        torch = _torch()
+        if getattr(self, "_dist_tabs", None) is None or self._dist_tabs[0] is not processor:
+            target, tol, goff, gidx, gdiam = processor.distance_tables()
+            up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)   # noqa: E731
+            self._dist_tabs = (processor, dict(target=up(target, np.float64), tol=float(tol), goff=up(goff, np.int32),
+                                               gidx=up(gidx if len(gidx) else np.zeros(1), np.int32),
+                                               gdiam=up(gdiam if len(gdiam) else np.zeros(1), np.float64),
+                                               ngrp=len(gdiam)))
+        return self._dist_tabs[1]
+
+    def distance_init(self, processor, feat, enth=None):
+        """extensive features ``feat [W, F]`` -> distance vectors in place; returns the vectors per supercell."""
+        torch = _torch()
+        d = self.distance_tables(processor)
+        W = feat.shape[0]
+        vec = torch.empty_like(feat)
+        capi.check(self.lib.lmc_distance_init(self.handle, W, feat.data_ptr(), vec.data_ptr(),
+                                              enth.data_ptr() if enth is not None else None, d["target"].data_ptr(),
+                                              d["tol"], d["ngrp"], d["goff"].data_ptr(), d["gidx"].data_ptr(),
+                                              d["gdiam"].data_ptr(), self._stream()))
+        return vec
+
     def run(self, cfg: capi.LmcRunConfig):
         capi.check(self.lib.lmc_run(self.handle, C.byref(cfg), self._stream()))
 

@@ -197,6 +197,105 @@ class ClusterDecompositionProcessor(Processor):
         return dict(expansion=self._exp)
 
 
+def _orbits_by_diameter(cluster_subspace):
+    """``clusterspace.py:367-381``: orbits grouped by diameter (rounded to 6 decimals), ascending."""
+    obd = getattr(cluster_subspace, "orbits_by_diameter", None)
+    if obd is not None:
+        return dict(obd)
+    from itertools import groupby
+
+    def diam(orb):
+        base = getattr(orb, "base_cluster", None)
+        d = getattr(base, "diameter", None)
+        return float(np.round(orb.diameter if d is None else d, 6))
+    return {size: tuple(orbs) for size, orbs in groupby(sorted(cluster_subspace.orbits, key=diam), key=diam)}
+
+
+class DistanceProcessor:
+    """Mixin of ``smol/moca/processor/distance.py:20-200``: features ``[L, |f_i - f_T,i| ...]`` with ``f`` the
+    correlation / cluster-interaction vector PER SUPERCELL, ``L`` the largest orbit diameter up to which all
+    features match the target within ``match_tol``, coefficients ``[-match_weight, target_weights ...]``.
+
+    On the device the running vector ``f`` is kept per walker and every proposal folds its per-record differences
+    into the change of ``f`` (``LmcRunConfig.dist_*``); the reference re-evaluates both full vectors per proposal
+    (``evaluator.pyx:319-435``)."""
+
+    def _init_distance(self, target_vector, match_weight, match_tol, target_weights, feature_indices):
+        if match_weight < 0:                                                     # distance.py:80-81
+            raise ValueError("The match weight must be a positive number.")
+        if len(target_weights) != len(target_vector) - 1:                       # distance.py:83-88
+            raise ValueError(f"The length of target_weights must be equal to the length ofthe target vector minus "
+                             f"one {len(target_vector) - 1}. \nGot {len(target_weights)} instead.")
+        self.target_vector = np.array(target_vector, dtype=np.float64)
+        self.match_tol = float(match_tol)
+        self.coefs = np.concatenate([[-float(match_weight)], np.asarray(target_weights, dtype=np.float64)])
+        groups = _orbits_by_diameter(self._subspace)
+        self._group_diam = np.array(list(groups.keys()), dtype=np.float64)
+        idx = [np.array(feature_indices(orbs), dtype=np.int32) for orbs in groups.values()]
+        self._group_off = np.concatenate([[0], np.cumsum([len(i) for i in idx])]).astype(np.int32)
+        self._group_idx = np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, dtype=np.int32)
+
+    def distance_tables(self):
+        """(target, tol, group offsets, group feature indices, group diameters) for ``LmcRunConfig.dist_*``."""
+        return self.target_vector, self.match_tol, self._group_off, self._group_idx, self._group_diam
+
+    def exact_match_max_diameter(self, distance_vector):
+        """``distance.py:309-331, 452-472`` (host helper for a vector already on the host)."""
+        out = 0.0
+        for q, diam in enumerate(self._group_diam):
+            ids = self._group_idx[self._group_off[q]:self._group_off[q + 1]]
+            if np.all(np.asarray(distance_vector)[ids] <= self.match_tol):
+                out = float(diam)
+            else:
+                break
+        return out
+
+    def compute_feature_vector_batch(self, occupancies):
+        """``[W, N]`` occupancies -> ``[W, F]`` distance vectors (``distance.py:133-154``) on the device."""
+        eng = self._get_engine()
+        occ = eng.upload_occupancy(_as_occu(occupancies).reshape(-1, self.num_sites))
+        feat, _ = eng.full_features(occ)
+        eng.distance_init(self, feat)
+        return feat.cpu().numpy()
+
+    def compute_feature_vector_change_batch(self, occupancies, sites, codes):
+        """distance vectors with the flips applied minus the current ones (``distance.py:156-180``)"""
+        occ = _as_occu(occupancies).reshape(-1, self.num_sites)
+        sites, codes = np.atleast_2d(sites), np.atleast_2d(codes)
+        nxt = occ.copy()
+        for k in range(sites.shape[1]):
+            nxt[np.arange(len(occ)), sites[:, k]] = codes[:, k]
+        both = self.compute_feature_vector_batch(np.concatenate([occ, nxt]))
+        return both[len(occ):] - both[:len(occ)]
+
+
+class CorrelationDistanceProcessor(DistanceProcessor, ClusterExpansionProcessor):
+    """``distance.py:209-331``."""
+
+    def __init__(self, cluster_subspace, supercell_matrix, target_vector=None, match_weight=1.0, match_tol=1e-8,
+                 target_weights=None, use_concentration=False, **processor_kwargs):
+        n = cluster_subspace.num_corr_functions
+        target_vector = np.zeros(n) if target_vector is None else target_vector          # distance.py:262-264
+        target_weights = np.ones(n - 1) if target_weights is None else target_weights
+        ClusterExpansionProcessor.__init__(self, cluster_subspace, supercell_matrix, np.zeros(n), **processor_kwargs)
+        self._init_distance(target_vector, match_weight, match_tol, target_weights,
+                            lambda orbs: [i for o in orbs for i in range(o.bit_id, o.bit_id + len(o))])
+
+
+class ClusterInteractionDistanceProcessor(DistanceProcessor, ClusterDecompositionProcessor):
+    """``distance.py:334-472``."""
+
+    def __init__(self, cluster_subspace, supercell_matrix, interaction_tensors, target_vector=None,
+                 match_weight=1.0, match_tol=1e-8, target_weights=None, use_concentration=False,
+                 **processor_kwargs):
+        n = cluster_subspace.num_orbits
+        target_vector = np.zeros(n) if target_vector is None else target_vector
+        target_weights = np.ones(n - 1) if target_weights is None else target_weights
+        ClusterDecompositionProcessor.__init__(self, cluster_subspace, supercell_matrix, interaction_tensors,
+                                               **processor_kwargs)
+        self._init_distance(target_vector, match_weight, match_tol, target_weights, lambda orbs: [o.id for o in orbs])
+
+
 class EwaldProcessor(Processor):
     """``smol/moca/processor/ewald.py:26-208``.
 

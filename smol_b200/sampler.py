@@ -428,6 +428,12 @@ class Sampler:
             raise RuntimeError("ewald_field=True needs an Ewald term whose matrix factorises as q_i q_j K[site_i, site_j]")
         if use_field:
             self._ew_field = eng.ewald_field(self._occ_dev, out=self._ew_field)
+        from .processor import DistanceProcessor
+        dist_proc = self.ensemble.processor if isinstance(self.ensemble.processor, DistanceProcessor) else None
+        dist_vec = None
+        if dist_proc is not None:
+            # distance processors: features = distance vector, running correlation vector kept beside it
+            dist_vec = eng.distance_init(dist_proc, feat, enth)
         if self.bias is not None:
             # initial bias of the starting occupancies (base.py:362-363), then kept current by the kernel
             if self._bias_dev is None:
@@ -528,6 +534,12 @@ class Sampler:
             cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
             cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
             cfg.ewald_field_dev = self._ew_field.data_ptr() if use_field else None
+            if dist_proc is not None:
+                dt = eng.distance_tables(dist_proc)
+                cfg.dist_mode, cfg.dist_num_groups, cfg.dist_tol = 1, dt["ngrp"], dt["tol"]
+                cfg.dist_target_dev, cfg.dist_group_off_dev = dt["target"].data_ptr(), dt["goff"].data_ptr()
+                cfg.dist_group_idx_dev, cfg.dist_group_diam_dev = dt["gidx"].data_ptr(), dt["gdiam"].data_ptr()
+                cfg.dist_vector_dev = dist_vec.data_ptr()
             if self._multistep is not None:
                 code, lens, cum = self._multistep
                 cfg.ms_usher, cfg.ms_num = code, len(lens)

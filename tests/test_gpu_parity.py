@@ -401,6 +401,64 @@ def test_page_locked_tensor_input_equals_array_input(cuda_device):
 
 
 # ---------------------------------------------------------------------------------------------
+# distance processors (processor/distance.py): the sampler minimises the distance to a target vector
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,usher", [("correlation", "swap"), ("correlation", "flip"), ("interaction", "swap")])
+def test_distance_processor_trajectory(cuda_device, kind, usher):
+    """features [L, |f_i - target_i| ...] per supercell; the target is the vector of another occupancy of the
+    same composition, so exact matches (L > 0) occur; single-call API and the whole chain against the oracle
+    restatement of distance.py / evaluator.pyx:319-435"""
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 2
+    rng = np.random.default_rng(12)
+    W = 6
+    occ0 = M.random_occupancies(sub, scm, W + 1, seed=21, balanced=True)
+    tgt_occ, occ0 = occ0[-1], occ0[:W]
+    if kind == "correlation":
+        base = O.ClusterExpansionProcessor(sub, scm, np.zeros(sub.num_corr_functions))
+        target = base.compute_feature_vector(tgt_occ) / base.size
+        weights = rng.uniform(0.5, 1.5, len(target) - 1)
+        gpu_p = S.CorrelationDistanceProcessor(sub, scm, target_vector=target, match_weight=0.7, match_tol=1e-8,
+                                               target_weights=weights)
+        ora_p = O.CorrelationDistanceProcessor(sub, scm, target_vector=target, match_weight=0.7, match_tol=1e-8,
+                                               target_weights=weights)
+    else:
+        it = L.cluster_interaction_tensors(sub, M.fcc_coefs(sub))
+        base = O.ClusterDecompositionProcessor(sub, scm, it)
+        target = base.compute_feature_vector(tgt_occ) / base.size
+        weights = rng.uniform(0.5, 1.5, len(target) - 1)
+        gpu_p = S.ClusterInteractionDistanceProcessor(sub, scm, it, target_vector=target, match_weight=0.7,
+                                                      target_weights=weights)
+        ora_p = O.ClusterInteractionDistanceProcessor(sub, scm, it, target_vector=target, match_weight=0.7,
+                                                      target_weights=weights)
+    # single calls
+    for o in (occ0[0], tgt_occ):
+        np.testing.assert_allclose(gpu_p.compute_feature_vector(o), ora_p.compute_feature_vector(o), rtol=0, atol=1e-12)
+    assert gpu_p.compute_feature_vector(tgt_occ)[0] > 0            # the target occupancy matches every diameter
+    flips = [(1, int(1 - occ0[0][1])), (5, int(1 - occ0[0][5]))]
+    np.testing.assert_allclose(gpu_p.compute_feature_vector_change(occ0[0], flips),
+                               ora_p.compute_feature_vector_change(occ0[0], flips), rtol=0, atol=1e-12)
+    ens_g = S.Ensemble(gpu_p)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices))
+
+    seeds = np.arange(800, 800 + W)
+    # kB T comparable to the distance differences: accepts and rejects both occur, matches are found
+    smp, ref, _ = _run_both(ens_g, ens_o, usher, W, 1200, 40, occ0, seeds, T=400.0)
+    _compare_traces(smp, ref)
+    feats = smp.samples.get_feature_vectors(flat=False)
+    assert 0 < smp.samples.step_efficiency() < 1
+    if usher == "swap":
+        assert (feats[:, :, 0] > 0).any(), "no exact match of the point/pair terms was ever reached; weak test"
+    with pytest.raises(ValueError):
+        S.CorrelationDistanceProcessor(sub, scm, target_vector=np.zeros(sub.num_corr_functions), match_weight=-1.0)
+
+
+# ---------------------------------------------------------------------------------------------
 # composite usher (mcusher.py:307-394)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("hybrid", [False, True])

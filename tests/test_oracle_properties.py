@@ -170,3 +170,38 @@ def test_table_flip_samples_neutral_states_uniformly():
     # compositions (Li,Zr,Mn|O,F): (2,1,0|3,0) 3 states, (2,0,1|2,1) 9 states, (3,0,0|0,3) 1 state
     assert len(cnt) == 13
     np.testing.assert_allclose(freq, 1.0, atol=0.15)
+
+
+def test_distance_processors_match_the_compiled_reference_evaluators():
+    """oracle restatement of evaluator.pyx:319-435 + processor/distance.py against the reference's own compiled
+    corr_distances / interaction_distances_from_occupancies (oracle/_ref); change == difference of vectors"""
+    from oracle import lmc_oracle as O
+    from smol_b200 import lattice as L
+    sub = M.rocksalt_subspace()
+    scm = np.eye(3, dtype=int) * 2
+    rng = np.random.default_rng(1)
+    occs = M.random_occupancies(sub, scm, 4, seed=3)
+    tv = rng.normal(0, 0.2, sub.num_corr_functions)
+    tv[0] = 1.0
+    it = L.cluster_interaction_tensors(sub, rng.normal(0, 0.05, sub.num_corr_functions))
+    tvi = rng.normal(0, 0.05, sub.num_orbits)
+    have_ref = O.load_ref() is not None
+    for make in (lambda r: O.CorrelationDistanceProcessor(sub, scm, target_vector=tv, match_weight=1.0, use_ref=r),
+                 lambda r: O.ClusterInteractionDistanceProcessor(sub, scm, it, target_vector=tvi, use_ref=r)):
+        port = make(False)
+        ref = make(True) if have_ref else None
+        for occ in occs:
+            flips = [(0, int((occ[0] + 1) % 3)), (3, int((occ[3] + 2) % 3))]
+            fv, dv = port.compute_feature_vector(occ), port.compute_feature_vector_change(occ, flips)
+            nxt = occ.copy()
+            for s_, c_ in flips:
+                nxt[s_] = c_
+            np.testing.assert_allclose(dv, port.compute_feature_vector(nxt) - fv, rtol=0, atol=1e-13)
+            if ref is not None:
+                np.testing.assert_allclose(fv, ref.compute_feature_vector(occ), rtol=1e-12, atol=1e-14)
+                np.testing.assert_allclose(dv, ref.compute_feature_vector_change(occ, flips), rtol=0, atol=1e-13)
+    # exact matches: the target taken from an occupancy gives L = the largest diameter
+    base = O.ClusterExpansionProcessor(sub, scm, np.zeros(sub.num_corr_functions))
+    p = O.CorrelationDistanceProcessor(sub, scm, target_vector=base.compute_feature_vector(occs[0]) / base.size)
+    assert p.compute_feature_vector(occs[0])[0] == max(O.orbits_by_diameter(sub))
+    assert p.compute_feature_vector(occs[1])[0] < max(O.orbits_by_diameter(sub))
