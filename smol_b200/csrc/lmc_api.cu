@@ -399,6 +399,8 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
   bool kone = true;
   if (host_orbits(d, orbs, tabA, kone)) { lmc_model_destroy(mdl); return -1; }
   m.kone = kone ? 1 : 0;
+  m.Kmax = 1;
+  for (const OrbDev& o : orbs) m.Kmax = std::max(m.Kmax, o.K);
   const int tabA_len = (int)tabA.size();
   m.tabA_len = tabA_len;
   std::vector<double> qtab;
@@ -549,14 +551,39 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       for (int r = (int)(b - a); r < m.Rstride; ++r) dst[r * 4 + 3] = (uint16_t)m.nCls;
     }
     UP(uint2, rec.data(), (size_t)m.N * m.Rstride, m.site_rec);
-    int smax = 1;
-    for (int i = 0; i < m.N; ++i) smax = std::max(smax, (int)(d->site_seg_off[i + 1] - d->site_seg_off[i]));
+    // orbit segments of a site -> lane entries (first, count, orbit, pieces that follow | -1).  A segment longer
+    // than SEG_PIECE clusters is cut into up to four pieces on adjacent lanes which flip_features merges with
+    // shuffles; a run of pieces never crosses a multiple of four lanes (first fit over 4-lane blocks), so it
+    // stays inside one group for every group size.
+    constexpr int SEG_PIECE = 6;
+    std::vector<std::vector<int4>> site_entries(m.N);
+    int smax = 4;
+    for (int i = 0; i < m.N; ++i) {
+      struct Run { int first, count, orbit, pieces; };
+      std::vector<Run> runs;
+      for (int64_t q = d->site_seg_off[i]; q < d->site_seg_off[i + 1]; ++q) {
+        const int cnt = d->site_seg[q * 3 + 1];
+        if (cnt <= 0) continue;
+        runs.push_back({d->site_seg[q * 3], cnt, d->site_seg[q * 3 + 2], std::min(4, (cnt + SEG_PIECE - 1) / SEG_PIECE)});
+      }
+      std::stable_sort(runs.begin(), runs.end(), [](const Run& x, const Run& y) { return x.pieces > y.pieces; });
+      std::vector<int> used;   // lanes taken in each 4-lane block
+      std::vector<int4>& ent = site_entries[i];
+      for (const Run& r : runs) {
+        size_t b = 0;
+        while (b < used.size() && used[b] + r.pieces > 4) ++b;
+        if (b == used.size()) { used.push_back(0); ent.resize(4 * used.size(), make_int4(0, 0, 0, -1)); }
+        const int len = (r.count + r.pieces - 1) / r.pieces;
+        for (int k = 0, at = 0; k < r.pieces; ++k, at += len)
+          ent[4 * b + used[b] + k] = make_int4(r.first + at, std::max(0, std::min(len, r.count - at)), r.orbit,
+                                               k == 0 ? r.pieces - 1 : -1);
+        used[b] += r.pieces;
+      }
+      smax = std::max(smax, (int)ent.size());
+    }
     m.Sstride = smax;
-    std::vector<int4> segs((size_t)m.N * smax, make_int4(0, 0, 0, 0));
-    for (int i = 0; i < m.N; ++i)
-      for (int64_t q = d->site_seg_off[i]; q < d->site_seg_off[i + 1]; ++q)
-        segs[(size_t)i * smax + (q - d->site_seg_off[i])] =
-            make_int4(d->site_seg[q * 3], d->site_seg[q * 3 + 1], d->site_seg[q * 3 + 2], 0);
+    std::vector<int4> segs((size_t)m.N * smax, make_int4(0, 0, 0, -1));
+    for (int i = 0; i < m.N; ++i) std::copy(site_entries[i].begin(), site_entries[i].end(), segs.begin() + (size_t)i * smax);
     UP(int4, segs.data(), segs.size(), m.site_seg);
     UP(uint2, d->full_rows, d->orb_row_off[m.nOrb], m.full_rows);
   }
@@ -886,6 +913,12 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   a.off_dist = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
   a.walker_smem = a.off_dist + (dist ? ((3 * m.F * 8 + 15) & ~15) : 0);   // distance processor: vector, delta, new distances
+  // Wang-Landau: entropy + histogram of the walker next to its occupancy while they are small (<= 24 KB)
+  a.off_wl = -1;
+  if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins > 0 && (size_t)c->wl.num_bins * 16 <= 24 * 1024 && !getenv("LMC_WL_GLOBAL")) {
+    a.off_wl = a.walker_smem;
+    a.walker_smem += (c->wl.num_bins * 16 + 15) & ~15;
+  }
   a.dist_ngrp = c->dist_num_groups; a.dist_tol = c->dist_tol; a.dist_target = c->dist_target_dev;
   a.dist_grp_off = c->dist_group_off_dev; a.dist_grp_idx = c->dist_group_idx_dev; a.dist_grp_diam = c->dist_group_diam_dev;
   a.dist_vec = c->dist_vector_dev;

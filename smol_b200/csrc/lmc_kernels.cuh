@@ -187,40 +187,62 @@ __device__ __forceinline__ double flip_energy_pair(const DevModel& m, const Smem
 }
 
 // phase B: fold the stashed per-record differences of an ACCEPTED flip into the running feature
-// vector.  One lane owns one orbit segment and sums it in cluster order (the reference's order,
-// evaluator.pyx:253-263); feature += p * (size / J_total).
-template <bool KONE>
+// vector.  One lane sums one piece of an orbit segment in cluster order (the reference's order,
+// evaluator.pyx:253-263).  lmc_model_create cuts long segments into up to four pieces on ADJACENT lanes
+// (never across a multiple of four, so they sit in one group for every group size): the head lane adds
+// the pieces of the next sg.w lanes (shuffles, still in cluster order) and owns the feature,
+// feature += p * (size / J_total).  sg = (first, count, orbit, pieces that follow | -1: not a head).
+template <int G>
+__device__ __forceinline__ double merge_pieces(double p, int follow, uint32_t gmask) {
+  const double q1 = __shfl_down_sync(gmask, p, 1, G), q2 = __shfl_down_sync(gmask, p, 2, G),
+               q3 = __shfl_down_sync(gmask, p, 3, G);
+  if (follow >= 1) p += q1;
+  if (follow >= 2) p += q2;
+  if (follow >= 3) p += q3;
+  return p;
+}
+// (called by every lane of the group: the merge shuffles are group wide)
+template <int G, bool KONE>
 __device__ __forceinline__ void fold_segment(const DevModel& m, const SmemTables& t, const int4 sg, const void* stash,
-                                             double* feat) {
-  if (sg.y <= 0) return;   // padding entry
-  const OrbDev& o = t.orb[sg.z];
+                                             double* feat, uint32_t gmask) {
+  const bool live = sg.y > 0;   // count 0 = padding entry
+  const OrbDev& o = t.orb[live ? sg.z : 0];
   if (KONE) {
     const double* d = reinterpret_cast<const double*>(stash) + sg.x;
     double p = 0.0;
     for (int j = 0; j < sg.y; ++j) p += d[j];
-    feat[o.fidx] += p * o.w;
+    p = merge_pieces<G>(p, sg.w, gmask);
+    if (live && sg.w >= 0) feat[o.fidx] += p * o.w;
   } else {
     const uint32_t* u = reinterpret_cast<const uint32_t*>(stash) + sg.x;
-    for (int k = 0; k < o.K; ++k) {
-      const double* tk = m.ftab + o.ftab_off + k * o.T;
+    for (int k = 0; k < m.Kmax; ++k) {   // uniform trip count (largest K of the model): shuffles inside
       double p = 0.0;
-      for (int j = 0; j < sg.y; ++j) p += __ldg(tk + (u[j] & 0xffffu)) - __ldg(tk + (u[j] >> 16));
-      feat[o.fidx + k] += p * o.w;
+      const bool on = live && k < o.K;
+      if (on) {
+        const double* tk = m.ftab + o.ftab_off + k * o.T;
+        for (int j = 0; j < sg.y; ++j) p += __ldg(tk + (u[j] & 0xffffu)) - __ldg(tk + (u[j] >> 16));
+      }
+      p = merge_pieces<G>(p, sg.w, gmask);
+      if (on && sg.w >= 0) feat[o.fidx + k] += p * o.w;
     }
   }
 }
-// the lane's first orbit segment of a site (fixed-stride table, count 0 = padding); state independent,
+// the lane's first segment entry of a site (fixed-stride table, count 0 = padding); state independent,
 // so it can be fetched together with the records
 template <int G>
 __device__ __forceinline__ int4 load_segment(const DevModel& m, int site, int g) {
-  return g < m.Sstride ? __ldg(m.site_seg + (size_t)site * m.Sstride + g) : make_int4(0, 0, 0, 0);
+  return g < m.Sstride ? __ldg(m.site_seg + (size_t)site * m.Sstride + g) : make_int4(0, 0, 0, -1);
 }
 template <int G, bool KONE>
 __device__ __forceinline__ void flip_features(const DevModel& m, const SmemTables& t, int site, const void* stash,
                                               double* feat, int g, const int4 seg0) {
-  fold_segment<KONE>(m, t, seg0, stash, feat);
-  for (int sidx = g + G; sidx < m.Sstride; sidx += G)
-    fold_segment<KONE>(m, t, __ldg(m.site_seg + (size_t)site * m.Sstride + sidx), stash, feat);
+  const uint32_t gmask = group_mask<G>();
+  fold_segment<G, KONE>(m, t, seg0, stash, feat, gmask);
+  for (int base = G; base < m.Sstride; base += G) {   // uniform over the group
+    const int sidx = base + g;
+    const int4 sg = sidx < m.Sstride ? __ldg(m.site_seg + (size_t)site * m.Sstride + sidx) : make_int4(0, 0, 0, -1);
+    fold_segment<G, KONE>(m, t, sg, stash, feat, gmask);
+  }
 }
 
 // Ewald energy change of one flip (delta_ewald_single_flip, smol/utils/cluster/ewald.pyx:9-59); lanes
@@ -447,6 +469,15 @@ __device__ __forceinline__ double exact_floordiv(double a, double b) {
   else if (r >= b) q += 1.0;
   return q;
 }
+// the same with the candidate from a multiplication by 1/b (within one of the exact floor; the remainder
+// test is exact, so the result is the same value): no double division on the step's critical path
+__device__ __forceinline__ double exact_floordiv_inv(double a, double b, double inv_b) {
+  double q = floor(a * inv_b);
+  const double r = fma(-q, b, a);
+  if (r < 0.0) q -= 1.0;
+  else if (r >= b) q += 1.0;
+  return q;
+}
 // st.<field>[f] for a RUNTIME f without dynamic indexing (keeps the arrays in registers)
 template <int MF>
 __device__ __forceinline__ int pick(const int (&arr)[MF], int f) {
@@ -455,6 +486,11 @@ __device__ __forceinline__ int pick(const int (&arr)[MF], int f) {
   for (int i = 1; i < MF; ++i) v = (f == i) ? arr[i] : v;
   return v;
 }
+
+// Wang-Landau per-walker arrays: plain loads from the shared-memory copy, L2 loads (the global arrays are
+// updated with reductions that bypass L1) otherwise
+template <typename T>
+__device__ __forceinline__ T wl_load(const T* p, bool in_smem) { return in_smem ? *p : __ldcg(p); }
 
 // Python float floor division `a // b` (CPython float_floor_div), used by WangLandau._get_bin_id
 __device__ __forceinline__ double py_floordiv(double a, double b) {
@@ -553,15 +589,29 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   double cur_fb = -1.0, s_cur = 0.0;   // current bin (floor value) and its entropy, kept in registers
   const bool wl_sum = a.wl.reserved != 0;  // mean_features buffer holds per-bin SUMS (update_period == 1)
   const int nb = a.wl.num_bins;
+  const double wl_inv_bin = WLMODE ? 1.0 / a.wl.bin_size : 0.0;
+  // entropy and histogram of the walker live in its shared-memory slab while they fit (a.off_wl >= 0,
+  // lmc_run): the entropy of the proposed bin is on the critical path of every step
+  const bool wl_sm = WLMODE && a.off_wl >= 0;
+  double* wlSg = nullptr; long long* wlHg = nullptr;   // the global arrays (loaded / written back)
+  int upd_rem = 0, chk_rem = 0;   // wl_cnt modulo update_period / check_period, carried along (no 64-bit division per step)
   if (wl_mode) {
-    wlS = a.wl.entropy_dev + (size_t)w * nb;
-    wlH = reinterpret_cast<long long*>(a.wl.histogram_dev) + (size_t)w * nb;
+    wlSg = wlS = a.wl.entropy_dev + (size_t)w * nb;
+    wlHg = wlH = reinterpret_cast<long long*>(a.wl.histogram_dev) + (size_t)w * nb;
     wlO = reinterpret_cast<long long*>(a.wl.occurrences_dev) + (size_t)w * nb;
     wlM = a.wl.mean_features_dev + (size_t)w * nb * m.F;
     wl_m = a.wl.mod_factor_dev[w];
     wl_cnt = a.wl.steps_counter_dev[w];
+    upd_rem = (int)(wl_cnt % a.wl.update_period);
+    chk_rem = (int)(wl_cnt % a.wl.check_period);
+    if (wl_sm) {
+      wlS = reinterpret_cast<double*>(priv + a.off_wl);
+      wlH = reinterpret_cast<long long*>(priv + a.off_wl) + nb;
+      for (int b = g; b < nb; b += G) { wlS[b] = __ldcg(wlSg + b); wlH[b] = __ldcg(wlHg + b); }
+      group_sync<G>(gmask);
+    }
     cur_fb = exact_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
-    s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? __ldcg(wlS + (int)cur_fb) : 0.0;
+    s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? wl_load(wlS + (int)cur_fb, wl_sm) : 0.0;
   }
 
   double* dvec = reinterpret_cast<double*>(priv + a.off_dist);   // DIST: [vector F][delta F][new distances F]
@@ -850,7 +900,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       // (high-acceptance workloads: Wang-Landau, Ewald, table flips); the 72-register swap/flip
       // kernel fetches them on accept
       constexpr bool SEGPRE = EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP || G < 32;
-      int4 seg0 = make_int4(0, 0, 0, 0), seg1 = make_int4(0, 0, 0, 0);
+      int4 seg0 = make_int4(0, 0, 0, -1), seg1 = make_int4(0, 0, 0, -1);
       if (st.n > 0) { pre0 = load_records<G>(m, st.site[0], g); if (SEGPRE) seg0 = load_segment<G>(m, st.site[0], g); }
       if (st.n > 1) { pre1 = load_records<G>(m, st.site[I1], g); if (SEGPRE) seg1 = load_segment<G>(m, st.site[I1], g); }
       // Ewald part first: it only touches the per-walker Ewald cache, never the occupancy.  Flip f is
@@ -1004,9 +1054,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         if (e_new < a.wl.min_enthalpy || e_new >= a.wl.max_enthalpy) {
           accepted = false;
         } else {
-          new_fb = exact_floordiv(e_new - a.wl.min_enthalpy, a.wl.bin_size);
+          new_fb = exact_floordiv_inv(e_new - a.wl.min_enthalpy, a.wl.bin_size, wl_inv_bin);
           s_new = new_fb == cur_fb ? s_cur
-                                   : ((new_fb >= 0.0 && new_fb < (double)nb) ? __ldcg(wlS + (int)new_fb) : 0.0);
+                                   : ((new_fb >= 0.0 && new_fb < (double)nb) ? wl_load(wlS + (int)new_fb, wl_sm) : 0.0);
           const double exponent = (s_cur - s_new) + st.log_priori;
           const int af = accept_fast(exponent, lf);
           accepted = af >= 0 ? (af != 0)
@@ -1093,7 +1143,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         if (cur_fb >= 0.0 && cur_fb < (double)nb) {
           const int bin = (int)cur_fb;
           ++wl_cnt;
-          const bool upd = wl_cnt % a.wl.update_period == 0;
+          if (++upd_rem == a.wl.update_period) upd_rem = 0;
+          if (++chk_rem == a.wl.check_period) chk_rem = 0;
+          const bool upd = upd_rem == 0;
           if (wl_sum) {
             // update_period == 1: the running mean (x_n + (n-1) M)/n is sum/n -- accumulate the sum with
             // fire-and-forget reductions, the host divides by `occurrences`
@@ -1111,27 +1163,32 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           if (upd) {
             s_cur += wl_m;
             if (g == 0) {
-              __stcg(wlS + bin, s_cur);
-              atomicAdd(reinterpret_cast<unsigned long long*>(wlH + bin), 1ull);
+              if (wl_sm) {
+                wlS[bin] = s_cur;
+                wlH[bin] += 1;
+              } else {
+                __stcg(wlS + bin, s_cur);
+                atomicAdd(reinterpret_cast<unsigned long long*>(wlH + bin), 1ull);
+              }
             }
           }
         }
         wl_m_traced = wl_m;   // trace.mod_factor is copied before the flatness check (wanglandau.py:251)
-        if (wl_cnt % a.wl.check_period == 0) {
+        if (chk_rem == 0) {
           __threadfence_block();
           group_sync<G>(gmask);   // lane 0's entropy/histogram updates are visible to the group
           int nvis = 0;
           double hsum = 0.0, hmin = 1e300;
           for (int b = g; b < nb; b += G)
-            if (__ldcg(wlS + b) > 0.0) {
-              const double h = (double)__ldcg(wlH + b);
+            if (wl_load(wlS + b, wl_sm) > 0.0) {
+              const double h = (double)wl_load(wlH + b, wl_sm);
               ++nvis; hsum += h; hmin = fmin(hmin, h);
             }
           nvis = group_sum_i<G>(nvis, gmask);
           hsum = group_sum<G>(hsum, gmask);
           hmin = group_min<G>(hmin, gmask);
           if (nvis >= 2 && hmin > a.wl.flatness * (hsum / (double)nvis)) {
-            for (int b = g; b < nb; b += G) __stcg(wlH + b, 0ll);
+            for (int b = g; b < nb; b += G) { if (wl_sm) wlH[b] = 0ll; else __stcg(wlH + b, 0ll); }
             wl_m = wl_m / a.wl.mod_update;
             group_sync<G>(gmask);
           }
@@ -1172,8 +1229,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       group_sync<G>(gmask);
       for (int b = g; b < nb; b += G) {
         const long long oc = __ldcg(wlO + b);
-        if (a.wl.trace_entropy_dev) __stcs(a.wl.trace_entropy_dev + sw * nb + b, __ldcg(wlS + b));
-        if (a.wl.trace_histogram_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_histogram_dev) + sw * nb + b, __ldcg(wlH + b));
+        if (a.wl.trace_entropy_dev) __stcs(a.wl.trace_entropy_dev + sw * nb + b, wl_load(wlS + b, wl_sm));
+        if (a.wl.trace_histogram_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_histogram_dev) + sw * nb + b, wl_load(wlH + b, wl_sm));
         if (a.wl.trace_occurrences_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_occurrences_dev) + sw * nb + b, oc);
       }
       if (a.wl.trace_mean_features_dev) {
@@ -1192,6 +1249,10 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   for (int f = g; f < m.F; f += G) a.features[(size_t)w * m.F + f] = feat[f];
   if (DIST)
     for (int f = g; f < m.F; f += G) a.dist_vec[(size_t)w * m.F + f] = dvec[f];
+  if (wl_sm) {
+    group_sync<G>(gmask);
+    for (int b = g; b < nb; b += G) { wlSg[b] = wlS[b]; wlHg[b] = wlH[b]; }
+  }
   if (g == 0) {
     a.enthalpy[w] = enth;
     if (!WLMODE && a.bias_mode) {

@@ -27,8 +27,9 @@ struct DevModel {
   int blob_bytes, off_tabA, off_nat, off_orb, off_qtab;
   const double* ftab;      // global copy of all feature tensors (phase B when K > 1, full evaluation)
   const uint2* site_rec;   // [N][Rstride] (idx0 | idx1<<16, idx2 | cls<<16), padded per site
-  const int4* site_seg;    // [N][Sstride] (first, count, orbit, 0); count 0 = padding
-  int Sstride;             // orbit segments per site (max over sites)
+  const int4* site_seg;    // [N][Sstride] (first, count, orbit, pieces that follow | -1); count 0 = padding
+  int Sstride;             // segment entries per site (multiple of 4; long segments are cut into pieces)
+  int Kmax;                // largest number of functions of one orbit
   const uint2* full_rows;  // [rows] 4 x u16 site indices
   // Ewald
   int E, ewW, ewF;
@@ -116,6 +117,7 @@ struct RunArgs {
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
   int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx, off_lists, off_bias;  // offsets inside a walker's shared-memory slab
+  int off_wl;         // Wang-Landau: [entropy nb][histogram nb] of the walker in its slab, -1 = kept in global memory
   unsigned long long* stats;  // [2] accepted / attempted step totals (device counters; kernel selection feedback)
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another
