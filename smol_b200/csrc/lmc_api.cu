@@ -606,6 +606,10 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
           return fail("species codes must be < 8");
         }
       }
+      for (int code = 0; code < LMC_MAX_CODES; ++code) {
+        m.sl_code_pos[s][code] = (unsigned char)m.sl_ncodes[s];
+        for (int c = m.sl_ncodes[s] - 1; c >= 0; --c) if (m.sl_codes[s][c] == code) m.sl_code_pos[s][code] = (unsigned char)c;
+      }
       cum += d->sl_prob[s];
       m.sl_cum[s] = (s == m.nSl - 1) ? 1.0 : cum;
       const int a = d->sl_site_off[s], b = d->sl_site_off[s + 1];
@@ -913,6 +917,9 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   a.off_dist = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
   a.walker_smem = a.off_dist + (dist ? ((3 * m.F * 8 + 15) & ~15) : 0);   // distance processor: vector, delta, new distances
+  // Wang-Landau flips: landing zone of the next step's records / segment entries
+  a.off_pref = a.walker_smem;
+  if (c->kernel == LMC_KERNEL_WANGLANDAU && c->usher == LMC_USHER_FLIP && !dist) a.walker_smem += m.Rstride * 8 + m.Sstride * 16;
   // Wang-Landau: entropy + histogram of the walker next to its occupancy while they are small (<= 24 KB)
   a.off_wl = -1;
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins > 0 && (size_t)c->wl.num_bins * 16 <= 24 * 1024 && !getenv("LMC_WL_GLOBAL")) {

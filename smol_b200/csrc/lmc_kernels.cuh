@@ -490,7 +490,9 @@ __device__ __forceinline__ int pick(const int (&arr)[MF], int f) {
 // Wang-Landau per-walker arrays: plain loads from the shared-memory copy, L2 loads (the global arrays are
 // updated with reductions that bypass L1) otherwise
 template <typename T>
-__device__ __forceinline__ T wl_load(const T* p, bool in_smem) { return in_smem ? *p : __ldcg(p); }
+__device__ __forceinline__ T wl_load(const T* smem_copy, const T* global, int i, bool in_smem) {
+  return in_smem ? smem_copy[i] : __ldcg(global + i);
+}
 
 // Python float floor division `a // b` (CPython float_floor_div), used by WangLandau._get_bin_id
 __device__ __forceinline__ double py_floordiv(double a, double b) {
@@ -593,11 +595,14 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // entropy and histogram of the walker live in its shared-memory slab while they fit (a.off_wl >= 0,
   // lmc_run): the entropy of the proposed bin is on the critical path of every step
   const bool wl_sm = WLMODE && a.off_wl >= 0;
-  double* wlSg = nullptr; long long* wlHg = nullptr;   // the global arrays (loaded / written back)
+  // (shared-memory copies addressed from the slab pointer, so that they compile to LDS / STS rather than generic
+  // accesses that wait on the long scoreboard)
+  double* wlSs = reinterpret_cast<double*>(priv + (WLMODE ? max(a.off_wl, 0) : 0));
+  long long* wlHs = reinterpret_cast<long long*>(wlSs) + a.wl.num_bins;
   int upd_rem = 0, chk_rem = 0;   // wl_cnt modulo update_period / check_period, carried along (no 64-bit division per step)
   if (wl_mode) {
-    wlSg = wlS = a.wl.entropy_dev + (size_t)w * nb;
-    wlHg = wlH = reinterpret_cast<long long*>(a.wl.histogram_dev) + (size_t)w * nb;
+    wlS = a.wl.entropy_dev + (size_t)w * nb;
+    wlH = reinterpret_cast<long long*>(a.wl.histogram_dev) + (size_t)w * nb;
     wlO = reinterpret_cast<long long*>(a.wl.occurrences_dev) + (size_t)w * nb;
     wlM = a.wl.mean_features_dev + (size_t)w * nb * m.F;
     wl_m = a.wl.mod_factor_dev[w];
@@ -605,13 +610,11 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     upd_rem = (int)(wl_cnt % a.wl.update_period);
     chk_rem = (int)(wl_cnt % a.wl.check_period);
     if (wl_sm) {
-      wlS = reinterpret_cast<double*>(priv + a.off_wl);
-      wlH = reinterpret_cast<long long*>(priv + a.off_wl) + nb;
-      for (int b = g; b < nb; b += G) { wlS[b] = __ldcg(wlSg + b); wlH[b] = __ldcg(wlHg + b); }
+      for (int b = g; b < nb; b += G) { wlSs[b] = __ldcg(wlS + b); wlHs[b] = __ldcg(wlH + b); }
       group_sync<G>(gmask);
     }
     cur_fb = exact_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
-    s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? wl_load(wlS + (int)cur_fb, wl_sm) : 0.0;
+    s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? wl_load(wlSs, wlS, (int)cur_fb, wl_sm) : 0.0;
   }
 
   double* dvec = reinterpret_cast<double*>(priv + a.off_dist);   // DIST: [vector F][delta F][new distances F]
@@ -636,6 +639,13 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // costs a few shuffles instead of a redundant Philox evaluation in all lanes.
   uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [G] x (sl<<24 | pos, site, word z, float log u)
   int bphase = 0;
+  // latency-bound variants (few resident warps: Wang-Landau flips): records of step t + 1 are fetched during step t
+  constexpr bool PREF = WLMODE && USHER == LMC_USHER_FLIP && !DIST;
+  // (asynchronous copies into the walker's slab, each lane its own records and segment entry: a register
+  // prefetch was measured useless -- its loads share a scoreboard slot with the next waits of the step)
+  uint2* nxt_rec = reinterpret_cast<uint2*>(priv + a.off_pref);
+  int4* nxt_seg = reinterpret_cast<int4*>(priv + a.off_pref + m.Rstride * 8);
+  bool have_nxt = false;
   long long nacc_total = 0;
   for (long long s = 0; s < a.S; ++s) {
     int nacc = 0;
@@ -796,8 +806,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         const int cur = occ[site];
         const int nc = m.sl_ncodes[sl];
         int ci = (int)mulhi32(q2, (uint32_t)(nc - 1));
-        int pos = nc;
-        for (int c = 0; c < nc; ++c) if (m.sl_codes[sl][c] == cur) { pos = c; break; }
+        const int pos = m.sl_code_pos[sl][cur];   // index of the current code in the encoding (nc if it is not in it)
         if (ci >= pos) ++ci;
         st.n = 1; st.site[0] = site; st.oldc[0] = cur; st.newc[0] = m.sl_codes[sl][ci]; st.sl[0] = sl; st.pos[0] = j;
       } else if (USHER == LMC_USHER_SWAP || usher == LMC_USHER_SWAP) {
@@ -901,8 +910,23 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       // kernel fetches them on accept
       constexpr bool SEGPRE = EWALD || WLMODE || USHER == LMC_USHER_TABLEFLIP || G < 32;
       int4 seg0 = make_int4(0, 0, 0, -1), seg1 = make_int4(0, 0, 0, -1);
-      if (st.n > 0) { pre0 = load_records<G>(m, st.site[0], g); if (SEGPRE) seg0 = load_segment<G>(m, st.site[0], g); }
+      if (PREF && have_nxt) {   // fetched during the previous step
+        cp_async_wait_all();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = g + u * G;
+          pre0.r[u] = r < m.Rstride ? nxt_rec[r] : make_uint2(0u, (uint32_t)m.nCls << 16);
+        }
+        seg0 = g < m.Sstride ? nxt_seg[g] : make_int4(0, 0, 0, -1);
+      } else if (st.n > 0) { pre0 = load_records<G>(m, st.site[0], g); if (SEGPRE) seg0 = load_segment<G>(m, st.site[0], g); }
       if (st.n > 1) { pre1 = load_records<G>(m, st.site[I1], g); if (SEGPRE) seg1 = load_segment<G>(m, st.site[I1], g); }
+      // chemical work (ensemble.py:369-373): table lookups of the proposal only, issued ahead of the evaluation
+      if (MU_POSSIBLE && m.muW) {
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          if (f < st.n)
+            dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
+      }
       // Ewald part first: it only touches the per-walker Ewald cache, never the occupancy.  Flip f is
       // evaluated with flips < f applied to the cache (sequential semantics, ewald.py:168-181); the
       // last flip is applied on accept only.  One loop, not unrolled: one copy of the row-gather code.
@@ -970,11 +994,21 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           if (f + 1 < st.n) group_sync<G>(gmask);
         }
       }
-      if (MU_POSSIBLE && m.muW) {
+      if (PREF) {
+        // the site of the NEXT step is already in the ring (state independent): fetch its records and segments
+        // now, so that their L2 latency overlaps with the reduction, the accept test and the update
+        have_nxt = bphase != 0;
+        if (have_nxt) {
+          const int ns = (int)ring[bphase].y;
+          const uint2* rp = m.site_rec + (size_t)ns * m.Rstride;
 #pragma unroll
-        for (int f = 0; f < MF; ++f)
-          if (f < st.n)
-            dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
+          for (int u = 0; u < 4; ++u) {
+            const int r = g + u * G;
+            if (r < m.Rstride) cp_async_8(nxt_rec + r, rp + r);
+          }
+          if (g < m.Sstride) cp_async_16(nxt_seg + g, m.site_seg + (size_t)ns * m.Sstride + g);
+          cp_async_commit();
+        }
       }
       double dH = group_sum<G>(acc, gmask);
       double dEw = 0.0;
@@ -1056,7 +1090,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
         } else {
           new_fb = exact_floordiv_inv(e_new - a.wl.min_enthalpy, a.wl.bin_size, wl_inv_bin);
           s_new = new_fb == cur_fb ? s_cur
-                                   : ((new_fb >= 0.0 && new_fb < (double)nb) ? wl_load(wlS + (int)new_fb, wl_sm) : 0.0);
+                                   : ((new_fb >= 0.0 && new_fb < (double)nb) ? wl_load(wlSs, wlS, (int)new_fb, wl_sm) : 0.0);
           const double exponent = (s_cur - s_new) + st.log_priori;
           const int af = accept_fast(exponent, lf);
           accepted = af >= 0 ? (af != 0)
@@ -1092,7 +1126,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           if (MU_POSSIBLE && m.muW) feat[m.muF] += dmu;
 #pragma unroll
           for (int f = 0; f < MF; ++f)
-            if (f < st.n) {
+            if (USHER != LMC_USHER_FLIP && f < st.n) {   // (a pure flip usher never reads the counts / bit-planes)
               cnt[st.sl[f] * LMC_MAX_CODES + st.oldc[f]]--;
               cnt[st.sl[f] * LMC_MAX_CODES + st.newc[f]]++;
               const int nw = m.sl_nwords[st.sl[f]];
@@ -1164,8 +1198,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
             s_cur += wl_m;
             if (g == 0) {
               if (wl_sm) {
-                wlS[bin] = s_cur;
-                wlH[bin] += 1;
+                wlSs[bin] = s_cur;
+                wlHs[bin] += 1;
               } else {
                 __stcg(wlS + bin, s_cur);
                 atomicAdd(reinterpret_cast<unsigned long long*>(wlH + bin), 1ull);
@@ -1180,15 +1214,15 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           int nvis = 0;
           double hsum = 0.0, hmin = 1e300;
           for (int b = g; b < nb; b += G)
-            if (wl_load(wlS + b, wl_sm) > 0.0) {
-              const double h = (double)wl_load(wlH + b, wl_sm);
+            if (wl_load(wlSs, wlS, b, wl_sm) > 0.0) {
+              const double h = (double)wl_load(wlHs, wlH, b, wl_sm);
               ++nvis; hsum += h; hmin = fmin(hmin, h);
             }
           nvis = group_sum_i<G>(nvis, gmask);
           hsum = group_sum<G>(hsum, gmask);
           hmin = group_min<G>(hmin, gmask);
           if (nvis >= 2 && hmin > a.wl.flatness * (hsum / (double)nvis)) {
-            for (int b = g; b < nb; b += G) { if (wl_sm) wlH[b] = 0ll; else __stcg(wlH + b, 0ll); }
+            for (int b = g; b < nb; b += G) { if (wl_sm) wlHs[b] = 0ll; else __stcg(wlH + b, 0ll); }
             wl_m = wl_m / a.wl.mod_update;
             group_sync<G>(gmask);
           }
@@ -1229,14 +1263,17 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       group_sync<G>(gmask);
       for (int b = g; b < nb; b += G) {
         const long long oc = __ldcg(wlO + b);
-        if (a.wl.trace_entropy_dev) __stcs(a.wl.trace_entropy_dev + sw * nb + b, wl_load(wlS + b, wl_sm));
-        if (a.wl.trace_histogram_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_histogram_dev) + sw * nb + b, wl_load(wlH + b, wl_sm));
+        if (a.wl.trace_entropy_dev) __stcs(a.wl.trace_entropy_dev + sw * nb + b, wl_load(wlSs, wlS, b, wl_sm));
+        if (a.wl.trace_histogram_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_histogram_dev) + sw * nb + b, wl_load(wlHs, wlH, b, wl_sm));
         if (a.wl.trace_occurrences_dev) __stcs(reinterpret_cast<long long*>(a.wl.trace_occurrences_dev) + sw * nb + b, oc);
       }
       if (a.wl.trace_mean_features_dev) {
         for (int i = g; i < nb * m.F; i += G) {
           double v = __ldcg(wlM + i);
-          if (wl_sum) { const long long oc = __ldcg(wlO + i / m.F); v = oc > 0 ? v / (double)oc : 0.0; }
+          if (wl_sum) {
+            const long long oc = __ldcg(wlO + i / m.F);
+            if (oc != 1) v = oc > 0 ? v / (double)oc : 0.0;   // (most bins of a short run were never or once visited)
+          }
           __stcs(a.wl.trace_mean_features_dev + (sw * nb) * m.F + i, v);
         }
       }
@@ -1251,7 +1288,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
     for (int f = g; f < m.F; f += G) a.dist_vec[(size_t)w * m.F + f] = dvec[f];
   if (wl_sm) {
     group_sync<G>(gmask);
-    for (int b = g; b < nb; b += G) { wlSg[b] = wlS[b]; wlHg[b] = wlH[b]; }
+    for (int b = g; b < nb; b += G) { wlS[b] = wlSs[b]; wlH[b] = wlHs[b]; }
   }
   if (g == 0) {
     a.enthalpy[w] = enth;

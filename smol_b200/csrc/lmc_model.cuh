@@ -49,6 +49,7 @@ struct DevModel {
   int sl_off[LMC_MAX_SUBLATTICES + 1];
   int sl_ncodes[LMC_MAX_SUBLATTICES];
   int sl_codes[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];
+  unsigned char sl_code_pos[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];   // index of a code in sl_codes (ncodes if absent)
   int sl_first[LMC_MAX_SUBLATTICES];   // first site if the active sites are one contiguous range, else -1
   double sl_cum[LMC_MAX_SUBLATTICES];  // cumulative proposal probabilities
   int sl_nwords[LMC_MAX_SUBLATTICES];  // 32-bit words of one species bit-plane (ceil(n_active/32))
@@ -117,6 +118,7 @@ struct RunArgs {
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
   int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx, off_lists, off_bias;  // offsets inside a walker's shared-memory slab
+  int off_pref;       // Wang-Landau flips: records and segment entries of the next step (asynchronous prefetch)
   int off_wl;         // Wang-Landau: [entropy nb][histogram nb] of the walker in its slab, -1 = kept in global memory
   unsigned long long* stats;  // [2] accepted / attempted step totals (device counters; kernel selection feedback)
   int max_flips;      // flips per step of the selected usher (stash slots)

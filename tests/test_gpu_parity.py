@@ -267,7 +267,12 @@ def test_canonical_ewald_swap_trajectory(cuda_device, mode):
     assert smp._ew_field is not None and 0 < smp.samples.step_efficiency() < 1
 
 
-def test_wang_landau_flip_trajectory(cuda_device):
+@pytest.mark.parametrize("wl_arrays", ["smem", "global"])
+def test_wang_landau_flip_trajectory(cuda_device, wl_arrays, monkeypatch):
+    """smem: the walker's entropy / histogram live in shared memory during a launch (the default while they
+    fit); global: kept in HBM / L2 (LMC_WL_GLOBAL, the path of very fine windows)"""
+    if wl_arrays == "global":
+        monkeypatch.setenv("LMC_WL_GLOBAL", "1")
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
