@@ -555,7 +555,7 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     // than SEG_PIECE clusters is cut into up to four pieces on adjacent lanes which flip_features merges with
     // shuffles; a run of pieces never crosses a multiple of four lanes (first fit over 4-lane blocks), so it
     // stays inside one group for every group size.
-    constexpr int SEG_PIECE = 6;
+    constexpr int SEG_PIECE = LMC_SEG_PIECE;
     std::vector<std::vector<int4>> site_entries(m.N);
     int smax = 4;
     for (int i = 0; i < m.N; ++i) {
@@ -919,7 +919,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.walker_smem = a.off_dist + (dist ? ((3 * m.F * 8 + 15) & ~15) : 0);   // distance processor: vector, delta, new distances
   // Wang-Landau flips: landing zone of the next step's records / segment entries
   a.off_pref = a.walker_smem;
-  if (c->kernel == LMC_KERNEL_WANGLANDAU && c->usher == LMC_USHER_FLIP && !dist) a.walker_smem += m.Rstride * 8 + m.Sstride * 16;
+  if (c->kernel == LMC_KERNEL_WANGLANDAU && c->usher == LMC_USHER_FLIP && !dist) a.walker_smem += 2 * (m.Rstride * 8 + m.Sstride * 16);   // double buffered
   // Wang-Landau: entropy + histogram of the walker next to its occupancy while they are small (<= 24 KB)
   a.off_wl = -1;
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins > 0 && (size_t)c->wl.num_bins * 16 <= 24 * 1024 && !getenv("LMC_WL_GLOBAL")) {

@@ -210,7 +210,12 @@ __device__ __forceinline__ void fold_segment(const DevModel& m, const SmemTables
   if (KONE) {
     const double* d = reinterpret_cast<const double*>(stash) + sg.x;
     double p = 0.0;
-    for (int j = 0; j < sg.y; ++j) p += d[j];
+    // pieces hold at most LMC_SEG_PIECE clusters unless a segment is longer than four pieces: straight-line
+    // chunks with the tail masked (adding +0.0 leaves the sum unchanged)
+    for (int j0 = 0; j0 < sg.y; j0 += LMC_SEG_PIECE) {
+#pragma unroll
+      for (int j = 0; j < LMC_SEG_PIECE; ++j) p += (j0 + j < sg.y) ? d[j0 + j] : 0.0;
+    }
     p = merge_pieces<G>(p, sg.w, gmask);
     if (live && sg.w >= 0) feat[o.fidx] += p * o.w;
   } else {
@@ -643,9 +648,10 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   constexpr bool PREF = WLMODE && USHER == LMC_USHER_FLIP && !DIST;
   // (asynchronous copies into the walker's slab, each lane its own records and segment entry: a register
   // prefetch was measured useless -- its loads share a scoreboard slot with the next waits of the step)
-  uint2* nxt_rec = reinterpret_cast<uint2*>(priv + a.off_pref);
-  int4* nxt_seg = reinterpret_cast<int4*>(priv + a.off_pref + m.Rstride * 8);
+  uint2* nxt_rec = reinterpret_cast<uint2*>(priv + a.off_pref);                   // [2][Rstride]
+  int4* nxt_seg = reinterpret_cast<int4*>(priv + a.off_pref + 2 * m.Rstride * 8);   // [2][Sstride]
   bool have_nxt = false;
+  int nxt_buf = 0;
   long long nacc_total = 0;
   for (long long s = 0; s < a.S; ++s) {
     int nacc = 0;
@@ -912,14 +918,33 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       int4 seg0 = make_int4(0, 0, 0, -1), seg1 = make_int4(0, 0, 0, -1);
       if (PREF && have_nxt) {   // fetched during the previous step
         cp_async_wait_all();
+        const uint2* br = nxt_rec + nxt_buf * m.Rstride;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int r = g + u * G;
-          pre0.r[u] = r < m.Rstride ? nxt_rec[r] : make_uint2(0u, (uint32_t)m.nCls << 16);
+          pre0.r[u] = r < m.Rstride ? br[r] : make_uint2(0u, (uint32_t)m.nCls << 16);
         }
-        seg0 = g < m.Sstride ? nxt_seg[g] : make_int4(0, 0, 0, -1);
+        seg0 = g < m.Sstride ? nxt_seg[nxt_buf * m.Sstride + g] : make_int4(0, 0, 0, -1);
       } else if (st.n > 0) { pre0 = load_records<G>(m, st.site[0], g); if (SEGPRE) seg0 = load_segment<G>(m, st.site[0], g); }
       if (st.n > 1) { pre1 = load_records<G>(m, st.site[I1], g); if (SEGPRE) seg1 = load_segment<G>(m, st.site[I1], g); }
+      if (PREF) {
+        // the site of the NEXT step is already in the ring (state independent): fetch its records and segment
+        // entries into the other buffer now; a whole step hides their L2 latency
+        have_nxt = bphase != 0;
+        if (have_nxt) {
+          nxt_buf ^= 1;
+          const int ns = (int)ring[bphase].y;
+          const uint2* rp = m.site_rec + (size_t)ns * m.Rstride;
+          uint2* br = nxt_rec + nxt_buf * m.Rstride;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = g + u * G;
+            if (r < m.Rstride) cp_async_8(br + r, rp + r);
+          }
+          if (g < m.Sstride) cp_async_16(nxt_seg + nxt_buf * m.Sstride + g, m.site_seg + (size_t)ns * m.Sstride + g);
+          cp_async_commit();
+        }
+      }
       // chemical work (ensemble.py:369-373): table lookups of the proposal only, issued ahead of the evaluation
       if (MU_POSSIBLE && m.muW) {
 #pragma unroll
@@ -992,22 +1017,6 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           acc += flip_energy<G, KONE>(m, t, occ, sf, of, nf, stash0 + f * stash_stride, g, pre0);
           if (g == 0) occ[sf] = (uint8_t)nf;
           if (f + 1 < st.n) group_sync<G>(gmask);
-        }
-      }
-      if (PREF) {
-        // the site of the NEXT step is already in the ring (state independent): fetch its records and segments
-        // now, so that their L2 latency overlaps with the reduction, the accept test and the update
-        have_nxt = bphase != 0;
-        if (have_nxt) {
-          const int ns = (int)ring[bphase].y;
-          const uint2* rp = m.site_rec + (size_t)ns * m.Rstride;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = g + u * G;
-            if (r < m.Rstride) cp_async_8(nxt_rec + r, rp + r);
-          }
-          if (g < m.Sstride) cp_async_16(nxt_seg + g, m.site_seg + (size_t)ns * m.Sstride + g);
-          cp_async_commit();
         }
       }
       double dH = group_sum<G>(acc, gmask);
@@ -1183,7 +1192,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           if (wl_sum) {
             // update_period == 1: the running mean (x_n + (n-1) M)/n is sum/n -- accumulate the sum with
             // fire-and-forget reductions, the host divides by `occurrences`
-            for (int f = g; f < m.F; f += G) atomicAdd(wlM + (size_t)bin * m.F + f, feat[f]);
+            double* mrow = wlM + (size_t)bin * m.F;
+            if (m.F <= G) { if (g < m.F) atomicAdd(mrow + g, feat[g]); }
+            else for (int f = g; f < m.F; f += G) atomicAdd(mrow + f, feat[f]);
             if (g == 0) atomicAdd(reinterpret_cast<unsigned long long*>(wlO + bin), 1ull);
           } else {
             const long long total = __ldcg(wlO + bin);

@@ -6,6 +6,8 @@
 namespace lmc {
 
 // one orbit of clusters: where its tensors live and how to fold them into features
+#define LMC_SEG_PIECE 6   // clusters per piece of an orbit segment (flip_features)
+
 struct OrbDev {
   int ftab_off;    // offset of the K*T block in ftab (doubles)
   int atab_off;    // offset of the T block in the phase-A table (raw tensor if K==1, else contracted)
