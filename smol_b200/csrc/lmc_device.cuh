@@ -75,6 +75,14 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// fire-and-forget reductions (REDG: no return value, no scoreboard wait; inside the big kernels `atomicAdd` with
+// an unused result was compiled to ATOMG ... RZ, whose L2 round trip the next loop iteration waited for)
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(void* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // per-thread asynchronous copies global -> shared (LDGSTS): no destination registers and no scoreboard slot, the
 // issuing thread sees the data after cp_async_wait_all()
 __device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src_gmem) {

@@ -1193,9 +1193,9 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
             // update_period == 1: the running mean (x_n + (n-1) M)/n is sum/n -- accumulate the sum with
             // fire-and-forget reductions, the host divides by `occurrences`
             double* mrow = wlM + (size_t)bin * m.F;
-            if (m.F <= G) { if (g < m.F) atomicAdd(mrow + g, feat[g]); }
-            else for (int f = g; f < m.F; f += G) atomicAdd(mrow + f, feat[f]);
-            if (g == 0) atomicAdd(reinterpret_cast<unsigned long long*>(wlO + bin), 1ull);
+            if (m.F <= G) { if (g < m.F) red_add_f64(mrow + g, feat[g]); }
+            else for (int f = g; f < m.F; f += G) red_add_f64(mrow + f, feat[f]);
+            if (g == 0) red_add_u64(wlO + bin, 1ull);
           } else {
             const long long total = __ldcg(wlO + bin);
             const double inv = 1.0 / (double)(total + 1);
@@ -1213,7 +1213,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
                 wlHs[bin] += 1;
               } else {
                 __stcg(wlS + bin, s_cur);
-                atomicAdd(reinterpret_cast<unsigned long long*>(wlH + bin), 1ull);
+                red_add_u64(wlH + bin, 1ull);
               }
             }
           }
