@@ -15,7 +15,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   --log-file $OUT/${TAG}_launches_bench_cfg2.csv python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/${TAG}_bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lmc_spec_kernel -s 3 -c 1 \
   -f -o $OUT/${TAG}_spec_cfg2 python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1
-ls -la $OUT
-# other BASELINE configs (kernel-only) and their ncu captures:
-#   python scripts/config_bench.py 3 4 5 > gpurun_out/configs.jsonl
+# other BASELINE configs (kernel-only) and the ncu capture of the Wang-Landau kernel (config 4)
+timeout 300 python scripts/config_bench.py 3 4 5 > $OUT/${TAG}_configs_3_4_5.jsonl 2> $OUT/${TAG}_configs.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:lmc_run_kernel -s 2 -c 1 \
+  -f -o $OUT/${TAG}_cfg4 python scripts/config_bench.py 4 > $OUT/${TAG}_cfg4_ncu.log 2>&1
+ls -la $OUT | tail -20
 #   ncu --set full --clock-control none --import-source on -k regex:lmc_run_kernel -s 2 -c 1 -f -o gpurun_out/cfg5 python scripts/config_bench.py 5

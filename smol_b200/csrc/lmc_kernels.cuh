@@ -1117,6 +1117,15 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
             dvec[f] += dvec[m.F + f] * inv_size;
             feat[f] = f > 0 ? dvec[2 * m.F + f] : dist_L;
           }
+        } else if (USHER == LMC_USHER_TABLEFLIP) {
+          // one copy of the fold (this variant is bound by instruction fetch, see above)
+#pragma unroll 1
+          for (int f = 0; f < st.n; ++f) {
+            if (f > 0) group_sync<G>(gmask);
+            const int sf = pick<MF>(st.site, f);
+            flip_features<G, KONE>(m, t, sf, stash0 + f * stash_stride, feat, g,
+                                   f == 0 ? seg0 : (f == 1 ? seg1 : load_segment<G>(m, sf, g)));
+          }
         } else {
 #pragma unroll
           for (int f = 0; f < MF; ++f)
