@@ -287,8 +287,8 @@ def run_ours(args):
     traffic = None
     try:
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel this bench runs, from the
-        # committed ncu --set full capture (profiles/r01d_lmc_spec_cfg2.md)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01d_summary.json")))
+        # committed ncu --set full capture (profiles/r01e_lmc_spec_cfg2.md)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01e_summary.json")))
         traffic = prof.get("dram_bytes_per_launch_at_bench_size")
     except Exception:
         pass
@@ -318,7 +318,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_attempted_step": ALGO_BYTES_PER_STEP,
                      "note": "sparse integer gather-reduce on an L2/SMEM-resident working set: DRAM traffic is far "
                              "below the algorithmic bytes; the kernel is bound by the L1/shared-memory data pipe "
-                             "(l1tex__data_pipe_lsu_wavefronts 86.5 % of peak, profiles/r01d_lmc_spec_cfg2.md)"},
+                             "(l1tex__data_pipe_lsu_wavefronts 88 % of peak, profiles/r01e_lmc_spec_cfg2.md)"},
         "cpu_baseline": {"value": cpu_rate, "unit": "steps/s", "cores": cores, "kind": kind,
                          "sample": sample},
         "cpu_port": {"value": port_rate, "unit": "steps/s", "cores": cores, "kind": "port",
