@@ -58,7 +58,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 12
+#define LMC_ABI_VERSION 13
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -227,6 +227,14 @@ typedef struct LmcRunConfig {
   int32_t ms_len[LMC_MAX_COMPOSITE];
   double ms_cum[LMC_MAX_COMPOSITE];                              /* cumulative probabilities of the lengths */
   LmcWangLandau wl;           /* used when kernel == LMC_KERNEL_WANGLANDAU */
+  /* Multicell sampling (MulticellKernel, kernel/base.py:439-722: one chain hops between supercell shapes, each with
+     its own occupancy; the host keeps one state array per shape and drives them with these two):
+     walker_mask_dev: only walkers with a non-zero byte take part in this call (the others keep their state and
+     their trace rows are not written); accept_offset_dev: added to the enthalpy change inside the Metropolis
+     exponent only -- a hop into shape k' is one step of k' judged by H_k'(after) - H_current
+     = dH_step + (H_k' - H_current) (base.py:612-622).  Classic Metropolis kernels; both may be NULL. */
+  const uint8_t* walker_mask_dev;   /* [W] */
+  const double* accept_offset_dev;  /* [W] */
 } LmcRunConfig;
 
 int lmc_version(void);

@@ -1221,3 +1221,104 @@ def run_sampler(kernels, initial_occupancies, nsteps, thin_by=1):
         if has_bias:
             out["bias"][s] = bias
     return out
+
+
+class MulticellMetropolis:
+    """kernel/base.py:439-722 (MulticellKernel) + kernel/metropolis.py:102-175 for ONE chain.
+
+    ``mckernels``: oracle ``Metropolis`` kernels, one per supercell shape, all of one walker.  The shape and
+    hop-period choices come from ``numpy.random.default_rng(seed).choice(..., p=...)`` in the reference's order
+    (base.py:530-533, 664, 678-680).  Proposals and acceptance uniforms are counter based (Philox keyed by the
+    sub-kernel's seed, counter = the chain's global step index, set by the caller through ``step_index``); the
+    reference draws a hop's uniform from the multicell generator (metropolis.py:46-48), data dependent."""
+
+    def __init__(self, mckernels, temperature, kernel_probabilities=None, kernel_hop_periods=5,
+                 kernel_hop_probabilities=None, seed=None, kB_=kB):
+        self._kernels = list(mckernels)
+        nk = len(self._kernels)
+        self._kernel_p = np.array(kernel_probabilities if kernel_probabilities is not None else [1.0 / nk] * nk)
+        self._hop_periods = np.array([kernel_hop_periods] if isinstance(kernel_hop_periods, int)
+                                     else kernel_hop_periods, dtype=int)
+        nh = len(self._hop_periods)
+        self._hop_p = np.array(kernel_hop_probabilities if kernel_hop_probabilities is not None else [1.0 / nh] * nh)
+        self._rng = np.random.default_rng(seed)
+        self.temperature, self.kB = temperature, kB_
+        self.natural_params = self._kernels[0].natural_params
+        self._current_hop_period = self._rng.choice(self._hop_periods, p=self._hop_p)     # base.py:532
+        self._kernel_hop_counter = 1
+        self._current_kernel_index = 0
+        self._features = np.zeros((nk, len(self.natural_params)))
+        self._occupancies = None
+        self.step_index = 0
+
+    @property
+    def beta(self):
+        return 1.0 / (self.kB * self.temperature)
+
+    def set_aux_state(self, occupancies):
+        """base.py:694-716: one occupancy per shape."""
+        self._occupancies = [np.array(o, dtype=np.int32) for o in occupancies]
+        for i, (k, o) in enumerate(zip(self._kernels, self._occupancies)):
+            self._features[i] = k.ensemble.compute_feature_vector(o)
+
+    def single_step(self):
+        """base.py:645-692.  Returns (accepted, current kernel index)."""
+        t = self.step_index
+        self.step_index += 1
+        if self._kernel_hop_counter % self._current_hop_period == 0:
+            new = int(self._rng.choice(len(self._kernels), p=self._kernel_p))              # base.py:664
+            k = self._kernels[new]
+            occ = self._occupancies[new]
+            rnd = StepRandom(k.seed, k.walker, t)
+            step = k.usher.propose_step(occ, rnd)
+            trial = occ.copy()
+            for site, sp in step:                                                            # base.py:612-614
+                trial[site] = sp
+            new_features = np.array(k.ensemble.compute_feature_vector(trial), dtype=np.float64)
+            dfeat = new_features - self._features[self._current_kernel_index]                # base.py:616-619
+            dH = _dot_seq(self.natural_params, dfeat)
+            exponent = -self.beta * dH + k.usher.compute_log_priori_factor(occ, step)       # metropolis.py:40-41
+            accepted = True if exponent >= 0 else exponent > math.log(u01(rnd.word(3)))
+            if accepted:                                                                     # base.py:637-642, 665-669
+                occ[:] = trial
+                self._features[new] = new_features
+                self._current_kernel_index = new
+            self._current_hop_period = self._rng.choice(self._hop_periods, p=self._hop_p)   # base.py:678-680
+            self._kernel_hop_counter = 1
+        else:
+            cur = self._current_kernel_index
+            k = self._kernels[cur]
+            k.step_index = t
+            st = k.single_step(self._occupancies[cur])
+            self._kernel_hop_counter += 1
+            accepted = st.accepted
+            if accepted:
+                self._features[cur] += st.dfeatures                                          # base.py:686-689
+        return accepted, self._current_kernel_index
+
+
+def run_multicell(chains, initial_occupancies, nsteps, thin_by=1):
+    """``chains``: one ``MulticellMetropolis`` per walker; ``initial_occupancies [W][K][N]``.  Sampled arrays
+    ``[S, W, ...]`` of the CURRENT shape's state (occupancy, features, enthalpy) plus ``kernel_index``."""
+    W = len(chains)
+    for c, o in zip(chains, initial_occupancies):
+        c.set_aux_state(o)
+    S = nsteps // thin_by
+    N, F = len(initial_occupancies[0][0]), len(chains[0].natural_params)
+    out = dict(occupancy=np.zeros((S, W, N), dtype=np.int32), features=np.zeros((S, W, F)),
+               enthalpy=np.zeros((S, W, 1)), accepted=np.zeros((S, W, 1), dtype=bool),
+               n_accepted=np.zeros((S, W), dtype=np.int64), kernel_index=np.zeros((S, W, 1), dtype=np.int64))
+    for s in range(S):
+        for i, c in enumerate(chains):
+            nacc, acc = 0, True
+            for _ in range(thin_by):
+                acc, _ = c.single_step()
+                nacc += bool(acc)
+            cur = c._current_kernel_index
+            out["occupancy"][s, i] = c._occupancies[cur]
+            out["features"][s, i] = c._features[cur]
+            out["enthalpy"][s, i, 0] = _dot_seq(c.natural_params, c._features[cur])
+            out["accepted"][s, i, 0] = acc
+            out["n_accepted"][s, i] = nacc
+            out["kernel_index"][s, i, 0] = cur
+    return out

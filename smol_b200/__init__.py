@@ -8,9 +8,10 @@ the C ABI of ``include/lmc.h``; this package is the Python host side mirroring
 from .ensemble import Ensemble
 from .processor import (ClusterDecompositionProcessor, ClusterExpansionProcessor, ClusterInteractionDistanceProcessor,
                         CompositeProcessor, CorrelationDistanceProcessor, EwaldProcessor)
+from .multicell import MulticellSampler
 from .sampler import Sampler
 from .sublattice import Sublattice
 
-__all__ = ["Ensemble", "Sampler", "Sublattice", "ClusterExpansionProcessor",
+__all__ = ["Ensemble", "Sampler", "MulticellSampler", "Sublattice", "ClusterExpansionProcessor",
            "ClusterDecompositionProcessor", "EwaldProcessor", "CompositeProcessor",
            "CorrelationDistanceProcessor", "ClusterInteractionDistanceProcessor"]

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 12
+LMC_ABI_VERSION = 13
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -109,6 +109,7 @@ class LmcRunConfig(C.Structure):
         ("ms_usher", C.c_int32), ("ms_num", C.c_int32), ("ms_len", C.c_int32 * LMC_MAX_COMPOSITE),
         ("ms_cum", C.c_double * LMC_MAX_COMPOSITE),
         ("wl", LmcWangLandau),
+        ("walker_mask_dev", _P), ("accept_offset_dev", _P),
     ]
 
 

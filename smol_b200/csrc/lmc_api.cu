@@ -832,7 +832,9 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
       return fail("distance processor pointers must not be null");
     if (c->bias_mode != LMC_BIAS_NONE) return fail("bias terms are not combined with distance processors");
   }
-  const bool spec_ok = m.spOK && !dist && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
+  const bool multicell = c->walker_mask_dev != nullptr || c->accept_offset_dev != nullptr;
+  if (multicell && c->kernel != LMC_KERNEL_METROPOLIS) return fail("walker_mask_dev / accept_offset_dev are for Metropolis kernels");
+  const bool spec_ok = m.spOK && !dist && !multicell && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
                        (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
   if (spec_mode == 2 && !spec_ok)
     return fail("the speculative kernel supports unbiased Metropolis flip/swap steps (an Ewald term through ewald_field_dev only)");
@@ -892,7 +894,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   }
   a.ms_usher = c->ms_usher; a.ms_num = c->usher == LMC_USHER_MULTISTEP ? c->ms_num : 0;
   for (int i = 0; i < LMC_MAX_COMPOSITE; ++i) { a.ms_len[i] = c->ms_len[i]; a.ms_cum[i] = c->ms_cum[i]; }
-  a.stats = mm->stats_dev;
+  a.stats = multicell ? nullptr : mm->stats_dev;   // (masked launches would skew the acceptance feedback)
+  a.mask = c->walker_mask_dev; a.acc_off = c->accept_offset_dev;
   if (!a.seeds || !a.occ || !a.features || !a.enthalpy) return fail("state pointers must not be null");
   if (c->kernel != LMC_KERNEL_WANGLANDAU && !a.beta) return fail("beta_dev must not be null");
   // per-walker shared-memory slab: [features][stash x MAX_FLIPS][counts]

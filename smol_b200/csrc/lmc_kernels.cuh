@@ -562,7 +562,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   const int wl_ = threadIdx.x / G;                  // walker slot in block
   const int w = blockIdx.x * a.wpb + wl_;            // walker on this device
   const int nw_blk = min(a.wpb, a.W - blockIdx.x * a.wpb);
-  const bool active = wl_ < a.wpb && w < a.W;
+  const bool active = wl_ < a.wpb && w < a.W && (a.mask == nullptr || a.mask[min(w, a.W - 1)] != 0);
   const uint32_t gmask = group_mask<G>();
 
   unsigned char* wbase = smem + ((m.off_dtab + 15) & ~15);
@@ -612,6 +612,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   const uint32_t wid = (uint32_t)(a.walker_base + w);
   constexpr bool wl_mode = WLMODE;
   const double beta = wl_mode ? 0.0 : a.beta[w];
+  const double acc_off = (!WLMODE && a.acc_off) ? a.acc_off[w] : 0.0;
   const double nat_ew = EWALD ? t.nat[m.ewF] : 0.0;
   const double nat_mu = m.muW ? t.nat[m.muF] : 0.0;
 
@@ -1088,7 +1089,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       double dbias = 0.0, dbc = 0.0;   // dbc: table difference of the last row (the only one for a table-sum bias)
       if (!wl_mode) {
         // MetropolisAcceptMixin._accept_step, kernel/metropolis.py:31-49
-        double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
+        // (multicell hop: judged by the enthalpy of the target shape's new state minus the current shape's)
+        double exponent = __dadd_rn(__dmul_rn(-beta, a.acc_off ? dH + acc_off : dH), st.log_priori);
         if (a.bias_mode) {
           // MCBias.compute_bias_change (bias.py:79-95, 193-214): table differences of the changed sites.
           // Square biases: bias(after) - bias(before) with bias = -penalty * sum_r c_r^2 (bias.py:276-287, 342-353);

@@ -123,6 +123,8 @@ struct RunArgs {
   int off_pref;       // Wang-Landau flips: records and segment entries of the next step (asynchronous prefetch)
   int off_wl;         // Wang-Landau: [entropy nb][histogram nb] of the walker in its slab, -1 = kept in global memory
   unsigned long long* stats;  // [2] accepted / attempted step totals (device counters; kernel selection feedback)
+  const uint8_t* mask;        // [W] multicell: walkers taking part in this launch (nullptr = all)
+  const double* acc_off;      // [W] multicell: enthalpy offset inside the Metropolis exponent (nullptr = 0)
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another
 };
