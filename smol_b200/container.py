@@ -140,10 +140,13 @@ class SampleContainer:
         return self.get_trace_value("features", discard, thin_by, flat)
 
     def get_energies(self, discard=0, thin_by=1, flat=True):
-        """container.py:208-229: energy = features[:n_energy] . coefs."""
-        feats = self.get_feature_vectors(discard, thin_by, flat)
+        """container.py:208-229: the enthalpies when there are no extra terms, else features[:n_energy] . coefs;
+        shape ``[..., 1]`` like the enthalpy trace."""
         n = self._ensemble.num_energy_coefs
-        return np.tensordot(feats[..., :n], self.natural_parameters[:n], axes=([-1], [0]))
+        if len(self.natural_parameters) == n:
+            return self.get_enthalpies(discard, thin_by, flat)
+        feats = self.get_feature_vectors(discard, thin_by, flat)
+        return np.tensordot(feats[..., :n], self.natural_parameters[:n], axes=([-1], [0]))[..., None]
 
     def get_temperatures(self, discard=0, thin_by=1):
         return self.get_trace_value("temperature", discard, thin_by, flat=False)[:, 0]
@@ -174,11 +177,67 @@ class SampleContainer:
         occus = self.get_occupancies(discard, thin_by, flat)
         return occus[inds[0]] if flat else occus[inds, np.arange(self._nwalkers)][0]
 
-    def get_species_counts(self, discard=0, thin_by=1, flat=True):
-        """container.py:336-347: counts per species code on each sublattice."""
+    def get_minimum_energy(self, discard=0, thin_by=1, flat=True):
+        """container.py:321-323."""
+        return self.get_energies(discard, thin_by, flat).min(axis=0)
+
+    def get_minimum_energy_occupancy(self, discard=0, thin_by=1, flat=True):
+        """container.py:325-334."""
+        inds = self.get_energies(discard, thin_by, flat).argmin(axis=0)
         occus = self.get_occupancies(discard, thin_by, flat)
-        out = {}
-        for i, s in enumerate(self.sublattices):
-            for sp, code in zip(s.species, s.encoding):
-                out[(i, sp)] = np.count_nonzero(occus[..., s.sites] == code, axis=-1)
-        return out
+        return occus[inds[0]] if flat else occus[inds, np.arange(self._nwalkers)][0]
+
+    def get_sublattice_species_counts(self, sublattice, discard=0, thin_by=1, flat=True):
+        """container.py:349-382: counts of each species of a sublattice, last axis in the order of its site space
+        (``sublattice.encoding``); one vectorised comparison per code instead of np.unique per sample."""
+        if not any(sublattice is s for s in self.sublattices) and sublattice not in list(self.sublattices):
+            raise ValueError("Sublattice provided is not recognized.\n Provide one included"
+                             " in the sublattices attribute of this SampleContainer.")
+        occus = self.get_occupancies(discard, thin_by, flat=False)[..., np.asarray(sublattice.sites, dtype=int)]
+        counts = np.stack([np.count_nonzero(occus == code, axis=-1) for code in sublattice.encoding],
+                          axis=-1).astype(np.float64)
+        return self._flatten(counts) if flat else counts
+
+    def get_species_counts(self, discard=0, thin_by=1, flat=True):
+        """container.py:336-347: counts per species summed over the sublattices, keyed by species."""
+        counts = {}
+        for s in self.sublattices:
+            sub = self.get_sublattice_species_counts(s, discard, thin_by, flat)
+            for sp, c in zip(s.species, np.moveaxis(sub, -1, 0)):
+                counts[sp] = counts[sp] + c if sp in counts else c.copy()
+        return counts
+
+    def get_sublattice_compositions(self, sublattice, discard=0, thin_by=1, flat=True):
+        """container.py:235-238."""
+        return self.get_sublattice_species_counts(sublattice, discard, thin_by, flat) / len(sublattice.sites)
+
+    def get_compositions(self, discard=0, thin_by=1, flat=True):
+        """container.py:240-243: species counts over ALL sites of the supercell."""
+        counts = self.get_species_counts(discard, thin_by, flat)
+        return {sp: c / self.shape[1] for sp, c in counts.items()}
+
+    def mean_composition(self, discard=0, thin_by=1, flat=True):
+        """container.py:283-286."""
+        return {sp: c.mean(axis=0) for sp, c in self.get_compositions(discard, thin_by, flat).items()}
+
+    def composition_variance(self, discard=0, thin_by=1, flat=True):
+        """container.py:288-291."""
+        return {sp: c.var(axis=0) for sp, c in self.get_compositions(discard, thin_by, flat).items()}
+
+    def mean_sublattice_composition(self, sublattice, discard=0, thin_by=1, flat=True):
+        """container.py:293-297."""
+        return self.get_sublattice_compositions(sublattice, discard, thin_by, flat).mean(axis=0)
+
+    def sublattice_composition_variance(self, sublattice, discard=0, thin_by=1, flat=True):
+        """container.py:299-305."""
+        return self.get_sublattice_compositions(sublattice, discard, thin_by, flat).var(axis=0)
+
+    def get_orbit_factors(self, function_orbit_ids, discard=0, thin_by=1, flat=True):
+        """container.py:269-281 (sum of natural parameter x feature over the functions of each orbit id)."""
+        vals = self.natural_parameters * self.get_feature_vectors(discard=discard, thin_by=thin_by, flat=flat)
+        ids = np.asarray(function_orbit_ids)
+        return np.array([np.sum(vals[..., ids == i]) for i in range(len(self.natural_parameters))])
+
+    def vacuum(self):
+        """container.py:399-411 trims unused pre-allocated rows; the chunks here hold sampled rows only."""
+        return None

@@ -129,9 +129,52 @@ def test_sample_container_accessors():
     assert c.get_occupancies().dtype == np.int32 and c.get_occupancies().shape == (15, 4)
     assert c.get_enthalpies(flat=False).shape == (5, 3, 1)
     assert c.sampling_efficiency() == 1.0 and c.step_efficiency() == 0.5
-    assert np.allclose(c.get_energies(), 3.0) and c.get_minimum_enthalpy()[0] == 0.0
+    # no extra terms: the energies ARE the enthalpies (container.py:210-211)
+    assert np.array_equal(c.get_energies(), c.get_enthalpies()) and c.get_minimum_enthalpy()[0] == 0.0
+    assert c.get_minimum_energy()[0] == 0.0 and c.get_minimum_energy_occupancy().shape == (4,)
     c.clear()
     assert c.num_samples == 0
+
+
+def test_sample_container_compositions_and_energies():
+    """accessors of smol/moca/sampler/container.py:208-382 on a hand-made chain"""
+    sl_a, sl_b = Sublattice(("A", "B"), np.array([0, 1, 2, 3])), Sublattice(("C", "A"), np.array([4, 5]))
+
+    class Ens:
+        sublattices = [sl_a, sl_b]
+        natural_parameters = np.array([1.0, 2.0, -1.0])      # two energy coefficients + chemical work
+        num_energy_coefs = 2
+    shapes = {"occupancy": ((6,), np.int32), "features": ((3,), np.float64), "enthalpy": ((1,), np.float64),
+              "accepted": ((1,), bool), "n_accepted": ((), np.int32)}
+    c = SampleContainer(Ens(), 2, shapes)
+    occ = np.array([[[0, 0, 1, 1, 0, 1], [1, 1, 1, 1, 0, 0]],
+                    [[0, 1, 1, 1, 1, 1], [0, 0, 0, 0, 1, 0]]], dtype=np.int8)     # [S=2][W=2][N=6]
+    feats = np.arange(12.0).reshape(2, 2, 3)
+    tr = dict(occupancy=occ, features=feats, enthalpy=(feats @ Ens.natural_parameters)[:, :, None],
+              accepted=np.ones((2, 2, 1), dtype=bool), n_accepted=np.ones((2, 2), dtype=np.int32))
+    c.append(tr, thinned_by=1)
+    # energies drop the chemical-work term and keep the trailing axis of the enthalpy trace
+    e = c.get_energies(flat=False)
+    assert e.shape == (2, 2, 1) and np.allclose(e[..., 0], feats[..., 0] + 2 * feats[..., 1])
+    assert c.get_energies().shape == (4, 1) and np.isclose(c.get_minimum_energy()[0], 2.0)
+    assert c.get_minimum_energy_occupancy().tolist() == occ[0, 0].tolist()
+    sub = c.get_sublattice_species_counts(sl_a, flat=False)
+    assert sub.shape == (2, 2, 2) and sub[0, 0].tolist() == [2, 2] and sub[1, 1].tolist() == [4, 0]
+    assert c.get_sublattice_species_counts(sl_b).tolist() == [[1, 1], [2, 0], [0, 2], [1, 1]]
+    counts = c.get_species_counts(flat=False)
+    assert set(counts) == {"A", "B", "C"}                      # species A lives on both sublattices
+    assert counts["A"].tolist() == [[3, 0], [3, 5]] and counts["B"].tolist() == [[2, 4], [3, 0]]
+    comps = c.get_compositions()
+    assert np.allclose(sum(comps.values()), 1.0) and np.allclose(comps["C"], np.array([1, 2, 0, 1]) / 6)
+    assert np.allclose(c.mean_composition()["A"], np.mean([3, 0, 3, 5]) / 6)
+    assert np.allclose(c.composition_variance()["B"], np.var(np.array([2, 4, 3, 0]) / 6))
+    assert np.allclose(c.mean_sublattice_composition(sl_a), [(2 + 0 + 1 + 4) / 16, (2 + 4 + 3 + 0) / 16])
+    assert np.allclose(c.sublattice_composition_variance(sl_b), np.var(np.array([[1, 1], [2, 0], [0, 2], [1, 1]]) / 2, axis=0))
+    with pytest.raises(ValueError, match="not recognized"):
+        c.get_sublattice_species_counts(Sublattice(("X", "Y"), np.array([0, 1])))
+    of = c.get_orbit_factors(np.array([0, 1, 1]))
+    vals = Ens.natural_parameters * feats.reshape(4, 3)
+    assert np.isclose(of[0], vals[:, 0].sum()) and np.isclose(of[1], vals[:, 1:].sum()) and of[2] == 0.0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
