@@ -40,6 +40,10 @@
  *                            (smol/moca/processor/distance.py:133-180, 281-331, 424-472) over
  *                            ClusterSpaceEvaluator.corr_distances / interaction_distances_from_occupancies
  *                            (smol/utils/cluster/evaluator.pyx:319-435)
+ *   LmcRunConfig.walker_mask_dev / accept_offset_dev <- MulticellKernel.single_step / _compute_step_trace
+ *                            (smol/moca/kernel/base.py:612-622, 645-692; MulticellMetropolis,
+ *                            kernel/metropolis.py:102-175): one lmc_run per supercell shape over the walkers
+ *                            sitting in it, hops judged by H_k'(new) - H_current
  *   lmc_cast_*            <- the int32 occupancy dtype contract (sampler.py:406)
  *
  * Conventions: every function returns 0 on success, <0 on error (message via lmc_last_error);
