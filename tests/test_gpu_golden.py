@@ -63,3 +63,13 @@ def test_processor_api_single_calls_and_errors(cuda_device):
     assert np.array_equal(proc.compute_feature_vector_change(occ, []), np.zeros(8))
     with pytest.raises(ValueError):
         S.ClusterExpansionProcessor(sub, scm, coefs[:-1])
+
+
+def test_cuda_matches_reference_known_answer_licabr(cuda_device):
+    """the CUDA full-vector kernel on the reference's stored correlation vector (test_clusterspace.py:663-725)"""
+    import smol_b200 as S
+    from tests.test_oracle_golden import LICABR_EXPECTED, licabr_case
+    sub, scm, occ = licabr_case()
+    proc = S.ClusterExpansionProcessor(sub, scm, np.ones(sub.num_corr_functions))
+    corr = proc.compute_feature_vector(occ) / sub.supercell_size(scm)
+    np.testing.assert_allclose(corr, LICABR_EXPECTED, rtol=1e-12, atol=1e-14)
