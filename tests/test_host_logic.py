@@ -295,3 +295,37 @@ def test_interop_extracts_a_smol_like_ensemble():
     with pytest.raises(NotImplementedError):
         interop.from_smol_processor(SimpleNamespace(cluster_subspace=smol_subspace, supercell_matrix=scm,
                                                     allowed_species=allowed))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """the ctypes mirrors in smol_b200/_capi.py have the size and field offsets gcc gives the structs of
+    include/lmc.h (an ABI drift here would silently shift every pointer of a run configuration)"""
+    import ctypes
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"LmcRunConfig": capi.LmcRunConfig, "LmcWangLandau": capi.LmcWangLandau, "LmcModelDesc": capi.LmcModelDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lmc.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name} {field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        if not line:
+            continue
+        name, field, value = line.split()
+        cls = structs[name]
+        expect = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == expect, f"{name}.{field}: C {value} vs ctypes {expect}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
