@@ -72,6 +72,10 @@ class MulticellSampler:
             raise ValueError("All ensembles must have the same number of sites.")                 # base.py:485-489
         if any(not np.allclose(e.natural_parameters, ensembles[0].natural_parameters) for e in ensembles):
             raise ValueError("All ensembles must have the same natural parameters.")              # base.py:491-495
+        from .processor import DistanceProcessor
+        if any(isinstance(e.processor, DistanceProcessor) for e in ensembles):
+            # (the distance kernels keep a running correlation vector per walker that this driver does not set up yet)
+            raise NotImplementedError("MulticellSampler does not drive distance processors yet")
         K = len(ensembles)
         if kernel_probabilities is not None:
             if sum(kernel_probabilities) != 1.0:
