@@ -55,7 +55,7 @@ def test_oracle_single_shape_is_plain_metropolis():
     sub = M.fcc_subspace()
     coefs = M.fcc_coefs(sub)
     shapes = [SHAPES[0]]
-    pens = _product_like_sublattices(O, sub, shapes)
+    pens = _product_ensembles(sub, coefs, shapes)     # host-only objects: their sublattices feed the oracle
     occ0 = M.random_occupancies(sub, shapes[0], 1, seed=3, balanced=True)
     chain = _oracle_chain(O, sub, coefs, shapes, pens, 2000.0, "swap", 5, [123], 0, kernel_hop_periods=3)
     got = O.run_multicell([chain], occ0[:, None, :], 240, 8)
@@ -65,17 +65,6 @@ def test_oracle_single_shape_is_plain_metropolis():
     np.testing.assert_array_equal(got["accepted"], ref["accepted"])
     np.testing.assert_allclose(got["enthalpy"], ref["enthalpy"], rtol=1e-12, atol=1e-12)
     assert 0 < got["n_accepted"].sum() < 240
-
-
-class _Sl:   # the oracle only needs the sublattice attributes
-    def __init__(self, sublattices):
-        self.sublattices = sublattices
-
-
-def _product_like_sublattices(O, sub, shapes):
-    """sublattices of the product ensembles without touching the GPU (Ensemble construction is host only)"""
-    coefs = M.fcc_coefs(sub)
-    return _product_ensembles(sub, coefs, shapes)
 
 
 def test_oracle_multicell_tracks_full_features():
