@@ -1229,11 +1229,19 @@ class MulticellMetropolis:
     ``mckernels``: oracle ``Metropolis`` kernels, one per supercell shape, all of one walker.  The shape and
     hop-period choices come from ``numpy.random.default_rng(seed).choice(..., p=...)`` in the reference's order
     (base.py:530-533, 664, 678-680).  Proposals and acceptance uniforms are counter based (Philox keyed by the
-    sub-kernel's seed, counter = the chain's global step index, set by the caller through ``step_index``); the
-    reference draws a hop's uniform from the multicell generator (metropolis.py:46-48), data dependent."""
+    sub-kernel's seed, counter = the chain's global step index); the reference draws a hop's uniform from the
+    multicell generator (metropolis.py:46-48), data dependent.
+
+    ``share_visited`` (default, what the reference DOES): ``MCKernel.single_step`` stores the array it was handed as
+    ``trace.occupancy`` without copying (base.py:162), and the sampler hands every kernel the chain's one live row
+    (sampler.py:436-440).  So once a shape has taken an ordinary step (or had a hop away from it rejected,
+    base.py:671-674) its "own" occupancy IS the chain's live occupancy: a later hop into it starts from the current
+    occupancy string re-read in that shape's supercell, and only shapes never visited keep the occupancy given at
+    set_aux_state.  Pinned against the reference's class in tests/golden/ref_python_steps.npz.
+    ``share_visited=False`` is the documented intent (base.py:665-666: every shape keeps an occupancy of its own)."""
 
     def __init__(self, mckernels, temperature, kernel_probabilities=None, kernel_hop_periods=5,
-                 kernel_hop_probabilities=None, seed=None, kB_=kB):
+                 kernel_hop_probabilities=None, seed=None, kB_=kB, share_visited=True):
         self._kernels = list(mckernels)
         nk = len(self._kernels)
         self._kernel_p = np.array(kernel_probabilities if kernel_probabilities is not None else [1.0 / nk] * nk)
@@ -1249,6 +1257,8 @@ class MulticellMetropolis:
         self._current_kernel_index = 0
         self._features = np.zeros((nk, len(self.natural_params)))
         self._occupancies = None
+        self.share_visited = bool(share_visited)
+        self._live, self._alias = None, [False] * nk
         self.step_index = 0
 
     @property
@@ -1256,10 +1266,21 @@ class MulticellMetropolis:
         return 1.0 / (self.kB * self.temperature)
 
     def set_aux_state(self, occupancies):
-        """base.py:694-716: one occupancy per shape."""
+        """base.py:694-716: one occupancy per shape; the chain's live row starts as a copy of shape 0's
+        (sampler.py:411-418)."""
         self._occupancies = [np.array(o, dtype=np.int32) for o in occupancies]
         for i, (k, o) in enumerate(zip(self._kernels, self._occupancies)):
             self._features[i] = k.ensemble.compute_feature_vector(o)
+        self._live = self._occupancies[self._current_kernel_index].copy()
+        self._alias = [False] * len(self._kernels)
+
+    def occupancy_of(self, k):
+        """the array shape k would read as its own"""
+        return self._live if (self.share_visited and self._alias[k]) else self._occupancies[k]
+
+    @property
+    def current_occupancy(self):
+        return self._live if self.share_visited else self._occupancies[self._current_kernel_index]
 
     def single_step(self):
         """base.py:645-692.  Returns (accepted, current kernel index)."""
@@ -1268,7 +1289,7 @@ class MulticellMetropolis:
         if self._kernel_hop_counter % self._current_hop_period == 0:
             new = int(self._rng.choice(len(self._kernels), p=self._kernel_p))              # base.py:664
             k = self._kernels[new]
-            occ = self._occupancies[new]
+            occ = self.occupancy_of(new)
             rnd = StepRandom(k.seed, k.walker, t)
             step = k.usher.propose_step(occ, rnd)
             trial = occ.copy()
@@ -1283,13 +1304,19 @@ class MulticellMetropolis:
                 occ[:] = trial
                 self._features[new] = new_features
                 self._current_kernel_index = new
+                if self.share_visited:
+                    self._live[:] = occ                                                      # base.py:669
+            elif self.share_visited:
+                self._alias[self._current_kernel_index] = True                               # base.py:672-673
             self._current_hop_period = self._rng.choice(self._hop_periods, p=self._hop_p)   # base.py:678-680
             self._kernel_hop_counter = 1
         else:
             cur = self._current_kernel_index
             k = self._kernels[cur]
             k.step_index = t
-            st = k.single_step(self._occupancies[cur])
+            st = k.single_step(self.current_occupancy)                                       # base.py:684 / 162
+            if self.share_visited:
+                self._alias[cur] = True
             self._kernel_hop_counter += 1
             accepted = st.accepted
             if accepted:
@@ -1315,7 +1342,7 @@ def run_multicell(chains, initial_occupancies, nsteps, thin_by=1):
                 acc, _ = c.single_step()
                 nacc += bool(acc)
             cur = c._current_kernel_index
-            out["occupancy"][s, i] = c._occupancies[cur]
+            out["occupancy"][s, i] = c.current_occupancy
             out["features"][s, i] = c._features[cur]
             out["enthalpy"][s, i, 0] = _dot_seq(c.natural_params, c._features[cur])
             out["accepted"][s, i, 0] = acc

@@ -63,7 +63,7 @@ class MulticellSampler:
     def __init__(self, ensembles, temperature, step_type="swap", nwalkers=1, seeds=None, kernel_seeds=None,
                  kernel_temperatures=None, kernel_probabilities=None, kernel_hop_periods=5,
                  kernel_hop_probabilities=None, sublattice_probabilities=None, walker_id_base=0, device=None,
-                 kB_=kB):
+                 kB_=kB, share_visited=True):
         from .engine import LmcEngine
         ensembles = list(ensembles)
         if not ensembles:
@@ -117,6 +117,14 @@ class MulticellSampler:
         self.kernel_temperatures = np.full(K, self.temperature) if kernel_temperatures is None \
             else np.array(kernel_temperatures, dtype=np.float64)
         self.walker_id_base = int(walker_id_base)
+        # What the reference does (default): MCKernel.single_step keeps the array it was handed as its trace occupancy
+        # without copying (base.py:162) and the sampler hands every kernel the chain's one live row, so a shape that
+        # has taken an ordinary step -- or had a hop away from it rejected (base.py:671-674) -- shares the chain's live
+        # occupancy from then on: a later hop into it starts from the CURRENT occupancy string re-read in that shape,
+        # and only shapes never visited keep the occupancy given at the start.  False: every shape keeps an
+        # occupancy of its own (the intent documented at base.py:665-666).  Both are restated in the oracle; the
+        # default is pinned against the reference's class (tests/golden/ref_python_steps.npz).
+        self.share_visited = bool(share_visited)
         self.engines = [LmcEngine(e.packed_model(sublattice_probabilities=sublattice_probabilities), device=device)
                         for e in ensembles]
         # hop schedule state per walker (base.py:530-533: the first period is drawn in the constructor)
@@ -207,6 +215,7 @@ class MulticellSampler:
             st["nacc_tmp"] = torch.zeros((W,), dtype=torch.int32, device=dev)
             st["acc_last"] = torch.ones((W,), dtype=torch.uint8, device=dev)
             st["ktemp"] = torch.from_numpy(self.kernel_temperatures.copy()).to(dev)
+            st["alias"] = [torch.zeros((W,), dtype=torch.bool, device=dev) for _ in range(K)]
             self._state = st
         st = self._state
         if nsteps % thin_by != 0:
@@ -234,6 +243,7 @@ class MulticellSampler:
                     m = mask.bool()
                     st["acc_last"] = torch.where(m, st["acc_tmp"], st["acc_last"])
                     nacc += torch.where(m, st["nacc_tmp"], torch.zeros_like(nacc))
+                    st["alias"][k] = st["alias"][k] | m
                 self._counter += seg
                 t += seg
             else:
@@ -243,7 +253,8 @@ class MulticellSampler:
                 target = np.array([self._draw_kernel(w) if hop[w] else -1 for w in range(W)], dtype=np.int64)
                 hop_d, target_d = torch.from_numpy(hop).to(dev), torch.from_numpy(target).to(dev)
                 cur0 = st["cur"].clone()
-                h_cur = torch.stack(st["enth"])[cur0, ar]          # enthalpy of the current shape's state
+                h_cur = torch.stack(st["enth"])[cur0, ar]          # (tracked) enthalpy of the current shape's state
+                live = torch.stack(st["occ"])[cur0, ar]            # the chain's live occupancy rows
                 if not hop.all():
                     for k in range(K):
                         mask = ((cur0 == k) & ~hop_d).to(torch.uint8)
@@ -251,15 +262,28 @@ class MulticellSampler:
                         m = mask.bool()
                         st["acc_last"] = torch.where(m, st["acc_tmp"], st["acc_last"])
                         nacc += torch.where(m, st["nacc_tmp"], torch.zeros_like(nacc))
+                        st["alias"][k] = st["alias"][k] | m
                 for k in sorted(set(int(x) for x in target[hop])):
-                    mask = (target_d == k).to(torch.uint8)
+                    m = target_d == k
+                    if self.share_visited:
+                        # a visited shape reads the live occupancy: re-read those rows in shape k and evaluate them
+                        # in full there (base.py:612-616 computes the new state's features from scratch)
+                        r = m & st["alias"][k]
+                        st["occ"][k] = torch.where(r[:, None], live, st["occ"][k])
+                        f_new, h_new = self.engines[k].full_features(st["occ"][k])
+                        st["feat"][k] = torch.where(r[:, None], f_new, st["feat"][k])
+                        st["enth"][k] = torch.where(r, h_new, st["enth"][k])
+                    mask = m.to(torch.uint8)
                     offset = st["enth"][k] - h_cur
                     self._launch(k, 1, self._step_counter + t, mask, st["beta_mc"], offset)
-                    m = mask.bool()
                     took = m & (st["acc_tmp"] != 0)
                     st["cur"] = torch.where(took, torch.full_like(st["cur"], k), st["cur"])
                     st["acc_last"] = torch.where(m, st["acc_tmp"], st["acc_last"])
                     nacc += torch.where(m, st["nacc_tmp"], torch.zeros_like(nacc))
+                    if self.share_visited:
+                        stay = m & ~took                           # rejected: the shape hopped FROM now holds the live row
+                        for c in range(K):
+                            st["alias"][c] = st["alias"][c] | (stay & (cur0 == c))
                 for w in np.nonzero(hop)[0]:
                     self._period[w] = self._draw_period(w)     # base.py:678-682
                     self._counter[w] = 1

@@ -1,0 +1,250 @@
+"""Golden step records from the reference's OWN Python kernels (run in the build container only).
+
+``smol.moca`` cannot be imported as a package here (pymatgen / monty / h5py are not installed), but the modules of
+the step loop itself -- ``smol/moca/kernel/{base,metropolis,wanglandau,mcusher}.py``, ``smol/moca/trace.py``,
+``smol/utils/math.py`` ... -- only need ``monty.json`` / ``monty.dev`` names and two helper modules at import time.
+This script registers empty package shells for ``smol`` (so that no ``__init__`` pulls pymatgen in), four stub modules,
+imports the UNMODIFIED reference files from ``/root/reference`` and drives their ``Metropolis`` / ``WangLandau``
+kernels with ``Flip`` / ``Swap`` ushers step by step.
+
+The reference draws from ``numpy.random.Generator`` (a data-dependent number of draws per step); the oracle and the
+CUDA engine use counter-based Philox words at fixed positions.  To compare STEP SEMANTICS the kernels' generator is
+replaced by ``ScriptedRng``: the n-th ``choice`` / ``random`` call of a step returns what the oracle derives from the
+same Philox word (``choice(seq, p)`` = first index whose cumulative probability exceeds u01(word 0), ``choice(seq)`` =
+``seq[mulhi32(word, len(seq))]`` for words 1 and 2, ``random()`` = u01(word 3)).  Everything else -- proposal
+logic, feature / enthalpy deltas, acceptance rule, occupancy update, Wang-Landau bookkeeping -- is the reference's code.
+
+Feature vectors come from the oracle's processors (pure-Python evaluator restatements, themselves pinned against the
+reference's compiled evaluators in ``ref_vectors.npz``) through a duck-typed ensemble.
+
+Output: ``tests/golden/ref_python_steps.npz`` (per-step proposals, acceptance flags, enthalpy changes, occupancy
+snapshots, final Wang-Landau arrays).  ``tests/test_oracle_golden.py`` replays the oracle against it anywhere.
+
+    python tests/golden/make_reference_python_golden.py
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/smol"
+
+
+def import_reference_kernels():
+    def pkg(name, paths):
+        m = types.ModuleType(name)
+        m.__path__ = paths
+        m.__package__ = name
+        sys.modules[name] = m
+    for name, sub in [("smol", ""), ("smol.moca", "/moca"), ("smol.moca.kernel", "/moca/kernel"),
+                      ("smol.utils", "/utils"), ("smol.cofe", "/cofe"), ("smol.cofe.space", "/cofe/space"),
+                      ("smol.moca.composition", "/moca/composition")]:
+        pkg(name, [REF + sub])
+    mj = types.ModuleType("monty.json")
+    mj.MSONable = type("MSONable", (), {})
+    mj.jsanitize = lambda x, **k: x
+    mj.MontyDecoder = object
+    md = types.ModuleType("monty.dev")
+    md.requires = lambda cond, msg: (lambda f: f)
+    sys.modules.update({"monty": types.ModuleType("monty"), "monty.json": mj, "monty.dev": md})
+    sp = types.ModuleType("smol.moca.composition.space")       # only TableFlip / the charge bias use these
+    sp.CompositionSpace = type("CompositionSpace", (), {})
+    sp.get_oxi_state = lambda s: 0
+    sys.modules["smol.moca.composition.space"] = sp
+    dm = types.ModuleType("smol.cofe.space.domain")
+    dm.get_species = lambda s: s
+    dm.Vacancy = type("Vacancy", (), {})
+    sys.modules["smol.cofe.space.domain"] = dm
+    met = importlib.import_module("smol.moca.kernel.metropolis")
+    wl = importlib.import_module("smol.moca.kernel.wanglandau")
+    assert met.__file__.startswith(REF) and wl.__file__.startswith(REF)
+    return met.Metropolis, wl.WangLandau
+
+
+class ScriptedRng:
+    """Stands in for the kernels' numpy Generator: values follow the oracle's Philox word positions."""
+
+    def __init__(self, O, seed, walker):
+        self.O, self.seed, self.walker = O, seed, walker
+        self.rnd, self.plain = None, 0
+
+    def begin_step(self, t):
+        self.rnd, self.plain = self.O.StepRandom(self.seed, self.walker, t), 0
+
+    def choice(self, a, p=None):
+        if p is not None:                      # MCUsher.get_random_sublattice
+            u = self.O.u01(self.rnd.word(0))
+            cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+            cdf[-1] = 1.0
+            return a[int(np.searchsorted(cdf, u, side="right"))] if len(a) > 1 else a[0]
+        self.plain += 1
+        assert self.plain <= 2
+        return a[self.O.mulhi32(self.rnd.word(self.plain), len(a))]
+
+    def random(self):
+        return self.O.u01(self.rnd.word(3))
+
+
+def models():
+    """name -> (oracle ensemble factory, initial occupancies [W][N]); rebuilt identically by the test"""
+    from oracle import lmc_oracle as O
+    from smol_b200 import lattice as L
+    from tests import models as M
+    out = {}
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 3
+    it = L.cluster_interaction_tensors(sub, M.fcc_coefs(sub, seed=7))
+    subl = [O.Sublattice(("A", "B"), np.arange(27))]
+    out["fcc3"] = (lambda: O.Ensemble(O.ClusterDecompositionProcessor(sub, scm, it), subl),
+                   M.random_occupancies(sub, scm, 2, seed=4, balanced=False))
+    rs = M.rocksalt_subspace()
+    scm2 = np.eye(3, dtype=int) * 2
+    rng = np.random.default_rng(11)
+    it2 = L.cluster_interaction_tensors(rs, rng.normal(0, 0.05, rs.num_corr_functions))
+    spaces = rs.allowed_species(scm2)
+    cat = np.array([i for i, s in enumerate(spaces) if len(s) > 1])
+    ani = np.array([i for i, s in enumerate(spaces) if len(s) == 1])
+    subl2 = [O.Sublattice(("Li+", "Mn3+", "Ti4+"), cat), O.Sublattice(("O2-",), ani)]
+    mus = {"Li+": 0.0, "Mn3+": 0.3, "Ti4+": -0.2}
+    out["rs2"] = (lambda: O.Ensemble(O.ClusterDecompositionProcessor(rs, scm2, it2), subl2, chemical_potentials=mus),
+                  M.random_occupancies(rs, scm2, 2, seed=2))
+    return out
+
+
+MC_SHAPES = [np.diag([2, 2, 2]), np.diag([4, 2, 1]), np.array([[2, 1, 0], [0, 2, 0], [0, 0, 2]])]
+
+
+def multicell_model():
+    """(shapes, oracle ensemble factory per shape, initial occupancies [W][K][N]) of the multicell case"""
+    from oracle import lmc_oracle as O
+    from smol_b200 import lattice as L
+    from tests import models as M
+    sub = M.fcc_subspace()
+    it = L.cluster_interaction_tensors(sub, M.fcc_coefs(sub))
+    subl = [O.Sublattice(("A", "B"), np.arange(8))]
+    occ0 = np.stack([np.stack([M.random_occupancies(sub, scm, 1, seed=100 * w + k, balanced=True)[0]
+                               for k, scm in enumerate(MC_SHAPES)]) for w in range(2)])
+    return MC_SHAPES, (lambda k: O.Ensemble(O.ClusterDecompositionProcessor(sub, MC_SHAPES[k], it), subl)), occ0
+
+
+def record(kernel, rngs, occ, nsteps, snap_every):
+    """drive ONE reference kernel: per-step (accepted, proposal, enthalpy change), occupancy snapshots"""
+    occ = np.array(occ, dtype=np.int32)
+    acc = np.zeros(nsteps, dtype=bool)
+    prop = np.full((nsteps, 2, 2), -1, dtype=np.int64)
+    dh = np.zeros(nsteps)
+    snaps = []
+    kernel.set_aux_state(occ)
+    for t in range(nsteps):
+        rngs.begin_step(t)
+        # (the proposal is re-derived here only to RECORD it: same scripted words, no state change)
+        step = kernel.mcusher.propose_step(occ)
+        for j, (s, c) in enumerate(step):
+            prop[t, j] = (s, c)
+        rngs.begin_step(t)
+        trace = kernel.single_step(occ)
+        acc[t] = bool(trace.accepted)
+        dh[t] = float(trace.delta_trace.enthalpy)
+        if (t + 1) % snap_every == 0:
+            snaps.append(occ.copy())
+    return acc, prop, dh, np.array(snaps)
+
+
+def main():
+    from oracle import lmc_oracle as O
+    Metropolis, WangLandau = import_reference_kernels()
+    mods = models()
+    out = {}
+    nsteps, snap = 300, 25
+    for name, step_type, T in [("fcc3", "swap", 2000.0), ("fcc3", "flip", 2500.0), ("rs2", "flip", 3000.0)]:
+        factory, occ0 = mods[name]
+        for w in range(len(occ0)):
+            ens = factory()
+            seed = 1000 + 17 * w
+            k = Metropolis(ens, step_type, T, seed=seed)
+            rngs = ScriptedRng(O, seed, w)
+            k._rng = rngs
+            k.mcusher._rng = rngs
+            acc, prop, dh, snaps = record(k, rngs, occ0[w], nsteps, snap)
+            key = f"met_{name}_{step_type}_w{w}"
+            out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps})
+            out[key + "_meta"] = np.array([seed, T])
+    # Wang-Landau (flip) on the binary FCC cell
+    factory, occ0 = mods["fcc3"]
+    ens = factory()
+    e0 = np.array([float(np.dot(ens.natural_parameters, ens.compute_feature_vector(o))) for o in occ0])
+    lo, hi = float(e0.min() - 2.0), float(e0.max() + 2.0)
+    bin_size = (hi - lo) / 23.7
+    for w in range(len(occ0)):
+        ens = factory()
+        seed = 500 + w
+        k = WangLandau(ens, "flip", lo, hi, bin_size, flatness=0.3, check_period=40, seed=seed)
+        rngs = ScriptedRng(O, seed, w)
+        k._rng = rngs
+        k.mcusher._rng = rngs
+        acc, prop, dh, snaps = record(k, rngs, occ0[w], 600, 50)
+        key = f"wl_fcc3_flip_w{w}"
+        out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps,
+                    key + "_entropy": np.array(k._entropy), key + "_histogram": np.array(k._histogram),
+                    key + "_occurrences": np.array(k._occurrences), key + "_mean_features": np.array(k._mean_features),
+                    key + "_mod_factor": np.array([k._m])})
+        out[key + "_meta"] = np.array([seed, lo, hi, bin_size, 0.3, 40])
+    # MulticellMetropolis over three shapes of the 8-site FCC cell (uniform kernel probabilities: passing
+    # kernel_probabilities to the reference raises AttributeError, base.py:505 sets `kernel_p`, :543 reads `_kernel_p`)
+    MulticellMetropolis = importlib.import_module("smol.moca.kernel.metropolis").MulticellMetropolis
+    shapes, ens_of, mc_occ0 = multicell_model()
+    T, hop_periods, hop_p = 3000.0, [3, 5], [0.5, 0.5]
+    for w in range(len(mc_occ0)):
+        seed, kseeds = 11 + w, [1000 * (k + 1) + w for k in range(len(shapes))]
+        kernels, rngs = [], []
+        for k in range(len(shapes)):
+            kk = Metropolis(ens_of(k), "swap", T, seed=kseeds[k])
+            r = ScriptedRng(O, kseeds[k], w)
+            kk._rng = r
+            kk.mcusher._rng = r
+            kernels.append(kk)
+            rngs.append(r)
+        mc = MulticellMetropolis(kernels, T, seed=seed, kernel_hop_periods=hop_periods, kernel_hop_probabilities=hop_p)
+
+        class McRng:
+            """shape / period choices from numpy as in the reference; a hop's uniform = Philox word 3 of the target"""
+            def __init__(self):
+                self.np = np.random.default_rng(seed)
+                self.np.choice(np.array(hop_periods), p=hop_p)      # the draw of the constructor (base.py:532)
+                self.t = 0
+
+            def choice(self, a, p=None):
+                return self.np.choice(a, p=p)
+
+            def random(self):
+                return O.u01(O.StepRandom(kseeds[int(mc.trace.kernel_index)], w, self.t).word(3))
+        mrng = McRng()
+        mc._rng = mrng
+        mc.set_aux_state(np.array(mc_occ0[w], dtype=np.int32))
+        occ = np.array(mc_occ0[w][0], dtype=np.int32)       # the sampler's live row (sampler.py:411-418)
+        nst = 240
+        idx, acc, occs = np.zeros(nst, dtype=np.int64), np.zeros(nst, dtype=bool), np.zeros((nst, len(occ)), dtype=np.int32)
+        for t in range(nst):
+            for r in rngs:
+                r.begin_step(t)
+            mrng.t = t
+            tr = mc.single_step(occ)
+            idx[t], acc[t], occs[t] = int(mc._current_kernel_index), bool(tr.accepted), occ
+        key = f"mc_fcc8_swap_w{w}"
+        out.update({key + "_idx": idx, key + "_acc": acc, key + "_occ": occs,
+                    key + "_meta": np.array([seed, T, *kseeds])})
+    path = os.path.join(HERE, "ref_python_steps.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in list(out.items())[:6]})
+    for k in out:
+        if k.endswith("_acc"):
+            print(k, "accepted", int(out[k].sum()), "of", len(out[k]))
+
+
+if __name__ == "__main__":
+    main()
