@@ -26,6 +26,7 @@ import importlib
 import os
 import sys
 import types
+import warnings
 
 import numpy as np
 
@@ -53,7 +54,11 @@ def import_reference_kernels():
     md.requires = lambda cond, msg: (lambda f: f)
     sys.modules.update({"monty": types.ModuleType("monty"), "monty.json": mj, "monty.dev": md})
     sp = types.ModuleType("smol.moca.composition.space")       # only TableFlip / the charge bias use these
-    sp.CompositionSpace = type("CompositionSpace", (), {})
+    class CompositionSpace:                 # TableFlip with a given flip table only reads the constraint system
+        def __init__(self, bits, sublattice_sizes, **kwargs):
+            d = sum(len(b) for b in bits)
+            self._A, self._b, self.flip_table = np.zeros((0, d)), np.zeros(0), None
+    sp.CompositionSpace = CompositionSpace
     sp.get_oxi_state = lambda s: 0
     sys.modules["smol.moca.composition.space"] = sp
     dm = types.ModuleType("smol.cofe.space.domain")
@@ -88,6 +93,75 @@ class ScriptedRng:
 
     def random(self):
         return self.O.u01(self.rnd.word(3))
+
+
+class TableFlipRng(ScriptedRng):
+    """TableFlip.propose_step (mcusher.py:553-639): random() #1 = swap decision (word 0), choose_section_from_partition
+    = rng.choice(n, p) (word 1), choice(list, size=m, replace=False) = m sequential bounded draws from the shrinking
+    list (words 4, 5, ...: the oracle's restatement of numpy's sampling without replacement), last random() = accept
+    (word 3).  The fallback Swap usher of the reference owns a separate generator (mcusher.py:539: Swap(sublattices)
+    without rng); it gets ``swapper()`` below (words 4, 5, 6)."""
+
+    def begin_step(self, t):
+        super().begin_step(t)
+        self.nrandom, self.pick = 0, 4
+
+    def random(self):
+        self.nrandom += 1
+        return self.O.u01(self.rnd.word(0 if self.nrandom == 1 else 3))
+
+    def choice(self, a, p=None, size=None, replace=True):
+        if p is not None:
+            n = a if isinstance(a, (int, np.integer)) else len(a)
+            u = self.O.u01(self.rnd.word(1))
+            cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+            i = int(np.searchsorted(cdf, u, side="right"))
+            i = min(i, n - 1)
+            return i if isinstance(a, (int, np.integer)) else a[i]
+        assert size is not None and replace is False
+        pool, out = list(a), []
+        for _ in range(int(size)):
+            out.append(pool.pop(self.O.mulhi32(self.rnd.word(self.pick), len(pool))))
+            self.pick += 1
+        return np.array(out, dtype=int)
+
+    def swapper(self):
+        parent = self
+
+        class _Sw:
+            def choice(self, a, p=None):
+                if p is not None:
+                    u = parent.O.u01(parent.rnd.word(4))
+                    cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+                    cdf[-1] = 1.0
+                    return a[int(np.searchsorted(cdf, u, side="right"))] if len(a) > 1 else a[0]
+                parent.plain += 1
+                return a[parent.O.mulhi32(parent.rnd.word(4 + parent.plain), len(a))]
+        return _Sw()
+
+
+TF_TABLE = [[-1, 1, 0, 2, -2], [0, -1, 1, 1, -1]]     # SURVEY 8(d) config 5: charge-neutral, site-conserving flips
+
+
+def table_flip_model():
+    """5-species rocksalt 2x2x2 (8 cation + 8 anion sites), charge-neutral starts: (ensemble factory, occupancies)"""
+    from oracle import lmc_oracle as O
+    from smol_b200 import lattice as L
+    from tests import models as M
+    rs = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * 2
+    rng = np.random.default_rng(21)
+    it = L.cluster_interaction_tensors(rs, rng.normal(0, 0.03, rs.num_corr_functions))
+    spaces = rs.allowed_species(scm)
+    cat = np.array([i for i, s in enumerate(spaces) if len(s) == 3])
+    ani = np.array([i for i, s in enumerate(spaces) if len(s) == 2])
+    subl = [O.Sublattice(("Li+", "Mn3+", "Ti4+"), cat), O.Sublattice(("O2-", "F-"), ani)]
+    mus = {"Li+": 0.0, "Mn3+": 0.4, "Ti4+": -0.3, "O2-": 0.1, "F-": 0.0}
+    occ0 = np.zeros((2, len(spaces)), dtype=np.int32)
+    for w in range(2):      # 6 Li+, 1 Mn3+, 1 Ti4+ (charge 13) against 5 O2- and 3 F-
+        occ0[w, cat] = rng.permutation([0] * 6 + [1, 2])
+        occ0[w, ani] = rng.permutation([0] * 5 + [1] * 3)
+    return (lambda: O.Ensemble(O.ClusterDecompositionProcessor(rs, scm, it), subl, chemical_potentials=mus)), occ0
 
 
 def models():
@@ -136,7 +210,7 @@ def record(kernel, rngs, occ, nsteps, snap_every):
     """drive ONE reference kernel: per-step (accepted, proposal, enthalpy change), occupancy snapshots"""
     occ = np.array(occ, dtype=np.int32)
     acc = np.zeros(nsteps, dtype=bool)
-    prop = np.full((nsteps, 2, 2), -1, dtype=np.int64)
+    prop = np.full((nsteps, 4, 2), -1, dtype=np.int64)
     dh = np.zeros(nsteps)
     snaps = []
     kernel.set_aux_state(occ)
@@ -174,6 +248,22 @@ def main():
             key = f"met_{name}_{step_type}_w{w}"
             out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps})
             out[key + "_meta"] = np.array([seed, T])
+    # Metropolis + TableFlip (swap_weight 0.2) on the 5-species rocksalt cell
+    factory, occ0 = table_flip_model()
+    for w in range(len(occ0)):
+        seed = 700 + w
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")      # the constructor's trace-initialising step runs on an all-zero occupancy
+            k = Metropolis(factory(), "table-flip", 4000.0, seed=seed, flip_table=TF_TABLE, swap_weight=0.2)
+        assert type(k.mcusher).__name__ == "TableFlip"
+        rngs = TableFlipRng(O, seed, w)
+        k._rng = rngs
+        k.mcusher._rng = rngs
+        k.mcusher._swapper._rng = rngs.swapper()
+        acc, prop, dh, snaps = record(k, rngs, occ0[w], 400, 25)
+        key = f"met_rs2of_tableflip_w{w}"
+        out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps})
+        out[key + "_meta"] = np.array([seed, 4000.0, 0.2])
     # Wang-Landau (flip) on the binary FCC cell
     factory, occ0 = mods["fcc3"]
     ens = factory()
