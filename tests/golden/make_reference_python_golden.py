@@ -59,7 +59,11 @@ def import_reference_kernels():
             d = sum(len(b) for b in bits)
             self._A, self._b, self.flip_table = np.zeros((0, d)), np.zeros(0), None
     sp.CompositionSpace = CompositionSpace
-    sp.get_oxi_state = lambda s: 0
+    def get_oxi_state(label):               # 'Mn3+' -> 3, 'O2-' -> -2, 'F-' -> -1, 'A' -> 0
+        import re
+        m = re.search(r"(\d*)([+-])$", str(label))
+        return 0 if not m else (int(m.group(1) or 1) * (1 if m.group(2) == "+" else -1))
+    sp.get_oxi_state = get_oxi_state
     sys.modules["smol.moca.composition.space"] = sp
     dm = types.ModuleType("smol.cofe.space.domain")
     dm.get_species = lambda s: s
@@ -140,6 +144,20 @@ class TableFlipRng(ScriptedRng):
         return _Sw()
 
 
+class _SiteSpace(dict):
+    """species -> concentration in site-space order, with the one pymatgen-flavoured method MCBias.__init__ calls"""
+
+    def as_dict(self):
+        return {"composition": dict(self)}
+
+
+BIAS_CASES = {
+    "fugacity": ("fugacity-bias", dict(fugacity_fractions=[{"Li+": 0.5, "Mn3+": 0.25, "Ti4+": 0.25},
+                                                           {"O2-": 0.75, "F-": 0.25}])),
+    "charge": ("square-charge-bias", dict(penalty=0.3)),
+    "hyperplane": ("square-hyperplane-bias", dict(hyperplane_normals=[[1, 3, 4, -2, -1], [1, 1, 1, 0, 0]],
+                                                  hyperplane_intercepts=[0, 8], penalty=0.2)),
+}
 TF_TABLE = [[-1, 1, 0, 2, -2], [0, -1, 1, 1, -1]]     # SURVEY 8(d) config 5: charge-neutral, site-conserving flips
 
 
@@ -212,6 +230,7 @@ def record(kernel, rngs, occ, nsteps, snap_every):
     acc = np.zeros(nsteps, dtype=bool)
     prop = np.full((nsteps, 4, 2), -1, dtype=np.int64)
     dh = np.zeros(nsteps)
+    db = np.zeros(nsteps)
     snaps = []
     kernel.set_aux_state(occ)
     for t in range(nsteps):
@@ -224,8 +243,11 @@ def record(kernel, rngs, occ, nsteps, snap_every):
         trace = kernel.single_step(occ)
         acc[t] = bool(trace.accepted)
         dh[t] = float(trace.delta_trace.enthalpy)
+        if kernel.bias is not None:
+            db[t] = float(trace.delta_trace.bias)
         if (t + 1) % snap_every == 0:
             snaps.append(occ.copy())
+    record.last_dbias = db
     return acc, prop, dh, np.array(snaps)
 
 
@@ -264,6 +286,22 @@ def main():
         key = f"met_rs2of_tableflip_w{w}"
         out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps})
         out[key + "_meta"] = np.array([seed, 4000.0, 0.2])
+    # biased Metropolis flips (kernel/bias.py) on the 5-species cell: the bias term of the exponent (metropolis.py:43-44)
+    for tag, (bname, bkw) in BIAS_CASES.items():
+        for w in range(len(occ0)):
+            seed = 900 + w
+            ens = factory()
+            for sl in ens.sublattices:               # the reference's biases read Sublattice.site_space
+                sl.site_space = _SiteSpace({spc: 1.0 / len(sl.species) for spc in sl.species})
+            k = Metropolis(ens, "flip", 4000.0, seed=seed, bias_type=bname, bias_kwargs=dict(bkw))
+            assert type(k.bias).__name__.lower() == bname.replace("-", "")
+            rngs = ScriptedRng(O, seed, w)
+            k._rng = rngs
+            k.mcusher._rng = rngs
+            acc, prop, dh, snaps = record(k, rngs, occ0[w], 300, 25)
+            key = f"met_rs2of_flip+{tag}_w{w}"
+            out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps,
+                        key + "_dbias": record.last_dbias.copy(), key + "_meta": np.array([seed, 4000.0])})
     # Wang-Landau (flip) on the binary FCC cell
     factory, occ0 = mods["fcc3"]
     ens = factory()
