@@ -144,6 +144,42 @@ class TableFlipRng(ScriptedRng):
         return _Sw()
 
 
+class PickRng:
+    """generator of a Composite / MultiStep usher itself: its one draw per step, rng.choice(seq, p=p), is random word 4"""
+
+    def __init__(self, parent):
+        self.parent = parent
+
+    def choice(self, a, p=None):
+        O = self.parent.O
+        u = O.u01(self.parent.rnd.word(4))
+        cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+        cdf[-1] = 1.0
+        return a[int(np.searchsorted(cdf, u, side="right"))]
+
+
+class ChainRng:
+    """generator of MultiStep's inner usher: proposal j of a step (each starts with the sublattice draw) reads the
+    words of Philox block 2 + j"""
+
+    def __init__(self, parent):
+        self.parent, self.step_seen, self.j, self.plain = parent, None, -1, 0
+
+    def choice(self, a, p=None):
+        par, O = self.parent, self.parent.O
+        if self.step_seen is not par.rnd:                    # first draw of a new step
+            self.step_seen, self.j = par.rnd, -1
+        if p is not None:
+            self.j += 1
+            self.plain = 0
+            u = O.u01(par.rnd.word(8 + 4 * self.j))
+            cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+            cdf[-1] = 1.0
+            return a[int(np.searchsorted(cdf, u, side="right"))] if len(a) > 1 else a[0]
+        self.plain += 1
+        return a[O.mulhi32(par.rnd.word(8 + 4 * self.j + self.plain), len(a))]
+
+
 class _SiteSpace(dict):
     """species -> concentration in site-space order, with the one pymatgen-flavoured method MCBias.__init__ calls"""
 
@@ -158,6 +194,7 @@ BIAS_CASES = {
     "hyperplane": ("square-hyperplane-bias", dict(hyperplane_normals=[[1, 3, 4, -2, -1], [1, 1, 1, 0, 0]],
                                                   hyperplane_intercepts=[0, 8], penalty=0.2)),
 }
+USHER_CASES = ("composite", "multistep-flip", "multistep-swap")
 TF_TABLE = [[-1, 1, 0, 2, -2], [0, -1, 1, 1, -1]]     # charge-neutral, site-conserving flips
 
 
@@ -302,6 +339,34 @@ def main():
             key = f"met_rs2of_flip+{tag}_w{w}"
             out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps,
                         key + "_dbias": record.last_dbias.copy(), key + "_meta": np.array([seed, 4000.0])})
+    # Composite (Flip with its own sublattice probabilities + Swap on the cation sublattice, weights 2:1) and MultiStep
+    # (chains of Flip / Swap proposals) ushers, mcusher.py:203-394
+    mcu = importlib.import_module("smol.moca.kernel.mcusher")
+    for tag in USHER_CASES:
+        for w in range(len(occ0)):
+            seed = 1300 + w
+            ens = factory()
+            subl = ens.sublattices
+            rngs = ScriptedRng(O, seed, w)
+            if tag == "composite":
+                subs = [mcu.Flip(subl, sublattice_probabilities=[0.7, 0.3]), mcu.Swap([subl[0]])]
+                k = Metropolis(ens, "composite", 4000.0, seed=seed, mcushers=subs, mcusher_weights=[2, 1])
+                for u in subs:
+                    u._rng = rngs
+            else:
+                inner = (mcu.Flip if tag == "multistep-flip" else mcu.Swap)(subl)
+                # (uniform length probabilities: passing step_probabilities to the reference raises AttributeError,
+                #  mcusher.py:247 sets `step_p`, :274 reads `_step_p`)
+                lens = [1, 2, 3] if tag == "multistep-flip" else [1, 2]
+                k = Metropolis(ens, "multi-step", 4000.0, seed=seed, mcusher=inner, step_lengths=lens)
+                inner._rng = ChainRng(rngs)
+            assert type(k.mcusher).__name__ == ("Composite" if tag == "composite" else "MultiStep")
+            k._rng = rngs
+            k.mcusher._rng = PickRng(rngs)
+            acc, prop, dh, snaps = record(k, rngs, occ0[w], 300, 25)
+            key = f"met_rs2of_{tag}_w{w}"
+            out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps,
+                        key + "_meta": np.array([seed, 4000.0])})
     # Wang-Landau (flip) on the binary FCC cell
     factory, occ0 = mods["fcc3"]
     ens = factory()
