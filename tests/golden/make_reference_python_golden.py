@@ -387,6 +387,35 @@ def main():
                     key + "_occurrences": np.array(k._occurrences), key + "_mean_features": np.array(k._mean_features),
                     key + "_mod_factor": np.array([k._m])})
         out[key + "_meta"] = np.array([seed, lo, hi, bin_size, 0.3, 40])
+    # Wang-Landau with canonical swaps, update_period 2 (entropy / histogram every second valid step, running mean
+    # of the features instead of sums) and a modification factor divided by 3
+    for w in range(len(occ0)):
+        ens = factory()
+        seed = 600 + w
+        k = WangLandau(ens, "swap", lo, hi, bin_size, flatness=0.25, check_period=30, update_period=2, mod_factor=0.5,
+                       mod_update=3.0, seed=seed)
+        rngs = ScriptedRng(O, seed, w)
+        k._rng = rngs
+        k.mcusher._rng = rngs
+        acc, prop, dh, snaps = record(k, rngs, occ0[w], 600, 50)
+        key = f"wl2_fcc3_swap_w{w}"
+        out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps,
+                    key + "_entropy": np.array(k._entropy), key + "_histogram": np.array(k._histogram),
+                    key + "_occurrences": np.array(k._occurrences), key + "_mean_features": np.array(k._mean_features),
+                    key + "_mod_factor": np.array([k._m])})
+        out[key + "_meta"] = np.array([seed, lo, hi, bin_size, 0.25, 30])
+    # UniformlyRandom kernel (kernel/random.py): every proposal with log_priori >= 0 is accepted
+    UniformlyRandom = importlib.import_module("smol.moca.kernel.random").UniformlyRandom
+    for w in range(len(occ0)):
+        seed = 650 + w
+        k = UniformlyRandom(factory(), "swap", seed=seed)
+        rngs = ScriptedRng(O, seed, w)
+        k._rng = rngs
+        k.mcusher._rng = rngs
+        acc, prop, dh, snaps = record(k, rngs, occ0[w], 100, 25)
+        key = f"uni_fcc3_swap_w{w}"
+        out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps,
+                    key + "_meta": np.array([seed, 0.0])})
     # MulticellMetropolis over three shapes of the 8-site FCC cell (uniform kernel probabilities: passing
     # kernel_probabilities to the reference raises AttributeError, base.py:505 sets `kernel_p`, :543 reads `_kernel_p`)
     MulticellMetropolis = importlib.import_module("smol.moca.kernel.metropolis").MulticellMetropolis
