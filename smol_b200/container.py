@@ -99,8 +99,9 @@ class SampleContainer:
 
     @staticmethod
     def _flatten(values):
+        """container.py:514-519: samples x walkers merged AND size-one axes squeezed (flat enthalpies are 1-D)."""
         s = values.shape
-        return values.reshape((s[0] * s[1], *s[2:]))
+        return np.squeeze(values.reshape((s[0] * s[1], *s[2:])))
 
     # ---- accessors (container.py:131-381) ---------------------------------------------------
     def get_trace_value(self, name, discard=0, thin_by=1, flat=True):
@@ -141,15 +142,17 @@ class SampleContainer:
 
     def get_energies(self, discard=0, thin_by=1, flat=True):
         """container.py:208-229: the enthalpies when there are no extra terms, else features[:n_energy] . coefs;
-        shape ``[..., 1]`` like the enthalpy trace."""
+        shape ``[S, W, 1]`` like the enthalpy trace (flattened and squeezed when ``flat``)."""
         n = self._ensemble.num_energy_coefs
         if len(self.natural_parameters) == n:
             return self.get_enthalpies(discard, thin_by, flat)
-        feats = self.get_feature_vectors(discard, thin_by, flat)
-        return np.tensordot(feats[..., :n], self.natural_parameters[:n], axes=([-1], [0]))[..., None]
+        feats = self.get_feature_vectors(discard, thin_by, flat=False)
+        energies = np.tensordot(feats[..., :n], self.natural_parameters[:n], axes=([-1], [0]))[..., None]
+        return self._flatten(energies) if flat else energies
 
     def get_temperatures(self, discard=0, thin_by=1):
-        return self.get_trace_value("temperature", discard, thin_by, flat=False)[:, 0]
+        """container.py:231-233 (always flat)."""
+        return self.get_trace_value("temperature", discard, thin_by)
 
     def mean_enthalpy(self, discard=0, thin_by=1, flat=True):
         return self.get_enthalpies(discard, thin_by, flat).mean(axis=0)
@@ -175,7 +178,7 @@ class SampleContainer:
     def get_minimum_enthalpy_occupancy(self, discard=0, thin_by=1, flat=True):
         inds = self.get_enthalpies(discard, thin_by, flat).argmin(axis=0)
         occus = self.get_occupancies(discard, thin_by, flat)
-        return occus[inds[0]] if flat else occus[inds, np.arange(self._nwalkers)][0]
+        return occus[inds] if flat else occus[inds, np.arange(self._nwalkers)][0]
 
     def get_minimum_energy(self, discard=0, thin_by=1, flat=True):
         """container.py:321-323."""
@@ -185,7 +188,7 @@ class SampleContainer:
         """container.py:325-334."""
         inds = self.get_energies(discard, thin_by, flat).argmin(axis=0)
         occus = self.get_occupancies(discard, thin_by, flat)
-        return occus[inds[0]] if flat else occus[inds, np.arange(self._nwalkers)][0]
+        return occus[inds] if flat else occus[inds, np.arange(self._nwalkers)][0]
 
     def get_sublattice_species_counts(self, sublattice, discard=0, thin_by=1, flat=True):
         """container.py:349-382: counts of each species of a sublattice, last axis in the order of its site space
@@ -199,11 +202,12 @@ class SampleContainer:
         return self._flatten(counts) if flat else counts
 
     def get_species_counts(self, discard=0, thin_by=1, flat=True):
-        """container.py:336-347: counts per species summed over the sublattices, keyed by species."""
+        """container.py:336-347: counts per species summed over the sublattices, keyed by species.  Like the
+        reference (``subcounts.T``) the chain form is ``[walkers, samples]``, transposed w.r.t. the traces."""
         counts = {}
         for s in self.sublattices:
             sub = self.get_sublattice_species_counts(s, discard, thin_by, flat)
-            for sp, c in zip(s.species, np.moveaxis(sub, -1, 0)):
+            for sp, c in zip(s.species, sub.T):
                 counts[sp] = counts[sp] + c if sp in counts else c.copy()
         return counts
 

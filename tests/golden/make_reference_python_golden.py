@@ -23,6 +23,7 @@ snapshots, final Wang-Landau arrays).  ``tests/test_oracle_golden.py`` replays t
     python tests/golden/make_reference_python_golden.py
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -142,6 +143,66 @@ class TableFlipRng(ScriptedRng):
                 parent.plain += 1
                 return a[parent.O.mulhi32(parent.rnd.word(4 + parent.plain), len(a))]
         return _Sw()
+
+
+class AutoRng(ScriptedRng):
+    """for runs driven by the reference's own Sampler loop (no hook between steps): a step of a Flip / Swap usher
+    always begins with the sublattice draw, which advances the step counter here"""
+
+    def __init__(self, O, seed, walker):
+        super().__init__(O, seed, walker)
+        self.t = -1
+
+    def choice(self, a, p=None):
+        if p is not None:
+            self.t += 1
+            self.begin_step(self.t)
+        return super().choice(a, p)
+
+
+def import_reference_sampler():
+    """smol/moca/sampler/{sampler,container}.py unmodified (after import_reference_kernels): h5py, the MSON encoder,
+    smol.moca.Ensemble / Sublattice are only named at import time"""
+    from oracle import lmc_oracle as O
+    sys.modules["h5py"] = types.ModuleType("h5py")
+    sys.modules["monty.json"].MontyEncoder = object
+    sl = types.ModuleType("smol.moca.sublattice")
+    sl.Sublattice = O.Sublattice
+    sys.modules["smol.moca.sublattice"] = sl
+    sys.modules["smol.moca"].Ensemble = O.Ensemble
+    m = types.ModuleType("smol.moca.sampler")
+    m.__path__ = [REF + "/moca/sampler"]
+    sys.modules["smol.moca.sampler"] = m
+    spec = importlib.util.spec_from_file_location("smol.moca.kernel._init", REF + "/moca/kernel/__init__.py")
+    ki = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ki)
+    sys.modules["smol.moca.kernel"].mckernel_factory = ki.mckernel_factory
+    return importlib.import_module("smol.moca.sampler.sampler").Sampler
+
+
+CONTAINER_QUERIES = [dict(discard=0, thin_by=1), dict(discard=7, thin_by=3)]
+
+
+def container_answers(c, sublattices, flat):
+    """every accessor of the reference's SampleContainer that this build mirrors, as a flat name -> array dict"""
+    out = {}
+    for qi, q in enumerate(CONTAINER_QUERIES):
+        tag = f"q{qi}_{'flat' if flat else 'chain'}_"
+        kw = dict(q, flat=flat)
+        for name in ("get_energies", "get_enthalpies", "get_feature_vectors", "mean_energy", "energy_variance",
+                     "mean_enthalpy", "enthalpy_variance", "mean_feature_vector", "feature_vector_variance",
+                     "get_minimum_energy", "get_minimum_enthalpy", "get_minimum_energy_occupancy",
+                     "get_minimum_enthalpy_occupancy"):
+            out[tag + name] = np.asarray(getattr(c, name)(**kw))
+        out[tag + "sampling_efficiency"] = np.asarray(c.sampling_efficiency(discard=q["discard"], flat=flat))
+        for name in ("get_compositions", "mean_composition", "composition_variance"):
+            for sp, v in getattr(c, name)(**kw).items():
+                out[tag + name + ":" + str(sp)] = np.asarray(v)
+        for i, sl in enumerate(sublattices):
+            for name in ("get_sublattice_species_counts", "get_sublattice_compositions",
+                         "mean_sublattice_composition", "sublattice_composition_variance"):
+                out[tag + name + f":{i}"] = np.asarray(getattr(c, name)(sl, **kw))
+    return out
 
 
 class PickRng:
@@ -460,6 +521,33 @@ def main():
         key = f"mc_fcc8_swap_w{w}"
         out.update({key + "_idx": idx, key + "_acc": acc, key + "_occ": occs,
                     key + "_meta": np.array([seed, T, *kseeds])})
+    # the reference's Sampler.run loop and SampleContainer accessors (sampler.py:164-297, container.py:131-382):
+    # semigrand flips on the 5-species cell, two walkers, 360 steps thinned by 6
+    Sampler = import_reference_sampler()
+    factory, occ0 = table_flip_model()
+    ens = factory()
+    ens.thermo_boundaries = {}
+    ens.num_energy_coefs = len(ens.natural_parameters) - 1          # the last natural parameter is the chemical work
+    for sl in ens.sublattices:
+        sl.site_space = _SiteSpace({spc: 1.0 / len(sl.species) for spc in sl.species})
+    seeds = [41, 42]
+    smp = Sampler.from_ensemble(ens, temperature=4000.0, step_type="flip", kernel_type="Metropolis", seeds=seeds,
+                                nwalkers=2)
+    for i, k in enumerate(smp.mckernels):
+        r = AutoRng(O, seeds[i], i)
+        k._rng = r
+        k.mcusher._rng = r
+    smp.run(360, occ0, thin_by=6, progress=False)
+    c = smp.samples
+    out["smp_occupancy"] = c.get_occupancies(flat=False)
+    out["smp_features"] = c.get_feature_vectors(flat=False)
+    out["smp_enthalpy"] = c.get_enthalpies(flat=False)
+    out["smp_accepted"] = c.get_trace_value("accepted", flat=False)
+    out["smp_temperature"] = c.get_trace_value("temperature", flat=False)
+    out["smp_meta"] = np.array([*seeds, 4000.0, c.num_samples, c.total_mc_steps])
+    for flat in (True, False):
+        for name, v in container_answers(c, ens.sublattices, flat).items():
+            out["smpq_" + name] = v
     path = os.path.join(HERE, "ref_python_steps.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in list(out.items())[:6]})

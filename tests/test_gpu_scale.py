@@ -230,8 +230,8 @@ def test_edge_cases(cuda_device):
     ens.reset_restricted_sites()
     smp = S.Sampler.from_ensemble(ens, 2000.0, step_type="swap", nwalkers=2, seeds=[5, 6])
     smp.anneal([2000.0, 1000.0, 500.0], 100, occ0[:2], thin_by=50)
-    t = smp.samples.get_temperatures()
-    assert t.shape[0] == 6 and list(t[:, 0]) == [2000.0, 2000.0, 1000.0, 1000.0, 500.0, 500.0]
+    t = smp.samples.get_temperatures()           # flat like the reference's (container.py:231-233): [samples x walkers]
+    assert t.shape == (12,) and list(t.reshape(6, 2)[:, 0]) == [2000.0, 2000.0, 1000.0, 1000.0, 500.0, 500.0]
     with pytest.raises(ValueError):
         smp.anneal([500.0, 1000.0], 10)
     with warnings.catch_warnings():

@@ -130,8 +130,10 @@ def test_sample_container_accessors():
     assert c.get_enthalpies(flat=False).shape == (5, 3, 1)
     assert c.sampling_efficiency() == 1.0 and c.step_efficiency() == 0.5
     # no extra terms: the energies ARE the enthalpies (container.py:210-211)
-    assert np.array_equal(c.get_energies(), c.get_enthalpies()) and c.get_minimum_enthalpy()[0] == 0.0
-    assert c.get_minimum_energy()[0] == 0.0 and c.get_minimum_energy_occupancy().shape == (4,)
+    # (flat values are squeezed like the reference's, container.py:514-519)
+    assert c.get_enthalpies().shape == (15,) and c.get_enthalpies(flat=False).shape == (5, 3, 1)
+    assert np.array_equal(c.get_energies(), c.get_enthalpies()) and c.get_minimum_enthalpy() == 0.0
+    assert c.get_minimum_energy() == 0.0 and c.get_minimum_energy_occupancy().shape == (4,)
     c.clear()
     assert c.num_samples == 0
 
@@ -156,14 +158,15 @@ def test_sample_container_compositions_and_energies():
     # energies drop the chemical-work term and keep the trailing axis of the enthalpy trace
     e = c.get_energies(flat=False)
     assert e.shape == (2, 2, 1) and np.allclose(e[..., 0], feats[..., 0] + 2 * feats[..., 1])
-    assert c.get_energies().shape == (4, 1) and np.isclose(c.get_minimum_energy()[0], 2.0)
+    assert c.get_energies().shape == (4,) and np.isclose(c.get_minimum_energy(), 2.0)
     assert c.get_minimum_energy_occupancy().tolist() == occ[0, 0].tolist()
     sub = c.get_sublattice_species_counts(sl_a, flat=False)
     assert sub.shape == (2, 2, 2) and sub[0, 0].tolist() == [2, 2] and sub[1, 1].tolist() == [4, 0]
     assert c.get_sublattice_species_counts(sl_b).tolist() == [[1, 1], [2, 0], [0, 2], [1, 1]]
     counts = c.get_species_counts(flat=False)
     assert set(counts) == {"A", "B", "C"}                      # species A lives on both sublattices
-    assert counts["A"].tolist() == [[3, 0], [3, 5]] and counts["B"].tolist() == [[2, 4], [3, 0]]
+    # (chain form [walkers, samples], as the reference's subcounts.T gives it)
+    assert counts["A"].tolist() == [[3, 3], [0, 5]] and counts["B"].tolist() == [[2, 3], [4, 0]]
     comps = c.get_compositions()
     assert np.allclose(sum(comps.values()), 1.0) and np.allclose(comps["C"], np.array([1, 2, 0, 1]) / 6)
     assert np.allclose(c.mean_composition()["A"], np.mean([3, 0, 3, 5]) / 6)
