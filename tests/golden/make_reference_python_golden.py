@@ -180,6 +180,105 @@ def import_reference_sampler():
     return importlib.import_module("smol.moca.sampler.sampler").Sampler
 
 
+def import_reference_processors():
+    """smol/moca/processor/{base,expansion}.py unmodified, on top of the reference's COMPILED evaluators in
+    oracle/_ref (after import_reference_kernels / import_reference_sampler).  pymatgen's Structure is only copied,
+    enlarged and measured by the constructors, so a four-method stand-in is enough; the cluster subspace is this
+    build's geometry-made one behind an adapter exposing the attribute names the reference reads."""
+    cref = os.path.join(ROOT, "oracle", "_ref", "smol")
+    assert os.path.isdir(cref + "/utils/cluster"), "build oracle/_ref first (python oracle/build_ref.py)"
+    sys.modules["smol.utils"].__path__ = [REF + "/utils", cref + "/utils"]
+    spec = importlib.util.spec_from_file_location(
+        "smol.utils.cluster", REF + "/utils/cluster/__init__.py",
+        submodule_search_locations=[cref + "/utils/cluster", REF + "/utils/cluster"])
+    uc = importlib.util.module_from_spec(spec)
+    sys.modules["smol.utils.cluster"] = uc
+    spec.loader.exec_module(uc)
+    container = importlib.import_module("smol.utils.cluster.container")
+    pm = types.ModuleType("pymatgen.core")
+    pm.PeriodicSite = pm.Structure = object
+    sys.modules.update({"pymatgen": types.ModuleType("pymatgen"), "pymatgen.core": pm})
+    space = sys.modules["smol.cofe.space"]
+    space.Vacancy = sys.modules["smol.cofe.space.domain"].Vacancy
+    space.get_allowed_species = lambda structure: structure.allowed
+    space.get_site_spaces = lambda structure, include_measure=False: list(structure.allowed)
+    cs = types.ModuleType("smol.cofe.space.clusterspace")
+
+    class OrbitIndices:
+        def __init__(self, arrays, container):
+            self.arrays, self.container = arrays, container
+    cs.OrbitIndices = OrbitIndices
+
+    class FakeStructure:
+        def __init__(self, prim_spaces, size=1):
+            self.prim_spaces, self.size = prim_spaces, size
+            self.allowed = [sp for sp in prim_spaces for _ in range(size)]      # basis major, like the tables
+
+        def copy(self):
+            return FakeStructure(self.prim_spaces, self.size)
+
+        def make_supercell(self, scm):
+            self.__init__(self.prim_spaces, int(round(abs(np.linalg.det(np.asarray(scm, dtype=float))))))
+
+        def __len__(self):
+            return len(self.allowed)
+
+    class RefSubspace:
+        """adapter: attribute names of smol.cofe.ClusterSubspace over this build's lattice.ClusterSubspace"""
+        def __init__(self, sub):
+            self._sub = sub
+            self.structure = FakeStructure([tuple(s) for s in sub.prim.site_spaces])
+            self.orbits, self.num_threads = sub.orbits, 1
+            self.num_orbits, self.num_corr_functions = sub.num_orbits, sub.num_corr_functions
+            self.orbit_multiplicities = sub.orbit_multiplicities
+
+        def num_prims_from_matrix(self, scm):
+            return self._sub.supercell_size(scm)
+
+        def get_orbit_indices(self, scm):
+            arrays = self._sub.get_orbit_indices(scm).arrays
+            return OrbitIndices(arrays, container.IntArray2DContainer(arrays))
+    cs.ClusterSubspace = RefSubspace
+    sys.modules["smol.cofe.space.clusterspace"] = cs
+    pkg = types.ModuleType("smol.moca.processor")
+    pkg.__path__ = [REF + "/moca/processor"]
+    sys.modules["smol.moca.processor"] = pkg
+    ex = importlib.import_module("smol.moca.processor.expansion")
+    assert ex.__file__.startswith(REF)
+    return ex.ClusterExpansionProcessor, ex.ClusterDecompositionProcessor, RefSubspace
+
+
+def processor_cases():
+    """name -> (subspace, supercell matrix, correlation coefficients); flips are drawn in processor_flips"""
+    from tests import models as M
+    out = {}
+    for name, sub, scm, seed in [("fcc3", M.fcc_subspace(), np.eye(3, dtype=int) * 3, 5),
+                                 ("fcc421", M.fcc_subspace(), np.diag([4, 2, 1]), 6),
+                                 ("rs2of", M.rocksalt_subspace(anions=("O2-", "F-")), np.eye(3, dtype=int) * 2, 7)]:
+        out[name] = (sub, scm, np.random.default_rng(seed).normal(0, 0.05, sub.num_corr_functions))
+    return out
+
+
+def processor_flips(sub, scm, seed, n=12):
+    """seeded occupancies and 1..3-site flip lists (sequential, a site may repeat)"""
+    from tests import models as M
+    rng = np.random.default_rng(seed)
+    spaces = sub.allowed_species(scm)
+    active = [i for i, s in enumerate(spaces) if len(s) > 1]
+    occs = M.random_occupancies(sub, scm, n, seed=seed)
+    flips = []
+    for w in range(n):
+        cur = occs[w].copy()
+        fl = []
+        for _ in range(1 + w % 3):
+            site = int(rng.choice(active))
+            code = int(rng.choice([c for c in range(len(spaces[site])) if c != cur[site]]))
+            fl.append((site, code))
+            cur[site] = code
+        flips.append(fl)
+    return occs, flips
+
+
 CONTAINER_QUERIES = [dict(discard=0, thin_by=1), dict(discard=7, thin_by=3)]
 
 
@@ -548,6 +647,21 @@ def main():
     for flat in (True, False):
         for name, v in container_answers(c, ens.sublattices, flat).items():
             out["smpq_" + name] = v
+    # the reference's processors: ClusterExpansionProcessor / ClusterDecompositionProcessor (expansion.py, unmodified
+    # Python on the compiled evaluators): full vectors, flip changes (1..3 sequential flips), properties
+    from smol_b200 import lattice as L
+    CE, CD, RefSubspace = import_reference_processors()
+    for name, (sub, scm, coefs) in processor_cases().items():
+        occs, flips = processor_flips(sub, scm, seed=3)
+        rsub = RefSubspace(sub)
+        it = L.cluster_interaction_tensors(sub, coefs)
+        for tag, proc in (("ce", CE(rsub, scm, coefs)), ("cd", CD(rsub, scm, it))):
+            key = f"proc_{name}_{tag}"
+            out[key + "_full"] = np.array([proc.compute_feature_vector(o) for o in occs])
+            out[key + "_delta"] = np.array([proc.compute_feature_vector_change(o, f) for o, f in zip(occs, flips)])
+            out[key + "_prop"] = np.array([proc.compute_property(o) for o in occs])
+            out[key + "_dprop"] = np.array([proc.compute_property_change(o, f) for o, f in zip(occs, flips)])
+            out[key + "_meta"] = np.array([proc.size, proc.num_sites])
     path = os.path.join(HERE, "ref_python_steps.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in list(out.items())[:6]})
