@@ -232,6 +232,18 @@ def import_reference_processors():
             self.num_orbits, self.num_corr_functions = sub.num_orbits, sub.num_corr_functions
             self.orbit_multiplicities = sub.orbit_multiplicities
 
+        external_terms = ()
+
+        def __len__(self):                       # clusterspace.py: number of correlation functions (+ external terms)
+            return self.num_corr_functions
+
+        @property
+        def orbits_by_diameter(self):
+            """clusterspace.py:367-381: {diameter rounded to 6 decimals: orbits}, ascending"""
+            from itertools import groupby
+            key = lambda orb: float(np.round(orb.diameter, 6))                      # noqa: E731
+            return {d: tuple(orbs) for d, orbs in groupby(sorted(self.orbits, key=key), key=key)}
+
         def num_prims_from_matrix(self, scm):
             return self._sub.supercell_size(scm)
 
@@ -245,6 +257,8 @@ def import_reference_processors():
     sys.modules["smol.moca.processor"] = pkg
     ex = importlib.import_module("smol.moca.processor.expansion")
     assert ex.__file__.startswith(REF)
+    pkg.ClusterExpansionProcessor, pkg.ClusterDecompositionProcessor = (ex.ClusterExpansionProcessor,
+                                                                        ex.ClusterDecompositionProcessor)
     return ex.ClusterExpansionProcessor, ex.ClusterDecompositionProcessor, RefSubspace
 
 
@@ -279,6 +293,8 @@ def processor_flips(sub, scm, seed, n=12):
     return occs, flips
 
 
+DIST_TOL = 0.12      # loose on purpose: the largest exactly-matched diameter L takes intermediate values
+DIST_TOL_INT = 0.004  # (cluster interactions are ~coefficient sized)
 CONTAINER_QUERIES = [dict(discard=0, thin_by=1), dict(discard=7, thin_by=3)]
 
 
@@ -662,6 +678,27 @@ def main():
             out[key + "_prop"] = np.array([proc.compute_property(o) for o in occs])
             out[key + "_dprop"] = np.array([proc.compute_property_change(o, f) for o, f in zip(occs, flips)])
             out[key + "_meta"] = np.array([proc.size, proc.num_sites])
+    # the distance processors behind smol's SQS generation (processor/distance.py, unmodified): features
+    # [L, |f_i - target_i| ...]; the target is the vector of the first occupancy, so part of the features match exactly
+    dist = importlib.import_module("smol.moca.processor.distance")
+    for name in ("fcc3", "rs2of"):
+        sub, scm, coefs = processor_cases()[name]
+        occs, flips = processor_flips(sub, scm, seed=3)
+        rsub = RefSubspace(sub)
+        it = L.cluster_interaction_tensors(sub, coefs)
+        size = sub.supercell_size(scm)
+        targets = {"corr": out[f"proc_{name}_ce_full"][0] / size, "int": out[f"proc_{name}_cd_full"][0] / size}
+        procs = {"corr": dist.CorrelationDistanceProcessor(rsub, scm, target_vector=targets["corr"], match_weight=0.7,
+                                                          match_tol=DIST_TOL),
+                 "int": dist.ClusterInteractionDistanceProcessor(rsub, scm, interaction_tensors=it,
+                                                                 target_vector=targets["int"], match_weight=0.7,
+                                                                 match_tol=DIST_TOL_INT)}
+        for tag, proc in procs.items():
+            key = f"dist_{name}_{tag}"
+            out[key + "_target"] = targets[tag]
+            out[key + "_full"] = np.array([proc.compute_feature_vector(o) for o in occs])
+            out[key + "_delta"] = np.array([proc.compute_feature_vector_change(o, f) for o, f in zip(occs, flips)])
+            out[key + "_coefs"] = np.array(proc.coefs)
     path = os.path.join(HERE, "ref_python_steps.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in list(out.items())[:6]})
