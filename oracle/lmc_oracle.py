@@ -16,7 +16,13 @@ Parity pinning (see tests/test_oracle_*.py):
     /root/reference by oracle/build_ref.py) on seeded random inputs, and the
     golden vectors generated from them in tests/golden/ (script committed);
   * against the reference's known-answer table-flip a-priori factors
-    (tests/test_moca/test_mcushers.py:199-234).
+    (tests/test_moca/test_mcushers.py:199-234) and the correlation vectors stored in its tests
+    (LiCaBr and the CASM-generated ones, tests/test_cofe/test_clusterspace.py:627-725, 881-996);
+  * against the reference's OWN Python classes, imported unmodified from /root/reference behind package shells
+    (tests/golden/make_reference_python_golden.py -> tests/golden/ref_python_steps.npz): Metropolis /
+    UniformlyRandom / WangLandau / MulticellMetropolis kernels, Flip / Swap / TableFlip / Composite / MultiStep
+    ushers, the three bias terms, the Sampler loop and SampleContainer, the expansion / decomposition / distance
+    processors -- step by step with the kernels' generator scripted to the Philox word positions below.
 
 RNG: the reference uses numpy PCG64 with a data-dependent number of draws per step
 (``kernel/mcusher.py:146-200``), which cannot be reproduced lane-wise on a GPU.  The
