@@ -374,6 +374,17 @@ USHER_CASES = ("composite", "multistep-flip", "multistep-swap")
 TF_TABLE = [[-1, 1, 0, 2, -2], [0, -1, 1, 1, -1]]     # charge-neutral, site-conserving flips
 
 
+TF_MUS = {"Li+": 0.0, "Mn3+": 0.4, "Ti4+": -0.3, "O2-": 0.1, "F-": 0.0}
+
+
+def TF_INTERACTIONS():
+    """interaction tensors of table_flip_model()"""
+    from smol_b200 import lattice as L
+    from tests import models as M
+    rs = M.rocksalt_subspace(anions=("O2-", "F-"))
+    return L.cluster_interaction_tensors(rs, np.random.default_rng(21).normal(0, 0.03, rs.num_corr_functions))
+
+
 def table_flip_model():
     """5-species rocksalt 2x2x2 (8 cation + 8 anion sites), charge-neutral starts: (ensemble factory, occupancies)"""
     from oracle import lmc_oracle as O
@@ -678,6 +689,36 @@ def main():
             out[key + "_prop"] = np.array([proc.compute_property(o) for o in occs])
             out[key + "_dprop"] = np.array([proc.compute_property_change(o, f) for o, f in zip(occs, flips)])
             out[key + "_meta"] = np.array([proc.size, proc.num_sites])
+    # the reference's Ensemble (ensemble.py, unmodified: chemical-potential table, chemical work, natural parameters)
+    # over its ClusterDecompositionProcessor inside its Metropolis kernel: semigrand flips on the 5-species cell -- every
+    # layer between the lattice tables and the random words is the reference's code
+    cm = types.ModuleType("pymatgen.core.composition")
+    cm.ChemicalPotential = dict
+    sys.modules["pymatgen.core.composition"] = cm
+    pp = sys.modules["smol.moca.processor"]
+    pp.CompositeProcessor = importlib.import_module("smol.moca.processor.composite").CompositeProcessor
+    pp.EwaldProcessor = type("EwaldProcessor", (), {})
+    RefEnsemble = importlib.import_module("smol.moca.ensemble").Ensemble
+    factory, occ0 = table_flip_model()
+    sub, scm, _ = processor_cases()["rs2of"]
+    for w in range(len(occ0)):
+        o_ens = factory()
+        for sl in o_ens.sublattices:
+            sl.site_space = _SiteSpace({spc: 1.0 / len(sl.species) for spc in sl.species})
+        proc = CD(RefSubspace(sub), scm, TF_INTERACTIONS())
+        ens = RefEnsemble(proc, sublattices=o_ens.sublattices, chemical_potentials=dict(TF_MUS))
+        assert len(ens.natural_parameters) == len(o_ens.natural_parameters)
+        seed = 1500 + w
+        k = Metropolis(ens, "flip", 4000.0, seed=seed)
+        rngs = ScriptedRng(O, seed, w)
+        k._rng = rngs
+        k.mcusher._rng = rngs
+        acc, prop, dh, snaps = record(k, rngs, occ0[w], 300, 25)
+        key = f"fullref_rs2of_flip_w{w}"
+        out.update({key + "_acc": acc, key + "_prop": prop, key + "_dh": dh, key + "_snaps": snaps,
+                    key + "_meta": np.array([seed, 4000.0]),
+                    key + "_feat0": np.array(ens.compute_feature_vector(occ0[w])),
+                    key + "_natural": np.array(ens.natural_parameters)})
     # the distance processors behind smol's SQS generation (processor/distance.py, unmodified): features
     # [L, |f_i - target_i| ...]; the target is the vector of the first occupancy, so part of the features match exactly
     dist = importlib.import_module("smol.moca.processor.distance")
