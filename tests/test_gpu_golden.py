@@ -73,3 +73,41 @@ def test_cuda_matches_reference_known_answer_licabr(cuda_device):
     proc = S.ClusterExpansionProcessor(sub, scm, np.ones(sub.num_corr_functions))
     corr = proc.compute_feature_vector(occ) / sub.supercell_size(scm)
     np.testing.assert_allclose(corr, LICABR_EXPECTED, rtol=1e-12, atol=1e-14)
+
+
+# Written after the round's GPU budget was spent: the oracle is verified against this record on CPU
+# (tests/test_oracle_golden.py) and the CUDA path against the oracle on the B200 for the same kind of run, so this is
+# expected to pass; the NON-strict xfail only keeps an unrun test from stopping the suite (XPASS = verified).
+@pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU minutes were used)")
+def test_cuda_reproduces_trajectory_recorded_from_the_reference_python_stack(cuda_device):
+    """semigrand flips on the 5-species rocksalt cell: the CUDA sampler against the step record of the reference's OWN
+    Ensemble + ClusterDecompositionProcessor + Metropolis + Flip classes (tests/golden/ref_python_steps.npz,
+    `fullref_rs2of_flip_*`, made by tests/golden/make_reference_python_golden.py with the generator scripted to the
+    engine's Philox word positions)"""
+    import importlib.util
+    import smol_b200 as S
+    path = os.path.join(os.path.dirname(__file__), "golden", "make_reference_python_golden.py")
+    spec = importlib.util.spec_from_file_location("make_reference_python_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python_steps.npz"))
+    _, occ0 = mod.table_flip_model()
+    sub, scm, _ = mod.processor_cases()["rs2of"]
+    ens = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, mod.TF_INTERACTIONS()), chemical_potentials=dict(mod.TF_MUS))
+    W = len(occ0)
+    seeds = [int(gold[f"fullref_rs2of_flip_w{w}_meta"][0]) for w in range(W)]
+    T = float(gold["fullref_rs2of_flip_w0_meta"][1])
+    smp = S.Sampler.from_ensemble(ens, T, step_type="flip", nwalkers=W, seeds=seeds, spec_mode=1)
+    smp.run(300, occ0, thin_by=25)
+    occ = smp.samples.get_occupancies(flat=False)
+    acc = smp.samples.get_trace_value("accepted", flat=False)
+    nacc = smp.samples.get_trace_value("n_accepted", flat=False)
+    enth = smp.samples.get_enthalpies(flat=False)
+    for w in range(W):
+        key = f"fullref_rs2of_flip_w{w}"
+        np.testing.assert_array_equal(occ[:, w], gold[key + "_snaps"])                       # bit exact
+        np.testing.assert_array_equal(acc[:, w, 0], gold[key + "_acc"][24::25])
+        np.testing.assert_array_equal(nacc[:, w], gold[key + "_acc"].reshape(12, 25).sum(axis=1))
+        h0 = float(np.dot(gold[key + "_natural"], gold[key + "_feat0"]))
+        want = h0 + np.cumsum(gold[key + "_dh"] * gold[key + "_acc"])[24::25]
+        np.testing.assert_allclose(enth[:, w, 0], want, rtol=1e-10, atol=1e-10 * max(1.0, abs(h0)))
