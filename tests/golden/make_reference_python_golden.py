@@ -519,6 +519,15 @@ def main():
                 sl.site_space = _SiteSpace({spc: 1.0 / len(sl.species) for spc in sl.species})
             k = Metropolis(ens, "flip", 4000.0, seed=seed, bias_type=bname, bias_kwargs=dict(bkw))
             assert type(k.bias).__name__.lower() == bname.replace("-", "")
+            if w == 0:      # the tables the reference's bias objects evaluate (host-side mirror: smol_b200/bias.py)
+                b = k.bias
+                if tag == "fugacity":
+                    out["bias_fugacity_table"] = np.array(b._fu_table)
+                elif tag == "charge":
+                    out["bias_charge_table"] = np.array(b._c_table)
+                else:
+                    out["bias_hyperplane_dim_ids"] = np.array(b._dim_ids_table)
+                out[f"bias_{tag}_values"] = np.array([b.compute_bias(o) for o in occ0])
             rngs = ScriptedRng(O, seed, w)
             k._rng = rngs
             k.mcusher._rng = rngs

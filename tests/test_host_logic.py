@@ -332,3 +332,28 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(value) == expect, f"{name}.{field}: C {value} vs ctypes {expect}"
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
+def test_bias_tables_match_reference_python_bias_objects():
+    """host-side tables of smol_b200/bias.py (what the device sums) against the tables of the reference's own
+    FugacityBias / SquareChargeBias / SquareHyperplaneBias objects (tests/golden/ref_python_steps.npz)"""
+    import importlib.util
+    from smol_b200.bias import mcbias_factory
+    path = os.path.join(os.path.dirname(__file__), "golden", "make_reference_python_golden.py")
+    spec = importlib.util.spec_from_file_location("make_reference_python_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python_steps.npz"))
+    factory, occ0 = mod.table_flip_model()
+    subl = [Sublattice(s.species, s.sites) for s in factory().sublattices]
+    n = np.arange(occ0.shape[1])
+    fug = mcbias_factory(*mod.BIAS_CASES["fugacity"][:1], subl, **mod.BIAS_CASES["fugacity"][1])
+    np.testing.assert_allclose(fug.table, np.log(gold["bias_fugacity_table"]), rtol=1e-15, atol=0)
+    np.testing.assert_allclose([fug.table[n, o].sum() for o in occ0], gold["bias_fugacity_values"], rtol=1e-13)
+    chg = mcbias_factory(*mod.BIAS_CASES["charge"][:1], subl, **mod.BIAS_CASES["charge"][1])
+    np.testing.assert_array_equal(chg.table, gold["bias_charge_table"])
+    np.testing.assert_allclose([-chg.penalty * chg.table[n, o].sum() ** 2 for o in occ0], gold["bias_charge_values"], rtol=1e-13)
+    hyp = mcbias_factory(*mod.BIAS_CASES["hyperplane"][:1], subl, **mod.BIAS_CASES["hyperplane"][1])
+    np.testing.assert_array_equal(hyp._dim_ids_table, gold["bias_hyperplane_dim_ids"])
+    resid = [hyp.table[n, o].sum(axis=0) - hyp.intercepts for o in occ0]
+    np.testing.assert_allclose([-hyp.penalty * (r ** 2).sum() for r in resid], gold["bias_hyperplane_values"], rtol=1e-13)
