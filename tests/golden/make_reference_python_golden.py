@@ -502,6 +502,11 @@ def main():
             warnings.simplefilter("ignore")      # the constructor's trace-initialising step runs on an all-zero occupancy
             k = Metropolis(factory(), "table-flip", 4000.0, seed=seed, flip_table=TF_TABLE, swap_weight=0.2)
         assert type(k.mcusher).__name__ == "TableFlip"
+        if w == 0:      # tables of the reference's usher (host-side mirror: smol_b200.sampler.table_flip_tables)
+            u = k.mcusher
+            out.update(tf_max_n=np.array(u.max_n), tf_d=np.array([u.d]), tf_weights=np.array(u.flip_weights),
+                       tf_dim_ids_active=np.array(u._dim_ids_table), tf_table=np.array(u.flip_table),
+                       tf_dim_ids=np.array([d for ids in u.dim_ids for d in ids]))
         rngs = TableFlipRng(O, seed, w)
         k._rng = rngs
         k.mcusher._rng = rngs

@@ -357,3 +357,29 @@ def test_bias_tables_match_reference_python_bias_objects():
     np.testing.assert_array_equal(hyp._dim_ids_table, gold["bias_hyperplane_dim_ids"])
     resid = [hyp.table[n, o].sum(axis=0) - hyp.intercepts for o in occ0]
     np.testing.assert_allclose([-hyp.penalty * (r ** 2).sum() for r in resid], gold["bias_hyperplane_values"], rtol=1e-13)
+
+
+def test_table_flip_tables_match_reference_python_usher():
+    """dimension layout, per-dimension site counts, weights of smol_b200.sampler.table_flip_tables against the
+    attributes of the reference's own TableFlip usher (tests/golden/ref_python_steps.npz)"""
+    import importlib.util
+    from smol_b200.sampler import table_flip_tables
+    path = os.path.join(os.path.dirname(__file__), "golden", "make_reference_python_golden.py")
+    spec = importlib.util.spec_from_file_location("make_reference_python_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python_steps.npz"))
+    factory, _ = mod.table_flip_model()
+    subl = [Sublattice(s.species, s.sites) for s in factory().sublattices]
+    t = table_flip_tables(subl, mod.TF_TABLE, swap_weight=0.2)
+    assert t["num_dims"] == int(gold["tf_d"][0]) and list(t["max_n"]) == gold["tf_max_n"].tolist()
+    np.testing.assert_array_equal(t["table"], gold["tf_table"])
+    np.testing.assert_array_equal(t["weights"], gold["tf_weights"])
+    assert gold["tf_dim_ids"].tolist() == list(range(t["num_dims"]))            # dims run sublattice by sublattice
+    # (site, code) -> dimension, the reference's active-sites table
+    active = [s for s in subl if len(s.active_sites) > 0]
+    ours = np.full(gold["tf_dim_ids_active"].shape, -1, dtype=int)
+    for d, (a, code) in enumerate(zip(t["dim_sl"], t["dim_code"])):
+        if a >= 0:
+            ours[active[a].active_sites, code] = d
+    np.testing.assert_array_equal(ours, gold["tf_dim_ids_active"])
