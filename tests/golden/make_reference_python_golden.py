@@ -722,6 +722,10 @@ def main():
         proc = CD(RefSubspace(sub), scm, TF_INTERACTIONS())
         ens = RefEnsemble(proc, sublattices=o_ens.sublattices, chemical_potentials=dict(TF_MUS))
         assert len(ens.natural_parameters) == len(o_ens.natural_parameters)
+        if w == 0:      # the reference ensemble's chemical-potential table (host-side mirror: smol_b200.Ensemble.mu_table)
+            out["ens_mu_table"] = np.array(ens._chemical_potentials["table"])
+            out["ens_natural_parameters"] = np.array(ens.natural_parameters)
+            out["ens_num_energy_coefs"] = np.array([ens.num_energy_coefs])
         seed = 1500 + w
         k = Metropolis(ens, "flip", 4000.0, seed=seed)
         rngs = ScriptedRng(O, seed, w)

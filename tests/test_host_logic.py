@@ -383,3 +383,22 @@ def test_table_flip_tables_match_reference_python_usher():
         if a >= 0:
             ours[active[a].active_sites, code] = d
     np.testing.assert_array_equal(ours, gold["tf_dim_ids_active"])
+
+
+def test_ensemble_mu_table_matches_reference_python_ensemble():
+    """smol_b200.Ensemble (host side): chemical-potential table, natural parameters and the number of energy
+    coefficients against the reference's own Ensemble object (tests/golden/ref_python_steps.npz)"""
+    import importlib.util
+    import smol_b200 as S
+    path = os.path.join(os.path.dirname(__file__), "golden", "make_reference_python_golden.py")
+    spec = importlib.util.spec_from_file_location("make_reference_python_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python_steps.npz"))
+    sub, scm, _ = mod.processor_cases()["rs2of"]
+    ens = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, mod.TF_INTERACTIONS()), chemical_potentials=dict(mod.TF_MUS))
+    np.testing.assert_array_equal(ens.mu_table, gold["ens_mu_table"])
+    np.testing.assert_allclose(ens.natural_parameters, gold["ens_natural_parameters"], rtol=1e-15, atol=0)
+    assert ens.num_energy_coefs == int(gold["ens_num_energy_coefs"][0]) and ens.natural_parameters[-1] == -1.0
+    ens.chemical_potentials = None                     # ChemicalPotentialManager.__delete__ (ensemble.py:72-84)
+    assert len(ens.natural_parameters) == ens.num_energy_coefs and ens.mu_table is None
