@@ -737,6 +737,47 @@ def main():
                     key + "_meta": np.array([seed, 4000.0]),
                     key + "_feat0": np.array(ens.compute_feature_vector(occ0[w])),
                     key + "_natural": np.array(ens.natural_parameters)})
+    # the reference's EwaldProcessor and CompositeProcessor (processor/ewald.py, composite.py, unmodified; the Ewald
+    # MATRIX is an input here -- pymatgen computes it in the reference -- so EwaldTerm's two structure-dependent
+    # methods are overridden to hand over this build's matrix / index layout; get_ewald_occu, the masked matrix sum,
+    # the sequential flip loop over the compiled delta_ewald_single_flip and the feature concatenation are the
+    # reference's)
+    pa = types.ModuleType("pymatgen.analysis")
+    pe = types.ModuleType("pymatgen.analysis.ewald")
+    pe.EwaldSummation = lambda *a, **k: None
+    sys.modules.update({"pymatgen.analysis": pa, "pymatgen.analysis.ewald": pe})
+    ext = types.ModuleType("smol.cofe.extern")
+    ext.__path__ = [REF + "/cofe/extern"]
+    sys.modules["smol.cofe.extern"] = ext
+    sys.modules["smol.cofe.space.domain"].get_allowed_species = sys.modules["smol.cofe.space"].get_allowed_species
+    RealEwaldTerm = importlib.import_module("smol.cofe.extern.ewald").EwaldTerm
+    RefEwaldProcessor = importlib.import_module("smol.moca.processor.ewald").EwaldProcessor
+    RefComposite = importlib.import_module("smol.moca.processor.composite").CompositeProcessor
+    sub, scm, coefs = processor_cases()["rs2of"]
+    occs, flips = processor_flips(sub, scm, seed=3)
+    ewm, ewi = L.ewald_matrix(sub, scm)
+
+    class GivenMatrixTerm(RealEwaldTerm):
+        def get_ewald_structure(self, structure):
+            return None, ewi
+
+        def get_ewald_matrix(self, ewald_summation):
+            return ewm
+    term = GivenMatrixTerm()
+    rsub = RefSubspace(sub)
+    rsub.external_terms = (term,)
+    rsub.add_external_term = lambda t: None
+    ew = RefEwaldProcessor(rsub, scm, term, coefficient=0.1)
+    comp = RefComposite(rsub, scm)
+    comp.add_processor(CD(rsub, scm, L.cluster_interaction_tensors(sub, coefs)))
+    comp.add_processor(ew)
+    for tag, proc in (("ewald", ew), ("composite", comp)):
+        key = f"proc_rs2of_{tag}"
+        out[key + "_full"] = np.array([np.atleast_1d(proc.compute_feature_vector(o)) for o in occs])
+        out[key + "_delta"] = np.array([np.atleast_1d(proc.compute_feature_vector_change(o, f)) for o, f in zip(occs, flips)])
+        out[key + "_prop"] = np.array([float(np.sum(proc.compute_property(o))) for o in occs])
+        out[key + "_dprop"] = np.array([float(np.sum(proc.compute_property_change(o, f))) for o, f in zip(occs, flips)])
+        out[key + "_coefs"] = np.atleast_1d(np.array(proc.coefs, dtype=np.float64))
     # the distance processors behind smol's SQS generation (processor/distance.py, unmodified): features
     # [L, |f_i - target_i| ...]; the target is the vector of the first occupancy, so part of the features match exactly
     dist = importlib.import_module("smol.moca.processor.distance")
