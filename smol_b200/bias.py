@@ -13,7 +13,6 @@ On the device both supported terms are a per-site table and a running table sum 
 from __future__ import annotations
 
 import re
-from math import log
 
 import numpy as np
 

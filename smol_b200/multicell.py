@@ -23,7 +23,6 @@ data dependent).
 """
 from __future__ import annotations
 
-import ctypes as C
 import warnings
 
 import numpy as np

@@ -10,7 +10,6 @@ block, global walker id) -- independent of how walkers are sharded over GPUs.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 import warnings
 
