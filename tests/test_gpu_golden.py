@@ -111,3 +111,29 @@ def test_cuda_reproduces_trajectory_recorded_from_the_reference_python_stack(cud
         h0 = float(np.dot(gold[key + "_natural"], gold[key + "_feat0"]))
         want = h0 + np.cumsum(gold[key + "_dh"] * gold[key + "_acc"])[24::25]
         np.testing.assert_allclose(enth[:, w, 0], want, rtol=1e-10, atol=1e-10 * max(1.0, abs(h0)))
+
+
+@pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU minutes were used)")
+@pytest.mark.parametrize("name", ["fcc3", "fcc421", "rs2of"])
+def test_cuda_matches_records_of_the_reference_python_processors(cuda_device, name):
+    """CUDA full vectors and 1..3-flip changes against the outputs recorded from the reference's OWN
+    ClusterExpansionProcessor / ClusterDecompositionProcessor (tests/golden/ref_python_steps.npz `proc_*`; the oracle
+    reproduces the same records on CPU and the CUDA path equals the oracle in test_gpu_parity.py)"""
+    import importlib.util
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    path = os.path.join(os.path.dirname(__file__), "golden", "make_reference_python_golden.py")
+    spec = importlib.util.spec_from_file_location("make_reference_python_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python_steps.npz"))
+    sub, scm, coefs = mod.processor_cases()[name]
+    occs, flips = mod.processor_flips(sub, scm, seed=3)
+    it = L.cluster_interaction_tensors(sub, coefs)
+    atol = 2e4 * np.finfo(float).eps * sub.supercell_size(scm)
+    for tag, proc in (("ce", S.ClusterExpansionProcessor(sub, scm, coefs)),
+                      ("cd", S.ClusterDecompositionProcessor(sub, scm, it))):
+        key = f"proc_{name}_{tag}"
+        np.testing.assert_allclose(proc.compute_feature_vector_batch(occs), gold[key + "_full"], rtol=1e-10, atol=atol)
+        delta = np.array([proc.compute_feature_vector_change(o, f) for o, f in zip(occs, flips)])
+        np.testing.assert_allclose(delta, gold[key + "_delta"], rtol=1e-10, atol=atol)
