@@ -293,6 +293,7 @@ def processor_flips(sub, scm, seed, n=12):
     return occs, flips
 
 
+SQS_T, SQS_TOL, SQS_W = 3000.0, 1e-5, 0.05   # light weight on the matched diameter: the chain keeps moving
 DIST_TOL = 0.12      # loose on purpose: the largest exactly-matched diameter L takes intermediate values
 DIST_TOL_INT = 0.004  # (cluster interactions are ~coefficient sized)
 CONTAINER_QUERIES = [dict(discard=0, thin_by=1), dict(discard=7, thin_by=3)]
@@ -799,6 +800,56 @@ def main():
             out[key + "_full"] = np.array([proc.compute_feature_vector(o) for o in occs])
             out[key + "_delta"] = np.array([proc.compute_feature_vector_change(o, f) for o, f in zip(occs, flips)])
             out[key + "_coefs"] = np.array(proc.coefs)
+    # the SQS sampling kernel as smol runs it (capp/generate/special/sqs.py:523-540): MulticellMetropolis over
+    # Metropolis kernels whose ensembles wrap CorrelationDistanceProcessors of different supercell shapes -- all of it
+    # the reference's classes (ensemble, distance processors on the compiled evaluators, kernels, ushers)
+    from tests import models as M
+    fsub = M.fcc_subspace()
+    target = np.zeros(fsub.num_corr_functions)
+    target[0] = 1.0                                   # random 50/50 alloy in the sinusoid basis
+    for w in range(len(mc_occ0)):
+        seed, kseeds = 21 + w, [4000 * (k + 1) + w for k in range(len(MC_SHAPES))]
+        kernels, rngs = [], []
+        for k, shape in enumerate(MC_SHAPES):
+            proc = dist.CorrelationDistanceProcessor(RefSubspace(fsub), shape, target_vector=target, match_weight=SQS_W,
+                                                     match_tol=SQS_TOL)
+            subl = [O.Sublattice(("A", "B"), np.arange(8))]
+            for sl in subl:
+                sl.site_space = _SiteSpace({spc: 0.5 for spc in sl.species})
+            kk = Metropolis(RefEnsemble(proc, sublattices=subl), "swap", SQS_T, seed=kseeds[k])
+            r = ScriptedRng(O, kseeds[k], w)
+            kk._rng = r
+            kk.mcusher._rng = r
+            kernels.append(kk)
+            rngs.append(r)
+        mc = MulticellMetropolis(kernels, SQS_T, seed=seed, kernel_hop_periods=[2, 4], kernel_hop_probabilities=[0.5, 0.5])
+
+        class McRng2:
+            def __init__(self):
+                self.np = np.random.default_rng(seed)
+                self.np.choice(np.array([2, 4]), p=[0.5, 0.5])
+                self.t = 0
+
+            def choice(self, a, p=None):
+                return self.np.choice(a, p=p)
+
+            def random(self):
+                return O.u01(O.StepRandom(kseeds[int(mc.trace.kernel_index)], w, self.t).word(3))
+        mrng = McRng2()
+        mc._rng = mrng
+        mc.set_aux_state(np.array(mc_occ0[w], dtype=np.int32))
+        occ = np.array(mc_occ0[w][0], dtype=np.int32)
+        nst = 200
+        idx, acc, occs_ = np.zeros(nst, dtype=np.int64), np.zeros(nst, dtype=bool), np.zeros((nst, 8), dtype=np.int32)
+        for t in range(nst):
+            for r in rngs:
+                r.begin_step(t)
+            mrng.t = t
+            tr = mc.single_step(occ)
+            idx[t], acc[t], occs_[t] = int(mc._current_kernel_index), bool(tr.accepted), occ
+        key = f"mcdist_fcc8_swap_w{w}"
+        out.update({key + "_idx": idx, key + "_acc": acc, key + "_occ": occs_, key + "_meta": np.array([seed, SQS_T, *kseeds]),
+                    key + "_features": np.array(mc._features[mc._current_kernel_index])})
     path = os.path.join(HERE, "ref_python_steps.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in list(out.items())[:6]})
