@@ -72,9 +72,12 @@ class MulticellSampler:
         if any(not np.allclose(e.natural_parameters, ensembles[0].natural_parameters) for e in ensembles):
             raise ValueError("All ensembles must have the same natural parameters.")              # base.py:491-495
         from .processor import DistanceProcessor
-        if any(isinstance(e.processor, DistanceProcessor) for e in ensembles):
-            # (the distance kernels keep a running correlation vector per walker that this driver does not set up yet)
-            raise NotImplementedError("MulticellSampler does not drive distance processors yet")
+        dist = [isinstance(e.processor, DistanceProcessor) for e in ensembles]
+        if any(dist) and not all(dist):
+            raise ValueError("either all or none of the ensembles wrap a distance processor")
+        # distance processors (processor/distance.py; the ensembles of smol's SQS generator): features are the distance
+        # vector, each shape keeps the walkers' running correlation vector beside it
+        self._dist = [e.processor for e in ensembles] if all(dist) else None
         K = len(ensembles)
         if kernel_probabilities is not None:
             if sum(kernel_probabilities) != 1.0:
@@ -181,6 +184,12 @@ class MulticellSampler:
         cfg.trace_accepted_dev, cfg.trace_naccepted_dev = st["acc_tmp"].data_ptr(), st["nacc_tmp"].data_ptr()
         cfg.walker_mask_dev = mask.data_ptr()
         cfg.accept_offset_dev = offset.data_ptr() if offset is not None else None
+        if self._dist is not None:
+            dt = eng.distance_tables(self._dist[k])
+            cfg.dist_mode, cfg.dist_num_groups, cfg.dist_tol = 1, dt["ngrp"], dt["tol"]
+            cfg.dist_target_dev, cfg.dist_group_off_dev = dt["target"].data_ptr(), dt["goff"].data_ptr()
+            cfg.dist_group_idx_dev, cfg.dist_group_diam_dev = dt["gidx"].data_ptr(), dt["gdiam"].data_ptr()
+            cfg.dist_vector_dev = st["vec"][k].data_ptr()
         eng.run(cfg)
         self.launches += 1
 
@@ -201,10 +210,12 @@ class MulticellSampler:
                 raise AttributeError("The given initial occcupancies have incompompatible dimensions. "
                                      f"Shape should be {(W, K, N)}.")
             # (set_aux_state, base.py:694-716: one occupancy per shape; the chain starts in shape 0)
-            st = dict(occ=[], feat=[], enth=[], kseeds=[], beta=[])
+            st = dict(occ=[], feat=[], enth=[], kseeds=[], beta=[], vec=[])
             for k, eng in enumerate(self.engines):
                 o = eng.upload_occupancy(np.ascontiguousarray(occ[:, k, :]))
                 f, h = eng.full_features(o)
+                if self._dist is not None:     # extensive features -> distance vector (in place) + vector per supercell
+                    st["vec"].append(eng.distance_init(self._dist[k], f, h))
                 st["occ"].append(o); st["feat"].append(f); st["enth"].append(h)
                 st["kseeds"].append(torch.from_numpy(self.kernel_seeds[k].view(np.int64).copy()).to(dev))
                 st["beta"].append(torch.full((W,), 1.0 / (self.kB * self.kernel_temperatures[k]), dtype=torch.float64, device=dev))
@@ -270,6 +281,9 @@ class MulticellSampler:
                         r = m & st["alias"][k]
                         st["occ"][k] = torch.where(r[:, None], live, st["occ"][k])
                         f_new, h_new = self.engines[k].full_features(st["occ"][k])
+                        if self._dist is not None:
+                            v_new = self.engines[k].distance_init(self._dist[k], f_new, h_new)
+                            st["vec"][k] = torch.where(r[:, None], v_new, st["vec"][k])
                         st["feat"][k] = torch.where(r[:, None], f_new, st["feat"][k])
                         st["enth"][k] = torch.where(r, h_new, st["enth"][k])
                     mask = m.to(torch.uint8)
