@@ -850,6 +850,20 @@ def main():
         key = f"mcdist_fcc8_swap_w{w}"
         out.update({key + "_idx": idx, key + "_acc": acc, key + "_occ": occs_, key + "_meta": np.array([seed, SQS_T, *kseeds]),
                     key + "_features": np.array(mc._features[mc._current_kernel_index])})
+    # site bases (cofe/space/basis.py, unmodified): function arrays of the sinusoid and indicator bases, raw and
+    # orthonormalised, uniform and concentration measures -- what every correlation tensor is built from
+    from collections import OrderedDict
+    sys.modules["smol.cofe.space.domain"].SiteSpace = type("SiteSpace", (), {})
+    basis = importlib.import_module("smol.cofe.space.basis")
+    for name in ("sinusoid", "indicator"):
+        for n in (2, 3, 4, 5):
+            for mtag, measure in (("uniform", np.full(n, 1.0 / n)), ("conc", np.arange(1, n + 1) / (n * (n + 1) / 2))):
+                space = OrderedDict((f"S{i}", float(measure[i])) for i in range(n))
+                b = basis.basis_factory(name, space)
+                out[f"basis_{name}_{n}_{mtag}_raw"] = np.array(b.function_array)
+                b.orthonormalize()
+                assert b.is_orthonormal
+                out[f"basis_{name}_{n}_{mtag}_orth"] = np.array(b.function_array)
     path = os.path.join(HERE, "ref_python_steps.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in list(out.items())[:6]})
