@@ -176,8 +176,11 @@ typedef struct LmcRunConfig {
   int32_t thin_by;            /* steps per interval */
   int32_t group_size;         /* lanes cooperating on one walker: 0 = auto, else 1..32 (power of 2) */
   int32_t block_threads;      /* 0 = auto */
-  int32_t spec_mode;          /* Metropolis flip/swap kernel: 0 = auto (by measured acceptance), 1 = classic
-                                 (one step per warp), 2 = speculative batch (8 steps per warp, first accept wins) */
+  int32_t spec_mode;          /* Metropolis flip/swap kernel: 0 = auto (by the acceptance the library has seen so far,
+                                 refreshed asynchronously: the choice may differ between identical runs -- the two kernels
+                                 sum dH in different orders), 1 = classic (one step per warp), 2 = speculative batch
+                                 (8 steps per warp, first accept wins; error if unsupported), 3 = speculative where the
+                                 model / run supports it, else classic (deterministic; what the Python host passes) */
   uint64_t step_begin;        /* global index of the first step (RNG counter words 0,1) */
   const uint64_t* seeds_dev;  /* [W] Philox key per walker */
   const double* beta_dev;     /* [W] 1/(kB T); ignored by Wang-Landau */

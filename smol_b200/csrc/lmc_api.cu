@@ -839,7 +839,9 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (spec_mode == 2 && !spec_ok)
     return fail("the speculative kernel supports unbiased Metropolis flip/swap steps (an Ewald term through ewald_field_dev only)");
   // auto: only while the staged tables leave room for a full complement of resident walkers per SM
-  const bool use_spec = spec_ok && (spec_mode == 2 || (spec_mode == 0 && G == 0 && mm->acc_rate < 0.35 && m.blob_bytes <= 40 * 1024));
+  // 3 = speculative whenever this model / run supports it (decided by the caller from ITS acceptance history:
+  // deterministic, unlike the asynchronously refreshed acc_rate of mode 0)
+  const bool use_spec = spec_ok && (spec_mode == 2 || ((spec_mode == 3 || (spec_mode == 0 && mm->acc_rate < 0.35)) && G == 0 && m.blob_bytes <= 40 * 1024));
   if (use_spec) G = 32;
   // lanes per speculated step (lmc_spec.cuh).  Four everywhere: with two or one lane per step (one uses
   // sorted position lists for the swap partner) the scalar work per step shrinks, but 16 / 32 unrelated

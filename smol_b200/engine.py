@@ -36,6 +36,21 @@ def _copy_into(dst: np.ndarray, src: np.ndarray):
                    zip(bounds[:-1], bounds[1:])))
 
 
+def _on_device(fn):
+    """run the method with the engine's device current (launches and allocations of the C ABI go to the current
+    device; a sampler built with ``device="cuda:1"`` must work while another device is current)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        torch = _torch()
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class LmcEngine:
     """One model resident on one CUDA device."""
 
@@ -46,6 +61,8 @@ class LmcEngine:
         self.lib = capi.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.packed = packed
         self.N = int(packed.desc.num_sites)
         self.F = int(packed.desc.num_features)
@@ -67,14 +84,46 @@ class LmcEngine:
     def _stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
-    def upload_occupancy(self, occ_host: np.ndarray):
-        """int32 ``[W, N]`` host array -> int8 ``[W, row_stride]`` device tensor."""
+    def _upload_stream(self):
         torch = _torch()
+        if getattr(self, "_up_stream", None) is None:
+            self._up_stream = torch.cuda.Stream(device=self.device)
+        return self._up_stream
+
+    def _h2d_int32(self, pinned):
+        """page-locked int32 ``[W, N]`` -> device, on the upload stream: the copy overlaps whatever the launching
+        stream is still running (the tail of the previous run); the launching stream waits for it."""
+        torch = _torch()
+        main = torch.cuda.current_stream(self.device)
+        up = self._upload_stream()
+        with torch.cuda.stream(up):
+            src = pinned.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(up)
+        src.record_stream(main)
+        main.wait_event(ev)
+        return src, ev
+
+    @_on_device
+    def upload_occupancy(self, occ_host):
+        """occupancies ``[W, N]`` (host array, page-locked int32 tensor or CUDA tensor) -> int8
+        ``[W, row_stride]`` device tensor.  The input is never modified."""
+        torch = _torch()
+        if isinstance(occ_host, torch.Tensor) and occ_host.is_cuda:
+            # device-resident entry: no host round trip
+            if occ_host.device != self.device:
+                occ_host = occ_host.to(self.device)
+            W = occ_host.shape[0]
+            src = occ_host if (occ_host.dtype == torch.int32 and occ_host.is_contiguous()) \
+                else occ_host.to(torch.int32).contiguous()
+            dst = torch.empty((W, self.row_stride), dtype=torch.int8, device=self.device)
+            capi.check(self.lib.lmc_cast_i32_to_i8(src.data_ptr(), dst.data_ptr(), W, self.N, self._stream()))
+            return dst
         if isinstance(occ_host, torch.Tensor) and occ_host.device.type == "cpu" and occ_host.is_pinned() \
                 and occ_host.dtype == torch.int32 and occ_host.is_contiguous():
             # the caller's buffer is already page-locked int32: copy straight from it (no staging pass)
             W = occ_host.shape[0]
-            src = occ_host.to(self.device, non_blocking=True)
+            src, self._pin_evt = self._h2d_int32(occ_host)
             dst = torch.empty((W, self.row_stride), dtype=torch.int8, device=self.device)
             capi.check(self.lib.lmc_cast_i32_to_i8(src.data_ptr(), dst.data_ptr(), W, self.N, self._stream()))
             return dst
@@ -91,14 +140,13 @@ class LmcEngine:
         if getattr(self, "_pin_evt", None) is not None:
             self._pin_evt.synchronize()          # the previous async copy has consumed the buffer
         _copy_into(self._pin_buf.numpy(), occ_host)   # one pass: copy + int32 conversion
-        src = self._pin_buf.to(self.device, non_blocking=True)
-        self._pin_evt = torch.cuda.Event()
-        self._pin_evt.record(torch.cuda.current_stream(self.device))
+        src, self._pin_evt = self._h2d_int32(self._pin_buf)
         dst = torch.empty((W, self.row_stride), dtype=torch.int8, device=self.device)
         capi.check(self.lib.lmc_cast_i32_to_i8(src.data_ptr(), dst.data_ptr(), W, self.N,
                                                self._stream()))
         return dst
 
+    @_on_device
     def occupancy_to_int32(self, occ_dev, rows: int, stride: int):
         """int8 device rows -> int32 ``[rows, N]`` device tensor."""
         torch = _torch()
@@ -107,6 +155,7 @@ class LmcEngine:
                                                stride, self._stream()))
         return out
 
+    @_on_device
     def full_features(self, occ_dev):
         torch = _torch()
         W = occ_dev.shape[0]
@@ -116,6 +165,7 @@ class LmcEngine:
                                               enth.data_ptr(), self._stream()))
         return feat, enth
 
+    @_on_device
     def delta_features(self, occ_dev, sites, codes):
         """sites/codes: int32 device tensors ``[W, k]``."""
         torch = _torch()
@@ -131,6 +181,7 @@ class LmcEngine:
         capi.check(self.lib.lmc_model_info(self.handle, info, 4))
         return tuple(int(x) for x in info)
 
+    @_on_device
     def ewald_field(self, occ_dev, out=None):
         """Ewald potential cache ``[W, N]`` (float64) of the walkers' occupancies, see ``lmc.h``."""
         torch = _torch()
@@ -140,6 +191,7 @@ class LmcEngine:
         capi.check(self.lib.lmc_ewald_field(self.handle, occ_dev.data_ptr(), W, out.data_ptr(), self._stream()))
         return out
 
+    @_on_device
     def distance_tables(self, processor):
         """device copies of a DistanceProcessor's target vector and orbit groups (cached per engine)"""
         torch = _torch()
@@ -152,6 +204,7 @@ class LmcEngine:
                                                ngrp=len(gdiam)))
         return self._dist_tabs[1]
 
+    @_on_device
     def distance_init(self, processor, feat, enth=None):
         """extensive features ``feat [W, F]`` -> distance vectors in place; returns the vectors per supercell."""
         torch = _torch()
@@ -164,6 +217,7 @@ class LmcEngine:
                                               d["gdiam"].data_ptr(), self._stream()))
         return vec
 
+    @_on_device
     def run(self, cfg: capi.LmcRunConfig):
         capi.check(self.lib.lmc_run(self.handle, C.byref(cfg), self._stream()))
 

@@ -68,8 +68,12 @@ class _PinnedPool:
         self.outstanding += t.numel() * t.element_size()
         return t
 
-    def release(self, t):
+    def release(self, t, recycle=True):
+        """``recycle=False``: the block is still viewed by a caller (it lives on until that view dies), it only
+        stops counting against the budget"""
         self.outstanding -= t.numel() * t.element_size()
+        if not recycle:
+            return
         lst = self.free.setdefault((tuple(t.shape), t.dtype), [])
         if len(lst) < 8:
             lst.append(t)
@@ -311,11 +315,14 @@ class Sampler:
     def samples(self):
         return self._container
 
+    def _slot_key(self, index, nmax, W, N, F):
+        return (index, nmax, W, N, F, self.record_occupancy, self.bias is not None, len(self._wl_trace))
+
     def _trace_slot(self, index, nmax, W, N, F, dev):
         """Cached trace slot ``index``: device buffers + page-locked host staging for ``nmax`` samples."""
         import torch
         cache = self.__dict__.setdefault("_slots", {})
-        key = (index, nmax, W, N, F, self.record_occupancy, self.bias is not None, len(self._wl_trace))
+        key = self._slot_key(index, nmax, W, N, F)
         if cache.get(index, {}).get("key") != key:
             shapes = {"features": ((nmax, W, F), torch.float64), "enthalpy": ((nmax, W), torch.float64),
                       "accepted": ((nmax, W), torch.uint8), "n_accepted": ((nmax, W), torch.int32),
@@ -337,6 +344,13 @@ class Sampler:
         if slot["host"] is None:
             slot["host"] = {k: torch.empty(sh, dtype=dt, pin_memory=True) for k, (sh, dt) in slot["shapes"].items()}
         return slot["host"]
+
+    def detach_samples(self):
+        """Hand over the samples collected so far and start an empty container: with ``run(block=False)`` the
+        returned container resolves its last chunk when it is first read, while the sampler already runs on."""
+        old = self._container
+        self._container = SampleContainer(self.ensemble, self.nwalkers, dict(old._shapes), dict(old.metadata))
+        return old
 
     def efficiency(self, discard=0, flat=True):
         return self.samples.sampling_efficiency(discard=discard, flat=flat)
@@ -384,13 +398,12 @@ class Sampler:
         return out
 
     # ---- run (sampler.py:164-297, 386-434) ------------------------------------------------------------
-    def run(self, nsteps, initial_occupancies=None, thin_by=1, progress=False, stream_chunk=0,
-            stream_file=None, keep_last_chunk=False, swmr_mode=False, max_chunk_bytes=2 << 30,
-            pipeline_chunks=4):
+    def _begin_run(self, initial_occupancies, thin_by):
+        """Everything ``Sampler.run`` does before the step loop (sampler.py:386-434): copy of the initial
+        occupancies onto the device, initial trace (full evaluation), auxiliary states of the kernels."""
         import torch
+        from types import SimpleNamespace
         eng = self.engine
-        if stream_chunk:
-            raise NotImplementedError("HDF5 streaming (container.py:420-512) is not part of this build")
         if initial_occupancies is None:
             if self._occ_dev is None:
                 raise RuntimeError("There are no saved samples to obtain the initial occupancies."
@@ -407,32 +420,30 @@ class Sampler:
                 raise AttributeError("The given initial occcupancies have incompompatible dimensions. "
                                      f"Shape should be {(self.nwalkers, eng.N)}.")
             # copied (sampler.py:401) and converted to int32 (sampler.py:406) on the way into the
-            # page-locked staging buffer; the caller's array is never modified
+            # page-locked staging buffer; the caller's array is never modified.  A CUDA tensor never
+            # touches the host (device-resident entry).
             self._occ_dev = eng.upload_occupancy(occ)
-        if nsteps % thin_by != 0:
-            warnings.warn(f"The number of steps {nsteps} is not a multiple of thin_by  {thin_by}. "
-                          f"The last {nsteps % thin_by} will be ignored.", category=RuntimeWarning)
-        S = nsteps // thin_by
         W, N, F = self.nwalkers, eng.N, eng.F
         dev = eng.device
+        ctx = SimpleNamespace(thin_by=thin_by)
         # initial trace: full evaluation of the starting occupancies (base.py:345-365,
         # wanglandau.py:290-300)
-        feat, enth = eng.full_features(self._occ_dev)
+        ctx.feat, ctx.enth = eng.full_features(self._occ_dev)
         # Ewald potential cache: rebuilt from the occupancies at every run (bounds its rounding drift to one
         # run), kept current by the kernels in between
-        use_field = False
+        ctx.use_field = False
         if self.ewald_field is not False and eng.model_info()[0]:
-            use_field = self.ewald_field is True or self._acc_est is None or self._acc_est < 0.25
+            ctx.use_field = self.ewald_field is True or self._acc_est is None or self._acc_est < 0.25
         elif self.ewald_field is True:
             raise RuntimeError("ewald_field=True needs an Ewald term whose matrix factorises as q_i q_j K[site_i, site_j]")
-        if use_field:
+        if ctx.use_field:
             self._ew_field = eng.ewald_field(self._occ_dev, out=self._ew_field)
         from .processor import DistanceProcessor
-        dist_proc = self.ensemble.processor if isinstance(self.ensemble.processor, DistanceProcessor) else None
-        dist_vec = None
-        if dist_proc is not None:
+        ctx.dist_proc = self.ensemble.processor if isinstance(self.ensemble.processor, DistanceProcessor) else None
+        ctx.dist_vec = None
+        if ctx.dist_proc is not None:
             # distance processors: features = distance vector, running correlation vector kept beside it
-            dist_vec = eng.distance_init(dist_proc, feat, enth)
+            ctx.dist_vec = eng.distance_init(ctx.dist_proc, ctx.feat, ctx.enth)
         if self.bias is not None:
             # initial bias of the starting occupancies (base.py:362-363), then kept current by the kernel
             if self._bias_dev is None:
@@ -450,15 +461,130 @@ class Sampler:
             self._init_wl()
         if getattr(self, "_seeds_dev", None) is None:
             self._seeds_dev = torch.from_numpy(self.seeds.view(np.int64)).to(dev)
-        seeds = self._seeds_dev
+        ctx.seeds = self._seeds_dev
         with np.errstate(divide="ignore"):
             beta_h = np.where(np.isinf(self._temperature), 0.0, 1.0 / (self.kB * self._temperature))
         bkey = beta_h.tobytes()
         if getattr(self, "_beta_key", None) != bkey:     # re-uploaded only when a temperature changed
             self._beta_dev = torch.from_numpy(np.ascontiguousarray(beta_h)).to(dev)
             self._beta_key = bkey
-        beta = self._beta_dev
-        per_sample = W * ((N if self.record_occupancy else 0) + 8 * F + 8 + 1 + 4)
+        ctx.beta = self._beta_dev
+        # Metropolis flip / swap kernel (classic or speculative batches): decided HERE from the acceptance of the
+        # runs this sampler has completed, so identical call sequences take identical kernels
+        ctx.spec_mode = self.spec_mode
+        if ctx.spec_mode == 0:
+            ctx.spec_mode = 3 if (self._acc_est is None or self._acc_est < 0.35) else 1
+        return ctx
+
+    def _run_config(self, ctx, d, n):
+        """``LmcRunConfig`` of one launch: ``n`` sampling intervals into the device trace buffers ``d``."""
+        eng = self.engine
+        thin_by = ctx.thin_by
+        cfg = capi.LmcRunConfig()
+        cfg.num_walkers, cfg.walker_id_base = self.nwalkers, self.walker_id_base
+        cfg.usher, cfg.kernel = self._usher, self._kernel
+        cfg.num_samples, cfg.thin_by = n, thin_by
+        cfg.group_size, cfg.block_threads = self.group_size, self.block_threads
+        cfg.spec_mode = ctx.spec_mode
+        cfg.step_begin = self._step_counter
+        cfg.seeds_dev, cfg.beta_dev = ctx.seeds.data_ptr(), ctx.beta.data_ptr()
+        cfg.occ_dev, cfg.features_dev, cfg.enthalpy_dev = \
+            self._occ_dev.data_ptr(), ctx.feat.data_ptr(), ctx.enth.data_ptr()
+        cfg.trace_occ_dev = d["occupancy"].data_ptr() if self.record_occupancy else None
+        cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
+        cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
+        cfg.ewald_field_dev = self._ew_field.data_ptr() if ctx.use_field else None
+        if ctx.dist_proc is not None:
+            dt = eng.distance_tables(ctx.dist_proc)
+            cfg.dist_mode, cfg.dist_num_groups, cfg.dist_tol = 1, dt["ngrp"], dt["tol"]
+            cfg.dist_target_dev, cfg.dist_group_off_dev = dt["target"].data_ptr(), dt["goff"].data_ptr()
+            cfg.dist_group_idx_dev, cfg.dist_group_diam_dev = dt["gidx"].data_ptr(), dt["gdiam"].data_ptr()
+            cfg.dist_vector_dev = ctx.dist_vec.data_ptr()
+        if self._multistep is not None:
+            code, lens, cum = self._multistep
+            cfg.ms_usher, cfg.ms_num = code, len(lens)
+            for i, ln in enumerate(lens):
+                cfg.ms_len[i] = ln
+                cfg.ms_cum[i] = float(cum[i])
+        if self._composite is not None:
+            codes, cum, sl_cum = self._composite
+            cfg.comp_num = len(codes)
+            for i, code in enumerate(codes):
+                cfg.comp_usher[i] = code
+                cfg.comp_cum[i] = float(cum[i])
+                for k in range(capi.LMC_MAX_SUBLATTICES):
+                    cfg.comp_sl_cum[i][k] = float(sl_cum[i, k])
+        if self.bias is not None:
+            b = self._bias_dev
+            cfg.bias_mode, cfg.bias_width, cfg.bias_rows = self.bias.mode, self.bias.table.shape[1], self.bias.rows
+            cfg.bias_penalty = float(self.bias.penalty)
+            cfg.bias_table_dev, cfg.bias_dev, cfg.bias_sum_dev = b["table"].data_ptr(), b["value"].data_ptr(), b["tsum"].data_ptr()
+            cfg.trace_bias_dev = d["bias"].data_ptr()
+        if self._kernel == capi.LMC_KERNEL_WANGLANDAU:
+            p, st = self._wl, self._wl_state
+            wl = cfg.wl
+            wl.min_enthalpy, wl.max_enthalpy, wl.bin_size = p["min_enthalpy"], p["max_enthalpy"], p["bin_size"]
+            wl.flatness = p["flatness"]
+            wl.mod_update = float(p["mod_update"]) if p.get("mod_update") is not None else 2.0
+            wl.num_bins, wl.check_period, wl.update_period = len(st["levels"]), p["check_period"], p["update_period"]
+            wl.reserved = 1 if int(p["update_period"]) == 1 else 0   # mean_features buffer holds sums
+            wl.entropy_dev, wl.histogram_dev = st["entropy"].data_ptr(), st["histogram"].data_ptr()
+            wl.occurrences_dev, wl.mean_features_dev = st["occurrences"].data_ptr(), st["mean_features"].data_ptr()
+            wl.mod_factor_dev, wl.steps_counter_dev = st["mod_factor"].data_ptr(), st["steps_counter"].data_ptr()
+            for name, _, _ in self._wl_trace:
+                field = {"entropy": "trace_entropy_dev", "histogram": "trace_histogram_dev",
+                         "occurrences": "trace_occurrences_dev", "mod_factor": "trace_mod_factor_dev",
+                         "cumulative_mean_features": "trace_mean_features_dev"}[name]
+                setattr(wl, field, d[name].data_ptr())
+        return cfg
+
+    def _bytes_per_sample(self):
+        """device / page-locked bytes of one sampling interval over all walkers (every trace array)"""
+        W, N, F = self.nwalkers, self.engine.N, self.engine.F
+        per_walker = (N if self.record_occupancy else 0) + 8 * F + 8 + 1 + 4
+        if self.bias is not None:
+            per_walker += 8
+        for _, shape, dtype in self._wl_trace:
+            per_walker += int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return W * per_walker
+
+    def run(self, nsteps, initial_occupancies=None, thin_by=1, progress=False, stream_chunk=0,
+            stream_file=None, keep_last_chunk=False, swmr_mode=False, max_chunk_bytes=2 << 30,
+            pipeline_chunks=4, block=True):
+        """``Sampler.run`` (sampler.py:212-301).
+
+        ``initial_occupancies`` may be a host array, a page-locked ``torch.int32`` tensor (copied straight from it)
+        or a CUDA tensor (never touches the host).  ``block=False`` returns as soon as every launch and copy of
+        the run is enqueued: the last chunk of traces is handed to the sample container when the samples are
+        first looked at (or by the next ``run``, after ITS first launch -- back-to-back runs then overlap the
+        upload and initial evaluation of run k+1 with the tail of run k).  ``stream_chunk`` / ``stream_file`` /
+        ``keep_last_chunk`` stream the samples to a file backend every ``stream_chunk`` samples
+        (sampler.py:271-297, container.py:420-512)."""
+        import torch
+        eng = self.engine
+        with torch.cuda.device(eng.device):
+            return self._run(nsteps, initial_occupancies, thin_by, stream_chunk, stream_file, keep_last_chunk,
+                             swmr_mode, max_chunk_bytes, pipeline_chunks, block)
+
+    def _run(self, nsteps, initial_occupancies, thin_by, stream_chunk, stream_file, keep_last_chunk, swmr_mode,
+             max_chunk_bytes, pipeline_chunks, block):
+        import torch
+        eng = self.engine
+        if stream_chunk > 0:
+            if nsteps % stream_chunk != 0:
+                raise ValueError("streaming chunk must be a divisor of nsteps.")     # sampler.py:281-282
+            if stream_chunk % thin_by != 0:
+                raise ValueError("streaming chunk must be a multiple of thin_by.")
+            backend = self.samples.get_backend(stream_file, nsteps // thin_by, swmr_mode=swmr_mode)
+        # (a deferred tail of the previous run is resolved after this run's first launch, see below)
+        ctx = self._begin_run(initial_occupancies, thin_by)
+        if nsteps % thin_by != 0:
+            warnings.warn(f"The number of steps {nsteps} is not a multiple of thin_by  {thin_by}. "
+                          f"The last {nsteps % thin_by} will be ignored.", category=RuntimeWarning)
+        S = nsteps // thin_by
+        W, N, F = self.nwalkers, eng.N, eng.F
+        dev = eng.device
+        per_sample = self._bytes_per_sample()
         # The run is cut into a few launches so that the device->host copy and the host-side
         # bookkeeping of chunk i overlap the kernel of chunk i+1 (double-buffered trace slots, copies
         # on a side stream).  The chains are unaffected: the RNG is counter based.
@@ -467,11 +593,18 @@ class Sampler:
             nmax = min(nmax, -(-S // pipeline_chunks))
         elif S >= 2:
             nmax = min(nmax, -(-S // 2))
+        if stream_chunk > 0:
+            per_flush = stream_chunk // thin_by       # launches end on flush boundaries
+            nmax = max(k for k in range(1, max(1, min(nmax, per_flush)) + 1) if per_flush % k == 0)
         self._kernel_events = []
         main = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+        if self.samples.has_deferred and self._slot_key(0, nmax, W, N, F) != self.__dict__.get("_slots", {}).get(0, {}).get("key"):
+            self.samples.resolve_deferred()      # the trace slots are about to be re-allocated under a pending copy
         slots = [self._trace_slot(i, nmax, W, N, F, dev) for i in range(2)]
+        # the previous run's deferred tail is still being copied out of the slot it used: start with the other one
+        phase = self.__dict__.get("_slot_phase", 0)
 
         def finalize(host, pooled, n, ev_copy):
             ev_copy.synchronize()
@@ -480,7 +613,7 @@ class Sampler:
                 # the trace arrays ARE the page-locked blocks the copy engine wrote: no host copy
                 arrs = {k: v.numpy() for k, v in host.items()}
                 for k, v in host.items():
-                    owned.append(((lambda t=v: _PINNED.release(t)), arrs[k]))
+                    owned.append(((lambda recycle=True, t=v: _PINNED.release(t, recycle)), arrs[k]))
                 traces = {"features": arrs["features"][:n], "enthalpy": arrs["enthalpy"][:n][:, :, None],
                           "accepted": arrs["accepted"][:n].view(np.bool_)[:, :, None],
                           "n_accepted": arrs["n_accepted"][:n]}
@@ -509,72 +642,20 @@ class Sampler:
             if not self.record_occupancy:
                 traces["occupancy"] = np.zeros((n, W, 0), dtype=np.int8)
             if "temperature" in self.samples._shapes:
-                traces["temperature"] = np.broadcast_to(self._temperature[None, :, None], (n, W, 1)).copy()
-            if n and W:   # acceptance of the chunk: steers the Ewald path of the next run
+                traces["temperature"] = np.broadcast_to(temperature[None, :, None], (n, W, 1)).copy()
+            if n and W:   # acceptance of the chunk: steers the kernel / Ewald path of the next run
                 self._acc_est = float(traces["n_accepted"][-1].mean()) / thin_by
-            self.samples.append(traces, thin_by, owned=owned)
+            return traces, thin_by, owned
 
+        temperature = self._temperature.copy()
         done, ci, pending = 0, 0, None
         while done < S:
             n = min(nmax, S - done)
-            slot = slots[ci % 2]
+            slot = slots[(ci + phase) % 2]
             d = slot["dev"]
-            cfg = capi.LmcRunConfig()
-            cfg.num_walkers, cfg.walker_id_base = W, self.walker_id_base
-            cfg.usher, cfg.kernel = self._usher, self._kernel
-            cfg.num_samples, cfg.thin_by = n, thin_by
-            cfg.group_size, cfg.block_threads = self.group_size, self.block_threads
-            cfg.spec_mode = self.spec_mode
-            cfg.step_begin = self._step_counter
-            cfg.seeds_dev, cfg.beta_dev = seeds.data_ptr(), beta.data_ptr()
-            cfg.occ_dev, cfg.features_dev, cfg.enthalpy_dev = \
-                self._occ_dev.data_ptr(), feat.data_ptr(), enth.data_ptr()
-            cfg.trace_occ_dev = d["occupancy"].data_ptr() if self.record_occupancy else None
-            cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
-            cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
-            cfg.ewald_field_dev = self._ew_field.data_ptr() if use_field else None
-            if dist_proc is not None:
-                dt = eng.distance_tables(dist_proc)
-                cfg.dist_mode, cfg.dist_num_groups, cfg.dist_tol = 1, dt["ngrp"], dt["tol"]
-                cfg.dist_target_dev, cfg.dist_group_off_dev = dt["target"].data_ptr(), dt["goff"].data_ptr()
-                cfg.dist_group_idx_dev, cfg.dist_group_diam_dev = dt["gidx"].data_ptr(), dt["gdiam"].data_ptr()
-                cfg.dist_vector_dev = dist_vec.data_ptr()
-            if self._multistep is not None:
-                code, lens, cum = self._multistep
-                cfg.ms_usher, cfg.ms_num = code, len(lens)
-                for i, ln in enumerate(lens):
-                    cfg.ms_len[i] = ln
-                    cfg.ms_cum[i] = float(cum[i])
-            if self._composite is not None:
-                codes, cum, sl_cum = self._composite
-                cfg.comp_num = len(codes)
-                for i, code in enumerate(codes):
-                    cfg.comp_usher[i] = code
-                    cfg.comp_cum[i] = float(cum[i])
-                    for k in range(capi.LMC_MAX_SUBLATTICES):
-                        cfg.comp_sl_cum[i][k] = float(sl_cum[i, k])
-            if self.bias is not None:
-                b = self._bias_dev
-                cfg.bias_mode, cfg.bias_width, cfg.bias_rows = self.bias.mode, self.bias.table.shape[1], self.bias.rows
-                cfg.bias_penalty = float(self.bias.penalty)
-                cfg.bias_table_dev, cfg.bias_dev, cfg.bias_sum_dev = b["table"].data_ptr(), b["value"].data_ptr(), b["tsum"].data_ptr()
-                cfg.trace_bias_dev = d["bias"].data_ptr()
-            if self._kernel == capi.LMC_KERNEL_WANGLANDAU:
-                p, st = self._wl, self._wl_state
-                wl = cfg.wl
-                wl.min_enthalpy, wl.max_enthalpy, wl.bin_size = p["min_enthalpy"], p["max_enthalpy"], p["bin_size"]
-                wl.flatness = p["flatness"]
-                wl.mod_update = float(p["mod_update"]) if p.get("mod_update") is not None else 2.0
-                wl.num_bins, wl.check_period, wl.update_period = len(st["levels"]), p["check_period"], p["update_period"]
-                wl.reserved = 1 if int(p["update_period"]) == 1 else 0   # mean_features buffer holds sums
-                wl.entropy_dev, wl.histogram_dev = st["entropy"].data_ptr(), st["histogram"].data_ptr()
-                wl.occurrences_dev, wl.mean_features_dev = st["occurrences"].data_ptr(), st["mean_features"].data_ptr()
-                wl.mod_factor_dev, wl.steps_counter_dev = st["mod_factor"].data_ptr(), st["steps_counter"].data_ptr()
-                for name, _, _ in self._wl_trace:
-                    field = {"entropy": "trace_entropy_dev", "histogram": "trace_histogram_dev",
-                             "occurrences": "trace_occurrences_dev", "mod_factor": "trace_mod_factor_dev",
-                             "cumulative_mean_features": "trace_mean_features_dev"}[name]
-                    setattr(wl, field, d[name].data_ptr())
+            cfg = self._run_config(ctx, d, n)
+            if slot.get("copy_event") is not None:
+                main.wait_event(slot["copy_event"])     # (a deferred tail may still be reading this slot)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(main)
             eng.run(cfg)
@@ -589,6 +670,7 @@ class Sampler:
                 for v in host.values():
                     if v is not None:
                         _PINNED.release(v)
+                self.samples.resolve_deferred()
                 host = self._slot_staging(slot)
             ev_copy = torch.cuda.Event()
             with torch.cuda.stream(self._copy_stream):
@@ -596,17 +678,84 @@ class Sampler:
                 for k in names:
                     host[k][:n].copy_(d[k][:n], non_blocking=True)
                 ev_copy.record(self._copy_stream)
+            slot["copy_event"] = ev_copy
+            # tail of the PREVIOUS run: resolved only now, behind this run's upload, initial evaluation and
+            # first launch, which therefore overlapped it
+            self.samples.resolve_deferred()
             if pending is not None:
-                finalize(*pending)        # overlaps the kernel just launched
+                self.samples.append(*finalize(*pending))        # overlaps the kernel just launched
+                if stream_chunk > 0 and self.samples.num_samples >= per_flush:
+                    self.samples.flush_to_backend(backend)      # sampler.py:286-291
             pending = (host, pooled, n, ev_copy)
             done += n
             ci += 1
+        self.samples.resolve_deferred()
+        self._slot_phase = (ci + phase) % 2          # slot the next launch would take = NOT the tail's
+        events, self._kernel_events = self._kernel_events, []
+        self._last_events = events
         if pending is not None:
-            finalize(*pending)
-        torch.cuda.synchronize(dev)
-        # device time of the lmc_run launches of this call (CUDA events on the launching stream)
-        self.last_kernel_ms = float(sum(a.elapsed_time(b) for a, b in self._kernel_events))
-        self._kernel_events = []
+            if block or stream_chunk > 0 or not pending[1]:
+                self.samples.append(*finalize(*pending))
+            else:
+                n_tail = pending[2]
+                self.samples.defer(n_tail, thin_by, lambda p=pending: finalize(*p))
+        if stream_chunk > 0:
+            if self.samples.num_samples:
+                self.samples.flush_to_backend(backend)
+            backend.close()
+            if keep_last_chunk is False:
+                self.clear_samples()                             # sampler.py:293-297
+        if block:
+            torch.cuda.synchronize(dev)
+        elif getattr(eng, "_pin_evt", None) is not None:
+            eng._pin_evt.synchronize()       # the caller's (page-locked) input buffer has been consumed
+
+    @property
+    def last_kernel_ms(self):
+        """device time of the lmc_run launches of the last ``run`` (CUDA events on the launching stream)"""
+        ev = getattr(self, "_last_events", None)
+        if not ev:
+            return 0.0
+        ev[-1][1].synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in ev))
+
+    def run_device(self, nsteps, initial_occupancies=None, thin_by=1, out=None, reuse_state=False):
+        """Device-resident form of ``run``: the same chains, but every trace stays in HBM.
+
+        Returns a dict of CUDA tensors ``[S, W, ...]`` (``occupancy`` int8 codes, ``features`` / ``enthalpy``
+        float64, ``accepted`` uint8, ``n_accepted`` int32, bias / Wang-Landau arrays when traced) for callers that
+        post-process on the GPU; nothing is copied to the host and nothing is appended to ``samples``.
+        ``initial_occupancies``: host array or CUDA tensor (int32 ``[W, N]``), ``None`` continues the chains.
+        ``out``: the dict of a previous call with the same shape, to be overwritten (no allocation).
+        ``reuse_state=True`` (with ``initial_occupancies=None``) continues from the running features / enthalpies
+        the previous ``run_device`` left on the device instead of re-evaluating the occupancies in full (the
+        reference re-evaluates at every ``run``, sampler.py:423-429; the kernels keep the running values
+        current, so the chains are the same up to the rounding of the running sums)."""
+        import torch
+        eng = self.engine
+        with torch.cuda.device(eng.device):
+            self.samples.resolve_deferred()
+            prev = getattr(self, "_resident_ctx", None)
+            if reuse_state and initial_occupancies is None and prev is not None and prev.thin_by == thin_by:
+                ctx = prev
+            else:
+                ctx = self._begin_run(initial_occupancies, thin_by)
+                self._resident_ctx = ctx
+            S = nsteps // thin_by
+            W, N, F = self.nwalkers, eng.N, eng.F
+            if out is None:
+                slot = self._trace_slot("resident", S, W, N, F, eng.device)
+                out = slot["dev"]
+            if S:
+                main = torch.cuda.current_stream(eng.device)
+                cfg = self._run_config(ctx, out, S)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(main)
+                eng.run(cfg)
+                ev1.record(main)
+                self._last_events = [(ev0, ev1)]
+                self._step_counter += S * thin_by
+            return out
 
     def anneal(self, temperatures, mcmc_steps, initial_occupancies=None, thin_by=1, progress=False,
                stream_chunk=0, stream_file=None, swmr_mode=True):

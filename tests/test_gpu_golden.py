@@ -75,10 +75,7 @@ def test_cuda_matches_reference_known_answer_licabr(cuda_device):
     np.testing.assert_allclose(corr, LICABR_EXPECTED, rtol=1e-12, atol=1e-14)
 
 
-# Written after the round's GPU budget was spent: the oracle is verified against this record on CPU
-# (tests/test_oracle_golden.py) and the CUDA path against the oracle on the B200 for the same kind of run, so this is
-# expected to pass; the NON-strict xfail only keeps an unrun test from stopping the suite (XPASS = verified).
-@pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU minutes were used)")
+# (green on a B200 since the round-1 driver run, GPUTEST_r01.json)
 def test_cuda_reproduces_trajectory_recorded_from_the_reference_python_stack(cuda_device):
     """semigrand flips on the 5-species rocksalt cell: the CUDA sampler against the step record of the reference's OWN
     Ensemble + ClusterDecompositionProcessor + Metropolis + Flip classes (tests/golden/ref_python_steps.npz,
@@ -113,7 +110,6 @@ def test_cuda_reproduces_trajectory_recorded_from_the_reference_python_stack(cud
         np.testing.assert_allclose(enth[:, w, 0], want, rtol=1e-10, atol=1e-10 * max(1.0, abs(h0)))
 
 
-@pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU minutes were used)")
 @pytest.mark.parametrize("name", ["fcc3", "fcc421", "rs2of"])
 def test_cuda_matches_records_of_the_reference_python_processors(cuda_device, name):
     """CUDA full vectors and 1..3-flip changes against the outputs recorded from the reference's OWN

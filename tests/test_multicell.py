@@ -85,13 +85,10 @@ def test_oracle_multicell_tracks_full_features():
     np.testing.assert_array_equal(out["occupancy"][-1, 0], chain.current_occupancy)
 
 
-# share=False ran green on a B200 (97-test round-1 pass).  share=True (the reference's aliasing semantics, found and
-# restated after the round's GPU budget was spent) adds only torch row copies and lmc_full_features calls in front of
-# the same masked launches and is checked against the oracle on CPU through the engine stand-in above; its first GPU
-# run is reported through a NON-strict xfail so that it cannot stop the suite: XPASS = verified, then drop the mark.
+# share=True = the reference's aliasing semantics: torch row copies and lmc_full_features calls in front of the same
+# masked launches; both modes green on a B200 (GPUTEST_r01.json)
 @pytest.mark.gpu
-@pytest.mark.parametrize("share", [False, pytest.param(True, marks=pytest.mark.xfail(
-    strict=False, reason="shared-live-row multicell mode has not yet run on a B200"))], ids=["own-rows", "shared-live-row"])
+@pytest.mark.parametrize("share", [False, True], ids=["own-rows", "shared-live-row"])
 @pytest.mark.parametrize("step", ["swap", "flip"])
 def test_multicell_trajectory_vs_oracle(cuda_device, step, share):
     from smol_b200.multicell import MulticellSampler
@@ -326,7 +323,6 @@ def test_multicell_over_distance_processors_host_logic(monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="multicell over distance processors has not yet run on a B200")
 def test_multicell_over_distance_processors_vs_oracle(cuda_device):
     """the same on the CUDA path (DIST kernel variants with walker masks and hop offsets)"""
     from smol_b200.multicell import MulticellSampler
