@@ -65,15 +65,32 @@ class ShardedSampler:
                                            seeds=list(seeds[self.start:self.start + self.count]),
                                            walker_id_base=self.start, **kwargs)
 
-    def run(self, nsteps, initial_occupancies=None, thin_by=1, **kw):
+    def run(self, nsteps, initial_occupancies=None, thin_by=1, resident=None, **kw):
+        """Advance this rank's walkers.  ``resident`` (default: on when the process group's backend is NCCL): the
+        traces stay on the device (``Sampler.run_device``) and ``gather`` all-gathers them GPU to GPU; otherwise they
+        go to the local ``samples`` container as in ``Sampler.run``."""
+        import torch.distributed as dist
+        if resident is None:
+            resident = dist.is_initialized() and dist.get_backend(self.group) == "nccl"
         occ = None
         if initial_occupancies is not None:
-            occ = np.asarray(initial_occupancies)[self.start:self.start + self.count]
-        self.local.run(nsteps, occ, thin_by=thin_by, **kw)
+            occ = initial_occupancies[self.start:self.start + self.count]
+        if resident:
+            self._resident = self.local.run_device(nsteps, occ, thin_by=thin_by)
+        else:
+            self._resident = None
+            self.local.run(nsteps, occ if occ is None else np.asarray(occ), thin_by=thin_by, **kw)
 
     def gather(self, name, device=None):
-        """Global ``[S, W, ...]`` trace ``name`` on every rank."""
+        """Global ``[S, W, ...]`` trace ``name`` on every rank (a CUDA tensor after a resident run: device
+        buffers -> NCCL -> device, nothing passes through the host; ``occupancy`` then holds int8 codes)."""
         import torch
+        res = getattr(self, "_resident", None)
+        if res is not None:
+            t = res[name]
+            if name in ("enthalpy", "accepted", "bias", "mod_factor"):
+                t = t[:, :, None]                   # the reference's trailing axis (trace.py)
+            return gather_walker_axis(t, self.nwalkers, self.group, axis=1)
         arr = self.local.samples.get_trace_value(name, flat=False)
         t = torch.from_numpy(np.ascontiguousarray(arr))
         if device is not None:

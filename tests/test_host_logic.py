@@ -402,3 +402,46 @@ def test_ensemble_mu_table_matches_reference_python_ensemble():
     assert ens.num_energy_coefs == int(gold["ens_num_energy_coefs"][0]) and ens.natural_parameters[-1] == -1.0
     ens.chemical_potentials = None                     # ChemicalPotentialManager.__delete__ (ensemble.py:72-84)
     assert len(ens.natural_parameters) == ens.num_energy_coefs and ens.mu_table is None
+
+
+def test_engine_limits_fail_loudly_without_a_device():
+    """Limits the reference does not have.  The ones the Python table builder or the argument
+    checks of ``lmc_model_create`` see are raised before any CUDA call, with a message naming the limit; the ones
+    that need the device tables (strides > 255, codes >= 8 after splitting) are in tests/test_gpu_api.py."""
+    import ctypes as C
+    import smol_b200 as S
+    from smol_b200.model import PackedModel
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 2
+    proc = S.ClusterDecompositionProcessor(sub, scm, L.cluster_interaction_tensors(sub, M.fcc_coefs(sub)))
+    lib = capi.load()
+
+    def create(mutate):
+        pm = PackedModel(proc.num_sites, proc.coefs, proc.get_sublattices(), **proc._tables())
+        mutate(pm.desc)
+        handle = C.c_void_p()
+        rc = lib.lmc_model_create(C.byref(pm.desc), C.byref(handle))
+        return rc, lib.lmc_last_error().decode()
+
+    rc, msg = create(lambda d: setattr(d, "num_sites", 70000))
+    assert rc < 0 and "65535" in msg                                       # u16 site indices
+    rc, msg = create(lambda d: setattr(d, "num_sublattices", 9))
+    assert rc < 0 and "sublattices" in msg
+    rc, msg = create(lambda d: setattr(d, "tf_num_dims", 17))
+    assert rc < 0 and "flip table" in msg
+    rc, msg = create(lambda d: setattr(d, "abi_version", 1))
+    assert rc < 0 and "ABI" in msg
+    # Python side: clusters of more than four sites, more than eight species codes
+    big = L.ClusterSubspace.from_cutoffs(L.fcc_prim(), {2: 3.0, 5: 3.0})
+    if any(o.num_sites > 4 for o in big.orbits):
+        with pytest.raises(ValueError, match="more than 4 sites"):
+            p5 = S.ClusterExpansionProcessor(big, scm, np.zeros(big.num_corr_functions))
+            PackedModel(p5.num_sites, p5.coefs, p5.get_sublattices(), **p5._tables())
+    nine = L.ClusterSubspace.from_cutoffs(L.fcc_prim(species=tuple("A%d" % i for i in range(9))), {2: 3.0})
+    p9 = S.ClusterExpansionProcessor(nine, scm, np.zeros(nine.num_corr_functions))
+    with pytest.raises(ValueError, match="species codes"):
+        PackedModel(p9.num_sites, p9.coefs, p9.get_sublattices(), **p9._tables())
+    # more than four changed sites per step
+    from smol_b200.sampler import table_flip_tables
+    with pytest.raises(ValueError, match="more than 4 sites"):
+        table_flip_tables(proc.get_sublattices(), [[-5, 5]])
