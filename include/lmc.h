@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 13
+#define LMC_ABI_VERSION 14
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -264,6 +264,13 @@ int lmc_cast_i8_to_i32(const int8_t* src_dev, int32_t* dst_dev, int64_t num_rows
 /* features_dev [W][F] <- full evaluation of every walker's occupancy; enthalpy_dev [W] may be NULL */
 int lmc_full_features(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* features_dev,
                       double* enthalpy_dev, void* stream);
+
+/* The same with the Ewald term evaluated through the walkers' potential: field_dev [W][N] (scratch owned by the caller) is
+ * filled as by lmc_ewald_field and the Ewald feature follows as sum_k q_k field[k] + sum_k M[e_k, e_k] -- O(W N^2) as one
+ * tiled product instead of a pair sum per walker; on return field_dev IS the potential cache of the occupancies.
+ * field_dev == NULL or a matrix that does not factorise (lmc_model_info): plain lmc_full_features. */
+int lmc_full_features_field(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* features_dev,
+                            double* enthalpy_dev, double* field_dev, void* stream);
 
 /* field_dev [W][N] <- Ewald potential cache of every walker's occupancy (see LmcRunConfig.ewald_field_dev) */
 int lmc_ewald_field(const LmcModel* model, const int8_t* occ_dev, int num_walkers, double* field_dev, void* stream);

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 13
+LMC_ABI_VERSION = 14
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -117,7 +117,7 @@ EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
     "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host", "lmc_model_info",
-    "lmc_ewald_field", "lmc_bias_init", "lmc_ewald_site_kernel", "lmc_distance_init",
+    "lmc_ewald_field", "lmc_bias_init", "lmc_ewald_site_kernel", "lmc_distance_init", "lmc_full_features_field",
 )
 
 _LIB = None
@@ -152,6 +152,7 @@ def load():
     lib.lmc_run.argtypes = [_P, C.POINTER(LmcRunConfig), _P]
     lib.lmc_model_info.argtypes = [_P, C.POINTER(C.c_int32), C.c_int]
     lib.lmc_ewald_field.argtypes = [_P, _P, C.c_int, _P, _P]
+    lib.lmc_full_features_field.argtypes = [_P, _P, C.c_int, _P, _P, _P, _P]
     lib.lmc_bias_init.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P, _P]
     lib.lmc_ewald_site_kernel.argtypes = [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_double,
                                           C.c_double, C.c_double, _P, _P]

@@ -34,6 +34,8 @@ def _deps(src):
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     if "lmc_spec_inst" not in src:
         hdrs = [h for h in hdrs if not h.endswith("lmc_spec.cuh")]
+    if "lmc_wl_inst" not in src:
+        hdrs = [h for h in hdrs if not h.endswith("lmc_wl.cuh")]
     return [src, os.path.join(HERE, "..", "include", "lmc.h"), *hdrs]
 
 
@@ -59,6 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             jobs.append((os.path.join(CSRC, "lmc_run_inst.cu"),
                          os.path.join(objdir, f"lmc_run_g{g}_wl{wl}.o"), [f"-DLMC_G={g}", f"-DLMC_WL={wl}"], force))
     jobs.append((os.path.join(CSRC, "lmc_run_dist_inst.cu"), os.path.join(objdir, "lmc_run_dist.o"), [], force))
+    jobs.append((os.path.join(CSRC, "lmc_wl_inst.cu"), os.path.join(objdir, "lmc_wl.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst.cu"), os.path.join(objdir, "lmc_spec.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst2.cu"), os.path.join(objdir, "lmc_spec2.o"), [], force))
     log = []

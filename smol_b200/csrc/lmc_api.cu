@@ -132,6 +132,11 @@ struct SpecTables {
   int ok = 0, NC = 0, L = 0, NQ = 0, nblocks = 0, merged = 0;
   std::vector<double> dtab;          // [NC][L]
   std::vector<unsigned char> rec;    // [N][NQ] x uint2 (s0 | s1<<16, s2 | tbase<<16)
+  // per-feature form of the same table for cluster-decomposition models (one feature per orbit):
+  // ftab[(new * L + entry) * F + f] = sum over the record's clusters of orbit f of w_f (T[after] - T[before]);
+  // an accepted flip's feature change is the sum of its records' rows (lmc_wl.cuh: bookkeeping warp)
+  std::vector<double> ftab;          // [NC][L][F], empty when not built
+  int F = 0;
 };
 
 static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& orbs, const std::vector<double>& tabA,
@@ -164,6 +169,19 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
     if (ii >= o.T || ff >= o.T || newc == oldc) return 0.0;
     return coef * (tabA[o.atab_off + ff] - tabA[o.atab_off + ii]);
   };
+  // the same contribution as a feature change: (feature index, w_orbit (T[after] - T[before])); cluster-decomposition
+  // models only (kone: the phase-A table IS the orbit's interaction tensor)
+  const int F = d->num_features;
+  const bool want_f = kone && F <= 32 && !getenv("LMC_SPEC_FTAB_OFF");
+  auto term_f = [&](int c, const int* oc, int oldc, int newc, int& fidx) -> double {
+    const OrbDev& o = orbs[d->cls_orbit[c]];
+    const int* st = d->cls_stride + c * 4;
+    fidx = o.fidx;
+    long ii = (long)st[3] * oldc, ff = (long)st[3] * newc;
+    for (int i = 0; i < 3 && st[i] > 0; ++i) { ii += (long)st[i] * oc[i]; ff += (long)st[i] * oc[i]; }
+    if (ii >= o.T || ff >= o.T || newc == oldc) return 0.0;
+    return o.w * (tabA[o.atab_off + ff] - tabA[o.atab_off + ii]);
+  };
   // a merged record: up to three gathered sites and the cluster terms folded into its table block;
   // slot[i] = which gathered site feeds the i-th other site of the term's cluster
   struct Term { int cls; int slot[3]; };
@@ -179,10 +197,12 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
   for (int level = max_level; level >= 1 && !sp.ok; --level) {
     // deduplicated [new][entry] blocks; block 0 = zeros (padding records)
     std::vector<std::vector<double>> store;
+    std::vector<std::vector<double>> store_f;   // feature rows of the blocks ([new][entry][F]), want_f only
     std::vector<long> store_base;
     std::map<std::vector<int>, int> keys;   // (ns, cls, slots ...) -> store index
     long L = (long)NC * NC * NC * NC;
     store.emplace_back((size_t)L * NC, 0.0);
+    store_f.emplace_back(want_f ? (size_t)L * NC * F : 0, 0.0);
     store_base.push_back(0);
     auto block_of = [&](MRec& r) -> int {
       std::sort(r.terms.begin(), r.terms.end(), [](const Term& a, const Term& b) {
@@ -198,6 +218,7 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
       for (int i = 0; i < r.ns; ++i) combos *= NC;
       const long len = combos * NC;
       std::vector<double> blk((size_t)len * NC, 0.0);
+      std::vector<double> blkf(want_f ? (size_t)len * NC * F : 0, 0.0);
       for (long q = 0; q < combos; ++q) {
         const int code[3] = {(int)(q % NC), (int)((q / NC) % NC), (int)(q / ((long)NC * NC))};
         for (int oldc = 0; oldc < NC; ++oldc)
@@ -206,15 +227,22 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
             for (const Term& t : r.terms) {
               const int oc[3] = {code[t.slot[0]], code[t.slot[1]], code[t.slot[2]]};
               v += term(t.cls, oc, oldc, newc);
+              if (want_f) {
+                int fi = 0;
+                const double vf = term_f(t.cls, oc, oldc, newc, fi);
+                blkf[((size_t)newc * len + oldc + NC * q) * F + fi] += vf;
+              }
             }
             blk[(size_t)newc * len + oldc + NC * q] = v;
           }
       }
       int idx = -1;
       for (size_t b = 1; b < store.size() && idx < 0; ++b)
-        if (store[b].size() == blk.size() && memcmp(store[b].data(), blk.data(), blk.size() * 8) == 0) idx = (int)b;
+        if (store[b].size() == blk.size() && memcmp(store[b].data(), blk.data(), blk.size() * 8) == 0 &&
+            (!want_f || memcmp(store_f[b].data(), blkf.data(), blkf.size() * 8) == 0)) idx = (int)b;
       if (idx < 0) {
         store.push_back(std::move(blk));
+        store_f.push_back(std::move(blkf));
         store_base.push_back(L);
         L += len;
         idx = (int)store.size() - 1;
@@ -330,6 +358,15 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
       const size_t len = store[b].size() / NC;
       for (int newc = 0; newc < NC; ++newc)
         memcpy(&sp.dtab[(size_t)newc * L + store_base[b]], &store[b][(size_t)newc * len], len * 8);
+    }
+    if (want_f && (size_t)L * NC * F * 8 <= (size_t(64) << 20)) {
+      sp.ftab.assign((size_t)L * NC * F, 0.0);
+      sp.F = F;
+      for (size_t b = 0; b < store.size(); ++b) {
+        const size_t len = store[b].size() / NC;
+        for (int newc = 0; newc < NC; ++newc)
+          memcpy(&sp.ftab[((size_t)newc * L + store_base[b]) * F], &store_f[b][(size_t)newc * len * F], len * F * 8);
+      }
     }
     sp.rec = std::move(rec);
     sp.ok = 1; sp.NC = NC; sp.L = (int)L; sp.NQ = NQ; sp.nblocks = (int)store.size(); sp.merged = level - 1;
@@ -532,6 +569,8 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     if (!dtab.empty()) memcpy(blob.data() + m.off_dtab, dtab.data(), dtab.size() * 8);
     UP(unsigned char, blob.data(), blob.size(), m.blob);
     if (m.spOK) UP(unsigned char, sprec.data(), sprec.size(), m.sp_rec);
+    m.spFtab = nullptr;
+    if (m.spOK && !sp.ftab.empty()) UP(double, sp.ftab.data(), sp.ftab.size(), m.spFtab);
   }
   UP(OrbDev, orbs.data(), orbs.size(), mdl->orb_dev);
   UP(double, d->natural_parameters, m.F, mdl->nat_dev);
@@ -670,9 +709,34 @@ extern "C" int lmc_ewald_field(const LmcModel* mdl, const int8_t* occ, int W, do
   const DevModel& m = mdl->dm;
   if (m.E <= 0 || !m.ewK) return fail("the Ewald potential cache needs an Ewald matrix of the form q_i q_j K[site_i, site_j]");
   const size_t smem = (size_t)FIELD_WPB * m.N * sizeof(double);
-  if ((int)smem > mdl->smem_optin) return fail("too many sites for the Ewald potential cache kernel");
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(lmc_ewald_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lmc_ewald_field_kernel<<<(W + FIELD_WPB - 1) / FIELD_WPB, 256, smem, (cudaStream_t)stream>>>(m, occ, W, field);
+  // many walkers: the tiled product (every element of K read W / 128 times); few walkers or LMC_FIELD_TILED=0: one
+  // warp per row of K, four walkers per block
+  bool tiled = W >= 64;
+  if (const char* e = getenv("LMC_FIELD_TILED")) tiled = atoi(e) != 0;
+  if (tiled) {
+    dim3 grid((m.N + FT_S - 1) / FT_S, (W + FT_W - 1) / FT_W);
+    lmc_ewald_field_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m, occ, W, field);
+  } else {
+    if ((int)smem > mdl->smem_optin) return fail("too many sites for the Ewald potential cache kernel");
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(lmc_ewald_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lmc_ewald_field_kernel<<<(W + FIELD_WPB - 1) / FIELD_WPB, 256, smem, (cudaStream_t)stream>>>(m, occ, W, field);
+  }
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lmc_full_features_field(const LmcModel* mdl, const int8_t* occ, int W, double* feat, double* enth,
+                                       double* field, void* stream) {
+  if (!mdl) return fail("null model");
+  if (W <= 0) return 0;
+  const DevModel& m = mdl->dm;
+  if (!field || m.E <= 0 || !m.ewK) return lmc_full_features(mdl, occ, W, feat, enth, stream);
+  const int rc = lmc_ewald_field(mdl, occ, W, field, stream);
+  if (rc != 0) return rc;
+  const size_t smem = (size_t)m.Npad + (size_t)m.N * 4 + 16;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(lmc_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lmc_full_kernel<<<W, 256, smem, (cudaStream_t)stream>>>(m, occ, feat, enth, mdl->orb_dev, mdl->nat_dev, field);
   g_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -743,7 +807,7 @@ extern "C" int lmc_full_features(const LmcModel* mdl, const int8_t* occ, int W, 
   const DevModel& m = mdl->dm;
   const size_t smem = (size_t)m.Npad + (m.E ? (size_t)m.N * 4 : 0) + 16;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(lmc_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lmc_full_kernel<<<W, 256, smem, (cudaStream_t)stream>>>(m, occ, feat, enth, mdl->orb_dev, mdl->nat_dev);
+  lmc_full_kernel<<<W, 256, smem, (cudaStream_t)stream>>>(m, occ, feat, enth, mdl->orb_dev, mdl->nat_dev, nullptr);
   g_launches++;
   CK(cudaGetLastError());
   return 0;
@@ -968,6 +1032,37 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     threads -= 32;
   }
   if ((int)smem > mdl->smem_optin - 1024) return fail("model + walker state do not fit in shared memory");
+  // Wang-Landau flips with few walkers: the warp-specialised kernel (decision warps + a bookkeeping warp per walker,
+  // lmc_wl.cuh) while every walker is resident at seven blocks per SM; LMC_WL2 = 0 classic, 1 one decision warp,
+  // 3 depth-2 speculation
+  if (c->kernel == LMC_KERNEL_WANGLANDAU && c->usher == LMC_USHER_FLIP && !dist && !ewald && a.off_wl >= 0 && !multicell &&
+      c->group_size == 0 && c->block_threads == 0 && !getenv("LMC_GROUP_SIZE") && c->num_walkers <= 7 * mdl->num_sms) {
+    int ne = 4;     // 4: merged-record variant where the model has the tables, else one decision warp over classic records
+    if (const char* e = getenv("LMC_WL2")) ne = atoi(e);
+    if (ne == 4) {
+      const size_t sm3 = m.spOK && m.spFtab && m.kone ? wl3_smem_bytes(m, c->wl.num_bins) : 0;
+      if (sm3 && m.spNQ % 8 == 0 && 7 * (sm3 + 1024) <= 227 * 1024 && (int)sm3 <= mdl->smem_optin - 1024) {
+        a.wpb = 1;
+        LaunchCfg lc3{a.W, 96, sm3, (cudaStream_t)stream};
+        const int rc3 = launch_wl3(m, a, lc3);
+        g_launches++;
+        if (rc3 != 0) return fail(std::string("launch failed: ") + cudaGetErrorString((cudaError_t)rc3));
+        return 0;
+      }
+      ne = 1;
+    }
+    if (ne == 1 || ne == 3) {
+      const size_t sm2 = wl2_smem_bytes(m, c->wl.num_bins, ne);
+      if (7 * (sm2 + 1024) <= 227 * 1024 && (int)sm2 <= mdl->smem_optin - 1024) {
+        a.wpb = 1;
+        LaunchCfg lc2{a.W, 32 * (ne + 1), sm2, (cudaStream_t)stream};
+        const int rc2 = launch_wl2(m, a, m.kone != 0, ne, lc2);
+        g_launches++;
+        if (rc2 != 0) return fail(std::string("launch failed: ") + cudaGetErrorString((cudaError_t)rc2));
+        return 0;
+      }
+    }
+  }
   const int grid = (a.W + a.wpb - 1) / a.wpb;
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};
   int rc = -2;

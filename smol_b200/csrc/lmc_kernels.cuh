@@ -162,6 +162,50 @@ __device__ __forceinline__ double flip_energy(const DevModel& m, const SmemTable
   return acc;
 }
 
+// the same against the occupancy with site `ps` reading as code `pc` (an earlier flip applied in this warp's view
+// only: lmc_wl.cuh evaluates step t+1 "given t accepted" without writing the shared row)
+template <bool KONE>
+__device__ __forceinline__ void eval_record_patched(const SmemTables& t, const uint8_t* occ, const uint2 rec, uint32_t oldsh,
+                                                    uint32_t xmask, void* stash, int r, double& acc, uint32_t ps, uint32_t pc) {
+  const uint4 ci = t.cls[rec.y >> 16];
+  const uint32_t s0 = rec.x & 0xffffu, s1 = rec.x >> 16, s2 = rec.y & 0xffffu;
+  const uint32_t o0 = occ[s0], o1 = occ[s1], o2 = occ[s2];
+  const uint32_t o = (s0 == ps ? pc : o0) | ((s1 == ps ? pc : o1) << 8) | ((s2 == ps ? pc : o2) << 16) | oldsh;
+  const uint32_t ii = __dp4a(o, ci.x, ci.y);
+  const uint32_t ff = __dp4a(o ^ xmask, ci.x, ci.y);
+  const double d = t.tabA[ff] - t.tabA[ii];
+  if (KONE) {
+    acc += __hiloint2double((int)ci.w, (int)ci.z) * d;
+    reinterpret_cast<double*>(stash)[r] = d;
+  } else {
+    acc += d;
+    reinterpret_cast<uint32_t*>(stash)[r] = (ff - ci.y) | ((ii - ci.y) << 16);
+  }
+}
+template <int G, bool KONE>
+__device__ __forceinline__ double flip_energy_patched(const DevModel& m, const SmemTables& t, const uint8_t* occ, int site,
+                                                      int olda, int newb, void* stash, int g, const RecChunk& pre,
+                                                      uint32_t ps, uint32_t pc) {
+  const uint32_t oldsh = (uint32_t)olda << 24;
+  const uint32_t xmask = (uint32_t)(olda ^ newb) << 24;
+  const int nper = m.Rstride / G;
+  double acc = 0.0;
+  const uint2* rp = m.site_rec + (size_t)site * m.Rstride;
+  for (int base = 0; base < nper; base += 4) {
+    uint2 rec[4];
+    if (base == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rec[u] = pre.r[u];
+    } else {
+      load_chunk<G>(m, rp, g + base * G, rec);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (base + u < nper) eval_record_patched<KONE>(t, occ, rec[u], oldsh, xmask, stash, g + (base + u) * G, acc, ps, pc);
+  }
+  return acc;
+}
+
 // energy change of a two-flip step (swap).  The caller has already written flip a's new code to
 // the occupancy: flip a's records never contain its own site, flip b's records must see flip a
 // applied (sequential semantics of expansion.py:217-229), so both can be evaluated interleaved.
@@ -1422,7 +1466,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 __global__ void lmc_full_kernel(const DevModel m, const int8_t* __restrict__ occ_g, double* __restrict__ features,
                                 double* __restrict__ enthalpy, const OrbDev* __restrict__ orbs,
-                                const double* __restrict__ nat) {
+                                const double* __restrict__ nat, const double* __restrict__ field) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double red[32];
   uint8_t* occ = smem;
@@ -1455,7 +1499,15 @@ __global__ void lmc_full_kernel(const DevModel m, const int8_t* __restrict__ occ
     for (int i = threadIdx.x; i < m.N; i += blockDim.x) eidx[i] = m.ewInds[i * m.ewW + occ[i]];
     __syncthreads();
     double p = 0.0;
-    const long long np = (long long)m.N * m.N;
+    const long long np = field ? 0ll : (long long)m.N * m.N;
+    if (field) {
+      // factorised matrix with the walker's potential fld[k] = sum_j q_j K[k][j] at hand (lmc_ewald_field_kernel):
+      // sum over occupied pairs = sum_k q_k fld[k] + sum_k M[e_k, e_k]   -- O(N) instead of O(N^2)
+      for (int k = threadIdx.x; k < m.N; k += blockDim.x) {
+        const double2 qd = __ldg(m.ewQD + k * m.ewW + occ[k]);
+        p += qd.x * field[(size_t)w * m.N + k] + qd.y;
+      }
+    }
     for (long long q = threadIdx.x; q < np; q += blockDim.x) {
       const int i = (int)(q / m.N), j = (int)(q % m.N);
       const int a = eidx[i], b = eidx[j];
@@ -1512,6 +1564,82 @@ __global__ void lmc_ewald_field_kernel(const DevModel m, const int8_t* __restric
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && w0 + ww < W) field[(size_t)(w0 + ww) * m.N + s] = v;
+    }
+  }
+}
+
+// The same as a tiled matrix product field[W][N] = Q[W][N] x K[N][N] (Q = charges of the walkers' species; K is
+// symmetric): a block owns 128 walkers x 64 sites, a thread 8 x 4 of them; k runs in chunks of 16 staged through
+// shared memory (charges looked up on the way in, rows of K coalesced), the next chunk's global loads in flight
+// during the current chunk's FMAs.  Every element of K is read W / 128 times from L2 instead of W / 4 times.
+constexpr int FT_W = 128, FT_S = 64, FT_K = 16;
+__global__ void __launch_bounds__(256) lmc_ewald_field_tiled_kernel(const DevModel m, const int8_t* __restrict__ occ_g, int W,
+                                                                    double* __restrict__ field) {
+  __shared__ __align__(16) double Qs[FT_K][FT_W];
+  __shared__ __align__(16) double Ks[FT_K][FT_S];
+  const int tid = threadIdx.x;
+  const int s0 = blockIdx.x * FT_S, w0 = blockIdx.y * FT_W;
+  const int ty = tid >> 4, tx = tid & 15;          // walkers ty*8.., sites tx*4..
+  // loaders: Q chunk = 16 k x 128 walkers = 2048 charges, 8 per thread (walker = tid >> 1, k = (tid & 1) * 8 ..);
+  // K chunk = 16 k x 64 sites = 1024 doubles, 4 per thread (k = tid >> 4, sites (tid & 15) * 4 ..)
+  const int qw = tid >> 1, qk = (tid & 1) * 8;
+  const int kk = tid >> 4, ks = (tid & 15) * 4;
+  double acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  double qreg[8], kreg[4];
+  auto load_chunk_regs = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + qk + u, ww = w0 + qw;
+      double q = 0.0;
+      if (k < m.N && ww < W) q = __ldg(m.ewQD + k * m.ewW + occ_g[(size_t)ww * m.Npad + k]).x;
+      qreg[u] = q;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + kk, sidx = s0 + ks + u;
+      kreg[u] = (k < m.N && sidx < m.N) ? __ldg(m.ewK + (size_t)k * m.N + sidx) : 0.0;
+    }
+  };
+  load_chunk_regs(0);
+  for (int k0 = 0; k0 < m.N; k0 += FT_K) {
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Qs[qk + u][qw] = qreg[u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Ks[kk][ks + u] = kreg[u];
+    __syncthreads();
+    if (k0 + FT_K < m.N) load_chunk_regs(k0 + FT_K);
+#pragma unroll
+    for (int k = 0; k < FT_K; ++k) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(&Qs[k][ty * 8 + i]);
+        a[i] = v.x; a[i + 1] = v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(&Ks[k][tx * 4 + j]);
+        b[j] = v.x; b[j + 1] = v.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ww = w0 + ty * 8 + i;
+    if (ww >= W) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sidx = s0 + tx * 4 + j;
+      if (sidx < m.N) field[(size_t)ww * m.N + sidx] = acc[i][j];
     }
   }
 }

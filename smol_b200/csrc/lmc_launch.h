@@ -27,4 +27,9 @@ int launch_run_wl_g4(const DevModel& m, const RunArgs& a, bool kone, int ewald, 
 int launch_run_wl_g8(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
 int launch_run_wl_g16(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
 int launch_run_wl_g32(const DevModel& m, const RunArgs& a, bool kone, int ewald, int usher, const LaunchCfg& lc);
+// warp-specialised Wang-Landau flip kernel (lmc_wl.cuh): one walker per block, ne decision warps + one bookkeeping warp
+int launch_wl2(const DevModel& m, const RunArgs& a, bool kone, int ne, const LaunchCfg& lc);
+size_t wl2_smem_bytes(const DevModel& m, int num_bins, int ne);
+int launch_wl3(const DevModel& m, const RunArgs& a, const LaunchCfg& lc);
+size_t wl3_smem_bytes(const DevModel& m, int num_bins);
 }  // namespace lmc

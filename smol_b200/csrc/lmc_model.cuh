@@ -78,6 +78,7 @@ struct DevModel {
   int spSb;                // bytes per site of sp_rec (8 spNQ)
   int off_dtab;            // offset of the difference table [spNC][spL] in the blob
   const unsigned char* sp_rec;  // [N][spNQ] x uint2 (s0 | s1<<16, s2 | tbase<<16)
+  const double* spFtab;    // [spNC][spL][F] per-feature form of the difference table (cluster decomposition), or nullptr
 };
 
 struct RunArgs {

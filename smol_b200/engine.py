@@ -156,11 +156,25 @@ class LmcEngine:
         return out
 
     @_on_device
-    def full_features(self, occ_dev):
+    def full_features(self, occ_dev, field=None):
+        """Full evaluation of every walker's occupancy.  With a factorising Ewald matrix the Ewald term goes
+        through the walkers' potential (one tiled product instead of a pair sum per walker): ``field`` (``[W, N]``
+        float64, allocated and cached here when not given) is filled on the way and IS the potential cache of
+        these occupancies afterwards (``self.last_field``)."""
         torch = _torch()
         W = occ_dev.shape[0]
         feat = torch.empty((W, self.F), dtype=torch.float64, device=self.device)
         enth = torch.empty((W,), dtype=torch.float64, device=self.device)
+        self.last_field = None
+        if self.model_info()[0]:
+            if field is None:
+                field = getattr(self, "_field_scratch", None)
+                if field is None or field.shape[0] != W:
+                    field = self._field_scratch = torch.empty((W, self.N), dtype=torch.float64, device=self.device)
+            capi.check(self.lib.lmc_full_features_field(self.handle, occ_dev.data_ptr(), W, feat.data_ptr(),
+                                                        enth.data_ptr(), field.data_ptr(), self._stream()))
+            self.last_field = field
+            return feat, enth
         capi.check(self.lib.lmc_full_features(self.handle, occ_dev.data_ptr(), W, feat.data_ptr(),
                                               enth.data_ptr(), self._stream()))
         return feat, enth
@@ -177,9 +191,11 @@ class LmcEngine:
 
     def model_info(self):
         """(Ewald matrix factorises, speculative tables built, table blob bytes, speculative records per site)"""
-        info = (C.c_int32 * 4)()
-        capi.check(self.lib.lmc_model_info(self.handle, info, 4))
-        return tuple(int(x) for x in info)
+        if getattr(self, "_info", None) is None:
+            info = (C.c_int32 * 4)()
+            capi.check(self.lib.lmc_model_info(self.handle, info, 4))
+            self._info = tuple(int(x) for x in info)
+        return self._info
 
     @_on_device
     def ewald_field(self, occ_dev, out=None):

@@ -428,16 +428,18 @@ class Sampler:
         ctx = SimpleNamespace(thin_by=thin_by)
         # initial trace: full evaluation of the starting occupancies (base.py:345-365,
         # wanglandau.py:290-300)
-        ctx.feat, ctx.enth = eng.full_features(self._occ_dev)
         # Ewald potential cache: rebuilt from the occupancies at every run (bounds its rounding drift to one
-        # run), kept current by the kernels in between
+        # run), kept current by the kernels in between.  With a factorising Ewald matrix the full evaluation
+        # computes it anyway (Ewald energy = sum_k q_k field[k] + diagonal terms).
         ctx.use_field = False
         if self.ewald_field is not False and eng.model_info()[0]:
             ctx.use_field = self.ewald_field is True or self._acc_est is None or self._acc_est < 0.25
         elif self.ewald_field is True:
             raise RuntimeError("ewald_field=True needs an Ewald term whose matrix factorises as q_i q_j K[site_i, site_j]")
-        if ctx.use_field:
-            self._ew_field = eng.ewald_field(self._occ_dev, out=self._ew_field)
+        self.ewald_cache_in_use = ctx.use_field     # (the field buffer doubles as scratch of the full evaluation)
+        if eng.model_info()[0] and (self._ew_field is None or self._ew_field.shape[0] != self.nwalkers):
+            self._ew_field = torch.empty((self.nwalkers, eng.N), dtype=torch.float64, device=dev)
+        ctx.feat, ctx.enth = eng.full_features(self._occ_dev, field=self._ew_field if eng.model_info()[0] else None)
         from .processor import DistanceProcessor
         ctx.dist_proc = self.ensemble.processor if isinstance(self.ensemble.processor, DistanceProcessor) else None
         ctx.dist_vec = None

@@ -199,7 +199,7 @@ def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
     seeds = np.arange(7, 7 + W)
     smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 300, 10, occ0, seeds, T=1500.0, usher_kwargs=kw)
     _compare_traces(smp, ref)
-    assert (smp._ew_field is not None) == (factorize in ("1", "spec", "spec-wide"))
+    assert smp.ewald_cache_in_use == (factorize in ("1", "spec", "spec-wide"))
     # a second run continues the chains (potential cache rebuilt from the occupancies, then kept current)
     smp.run(100, thin_by=10)
     assert smp.samples.num_samples == 40
@@ -264,15 +264,19 @@ def test_canonical_ewald_swap_trajectory(cuda_device, mode):
     smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, 520, 13, occ0, seeds, T=2500.0,
                             usher_kwargs=dict(spec_mode=2 if mode == "spec" else 1))
     _compare_traces(smp, ref)
-    assert smp._ew_field is not None and 0 < smp.samples.step_efficiency() < 1
+    assert smp.ewald_cache_in_use and 0 < smp.samples.step_efficiency() < 1
 
 
-@pytest.mark.parametrize("wl_arrays", ["smem", "global"])
+@pytest.mark.parametrize("wl_arrays", ["smem", "global", "pipeline", "speculative", "merged"])
 def test_wang_landau_flip_trajectory(cuda_device, wl_arrays, monkeypatch):
-    """smem: the walker's entropy / histogram live in shared memory during a launch (the default while they
-    fit); global: kept in HBM / L2 (LMC_WL_GLOBAL, the path of very fine windows)"""
+    """smem: classic kernel, the walker's entropy / histogram in shared memory during a launch; global: kept in
+    HBM / L2 (LMC_WL_GLOBAL, the path of very fine windows); pipeline / speculative: the warp-specialised kernel
+    of lmc_wl.cuh with one decision warp or three (depth-2 speculation) over the classic records; merged: its
+    merged-record form (one decision warp evaluates the three candidates of the speculation, features from the
+    per-feature difference table: the default for few walkers)"""
     if wl_arrays == "global":
         monkeypatch.setenv("LMC_WL_GLOBAL", "1")
+    monkeypatch.setenv("LMC_WL2", {"pipeline": "1", "speculative": "3", "merged": "4"}.get(wl_arrays, "0"))
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()

@@ -95,7 +95,8 @@ def test_config3_semigrand_ewald_full_size(cuda_device):
         np.testing.assert_allclose(out["features"][:, 0], feats[:, w], rtol=RTOL, atol=RTOL * scale)
 
 
-def test_config4_wang_landau_full_size(cuda_device):
+@pytest.mark.parametrize("kernel", ["classic", "warp-specialised"])
+def test_config4_wang_landau_full_size(cuda_device, kernel, monkeypatch):
     """binary FCC 8x8x8 Wang-Landau (AFM Ising coefficients of the wang-landau notebook), 1024 independent
     walkers: walkers checked bit-exact against the C oracle incl. their entropy / histogram; ALL walkers:
     occurrences count every step inside the window, histogram <= occurrences, enthalpy == full re-evaluation,
@@ -103,6 +104,10 @@ def test_config4_wang_landau_full_size(cuda_device):
     import smol_b200 as S
     from oracle import lmc_oracle as O
     from smol_b200 import lattice as L
+    if kernel == "classic":
+        monkeypatch.setenv("LMC_WL2", "0")
+    else:
+        monkeypatch.delenv("LMC_WL2", raising=False)      # default: lmc_wl.cuh (1024 walkers: all resident)
     sub = M.fcc_subspace()
     scm = np.eye(3, dtype=int) * 8
     coefs = np.zeros(sub.num_corr_functions)
