@@ -334,14 +334,57 @@ def run_ours(args):
             wl_state = {"bins": int(len(st["levels"])), "min_mod_factor": float(st["mod_factor"].min()),
                         "max_mod_factor": float(st["mod_factor"].max()),
                         "visited_bins_mean": float((st["entropy"] > 0).sum(1).mean())}
+        cache = bool(getattr(smp, "ewald_cache_in_use", False))
         del smp, flush
         torch.cuda.empty_cache()
         return dict(W=W, dev_ms=float(t[0]), e2e_s=float(t[1]), launches=launches, acc=acc, clk=clk, extra=extra,
-                    e2e=e2e, steps=steps, wl=wl_state)
+                    e2e=e2e, steps=steps, wl=wl_state, cache=cache)
 
     W = args.walkers or wk.walkers_per_gpu
     setup_s = time.perf_counter() - t_setup
     main_res = one_size(W, args.steps, True)
+    # the rate is a property of the acceptance ratio (rejected steps cost less than accepted ones): the same
+    # workload at other temperatures, device-resident, equilibrated for a few launches each (Metropolis configs)
+    curve = None
+    if args.curve and wk.kernel == "Metropolis" and world == 1:
+        curve = []
+        for mult in args.curve_temperatures:
+            T = wk.temperature * mult
+            smp = wk.sampler(ens, W, list(range(W)))
+            smp._temperature[:] = T
+            out = smp.run_device(nsteps, wk.initial_occupancies(W, seed=7), thin_by=thin)
+            for _ in range(4):
+                smp.run_device(nsteps, None, thin_by=thin, out=out, reuse_state=True)
+            ms = 0.0
+            for _ in range(3):
+                smp.run_device(nsteps, None, thin_by=thin, out=out, reuse_state=True)
+                ms += smp.last_kernel_ms
+            acc = float(out["n_accepted"].sum().item()) / (out["n_accepted"].numel() * thin)
+            curve.append({"temperature_K": T, "acceptance_ratio": acc, "steps_per_s": 3 * W * nsteps / (ms * 1e-3)})
+            del smp, out
+            torch.cuda.empty_cache()
+    # a sustained region: the same launches back to back for >= args.sustain_seconds (no L2 flush in between)
+    sustained = None
+    if args.sustain_seconds > 0 and rank == 0 and world == 1:
+        smp = wk.sampler(ens, W, list(range(W)))
+        out = smp.run_device(nsteps, wk.initial_occupancies(W, seed=0), thin_by=thin)
+        for _ in range(3):
+            smp.run_device(nsteps, None, thin_by=thin, out=out, reuse_state=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_l, t0 = 0, time.perf_counter()
+        e0.record()
+        while time.perf_counter() - t0 < args.sustain_seconds:
+            for _ in range(8):
+                smp.run_device(nsteps, None, thin_by=thin, out=out, reuse_state=True)
+            n_l += 8
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        sms = e0.elapsed_time(e1)
+        sustained = {"seconds": sms / 1e3, "launches": n_l, "value": n_l * W * nsteps / (sms * 1e-3), "unit": "steps/s"}
+        del smp, out
+        torch.cuda.empty_cache()
     strong = None
     if args.config == 5 and not args.no_strong:
         # north star: 32768 walkers over the GPUs of the box (strong scaling), beside the weak line above
@@ -363,13 +406,13 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     per_gpu_rate = steps_per_launch * args.steps / (dev_ms * 1e-3)
-    built, built_note = wk.built_bytes(main_res["acc"])
+    built, built_note = wk.built_bytes(main_res["acc"], main_res["cache"])
     primary = wk.algorithmic_bytes if wk.roofline_uses_survey_bytes else built
     achieved = per_gpu_rate * primary / 1e9
     prof = _profile_summary(args.config)
     cpu_rate, cores, kind, sample = (None, 0, "skipped", "")
     port_rate = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # the CPU legs run beside the one-GPU line only
         cpu_rate, cores, kind, sample = cpu_arm(args.config, "reference", target_seconds=args.cpu_seconds)
         port_rate = cpu_arm(args.config, "port", target_seconds=min(6.0, args.cpu_seconds))[0]
     e2e_s, h2d, d2h, e2e_steps, check = main_res["e2e"]
@@ -382,7 +425,7 @@ def run_ours(args):
                    "attempted_steps_per_bench_step": steps_per_launch,
                    "sampling_intervals_per_bench_step": S_, "thin_by": thin, "l2_flush_between_iterations": True,
                    "parallelism": "walkers sharded, %d/GPU" % W, "acceptance_ratio": main_res["acc"],
-                   "model_setup_s": setup_s},
+                   "model_setup_s": setup_s, "ewald_potential_cache": main_res["cache"]},
         "e2e": {"value": world * steps_per_launch * e2e_steps / main_res["e2e_s"], "unit": "steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "smol_b200.Sampler.run(nsteps, initial_occupancies=<page-locked host int32>, thin_by, "
@@ -409,6 +452,10 @@ def run_ours(args):
                      "sample": "C restatement oracle/lmc_oracle.c, one process per core"},
     }
     out.update(main_res["extra"])
+    if curve:
+        out["config"]["acceptance_curve"] = curve
+    if sustained:
+        out["sustained"] = sustained
     if main_res["wl"]:
         out["config"]["wang_landau"] = main_res["wl"]
     if strong:
@@ -477,6 +524,12 @@ def main():
     ap.add_argument("--strong-walkers", type=int, default=32768, help="config 5: total walkers of the strong-scaling line")
     ap.add_argument("--no-strong", action="store_true", help="config 5: skip the strong-scaling line")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-curve", dest="curve", action="store_false",
+                    help="skip the acceptance curve (the workload at other temperatures; Metropolis configs, one GPU)")
+    ap.add_argument("--curve-temperatures", type=float, nargs="*", default=[2.0, 4.0, 8.0, 16.0],
+                    help="temperature multipliers of the acceptance curve")
+    ap.add_argument("--sustain-seconds", type=float, default=1.5,
+                    help="length of the additional back-to-back region (0 = off)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     args = ap.parse_args()

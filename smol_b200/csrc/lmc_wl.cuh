@@ -479,6 +479,35 @@ __host__ __device__ inline Wl3Layout wl3_layout(int F, int NQ, int nb) {
   return L;
 }
 
+// feature change of an accepted flip: sum of its records' rows of the per-feature table.  Lane = (row group, feature):
+// FP = features padded to a power of two, RG = 32 / FP groups; group rgp takes the contiguous rows [rgp, rgp + 1) * NQ / RG,
+// the groups' partial sums are combined in a fixed order.  `off` = the records' row offsets (entry * F) left by the
+// decision warp.
+template <int FP, int NQ8>
+__device__ __forceinline__ double wl3_dfeat(const double* __restrict__ bp, const uint32_t* __restrict__ off, int NQ, int g) {
+  constexpr int RG = 32 / FP;
+  const int rgp = g / FP;
+  double p = 0.0;
+  if (NQ8 > 0 && (NQ8 * 8) % RG == 0) {
+    constexpr int ROWS = NQ8 > 0 ? NQ8 * 8 / RG : 1;
+    const uint32_t* o = off + rgp * ROWS;
+    double v[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) v[k] = __ldg(bp + o[k]);
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) p += v[k];
+  } else {
+    const int rows = (NQ + RG - 1) / RG;
+    for (int k = 0; k < rows; ++k) {
+      const int r = rgp * rows + k;
+      p += r < NQ ? __ldg(bp + off[r]) : 0.0;
+    }
+  }
+#pragma unroll
+  for (int x = FP; x < 32; x <<= 1) p += __shfl_xor_sync(0xffffffffu, p, x);
+  return p;
+}
+
 // NQ8 = merged records per lane of a candidate (spNQ / 8), 0 = run-time loop.  Three warps: decision (0), features (1:
 // feature change of accepted flips, per-bin feature sums), Wang-Landau state (2: histogram, flatness check, sample
 // traces, random numbers and record prefetch of future steps).
@@ -524,7 +553,7 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
     // lane = (row group, feature): FP = features padded to a power of two, 32 / FP rows of the table in flight
     int FP = 8;
     while (FP < m.F) FP <<= 1;
-    const int f = g & (FP - 1), rgp = g / FP, RG = 32 / FP;
+    const int f = g & (FP - 1), rgp = g / FP;
     const bool fl = f < m.F;
     __syncthreads();                            // P0
     long long sidx = 0;
@@ -536,15 +565,15 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         if (i < n) {
-          const int flags = mb->st[i].flags, bin = mb->st[i].bin, src = mb->st[i].src;
+          const int2 mt = *reinterpret_cast<const int2*>(&mb->st[i].flags);
+          const int flags = mt.x & 3, bin = mt.x >> 2, src = mt.y;
           if (flags & 1) {
             // feature change of the accepted flip = sum of its records' rows of the per-feature table: row group rgp
             // takes rows rgp, rgp + RG, ...; the groups' partial sums are combined in a fixed order
-            const uint32_t* idx = stash_b + (src & 0xff) * NQ;
+            const uint32_t* off = stash_b + (src & 0xff) * NQ;
             const double* bp = m.spFtab + (size_t)(src >> 8) * m.spL * m.F + (fl ? f : 0);
-            double p = 0.0;
-            for (int r = rgp; r < NQ; r += RG) p += __ldg(bp + idx[r] * (uint32_t)m.F);
-            for (int off = FP; off < 32; off <<= 1) p += __shfl_xor_sync(FULL, p, off);
+            const double p = FP == 8 ? wl3_dfeat<8, NQ8>(bp, off, NQ, g)
+                                     : (FP == 16 ? wl3_dfeat<16, NQ8>(bp, off, NQ, g) : wl3_dfeat<32, NQ8>(bp, off, NQ, g));
             if (fl && rgp == 0) feat[f] += p;
             if (m.muW && g == 0) feat[m.muF] += mb->st[i].dmu;
             __syncwarp();
@@ -642,10 +671,11 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         if (i < n) {
-          const int flags = mb->st[i].flags, bin = mb->st[i].bin;
+          const int4 mt = *reinterpret_cast<const int4*>(&mb->st[i].flags);
+          const int flags = mt.x & 3, bin = mt.x >> 2;
           accepted = (flags & 1) != 0;
           nacc += flags & 1;
-          enth_last = mb->st[i].enth;
+          enth_last = __hiloint2double(mt.w, mt.z);
           wl_m_traced = wl_m;   // trace.mod_factor is copied before the flatness check (wanglandau.py:251)
           if (flags & 2) {
             ++wl_cnt;
@@ -745,17 +775,23 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
   const double nat_mu = m.muW ? t.nat[m.muF] : 0.0;
   const double wl_inv_bin = 1.0 / a.wl.bin_size;
   double wl_m = a.wl.mod_factor_dev[w];
-  int upd_rem, chk_rem;
+  // steps until the next entropy update / flatness check (counted over steps that end inside the window)
+  int upd_left, chk_left;
   {
     const long long c0 = a.wl.steps_counter_dev[w];
-    upd_rem = (int)(c0 % a.wl.update_period);
-    chk_rem = (int)(c0 % a.wl.check_period);
+    upd_left = a.wl.update_period - (int)(c0 % a.wl.update_period);
+    chk_left = a.wl.check_period - (int)(c0 % a.wl.check_period);
   }
+  const bool every_step = a.wl.update_period == 1;
   double enth = a.enthalpy[w];
   if (g == 0) occ[m.N] = 0;                     // pad byte behind the row: the zero code gathered by unused record slots
   __syncthreads();                              // P0
-  double cur_fb = exact_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
-  double s_cur = (cur_fb >= 0.0 && cur_fb < (double)nb) ? wlSs[(int)cur_fb] : 0.0;
+  int cur_bin;                                  // bin of the current enthalpy; -1 while the walker is outside the window
+  {
+    const double fb = exact_floordiv(enth - a.wl.min_enthalpy, a.wl.bin_size);
+    cur_bin = (fb >= 0.0 && fb < (double)nb) ? (int)fb : -1;
+  }
+  double s_cur = cur_bin >= 0 ? wlSs[cur_bin] : 0.0;
   const int cand = g >> 3, l = g & 7;           // candidate of this lane group (3 = spare lanes), lane inside the group
   const uint32_t NC = (uint32_t)m.spNC;
   unsigned long long step = a.step0;
@@ -792,7 +828,7 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
           const uint32_t o0 = occ[s0], o1 = occ[s1], o2 = occ[s2];
           const uint32_t c0 = s0 == ps ? pc : o0, c1 = s1 == ps ? pc : o1, c2 = s2 == ps ? pc : o2;
           const uint32_t idx = (v.y >> 16) + NC * (c0 + NC * (c1 + NC * c2));
-          if (cand < 3) st_out[qq * 8] = idx + cur;
+          if (cand < 3) st_out[qq * 8] = (idx + cur) * (uint32_t)m.F;      // row offset in the per-feature table
           const double d = Dn[idx];
           if ((qq % 3) == 0) acc += d; else if ((qq % 3) == 1) a1 += d; else a2 += d;   // (fixed order, three chains)
         }
@@ -823,10 +859,13 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
           const float lfc = __uint_as_float(i == 0 ? rq0.z : rq1.z);
           const double e_new = enth + dHc;
           bool acc_ = false;
-          double new_fb = cur_fb, s_new = s_cur;
+          int new_bin = cur_bin;
+          double s_new = s_cur;
           if (!(e_new < a.wl.min_enthalpy || e_new >= a.wl.max_enthalpy)) {
-            new_fb = exact_floordiv_inv(e_new - a.wl.min_enthalpy, a.wl.bin_size, wl_inv_bin);
-            s_new = new_fb == cur_fb ? s_cur : ((new_fb >= 0.0 && new_fb < (double)nb) ? wlSs[(int)new_fb] : 0.0);
+            // (inside the window the bin index is inside [0, nb): nb = ceil((max - min) / bin_size); the clamp only
+            // guards the table against a rounding surprise)
+            new_bin = min((int)exact_floordiv_inv(e_new - a.wl.min_enthalpy, a.wl.bin_size, wl_inv_bin), nb - 1);
+            if (new_bin != cur_bin) s_new = wlSs[new_bin];
             const double exponent = s_cur - s_new;
             const int af = accept_fast(exponent, lfc);
             const unsigned long long st_ = step + (unsigned long long)i;
@@ -836,27 +875,23 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
           if (acc_) {
             if (g == 0) occ[sitec] = (uint8_t)newcc;
             enth += dHc;
-            cur_fb = new_fb;
+            cur_bin = new_bin;
             s_cur = s_new;
           }
-          const bool valid = cur_fb >= 0.0 && cur_fb < (double)nb;
-          if (valid) {
-            if (++upd_rem == a.wl.update_period) upd_rem = 0;
-            if (++chk_rem == a.wl.check_period) chk_rem = 0;
-            if (upd_rem == 0) {
+          if (cur_bin >= 0) {
+            if (every_step || --upd_left == 0) {
+              upd_left = a.wl.update_period;
               s_cur += wl_m;
-              if (g == 0) wlSs[(int)cur_fb] = s_cur;
+              if (g == 0) wlSs[cur_bin] = s_cur;
             }
-            if (chk_rem == 0) mflags |= 1;
+            if (--chk_left == 0) { chk_left = a.wl.check_period; mflags |= 1; }
           }
           if (g == 0) {
-            Wl2Step o;
-            o.enth = enth; o.dmu = dmuc;
-            o.flags = (acc_ ? 1 : 0) | (valid ? 2 : 0);
-            o.bin = valid ? (int)cur_fb : 0;
-            o.src = (i == 0 ? 0 : (prev_acc ? 2 : 1)) | ((int)newcc << 8);     // stash row | new code (table plane)
-            o.slot = 0;
-            mb->st[i] = o;
+            // (enthalpy after the step, flags | bin, stash row | new code << 8): one 16-byte store; dmu beside it
+            const int meta = (acc_ ? 1 : 0) | (cur_bin >= 0 ? 2 | (cur_bin << 2) : 0);
+            const int src = (i == 0 ? 0 : (prev_acc ? 2 : 1)) | ((int)newcc << 8);
+            *reinterpret_cast<int4*>(&mb->st[i].flags) = make_int4(meta, src, __double2loint(enth), __double2hiint(enth));
+            if (m.muW) mb->st[i].dmu = dmuc;
           }
           prev_acc = acc_;
           ++ncommit;

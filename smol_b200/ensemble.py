@@ -25,6 +25,8 @@ class Ensemble:
     def from_cluster_expansion(cls, cluster_expansion, supercell_matrix,
                                processor_type="decomposition", use_concentration=False, **kwargs):
         """ensemble.py:132-217."""
+        from .processor import _reject_use_concentration
+        _reject_use_concentration(use_concentration)
         subspace = cluster_expansion.cluster_subspace
         has_ext = len(getattr(subspace, "external_terms", [])) > 0
         coefs = cluster_expansion.coefs[:-1] if has_ext else cluster_expansion.coefs

@@ -16,6 +16,39 @@ from .model import ExpansionTables, PackedModel
 from .sublattice import Sublattice
 
 
+# Pauling electronegativities (pymatgen's Element.X; elements without a value compare as +inf there)
+_PAULING_X = dict(
+    H=2.20, Li=0.98, Be=1.57, B=2.04, C=2.55, N=3.04, O=3.44, F=3.98, Na=0.93, Mg=1.31, Al=1.61, Si=1.90, P=2.19,
+    S=2.58, Cl=3.16, K=0.82, Ca=1.00, Sc=1.36, Ti=1.54, V=1.63, Cr=1.66, Mn=1.55, Fe=1.83, Co=1.88, Ni=1.91, Cu=1.90,
+    Zn=1.65, Ga=1.81, Ge=2.01, As=2.18, Se=2.55, Br=2.96, Kr=3.00, Rb=0.82, Sr=0.95, Y=1.22, Zr=1.33, Nb=1.6, Mo=2.16,
+    Tc=1.9, Ru=2.2, Rh=2.28, Pd=2.20, Ag=1.93, Cd=1.69, In=1.78, Sn=1.96, Sb=2.05, Te=2.1, I=2.66, Xe=2.6, Cs=0.79,
+    Ba=0.89, La=1.10, Ce=1.12, Pr=1.13, Nd=1.14, Pm=1.13, Sm=1.17, Eu=1.2, Gd=1.2, Tb=1.1, Dy=1.22, Ho=1.23, Er=1.24,
+    Tm=1.25, Yb=1.1, Lu=1.27, Hf=1.3, Ta=1.5, W=2.36, Re=1.9, Os=2.2, Ir=2.20, Pt=2.28, Au=2.54, Hg=2.00, Tl=1.62,
+    Pb=2.33, Bi=2.02, Th=1.3, U=1.38)
+
+
+def species_sort_key(label):
+    """Ordering key of a species label ('Li+', 'Mn3+', 'O2-', 'Au', a pymatgen Species ...) equal to pymatgen's
+    ``Species.__lt__``: electronegativity (unknown = +inf), symbol, oxidation state; labels that are not element
+    symbols sort by the label itself behind every element of known electronegativity."""
+    import re
+    text = str(label)
+    m = re.match(r"^([A-Z][a-z]?)(\d*\.?\d*)([+-]?)$", text)
+    if not m or m.group(1) not in _PAULING_X:
+        return (float("inf"), text, 0.0)
+    oxi = float(m.group(2) or 1.0) * (1 if m.group(3) == "+" else -1) if m.group(3) else 0.0
+    return (_PAULING_X[m.group(1)], m.group(1), oxi)
+
+
+def _reject_use_concentration(flag):
+    """base.py:60-62: the site-basis measure comes from the prim's site concentrations.  The bases (and so the
+    correlation / interaction tensors) are inputs here; a subspace built with the concentration measure already
+    carries them, the flag itself cannot be honoured after the fact."""
+    if flag:
+        raise NotImplementedError("use_concentration=True is not supported: build the cluster subspace (site bases) "
+                                  "with the concentration measure instead")
+
+
 def _as_occu(occupancy):
     """int32 conversion with the reference's error (expansion.py:176-189, 210-214)."""
     try:
@@ -58,11 +91,15 @@ class Processor(ABC):
         return [species[i] for i, species in zip(encoded_occupancy, self.allowed_species)]
 
     def get_sublattices(self):
-        """base.py:245-268: one sublattice per unique site space."""
+        """base.py:75-82, 245-268: one sublattice per unique site space, in the reference's FIXED order -- the site
+        spaces sorted by their species lists (``SiteSpace.__lt__``, cofe/space/domain.py:201-203), species compared as
+        pymatgen compares them (electronegativity, then symbol, then oxidation state).  Positional arguments such as
+        ``sublattice_probabilities``, the table-flip dimensions and hyperplane columns follow this order."""
         spaces = []
         for sp in self.allowed_species:
             if sp not in spaces:
                 spaces.append(sp)
+        spaces.sort(key=lambda space: [species_sort_key(sp) for sp in space])
         return [Sublattice(space, np.array([i for i, sp in enumerate(self.allowed_species)
                                             if sp == space])) for space in spaces]
 
@@ -154,6 +191,7 @@ class ClusterExpansionProcessor(Processor):
 
     def __init__(self, cluster_subspace, supercell_matrix, coefficients, use_concentration=False,
                  num_threads=None, num_threads_full=None):
+        _reject_use_concentration(use_concentration)
         super().__init__(cluster_subspace, supercell_matrix, coefficients)
         if len(coefficients) != cluster_subspace.num_corr_functions:
             raise ValueError(
@@ -181,6 +219,7 @@ class ClusterDecompositionProcessor(Processor):
                 f"The number of cluster interaction tensors must match the number  of orbits in "
                 f"the subspace. Got {len(interaction_tensors)} interaction tensors, but need "
                 f"{cluster_subspace.num_orbits}  for the given cluster_subspace.")
+        _reject_use_concentration(use_concentration)
         coefficients = (cluster_subspace.orbit_multiplicities if coefficients is None
                         else coefficients)                                   # expansion.py:311-316
         super().__init__(cluster_subspace, supercell_matrix, coefficients)
@@ -277,7 +316,8 @@ class CorrelationDistanceProcessor(DistanceProcessor, ClusterExpansionProcessor)
         n = cluster_subspace.num_corr_functions
         target_vector = np.zeros(n) if target_vector is None else target_vector          # distance.py:262-264
         target_weights = np.ones(n - 1) if target_weights is None else target_weights
-        ClusterExpansionProcessor.__init__(self, cluster_subspace, supercell_matrix, np.zeros(n), **processor_kwargs)
+        ClusterExpansionProcessor.__init__(self, cluster_subspace, supercell_matrix, np.zeros(n),
+                                           use_concentration=use_concentration, **processor_kwargs)
         self._init_distance(target_vector, match_weight, match_tol, target_weights,
                             lambda orbs: [i for o in orbs for i in range(o.bit_id, o.bit_id + len(o))])
 
@@ -292,7 +332,7 @@ class ClusterInteractionDistanceProcessor(DistanceProcessor, ClusterDecompositio
         target_vector = np.zeros(n) if target_vector is None else target_vector
         target_weights = np.ones(n - 1) if target_weights is None else target_weights
         ClusterDecompositionProcessor.__init__(self, cluster_subspace, supercell_matrix, interaction_tensors,
-                                               **processor_kwargs)
+                                               use_concentration=use_concentration, **processor_kwargs)
         self._init_distance(target_vector, match_weight, match_tol, target_weights, lambda orbs: [o.id for o in orbs])
 
 
@@ -344,6 +384,7 @@ class CompositeProcessor(Processor):
     """
 
     def __init__(self, cluster_subspace, supercell_matrix, use_concentration=False):
+        _reject_use_concentration(use_concentration)
         super().__init__(cluster_subspace, supercell_matrix, None)
         self._processors = []
         self.coefs = np.empty(0)

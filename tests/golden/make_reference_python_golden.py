@@ -476,6 +476,63 @@ def record(kernel, rngs, occ, nsteps, snap_every):
     return acc, prop, dh, np.array(snaps)
 
 
+def reference_ensemble_objects():
+    """LIVE objects of the reference's own classes (smol/moca/ensemble.py, processor/{expansion,ewald,composite}.py,
+    unmodified, imported behind the package shells) for the extractor test of smol_b200.interop:
+    name -> (reference Ensemble, (subspace, supercell matrix, interaction tensors, Ewald (matrix, inds, coef) | None,
+    chemical potentials)).  Fresh process only (it rewires sys.modules)."""
+    from smol_b200 import lattice as L
+    import_reference_kernels()
+    import_reference_sampler()
+    CE, CD, RefSubspace = import_reference_processors()
+    cm = types.ModuleType("pymatgen.core.composition")
+    cm.ChemicalPotential = dict
+    sys.modules["pymatgen.core.composition"] = cm
+    pp = sys.modules["smol.moca.processor"]
+    pa = types.ModuleType("pymatgen.analysis")
+    pe = types.ModuleType("pymatgen.analysis.ewald")
+    pe.EwaldSummation = lambda *a, **k: None
+    sys.modules.update({"pymatgen.analysis": pa, "pymatgen.analysis.ewald": pe})
+    ext = types.ModuleType("smol.cofe.extern")
+    ext.__path__ = [REF + "/cofe/extern"]
+    sys.modules["smol.cofe.extern"] = ext
+    sys.modules["smol.cofe.space.domain"].get_allowed_species = sys.modules["smol.cofe.space"].get_allowed_species
+    RealEwaldTerm = importlib.import_module("smol.cofe.extern.ewald").EwaldTerm
+    RefEwaldProcessor = importlib.import_module("smol.moca.processor.ewald").EwaldProcessor
+    RefComposite = importlib.import_module("smol.moca.processor.composite").CompositeProcessor
+    pp.CompositeProcessor, pp.EwaldProcessor = RefComposite, RefEwaldProcessor
+    RefEnsemble = importlib.import_module("smol.moca.ensemble").Ensemble
+    factory, _ = table_flip_model()
+    sub, scm, coefs = processor_cases()["rs2of"]
+    it = TF_INTERACTIONS()
+    out = {}
+
+    def sublattices():
+        o_ens = factory()
+        for sl in o_ens.sublattices:
+            sl.site_space = _SiteSpace({spc: 1.0 / len(sl.species) for spc in sl.species})
+        return o_ens.sublattices
+    out["semigrand_decomposition"] = (RefEnsemble(CD(RefSubspace(sub), scm, it), sublattices=sublattices(),
+                                                  chemical_potentials=dict(TF_MUS)), (sub, scm, it, None, dict(TF_MUS)))
+    ewm, ewi = L.ewald_matrix(sub, scm)
+
+    class GivenMatrixTerm(RealEwaldTerm):
+        def get_ewald_structure(self, structure):
+            return None, ewi
+
+        def get_ewald_matrix(self, ewald_summation):
+            return ewm
+    term = GivenMatrixTerm()
+    rsub = RefSubspace(sub)
+    rsub.external_terms = (term,)
+    rsub.add_external_term = lambda t: None
+    comp = RefComposite(rsub, scm)
+    comp.add_processor(CD(rsub, scm, it))
+    comp.add_processor(RefEwaldProcessor(rsub, scm, term, coefficient=0.1))
+    out["canonical_composite_ewald"] = (RefEnsemble(comp, sublattices=sublattices()), (sub, scm, it, (ewm, ewi, 0.1), None))
+    return out
+
+
 def main():
     from oracle import lmc_oracle as O
     Metropolis, WangLandau = import_reference_kernels()

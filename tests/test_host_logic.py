@@ -445,3 +445,41 @@ def test_engine_limits_fail_loudly_without_a_device():
     from smol_b200.sampler import table_flip_tables
     with pytest.raises(ValueError, match="more than 4 sites"):
         table_flip_tables(proc.get_sublattices(), [[-5, 5]])
+
+
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/smol") and os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "smol"))),
+                    reason="needs the reference sources and its compiled evaluators (build container only)")
+def test_interop_extracts_live_reference_objects():
+    """processor/expansion.py:142-156, ensemble.py:89-99, processor/ewald.py:76-101: the reference's REAL Ensemble /
+    ClusterDecompositionProcessor / EwaldProcessor / CompositeProcessor instances go through
+    smol_b200.interop.from_smol_ensemble (fresh process: the import shells rewire sys.modules)"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "extractor_reference_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res == {"semigrand_decomposition": True, "canonical_composite_ewald": True}
+
+
+def test_sublattice_order_and_use_concentration():
+    """processor/base.py:75-82: sublattices in the order of the SORTED site spaces (species compared as pymatgen does:
+    electronegativity, symbol, oxidation state), whatever the order of the sites; use_concentration is refused loudly"""
+    import smol_b200 as S
+    from smol_b200.processor import species_sort_key
+    assert sorted(["O2-", "F-", "Li+", "Mn3+", "Ti4+", "Mn2+"], key=species_sort_key) == \
+        ["Li+", "Ti4+", "Mn2+", "Mn3+", "O2-", "F-"]
+    # anion site first in the primitive cell: the sublattices still come cations first (Li < O by electronegativity)
+    lat = 0.5 * 4.2 * np.array([[0, 1, 1], [1, 0, 1], [1, 1, 0]], dtype=float)
+    prim = L.PrimCell(lat, [[0.5, 0.5, 0.5], [0, 0, 0]], [("O2-", "F-"), ("Li+", "Mn3+")],
+                      {"Li+": 1, "Mn3+": 3, "O2-": -2, "F-": -1})
+    sub = L.ClusterSubspace.from_cutoffs(prim, {2: 3.1})
+    proc = S.ClusterExpansionProcessor(sub, np.eye(3, dtype=int) * 2, np.zeros(sub.num_corr_functions))
+    subl = proc.get_sublattices()
+    assert [s.species for s in subl] == [("Li+", "Mn3+"), ("O2-", "F-")]
+    assert subl[0].sites.tolist() == list(range(8, 16)) and subl[1].sites.tolist() == list(range(8))
+    with pytest.raises(NotImplementedError, match="use_concentration"):
+        S.ClusterExpansionProcessor(sub, np.eye(3, dtype=int), np.zeros(sub.num_corr_functions), use_concentration=True)
+    with pytest.raises(NotImplementedError, match="use_concentration"):
+        S.CompositeProcessor(sub, np.eye(3, dtype=int), use_concentration=True)

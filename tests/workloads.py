@@ -119,7 +119,7 @@ class Workload:
     # False: the built algorithm replaces the reference's (frac is quoted on built_bytes)
     roofline_uses_survey_bytes = True
 
-    def built_bytes(self, acceptance):
+    def built_bytes(self, acceptance, ewald_cache=False):
         """(bytes per attempted step the BUILT algorithm moves per walker, description) -- same accounting as
         SURVEY 8(d): per-walker state and per-flip gathers count, tables shared by all walkers do not"""
         return self.algorithmic_bytes, "the reference algorithm's (SURVEY 8d)"
@@ -151,7 +151,7 @@ class Config2(Workload):
     def initial_occupancies(self, W, seed=0):
         return M.random_occupancies(self.subspace(), self.supercell(), W, seed=seed, balanced=True)
 
-    def built_bytes(self, acceptance):
+    def built_bytes(self, acceptance, ewald_cache=False):
         # speculative kernel + cover merge: 22 records x 3 byte gathers per flip, 2 flips; an accepted step is
         # re-evaluated with the classic records (213 gathers per flip) and writes 2 bytes
         b = 2 * 66 + acceptance * (2 * 213 + 2) + (512 + 64 + 9) / 512
@@ -194,7 +194,7 @@ class Config3(Workload):
 
     roofline_uses_survey_bytes = False
 
-    def built_bytes(self, acceptance):
+    def built_bytes(self, acceptance, ewald_cache=True):
         # speculative kernel + Ewald potential cache: 66 gathers + 8 B cached potential per attempted flip; an
         # accepted flip re-evaluates (213 gathers), writes 1 byte, reads one row of the site kernel K (N f64) and
         # read-modify-writes the walker's potential row (2 x N f64)
@@ -342,10 +342,17 @@ class Config5(Workload):
 
     roofline_uses_survey_bytes = False
 
-    def built_bytes(self, acceptance):
-        # classic kernel, Ewald through the factorised site kernel: per changed site ~241 gathers + ONE row of
-        # K (N f64) + the walker's charge indices (N bytes); k ~ 2.5 changed sites per step
+    def built_bytes(self, acceptance, ewald_cache=False):
         N = 2 * self.n_cell ** 3
+        if ewald_cache:
+            # potential cache (acceptance below 25 %): per changed site ~241 gathers + the cached potential (8 B) + one
+            # element of K per earlier flip of the step; an accepted step reads one row of K per changed site and
+            # read-modify-writes the walker's potential row
+            b = 2.5 * (241 + 8 + 8 + 1) + acceptance * (2.5 * 8 * N + 16 * N) + (N + 88 + 9) / self.thin_by
+            return b, ("potential cache: per changed site ~241 int8 gathers + 16 B of cached potential / K elements; per "
+                       "ACCEPTED step 2.5 rows of K (8N B each) + the potential row read-modify-write (16N B)")
+        # Ewald through the factorised site kernel: per changed site ~241 gathers + ONE row of K (N f64) + the
+        # walker's charge indices (N bytes); k ~ 2.5 changed sites per step
         b = 2.5 * (241 + 8 * N + N + 1) + (N + 88 + 9) / self.thin_by
         return b, ("per changed site: ~241 int8 gathers + one row of the site kernel K (8N B, instead of the "
                    "reference's two E-matrix rows) + the walker's charge indices (N B); 2.5 changed sites per step")
