@@ -10,9 +10,8 @@ A bench "step" = one ``lmc_run`` launch advancing every walker of the GPU by ``s
 sampling intervals of ``thin_by`` attempted MC steps, writing the per-interval traces to HBM.
 
   value     device-resident throughput: CUDA events around the launches, state, tables and traces in HBM
-            (``Sampler.run_device``); N > 1: the per-step all-gather of the enthalpy trace (the path's only
-            collective) runs on a side stream, and whatever of it is still outstanding after the last
-            launch is added to the timed total
+            (``Sampler.run_device``); N > 1: the enthalpy traces of the timed region are all-gathered once behind
+            the last launch (the path's only collective) and that time is added to the total
   e2e       the same metric through the public API with HOST buffers: per step the initial occupancies go
             host->device from page-locked int32 memory and every trace comes back to the host;
             ``Sampler.run(..., block=False)`` back to back, each step's result read on the host while the next
@@ -192,23 +191,21 @@ def _device_arm(wk, smp, occ_host, W, nsteps, thin, args, world, dist, dev, loca
     import torch
     out = smp.run_device(nsteps, occ_host, thin_by=thin)                 # allocations + initial evaluation
     enth = out["enthalpy"]
-    gathered = torch.empty((world * enth.numel(),), dtype=torch.float64, device=dev) if world > 1 else None
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    main = torch.cuda.current_stream(dev)
+    # N > 1: the path's only collective gathers the per-interval observable trace of the WHOLE timed region once,
+    # behind the last launch ("once per saved sample (or once per run)"); every launch parks its
+    # enthalpy trace in a device buffer (a 256 KB device-to-device copy inside the timed launch interval)
+    hist = torch.empty((max(args.steps, 1), *enth.shape), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.empty((world * hist.numel(),), dtype=torch.float64, device=dev) if world > 1 else None
 
-    def step():
+    def step(i):
         smp.run_device(nsteps, None, thin_by=thin, out=out, reuse_state=True)
         if world > 1:
-            # the only collective of the path: gather the per-interval observable trace.  It runs on a side
-            # stream behind this launch; the chains never wait for it
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(comm):
-                comm.wait_event(ev)
-                dist.all_gather_into_tensor(gathered, enth.view(-1))
+            hist[i % hist.shape[0]].copy_(enth, non_blocking=True)
 
-    for _ in range(args.warmup):
-        step()
+    for i in range(args.warmup):
+        step(i)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, hist.view(-1))            # (communicator set up outside the timed region)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -224,14 +221,14 @@ def _device_arm(wk, smp, occ_host, W, nsteps, thin, args, world, dist, dev, loca
             flush.fill_(i & 0xff)                      # evict L2 between timed iterations (not timed)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step()
+        step(i)
         e1.record()
         evs.append((e0, e1))
     tail_ms = 0.0
-    if world > 1:   # gathers still outstanding behind the last launch count
+    if world > 1:   # the trace gather of the region, timed and added to the total
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        main.wait_stream(comm)
+        dist.all_gather_into_tensor(gathered, hist.view(-1))
         t1.record()
         torch.cuda.synchronize()
         tail_ms = t0.elapsed_time(t1)
