@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 14
+#define LMC_ABI_VERSION 15
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -165,6 +165,12 @@ typedef struct LmcWangLandau {
   int64_t* trace_occurrences_dev;   /* [S][W][num_bins] */
   double* trace_mean_features_dev;  /* [S][W][num_bins][F] cumulative MEAN features (sums / occurrences if reserved == 1) */
   double* trace_mod_factor_dev;     /* [S][W] modification factor before the flatness check of the sampled step */
+  /* optional successor table of the modification factor (a callable `mod_update`, wanglandau.py:100-105, tabulated by
+   * the host: entry k + 1 = mod_update(entry k), entry 0 = the initial factor).  A flatness event replaces a factor
+   * equal to entry k by entry k + 1 (the last entry maps to itself); NULL: factor / mod_update */
+  const double* mod_table_dev;      /* [mod_table_len] */
+  int32_t mod_table_len;
+  int32_t reserved2;
 } LmcWangLandau;
 
 typedef struct LmcRunConfig {

@@ -1164,7 +1164,7 @@ class WangLandau:
             histogram = self._histogram[self._entropy > 0]
             if len(histogram) >= 2 and (histogram > self.flatness * histogram.mean()).all():
                 self._histogram[:] = 0
-                self._m = self._m / self._mod_update
+                self._m = self._mod_update(self._m) if callable(self._mod_update) else self._m / self._mod_update   # wanglandau.py:100-105
         return SimpleNamespace(accepted=accepted, dfeatures=dfeat, denthalpy=dH, step=step)
 
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 14
+LMC_ABI_VERSION = 15
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -86,6 +86,7 @@ class LmcWangLandau(C.Structure):
         ("mean_features_dev", _P), ("mod_factor_dev", _P), ("steps_counter_dev", _P),
         ("trace_entropy_dev", _P), ("trace_histogram_dev", _P), ("trace_occurrences_dev", _P),
         ("trace_mean_features_dev", _P), ("trace_mod_factor_dev", _P),
+        ("mod_table_dev", _P), ("mod_table_len", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

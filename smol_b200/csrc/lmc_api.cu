@@ -851,7 +851,6 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     for (int i = 0; i < c->comp_num; ++i)
       if (c->comp_usher[i] != LMC_USHER_FLIP && c->comp_usher[i] != LMC_USHER_SWAP)
         return fail("composite sub-ushers must be Flip or Swap");
-    if (c->kernel == LMC_KERNEL_WANGLANDAU) return fail("the composite usher is built for the Metropolis kernel only");
   }
   if (c->usher == LMC_USHER_MULTISTEP) {
     if (c->ms_usher != LMC_USHER_FLIP && c->ms_usher != LMC_USHER_SWAP) return fail("the multi-step sub-usher must be Flip or Swap");
@@ -859,7 +858,6 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     for (int i = 0; i < c->ms_num; ++i)
       if (c->ms_len[i] < 1 || c->ms_len[i] * (c->ms_usher == LMC_USHER_SWAP ? 2 : 1) > LMC_MAX_FLIPS)
         return fail("multi-step lengths must change at most 4 sites per step (<= 4 flips or <= 2 swaps)");
-    if (c->kernel == LMC_KERNEL_WANGLANDAU) return fail("the multi-step usher is built for the Metropolis kernel only");
   }
   if (c->usher < 0 || c->usher > LMC_USHER_MULTISTEP) return fail("unknown usher");
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->wl.num_bins <= 1) return fail("Wang-Landau needs more than one bin");

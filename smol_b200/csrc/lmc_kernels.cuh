@@ -561,6 +561,15 @@ __device__ __forceinline__ int pick(const int (&arr)[MF], int f) {
   return v;
 }
 
+// next modification factor after a flat histogram (wanglandau.py:253-264): m / mod_update, or the successor of m in the
+// host-tabulated sequence of a callable mod_update (rare path: a linear search over a short table)
+__device__ __forceinline__ double wl_next_mod_factor(const LmcWangLandau& wl, double m) {
+  if (wl.mod_table_dev == nullptr || wl.mod_table_len <= 0) return m / wl.mod_update;
+  for (int i = 0; i + 1 < wl.mod_table_len; ++i)
+    if (__ldg(wl.mod_table_dev + i) == m) return __ldg(wl.mod_table_dev + i + 1);
+  return __ldg(wl.mod_table_dev + wl.mod_table_len - 1);
+}
+
 // Wang-Landau per-walker arrays: plain loads from the shared-memory copy, L2 loads (the global arrays are
 // updated with reductions that bypass L1) otherwise
 template <typename T>
@@ -1314,7 +1323,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           hmin = group_min<G>(hmin, gmask);
           if (nvis >= 2 && hmin > a.wl.flatness * (hsum / (double)nvis)) {
             for (int b = g; b < nb; b += G) { if (wl_sm) wlHs[b] = 0ll; else __stcg(wlH + b, 0ll); }
-            wl_m = wl_m / a.wl.mod_update;
+            wl_m = wl_next_mod_factor(a.wl, wl_m);
             group_sync<G>(gmask);
           }
         }

@@ -27,7 +27,7 @@ static int launch_usher(const DevModel& m, const RunArgs& a, int usher, const La
 #if LMC_G == 8 || LMC_G == 32
     case LMC_USHER_TABLEFLIP: return launch_one<KONE, EWALD, LMC_USHER_TABLEFLIP>(m, a, lc);
 #endif
-#if LMC_G == 32 && !LMC_WL
+#if LMC_G == 32
     case LMC_USHER_COMPOSITE: return launch_one<KONE, EWALD, LMC_USHER_COMPOSITE>(m, a, lc);
     case LMC_USHER_MULTISTEP: return launch_one<KONE, EWALD, LMC_USHER_MULTISTEP>(m, a, lc);
 #endif

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(32 * (NE + 1), 7) lmc_wl2_kernel(const DevMode
               hmin = group_min<G>(hmin, FULL);
               if (nvis >= 2 && hmin > a.wl.flatness * (hsum / (double)nvis)) {
                 for (int q = g; q < nb; q += G) wlHs[q] = 0ll;
-                wl_m = wl_m / a.wl.mod_update;
+                wl_m = wl_next_mod_factor(a.wl, wl_m);
                 __syncwarp();
               }
             }
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(96, 7) lmc_wl3_kernel(const DevModel m, const 
         hmin = group_min<G>(hmin, FULL);
         if (nvis >= 2 && hmin > a.wl.flatness * (hsum / (double)nvis)) {
           for (int q = g; q < nb; q += G) wlHs[q] = 0ll;
-          wl_m = wl_m / a.wl.mod_update;
+          wl_m = wl_next_mod_factor(a.wl, wl_m);
           __syncwarp();
         }
       }

@@ -578,7 +578,9 @@ def _ewald_rows_gpu(cart, rows, gv, coef, tv, eta, real_cut, vol):
     def up(a, dt):
         return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
     cart_d, rows_d = up(cart, np.float64), up(rows, np.int32)
-    gv_d, gc_d, tv_d = up(gv, np.float64), up(coef, np.float64), up(tv, np.float64)
+    pad3, pad1 = np.zeros((1, 3)), np.zeros(1)      # (an empty sum still hands the library a valid pointer)
+    gv_d, gc_d, tv_d = up(gv if len(gv) else pad3, np.float64), up(coef if len(coef) else pad1, np.float64), \
+        up(tv if len(tv) else pad3, np.float64)
     out = torch.empty((len(rows), len(cart)), dtype=torch.float64, device=dev)
     capi.check(lib.lmc_ewald_site_kernel(cart_d.data_ptr(), len(cart), rows_d.data_ptr(), len(rows), gv_d.data_ptr(),
                                          gc_d.data_ptr(), len(gv), tv_d.data_ptr(), len(tv), float(eta),
@@ -588,8 +590,10 @@ def _ewald_rows_gpu(cart, rows, gv, coef, tv, eta, real_cut, vol):
 
 
 def ewald_matrix(subspace: ClusterSubspace, scmatrix, eta=None, real_cut=None, recip_cut=None,
-                 acc=12.0, backend="auto"):
-    """Total Ewald pair matrix M (eV) with ``E_total = sum(M[occupied][:, occupied])``.
+                 acc=12.0, backend="auto", term="total"):
+    """Ewald pair matrix M (eV) with ``E = sum(M[occupied][:, occupied])``; ``term`` selects the part as
+    ``EwaldTerm.use_term`` does (cofe/extern/ewald.py:168-177): "total" = reciprocal + real + point, or one of them
+    ("point" is the diagonal self term).
 
     Same decomposition as pymatgen's ``EwaldSummation.total_energy_matrix`` used by
     ``cofe/extern/ewald.py:159-177``: reciprocal + real (+ point/self term on the diagonal),
@@ -638,6 +642,12 @@ def ewald_matrix(subspace: ClusterSubspace, scmatrix, eta=None, real_cut=None, r
             backend = "numpy"
     if backend not in ("gpu", "numpy"):
         raise ValueError("backend must be 'auto', 'gpu' or 'numpy'")
+    if term not in ("total", "reciprocal", "real", "point"):
+        raise ValueError("term must be one of 'total', 'reciprocal', 'real', 'point'")     # cofe/extern/ewald.py:48-52
+    if term in ("real", "point"):
+        gv, coef = gv[:0], coef[:0]
+    if term in ("reciprocal", "point"):
+        tv = tv[:0]
     k_rows = (_ewald_rows_gpu if backend == "gpu" else _ewald_rows_numpy)(cart, rows, gv, coef, tv, eta, real_cut, vol)
     # expand by translation invariance: K[(b,c),(b2,c2)] = k_rows[b][(b2, c2 - c)]
     Sinv = np.linalg.inv(S)
@@ -664,6 +674,7 @@ def ewald_matrix(subspace: ClusterSubspace, scmatrix, eta=None, real_cut=None, r
                 k_rows[b][b2 * ncell + cellsub]
     k_rec, k_real = k_full, 0.0
     m = np.outer(q, q) * (k_rec + k_real)[np.ix_(site_of_row, site_of_row)]
-    m[np.arange(len(q)), np.arange(len(q))] += -q * q * math.sqrt(eta / math.pi)
+    if term in ("total", "point"):
+        m[np.arange(len(q)), np.arange(len(q))] += -q * q * math.sqrt(eta / math.pi)
     m = 0.5 * (m + m.T)  # exact symmetry (the delta path reads one triangle only)
     return np.ascontiguousarray(m * conv, dtype=np.float64), inds

@@ -353,10 +353,11 @@ class EwaldProcessor(Processor):
         if ewald_matrix is None:
             from .lattice import ewald_matrix as _ewm
             kw = {}
-            if ewald_term is not None:
+            if ewald_term is not None:      # EwaldTerm(eta, real_space_cut, recip_space_cut, use_term), cofe/extern/ewald.py:35-62
                 kw = dict(eta=getattr(ewald_term, "eta", None),
                           real_cut=getattr(ewald_term, "real_space_cut", None),
-                          recip_cut=getattr(ewald_term, "recip_space_cut", None))
+                          recip_cut=getattr(ewald_term, "recip_space_cut", None),
+                          term=getattr(ewald_term, "use_term", "total"))
             ewald_matrix, ewald_inds = _ewm(cluster_subspace, self._scmatrix, **kw)
         self._matrix = np.ascontiguousarray(ewald_matrix, dtype=np.float64)
         self._ewald_inds = np.ascontiguousarray(ewald_inds, dtype=np.int32)

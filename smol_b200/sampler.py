@@ -176,8 +176,6 @@ class Sampler:
         if self._usher == capi.LMC_USHER_COMPOSITE:
             # Composite(sublattices, mcushers, mcusher_weights), mcusher.py:314-350
             from .usher import Composite
-            if self._kernel != capi.LMC_KERNEL_METROPOLIS:
-                raise NotImplementedError("the composite usher is built for the Metropolis kernel only")
             comp = Composite(ensemble.sublattices, usher_kwargs.pop("mcushers", None),
                              usher_kwargs.pop("mcusher_weights", None))
             if not comp.mcushers:
@@ -188,8 +186,6 @@ class Sampler:
         if self._usher == capi.LMC_USHER_MULTISTEP:
             # MultiStep(sublattices, mcusher, step_lengths, step_probabilities), mcusher.py:206-272
             from .usher import MultiStep
-            if self._kernel != capi.LMC_KERNEL_METROPOLIS:
-                raise NotImplementedError("the multi-step usher is built for the Metropolis kernel only")
             if "mcusher" not in usher_kwargs or "step_lengths" not in usher_kwargs:
                 raise TypeError("MultiStep needs mcusher and step_lengths")
             ms = MultiStep(ensemble.sublattices, usher_kwargs.pop("mcusher"), usher_kwargs.pop("step_lengths"),
@@ -369,8 +365,19 @@ class Sampler:
                              "a single bin!")
         if p["mod_factor"] <= 0:
             raise ValueError("mod_factor must be greater than 0.")
+        # a callable mod_update (wanglandau.py:100-105) cannot run on the device: its orbit from the initial factor is
+        # tabulated here (every walker's factor is always a member of it) and a flatness event steps along the table
+        self._wl_mod_table = None
         if callable(p.get("mod_update")):
-            raise NotImplementedError("callable mod_update is not supported on the GPU path")
+            tab = [float(p["mod_factor"])]
+            for _ in range(255):
+                nxt = float(p["mod_update"](tab[-1]))
+                if not np.isfinite(nxt) or nxt == tab[-1]:
+                    break
+                if nxt in tab:
+                    raise ValueError("mod_update revisits a modification factor: the sequence must not cycle")
+                tab.append(nxt)
+            self._wl_mod_table = np.array(tab, dtype=np.float64)
         levels = np.arange(p["min_enthalpy"], p["max_enthalpy"], p["bin_size"])  # wanglandau.py:107
         nb, W, F = len(levels), self.nwalkers, self.engine.F
         dev = self.engine.device
@@ -381,6 +388,7 @@ class Sampler:
             occurrences=torch.zeros((W, nb), dtype=torch.int64, device=dev),
             mean_features=torch.zeros((W, nb, F), dtype=torch.float64, device=dev),
             mod_factor=torch.full((W,), float(p["mod_factor"]), dtype=torch.float64, device=dev),
+            mod_table=None if self._wl_mod_table is None else torch.from_numpy(self._wl_mod_table).to(dev),
             steps_counter=torch.zeros((W,), dtype=torch.int64, device=dev))
 
     @property
@@ -527,7 +535,9 @@ class Sampler:
             wl = cfg.wl
             wl.min_enthalpy, wl.max_enthalpy, wl.bin_size = p["min_enthalpy"], p["max_enthalpy"], p["bin_size"]
             wl.flatness = p["flatness"]
-            wl.mod_update = float(p["mod_update"]) if p.get("mod_update") is not None else 2.0
+            wl.mod_update = float(p["mod_update"]) if (p.get("mod_update") is not None and not callable(p["mod_update"])) else 2.0
+            if st.get("mod_table") is not None:
+                wl.mod_table_dev, wl.mod_table_len = st["mod_table"].data_ptr(), int(st["mod_table"].numel())
             wl.num_bins, wl.check_period, wl.update_period = len(st["levels"]), p["check_period"], p["update_period"]
             wl.reserved = 1 if int(p["update_period"]) == 1 else 0   # mean_features buffer holds sums
             wl.entropy_dev, wl.histogram_dev = st["entropy"].data_ptr(), st["histogram"].data_ptr()

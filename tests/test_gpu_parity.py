@@ -722,3 +722,89 @@ def test_speculative_rejects_unsupported(cuda_device):
                                   nwalkers=2, seeds=[1, 2], spec_mode=2)
     with pytest.raises(RuntimeError, match="speculative"):
         smp.run(100, occ0, thin_by=10)
+
+
+# ---------------------------------------------------------------------------------------------
+# the kernel x usher matrix of tests/test_moca/test_kernel.py:22-94 under Wang-Landau
+# ---------------------------------------------------------------------------------------------
+def _wl_fcc_case(W=4, seed=4):
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * 3
+    it = L.cluster_interaction_tensors(sub, M.fcc_coefs(sub, seed=7))
+    ens_g = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, it))
+    ora_p = O.ClusterDecompositionProcessor(sub, scm, it)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices))
+    occ0 = M.random_occupancies(sub, scm, W, seed=seed)
+    e0 = np.array([ora_p.compute_property(o) for o in occ0])
+    lo, hi = e0.min() - 2.0, e0.max() + 2.0
+    return ens_g, ens_o, occ0, dict(min=lo, max=hi, bin=(hi - lo) / 29.3, check=40, flatness=0.3)
+
+
+@pytest.mark.parametrize("usher", ["composite", "multistep", "swap"])
+def test_wang_landau_usher_matrix_trajectory(cuda_device, usher):
+    """WangLandau x {Composite(Flip, Swap), MultiStep(Flip), Swap}: occupancies bit-exact, entropy / histogram of
+    every walker as the oracle's (kernel/wanglandau.py:186-266 over mcusher.py:203-394)"""
+    ens_g, ens_o, occ0, wl = _wl_fcc_case()
+    W = len(occ0)
+    seeds = np.arange(60, 60 + W)
+    kw = {}
+    if usher == "composite":
+        kw = dict(mcushers=["flip", "swap"], mcusher_weights=[2, 1],
+                  oracle_composite=([("flip", None, None), ("swap", None, None)], [2, 1]))
+    elif usher == "multistep":
+        kw = dict(mcusher="flip", step_lengths=[1, 2, 3], oracle_multistep=("flip", [1, 2, 3], None))
+    smp, ref, kernels = _run_both(ens_g, ens_o, usher, W, 1200, 40, occ0, seeds, wl=wl, usher_kwargs=kw)
+    _compare_traces(smp, ref)
+    st = smp.wang_landau_state
+    for w, k in enumerate(kernels):
+        np.testing.assert_array_equal(st["histogram"][w], k._histogram)
+        np.testing.assert_array_equal(st["occurrences"][w], k._occurrences)
+        np.testing.assert_allclose(st["entropy"][w], k._entropy, rtol=1e-13, atol=0)
+        assert st["mod_factor"][w] == k._m
+    assert (st["mod_factor"] < 1.0).any() and 0 < smp.samples.step_efficiency() < 1
+
+
+@pytest.mark.parametrize("kernel", ["classic", "merged"])
+def test_wang_landau_callable_mod_update(cuda_device, kernel, monkeypatch):
+    """a callable mod_update (wanglandau.py:100-105): tabulated on the host, stepped through on the device"""
+    import smol_b200 as S
+    O = _oracle()
+    monkeypatch.setenv("LMC_WL2", "0" if kernel == "classic" else "4")
+    ens_g, ens_o, occ0, wl = _wl_fcc_case()
+    W = len(occ0)
+    seeds = np.arange(80, 80 + W)
+
+    def update(m):
+        return 0.4 * m + 1e-4          # not a division: the device cannot guess it
+
+    smp = S.Sampler.from_ensemble(ens_g, wl["min"], wl["max"], wl["bin"], step_type="flip", kernel_type="WangLandau",
+                                  nwalkers=W, seeds=list(seeds), check_period=wl["check"], flatness=wl["flatness"],
+                                  mod_update=update, mod_factor=0.7)
+    smp.run(1500, occ0, thin_by=50)
+    kernels = [O.WangLandau(ens_o(), O.Flip(ens_o().sublattices), wl["min"], wl["max"], wl["bin"], flatness=wl["flatness"],
+                            check_period=wl["check"], mod_factor=0.7, mod_update=update, seed=int(seeds[w]), walker=w)
+               for w in range(W)]
+    ref = O.run_sampler(kernels, occ0, 1500, 50)
+    _compare_traces(smp, ref)
+    st = smp.wang_landau_state
+    for w, k in enumerate(kernels):
+        assert st["mod_factor"][w] == k._m
+        np.testing.assert_allclose(st["entropy"][w], k._entropy, rtol=1e-13, atol=0)
+    np.testing.assert_array_equal(smp.samples.get_trace_value("mod_factor", flat=False), ref["mod_factor"])
+    assert len(np.unique(st["mod_factor"])) >= 1 and (st["mod_factor"] < 0.7).any()
+
+
+def test_ewald_term_matrices_on_the_gpu(cuda_device):
+    """EwaldTerm.use_term parts from lmc_ewald_site_kernel (empty reciprocal / real sums) == the numpy sums"""
+    from smol_b200 import lattice as L
+    sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * 2
+    for term in ("reciprocal", "real", "point", "total"):
+        g = L.ewald_matrix(sub, scm, backend="gpu", term=term)[0]
+        c = L.ewald_matrix(sub, scm, backend="numpy", term=term)[0]
+        np.testing.assert_allclose(g, c, rtol=0, atol=1e-12 * max(np.abs(c).max(), 1e-300))

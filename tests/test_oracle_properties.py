@@ -205,3 +205,23 @@ def test_distance_processors_match_the_compiled_reference_evaluators():
     p = O.CorrelationDistanceProcessor(sub, scm, target_vector=base.compute_feature_vector(occs[0]) / base.size)
     assert p.compute_feature_vector(occs[0])[0] == max(O.orbits_by_diameter(sub))
     assert p.compute_feature_vector(occs[1])[0] < max(O.orbits_by_diameter(sub))
+
+
+def test_ewald_term_matrices_add_up():
+    """EwaldTerm.use_term (cofe/extern/ewald.py:168-177): total = reciprocal + real + point; the point matrix is the
+    diagonal self term; each part keeps the q_i q_j structure the engine factorises"""
+    from types import SimpleNamespace
+    import smol_b200 as S
+    sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+    scm = np.eye(3, dtype=int) * 2
+    parts = {t: L.ewald_matrix(sub, scm, backend="numpy", term=t)[0] for t in ("total", "reciprocal", "real", "point")}
+    np.testing.assert_allclose(parts["reciprocal"] + parts["real"] + parts["point"], parts["total"], rtol=0,
+                               atol=1e-12 * np.abs(parts["total"]).max())
+    assert np.count_nonzero(parts["point"] - np.diag(np.diag(parts["point"]))) == 0 and (np.diag(parts["point"]) < 0).all()
+    assert np.abs(parts["real"]).max() > 0 and np.abs(parts["reciprocal"]).max() > 0
+    with pytest.raises(ValueError, match="term"):
+        L.ewald_matrix(sub, scm, backend="numpy", term="madelung")
+    # the processor reads the term off an EwaldTerm-like object
+    term = SimpleNamespace(eta=None, real_space_cut=None, recip_space_cut=None, use_term="real")
+    proc = S.EwaldProcessor(sub, scm, ewald_term=term, coefficient=1.0)
+    np.testing.assert_allclose(proc.ewald_matrix, L.ewald_matrix(sub, scm, term="real")[0], rtol=0, atol=1e-12)
