@@ -435,7 +435,8 @@ def run_ours(args):
         "clocks": main_res["clk"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     "traffic": prof.get("dram_bytes_per_launch"),
+                     "traffic": (prof["dram_bytes_per_attempted_step"] * steps_per_launch
+                                 if "dram_bytes_per_attempted_step" in prof else prof.get("dram_bytes_per_launch")),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                      "bytes_per_step": primary,
                      "bytes_model": ("SURVEY 8(d) algorithmic bytes of the reference algorithm"
