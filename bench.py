@@ -450,6 +450,16 @@ def run_ours(args):
                      "sample": "C restatement oracle/lmc_oracle.c, one process per core"},
     }
     out.update(main_res["extra"])
+    if args.config == 2:
+        # the reference's OWN Python loop cannot run on the GPU box (it needs the reference tree): its rate measured in
+        # the build container is quoted from the committed file for context (scripts/reference_python_rate.py)
+        try:
+            rp = json.load(open(os.path.join(ROOT, "profiles", "r02_reference_python.json")))
+            out["cpu_baseline"]["note"] = ("kind 'reference' = smol's compiled evaluators under the RESTATED step loop; smol's own "
+                                           "unmodified Python loop over the same evaluators: %.3g steps/s per process (%s, "
+                                           "profiles/r02_reference_python.json)" % (rp["single_process_steps_per_s"], rp["where"]))
+        except Exception:
+            pass
     if curve:
         out["config"]["acceptance_curve"] = curve
     if sustained:

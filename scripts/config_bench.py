@@ -7,7 +7,11 @@ import smol_b200 as S
 from smol_b200 import lattice as L
 from tests import models as M
 
-PEAK = 6450.6
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0      # B200_PROFILING.md fallback
+# (superseded by `bench.py --config {3,4,5}`; kept for quick kernel-only A/B runs)
 
 
 def timed(smp, nsteps, occ0, thin, reps=3):

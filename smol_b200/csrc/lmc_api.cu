@@ -1003,13 +1003,17 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     // shared memory limits residency here: take the block size with the most resident walkers per SM
     // (fewest waves); 16 warps/SM is the register ceiling of these variants
     const size_t sm_smem = 227 * 1024;
+    // threads per SM the register budget of these variants allows: 512 at <= 128 registers; the table-flip + Ewald
+    // variants are compiled for LMC_TF_MINB resident 256-thread blocks
+    int reg_threads_sm = 512;
+    if (c->usher == LMC_USHER_TABLEFLIP && ewald && c->kernel == LMC_KERNEL_METROPOLIS) reg_threads_sm = 256 * LMC_TF_MINB;
     int best_t = 0; long best_w = -1;
     for (int t = G; t <= max_threads; t += G) {
       if (t % 32) continue;
       const size_t bs = blob + (size_t)(t / G) * (m.Npad + a.walker_smem);
       if ((int)bs > mdl->smem_optin - 1024) break;
       long blocks = (long)(sm_smem / (bs + 1024));
-      blocks = std::min(blocks, (long)(512 / t));
+      blocks = std::min(blocks, (long)(reg_threads_sm / t));
       const long wsm = blocks * (t / G);
       if (wsm > best_w) { best_w = wsm; best_t = t; }
     }
@@ -1036,10 +1040,11 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->usher == LMC_USHER_FLIP && !dist && !ewald && a.off_wl >= 0 && !multicell &&
       c->group_size == 0 && c->block_threads == 0 && !getenv("LMC_GROUP_SIZE") && c->num_walkers <= 7 * mdl->num_sms) {
     int ne = 4;     // 4: merged-record variant where the model has the tables, else one decision warp over classic records
-    if (const char* e = getenv("LMC_WL2")) ne = atoi(e);
+    bool forced = false;   // an explicit LMC_WL2 takes the variant whenever it fits a block (tests), not only at seven blocks per SM
+    if (const char* e = getenv("LMC_WL2")) { ne = atoi(e); forced = true; }
     if (ne == 4) {
       const size_t sm3 = m.spOK && m.spFtab && m.kone ? wl3_smem_bytes(m, c->wl.num_bins) : 0;
-      if (sm3 && m.spNQ % 8 == 0 && 7 * (sm3 + 1024) <= 227 * 1024 && (int)sm3 <= mdl->smem_optin - 1024) {
+      if (sm3 && m.spNQ % 8 == 0 && (forced || 7 * (sm3 + 1024) <= 227 * 1024) && (int)sm3 <= mdl->smem_optin - 1024) {
         a.wpb = 1;
         LaunchCfg lc3{a.W, 96, sm3, (cudaStream_t)stream};
         const int rc3 = launch_wl3(m, a, lc3);
@@ -1051,7 +1056,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     }
     if (ne == 1 || ne == 3) {
       const size_t sm2 = wl2_smem_bytes(m, c->wl.num_bins, ne);
-      if (7 * (sm2 + 1024) <= 227 * 1024 && (int)sm2 <= mdl->smem_optin - 1024) {
+      if ((forced || 7 * (sm2 + 1024) <= 227 * 1024) && (int)sm2 <= mdl->smem_optin - 1024) {
         a.wpb = 1;
         LaunchCfg lc2{a.W, 32 * (ne + 1), sm2, (cudaStream_t)stream};
         const int rc2 = launch_wl2(m, a, m.kone != 0, ne, lc2);

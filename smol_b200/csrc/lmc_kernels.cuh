@@ -601,8 +601,12 @@ __device__ __forceinline__ double py_floordiv(double a, double b) {
 // [L, |f_i - target_i| ...]; every proposal folds its per-record differences into the change of the
 // correlation / interaction vector f (phase B for each proposal, not only on accept) to get the new distances.
 template <int G, bool KONE, int EWMODE, int USHER, bool WLMODE, bool DIST = false>
+#ifndef LMC_TF_MINB
+#define LMC_TF_MINB 2   // resident 256-thread blocks per SM the table-flip + Ewald variants are compiled for (register cap)
+#endif
 __global__ void __launch_bounds__((EWMODE || WLMODE || USHER >= LMC_USHER_TABLEFLIP) ? 256 : 128,
-                                  (EWMODE || WLMODE || USHER >= LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7))
+                                  (USHER == LMC_USHER_TABLEFLIP && EWMODE != 0 && !WLMODE) ? LMC_TF_MINB :
+                                  ((EWMODE || WLMODE || USHER >= LMC_USHER_TABLEFLIP) ? 2 : (G < 32 ? 5 : 7)))
 lmc_run_kernel(const DevModel m, const RunArgs a) {
   constexpr bool EWALD = EWMODE != 0, EWGATHER = EWMODE == 1, EWFIELD = EWMODE == 2;
   constexpr bool COMP = USHER == LMC_USHER_COMPOSITE;   // flip / swap sub-ushers picked per step
@@ -1234,7 +1238,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
               pl[st.newc[f] * nw] ^= bit;
             }
         }
-        if (EWFIELD) {   // accepted: shift the potential cache by the changed charges
+        if (EWFIELD) {   // accepted: shift the potential cache by the changed charges (rows of K: four loads per row in flight)
+#pragma unroll 4
           for (int k = g; k < m.N; k += G) {
             double v = fld[k];
 #pragma unroll

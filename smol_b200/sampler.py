@@ -614,9 +614,14 @@ class Sampler:
             self._copy_stream = torch.cuda.Stream(device=dev)
         if self.samples.has_deferred and self._slot_key(0, nmax, W, N, F) != self.__dict__.get("_slots", {}).get(0, {}).get("key"):
             self.samples.resolve_deferred()      # the trace slots are about to be re-allocated under a pending copy
-        slots = [self._trace_slot(i, nmax, W, N, F, dev) for i in range(2)]
-        # the previous run's deferred tail is still being copied out of the slot it used: start with the other one
-        phase = self.__dict__.get("_slot_phase", 0)
+        # non-blocking runs give every launch its own trace slot and defer EVERY chunk: the call returns once all
+        # launches and copies are enqueued, so the next run's upload / initial evaluation / launches are queued long
+        # before the device needs them (no bubble between back-to-back runs)
+        async_all = (not block) and stream_chunk == 0 and S > 0
+        nslots = max(2, min(8, -(-S // nmax))) if async_all else 2
+        slots = [self._trace_slot(i, nmax, W, N, F, dev) for i in range(nslots)]
+        # the previous run's deferred chunks may still be copied out of the slots they used: keep rotating
+        phase = self.__dict__.get("_slot_phase", 0) % nslots
 
         def finalize(host, pooled, n, ev_copy):
             ev_copy.synchronize()
@@ -663,7 +668,7 @@ class Sampler:
         done, ci, pending = 0, 0, None
         while done < S:
             n = min(nmax, S - done)
-            slot = slots[(ci + phase) % 2]
+            slot = slots[(ci + phase) % nslots]
             d = slot["dev"]
             cfg = self._run_config(ctx, d, n)
             if slot.get("copy_event") is not None:
@@ -691,6 +696,11 @@ class Sampler:
                     host[k][:n].copy_(d[k][:n], non_blocking=True)
                 ev_copy.record(self._copy_stream)
             slot["copy_event"] = ev_copy
+            if async_all and pooled:
+                self.samples.defer(n, thin_by, lambda p=(host, pooled, n, ev_copy): finalize(*p))
+                done += n
+                ci += 1
+                continue
             # tail of the PREVIOUS run: resolved only now, behind this run's upload, initial evaluation and
             # first launch, which therefore overlapped it
             self.samples.resolve_deferred()
@@ -701,8 +711,9 @@ class Sampler:
             pending = (host, pooled, n, ev_copy)
             done += n
             ci += 1
-        self.samples.resolve_deferred()
-        self._slot_phase = (ci + phase) % 2          # slot the next launch would take = NOT the tail's
+        if not async_all:
+            self.samples.resolve_deferred()
+        self._slot_phase = (ci + phase) % nslots     # slot the next launch would take
         events, self._kernel_events = self._kernel_events, []
         self._last_events = events
         if pending is not None:

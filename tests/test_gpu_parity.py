@@ -808,3 +808,60 @@ def test_ewald_term_matrices_on_the_gpu(cuda_device):
         g = L.ewald_matrix(sub, scm, backend="gpu", term=term)[0]
         c = L.ewald_matrix(sub, scm, backend="numpy", term=term)[0]
         np.testing.assert_allclose(g, c, rtol=0, atol=1e-12 * max(np.abs(c).max(), 1e-300))
+
+
+@pytest.mark.parametrize("variant", ["thin1", "odd-periods", "rocksalt-semigrand"])
+@pytest.mark.parametrize("kernel", ["pipeline", "speculative", "merged"])
+def test_wang_landau_warp_specialised_edge_cases(cuda_device, kernel, variant, monkeypatch):
+    """corners of lmc_wl.cuh: a sample boundary after every step (thin_by = 1: every batch is a single step followed
+    by the trace rendezvous), thin_by / check_period / update_period that are odd and mutually prime (batches cut
+    short by checks; update_period 2 = running means instead of sums), and a two-sublattice five-species cell with
+    chemical potentials (ternary code radix, 152 merged records per site: the run-time record loop, chemical work)"""
+    import smol_b200 as S
+    from smol_b200 import lattice as L
+    O = _oracle()
+    monkeypatch.setenv("LMC_WL2", {"pipeline": "1", "speculative": "3", "merged": "4"}[kernel])
+    if variant == "rocksalt-semigrand":
+        sub = M.rocksalt_subspace(anions=("O2-", "F-"))
+        scm = np.eye(3, dtype=int) * 2
+        it = L.cluster_interaction_tensors(sub, np.random.default_rng(12).normal(0, 0.04, sub.num_corr_functions))
+        mus = {"Li+": 0.0, "Mn3+": 0.2, "Ti4+": -0.1, "O2-": 0.05, "F-": 0.0}
+        ens_g = S.Ensemble(S.ClusterDecompositionProcessor(sub, scm, it), chemical_potentials=mus)
+        ora_p = O.ClusterDecompositionProcessor(sub, scm, it)
+
+        def ens_o():
+            return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices), chemical_potentials=mus)
+        W = 3
+        occ0 = M.random_occupancies(sub, scm, W, seed=9)
+        e0 = np.array([np.dot(ens_o().natural_parameters, ens_o().compute_feature_vector(o)) for o in occ0])
+        lo, hi = e0.min() - 1.5, e0.max() + 1.5
+        wl = dict(min=lo, max=hi, bin=(hi - lo) / 17.2, check=30, flatness=0.2)
+        nsteps, thin, kw = 900, 30, {}
+    else:
+        ens_g, ens_o, occ0, wl = _wl_fcc_case(W=3, seed=11)
+        W = 3
+        if variant == "thin1":
+            nsteps, thin, kw = 240, 1, {}
+        else:
+            wl = dict(wl, check=7)
+            nsteps, thin, kw = 13 * 60, 13, dict(update_period=2)
+    seeds = np.arange(500, 500 + W)
+    smp = S.Sampler.from_ensemble(ens_g, wl["min"], wl["max"], wl["bin"], step_type="flip", kernel_type="WangLandau",
+                                  nwalkers=W, seeds=list(seeds), check_period=wl["check"], flatness=wl["flatness"], **kw)
+    smp.run(nsteps, occ0, thin_by=thin)
+    kernels = [O.WangLandau(ens_o(), O.Flip(ens_o().sublattices), wl["min"], wl["max"], wl["bin"], flatness=wl["flatness"],
+                            check_period=wl["check"], seed=int(seeds[w]), walker=w, **kw) for w in range(W)]
+    ref = O.run_sampler(kernels, occ0, nsteps, thin)
+    _compare_traces(smp, ref)
+    st = smp.wang_landau_state
+    g = smp.samples.get_trace_value
+    for w, k in enumerate(kernels):
+        np.testing.assert_array_equal(st["histogram"][w], k._histogram)
+        np.testing.assert_array_equal(st["occurrences"][w], k._occurrences)
+        np.testing.assert_allclose(st["entropy"][w], k._entropy, rtol=1e-13, atol=0)
+        assert st["mod_factor"][w] == k._m
+        np.testing.assert_allclose(st["mean_features"][w], k._mean_features, rtol=RTOL, atol=RTOL * max(np.abs(k._mean_features).max(), 1.0))
+    np.testing.assert_array_equal(g("histogram", flat=False), ref["histogram"])
+    np.testing.assert_array_equal(g("mod_factor", flat=False), ref["mod_factor"])
+    np.testing.assert_allclose(g("entropy", flat=False), ref["entropy"], rtol=1e-13, atol=0)
+    assert 0 < smp.samples.step_efficiency() < 1

@@ -483,3 +483,17 @@ def test_sublattice_order_and_use_concentration():
         S.ClusterExpansionProcessor(sub, np.eye(3, dtype=int), np.zeros(sub.num_corr_functions), use_concentration=True)
     with pytest.raises(NotImplementedError, match="use_concentration"):
         S.CompositeProcessor(sub, np.eye(3, dtype=int), use_concentration=True)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference --config 2`: the CPU arm alone, same JSON shape (no GPU needed)"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "2", "--steps", "1",
+                        "--warmup", "0", "--ref-seconds", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "steps/s" and line["value"] > 0 and line["higher_is_better"]
+    assert line["cpu_baseline"]["kind"] in ("reference", "oracle") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["baseline_config"] == 2 and line["gpu_launches"] == 0
