@@ -576,10 +576,10 @@ class Sampler:
         eng = self.engine
         with torch.cuda.device(eng.device):
             return self._run(nsteps, initial_occupancies, thin_by, stream_chunk, stream_file, keep_last_chunk,
-                             swmr_mode, max_chunk_bytes, pipeline_chunks, block)
+                             swmr_mode, max_chunk_bytes, pipeline_chunks, block, progress)
 
     def _run(self, nsteps, initial_occupancies, thin_by, stream_chunk, stream_file, keep_last_chunk, swmr_mode,
-             max_chunk_bytes, pipeline_chunks, block):
+             max_chunk_bytes, pipeline_chunks, block, progress=False):
         import torch
         eng = self.engine
         if stream_chunk > 0:
@@ -666,6 +666,13 @@ class Sampler:
 
         temperature = self._temperature.copy()
         done, ci, pending = 0, 0, None
+        bar = None
+        if progress:      # sampler.py:190-194 shows steps per walker; here the bar advances launch by launch
+            try:
+                from tqdm import tqdm
+                bar = tqdm(total=S * thin_by, desc=f"Sampling {self.nwalkers} walker(s) on {eng.device}", unit="step")
+            except ImportError:
+                bar = None
         while done < S:
             n = min(nmax, S - done)
             slot = slots[(ci + phase) % nslots]
@@ -711,6 +718,11 @@ class Sampler:
             pending = (host, pooled, n, ev_copy)
             done += n
             ci += 1
+            if bar is not None:
+                bar.update(n * thin_by)
+        if bar is not None:
+            bar.update(S * thin_by - bar.n)
+            bar.close()
         if not async_all:
             self.samples.resolve_deferred()
         self._slot_phase = (ci + phase) % nslots     # slot the next launch would take
@@ -782,17 +794,19 @@ class Sampler:
 
     def anneal(self, temperatures, mcmc_steps, initial_occupancies=None, thin_by=1, progress=False,
                stream_chunk=0, stream_file=None, swmr_mode=True):
-        """sampler.py:303-384."""
+        """sampler.py:303-384: one ``run`` per temperature, each starting from the last configuration of the
+        previous one; everything goes to the same container (or, streaming, to the same file)."""
         if temperatures[0] < temperatures[-1]:
             raise ValueError("End temperature is greater than start "
                              f"temperature {temperatures[-1]:.2f} > {temperatures[0]:.2f}.")
-        for k in self.mckernels:
-            k.temperature = temperatures[0]
-        self.run(mcmc_steps, initial_occupancies=initial_occupancies, thin_by=thin_by)
-        for t in temperatures[1:]:
+        for i, t in enumerate(temperatures):
             for k in self.mckernels:
                 k.temperature = t
-            self.run(mcmc_steps, thin_by=thin_by)
+            self.run(mcmc_steps, initial_occupancies=initial_occupancies if i == 0 else None, thin_by=thin_by,
+                     progress=progress, stream_chunk=stream_chunk, stream_file=stream_file, swmr_mode=swmr_mode,
+                     keep_last_chunk=True)
+        if stream_chunk > 0:       # if streaming to file was done then clear the samples now (sampler.py:382-384)
+            self.clear_samples()
 
     def current_occupancies(self):
         """int32 ``[W, N]`` host copy of the walkers' current occupancies."""

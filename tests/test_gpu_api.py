@@ -231,3 +231,23 @@ def test_engine_limits_fail_loudly(cuda_device):
     coefs = np.zeros(sub.num_corr_functions)
     with pytest.raises((RuntimeError, ValueError), match="stride"):
         S.Ensemble(S.ClusterExpansionProcessor(sub, scm, coefs)).compute_feature_vector(np.zeros(8, dtype=np.int32))
+
+
+def test_anneal_streams_every_temperature_to_one_file(cuda_device, tmp_path):
+    """Sampler.anneal(..., stream_chunk, stream_file) (sampler.py:303-384): one file, all temperatures, the container
+    cleared at the end; progress=True only draws a bar"""
+    from smol_b200.container import SampleContainer
+    W, thin = 8, 32
+    a, occ0 = _fcc_sampler(W)
+    a.anneal([1500.0, 1000.0, 500.0], 32 * 6, occ0, thin_by=thin)
+    want = _traces(a.samples)
+    temps = a.samples.get_trace_value("temperature", flat=False)
+    b, _ = _fcc_sampler(W)
+    path = str(tmp_path / "anneal.lmc")
+    b.anneal([1500.0, 1000.0, 500.0], 32 * 6, occ0, thin_by=thin, stream_chunk=32 * 3, stream_file=path, progress=True)
+    assert b.samples.num_samples == 0
+    loaded = SampleContainer.from_hdf5(path, ensemble=b.ensemble)
+    assert loaded.num_samples == 18 and loaded.total_mc_steps == 3 * 32 * 6
+    np.testing.assert_array_equal(loaded.get_occupancies(flat=False), want["occupancy"])
+    np.testing.assert_array_equal(loaded.get_trace_value("temperature", flat=False), temps)
+    assert sorted(set(temps[:, 0, 0].tolist())) == [500.0, 1000.0, 1500.0]
