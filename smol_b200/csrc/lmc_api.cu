@@ -984,6 +984,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   a.off_dist = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
   a.walker_smem = a.off_dist + (dist ? ((3 * m.F * 8 + 15) & ~15) : 0);   // distance processor: vector, delta, new distances
+  a.off_tfc = a.walker_smem;
+  if (c->usher == LMC_USHER_TABLEFLIP) a.walker_smem += (6 * LMC_MAX_TABLE_FLIPS + 2) * 8;
   // Wang-Landau flips: landing zone of the next step's records / segment entries
   a.off_pref = a.walker_smem;
   if (c->kernel == LMC_KERNEL_WANGLANDAU && c->usher == LMC_USHER_FLIP && !dist) a.walker_smem += 2 * (m.Rstride * 8 + m.Sstride * 16);   // double buffered

@@ -727,6 +727,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
   // costs a few shuffles instead of a redundant Philox evaluation in all lanes.
   uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [G] x (sl<<24 | pos, site, word z, float log u)
   int bphase = 0;
+  double* tfc = reinterpret_cast<double*>(priv + a.off_tfc);   // table-flip proposal tables of the walker's current counts
+  bool tfc_valid = false;
   // latency-bound variants (few resident warps: Wang-Landau flips): records of step t + 1 are fetched during step t
   constexpr bool PREF = WLMODE && USHER == LMC_USHER_FLIP && !DIST;
   // (asynchronous copies into the walker's slab, each lane its own records and segment entry: a register
@@ -777,32 +779,60 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       U4 r1blk{0, 0, 0, 0};
       int ms_toggled = 0;   // flips of chained swaps whose plane bits are temporarily toggled
       int tf_idx = -1;
-      double tfw[2 * LMC_MAX_TABLE_FLIPS];
-      double tfsum = 0.0;
       int nd[LMC_MAX_DIMS];
       if (USHER == LMC_USHER_TABLEFLIP) {
         // TableFlip.propose_step, mcusher.py:553-639
         r1blk = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 1u, wid, k0, k1);
         for (int d = 0; d < m.tfD; ++d)
           nd[d] = m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
-        bool do_swap = u01(r.x) < m.tf_sw;
-        if (!do_swap) {
-          tfsum = tf_masked_weights<G>(m, nd, tfw, g, gmask);
-          if (!(tfsum > 0.0)) do_swap = true;
+        if (!tfc_valid) {
+          // The direction weights (utils/math.py:832-867), their cumulative probabilities and the a-priori factor of
+          // every direction (mcusher.py:656-711) depend on the species COUNTS only, which change when a table flip is
+          // accepted: evaluated here once per such change (the same expressions, in the same order) and kept in the
+          // walker's slab -- [weights 16][cumulative 16][log a-priori factor 16][sum].
+          double tw[2 * LMC_MAX_TABLE_FLIPS];
+          const double sum = tf_masked_weights<G>(m, nd, tw, g, gmask);
+          group_sync<G>(gmask);
+          if (g == 0) {
+            double cum = 0.0;
+            for (int i = 0; i < 2 * m.tfNF; ++i) {
+              cum += tw[i] / sum;
+              tfc[i] = tw[i];
+              tfc[2 * LMC_MAX_TABLE_FLIPS + i] = cum;
+            }
+            tfc[6 * LMC_MAX_TABLE_FLIPS] = sum;
+          }
+          for (int i = 0; i < 2 * m.tfNF; ++i) {   // uniform over the group
+            double lfi = 0.0;
+            if (sum > 0.0 && tw[i] > 0.0) {
+              const int sgn_i = (i & 1) ? -1 : 1;
+              const int* urow_i = m.tf_table[i >> 1];
+              int nn[LMC_MAX_DIMS];
+              for (int d = 0; d < m.tfD; ++d) nn[d] = nd[d] + sgn_i * urow_i[d];
+              double tw2[2 * LMC_MAX_TABLE_FLIPS];
+              const double sum2 = tf_masked_weights<G>(m, nn, tw2, g, gmask);
+              const double p_now = (1.0 - m.tf_sw) * tw[i] / sum;
+              const double p_next = (1.0 - m.tf_sw) * tw2[i ^ 1] / sum2;
+              lfi = log(p_next / p_now);
+              for (int d = 0; d < m.tfD; ++d)
+                if (urow_i[d] != 0) lfi += __ldg(m.lgam + nd[d]) - __ldg(m.lgam + nn[d]);   // ln n! table (gammaln(n+1))
+            }
+            if (g == 0) tfc[4 * LMC_MAX_TABLE_FLIPS + i] = lfi;
+          }
+          group_sync<G>(gmask);
+          tfc_valid = true;
         }
+        const double tfsum = tfc[6 * LMC_MAX_TABLE_FLIPS];
+        const bool do_swap = u01(r.x) < m.tf_sw || !(tfsum > 0.0);
         if (do_swap) {
           usher = LMC_USHER_SWAP;
           q0 = r1blk.x; q1 = r1blk.y; q2 = r1blk.z;
         } else {
           // choose_section_from_partition, utils/math.py:870-893
           const double u = u01(r.y);
-          double cum = 0.0;
           tf_idx = 2 * m.tfNF - 1;
-          for (int i = 0; i < 2 * m.tfNF; ++i) {
-            const double p = tfw[i] / tfsum;
-            cum += p;
-            if (cum > u && p > 0.0) { tf_idx = i; break; }
-          }
+          for (int i = 0; i < 2 * m.tfNF; ++i)
+            if (tfc[2 * LMC_MAX_TABLE_FLIPS + i] > u && tfc[i] > 0.0) { tf_idx = i; break; }
         }
       }
       if (COMP) {
@@ -971,17 +1001,8 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           }
           d0 = d1;
         }
-        // compute_log_priori_factor, mcusher.py:656-711
-        const double p_now = (1.0 - m.tf_sw) * tfw[tf_idx] / tfsum;
-        int nn[LMC_MAX_DIMS];
-        for (int d = 0; d < m.tfD; ++d) nn[d] = nd[d] + sgn * urow[d];
-        double tfw2[2 * LMC_MAX_TABLE_FLIPS];
-        const double sum2 = tf_masked_weights<G>(m, nn, tfw2, g, gmask);
-        const double p_next = (1.0 - m.tf_sw) * tfw2[tf_idx ^ 1] / sum2;
-        double lf = log(p_next / p_now);
-        for (int d = 0; d < m.tfD; ++d)
-          if (urow[d] != 0) lf += __ldg(m.lgam + nd[d]) - __ldg(m.lgam + nn[d]);   // ln n! table (gammaln(n+1))
-        st.log_priori = lf;
+        // compute_log_priori_factor, mcusher.py:656-711 (tabulated per direction above)
+        st.log_priori = tfc[4 * LMC_MAX_TABLE_FLIPS + tf_idx];
       }
 
       // ------------------------------ evaluate ------------------------------------------
@@ -1249,6 +1270,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           }
         }
         enth += dH;
+        if (USHER == LMC_USHER_TABLEFLIP && tf_idx >= 0) tfc_valid = false;   // the species counts changed
         if (!WLMODE && a.bias_mode && g == 0) {   // read again after the step's final sync
           bstate[0] += dbias;
           for (int r = 0; r < a.bias_rows; ++r) {

@@ -121,6 +121,7 @@ struct RunArgs {
   int wpb;            // walkers per block
   int walker_smem;    // bytes of shared memory per walker
   int off_feat, off_stash, off_cnt, off_plane, off_ring, off_eidx, off_lists, off_bias;  // offsets inside a walker's shared-memory slab
+  int off_tfc;        // table-flip usher: [weights][cumulative probabilities][log a-priori factors][sum] of the current counts
   int off_pref;       // Wang-Landau flips: records and segment entries of the next step (asynchronous prefetch)
   int off_wl;         // Wang-Landau: [entropy nb][histogram nb] of the walker in its slab, -1 = kept in global memory
   unsigned long long* stats;  // [2] accepted / attempted step totals (device counters; kernel selection feedback)
