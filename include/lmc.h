@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define LMC_ABI_VERSION 15
+#define LMC_ABI_VERSION 16
 #define LMC_MAX_CLUSTER_SITES 4 /* sites per cluster (record = 3 other sites + class) */
 #define LMC_MAX_SUBLATTICES 8
 #define LMC_MAX_CODES 8       /* species codes per sublattice */
@@ -248,6 +248,11 @@ typedef struct LmcRunConfig {
      = dH_step + (H_k' - H_current) (base.py:612-622).  Classic Metropolis kernels; both may be NULL. */
   const uint8_t* walker_mask_dev;   /* [W] */
   const double* accept_offset_dev;  /* [W] */
+  /* optional workspace of the speculative kernel (ABI 16): W x lmc_model_info()[4] bytes.  Non-NULL (and info[4] > 0):
+     every active site keeps the species codes its merged records gather as packed "environment words" here, rebuilt
+     from occ_dev at the start of every call and kept current by accepted steps, so a rejected step reads one word per
+     flip and lane instead of three occupancy bytes per record.  Same chains, same arithmetic; NULL: gathers. */
+  void* spec_env_dev;
 } LmcRunConfig;
 
 int lmc_version(void);
@@ -259,7 +264,8 @@ int lmc_model_destroy(LmcModel* model);
 int lmc_model_num_features(const LmcModel* model);
 /* info[0] = 1 if the Ewald matrix factorises as M[i,j] = q_i q_j K[site_i, site_j] (potential cache usable),
  * info[1] = speculative-kernel tables built, info[2] = bytes of the staged table blob, info[3] = records per site
- * of the speculative kernel; entries beyond `n` are not written */
+ * of the speculative kernel, info[4] = bytes per walker of LmcRunConfig.spec_env_dev (0: environment words not
+ * available for this model); entries beyond `n` are not written */
 int lmc_model_info(const LmcModel* model, int32_t* info, int n);
 
 /* int32 [W][N] <-> int8 [W][row_stride] */
@@ -300,6 +306,13 @@ int lmc_run(const LmcModel* model, const LmcRunConfig* cfg, void* stream);
  * record bytes}; dtab_out [NC][L] doubles and rec_out [N][records] x 8 bytes are filled when large enough */
 int lmc_spec_tables_host(const LmcModelDesc* desc, int32_t* info, double* dtab_out, int64_t dtab_cap,
                          uint8_t* rec_out, int64_t rec_cap);
+/* host-only: environment-word tables of the speculative kernel (LmcRunConfig.spec_env_dev).  info[8] = {built, bits
+ * per code b, records per lane, padded records per lane P, wide (64-bit lane chunks), active sites A, reverse entries
+ * per site R, pair table built}; tb_out [N][4][P] u16 table bases in lane order, rev_out [A][R] u32 (gathering
+ * active site | bit << 16, 0xffffffff = none), pair_out [A][A][4] x (u32, or u64 when wide) slot masks of the column
+ * site inside the row site's words; each filled when large enough (capacities in elements / bytes for pair_out) */
+int lmc_spec_env_host(const LmcModelDesc* desc, int32_t* info, uint16_t* tb_out, int64_t tb_cap, uint32_t* rev_out,
+                      int64_t rev_cap, uint8_t* pair_out, int64_t pair_cap);
 
 /* Distance processor state of every walker: features_dev [W][F] holds the EXTENSIVE features on entry
  * (lmc_full_features) and the distance vector on return; vector_dev [W][F] <- features / supercell size;
@@ -320,6 +333,8 @@ int lmc_ewald_site_kernel(const double* cart_dev, int num_sites, const int32_t* 
 
 /* number of kernel launches issued by this library since load (for bench accounting) */
 int64_t lmc_launch_count(void);
+/* how many of them were environment-word variants of the speculative kernel (LmcRunConfig.spec_env_dev) */
+int64_t lmc_env_launch_count(void);
 
 #ifdef __cplusplus
 }

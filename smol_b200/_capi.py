@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LMC_ABI_VERSION = 15
+LMC_ABI_VERSION = 16
 LMC_MAX_CLUSTER_SITES = 4
 LMC_MAX_SUBLATTICES = 8
 LMC_MAX_CODES = 8
@@ -110,14 +110,14 @@ class LmcRunConfig(C.Structure):
         ("ms_usher", C.c_int32), ("ms_num", C.c_int32), ("ms_len", C.c_int32 * LMC_MAX_COMPOSITE),
         ("ms_cum", C.c_double * LMC_MAX_COMPOSITE),
         ("wl", LmcWangLandau),
-        ("walker_mask_dev", _P), ("accept_offset_dev", _P),
+        ("walker_mask_dev", _P), ("accept_offset_dev", _P), ("spec_env_dev", _P),
     ]
 
 
 EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
-    "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_spec_tables_host", "lmc_model_info",
+    "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_env_launch_count", "lmc_spec_tables_host", "lmc_spec_env_host", "lmc_model_info",
     "lmc_ewald_field", "lmc_bias_init", "lmc_ewald_site_kernel", "lmc_distance_init", "lmc_full_features_field",
 )
 
@@ -159,7 +159,10 @@ def load():
                                           C.c_double, C.c_double, _P, _P]
     lib.lmc_distance_init.argtypes = [_P, C.c_int, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P]
     lib.lmc_launch_count.restype = C.c_int64
+    lib.lmc_env_launch_count.restype = C.c_int64
     lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
+    lib.lmc_spec_env_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64,
+                                      _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:
         raise RuntimeError("liblmc.so ABI version mismatch; rebuild with python -m smol_b200.build")
     _LIB = lib

@@ -64,6 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     jobs.append((os.path.join(CSRC, "lmc_wl_inst.cu"), os.path.join(objdir, "lmc_wl.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst.cu"), os.path.join(objdir, "lmc_spec.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst2.cu"), os.path.join(objdir, "lmc_spec2.o"), [], force))
+    jobs.append((os.path.join(CSRC, "lmc_spec_inst3.cu"), os.path.join(objdir, "lmc_spec3.o"), [], force))
     log = []
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:
         for cmd, r in ex.map(_compile, jobs):

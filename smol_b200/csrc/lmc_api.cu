@@ -20,6 +20,7 @@ using namespace lmc;
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_env_launches{0};   // launches of the environment-word variants (tests / diagnostics)
 
 static int fail(const std::string& msg) {
   g_err = msg;
@@ -67,6 +68,7 @@ extern "C" int lmc_version(void) { return LMC_ABI_VERSION; }
 extern "C" const char* lmc_last_error(void) { return g_err.c_str(); }
 extern "C" int lmc_row_stride(int n) { return (n + 16) & ~15; }   // always at least one zero pad byte behind the row
 extern "C" int64_t lmc_launch_count(void) { return g_launches.load(); }
+extern "C" int64_t lmc_env_launch_count(void) { return g_env_launches.load(); }
 extern "C" int lmc_model_num_features(const LmcModel* m) { return m ? m->dm.F : -1; }
 
 extern "C" int lmc_model_destroy(LmcModel* m) {
@@ -373,6 +375,97 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
   }
 }
 
+// Environment words of the speculative kernel (lmc_spec.cuh, ENV variants).  Every ACTIVE site keeps the species codes
+// its merged records gather as one packed word per lane of the 4-lane step group: record i of lane l (records
+// 2 (l + 4 q) + e, i = 2 q + e, the order spec_rec2 walks them) owns the bit field [i * 3b, (i + 1) * 3b) of the lane's
+// chunk, slot j of the record the b bits at j * b inside it (b = bits per species code).  A rejected step then costs one
+// chunk load per flip instead of three byte gathers per record; an ACCEPTED flip of site s xors (old ^ new) into the
+// slots of every site that gathers s (reverse map).  The second flip of a swap sees the first one applied through a
+// per-pair slot mask (adjacency ordinal + mask table), the PATCH of the gather variant.
+struct EnvTables {
+  int ok = 0, b = 0, nrl = 0, nrlp = 0, wide = 0, NA = 0, RV = 0, pair_ok = 0;
+  std::vector<uint16_t> tb;              // [N][4][nrlp] table base of the lane's i-th record
+  // the same lists deduplicated (translation-equivalent sites share theirs): cls[site] -> row of tbc; staged to shared
+  // memory with the table blob while there are at most 256 classes / 8 KB of lists (ncls == 0: not built)
+  int ncls = 0;
+  std::vector<uint8_t> cls;              // [N]
+  std::vector<uint16_t> tbc;             // [ncls][4][nrlp]
+  std::vector<uint32_t> rev;             // [NA][RV] active index of the gathering site | bit position << 16; ~0 = none
+  // [NA][NA][4] x (u32 | u64 when wide): lowest slot bits, per lane chunk, where the COLUMN site sits among the codes the
+  // ROW site gathers (all zero for pairs that do not see each other); swaps only, built while it stays below 64 MB
+  std::vector<unsigned char> pair;
+};
+
+static void build_env_tables(const LmcModelDesc* d, const SpecTables& sp, EnvTables& ev) {
+  ev = EnvTables();
+  if (!sp.ok || getenv("LMC_SPEC_ENV_OFF")) return;
+  const int N = d->num_sites, NQ = sp.NQ, NC = sp.NC;
+  if (NC > 4) return;                                   // kernels are instantiated for 1 and 2 bits per code
+  const int b = NC <= 2 ? 1 : 2, fb = 3 * b;
+  const int nrl = NQ / 4;                               // NQ is a multiple of 8
+  if (nrl * fb > 64) return;
+  const int wide = nrl * fb > 32 ? 1 : 0;
+  const int lane_bits = wide ? 64 : 32;
+  const int NA = d->sl_site_off[d->num_sublattices];
+  if (NA <= 0 || NA > 65535) return;
+  std::vector<int> aidx(N, -1);
+  for (int a = 0; a < NA; ++a) {
+    const int s = d->sl_sites[a];
+    if (s < 0 || s >= N || aidx[s] >= 0) return;        // overlapping sublattices: not served
+    aidx[s] = a;
+  }
+  const int nrlp = (nrl + 7) & ~7;
+  const size_t pair_el = wide ? 8 : 4;
+  const bool want_pair = (size_t)NA * NA * 4 * pair_el <= (size_t(64) << 20);
+  ev.tb.assign((size_t)N * 4 * nrlp, 0);
+  if (want_pair) ev.pair.assign((size_t)NA * NA * 4 * pair_el, 0);
+  std::vector<std::vector<uint32_t>> rev(NA);
+  const uint32_t* rec = reinterpret_cast<const uint32_t*>(sp.rec.data());
+  for (int k = 0; k < N; ++k)
+    for (int l = 0; l < 4; ++l)
+      for (int i = 0; i < nrl; ++i) {
+        const int r = 2 * (l + 4 * (i >> 1)) + (i & 1);
+        const uint32_t x = rec[((size_t)k * NQ + r) * 2], y = rec[((size_t)k * NQ + r) * 2 + 1];
+        ev.tb[((size_t)k * 4 + l) * nrlp + i] = (uint16_t)(y >> 16);
+        if (aidx[k] < 0) continue;
+        const int site[3] = {(int)(x & 0xffffu), (int)(x >> 16), (int)(y & 0xffffu)};
+        for (int j = 0; j < 3; ++j) {
+          const int s = site[j];
+          if (s >= N || aidx[s] < 0) continue;          // pad slot or a site that never changes
+          const int bit = i * fb + j * b;
+          rev[aidx[s]].push_back((uint32_t)aidx[k] | ((uint32_t)(l * lane_bits + bit) << 16));
+          if (want_pair) {
+            unsigned char* p = ev.pair.data() + (((size_t)aidx[k] * NA + aidx[s]) * 4 + l) * pair_el;
+            if (wide) { unsigned long long v; memcpy(&v, p, 8); v |= 1ull << bit; memcpy(p, &v, 8); }
+            else { uint32_t v; memcpy(&v, p, 4); v |= 1u << bit; memcpy(p, &v, 4); }
+          }
+        }
+      }
+  size_t rv = 1;
+  for (int a = 0; a < NA; ++a) rv = std::max(rv, rev[a].size());
+  ev.RV = (int)((rv + 31) & ~size_t(31));
+  ev.rev.assign((size_t)NA * ev.RV, 0xffffffffu);
+  for (int a = 0; a < NA; ++a) std::copy(rev[a].begin(), rev[a].end(), ev.rev.begin() + (size_t)a * ev.RV);
+  {
+    std::map<std::vector<uint16_t>, int> seen;
+    std::vector<uint8_t> cls(N, 0);
+    std::vector<uint16_t> tbc;
+    bool fits = true;
+    for (int k = 0; k < N && fits; ++k) {
+      std::vector<uint16_t> row(ev.tb.begin() + (size_t)k * 4 * nrlp, ev.tb.begin() + (size_t)(k + 1) * 4 * nrlp);
+      auto it = seen.find(row);
+      if (it == seen.end()) {
+        if (seen.size() >= 256 || (seen.size() + 1) * row.size() * 2 > 8 * 1024) { fits = false; break; }
+        it = seen.emplace(row, (int)seen.size()).first;
+        tbc.insert(tbc.end(), row.begin(), row.end());
+      }
+      cls[k] = (uint8_t)it->second;
+    }
+    if (fits) { ev.ncls = (int)seen.size(); ev.cls = std::move(cls); ev.tbc = std::move(tbc); }
+  }
+  ev.ok = 1; ev.b = b; ev.nrl = nrl; ev.nrlp = nrlp; ev.wide = wide; ev.NA = NA; ev.pair_ok = want_pair ? 1 : 0;
+}
+
 // host-only: build the tables of the speculative kernel for a model description (tests / diagnostics)
 // info = {ok, NC, L, NQ, nblocks, merged, table bytes, record bytes}
 extern "C" int lmc_spec_tables_host(const LmcModelDesc* d, int32_t* info, double* dtab_out, int64_t dtab_cap,
@@ -388,6 +481,27 @@ extern "C" int lmc_spec_tables_host(const LmcModelDesc* d, int32_t* info, double
   info[6] = (int32_t)(sp.dtab.size() * 8); info[7] = (int32_t)sp.rec.size();
   if (dtab_out && (int64_t)sp.dtab.size() <= dtab_cap) memcpy(dtab_out, sp.dtab.data(), sp.dtab.size() * 8);
   if (rec_out && (int64_t)sp.rec.size() <= rec_cap) memcpy(rec_out, sp.rec.data(), sp.rec.size());
+  return 0;
+}
+
+// host-only: environment-word tables of a model description (tests / diagnostics)
+// info = {ok, bits per code, records per lane, padded records per lane, wide, active sites, reverse entries per site, pair table built}
+extern "C" int lmc_spec_env_host(const LmcModelDesc* d, int32_t* info, uint16_t* tb_out, int64_t tb_cap, uint32_t* rev_out,
+                                 int64_t rev_cap, uint8_t* pair_out, int64_t pair_cap) {
+  if (!d || !info) return fail("null argument");
+  std::vector<OrbDev> orbs;
+  std::vector<double> tabA;
+  bool kone = true;
+  if (host_orbits(d, orbs, tabA, kone)) return -1;
+  SpecTables sp;
+  build_spec_tables(d, orbs, tabA, kone, sp);
+  EnvTables ev;
+  build_env_tables(d, sp, ev);
+  info[0] = ev.ok; info[1] = ev.b; info[2] = ev.nrl; info[3] = ev.nrlp; info[4] = ev.wide; info[5] = ev.NA; info[6] = ev.RV;
+  info[7] = ev.pair_ok;
+  if (tb_out && (int64_t)ev.tb.size() <= tb_cap) memcpy(tb_out, ev.tb.data(), ev.tb.size() * 2);
+  if (rev_out && (int64_t)ev.rev.size() <= rev_cap) memcpy(rev_out, ev.rev.data(), ev.rev.size() * 4);
+  if (pair_out && (int64_t)ev.pair.size() <= pair_cap) memcpy(pair_out, ev.pair.data(), ev.pair.size());
   return 0;
 }
 
@@ -441,6 +555,7 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
   const int tabA_len = (int)tabA.size();
   m.tabA_len = tabA_len;
   std::vector<double> qtab;
+  std::vector<double2> qd_host;   // (charge, diagonal) per (site, code) of a factorised Ewald matrix
   // Ewald.  Generic form: keep the TRANSPOSE so that the reference's column gathers become row
   // gathers.  Ewald matrices are charge products times a geometric site kernel,
   // M[i,j] = q_i q_j K[site_i, site_j] (pymatgen EwaldSummation), which turns the two strided E-long
@@ -516,6 +631,7 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
           if (e >= 0) qd[k * m.ewW + c] = make_double2(q[e], dg[e]);
         }
       UP(double2, qd.data(), qd.size(), m.ewQD);
+      qd_host = qd;
       UP(double, K.data(), N * N, m.ewK);
       UP(double, q.data(), E, m.ewQ);
       UP(double, dg.data(), E, m.ewD);
@@ -536,6 +652,8 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
   const std::vector<double>& dtab = sp.dtab;
   const std::vector<unsigned char>& sprec = sp.rec;
   m.spOK = sp.ok; m.spNC = sp.NC; m.spL = sp.L; m.spNQ = sp.NQ; m.spSb = sp.NQ * 8;
+  EnvTables ev;
+  build_env_tables(d, sp, ev);
   // blob: cls (nCls + 1 entries, the last is the all-zero padding class) | tabA | nat | orb
   {
     const int C = m.nCls + 1;
@@ -546,7 +664,11 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     m.off_orb = (int)off; off += ((size_t)m.nOrb * sizeof(OrbDev) + 15) & ~size_t(15);
     m.off_qtab = (int)off; off += ((size_t)std::max<size_t>(qtab.size(), 2) * 8 + 15) & ~size_t(15);
     m.off_dtab = (int)off; off += (dtab.size() * 8 + 15) & ~size_t(15);
-    m.blob_bytes = (int)off;
+    // environment words: per-class table-base lists and the class of every site (speculative kernels only)
+    m.blob_bytes = (int)off;      // what every kernel but the environment-word variants stages
+    m.off_envtb = (int)off; off += (ev.tbc.size() * 2 + 15) & ~size_t(15);
+    m.off_envcls = (int)off; off += (ev.cls.size() + 15) & ~size_t(15);
+    m.blob_env_bytes = (int)off;
     std::vector<unsigned char> blob(off, 0);
     uint32_t* cls = reinterpret_cast<uint32_t*>(blob.data() + off_cls);
     for (int c = 0; c < m.nCls; ++c) {
@@ -567,10 +689,23 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     memcpy(blob.data() + m.off_orb, orbs.data(), (size_t)m.nOrb * sizeof(OrbDev));
     if (!qtab.empty()) memcpy(blob.data() + m.off_qtab, qtab.data(), qtab.size() * 8);
     if (!dtab.empty()) memcpy(blob.data() + m.off_dtab, dtab.data(), dtab.size() * 8);
+    if (ev.ncls) {
+      memcpy(blob.data() + m.off_envtb, ev.tbc.data(), ev.tbc.size() * 2);
+      memcpy(blob.data() + m.off_envcls, ev.cls.data(), ev.cls.size());
+    }
     UP(unsigned char, blob.data(), blob.size(), m.blob);
     if (m.spOK) UP(unsigned char, sprec.data(), sprec.size(), m.sp_rec);
     m.spFtab = nullptr;
     if (m.spOK && !sp.ftab.empty()) UP(double, sp.ftab.data(), sp.ftab.size(), m.spFtab);
+    m.envNCls = ev.ncls;
+    m.envOK = ev.ok; m.envB = ev.b; m.envNRL = ev.nrl; m.envNRLP = ev.nrlp; m.envWide = ev.wide; m.envNA = ev.NA;
+    m.envRV = ev.RV;
+    m.envTb = nullptr; m.envRev = nullptr; m.envPair = nullptr;
+    if (ev.ok) {
+      UP(uint16_t, ev.tb.data(), ev.tb.size(), m.envTb);
+      UP(uint32_t, ev.rev.data(), ev.rev.size(), m.envRev);
+      if (ev.pair_ok) UP(unsigned char, ev.pair.data(), ev.pair.size(), m.envPair);
+    }
   }
   UP(OrbDev, orbs.data(), orbs.size(), mdl->orb_dev);
   UP(double, d->natural_parameters, m.F, mdl->nat_dev);
@@ -657,6 +792,31 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       m.sl_first[s] = contig ? d->sl_sites[a] : -1;
     }
     m.sl_off[m.nSl] = d->sl_site_off[m.nSl];
+    // per-sublattice chemical-potential / (charge, diagonal) tables (see DevModel): bitwise identical rows only
+    m.muC = m.muW > 0 && m.muW <= LMC_MAX_CODES;
+    m.qdC = m.E > 0 && m.ewK != nullptr && m.ewW <= LMC_MAX_CODES;
+    memset(m.mu_c, 0, sizeof(m.mu_c));
+    memset(m.qc_c, 0, sizeof(m.qc_c));
+    memset(m.qg_c, 0, sizeof(m.qg_c));
+    for (int s = 0; s < m.nSl; ++s) {
+      const int a = d->sl_site_off[s], b = d->sl_site_off[s + 1];
+      if (b <= a) continue;
+      const int s0 = d->sl_sites[a];
+      for (int j = a; j < b; ++j) {
+        const int k = d->sl_sites[j];
+        if (m.muC)
+          for (int c = 0; c < m.muW; ++c)
+            if (memcmp(&d->mu_table[(size_t)k * m.muW + c], &d->mu_table[(size_t)s0 * m.muW + c], 8) != 0) m.muC = 0;
+        if (m.qdC)
+          for (int c = 0; c < m.ewW; ++c)
+            if (memcmp(&qd_host[(size_t)k * m.ewW + c], &qd_host[(size_t)s0 * m.ewW + c], 16) != 0) m.qdC = 0;
+      }
+      for (int c = 0; c < LMC_MAX_CODES; ++c) {
+        if (m.muC && c < m.muW) m.mu_c[s][c] = d->mu_table[(size_t)s0 * m.muW + c];
+        if (m.qdC && c < m.ewW) { m.qc_c[s][c] = qd_host[(size_t)s0 * m.ewW + c].x; m.qg_c[s][c] = qd_host[(size_t)s0 * m.ewW + c].y; }
+      }
+    }
+    if (getenv("LMC_COMPACT_TABLES_OFF")) m.muC = m.qdC = 0;
     int pw = 0, le = 0;
     for (int s = 0; s < m.nSl; ++s) {
       int maxcode = 0;
@@ -698,8 +858,9 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
 extern "C" int lmc_model_info(const LmcModel* mdl, int32_t* info, int n) {
   if (!mdl || !info) return fail("null argument");
   const DevModel& m = mdl->dm;
-  const int32_t v[4] = {m.E > 0 && m.ewK != nullptr, m.spOK, m.blob_bytes, m.spNQ};
-  for (int i = 0; i < n && i < 4; ++i) info[i] = v[i];
+  const int32_t v[5] = {m.E > 0 && m.ewK != nullptr, m.spOK, m.blob_bytes, m.spNQ,
+                        m.envOK ? m.envNA * (m.envWide ? 32 : 16) : 0};
+  for (int i = 0; i < n && i < 5; ++i) info[i] = v[i];
   return 0;
 }
 
@@ -999,7 +1160,12 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   a.dist_grp_off = c->dist_group_off_dev; a.dist_grp_idx = c->dist_group_idx_dev; a.dist_grp_diam = c->dist_group_diam_dev;
   a.dist_vec = c->dist_vector_dev;
   // staged tables: the speculative kernel takes the whole blob, the classic kernels stop before its difference table
-  const size_t blob = ((size_t)(use_spec ? m.blob_bytes : m.off_dtab) + 15) & ~size_t(15);
+  // environment words: caller's workspace + tables built + the default four-lane rank-select variant
+  bool spec_env = use_spec && c->spec_env_dev != nullptr && m.envOK && spec_sg == 4 && !spec_lists &&
+                  (c->usher == LMC_USHER_FLIP || m.envPair != nullptr);
+  if (const char* e = getenv("LMC_SPEC_ENV")) spec_env = spec_env && atoi(e) != 0;
+  a.env = spec_env ? reinterpret_cast<uint32_t*>(c->spec_env_dev) : nullptr;
+  const size_t blob = ((size_t)(use_spec ? (spec_env ? m.blob_env_bytes : m.blob_bytes) : m.off_dtab) + 15) & ~size_t(15);
   size_t smem = 0;
   if (auto_threads && relaxed) {
     // shared memory limits residency here: take the block size with the most resident walkers per SM
@@ -1074,7 +1240,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
   const int ewmode = !ewald ? 0 : (field ? 2 : 1);   // Ewald path of the classic kernels
   spec_wide = spec_wide && threads == 448;
-  if (use_spec && (field || spec_wide)) rc = launch_spec_x(m, a, m.kone != 0, c->usher, field, spec_wide, lc);
+  if (spec_env) { rc = launch_spec_env(m, a, m.kone != 0, c->usher, field, spec_wide, lc); g_env_launches++; }
+  else if (use_spec && (field || spec_wide)) rc = launch_spec_x(m, a, m.kone != 0, c->usher, field, spec_wide, lc);
   else if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, spec_lists, lc);
   else if (dist) rc = launch_run_dist(m, a, m.kone != 0, c->usher, lc);
   else switch (G) {

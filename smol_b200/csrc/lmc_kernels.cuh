@@ -367,6 +367,13 @@ __device__ __forceinline__ void ewald_cache_set(const DevModel& m, void* ecache,
 __device__ __forceinline__ double2 ewald_qd(const DevModel& m, int site, int code) {
   return __ldg(m.ewQD + site * m.ewW + code);
 }
+// the same for a site of ACTIVE sublattice `sl` (per-sublattice table in the parameter bank when the rows agree)
+__device__ __forceinline__ double2 ewald_qd(const DevModel& m, int site, int code, int sl) {
+  return m.qdC ? make_double2(m.qc_c[sl][code], m.qg_c[sl][code]) : __ldg(m.ewQD + site * m.ewW + code);
+}
+__device__ __forceinline__ double mu_of(const DevModel& m, int site, int code, int sl) {
+  return m.muC ? m.mu_c[sl][code] : __ldg(m.mu + site * m.muW + code);
+}
 
 template <int G>
 __device__ __forceinline__ int select_pos_scan(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,
@@ -1054,7 +1061,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
 #pragma unroll
         for (int f = 0; f < MF; ++f)
           if (f < st.n)
-            dmu += __ldg(m.mu + st.site[f] * m.muW + st.newc[f]) - __ldg(m.mu + st.site[f] * m.muW + st.oldc[f]);
+            dmu += mu_of(m, st.site[f], st.newc[f], st.sl[f]) - mu_of(m, st.site[f], st.oldc[f], st.sl[f]);
       }
       // Ewald part first: it only touches the per-walker Ewald cache, never the occupancy.  Flip f is
       // evaluated with flips < f applied to the cache (sequential semantics, ewald.py:168-181); the
@@ -1067,7 +1074,7 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
 #pragma unroll
         for (int f = 0; f < MF; ++f)
           if (f < st.n) {
-            const double2 qn = ewald_qd(m, st.site[f], st.newc[f]), qo = ewald_qd(m, st.site[f], st.oldc[f]);
+            const double2 qn = ewald_qd(m, st.site[f], st.newc[f], st.sl[f]), qo = ewald_qd(m, st.site[f], st.oldc[f], st.sl[f]);
             dq[f] = qn.x - qo.x;
             double phi = fld[st.site[f]];
 #pragma unroll

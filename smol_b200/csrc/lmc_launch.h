@@ -20,6 +20,8 @@ int launch_run_g32(const DevModel& m, const RunArgs& a, bool kone, int ewald, in
 int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int sg, bool lists, const LaunchCfg& lc);
 // Ewald potential cache (ewf) and / or 448-thread blocks (wide), four lanes per step
 int launch_spec_x(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
+// environment-word variants (RunArgs.env), four lanes per step
+int launch_spec_env(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
 // distance processors (Metropolis flip / swap, G = 32)
 int launch_run_dist(const DevModel& m, const RunArgs& a, bool kone, int usher, const LaunchCfg& lc);
 // Wang-Landau variants

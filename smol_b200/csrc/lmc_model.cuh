@@ -47,6 +47,12 @@ struct DevModel {
   // chemical potentials
   int muW, muF;
   const double* mu;        // [N][muW]
+  // per-sublattice forms of the two per-site tables above, valid when every active site of a sublattice carries the
+  // same row (what ChemicalPotentialManager / an Ewald summation produce): the proposal knows the sublattice, so the
+  // lookups come from the parameter bank instead of L2
+  int muC, qdC;
+  double mu_c[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];
+  double qc_c[LMC_MAX_SUBLATTICES][LMC_MAX_CODES], qg_c[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];   // charge, diagonal (two 8-byte tables: a 16-byte element was copied to a misaligned local frame)
   // active sublattices
   int sl_off[LMC_MAX_SUBLATTICES + 1];
   int sl_ncodes[LMC_MAX_SUBLATTICES];
@@ -79,6 +85,20 @@ struct DevModel {
   int off_dtab;            // offset of the difference table [spNC][spL] in the blob
   const unsigned char* sp_rec;  // [N][spNQ] x uint2 (s0 | s1<<16, s2 | tbase<<16)
   const double* spFtab;    // [spNC][spL][F] per-feature form of the difference table (cluster decomposition), or nullptr
+  // environment words (ENV variants of the speculative kernel, see build_env_tables in lmc_api.cu)
+  int envOK;               // tables built
+  int envB;                // bits per species code (1 or 2); a record's field is 3 envB bits
+  int envNRL, envNRLP;     // records per lane of the 4-lane step group (spNQ / 4), rounded up to a multiple of 8
+  int envWide;             // lane chunk: 0 = one 32-bit word (4 words per site), 1 = one 64-bit word (8 words per site)
+  int envNA;               // active sites (index = sl_off[sublattice] + position)
+  int envRV;               // reverse-map entries per active site (multiple of 32)
+  int envNCls;             // classes of sites with equal table-base lists, staged to shared memory (0: read envTb)
+  int off_envtb, off_envcls;   // blob, behind blob_bytes: [envNCls][4][envNRLP] u16 lists, [N] u8 class of a site
+  int blob_env_bytes;          // blob size including them (what the environment-word variants stage)
+  const uint16_t* envTb;   // [N][4][envNRLP] table base of the lane's i-th record
+  const uint32_t* envRev;  // [envNA][envRV] gathering site (active index) | bit position << 16; 0xffffffff = none
+  const unsigned char* envPair;   // [envNA][envNA][4] x (u32 | u64 if envWide): lowest slot bits, per lane chunk, where the column
+                                  // site sits among the codes the row site gathers; nullptr when not built (swaps need it)
 };
 
 struct RunArgs {
@@ -127,6 +147,7 @@ struct RunArgs {
   unsigned long long* stats;  // [2] accepted / attempted step totals (device counters; kernel selection feedback)
   const uint8_t* mask;        // [W] multicell: walkers taking part in this launch (nullptr = all)
   const double* acc_off;      // [W] multicell: enthalpy offset inside the Metropolis exponent (nullptr = 0)
+  uint32_t* env;      // [W][envNA][4 or 8] environment words of the walkers (ENV variants), workspace rebuilt by every launch
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another
 };

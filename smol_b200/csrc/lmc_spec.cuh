@@ -195,13 +195,121 @@ __device__ __forceinline__ double spec_swap_energy(const DevModel& m, const uint
   return (a0 + a1) + (b0 + b1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ENV variants: environment words instead of occupancy gathers (tables: build_env_tables, lmc_api.cu).
+// The walker's words live in global memory (a.env, L2 resident: 16 or 32 bytes per active site), are read with
+// ld.global.cg and updated by accepted steps with red.global.xor; one warp owns them.
+
+// lane chunk of active site `ai`
+__device__ __forceinline__ unsigned long long env_load(const DevModel& m, const uint32_t* envw, int ai, int l) {
+  if (m.envWide) return __ldcg(reinterpret_cast<const unsigned long long*>(envw) + (size_t)ai * 4 + l);
+  return (unsigned long long)__ldcg(envw + (size_t)ai * 4 + l);
+}
+
+// slot mask of active site `aj` inside lane chunk l of active site `ai` (0 where ai does not gather aj)
+__device__ __forceinline__ unsigned long long env_pair(const DevModel& m, int ai, int aj, int l) {
+  const size_t at = ((size_t)ai * m.envNA + aj) * 4 + l;
+  // (ld.global.cg: the table is megabytes of mostly zero words read at random; it must not evict the L1-resident tables)
+  if (m.envWide) return __ldcg(reinterpret_cast<const unsigned long long*>(m.envPair) + at);
+  return (unsigned long long)__ldcg(reinterpret_cast<const uint32_t*>(m.envPair) + at);
+}
+
+// field of three EB-bit codes -> c0 + NC (c1 + NC c2); P2: NC == 2^EB, the field IS that number
+template <int EB, bool P2>
+__device__ __forceinline__ uint32_t env_cidx(uint32_t field, uint32_t NC) {
+  if (P2) return field;
+  constexpr uint32_t cm = (1u << EB) - 1u;
+  return (field & cm) + NC * (((field >> EB) & cm) + NC * (field >> (2 * EB)));
+}
+
+// NP record pairs of a lane (one 16-byte group of table bases holds four); c = the chunk shifted to the group's first
+// field.  a0: even records of the lane, a1: odd ones -- the order spec_rec2 sums them in.
+template <int EB, bool P2, int NP>
+__device__ __forceinline__ void env_pairs(const double* Dn, unsigned long long c, const uint4 tv, uint32_t NC, double& a0, double& a1) {
+  constexpr uint32_t FB = 3 * EB, FM = (1u << FB) - 1u;
+  const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    a0 += Dn[(tw[p] & 0xffffu) + NC * env_cidx<EB, P2>((uint32_t)(c >> (2 * p * FB)) & FM, NC)];
+    a1 += Dn[(tw[p] >> 16) + NC * env_cidx<EB, P2>((uint32_t)(c >> ((2 * p + 1) * FB)) & FM, NC)];
+  }
+}
+
+// (tbp: the lane's table-base list, in shared memory when the model's site classes are staged, else global)
+template <int EB, bool P2>
+__device__ __forceinline__ double env_flip_energy_p(const DevModel& m, const double* Dn, unsigned long long chunk, const uint4* tbp,
+                                                    uint32_t NC) {
+  constexpr int FB = 3 * EB;
+  double a0 = 0.0, a1 = 0.0;
+  // record pairs per lane: straight-line code for up to four (one group of table bases; the FCC and rocksalt cluster
+  // sets have three), whole groups beyond that (the pad records of the last group add exact zeros)
+  switch (m.envNRL) {   // kernel parameter: a uniform branch
+    case 2: env_pairs<EB, P2, 1>(Dn, chunk, tbp[0], NC, a0, a1); break;
+    case 4: env_pairs<EB, P2, 2>(Dn, chunk, tbp[0], NC, a0, a1); break;
+    case 6: env_pairs<EB, P2, 3>(Dn, chunk, tbp[0], NC, a0, a1); break;
+    case 8: env_pairs<EB, P2, 4>(Dn, chunk, tbp[0], NC, a0, a1); break;
+    default:
+      for (int i0 = 0; i0 < m.envNRL; i0 += 8) env_pairs<EB, P2, 4>(Dn, chunk >> (i0 * FB), tbp[i0 >> 3], NC, a0, a1);
+  }
+  return a0 + a1;
+}
+
+// scaled energy change of one flip from the lane's chunk: the records and table entries of spec_flip_energy
+template <int EB>
+__device__ __forceinline__ double env_flip_energy(const DevModel& m, const unsigned char* smem, const double* dtab,
+                                                  unsigned long long chunk, int site, int oldc, int newc, int l) {
+  const uint4* tbp = m.envNCls
+      ? reinterpret_cast<const uint4*>(smem + m.off_envtb) + (((int)smem[m.off_envcls + site] * 4 + l) * m.envNRLP >> 3)
+      : reinterpret_cast<const uint4*>(m.envTb + ((size_t)site * 4 + l) * m.envNRLP);
+  const double* Dn = dtab + newc * m.spL + oldc;   // the old code is the fastest index of a block
+  const uint32_t NC = (uint32_t)m.spNC;
+  if (NC == (1u << EB)) return env_flip_energy_p<EB, true>(m, Dn, chunk, tbp, NC);
+  return env_flip_energy_p<EB, false>(m, Dn, chunk, tbp, NC);
+}
+
+// words of every active site from the occupancy row (whole warp, start of a launch)
+__device__ __forceinline__ void env_build(const DevModel& m, uint32_t* envw, const uint8_t* occ, int g) {
+  const uint32_t b = (uint32_t)m.envB, fb = 3u * b;
+  const int nrl = m.envNRL;
+  for (int ai = g; ai < m.envNA; ai += 32) {
+    const int site = __ldg(m.sl_sites + ai);
+    const uint2* rp = reinterpret_cast<const uint2*>(m.sp_rec + (size_t)site * m.spSb);
+    for (int l = 0; l < 4; ++l) {
+      unsigned long long chunk = 0ull;
+      for (int i = 0; i < nrl; ++i) {
+        const uint2 rc = __ldg(rp + 2 * (l + 4 * (i >> 1)) + (i & 1));
+        const uint32_t field = (uint32_t)occ[rc.x & 0xffffu] | ((uint32_t)occ[rc.x >> 16] << b) | ((uint32_t)occ[rc.y & 0xffffu] << (2u * b));
+        chunk |= (unsigned long long)field << (i * fb);
+      }
+      if (m.envWide) reinterpret_cast<unsigned long long*>(envw)[(size_t)ai * 4 + l] = chunk;
+      else envw[(size_t)ai * 4 + l] = (uint32_t)chunk;
+    }
+  }
+}
+
+// an accepted flip of active site `ai` (code old -> new, x = old ^ new): every site that gathers it sees the new code
+__device__ __forceinline__ void env_commit(const DevModel& m, uint32_t* envw, int ai, uint32_t x, int g) {
+  const uint32_t* rv = m.envRev + (size_t)ai * m.envRV;
+  for (int e = g; e < m.envRV; e += 32) {
+    const uint32_t ent = __ldg(rv + e);
+    if (ent == 0xffffffffu) continue;
+    const uint32_t k = ent & 0xffffu, p = ent >> 16;
+    if (m.envWide) atomicXor(reinterpret_cast<unsigned long long*>(envw) + (size_t)k * 4 + (p >> 6), (unsigned long long)x << (p & 63u));
+    else atomicXor(envw + (size_t)k * 4 + (p >> 5), x << (p & 31u));
+  }
+}
+
 // EWF: Ewald term through the potential cache (a.ew_field, see lmc_kernels.cuh): two cached doubles and
 // a charge table lookup per flip, one row of the site kernel per ACCEPTED flip.
 // MAXT / MINB: launch bounds.  (128, 7) while seven blocks of four walkers fit an SM's shared memory;
 // (448, 2) -- fourteen walkers share one copy of a larger table blob -- otherwise: both keep 28 walkers
 // resident per SM (4096 walkers = one wave on 148 SMs) at 72 registers.
-template <bool KONE, int USHER, int SPEC_SG, bool LISTS, bool EWF, int MAXT, int MINB>
+// EB > 0: environment words (a.env) of EB bits per species code instead of occupancy gathers, four lanes per step.
+template <bool KONE, int USHER, int SPEC_SG, bool LISTS, bool EWF, int MAXT, int MINB, int EB = 0>
 __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, const RunArgs a) {
+  constexpr bool ENV = EB != 0;
+  static_assert(!ENV || (SPEC_SG == 4 && !LISTS), "environment words: four lanes per step, rank select");
+  static_assert(EB >= 0 && EB <= 2, "one or two bits per species code");
   static_assert(USHER == LMC_USHER_FLIP || USHER == LMC_USHER_SWAP, "flip / swap only");
   static_assert(SPEC_SG == 1 || SPEC_SG == 2 || SPEC_SG == 4, "1, 2 or 4 lanes per speculated step");
   static_assert(!LISTS || USHER == LMC_USHER_SWAP, "position lists serve the swap usher");
@@ -217,7 +325,8 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
   const bool active = wl_ < a.wpb && w < a.W;
   const int sg = g / SPEC_SG, l = g % SPEC_SG;
 
-  unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
+  const int blob_bytes = EB != 0 ? m.blob_env_bytes : m.blob_bytes;
+  unsigned char* wbase = smem + ((blob_bytes + 15) & ~15);
   uint8_t* occ_rows = wbase;
   unsigned char* rest = wbase + (size_t)a.wpb * m.Npad;
   uint8_t* occ = occ_rows + (size_t)wl_ * m.Npad;
@@ -230,7 +339,7 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
   uint16_t* lists = reinterpret_cast<uint16_t*>(priv + a.off_lists);   // LISTS: [sublattice][code][n_active]
 
   stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad),
-               (uint32_t)m.blob_bytes);
+               (uint32_t)blob_bytes);
   const SmemTables t = smem_tables(m, smem);
   const double* dtab = reinterpret_cast<const double*>(smem + m.off_dtab);
   if (!active) return;
@@ -284,6 +393,13 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
     __syncwarp();
   }
 
+  uint32_t* envw = ENV ? a.env + (size_t)w * m.envNA * (m.envWide ? 8 : 4) : nullptr;
+  if (ENV) {
+    env_build(m, envw, occ, g);
+    __threadfence();
+    __syncwarp();
+  }
+
   const unsigned long long seed = a.seeds[w];
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint32_t wid = (uint32_t)(a.walker_base + w);
@@ -329,6 +445,10 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
       if (SPEC_SG > 1) rq = ring[min((int)(step - rbase) + sg, 31)];
       const int sl = (int)(rq.x >> 24), pos1 = (int)(rq.x & 0xffffffu), site1 = (int)rq.y;
       const float lf = __uint_as_float(rq.w);
+      // environment words of the first site: state-independent address, the load overlaps the proposal
+      const int ai1 = ENV ? m.sl_off[sl] + pos1 : 0;
+      unsigned long long ch1 = 0ull;
+      if (ENV) ch1 = env_load(m, envw, ai1, l);
 
       // ------------------------------ propose (one step per subgroup) -------------------------
       int n = 0, s1, site2 = 0, s2 = 0, pos2 = 0;
@@ -356,21 +476,35 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
         }
       }
 
+      // site 2 sees site 1 already holding s2 (expansion.py:217-229): its slots that gather site 1 flip s1 -> s2.
+      // Both loads are in flight while flip 1 is evaluated.
+      unsigned long long ch2 = 0ull, pm2 = 0ull;
+      if (ENV && USHER == LMC_USHER_SWAP) {
+        const int ai2 = m.sl_off[sl] + pos2;
+        ch2 = env_load(m, envw, ai2, l);
+        pm2 = env_pair(m, ai2, ai1, l);
+      }
+
       // ------------------------------ evaluate ------------------------------------------------
       // Ewald term first: its (L2) loads are in flight while the cluster records are evaluated
       double dEw = 0.0;
       if (EWF && n > 0) {
-        const double2 qn = ewald_qd(m, site1, s2), qo = ewald_qd(m, site1, s1);
+        const double2 qn = ewald_qd(m, site1, s2, sl), qo = ewald_qd(m, site1, s1, sl);
         const double dq1 = qn.x - qo.x;
         dEw = 2.0 * dq1 * fld[site1] + (qn.y - qo.y);
         if (USHER == LMC_USHER_SWAP) {   // site 2 takes s1; it sees the cache shifted by flip 1
-          const double2 qn2 = ewald_qd(m, site2, s1), qo2 = ewald_qd(m, site2, s2);
+          const double2 qn2 = ewald_qd(m, site2, s1, sl), qo2 = ewald_qd(m, site2, s2, sl);
           dEw += 2.0 * (qn2.x - qo2.x) * (fld[site2] + dq1 * __ldg(m.ewK + (size_t)site1 * m.N + site2)) + (qn2.y - qo2.y);
         }
       }
       double acc = 0.0, dmu = 0.0;
       if (live && n > 0) {
-        if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, l);
+        if (ENV) {
+          constexpr int EBK = ENV ? EB : 1;
+          const double ea = env_flip_energy<EBK>(m, smem, dtab, ch1, site1, s1, s2, l);
+          acc = USHER == LMC_USHER_FLIP ? ea
+              : ea + env_flip_energy<EBK>(m, smem, dtab, ch2 ^ (pm2 * (unsigned long long)(s1 ^ s2)), site2, s2, s1, l);
+        } else if (USHER == LMC_USHER_FLIP) acc = spec_flip_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, l);
         else acc = spec_swap_energy<SPEC_SG>(m, occ, dtab, site1, s1, s2, site2, s2, s1, l);
       }
       if (SPEC_SG > 1) acc += __shfl_xor_sync(FULL, acc, 1);
@@ -378,7 +512,7 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
       double dH = acc;
       if (EWF) dH += nat_ew * dEw;
       if (MU_POSSIBLE && m.muW) {
-        dmu = __ldg(m.mu + site1 * m.muW + s2) - __ldg(m.mu + site1 * m.muW + s1);
+        dmu = mu_of(m, site1, s2, sl) - mu_of(m, site1, s1, sl);
         dH += nat_mu * dmu;
       }
 
@@ -461,6 +595,11 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
           pl[c_s1 * nw] ^= bit;
           pl[c_s2 * nw] ^= bit;
         }
+      }
+      if (ENV && c_n > 0) {
+        env_commit(m, envw, m.sl_off[c_sl] + c_pos1, (uint32_t)(c_s1 ^ c_s2), g);
+        if (c_n == 2) env_commit(m, envw, m.sl_off[c_sl] + c_pos2, (uint32_t)(c_s1 ^ c_s2), g);
+        __threadfence();   // the next batch reads the words (ld.global.cg) after the __syncwarp below
       }
       __syncwarp();
       enth += c_dH;

@@ -190,10 +190,11 @@ class LmcEngine:
         return out
 
     def model_info(self):
-        """(Ewald matrix factorises, speculative tables built, table blob bytes, speculative records per site)"""
+        """(Ewald matrix factorises, speculative tables built, table blob bytes, speculative records per site,
+        bytes per walker of the environment-word workspace ``LmcRunConfig.spec_env_dev`` or 0)"""
         if getattr(self, "_info", None) is None:
-            info = (C.c_int32 * 4)()
-            capi.check(self.lib.lmc_model_info(self.handle, info, 4))
+            info = (C.c_int32 * 5)()
+            capi.check(self.lib.lmc_model_info(self.handle, info, 5))
             self._info = tuple(int(x) for x in info)
         return self._info
 
@@ -239,3 +240,7 @@ class LmcEngine:
 
     def launch_count(self) -> int:
         return int(self.lib.lmc_launch_count())
+
+    def env_launch_count(self) -> int:
+        """launches of the speculative kernel's environment-word variants (process-wide)"""
+        return int(self.lib.lmc_env_launch_count())

@@ -154,7 +154,7 @@ class Sampler:
     def __init__(self, ensemble, kernel_type="Metropolis", step_type="swap", nwalkers=1, seeds=None,
                  temperature=None, wl_params=None, usher_kwargs=None, walker_id_base=0,
                  group_size=0, block_threads=0, record_occupancy=True, device=None, kB_=kB,
-                 spec_mode=0, ewald_field="auto", bias_type=None, bias_kwargs=None, wl_trace="full"):
+                 spec_mode=0, ewald_field="auto", bias_type=None, bias_kwargs=None, wl_trace="full", spec_env=False):
         from .engine import LmcEngine
         self.ensemble = ensemble
         self.kernel_type = kernel_type
@@ -228,6 +228,11 @@ class Sampler:
         self.group_size, self.block_threads = int(group_size), int(block_threads)
         # Metropolis flip/swap kernel: 0 auto (by measured acceptance), 1 classic, 2 speculative batch
         self.spec_mode = int(spec_mode)
+        # speculative kernel over per-site environment words (one packed word per flip and lane instead of three
+        # occupancy gathers per record) where the model has the tables.  Opt-in: the words live in L2 (16-32 bytes
+        # per site and walker do not fit shared memory at 28 walkers per SM) and the exposed L2 latency costs more than
+        # the gathers save on the measured configurations
+        self.spec_env = bool(spec_env) or os.environ.get("LMC_SPEC_ENV_DEFAULT") == "1"
         # Ewald term through the per-walker potential cache (O(1) per flip, one row of the site kernel per
         # accepted flip) instead of gathering matrix rows at every flip: "auto" = while fewer than a quarter
         # of the steps are accepted (needs an Ewald matrix of the form q_i q_j K[site_i, site_j])
@@ -237,6 +242,7 @@ class Sampler:
             raise ValueError("ewald_field must be 'auto', True or False")
         self.ewald_field = ewald_field
         self._ew_field = None
+        self._spec_env_ws = None
         self._acc_est = None
         self.record_occupancy = record_occupancy
         # bias term of the Metropolis exponent (kernel/base.py:229-235, metropolis.py:43-44)
@@ -288,7 +294,7 @@ class Sampler:
         if kernel_type is None:
             kernel_type = "Metropolis"
         engine_kw = {k: kwargs.pop(k) for k in ("walker_id_base", "group_size", "block_threads", "spec_mode",
-                                                "record_occupancy", "device", "ewald_field", "bias_type", "bias_kwargs", "wl_trace") if k in kwargs}
+                                                "record_occupancy", "device", "ewald_field", "bias_type", "bias_kwargs", "wl_trace", "spec_env") if k in kwargs}
         key = kernel_type.lower().replace("_", "").replace("-", "")
         temperature, wl = None, None
         if key == "wanglandau":
@@ -484,6 +490,16 @@ class Sampler:
         ctx.spec_mode = self.spec_mode
         if ctx.spec_mode == 0:
             ctx.spec_mode = 3 if (self._acc_est is None or self._acc_est < 0.35) else 1
+        # workspace of the speculative kernel's environment words (lmc.h: LmcRunConfig.spec_env_dev), rebuilt by every
+        # launch from the occupancies: allocated once per sampler, only where a speculative launch can happen
+        env_bytes = eng.model_info()[4]
+        if (self.spec_env and env_bytes > 0 and ctx.spec_mode != 1 and self._kernel == capi.LMC_KERNEL_METROPOLIS
+                and self._usher in (capi.LMC_USHER_FLIP, capi.LMC_USHER_SWAP)):
+            if self._spec_env_ws is None or self._spec_env_ws.numel() != self.nwalkers * env_bytes:
+                self._spec_env_ws = torch.empty((self.nwalkers * env_bytes,), dtype=torch.uint8, device=dev)
+            ctx.spec_env = self._spec_env_ws
+        else:
+            ctx.spec_env = None
         return ctx
 
     def _run_config(self, ctx, d, n):
@@ -504,6 +520,7 @@ class Sampler:
         cfg.trace_features_dev, cfg.trace_enthalpy_dev = d["features"].data_ptr(), d["enthalpy"].data_ptr()
         cfg.trace_accepted_dev, cfg.trace_naccepted_dev = d["accepted"].data_ptr(), d["n_accepted"].data_ptr()
         cfg.ewald_field_dev = self._ew_field.data_ptr() if ctx.use_field else None
+        cfg.spec_env_dev = ctx.spec_env.data_ptr() if ctx.spec_env is not None else None
         if ctx.dist_proc is not None:
             dt = eng.distance_tables(ctx.dist_proc)
             cfg.dist_mode, cfg.dist_num_groups, cfg.dist_tol = 1, dt["ngrp"], dt["tol"]

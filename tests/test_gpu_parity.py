@@ -156,7 +156,7 @@ def test_canonical_swap_trajectory(cuda_device, kind, n, group):
     assert 0 < smp.samples.step_efficiency() <= 1
 
 
-@pytest.mark.parametrize("factorize", ["1", "gather", "spec", "spec-wide", "0", "random"])
+@pytest.mark.parametrize("factorize", ["1", "gather", "spec", "spec-wide", "spec-env", "spec-wide-env", "0", "random"])
 def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
     """factorize=1: M = q q^T x K, Ewald through the per-walker potential cache (the default); gather: the
     same matrix with one row of K gathered per flip; spec / spec-wide: potential cache inside the speculative
@@ -167,8 +167,8 @@ def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
     if factorize == "gather":
         kw = dict(ewald_field=False)
     elif factorize.startswith("spec"):
-        kw = dict(spec_mode=2, ewald_field=True)
-        monkeypatch.setenv("LMC_SPEC_WIDE", "1" if factorize == "spec-wide" else "0")
+        kw = dict(spec_mode=2, ewald_field=True, spec_env=factorize.endswith("env"))   # environment words / gathers
+        monkeypatch.setenv("LMC_SPEC_WIDE", "1" if "wide" in factorize else "0")
     else:
         kw = dict(spec_mode=1)
     import smol_b200 as S
@@ -199,7 +199,7 @@ def test_semigrand_ewald_flip_trajectory(cuda_device, factorize, monkeypatch):
     seeds = np.arange(7, 7 + W)
     smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 300, 10, occ0, seeds, T=1500.0, usher_kwargs=kw)
     _compare_traces(smp, ref)
-    assert smp.ewald_cache_in_use == (factorize in ("1", "spec", "spec-wide"))
+    assert smp.ewald_cache_in_use == (factorize == "1" or factorize.startswith("spec"))
     # a second run continues the chains (potential cache rebuilt from the occupancies, then kept current)
     smp.run(100, thin_by=10)
     assert smp.samples.num_samples == 40
@@ -236,10 +236,10 @@ def test_ewald_potential_cache_stays_consistent(cuda_device):
         np.testing.assert_allclose(last, feat.cpu().numpy(), rtol=1e-10, atol=1e-10 * np.abs(last).max())
 
 
-@pytest.mark.parametrize("mode", ["classic", "spec"])
+@pytest.mark.parametrize("mode", ["classic", "spec", "spec-env"])
 def test_canonical_ewald_swap_trajectory(cuda_device, mode):
     """canonical swaps with an Ewald term through the potential cache: flip 2 of a swap sees the cache
-    shifted by flip 1 (one element of the site kernel); classic and speculative kernels"""
+    shifted by flip 1 (one element of the site kernel); classic and speculative kernels (environment words / gathers)"""
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
@@ -262,7 +262,7 @@ def test_canonical_ewald_swap_trajectory(cuda_device, mode):
     occ0 = M.random_occupancies(sub, scm, W, seed=6)
     seeds = np.arange(40, 40 + W)
     smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, 520, 13, occ0, seeds, T=2500.0,
-                            usher_kwargs=dict(spec_mode=2 if mode == "spec" else 1))
+                            usher_kwargs=dict(spec_mode=2 if mode.startswith("spec") else 1, spec_env=mode.endswith("env")))
     _compare_traces(smp, ref)
     assert smp.ewald_cache_in_use and 0 < smp.samples.step_efficiency() < 1
 
@@ -627,12 +627,13 @@ def test_bias_rejected_where_the_reference_rejects_it(cuda_device):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["decomposition", "expansion"])
 @pytest.mark.parametrize("n,T,thin", [(2, 1000.0, 20), (4, 300.0, 7), (4, 1000.0, 64), (3, 1e5, 13)])
-@pytest.mark.parametrize("sg", ["4", "4L", "2", "1"])
+@pytest.mark.parametrize("sg", ["4", "4E", "4L", "2", "1"])
 def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypatch):
     """low / medium / near-infinite temperature (acceptance ~0 .. ~1), sampling intervals that are not
     multiples of the batch, aliased 2x2x2 cell; spec_mode=2 forces the speculative kernel, 1 the classic
     one: both must reproduce the oracle chain bit for bit.  sg = lanes per speculated step, L = swap partner
-    from sorted position lists instead of the rank select."""
+    from sorted position lists instead of the rank select, E = environment words instead of occupancy gathers
+    (``Sampler(spec_env=True)``, where the model has the tables)."""
     import smol_b200 as S
     monkeypatch.setenv("LMC_SPEC_SG", sg[0])
     monkeypatch.setenv("LMC_SPEC_LISTS", "1" if sg.endswith("L") else "0")
@@ -650,9 +651,15 @@ def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypa
     occ0 = M.random_occupancies(sub, scm, W, seed=3, balanced=True)
     seeds = np.arange(500, 500 + W)
     nsteps = thin * 30
+    env0 = S.Sampler.from_ensemble(ens_g, T, step_type="swap", nwalkers=W, seeds=list(seeds)).engine.env_launch_count()
     smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, nsteps, thin, occ0, seeds, T=T,
-                            usher_kwargs=dict(spec_mode=2))
+                            usher_kwargs=dict(spec_mode=2, spec_env=sg.endswith("E")))
     _compare_traces(smp, ref)
+    # the environment-word variant ran exactly where it is meant to (decomposition: merged records fit the lane chunks)
+    took_env = smp.engine.env_launch_count() > env0
+    assert took_env == (sg == "4E" and smp.engine.model_info()[4] > 0)
+    if sg == "4E" and kind == "decomposition":
+        assert took_env
     smp1 = S.Sampler.from_ensemble(ens_g, T, step_type="swap", nwalkers=W, seeds=list(seeds), spec_mode=1)
     smp1.run(nsteps, occ0, thin_by=thin)
     np.testing.assert_array_equal(smp1.samples.get_occupancies(flat=False),
@@ -662,11 +669,12 @@ def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypa
 
 
 @pytest.mark.parametrize("T", [400.0, 3000.0])
-@pytest.mark.parametrize("sg", ["4", "2", "1"])
+@pytest.mark.parametrize("sg", ["4", "4E", "2", "1"])
 def test_speculative_semigrand_flip_trajectory(cuda_device, T, sg, monkeypatch):
-    """ternary rocksalt cations, chemical potentials, single flips (no Ewald term): speculative kernel"""
+    """ternary rocksalt cations, chemical potentials, single flips (no Ewald term): speculative kernel
+    (4E = environment words with two bits per code and 64-bit lane chunks instead of occupancy gathers)"""
     import smol_b200 as S
-    monkeypatch.setenv("LMC_SPEC_SG", sg)
+    monkeypatch.setenv("LMC_SPEC_SG", sg[0])
     from smol_b200 import lattice as L
     O = _oracle()
     sub = M.rocksalt_subspace()
@@ -684,8 +692,11 @@ def test_speculative_semigrand_flip_trajectory(cuda_device, T, sg, monkeypatch):
     W = 4
     occ0 = M.random_occupancies(sub, scm, W, seed=8)
     seeds = np.arange(70, 70 + W)
-    smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 330, 11, occ0, seeds, T=T, usher_kwargs=dict(spec_mode=2))
+    env0 = S.Sampler.from_ensemble(ens_g, T, step_type="flip", nwalkers=W, seeds=list(seeds)).engine.env_launch_count()
+    smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 330, 11, occ0, seeds, T=T,
+                            usher_kwargs=dict(spec_mode=2, spec_env=sg.endswith("E")))
     _compare_traces(smp, ref)
+    assert (smp.engine.env_launch_count() > env0) == (sg == "4E")
 
 
 def test_speculative_two_sublattice_swap(cuda_device):

@@ -31,7 +31,7 @@ def _tables(packed):
     return info, dtab.reshape(NC, Lp), rec.view(np.uint32).reshape(packed.desc.num_sites, NQ, 2)
 
 
-def _spec_delta(dtab, rec, NC, occ, site, new, patch=None):
+def _spec_delta(dtab, rec, NC, occ, site, new, patch=None, entries=False):
     """energy change of flipping `site` to `new` as the kernel computes it (spec_rec2)"""
     N = len(occ)
     row = np.append(occ, 0)                 # zero pad byte gathered by unused slots
@@ -42,6 +42,8 @@ def _spec_delta(dtab, rec, NC, occ, site, new, patch=None):
     s0, s1, s2, tb = x & 0xffff, x >> 16, y & 0xffff, y >> 16
     assert max(s0.max(), s1.max(), s2.max()) <= N
     idx = tb + old + NC * (row[s0] + NC * (row[s1] + NC * row[s2]))
+    if entries:
+        return np.sort(dtab[new][idx])
     return dtab[new][idx].sum()
 
 
@@ -122,3 +124,135 @@ def test_cover_merge_quarters_the_lookups():
     # tetrahedron, its three triangles and nearest-neighbour pairs) + 14 records of three farther pairs
     assert info[3] == 24
     assert info[6] <= 8 * 1024    # the difference table stays a few KB of shared memory
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# environment words (csrc/lmc_api.cu:build_env_tables, ENV variants of the speculative kernel)
+def _env_tables(packed):
+    lib = capi.load()
+    info = (C.c_int32 * 8)()
+    capi.check(lib.lmc_spec_env_host(C.byref(packed.desc), info, None, 0, None, 0, None, 0))
+    ok, b, nrl, nrlp, wide, NA, RV, pair_ok = list(info)
+    if not ok:
+        return list(info), None
+    N = packed.desc.num_sites
+    tb = np.zeros(N * 4 * nrlp, dtype=np.uint16)
+    rev = np.zeros(NA * RV, dtype=np.uint32)
+    pair = np.zeros(NA * NA * 4 if pair_ok else 0, dtype=np.uint64 if wide else np.uint32)
+    capi.check(lib.lmc_spec_env_host(C.byref(packed.desc), (C.c_int32 * 8)(), tb.ctypes.data_as(C.c_void_p), tb.size,
+                                     rev.ctypes.data_as(C.c_void_p), rev.size, pair.ctypes.data_as(C.c_void_p), pair.nbytes))
+    return list(info), dict(tb=tb.reshape(N, 4, nrlp), rev=rev.reshape(NA, RV),
+                            pair=pair.reshape(NA, NA, 4) if pair_ok else None)
+
+
+class _EnvModel:
+    """the kernel's environment-word arithmetic (env_build / env_flip_energy / env_commit / the swap patch) in Python"""
+
+    def __init__(self, info, tabs, dtab, rec, NC, active_sites):
+        _, self.b, self.nrl, _, self.wide, self.NA, _, _ = info
+        self.t, self.dtab, self.rec, self.NC = tabs, dtab, rec, NC
+        self.sites = list(active_sites)            # active index -> site
+        self.lane_bits = 64 if self.wide else 32
+
+    def build(self, occ):
+        row = np.append(occ, 0)
+        b, fb = self.b, 3 * self.b
+        env = np.zeros((self.NA, 4), dtype=object)
+        for ai, site in enumerate(self.sites):
+            for l in range(4):
+                chunk = 0
+                for i in range(self.nrl):
+                    r = 2 * (l + 4 * (i >> 1)) + (i & 1)
+                    x, y = int(self.rec[site, r, 0]), int(self.rec[site, r, 1])
+                    field = int(row[x & 0xffff]) | (int(row[x >> 16]) << b) | (int(row[y & 0xffff]) << (2 * b))
+                    chunk |= field << (i * fb)
+                assert chunk < (1 << self.lane_bits)
+                env[ai, l] = chunk
+        return env
+
+    def delta(self, env_row, site, old, new):
+        b, fb, NC = self.b, 3 * self.b, self.NC
+        vals = []
+        for l in range(4):
+            for i in range(self.nrl):
+                field = (env_row[l] >> (i * fb)) & ((1 << fb) - 1)
+                cm = (1 << b) - 1
+                ci = (field & cm) + NC * (((field >> b) & cm) + NC * (field >> (2 * b)))
+                vals.append(self.dtab[new][int(self.t["tb"][site, l, i]) + old + NC * ci])
+        return np.sort(np.array(vals))     # the table entries the kernel adds up
+
+    def patched(self, env, ai2, ai1, x):
+        return [env[ai2, l] ^ (int(self.t["pair"][ai2, ai1, l]) * x) for l in range(4)]
+
+    def commit(self, env, ai, x):
+        for ent in self.t["rev"][ai]:
+            ent = int(ent)
+            if ent == 0xffffffff:
+                continue
+            k, p = ent & 0xffff, ent >> 16
+            env[k, p // self.lane_bits] ^= x << (p % self.lane_bits)
+
+
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_environment_words_reproduce_the_gather_variant(name, make):
+    """environment words built from an occupancy, patched for a swap's second flip and updated by accepted flips
+    give exactly the table entries the gather variant reads (so the two kernels sum the same doubles)"""
+    import smol_b200 as S
+    sub, n, kind = make()
+    scm = np.eye(3, dtype=int) * n
+    rng = np.random.default_rng(11)
+    coefs = rng.normal(0, 0.05, sub.num_corr_functions)
+    proc = (S.ClusterDecompositionProcessor(sub, scm, L.cluster_interaction_tensors(sub, coefs))
+            if kind == "decomposition" else S.ClusterExpansionProcessor(sub, scm, coefs))
+    ens = S.Ensemble(proc)
+    packed = ens.packed_model()
+    info, dtab, rec = _tables(packed)
+    einfo, tabs = _env_tables(packed)
+    NC = info[1]
+    bits = 1 if NC <= 2 else 2
+    if NC > 4 or info[3] // 4 * 3 * bits > 64:   # a lane's records do not fit one 64-bit chunk: the model keeps the gather variant
+        assert einfo[0] == 0
+        return
+    assert info[0] == 1 and einfo[0] == 1, (info, einfo)
+    assert einfo[1] == bits and einfo[2] == info[3] // 4 and einfo[7] == 1
+    d = packed.desc
+    sl_off = list(np.ctypeslib.as_array(C.cast(d.sl_site_off, C.POINTER(C.c_int32)), (d.num_sublattices + 1,)))
+    active = [int(v) for v in np.ctypeslib.as_array(C.cast(d.sl_sites, C.POINTER(C.c_int32)), (int(sl_off[-1]),))]
+    # (active index = sl_off[sublattice] + position)
+    assert einfo[5] == len(active)
+    aidx = {s: a for a, s in enumerate(active)}
+    em = _EnvModel(einfo, tabs, dtab, rec, NC, active)
+    occ = M.random_occupancies(sub, scm, 1, seed=8)[0].copy()
+    spaces = sub.allowed_species(scm)
+    env = em.build(occ)
+    nflips = npatched = 0
+    for it in range(60):
+        # single flips against the current words
+        site = int(rng.choice(active))
+        new = int(rng.choice([c for c in range(len(spaces[site])) if c != occ[site]]))
+        got = em.delta([env[aidx[site], l] for l in range(4)], site, int(occ[site]), new)
+        ref = _spec_delta(dtab, rec, NC, occ, site, new, entries=True)
+        assert np.array_equal(got, ref), (it, site, new)
+        # a swap inside one sublattice: the second flip sees the first through the slot masks
+        k = int(rng.integers(d.num_sublattices))
+        sites_sl = active[sl_off[k]:sl_off[k + 1]]
+        a, bq = (int(v) for v in rng.choice(sites_sl, 2, replace=False))
+        if occ[a] != occ[bq]:
+            # prefer neighbours now and then so that the patch is exercised
+            nb = [active[k] for k in range(len(active)) if tabs["pair"][aidx[bq], k].any()] if it % 2 else []
+            nb = [s for s in nb if s in sites_sl and occ[s] != occ[bq]]
+            if nb:
+                a = nb[0]
+            x = int(occ[a]) ^ int(occ[bq])
+            row2 = em.patched(env, aidx[bq], aidx[a], x)
+            npatched += int(tabs["pair"][aidx[bq], aidx[a]].any())
+            got2 = em.delta(row2, bq, int(occ[bq]), int(occ[a]))
+            ref2 = _spec_delta(dtab, rec, NC, occ, bq, int(occ[a]), patch=(a, int(occ[bq])), entries=True)
+            assert np.array_equal(got2, ref2), (it, a, bq)
+        # accept the flip: the words of every gathering site follow
+        em.commit(env, aidx[site], int(occ[site]) ^ new)
+        occ[site] = new
+        nflips += 1
+    assert npatched >= 3
+    fresh = em.build(occ)
+    assert all(env[a, l] == fresh[a, l] for a in range(len(active)) for l in range(4))
