@@ -1059,8 +1059,13 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (multicell && c->kernel != LMC_KERNEL_METROPOLIS) return fail("walker_mask_dev / accept_offset_dev are for Metropolis kernels");
   const bool spec_ok = m.spOK && !dist && !multicell && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && c->kernel == LMC_KERNEL_METROPOLIS &&
                        (c->usher == LMC_USHER_FLIP || c->usher == LMC_USHER_SWAP) && (G == 0 || G == 32);
-  if (spec_mode == 2 && !spec_ok)
-    return fail("the speculative kernel supports unbiased Metropolis flip/swap steps (an Ewald term through ewald_field_dev only)");
+  // table flips: speculative batches of their own (lmc_spec_tf.cuh), one block of up to 16 walkers per SM
+  const bool tf_spec_ok = m.spOK && m.spNQ % 8 == 0 && c->usher == LMC_USHER_TABLEFLIP && c->kernel == LMC_KERNEL_METROPOLIS && !dist &&
+                          !multicell && c->bias_mode == LMC_BIAS_NONE && (!ewald || field) && (G == 0 || G == 32) && c->block_threads == 0;
+  if (spec_mode == 2 && !spec_ok && !tf_spec_ok)
+    return fail("the speculative kernels support unbiased Metropolis flip / swap / table-flip steps (an Ewald term through ewald_field_dev only)");
+  bool tf_spec = tf_spec_ok && (spec_mode == 2 || ((spec_mode == 3 || (spec_mode == 0 && mm->acc_rate < 0.35)) && G == 0));
+  if (const char* e = getenv("LMC_SPEC_TF")) tf_spec = tf_spec && atoi(e) != 0;
   // auto: only while the staged tables leave room for a full complement of resident walkers per SM
   // 3 = speculative whenever this model / run supports it (decided by the caller from ITS acceptance history:
   // deterministic, unlike the asynchronously refreshed acc_rate of mode 0)
@@ -1136,10 +1141,23 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     }
   if (const char* e = getenv("LMC_SEQUENTIAL_FLIPS")) a.seq_flips = atoi(e);
   if (a.max_flips > LMC_MAX_FLIPS) return fail("flip table changes more than 4 sites per step");
-  a.off_cnt = a.off_stash + (int)(((size_t)a.max_flips * m.Rstride * stash_el + 15) & ~size_t(15));
+  if (tf_spec) {
+    // one stash slot (the commit evaluates and folds flip by flip) and two rings of 32 random-word blocks; the
+    // variant is taken when at least four walkers and the whole table blob fit a block
+    const size_t slab = (size_t)m.Npad + (((size_t)m.F * 8 + 15) & ~size_t(15)) + (((size_t)m.Rstride * stash_el + 15) & ~size_t(15)) +
+                        LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4 + ((m.plane_words * 4 + 15) & ~15) + 2 * 32 * 16 +
+                        (6 * LMC_MAX_TABLE_FLIPS + 2) * 8;
+    if ((((size_t)m.blob_bytes + 15) & ~size_t(15)) + 4 * slab > (size_t)mdl->smem_optin - 1024) {
+      if (spec_mode == 2) return fail("the speculative table-flip kernel does not fit this model in shared memory");
+      tf_spec = false;
+    }
+  }
+  if (tf_spec) G = 32;
+  const int stash_slots = tf_spec ? 1 : a.max_flips;
+  a.off_cnt = a.off_stash + (int)(((size_t)stash_slots * m.Rstride * stash_el + 15) & ~size_t(15));
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
   a.off_ring = a.off_plane + ((m.plane_words * 4 + 15) & ~15);   // species bit-planes
-  a.off_eidx = a.off_ring + G * 16;                                   // per-lane precomputed proposals
+  a.off_eidx = a.off_ring + G * 16 * (tf_spec ? 2 : 1);               // per-lane precomputed proposals
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
@@ -1233,6 +1251,22 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
         return 0;
       }
     }
+  }
+  if (tf_spec) {
+    // as many walkers per block as fit (<= 16 warps), then evened out over the waves the launch needs anyway
+    const size_t blob_all = ((size_t)m.blob_bytes + 15) & ~size_t(15);
+    int wpb = 16;
+    while (wpb > 1 && blob_all + (size_t)wpb * (m.Npad + a.walker_smem) > (size_t)mdl->smem_optin - 1024) --wpb;
+    const long per_wave = (long)wpb * mdl->num_sms;
+    const long waves = (a.W + per_wave - 1) / per_wave;
+    wpb = (int)std::min<long>(wpb, std::max<long>(1, (a.W + waves * mdl->num_sms - 1) / (waves * mdl->num_sms)));
+    a.wpb = wpb;
+    LaunchCfg lct{(a.W + wpb - 1) / wpb, 32 * wpb, blob_all + (size_t)wpb * (m.Npad + a.walker_smem), (cudaStream_t)stream};
+    const int rct = launch_spec_tf(m, a, m.kone != 0, field, lct);
+    g_launches++;
+    if (rct != 0) return fail(std::string("launch failed: ") + cudaGetErrorString((cudaError_t)rct));
+    if (mm->stats_host) cudaMemcpyAsync(mm->stats_host, mm->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    return 0;
   }
   const int grid = (a.W + a.wpb - 1) / a.wpb;
   LaunchCfg lc{grid, threads, smem, (cudaStream_t)stream};

@@ -22,6 +22,8 @@ int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int s
 int launch_spec_x(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
 // environment-word variants (RunArgs.env), four lanes per step
 int launch_spec_env(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
+// speculative table-flip kernel (lmc_spec_tf.cuh): up to 16 walkers per block, ewf = Ewald through the potential cache
+int launch_spec_tf(const DevModel& m, const RunArgs& a, bool kone, bool ewf, const LaunchCfg& lc);
 // distance processors (Metropolis flip / swap, G = 32)
 int launch_run_dist(const DevModel& m, const RunArgs& a, bool kone, int usher, const LaunchCfg& lc);
 // Wang-Landau variants

@@ -1,0 +1,432 @@
+// Speculative-batch Metropolis kernel for the TABLE-FLIP usher (sm_100a).
+//
+// The classic kernel (lmc_kernels.cuh) spends a whole warp on one table-flip step: two Philox blocks, the
+// direction choice, up to eight sequential site picks (a rank select over species bit-planes each) and the
+// a-priori factor are scalar work replicated 32 wide -- ~2400 warp instructions per step on BASELINE config 5,
+// of which the record evaluation is a tenth.  Here, as in lmc_spec.cuh, a warp still owns one walker but each
+// group of four lanes proposes and evaluates a DIFFERENT upcoming step (eight per batch) against the current
+// state; steps up to the first accepted one are exactly the sequential chain of smol (kernel/base.py:145-166,
+// mcusher.py:553-711), the accepted step is committed by the whole warp and the rest is proposed again.
+//
+// A step changes up to four sites.  Flip f of a step must see flips < f of the SAME step applied
+// (expansion.py:217-229) while the other seven steps of the batch read the unchanged occupancy, so nothing is
+// written during the evaluation: the gathers of flip f compare their site against the f earlier ones
+// (spec_flip_energy_n<f>).  The Ewald term comes from the walker's potential cache (lmc.h: ewald_field_dev) with
+// the cross terms K[site_h][site_f] of the step's earlier flips, as in the classic kernel.
+#pragma once
+#include "lmc_spec.cuh"
+
+namespace lmc {
+
+// occupancy code of site s with the NP earlier flips of the step applied
+template <int NP>
+__device__ __forceinline__ uint32_t spec_code_n(const uint8_t* occ, uint32_t s, const uint32_t (&ps)[3], const uint32_t (&pc)[3]) {
+  uint32_t c = occ[s];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) c = (s == ps[i]) ? pc[i] : c;
+  return c;
+}
+
+// scaled energy change of one flip over the merged records (lane l of four takes every fourth 16-byte chunk)
+template <int NP>
+__device__ __forceinline__ double spec_flip_energy_n(const DevModel& m, const uint8_t* occ, const double* dtab, int site, int oldc,
+                                                     int newc, int l, const uint32_t (&ps)[3], const uint32_t (&pc)[3]) {
+  const uint4* rp = reinterpret_cast<const uint4*>(m.sp_rec + (size_t)site * m.spSb) + l;
+  const double* Dn = dtab + newc * m.spL + oldc;   // the old code is the fastest index of a block
+  const uint32_t NC = (uint32_t)m.spNC;
+  double a0 = 0.0, a1 = 0.0;
+  const int nchunk = m.spNQ / 8;   // spNQ is a multiple of 8
+#pragma unroll 2
+  for (int q = 0; q < nchunk; ++q) {
+    const uint4 v = __ldg(rp + q * 4);
+    a0 += Dn[(v.y >> 16) + NC * (spec_code_n<NP>(occ, v.x & 0xffffu, ps, pc) +
+                                 NC * (spec_code_n<NP>(occ, v.x >> 16, ps, pc) + NC * spec_code_n<NP>(occ, v.y & 0xffffu, ps, pc)))];
+    a1 += Dn[(v.w >> 16) + NC * (spec_code_n<NP>(occ, v.z & 0xffffu, ps, pc) +
+                                 NC * (spec_code_n<NP>(occ, v.z >> 16, ps, pc) + NC * spec_code_n<NP>(occ, v.w & 0xffffu, ps, pc)))];
+  }
+  return a0 + a1;
+}
+
+// EWF: Ewald term through the potential cache (a.ew_field).  One block per SM: up to 16 walkers share one copy of
+// the staged tables (the difference table of a five-species model is ~50 KB).
+template <bool KONE, bool EWF>
+__global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, const RunArgs a) {
+  constexpr int SG = 4, SPEC_B = 8, G = 32, MF = LMC_MAX_FLIPS, TF = LMC_MAX_TABLE_FLIPS;
+  constexpr uint32_t FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint64_t bar;
+  const int g = threadIdx.x & 31;
+  const int wl_ = threadIdx.x >> 5;                 // walker slot in block
+  const int w = blockIdx.x * a.wpb + wl_;
+  const int nw_blk = min(a.wpb, a.W - blockIdx.x * a.wpb);
+  const bool active = wl_ < a.wpb && w < a.W;
+  const int sg = g / SG, l = g % SG;
+  const uint32_t gmask = group_mask<SG>();
+
+  unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
+  uint8_t* occ_rows = wbase;
+  unsigned char* rest = wbase + (size_t)a.wpb * m.Npad;
+  uint8_t* occ = occ_rows + (size_t)wl_ * m.Npad;
+  unsigned char* priv = rest + (size_t)wl_ * a.walker_smem;
+  double* feat = reinterpret_cast<double*>(priv + a.off_feat);
+  unsigned char* stash0 = priv + a.off_stash;       // ONE slot: the commit evaluates and folds flip by flip
+  int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
+  uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [32] x (word 0, word 1, word 2, float log u) of block 0
+  uint4* ring2 = ring + 32;                                    // [32] x block 1 (words 4..7 of the step)
+  double* tfc = reinterpret_cast<double*>(priv + a.off_tfc);   // [weights][cumulative][log a-priori][sum], see lmc_kernels.cuh
+
+  stage_tables(m, smem, &bar, occ_rows, a.occ + (size_t)blockIdx.x * a.wpb * m.Npad, (uint32_t)(nw_blk * m.Npad),
+               (uint32_t)m.blob_bytes);
+  const SmemTables t = smem_tables(m, smem);
+  const double* dtab = reinterpret_cast<const double*>(smem + m.off_dtab);
+  if (!active) return;
+  if (g == 0) occ[m.N] = 0;   // pad byte behind the row: the zero code gathered by unused record slots
+
+  for (int f = g; f < m.F; f += G) feat[f] = a.features[(size_t)w * m.F + f];
+  double enth = a.enthalpy[w];
+  for (int i = g; i < LMC_MAX_SUBLATTICES * LMC_MAX_CODES; i += G) cnt[i] = 0;
+  for (int i = g; i < m.plane_words; i += G) planes[i] = 0u;
+  __syncwarp();
+  for (int sl = 0; sl < m.nSl; ++sl) {
+    const int n_act = m.sl_off[sl + 1] - m.sl_off[sl], nw = m.sl_nwords[sl];
+    for (int wd = g; wd < nw; wd += G) {
+      const int jn = min(32, n_act - 32 * wd);
+      for (int b = 0; b < jn; ++b) {
+        const int code = occ[site_of_pos(m, sl, wd * 32 + b)];
+        planes[m.sl_plane_off[sl] + code * nw + wd] |= 1u << b;
+        atomicAdd(&cnt[sl * LMC_MAX_CODES + code], 1);
+      }
+    }
+  }
+  __syncwarp();
+
+  const unsigned long long seed = a.seeds[w];
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t wid = (uint32_t)(a.walker_base + w);
+  const double beta = a.beta[w];
+  const double nat_mu = m.muW ? t.nat[m.muF] : 0.0;
+  const double nat_ew = EWF ? t.nat[m.ewF] : 0.0;
+  double* fld = EWF ? a.ew_field + (size_t)w * m.N : nullptr;
+
+  unsigned long long step = a.step0;
+  unsigned long long rbase = step;
+  bool ring_valid = false, tfc_valid = false;
+  long long nacc_total = 0;
+  for (long long s = 0; s < a.S; ++s) {
+    int nacc = 0;
+    bool accepted = true;
+    int it = 0;
+    while (it < a.thin) {
+      __syncwarp();
+      const int nb = min(SPEC_B, a.thin - it);
+      if (!ring_valid || step + (unsigned long long)nb > rbase + 32ull) {
+        // random words of the next 32 steps, one step per lane: blocks 0 and 1
+        rbase = step;
+        const unsigned long long st_ = step + (unsigned long long)g;
+        const U4 b0 = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 0u, wid, k0, k1);
+        const U4 b1 = philox4x32_10((uint32_t)st_, (uint32_t)(st_ >> 32), 1u, wid, k0, k1);
+        __syncwarp();
+        ring[g] = make_uint4(b0.x, b0.y, b0.z, __float_as_uint(log_u_float(b0.w)));
+        ring2[g] = make_uint4(b1.x, b1.y, b1.z, b1.w);
+        __syncwarp();
+        ring_valid = true;
+      }
+      int nd[LMC_MAX_DIMS];
+      for (int d = 0; d < m.tfD; ++d)
+        nd[d] = m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
+      if (!tfc_valid) {
+        // direction weights, cumulative probabilities and a-priori factors of the current species counts
+        // (whole warp; the same expressions in the same order as the classic kernel)
+        double tw[2 * TF];
+        const double sum = tf_masked_weights<G>(m, nd, tw, g, FULL);
+        __syncwarp();
+        if (g == 0) {
+          double cum = 0.0;
+          for (int i = 0; i < 2 * m.tfNF; ++i) {
+            cum += tw[i] / sum;
+            tfc[i] = tw[i];
+            tfc[2 * TF + i] = cum;
+          }
+          tfc[6 * TF] = sum;
+        }
+        for (int i = 0; i < 2 * m.tfNF; ++i) {
+          double lfi = 0.0;
+          if (sum > 0.0 && tw[i] > 0.0) {
+            const int sgn_i = (i & 1) ? -1 : 1;
+            const int* urow_i = m.tf_table[i >> 1];
+            int nn[LMC_MAX_DIMS];
+            for (int d = 0; d < m.tfD; ++d) nn[d] = nd[d] + sgn_i * urow_i[d];
+            double tw2[2 * TF];
+            const double sum2 = tf_masked_weights<G>(m, nn, tw2, g, FULL);
+            const double p_now = (1.0 - m.tf_sw) * tw[i] / sum;
+            const double p_next = (1.0 - m.tf_sw) * tw2[i ^ 1] / sum2;
+            lfi = log(p_next / p_now);
+            for (int d = 0; d < m.tfD; ++d)
+              if (urow_i[d] != 0) lfi += __ldg(m.lgam + nd[d]) - __ldg(m.lgam + nn[d]);
+          }
+          if (g == 0) tfc[4 * TF + i] = lfi;
+        }
+        __syncwarp();
+        tfc_valid = true;
+      }
+
+      // ------------------------------ propose (one step per four-lane group) ------------------
+      const bool live = sg < nb;
+      const int ri = min((int)(step - rbase) + sg, 31);
+      const unsigned long long mystep = rbase + (unsigned long long)ri;
+      const uint4 rq = ring[ri];
+      const uint4 r1 = ring2[ri];
+      const float lf = __uint_as_float(rq.w);
+      Step<MF> st;
+      st.n = 0;
+      st.log_priori = 0.0;
+#pragma unroll
+      for (int i = 0; i < MF; ++i) { st.site[i] = 0; st.oldc[i] = 0; st.newc[i] = 0; st.sl[i] = 0; st.pos[i] = 0; }
+      int tf_idx = -1;
+      const double tfsum = tfc[6 * TF];
+      const bool do_swap = u01(rq.x) < m.tf_sw || !(tfsum > 0.0);
+      if (do_swap) {
+        // fallback swap of the table-flip usher (mcusher.py:597-600): Swap.propose_step on words 4, 5, 6
+        const int sl = choose_sublattice(m, r1.x);
+        const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+        const int j = (int)mulhi32(r1.y, (uint32_t)n_act);
+        const int site1 = site_of_pos(m, sl, j);
+        const int s1 = occ[site1];
+        const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
+        if (ndiff > 0) {
+          const int k = (int)mulhi32(r1.z, (uint32_t)ndiff);
+          const int p2 = select_pos<SG>(m, planes, sl, s1, k, true, l, gmask);
+          const int site2 = site_of_pos(m, sl, p2);
+          const int s2 = occ[site2];
+          st.n = 2;
+          st.site[0] = site1; st.oldc[0] = s1; st.newc[0] = s2; st.sl[0] = sl; st.pos[0] = j;
+          st.site[1] = site2; st.oldc[1] = s2; st.newc[1] = s1; st.sl[1] = sl; st.pos[1] = p2;
+        }
+      } else {
+        // choose_section_from_partition, utils/math.py:870-893
+        const double u = u01(rq.y);
+        tf_idx = 2 * m.tfNF - 1;
+        for (int i = 0; i < 2 * m.tfNF; ++i)
+          if (tfc[2 * TF + i] > u && tfc[i] > 0.0) { tf_idx = i; break; }
+        // table flip: sequential picks, one random word each (words 4.. of the step), mcusher.py:602-639
+        const int sgn = (tf_idx & 1) ? -1 : 1;
+        const int* urow = m.tf_table[tf_idx >> 1];
+        int wi = 0;
+        U4 rb{r1.x, r1.y, r1.z, r1.w};
+        int cur_blk = 1;
+        auto next_word = [&]() -> uint32_t {
+          const int b = 1 + (wi >> 2);
+          if (b != cur_blk) { rb = philox4x32_10((uint32_t)mystep, (uint32_t)(mystep >> 32), (uint32_t)b, wid, k0, k1); cur_blk = b; }
+          const int c = wi & 3;
+          ++wi;
+          return c == 0 ? rb.x : c == 1 ? rb.y : c == 2 ? rb.z : rb.w;
+        };
+        int d0 = 0;
+        while (d0 < m.tfD) {
+          const int sl = m.tf_dim_sl[d0];
+          int d1 = d0 + 1;
+          while (d1 < m.tfD && m.tf_dim_sl[d1] == sl) ++d1;
+          if (sl >= 0) {
+            int pool[LMC_MAX_FLIPS], ppos[LMC_MAX_FLIPS];
+            int npool = 0;
+            for (int d = d0; d < d1; ++d) {
+              const int ud = sgn * urow[d];
+              if (ud >= 0) continue;
+              int ranks[LMC_MAX_FLIPS];
+              int nr = 0;
+              for (int p = 0; p < -ud; ++p) {
+                int idx = (int)mulhi32(next_word(), (uint32_t)(nd[d] - p));
+                for (int q = 0; q < nr; ++q) if (idx >= ranks[q]) ++idx;
+                int q = nr;
+                while (q > 0 && ranks[q - 1] > idx) { ranks[q] = ranks[q - 1]; --q; }
+                ranks[q] = idx; ++nr;
+                const int pp = select_pos<SG>(m, planes, sl, m.tf_dim_code[d], idx, false, l, gmask);
+                if (npool < LMC_MAX_FLIPS) { pool[npool] = site_of_pos(m, sl, pp); ppos[npool] = pp; ++npool; }
+              }
+            }
+            for (int d = d0; d < d1; ++d) {
+              const int ud = sgn * urow[d];
+              if (ud <= 0) continue;
+              for (int p = 0; p < ud; ++p) {
+                const int idx = (int)mulhi32(next_word(), (uint32_t)npool);
+                const int site = pool[idx], pp = ppos[idx];
+                for (int q = idx; q + 1 < npool; ++q) { pool[q] = pool[q + 1]; ppos[q] = ppos[q + 1]; }
+                --npool;
+                push_flip(st, site, occ[site], m.tf_dim_code[d], sl, pp);
+              }
+            }
+          }
+          d0 = d1;
+        }
+        st.log_priori = tfc[4 * TF + tf_idx];   // compute_log_priori_factor, mcusher.py:656-711 (tabulated per direction)
+      }
+
+      // ------------------------------ evaluate ------------------------------------------------
+      // the groups took different paths through the proposal (swap / table flip, different numbers of picks): bring the
+      // warp back together, or the record loops below run once per group
+      __syncwarp();
+      double dmu = 0.0, dEw = 0.0;
+      if (m.muW) {
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          if (f < st.n) dmu += mu_of(m, st.site[f], st.newc[f], st.sl[f]) - mu_of(m, st.site[f], st.oldc[f], st.sl[f]);
+      }
+      if (EWF) {
+        // flip f sees the potential shifted by the step's earlier flips (ewald.py:168-181)
+        double dq[MF];
+#pragma unroll
+        for (int f = 0; f < MF; ++f) dq[f] = 0.0;
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          if (f < st.n) {
+            const double2 qn = ewald_qd(m, st.site[f], st.newc[f], st.sl[f]), qo = ewald_qd(m, st.site[f], st.oldc[f], st.sl[f]);
+            dq[f] = qn.x - qo.x;
+            double phi = fld[st.site[f]];
+#pragma unroll
+            for (int h = 0; h < f; ++h) phi += dq[h] * __ldg(m.ewK + (size_t)st.site[h] * m.N + st.site[f]);
+            dEw += 2.0 * dq[f] * phi + (qn.y - qo.y);
+          }
+      }
+      // (a full-warp barrier in front of every record loop: the groups hold steps with two, three or four flips and
+      // must walk each loop together)
+      double acc = 0.0;
+      uint32_t ps[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, pc[3] = {0u, 0u, 0u};
+      __syncwarp();
+      if (live && st.n > 0) acc = spec_flip_energy_n<0>(m, occ, dtab, st.site[0], st.oldc[0], st.newc[0], l, ps, pc);
+      ps[0] = (uint32_t)st.site[0]; pc[0] = (uint32_t)st.newc[0];
+      __syncwarp();
+      if (live && st.n > 1) acc += spec_flip_energy_n<1>(m, occ, dtab, st.site[1], st.oldc[1], st.newc[1], l, ps, pc);
+      ps[1] = (uint32_t)st.site[1]; pc[1] = (uint32_t)st.newc[1];
+      __syncwarp();
+      if (__any_sync(FULL, live && st.n > 2)) {
+        if (live && st.n > 2) acc += spec_flip_energy_n<2>(m, occ, dtab, st.site[2], st.oldc[2], st.newc[2], l, ps, pc);
+        ps[2] = (uint32_t)st.site[2]; pc[2] = (uint32_t)st.newc[2];
+        __syncwarp();
+        if (live && st.n > 3) acc += spec_flip_energy_n<3>(m, occ, dtab, st.site[3], st.oldc[3], st.newc[3], l, ps, pc);
+        __syncwarp();
+      }
+      acc += __shfl_xor_sync(FULL, acc, 1);
+      acc += __shfl_xor_sync(FULL, acc, 2);
+      double dH = acc;
+      if (EWF) dH += nat_ew * dEw;
+      if (m.muW) dH += nat_mu * dmu;
+
+      // ------------------------------ accept (metropolis.py:31-49) ----------------------------
+      const double exponent = __dadd_rn(__dmul_rn(-beta, dH), st.log_priori);
+      const int af = accept_fast(exponent, lf);
+      bool acc_ = af != 0;
+      if (af < 0)
+        acc_ = exponent > log(u01(philox4x32_10((uint32_t)mystep, (uint32_t)(mystep >> 32), 0u, wid, k0, k1).w));
+      const uint32_t bal = __ballot_sync(FULL, acc_ && live);
+      if (bal == 0u) {
+        step += (unsigned long long)nb;
+        it += nb;
+        accepted = false;
+        continue;
+      }
+
+      // ------------------------------ commit the first accepted step --------------------------
+      const int src = __ffs(bal) - 1;
+      const int j = src / SG;
+      const int c_n = __shfl_sync(FULL, st.n, src);
+      const bool c_tf = __shfl_sync(FULL, tf_idx, src) >= 0;
+      const double c_dH = __shfl_sync(FULL, dH, src);
+      const double c_dmu = __shfl_sync(FULL, dmu, src);
+      const double c_dEw = __shfl_sync(FULL, dEw, src);
+      int c_site[MF], c_old[MF], c_new[MF], c_sl[MF], c_pos[MF];
+#pragma unroll
+      for (int f = 0; f < MF; ++f) {
+        c_site[f] = __shfl_sync(FULL, st.site[f], src);
+        c_old[f] = __shfl_sync(FULL, st.oldc[f], src);
+        c_new[f] = __shfl_sync(FULL, st.newc[f], src);
+        c_sl[f] = __shfl_sync(FULL, st.sl[f], src);
+        c_pos[f] = __shfl_sync(FULL, st.pos[f], src);
+      }
+      if (EWF && c_n > 0) {
+        // the changed charges shift the potential cache (rows of K), as in the classic kernel
+        double dq[MF];
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          dq[f] = f < c_n ? ewald_qd(m, c_site[f], c_new[f], c_sl[f]).x - ewald_qd(m, c_site[f], c_old[f], c_sl[f]).x : 0.0;
+#pragma unroll 4
+        for (int k = g; k < m.N; k += G) {
+          double v = fld[k];
+#pragma unroll
+          for (int f = 0; f < MF; ++f)
+            if (f < c_n) v += dq[f] * __ldg(m.ewK + (size_t)c_site[f] * m.N + k);
+          fld[k] = v;
+        }
+        if (g == 0) feat[m.ewF] += c_dEw;
+      }
+      // classic record path flip by flip: per-record differences in the reference's cluster order (evaluator.pyx:253-263)
+      // for the feature update; flip f is evaluated with flips < f written to the occupancy
+#pragma unroll
+      for (int f = 0; f < MF; ++f)
+        if (f < c_n) {   // uniform
+          const RecChunk pre = load_records<G>(m, c_site[f], g);
+          (void)flip_energy<G, KONE>(m, t, occ, c_site[f], c_old[f], c_new[f], stash0, g, pre);
+          __syncwarp();
+          flip_features<G, KONE>(m, t, c_site[f], stash0, feat, g, load_segment<G>(m, c_site[f], g));
+          __syncwarp();
+          if (g == 0) {
+            occ[c_site[f]] = (uint8_t)c_new[f];
+            cnt[c_sl[f] * LMC_MAX_CODES + c_old[f]]--;
+            cnt[c_sl[f] * LMC_MAX_CODES + c_new[f]]++;
+            const int nw = m.sl_nwords[c_sl[f]];
+            uint32_t* pl = planes + m.sl_plane_off[c_sl[f]] + (c_pos[f] >> 5);
+            const uint32_t bit = 1u << (c_pos[f] & 31);
+            pl[c_old[f] * nw] ^= bit;
+            pl[c_new[f] * nw] ^= bit;
+          }
+          __syncwarp();
+        }
+      if (g == 0 && m.muW && c_n > 0) feat[m.muF] += c_dmu;
+      __syncwarp();
+      if (c_tf) tfc_valid = false;   // the species counts changed
+      enth += c_dH;
+      ++nacc;
+      accepted = true;
+      step += (unsigned long long)(j + 1);
+      it += j + 1;
+    }  // thin
+
+    // ------------------------------ sample trace ------------------------------------------
+    nacc_total += nacc;
+    const size_t sw = (size_t)s * a.W + w;
+    if (a.tr_occ) {
+      int8_t* dst = a.tr_occ + sw * m.N;
+      if ((m.N & 15) == 0) {
+        if (g == 0) {
+          fence_proxy_async();
+          tma_store_1d(dst, occ, (uint32_t)m.N);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+      } else {
+        for (int i = g; i < m.N; i += G) dst[i] = (int8_t)occ[i];
+      }
+    }
+    if (a.tr_feat)
+      for (int f = g; f < m.F; f += G) a.tr_feat[sw * m.F + f] = feat[f];
+    if (g == 0) {
+      if (a.tr_enth) a.tr_enth[sw] = enth;
+      if (a.tr_acc) a.tr_acc[sw] = accepted ? 1 : 0;
+      if (a.tr_nacc) a.tr_nacc[sw] = nacc;
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------ final state ---------------------------------------------
+  for (int i = g; i < m.N; i += G) a.occ[(size_t)w * m.Npad + i] = (int8_t)occ[i];
+  for (int f = g; f < m.F; f += G) a.features[(size_t)w * m.F + f] = feat[f];
+  if (g == 0) {
+    a.enthalpy[w] = enth;
+    if (a.stats) {
+      atomicAdd(a.stats, (unsigned long long)nacc_total);
+      atomicAdd(a.stats + 1, (unsigned long long)(a.S * (long long)a.thin));
+    }
+  }
+}
+
+}  // namespace lmc

@@ -163,7 +163,8 @@ def test_sharded_sampler_on_two_gpus_equals_one_rank(cuda_device, tmp_path):
 
 def test_config5_full_cell_table_flips_bit_exact_vs_oracle(cuda_device):
     """12x12x12 five-species rocksalt + Ewald (N = 3456, E = 8640), charge-neutral table flips: 2 walkers x 600
-    steps against the oracle's TableFlip (kernel/mcusher.py:553-711), occupancies bit-exact; both Ewald paths"""
+    steps against the oracle's TableFlip (kernel/mcusher.py:553-711), occupancies bit-exact; both Ewald paths of the
+    classic kernel and the speculative table-flip kernel (the default while few steps are accepted)"""
     from oracle import lmc_oracle as O
     wk = WK.get(5)
     ens = wk.product_ensemble()
@@ -174,8 +175,8 @@ def test_config5_full_cell_table_flips_bit_exact_vs_oracle(cuda_device):
     ref = O.run_sampler(kernels, occ0, 600, 100)
     assert ref["n_accepted"].sum() > 100
     scale = np.abs(ref["features"]).max()
-    for field in (False, True):
-        smp = wk.sampler(ens, W, seeds, ewald_field=field)
+    for field, spec_mode in ((False, 1), (True, 1), (True, 2), ("auto", 0)):
+        smp = wk.sampler(ens, W, seeds, ewald_field=field, spec_mode=spec_mode)
         smp.run(600, occ0, thin_by=100)
         s = smp.samples
         np.testing.assert_array_equal(s.get_occupancies(flat=False), ref["occupancy"])

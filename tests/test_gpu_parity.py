@@ -326,11 +326,16 @@ def test_wang_landau_flip_trajectory(cuda_device, wl_arrays, monkeypatch):
     np.testing.assert_array_equal(smp2.samples.get_trace_value("histogram", flat=False), ref["histogram"][:10])
 
 
-@pytest.mark.parametrize("group,factorize", [(8, "1"), (32, "1"), (32, "gather"), (32, "0")])
+@pytest.mark.parametrize("group,factorize", [(8, "1"), (32, "1"), (32, "gather"), (32, "0"), (0, "spec"), (0, "spec-noewald"),
+                                             (0, "classic")])
 def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, monkeypatch):
     """factorize=1: potential cache (flips of one step chained through elements of the site kernel);
-    gather: one row of K per flip; 0: generic matrix rows"""
+    gather: one row of K per flip; 0: generic matrix rows; spec: speculative batches (csrc/lmc_spec_tf.cuh: eight steps
+    per warp, flips of a step patched into the gathers of the later ones), with and without the Ewald term; classic:
+    the automatic choice switched off"""
     monkeypatch.setenv("LMC_EWALD_FACTORIZE", "0" if factorize == "0" else "1")
+    spec = factorize.startswith("spec")
+    noew = factorize == "spec-noewald"
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
@@ -342,11 +347,12 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
     ewm, ewi = L.ewald_matrix(sub, scm)
     comp = S.CompositeProcessor(sub, scm)
     comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
-    comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.05, ewald_matrix=ewm, ewald_inds=ewi))
+    if not noew:
+        comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.05, ewald_matrix=ewm, ewald_inds=ewi))
     mus = {"Li+": 0.0, "Mn3+": 0.4, "Ti4+": -0.3, "O2-": 0.1, "F-": 0.0}
     ens_g = S.Ensemble(comp, chemical_potentials=mus)
-    ora_p = O.CompositeProcessor([O.ClusterDecompositionProcessor(sub, scm, it),
-                                  O.EwaldProcessor(ewm, ewi, 0.05)])
+    ora_p = O.CompositeProcessor([O.ClusterDecompositionProcessor(sub, scm, it)] +
+                                 ([] if noew else [O.EwaldProcessor(ewm, ewi, 0.05)]))
 
     def ens_o():
         return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices), chemical_potentials=mus)
@@ -360,9 +366,12 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
         occ0[w, :ncell] = rng.permutation(cat)
         occ0[w, ncell:] = rng.permutation(ani)
     seeds = np.arange(900, 900 + W)
-    smp, ref, _ = _run_both(ens_g, ens_o, "table_flip", W, 400, 20, occ0, seeds, T=2000.0,
-                            usher_kwargs=dict(flip_table=table, swap_weight=0.2, ewald_field=factorize != "gather"
-                                              if factorize != "0" else "auto"), group_size=group)
+    kw = dict(flip_table=table, swap_weight=0.2, ewald_field=factorize != "gather" if factorize != "0" else "auto")
+    if spec:
+        kw.update(spec_mode=2, ewald_field="auto" if noew else True)
+    elif factorize == "classic":
+        kw.update(spec_mode=1, ewald_field=True)
+    smp, ref, _ = _run_both(ens_g, ens_o, "table_flip", W, 400, 20, occ0, seeds, T=2000.0, usher_kwargs=kw, group_size=group)
     _compare_traces(smp, ref)
     # charge neutrality is conserved by construction of the table
     occ = smp.samples.get_occupancies(flat=True)
