@@ -194,9 +194,15 @@ static void build_spec_tables(const LmcModelDesc* d, const std::vector<OrbDev>& 
   // pairs), 2: one cluster + pair terms per record, 1: one cluster per record
   int max_level = 3;
   if (const char* e = getenv("LMC_SPEC_MERGE")) max_level = std::min(3, std::max(1, atoi(e) + 1));
-  size_t budget = 64 * 1024;   // bytes of shared memory the difference table may take
-  if (const char* e = getenv("LMC_SPEC_TABLE_KB")) budget = (size_t)atoi(e) * 1024;
+  // Bytes of shared memory the difference table may take.  Two passes: first the highest level whose table leaves room
+  // for 28 walkers per SM next to seven or two copies of it (flip / swap kernels, blob <= 40 KB); failing that the
+  // highest level that fits ONE copy per SM beside fourteen walkers (the table-flip kernel of lmc_spec_tf.cuh: a
+  // five-species rocksalt model takes 47 KB at level 1 with 152 records per site, 112 KB at level 3 with 64)
+  size_t budgets[2] = {39 * 1024, 114 * 1024};
+  if (const char* e = getenv("LMC_SPEC_TABLE_KB")) budgets[0] = budgets[1] = (size_t)atoi(e) * 1024;
+  for (int pass = 0; pass < 2 && !sp.ok; ++pass)
   for (int level = max_level; level >= 1 && !sp.ok; --level) {
+    const size_t budget = budgets[pass];
     // deduplicated [new][entry] blocks; block 0 = zeros (padding records)
     std::vector<std::vector<double>> store;
     std::vector<std::vector<double>> store_f;   // feature rows of the blocks ([new][entry][F]), want_f only
@@ -1144,9 +1150,9 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (tf_spec) {
     // one stash slot (the commit evaluates and folds flip by flip) and two rings of 32 random-word blocks; the
     // variant is taken when at least four walkers and the whole table blob fit a block
-    const size_t slab = (size_t)m.Npad + (((size_t)m.F * 8 + 15) & ~size_t(15)) + (((size_t)m.Rstride * stash_el + 15) & ~size_t(15)) +
-                        LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4 + ((m.plane_words * 4 + 15) & ~15) + 2 * 32 * 16 +
-                        (6 * LMC_MAX_TABLE_FLIPS + 2) * 8;
+    const size_t slab = (size_t)m.Npad + (((size_t)m.F * 8 + 15) & ~size_t(15)) +
+                        std::max<size_t>(((size_t)m.Rstride * stash_el + 15) & ~size_t(15), 2 * 32 * 16) +
+                        LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4 + ((m.plane_words * 4 + 15) & ~15) + (6 * LMC_MAX_TABLE_FLIPS + 2) * 8;
     if ((((size_t)m.blob_bytes + 15) & ~size_t(15)) + 4 * slab > (size_t)mdl->smem_optin - 1024) {
       if (spec_mode == 2) return fail("the speculative table-flip kernel does not fit this model in shared memory");
       tf_spec = false;
@@ -1154,10 +1160,13 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   }
   if (tf_spec) G = 32;
   const int stash_slots = tf_spec ? 1 : a.max_flips;
-  a.off_cnt = a.off_stash + (int)(((size_t)stash_slots * m.Rstride * stash_el + 15) & ~size_t(15));
+  size_t stash_bytes = ((size_t)stash_slots * m.Rstride * stash_el + 15) & ~size_t(15);
+  if (tf_spec) stash_bytes = std::max<size_t>(stash_bytes, 2 * 32 * 16);   // the two random-word rings live in the idle stash
+  a.off_cnt = a.off_stash + (int)stash_bytes;
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
   a.off_ring = a.off_plane + ((m.plane_words * 4 + 15) & ~15);   // species bit-planes
-  a.off_eidx = a.off_ring + G * 16 * (tf_spec ? 2 : 1);               // per-lane precomputed proposals
+  a.off_eidx = a.off_ring + (tf_spec ? 0 : G * 16);                   // per-lane precomputed proposals
+  if (tf_spec) a.off_ring = a.off_stash;
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists

@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
   uint8_t* occ = occ_rows + (size_t)wl_ * m.Npad;
   unsigned char* priv = rest + (size_t)wl_ * a.walker_smem;
   double* feat = reinterpret_cast<double*>(priv + a.off_feat);
-  unsigned char* stash0 = priv + a.off_stash;       // ONE slot: the commit evaluates and folds flip by flip
+  unsigned char* stash0 = priv + a.off_stash;       // ONE slot: the commit evaluates and folds flip by flip.  Between
+                                                    // commits the slot holds the two random-word rings (a.off_ring ==
+                                                    // a.off_stash): a commit overwrites them, the next batch refills them
   int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
   uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
   uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [32] x (word 0, word 1, word 2, float log u) of block 0
@@ -384,6 +386,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
       if (g == 0 && m.muW && c_n > 0) feat[m.muF] += c_dmu;
       __syncwarp();
       if (c_tf) tfc_valid = false;   // the species counts changed
+      if (c_n > 0) ring_valid = false;   // the stash slot of the commit is where the rings live
       enth += c_dH;
       ++nacc;
       accepted = true;
