@@ -36,7 +36,7 @@ __device__ __forceinline__ double spec_flip_energy_n(const DevModel& m, const ui
   const uint32_t NC = (uint32_t)m.spNC;
   double a0 = 0.0, a1 = 0.0;
   const int nchunk = m.spNQ / 8;   // spNQ is a multiple of 8
-#pragma unroll 2
+#pragma unroll 4
   for (int q = 0; q < nchunk; ++q) {
     const uint4 v = __ldg(rp + q * 4);
     a0 += Dn[(v.y >> 16) + NC * (spec_code_n<NP>(occ, v.x & 0xffffu, ps, pc) +
@@ -134,10 +134,13 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
         __syncwarp();
         ring_valid = true;
       }
-      int nd[LMC_MAX_DIMS];
-      for (int d = 0; d < m.tfD; ++d)
-        nd[d] = m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
+      // species count of table dimension d (shared memory; a per-thread array would live in local memory)
+      auto count_of = [&](int d) -> int {
+        return m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
+      };
       if (!tfc_valid) {
+        int nd[LMC_MAX_DIMS];
+        for (int d = 0; d < m.tfD; ++d) nd[d] = count_of(d);
         // direction weights, cumulative probabilities and a-priori factors of the current species counts
         // (whole warp; the same expressions in the same order as the classic kernel)
         double tw[2 * TF];
@@ -230,21 +233,31 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
           int d1 = d0 + 1;
           while (d1 < m.tfD && m.tf_dim_sl[d1] == sl) ++d1;
           if (sl >= 0) {
-            int pool[LMC_MAX_FLIPS], ppos[LMC_MAX_FLIPS];
+            // picked sites / positions / ranks: four 16-bit fields of one register pair each (indexed by shifts; arrays
+            // indexed at run time would be local memory)
+            unsigned long long pool = 0ull, ppos = 0ull;
             int npool = 0;
             for (int d = d0; d < d1; ++d) {
               const int ud = sgn * urow[d];
               if (ud >= 0) continue;
-              int ranks[LMC_MAX_FLIPS];
+              unsigned long long ranks = 0ull;   // ascending
               int nr = 0;
+              const int ndd = count_of(d);
               for (int p = 0; p < -ud; ++p) {
-                int idx = (int)mulhi32(next_word(), (uint32_t)(nd[d] - p));
-                for (int q = 0; q < nr; ++q) if (idx >= ranks[q]) ++idx;
-                int q = nr;
-                while (q > 0 && ranks[q - 1] > idx) { ranks[q] = ranks[q - 1]; --q; }
-                ranks[q] = idx; ++nr;
+                int idx = (int)mulhi32(next_word(), (uint32_t)(ndd - p));
+                // index among the remaining sites -> rank in the original (ascending-site) list
+                int at = 0;
+                for (int q = 0; q < nr; ++q)
+                  if (idx >= (int)((ranks >> (16 * q)) & 0xffffull)) { ++idx; at = q + 1; }
+                const unsigned long long low = (1ull << (16 * at)) - 1ull;
+                ranks = (ranks & low) | ((unsigned long long)idx << (16 * at)) | ((ranks & ~low) << 16);
+                ++nr;
                 const int pp = select_pos<SG>(m, planes, sl, m.tf_dim_code[d], idx, false, l, gmask);
-                if (npool < LMC_MAX_FLIPS) { pool[npool] = site_of_pos(m, sl, pp); ppos[npool] = pp; ++npool; }
+                if (npool < LMC_MAX_FLIPS) {
+                  pool |= (unsigned long long)site_of_pos(m, sl, pp) << (16 * npool);
+                  ppos |= (unsigned long long)pp << (16 * npool);
+                  ++npool;
+                }
               }
             }
             for (int d = d0; d < d1; ++d) {
@@ -252,8 +265,10 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
               if (ud <= 0) continue;
               for (int p = 0; p < ud; ++p) {
                 const int idx = (int)mulhi32(next_word(), (uint32_t)npool);
-                const int site = pool[idx], pp = ppos[idx];
-                for (int q = idx; q + 1 < npool; ++q) { pool[q] = pool[q + 1]; ppos[q] = ppos[q + 1]; }
+                const int site = (int)((pool >> (16 * idx)) & 0xffffull), pp = (int)((ppos >> (16 * idx)) & 0xffffull);
+                const unsigned long long low = (1ull << (16 * idx)) - 1ull;
+                pool = (pool & low) | ((pool >> 16) & ~low);
+                ppos = (ppos & low) | ((ppos >> 16) & ~low);
                 --npool;
                 push_flip(st, site, occ[site], m.tf_dim_code[d], sl, pp);
               }
@@ -274,21 +289,20 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
         for (int f = 0; f < MF; ++f)
           if (f < st.n) dmu += mu_of(m, st.site[f], st.newc[f], st.sl[f]) - mu_of(m, st.site[f], st.oldc[f], st.sl[f]);
       }
+      // Ewald term: the cached potential of every changed site and the site-kernel elements between them are
+      // loaded here (L2 / HBM) and consumed after the record loops
+      double fl[MF], kx[MF * (MF - 1) / 2];
       if (EWF) {
-        // flip f sees the potential shifted by the step's earlier flips (ewald.py:168-181)
-        double dq[MF];
 #pragma unroll
-        for (int f = 0; f < MF; ++f) dq[f] = 0.0;
+        for (int f = 0; f < MF; ++f) {
+          fl[f] = 0.0;
+          if (f < st.n) fl[f] = fld[st.site[f]];
 #pragma unroll
-        for (int f = 0; f < MF; ++f)
-          if (f < st.n) {
-            const double2 qn = ewald_qd(m, st.site[f], st.newc[f], st.sl[f]), qo = ewald_qd(m, st.site[f], st.oldc[f], st.sl[f]);
-            dq[f] = qn.x - qo.x;
-            double phi = fld[st.site[f]];
-#pragma unroll
-            for (int h = 0; h < f; ++h) phi += dq[h] * __ldg(m.ewK + (size_t)st.site[h] * m.N + st.site[f]);
-            dEw += 2.0 * dq[f] * phi + (qn.y - qo.y);
+          for (int h = 0; h < f; ++h) {
+            kx[f * (f - 1) / 2 + h] = 0.0;
+            if (f < st.n) kx[f * (f - 1) / 2 + h] = __ldg(m.ewK + (size_t)st.site[h] * m.N + st.site[f]);
           }
+        }
       }
       // (a full-warp barrier in front of every record loop: the groups hold steps with two, three or four flips and
       // must walk each loop together)
@@ -307,6 +321,22 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
         __syncwarp();
         if (live && st.n > 3) acc += spec_flip_energy_n<3>(m, occ, dtab, st.site[3], st.oldc[3], st.newc[3], l, ps, pc);
         __syncwarp();
+      }
+      if (EWF) {
+        // flip f sees the potential shifted by the step's earlier flips (ewald.py:168-181)
+        double dq[MF];
+#pragma unroll
+        for (int f = 0; f < MF; ++f) dq[f] = 0.0;
+#pragma unroll
+        for (int f = 0; f < MF; ++f)
+          if (f < st.n) {
+            const double2 qn = ewald_qd(m, st.site[f], st.newc[f], st.sl[f]), qo = ewald_qd(m, st.site[f], st.oldc[f], st.sl[f]);
+            dq[f] = qn.x - qo.x;
+            double phi = fl[f];
+#pragma unroll
+            for (int h = 0; h < f; ++h) phi += dq[h] * kx[f * (f - 1) / 2 + h];
+            dEw += 2.0 * dq[f] * phi + (qn.y - qo.y);
+          }
       }
       acc += __shfl_xor_sync(FULL, acc, 1);
       acc += __shfl_xor_sync(FULL, acc, 2);
