@@ -671,6 +671,9 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     m.off_qtab = (int)off; off += ((size_t)std::max<size_t>(qtab.size(), 2) * 8 + 15) & ~size_t(15);
     m.off_dtab = (int)off; off += (dtab.size() * 8 + 15) & ~size_t(15);
     // environment words: per-class table-base lists and the class of every site (speculative kernels only)
+    // per-sublattice chemical-potential / charge / diagonal tables for the speculative kernels (groups of a warp look up
+    // DIFFERENT entries at once: shared memory serves that, the constant bank serialises it); filled below
+    m.off_ctab = (int)off; off += 3 * LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 8;
     m.blob_bytes = (int)off;      // what every kernel but the environment-word variants stages
     m.off_envtb = (int)off; off += (ev.tbc.size() * 2 + 15) & ~size_t(15);
     m.off_envcls = (int)off; off += (ev.cls.size() + 15) & ~size_t(15);
@@ -823,6 +826,14 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
       }
     }
     if (getenv("LMC_COMPACT_TABLES_OFF")) m.muC = m.qdC = 0;
+    {
+      double ct[3 * LMC_MAX_SUBLATTICES * LMC_MAX_CODES];
+      memcpy(ct, m.mu_c, sizeof(m.mu_c));
+      memcpy(ct + LMC_MAX_SUBLATTICES * LMC_MAX_CODES, m.qc_c, sizeof(m.qc_c));
+      memcpy(ct + 2 * LMC_MAX_SUBLATTICES * LMC_MAX_CODES, m.qg_c, sizeof(m.qg_c));
+      cudaError_t e = cudaMemcpy(const_cast<unsigned char*>(m.blob) + m.off_ctab, ct, sizeof(ct), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { lmc_model_destroy(mdl); return fail(std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
+    }
     int pw = 0, le = 0;
     for (int s = 0; s < m.nSl; ++s) {
       int maxcode = 0;
@@ -1075,7 +1086,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   // auto: only while the staged tables leave room for a full complement of resident walkers per SM
   // 3 = speculative whenever this model / run supports it (decided by the caller from ITS acceptance history:
   // deterministic, unlike the asynchronously refreshed acc_rate of mode 0)
-  const bool use_spec = spec_ok && (spec_mode == 2 || ((spec_mode == 3 || (spec_mode == 0 && mm->acc_rate < 0.35)) && G == 0 && m.blob_bytes <= 40 * 1024));
+  const bool use_spec = spec_ok && (spec_mode == 2 || ((spec_mode == 3 || (spec_mode == 0 && mm->acc_rate < 0.35)) && G == 0 && m.off_ctab <= 40 * 1024));
   if (use_spec) G = 32;
   // lanes per speculated step (lmc_spec.cuh).  Four everywhere: with two or one lane per step (one uses
   // sorted position lists for the swap partner) the scalar work per step shrinks, but 16 / 32 unrelated
@@ -1152,7 +1163,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     // variant is taken when at least four walkers and the whole table blob fit a block
     const size_t slab = (size_t)m.Npad + (((size_t)m.F * 8 + 15) & ~size_t(15)) +
                         std::max<size_t>(((size_t)m.Rstride * stash_el + 15) & ~size_t(15), 2 * 32 * 16) +
-                        LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4 + ((m.plane_words * 4 + 15) & ~15) + (6 * LMC_MAX_TABLE_FLIPS + 2) * 8;
+                        LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4 + ((m.plane_words * 4 + 15) & ~15) + ((m.plane_words * 2 + 15) & ~15) +
+                        (6 * LMC_MAX_TABLE_FLIPS + 2) * 8;
     if ((((size_t)m.blob_bytes + 15) & ~size_t(15)) + 4 * slab > (size_t)mdl->smem_optin - 1024) {
       if (spec_mode == 2) return fail("the speculative table-flip kernel does not fit this model in shared memory");
       tf_spec = false;
@@ -1169,6 +1181,7 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   if (tf_spec) a.off_ring = a.off_stash;
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
+  if (tf_spec) a.off_lists = a.off_eidx + ((m.plane_words * 2 + 15) & ~15);   // (off_eidx: prefix popcounts of the plane words, u16)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   a.off_dist = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
   a.walker_smem = a.off_dist + (dist ? ((3 * m.F * 8 + 15) & ~15) : 0);   // distance processor: vector, delta, new distances

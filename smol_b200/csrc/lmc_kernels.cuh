@@ -374,6 +374,16 @@ __device__ __forceinline__ double2 ewald_qd(const DevModel& m, int site, int cod
 __device__ __forceinline__ double mu_of(const DevModel& m, int site, int code, int sl) {
   return m.muC ? m.mu_c[sl][code] : __ldg(m.mu + site * m.muW + code);
 }
+// the same from the staged copy of the tables (ct = smem + m.off_ctab): the lanes of a speculative warp look up
+// different (sublattice, code) entries in one instruction, which the constant bank would serialise
+__device__ __forceinline__ double mu_of_s(const DevModel& m, const double* ct, int site, int code, int sl) {
+  return m.muC ? ct[sl * LMC_MAX_CODES + code] : __ldg(m.mu + site * m.muW + code);
+}
+__device__ __forceinline__ double2 ewald_qd_s(const DevModel& m, const double* ct, int site, int code, int sl) {
+  constexpr int T = LMC_MAX_SUBLATTICES * LMC_MAX_CODES;
+  return m.qdC ? make_double2(ct[T + sl * LMC_MAX_CODES + code], ct[2 * T + sl * LMC_MAX_CODES + code])
+               : __ldg(m.ewQD + site * m.ewW + code);
+}
 
 template <int G>
 __device__ __forceinline__ int select_pos_scan(const DevModel& m, const uint32_t* planes, int sl, int code, int k, bool ne,

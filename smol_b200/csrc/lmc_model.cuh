@@ -51,6 +51,7 @@ struct DevModel {
   // same row (what ChemicalPotentialManager / an Ewald summation produce): the proposal knows the sublattice, so the
   // lookups come from the parameter bank instead of L2
   int muC, qdC;
+  int off_ctab;            // blob: [mu][charge][diagonal] x [LMC_MAX_SUBLATTICES][LMC_MAX_CODES] doubles (speculative kernels)
   double mu_c[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];
   double qc_c[LMC_MAX_SUBLATTICES][LMC_MAX_CODES], qg_c[LMC_MAX_SUBLATTICES][LMC_MAX_CODES];   // charge, diagonal (two 8-byte tables: a 16-byte element was copied to a misaligned local frame)
   // active sublattices

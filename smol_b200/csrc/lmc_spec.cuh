@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
                (uint32_t)blob_bytes);
   const SmemTables t = smem_tables(m, smem);
   const double* dtab = reinterpret_cast<const double*>(smem + m.off_dtab);
+  const double* ctab = reinterpret_cast<const double*>(smem + m.off_ctab);
   if (!active) return;
   if (g == 0) occ[m.N] = 0;   // pad byte behind the row: the zero code gathered by unused record slots
 
@@ -489,11 +490,11 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
       // Ewald term first: its (L2) loads are in flight while the cluster records are evaluated
       double dEw = 0.0;
       if (EWF && n > 0) {
-        const double2 qn = ewald_qd(m, site1, s2, sl), qo = ewald_qd(m, site1, s1, sl);
+        const double2 qn = ewald_qd_s(m, ctab, site1, s2, sl), qo = ewald_qd_s(m, ctab, site1, s1, sl);
         const double dq1 = qn.x - qo.x;
         dEw = 2.0 * dq1 * fld[site1] + (qn.y - qo.y);
         if (USHER == LMC_USHER_SWAP) {   // site 2 takes s1; it sees the cache shifted by flip 1
-          const double2 qn2 = ewald_qd(m, site2, s1, sl), qo2 = ewald_qd(m, site2, s2, sl);
+          const double2 qn2 = ewald_qd_s(m, ctab, site2, s1, sl), qo2 = ewald_qd_s(m, ctab, site2, s2, sl);
           dEw += 2.0 * (qn2.x - qo2.x) * (fld[site2] + dq1 * __ldg(m.ewK + (size_t)site1 * m.N + site2)) + (qn2.y - qo2.y);
         }
       }
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(MAXT, MINB) lmc_spec_kernel(const DevModel m, 
       double dH = acc;
       if (EWF) dH += nat_ew * dEw;
       if (MU_POSSIBLE && m.muW) {
-        dmu = mu_of(m, site1, s2, sl) - mu_of(m, site1, s1, sl);
+        dmu = mu_of_s(m, ctab, site1, s2, sl) - mu_of_s(m, ctab, site1, s1, sl);
         dH += nat_mu * dmu;
       }
 

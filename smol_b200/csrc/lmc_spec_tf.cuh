@@ -47,6 +47,30 @@ __device__ __forceinline__ double spec_flip_energy_n(const DevModel& m, const ui
   return a0 + a1;
 }
 
+// k-th (0-based) active position of sublattice `sl` that holds species `code` (ne: that does NOT hold it), from the
+// bit-plane of the code and the exclusive prefix popcounts of its words: a binary search over the words and a rank
+// select inside one, by every lane on its own (no shuffles; the scan of select_pos costs four times as much with
+// four lanes per step and 54 words per plane)
+__device__ __forceinline__ int tf_select(const DevModel& m, const uint32_t* planes, const uint16_t* pfx, int sl, int code, int k, bool ne) {
+  const int nw = m.sl_nwords[sl];
+  const int base = m.sl_plane_off[sl] + code * nw;
+  int lo = 0, hi = nw - 1;   // largest word whose prefix rank is <= k
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    const int before = ne ? 32 * mid - (int)pfx[base + mid] : (int)pfx[base + mid];
+    if (before <= k) lo = mid; else hi = mid - 1;
+  }
+  uint32_t word = planes[base + lo];
+  int rem = k - (int)pfx[base + lo];
+  if (ne) {
+    const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+    const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
+    word = ~word & (lo == nw - 1 ? tail : 0xffffffffu);
+    rem = k - (32 * lo - (int)pfx[base + lo]);
+  }
+  return lo * 32 + spec_nth_bit(word, rem);
+}
+
 // EWF: Ewald term through the potential cache (a.ew_field).  One block per SM: up to 16 walkers share one copy of
 // the staged tables (the difference table of a five-species model is ~50 KB).
 template <bool KONE, bool EWF>
@@ -74,6 +98,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
                                                     // a.off_stash): a commit overwrites them, the next batch refills them
   int* cnt = reinterpret_cast<int*>(priv + a.off_cnt);
   uint32_t* planes = reinterpret_cast<uint32_t*>(priv + a.off_plane);
+  uint16_t* pfx = reinterpret_cast<uint16_t*>(priv + a.off_eidx);   // set bits in the earlier words of the same plane
   uint4* ring = reinterpret_cast<uint4*>(priv + a.off_ring);   // [32] x (word 0, word 1, word 2, float log u) of block 0
   uint4* ring2 = ring + 32;                                    // [32] x block 1 (words 4..7 of the step)
   double* tfc = reinterpret_cast<double*>(priv + a.off_tfc);   // [weights][cumulative][log a-priori][sum], see lmc_kernels.cuh
@@ -82,6 +107,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
                (uint32_t)m.blob_bytes);
   const SmemTables t = smem_tables(m, smem);
   const double* dtab = reinterpret_cast<const double*>(smem + m.off_dtab);
+  const double* ctab = reinterpret_cast<const double*>(smem + m.off_ctab);
   if (!active) return;
   if (g == 0) occ[m.N] = 0;   // pad byte behind the row: the zero code gathered by unused record slots
 
@@ -98,6 +124,17 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
         const int code = occ[site_of_pos(m, sl, wd * 32 + b)];
         planes[m.sl_plane_off[sl] + code * nw + wd] |= 1u << b;
         atomicAdd(&cnt[sl * LMC_MAX_CODES + code], 1);
+      }
+    }
+  }
+  __syncwarp();
+  for (int sl = 0; sl < m.nSl; ++sl) {
+    const int nw = m.sl_nwords[sl];
+    for (int c = g; c < m.sl_nplanes[sl]; c += G) {
+      int run = 0;
+      for (int wd = 0; wd < nw; ++wd) {
+        pfx[m.sl_plane_off[sl] + c * nw + wd] = (uint16_t)run;
+        run += __popc(planes[m.sl_plane_off[sl] + c * nw + wd]);
       }
     }
   }
@@ -201,7 +238,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
         const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
         if (ndiff > 0) {
           const int k = (int)mulhi32(r1.z, (uint32_t)ndiff);
-          const int p2 = select_pos<SG>(m, planes, sl, s1, k, true, l, gmask);
+          const int p2 = tf_select(m, planes, pfx, sl, s1, k, true);
           const int site2 = site_of_pos(m, sl, p2);
           const int s2 = occ[site2];
           st.n = 2;
@@ -252,7 +289,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
                 const unsigned long long low = (1ull << (16 * at)) - 1ull;
                 ranks = (ranks & low) | ((unsigned long long)idx << (16 * at)) | ((ranks & ~low) << 16);
                 ++nr;
-                const int pp = select_pos<SG>(m, planes, sl, m.tf_dim_code[d], idx, false, l, gmask);
+                const int pp = tf_select(m, planes, pfx, sl, m.tf_dim_code[d], idx, false);
                 if (npool < LMC_MAX_FLIPS) {
                   pool |= (unsigned long long)site_of_pos(m, sl, pp) << (16 * npool);
                   ppos |= (unsigned long long)pp << (16 * npool);
@@ -287,7 +324,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
       if (m.muW) {
 #pragma unroll
         for (int f = 0; f < MF; ++f)
-          if (f < st.n) dmu += mu_of(m, st.site[f], st.newc[f], st.sl[f]) - mu_of(m, st.site[f], st.oldc[f], st.sl[f]);
+          if (f < st.n) dmu += mu_of_s(m, ctab, st.site[f], st.newc[f], st.sl[f]) - mu_of_s(m, ctab, st.site[f], st.oldc[f], st.sl[f]);
       }
       // Ewald term: the cached potential of every changed site and the site-kernel elements between them are
       // loaded here (L2 / HBM) and consumed after the record loops
@@ -330,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
 #pragma unroll
         for (int f = 0; f < MF; ++f)
           if (f < st.n) {
-            const double2 qn = ewald_qd(m, st.site[f], st.newc[f], st.sl[f]), qo = ewald_qd(m, st.site[f], st.oldc[f], st.sl[f]);
+            const double2 qn = ewald_qd_s(m, ctab, st.site[f], st.newc[f], st.sl[f]), qo = ewald_qd_s(m, ctab, st.site[f], st.oldc[f], st.sl[f]);
             dq[f] = qn.x - qo.x;
             double phi = fl[f];
 #pragma unroll
@@ -410,6 +447,12 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
             const uint32_t bit = 1u << (c_pos[f] & 31);
             pl[c_old[f] * nw] ^= bit;
             pl[c_new[f] * nw] ^= bit;
+          }
+          {   // words behind the flipped position: one set bit fewer in the old code's plane, one more in the new one's
+            const int nw = m.sl_nwords[c_sl[f]];
+            uint16_t* po = pfx + m.sl_plane_off[c_sl[f]] + c_old[f] * nw;
+            uint16_t* pn = pfx + m.sl_plane_off[c_sl[f]] + c_new[f] * nw;
+            for (int wd = (c_pos[f] >> 5) + 1 + g; wd < nw; wd += G) { po[wd] -= 1; pn[wd] += 1; }
           }
           __syncwarp();
         }
