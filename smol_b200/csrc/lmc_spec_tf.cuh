@@ -47,13 +47,52 @@ __device__ __forceinline__ double spec_flip_energy_n(const DevModel& m, const ui
   return a0 + a1;
 }
 
+// The flips of one proposed step, packed into scalar registers (arrays written at a run-time index, as Step<MF> of the
+// classic kernel, were placed in local memory here and every later read of a site waited on L2): 16-bit sites and
+// positions, 4-bit codes and sublattices, flip f in field f.
+struct PackedStep {
+  unsigned long long site, pos;
+  uint32_t codes;   // old codes in bits [4 f, 4 f + 4), new codes in bits [16 + 4 f, 16 + 4 f + 4)
+  uint32_t sl;      // bits [4 f, 4 f + 4)
+  int n;
+  double log_priori;
+  __device__ __forceinline__ void push(int site_, int oldc, int newc, int sl_, int pos_) {
+    if (n < LMC_MAX_FLIPS) {
+      site |= (unsigned long long)(uint32_t)site_ << (16 * n);
+      pos |= (unsigned long long)(uint32_t)pos_ << (16 * n);
+      codes |= ((uint32_t)oldc << (4 * n)) | ((uint32_t)newc << (16 + 4 * n));
+      sl |= (uint32_t)sl_ << (4 * n);
+      ++n;
+    }
+  }
+  __device__ __forceinline__ int site_of(int f) const { return (int)((site >> (16 * f)) & 0xffffull); }
+  __device__ __forceinline__ int pos_of(int f) const { return (int)((pos >> (16 * f)) & 0xffffull); }
+  __device__ __forceinline__ int old_of(int f) const { return (int)((codes >> (4 * f)) & 0xfu); }
+  __device__ __forceinline__ int new_of(int f) const { return (int)((codes >> (16 + 4 * f)) & 0xfu); }
+  __device__ __forceinline__ int sl_of(int f) const { return (int)((sl >> (4 * f)) & 0xfu); }
+};
+
+// Descriptor tables of the usher and the sublattices, copied from the kernel parameters to shared memory once per
+// block: the eight steps of a batch index them with DIFFERENT dimensions / sublattices in one instruction, which the
+// constant bank serves one address at a time (the proposal waited on those loads more than on anything else)
+struct TfShared {
+  int table[LMC_MAX_TABLE_FLIPS][LMC_MAX_DIMS];
+  int dim_sl[LMC_MAX_DIMS], dim_code[LMC_MAX_DIMS];
+  int sl_off[LMC_MAX_SUBLATTICES + 1], sl_nwords[LMC_MAX_SUBLATTICES], sl_plane_off[LMC_MAX_SUBLATTICES], sl_first[LMC_MAX_SUBLATTICES];
+  double sl_cum[LMC_MAX_SUBLATTICES];
+};
+
+__device__ __forceinline__ int tf_site_of_pos(const DevModel& m, const TfShared& ts, int sl, int pos) {
+  return ts.sl_first[sl] >= 0 ? ts.sl_first[sl] + pos : __ldg(m.sl_sites + ts.sl_off[sl] + pos);
+}
+
 // k-th (0-based) active position of sublattice `sl` that holds species `code` (ne: that does NOT hold it), from the
 // bit-plane of the code and the exclusive prefix popcounts of its words: a binary search over the words and a rank
 // select inside one, by every lane on its own (no shuffles; the scan of select_pos costs four times as much with
 // four lanes per step and 54 words per plane)
-__device__ __forceinline__ int tf_select(const DevModel& m, const uint32_t* planes, const uint16_t* pfx, int sl, int code, int k, bool ne) {
-  const int nw = m.sl_nwords[sl];
-  const int base = m.sl_plane_off[sl] + code * nw;
+__device__ __forceinline__ int tf_select(const TfShared& ts, const uint32_t* planes, const uint16_t* pfx, int sl, int code, int k, bool ne) {
+  const int nw = ts.sl_nwords[sl];
+  const int base = ts.sl_plane_off[sl] + code * nw;
   int lo = 0, hi = nw - 1;   // largest word whose prefix rank is <= k
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -63,7 +102,7 @@ __device__ __forceinline__ int tf_select(const DevModel& m, const uint32_t* plan
   uint32_t word = planes[base + lo];
   int rem = k - (int)pfx[base + lo];
   if (ne) {
-    const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+    const int n_act = ts.sl_off[sl + 1] - ts.sl_off[sl];
     const uint32_t tail = (n_act & 31) ? ((1u << (n_act & 31)) - 1u) : 0xffffffffu;
     word = ~word & (lo == nw - 1 ? tail : 0xffffffffu);
     rem = k - (32 * lo - (int)pfx[base + lo]);
@@ -79,13 +118,22 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint64_t bar;
+  __shared__ TfShared ts;
   const int g = threadIdx.x & 31;
   const int wl_ = threadIdx.x >> 5;                 // walker slot in block
   const int w = blockIdx.x * a.wpb + wl_;
   const int nw_blk = min(a.wpb, a.W - blockIdx.x * a.wpb);
   const bool active = wl_ < a.wpb && w < a.W;
   const int sg = g / SG, l = g % SG;
-  const uint32_t gmask = group_mask<SG>();
+  for (int i = threadIdx.x; i < LMC_MAX_TABLE_FLIPS * LMC_MAX_DIMS; i += blockDim.x)
+    ts.table[i / LMC_MAX_DIMS][i % LMC_MAX_DIMS] = m.tf_table[i / LMC_MAX_DIMS][i % LMC_MAX_DIMS];
+  for (int i = threadIdx.x; i < LMC_MAX_DIMS; i += blockDim.x) { ts.dim_sl[i] = m.tf_dim_sl[i]; ts.dim_code[i] = m.tf_dim_code[i]; }
+  for (int i = threadIdx.x; i < LMC_MAX_SUBLATTICES; i += blockDim.x) {
+    ts.sl_off[i] = m.sl_off[i]; ts.sl_nwords[i] = m.sl_nwords[i]; ts.sl_plane_off[i] = m.sl_plane_off[i];
+    ts.sl_first[i] = m.sl_first[i]; ts.sl_cum[i] = m.sl_cum[i];
+    if (i == 0) ts.sl_off[LMC_MAX_SUBLATTICES] = m.sl_off[LMC_MAX_SUBLATTICES];
+  }
+  // (stage_tables below ends with a block-wide barrier: the tables are complete before anyone reads them)
 
   unsigned char* wbase = smem + ((m.blob_bytes + 15) & ~15);
   uint8_t* occ_rows = wbase;
@@ -173,7 +221,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
       }
       // species count of table dimension d (shared memory; a per-thread array would live in local memory)
       auto count_of = [&](int d) -> int {
-        return m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
+        return ts.dim_sl[d] >= 0 ? cnt[ts.dim_sl[d] * LMC_MAX_CODES + ts.dim_code[d]] : 0;
       };
       if (!tfc_valid) {
         int nd[LMC_MAX_DIMS];
@@ -220,30 +268,31 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
       const uint4 rq = ring[ri];
       const uint4 r1 = ring2[ri];
       const float lf = __uint_as_float(rq.w);
-      Step<MF> st;
-      st.n = 0;
+      PackedStep st;
+      st.site = 0ull; st.pos = 0ull; st.codes = 0u; st.sl = 0u; st.n = 0;
       st.log_priori = 0.0;
-#pragma unroll
-      for (int i = 0; i < MF; ++i) { st.site[i] = 0; st.oldc[i] = 0; st.newc[i] = 0; st.sl[i] = 0; st.pos[i] = 0; }
       int tf_idx = -1;
       const double tfsum = tfc[6 * TF];
       const bool do_swap = u01(rq.x) < m.tf_sw || !(tfsum > 0.0);
       if (do_swap) {
         // fallback swap of the table-flip usher (mcusher.py:597-600): Swap.propose_step on words 4, 5, 6
-        const int sl = choose_sublattice(m, r1.x);
-        const int n_act = m.sl_off[sl + 1] - m.sl_off[sl];
+        int sl = 0;   // choose_sublattice
+        if (m.nSl > 1) {
+          const double us = u01(r1.x);
+          while (sl < m.nSl - 1 && !(ts.sl_cum[sl] > us)) ++sl;
+        }
+        const int n_act = ts.sl_off[sl + 1] - ts.sl_off[sl];
         const int j = (int)mulhi32(r1.y, (uint32_t)n_act);
-        const int site1 = site_of_pos(m, sl, j);
+        const int site1 = tf_site_of_pos(m, ts, sl, j);
         const int s1 = occ[site1];
         const int ndiff = n_act - cnt[sl * LMC_MAX_CODES + s1];
         if (ndiff > 0) {
           const int k = (int)mulhi32(r1.z, (uint32_t)ndiff);
-          const int p2 = tf_select(m, planes, pfx, sl, s1, k, true);
-          const int site2 = site_of_pos(m, sl, p2);
+          const int p2 = tf_select(ts, planes, pfx, sl, s1, k, true);
+          const int site2 = tf_site_of_pos(m, ts, sl, p2);
           const int s2 = occ[site2];
-          st.n = 2;
-          st.site[0] = site1; st.oldc[0] = s1; st.newc[0] = s2; st.sl[0] = sl; st.pos[0] = j;
-          st.site[1] = site2; st.oldc[1] = s2; st.newc[1] = s1; st.sl[1] = sl; st.pos[1] = p2;
+          st.push(site1, s1, s2, sl, j);
+          st.push(site2, s2, s1, sl, p2);
         }
       } else {
         // choose_section_from_partition, utils/math.py:870-893
@@ -253,7 +302,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
           if (tfc[2 * TF + i] > u && tfc[i] > 0.0) { tf_idx = i; break; }
         // table flip: sequential picks, one random word each (words 4.. of the step), mcusher.py:602-639
         const int sgn = (tf_idx & 1) ? -1 : 1;
-        const int* urow = m.tf_table[tf_idx >> 1];
+        const int* urow = ts.table[tf_idx >> 1];
         int wi = 0;
         U4 rb{r1.x, r1.y, r1.z, r1.w};
         int cur_blk = 1;
@@ -266,9 +315,9 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
         };
         int d0 = 0;
         while (d0 < m.tfD) {
-          const int sl = m.tf_dim_sl[d0];
+          const int sl = ts.dim_sl[d0];
           int d1 = d0 + 1;
-          while (d1 < m.tfD && m.tf_dim_sl[d1] == sl) ++d1;
+          while (d1 < m.tfD && ts.dim_sl[d1] == sl) ++d1;
           if (sl >= 0) {
             // picked sites / positions / ranks: four 16-bit fields of one register pair each (indexed by shifts; arrays
             // indexed at run time would be local memory)
@@ -289,9 +338,9 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
                 const unsigned long long low = (1ull << (16 * at)) - 1ull;
                 ranks = (ranks & low) | ((unsigned long long)idx << (16 * at)) | ((ranks & ~low) << 16);
                 ++nr;
-                const int pp = tf_select(m, planes, pfx, sl, m.tf_dim_code[d], idx, false);
+                const int pp = tf_select(ts, planes, pfx, sl, ts.dim_code[d], idx, false);
                 if (npool < LMC_MAX_FLIPS) {
-                  pool |= (unsigned long long)site_of_pos(m, sl, pp) << (16 * npool);
+                  pool |= (unsigned long long)tf_site_of_pos(m, ts, sl, pp) << (16 * npool);
                   ppos |= (unsigned long long)pp << (16 * npool);
                   ++npool;
                 }
@@ -307,7 +356,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
                 pool = (pool & low) | ((pool >> 16) & ~low);
                 ppos = (ppos & low) | ((ppos >> 16) & ~low);
                 --npool;
-                push_flip(st, site, occ[site], m.tf_dim_code[d], sl, pp);
+                st.push(site, occ[site], ts.dim_code[d], sl, pp);
               }
             }
           }
@@ -324,7 +373,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
       if (m.muW) {
 #pragma unroll
         for (int f = 0; f < MF; ++f)
-          if (f < st.n) dmu += mu_of_s(m, ctab, st.site[f], st.newc[f], st.sl[f]) - mu_of_s(m, ctab, st.site[f], st.oldc[f], st.sl[f]);
+          if (f < st.n) dmu += mu_of_s(m, ctab, st.site_of(f), st.new_of(f), st.sl_of(f)) - mu_of_s(m, ctab, st.site_of(f), st.old_of(f), st.sl_of(f));
       }
       // Ewald term: the cached potential of every changed site and the site-kernel elements between them are
       // loaded here (L2 / HBM) and consumed after the record loops
@@ -333,11 +382,11 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
 #pragma unroll
         for (int f = 0; f < MF; ++f) {
           fl[f] = 0.0;
-          if (f < st.n) fl[f] = fld[st.site[f]];
+          if (f < st.n) fl[f] = fld[st.site_of(f)];
 #pragma unroll
           for (int h = 0; h < f; ++h) {
             kx[f * (f - 1) / 2 + h] = 0.0;
-            if (f < st.n) kx[f * (f - 1) / 2 + h] = __ldg(m.ewK + (size_t)st.site[h] * m.N + st.site[f]);
+            if (f < st.n) kx[f * (f - 1) / 2 + h] = __ldg(m.ewK + (size_t)st.site_of(h) * m.N + st.site_of(f));
           }
         }
       }
@@ -346,17 +395,17 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
       double acc = 0.0;
       uint32_t ps[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, pc[3] = {0u, 0u, 0u};
       __syncwarp();
-      if (live && st.n > 0) acc = spec_flip_energy_n<0>(m, occ, dtab, st.site[0], st.oldc[0], st.newc[0], l, ps, pc);
-      ps[0] = (uint32_t)st.site[0]; pc[0] = (uint32_t)st.newc[0];
+      if (live && st.n > 0) acc = spec_flip_energy_n<0>(m, occ, dtab, st.site_of(0), st.old_of(0), st.new_of(0), l, ps, pc);
+      ps[0] = (uint32_t)st.site_of(0); pc[0] = (uint32_t)st.new_of(0);
       __syncwarp();
-      if (live && st.n > 1) acc += spec_flip_energy_n<1>(m, occ, dtab, st.site[1], st.oldc[1], st.newc[1], l, ps, pc);
-      ps[1] = (uint32_t)st.site[1]; pc[1] = (uint32_t)st.newc[1];
+      if (live && st.n > 1) acc += spec_flip_energy_n<1>(m, occ, dtab, st.site_of(1), st.old_of(1), st.new_of(1), l, ps, pc);
+      ps[1] = (uint32_t)st.site_of(1); pc[1] = (uint32_t)st.new_of(1);
       __syncwarp();
       if (__any_sync(FULL, live && st.n > 2)) {
-        if (live && st.n > 2) acc += spec_flip_energy_n<2>(m, occ, dtab, st.site[2], st.oldc[2], st.newc[2], l, ps, pc);
-        ps[2] = (uint32_t)st.site[2]; pc[2] = (uint32_t)st.newc[2];
+        if (live && st.n > 2) acc += spec_flip_energy_n<2>(m, occ, dtab, st.site_of(2), st.old_of(2), st.new_of(2), l, ps, pc);
+        ps[2] = (uint32_t)st.site_of(2); pc[2] = (uint32_t)st.new_of(2);
         __syncwarp();
-        if (live && st.n > 3) acc += spec_flip_energy_n<3>(m, occ, dtab, st.site[3], st.oldc[3], st.newc[3], l, ps, pc);
+        if (live && st.n > 3) acc += spec_flip_energy_n<3>(m, occ, dtab, st.site_of(3), st.old_of(3), st.new_of(3), l, ps, pc);
         __syncwarp();
       }
       if (EWF) {
@@ -367,7 +416,7 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
 #pragma unroll
         for (int f = 0; f < MF; ++f)
           if (f < st.n) {
-            const double2 qn = ewald_qd_s(m, ctab, st.site[f], st.newc[f], st.sl[f]), qo = ewald_qd_s(m, ctab, st.site[f], st.oldc[f], st.sl[f]);
+            const double2 qn = ewald_qd_s(m, ctab, st.site_of(f), st.new_of(f), st.sl_of(f)), qo = ewald_qd_s(m, ctab, st.site_of(f), st.old_of(f), st.sl_of(f));
             dq[f] = qn.x - qo.x;
             double phi = fl[f];
 #pragma unroll
@@ -403,14 +452,14 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
       const double c_dH = __shfl_sync(FULL, dH, src);
       const double c_dmu = __shfl_sync(FULL, dmu, src);
       const double c_dEw = __shfl_sync(FULL, dEw, src);
+      PackedStep cs;
+      cs.site = __shfl_sync(FULL, st.site, src); cs.pos = __shfl_sync(FULL, st.pos, src);
+      cs.codes = __shfl_sync(FULL, st.codes, src); cs.sl = __shfl_sync(FULL, st.sl, src);
+      cs.n = c_n; cs.log_priori = 0.0;
       int c_site[MF], c_old[MF], c_new[MF], c_sl[MF], c_pos[MF];
 #pragma unroll
       for (int f = 0; f < MF; ++f) {
-        c_site[f] = __shfl_sync(FULL, st.site[f], src);
-        c_old[f] = __shfl_sync(FULL, st.oldc[f], src);
-        c_new[f] = __shfl_sync(FULL, st.newc[f], src);
-        c_sl[f] = __shfl_sync(FULL, st.sl[f], src);
-        c_pos[f] = __shfl_sync(FULL, st.pos[f], src);
+        c_site[f] = cs.site_of(f); c_old[f] = cs.old_of(f); c_new[f] = cs.new_of(f); c_sl[f] = cs.sl_of(f); c_pos[f] = cs.pos_of(f);
       }
       if (EWF && c_n > 0) {
         // the changed charges shift the potential cache (rows of K), as in the classic kernel
