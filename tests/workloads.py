@@ -345,12 +345,14 @@ class Config5(Workload):
     def built_bytes(self, acceptance, ewald_cache=False):
         N = 2 * self.n_cell ** 3
         if ewald_cache:
-            # potential cache (acceptance below 25 %): per changed site ~241 gathers + the cached potential (8 B) + one
-            # element of K per earlier flip of the step; an accepted step reads one row of K per changed site and
-            # read-modify-writes the walker's potential row
-            b = 2.5 * (241 + 8 + 8 + 1) + acceptance * (2.5 * 8 * N + 16 * N) + (N + 88 + 9) / self.thin_by
-            return b, ("potential cache: per changed site ~241 int8 gathers + 16 B of cached potential / K elements; per "
-                       "ACCEPTED step 2.5 rows of K (8N B each) + the potential row read-modify-write (16N B)")
+            # speculative table-flip kernel + potential cache (while fewer than ~1/3 of the steps are accepted): per
+            # changed site 64 merged records x 3 int8 gathers + the cached potential (8 B) + one element of K per earlier
+            # flip of the step; an ACCEPTED step is re-evaluated with the classic records (~241 gathers per changed
+            # site), reads one row of K per changed site and read-modify-writes the walker's potential row
+            b = 2.5 * (192 + 8 + 8 + 1) + acceptance * (2.5 * (241 + 8 * N) + 16 * N) + (N + 88 + 9) / self.thin_by
+            return b, ("speculative table-flip kernel, potential cache: per changed site 192 int8 gathers (64 merged "
+                       "records) + 16 B of cached potential / K elements; per ACCEPTED step 2.5 x (241 gathers + one row "
+                       "of K, 8N B) + the potential row read-modify-write (16N B)")
         # Ewald through the factorised site kernel: per changed site ~241 gathers + ONE row of K (N f64) + the
         # walker's charge indices (N bytes); k ~ 2.5 changed sites per step
         b = 2.5 * (241 + 8 * N + N + 1) + (N + 88 + 9) / self.thin_by
