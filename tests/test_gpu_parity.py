@@ -327,15 +327,18 @@ def test_wang_landau_flip_trajectory(cuda_device, wl_arrays, monkeypatch):
 
 
 @pytest.mark.parametrize("group,factorize", [(8, "1"), (32, "1"), (32, "gather"), (32, "0"), (0, "spec"), (0, "spec-noewald"),
-                                             (0, "classic")])
+                                             (0, "spec-expansion"), (0, "spec-thin3"), (0, "classic")])
 def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, monkeypatch):
     """factorize=1: potential cache (flips of one step chained through elements of the site kernel);
     gather: one row of K per flip; 0: generic matrix rows; spec: speculative batches (csrc/lmc_spec_tf.cuh: eight steps
     per warp, flips of a step patched into the gathers of the later ones), with and without the Ewald term; classic:
-    the automatic choice switched off"""
+    the automatic choice switched off; spec-expansion: correlation-function basis (several functions per orbit);
+    spec-thin3: sampling intervals shorter than a batch"""
     monkeypatch.setenv("LMC_EWALD_FACTORIZE", "0" if factorize == "0" else "1")
     spec = factorize.startswith("spec")
     noew = factorize == "spec-noewald"
+    expansion = factorize == "spec-expansion"
+    nsteps, thin = (120, 3) if factorize == "spec-thin3" else (400, 20)
     import smol_b200 as S
     from smol_b200 import lattice as L
     O = _oracle()
@@ -346,12 +349,13 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
     it = L.cluster_interaction_tensors(sub, coefs)
     ewm, ewi = L.ewald_matrix(sub, scm)
     comp = S.CompositeProcessor(sub, scm)
-    comp.add_processor(S.ClusterDecompositionProcessor(sub, scm, it))
+    comp.add_processor(S.ClusterExpansionProcessor(sub, scm, coefs) if expansion else S.ClusterDecompositionProcessor(sub, scm, it))
     if not noew:
         comp.add_processor(S.EwaldProcessor(sub, scm, coefficient=0.05, ewald_matrix=ewm, ewald_inds=ewi))
     mus = {"Li+": 0.0, "Mn3+": 0.4, "Ti4+": -0.3, "O2-": 0.1, "F-": 0.0}
     ens_g = S.Ensemble(comp, chemical_potentials=mus)
-    ora_p = O.CompositeProcessor([O.ClusterDecompositionProcessor(sub, scm, it)] +
+    ora_p = O.CompositeProcessor([O.ClusterExpansionProcessor(sub, scm, coefs) if expansion
+                                  else O.ClusterDecompositionProcessor(sub, scm, it)] +
                                  ([] if noew else [O.EwaldProcessor(ewm, ewi, 0.05)]))
 
     def ens_o():
@@ -371,7 +375,7 @@ def test_table_flip_ewald_semigrand_trajectory(cuda_device, group, factorize, mo
         kw.update(spec_mode=2, ewald_field="auto" if noew else True)
     elif factorize == "classic":
         kw.update(spec_mode=1, ewald_field=True)
-    smp, ref, _ = _run_both(ens_g, ens_o, "table_flip", W, 400, 20, occ0, seeds, T=2000.0, usher_kwargs=kw, group_size=group)
+    smp, ref, _ = _run_both(ens_g, ens_o, "table_flip", W, nsteps, thin, occ0, seeds, T=2000.0, usher_kwargs=kw, group_size=group)
     _compare_traces(smp, ref)
     # charge neutrality is conserved by construction of the table
     occ = smp.samples.get_occupancies(flat=True)
