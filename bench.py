@@ -319,7 +319,9 @@ def run_ours(args):
                                                         local_rank, rank, flush)
         e2e = None
         if with_e2e:
-            e2e_steps = max(3, min(steps, 20))
+            # enough back-to-back API calls that the fill / drain of the copy pipeline (first upload, last download) is a
+            # small part of the region: three times the device arm's steps, 20 .. 100
+            e2e_steps = args.e2e_steps or max(20, min(3 * steps, 100))
             e2e_s, h2d, d2h, check = _e2e_arm(wk, smp, smp._occ_dev, W, N, nsteps, thin, e2e_steps, world, dist)
             e2e = (e2e_s, h2d, d2h, e2e_steps, check)
         t = torch.tensor([dev_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
@@ -531,6 +533,7 @@ def main():
                     help="sampling intervals per bench step (default: the config's; raise for a sustained run)")
     ap.add_argument("--strong-walkers", type=int, default=32768, help="config 5: total walkers of the strong-scaling line")
     ap.add_argument("--no-strong", action="store_true", help="config 5: skip the strong-scaling line")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="API calls of the end-to-end arm (default: 3 x steps, 20..100)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-curve", dest="curve", action="store_false",
                     help="skip the acceptance curve (the workload at other temperatures; Metropolis configs, one GPU)")

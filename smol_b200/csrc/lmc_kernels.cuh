@@ -1626,13 +1626,14 @@ __global__ void lmc_ewald_field_kernel(const DevModel m, const int8_t* __restric
 // shared memory (charges looked up on the way in, rows of K coalesced), the next chunk's global loads in flight
 // during the current chunk's FMAs.  Every element of K is read W / 128 times from L2 instead of W / 4 times.
 constexpr int FT_W = 128, FT_S = 64, FT_K = 16;
-__global__ void __launch_bounds__(256) lmc_ewald_field_tiled_kernel(const DevModel m, const int8_t* __restrict__ occ_g, int W,
+__global__ void __launch_bounds__(256, 2) lmc_ewald_field_tiled_kernel(const DevModel m, const int8_t* __restrict__ occ_g, int W,
                                                                     double* __restrict__ field) {
   __shared__ __align__(16) double Qs[FT_K][FT_W];
   __shared__ __align__(16) double Ks[FT_K][FT_S];
   const int tid = threadIdx.x;
   const int s0 = blockIdx.x * FT_S, w0 = blockIdx.y * FT_W;
-  const int ty = tid >> 4, tx = tid & 15;          // walkers ty*8.., sites tx*4..
+  const int ty = tid >> 4, tx = tid & 15;          // walkers ty*8.., sites tx*2, tx*2+1, 32+tx*2, 33+tx*2 (consecutive lanes read
+                                                   // consecutive 16-byte pieces of a Ks row: no bank conflicts)
   // loaders: Q chunk = 16 k x 128 walkers = 2048 charges, 8 per thread (walker = tid >> 1, k = (tid & 1) * 8 ..);
   // K chunk = 16 k x 64 sites = 1024 doubles, 4 per thread (k = tid >> 4, sites (tid & 15) * 4 ..)
   const int qw = tid >> 1, qk = (tid & 1) * 8;
@@ -1676,7 +1677,7 @@ __global__ void __launch_bounds__(256) lmc_ewald_field_tiled_kernel(const DevMod
       }
 #pragma unroll
       for (int j = 0; j < 4; j += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(&Ks[k][tx * 4 + j]);
+        const double2 v = *reinterpret_cast<const double2*>(&Ks[k][(j >> 1) * 32 + tx * 2]);
         b[j] = v.x; b[j + 1] = v.y;
       }
 #pragma unroll
@@ -1691,7 +1692,7 @@ __global__ void __launch_bounds__(256) lmc_ewald_field_tiled_kernel(const DevMod
     if (ww >= W) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int sidx = s0 + tx * 4 + j;
+      const int sidx = s0 + (j >> 1) * 32 + tx * 2 + (j & 1);
       if (sidx < m.N) field[(size_t)ww * m.N + sidx] = acc[i][j];
     }
   }
