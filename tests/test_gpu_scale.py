@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from tests import models as M
+from tests import workloads as WK
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
@@ -188,6 +189,35 @@ def test_config5_table_flip_ewald_full_cell(cuda_device):
         res.append(occ)
     np.testing.assert_array_equal(res[0], res[1])
     assert (res[0][-1] != occ0).any()
+
+
+def test_config5_speculative_table_flips_equal_classic_chains_over_many_sweeps(cuda_device):
+    """BASELINE config 5 (N = 3456), 256 walkers x 12 sweeps (1.06e7 steps) through the equilibration -- acceptance from
+    ~18 % of the first sweep down to a few per cent: the speculative table-flip kernel (csrc/lmc_spec_tf.cuh) and the classic kernel walk
+    the SAME chains (occupancies and accepted-step counts identical at every sample, features / enthalpies to rounding),
+    and the running features equal a full re-evaluation at the end"""
+    wk = WK.get(5)
+    ens = wk.product_ensemble()
+    W = 256
+    occ0 = wk.initial_occupancies(W, seed=5)
+    seeds = list(range(9000, 9000 + W))
+    runs = []
+    for spec_mode in (1, 2):
+        smp = wk.sampler(ens, W, seeds, ewald_field=True, spec_mode=spec_mode)
+        smp.run(12 * wk.thin_by, occ0, thin_by=wk.thin_by)
+        runs.append(smp.samples)
+    a, b = runs
+    np.testing.assert_array_equal(a.get_occupancies(flat=False), b.get_occupancies(flat=False))
+    np.testing.assert_array_equal(a.get_trace_value("n_accepted", flat=False), b.get_trace_value("n_accepted", flat=False))
+    nacc = b.get_trace_value("n_accepted", flat=False)
+    assert nacc[0].mean() > 0.1 * wk.thin_by and 0 < nacc[-1].mean() < 0.5 * nacc[0].mean()     # hot start, then cold
+    fa, fb = a.get_feature_vectors(flat=False), b.get_feature_vectors(flat=False)
+    scale = np.abs(fa).max()
+    np.testing.assert_allclose(fb, fa, rtol=1e-10, atol=1e-10 * scale)
+    np.testing.assert_allclose(b.get_enthalpies(flat=False), a.get_enthalpies(flat=False), rtol=1e-10,
+                               atol=1e-10 * np.abs(a.get_enthalpies(flat=False)).max())
+    full = ens.compute_feature_vector_batch(b.get_occupancies(flat=False)[-1])
+    np.testing.assert_allclose(fb[-1], full, rtol=1e-9, atol=1e-9 * np.abs(full).max())
 
 
 def test_edge_cases(cuda_device):
