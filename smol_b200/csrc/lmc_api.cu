@@ -860,6 +860,35 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     m.tf_dim_code[k] = d->tf_dim_code[k];
   }
   m.tf_sw = d->tf_swap_weight;
+  memset(m.tf_npick, 0, sizeof(m.tf_npick));
+  memset(m.tf_pick, 0, sizeof(m.tf_pick));
+  for (int i = 0; i < 2 * m.tfNF; ++i) {
+    const int sgn = (i & 1) ? -1 : 1;
+    int n = 0;
+    bool fits = true;
+    int d0 = 0;
+    while (d0 < m.tfD) {   // dims of one sublattice are consecutive (occu_utils.py:20-25)
+      const int sl = m.tf_dim_sl[d0];
+      int d1 = d0 + 1;
+      while (d1 < m.tfD && m.tf_dim_sl[d1] == sl) ++d1;
+      if (sl >= 0) {
+        bool first = true;
+        for (int pass = 0; pass < 2; ++pass)
+          for (int dd = d0; dd < d1; ++dd) {
+            const int ud = sgn * m.tf_table[i >> 1][dd];
+            const int cnt = pass == 0 ? -ud : ud;
+            for (int p = 0; p < cnt; ++p) {
+              if (n >= 2 * LMC_MAX_FLIPS) { fits = false; break; }
+              m.tf_pick[i][n++] = (uint32_t)pass | ((uint32_t)sl << 1) | ((uint32_t)m.tf_dim_code[dd] << 4) | ((uint32_t)dd << 8) |
+                                  ((uint32_t)p << 12) | ((first ? 1u : 0u) << 16);
+              first = false;
+            }
+          }
+      }
+      d0 = d1;
+    }
+    m.tf_npick[i] = fits ? n : -1;   // -1: more picks than descriptors (the flip table changes more than 4 sites: refused at lmc_run)
+  }
   {
     int maxn = 1;
     for (int k = 0; k < m.tfD; ++k) maxn = std::max(maxn, m.tf_max_n[k]);

@@ -76,6 +76,13 @@ struct DevModel {
   int tf_dim_sl[LMC_MAX_DIMS];
   int tf_dim_code[LMC_MAX_DIMS];
   double tf_sw;
+  // the site picks of every flip direction in the order TableFlip.propose_step draws them (mcusher.py:602-639: per
+  // sublattice the sites to vacate, dimension by dimension, then the species that take them): one descriptor per
+  // random word -- kind (bit 0: 0 = pick a site holding `code`, 1 = hand a picked site to `code`) | sublattice << 1
+  // | code << 4 | dimension << 8 | pick index inside its dimension << 12 | first pick of a sublattice << 16
+  // (speculative table-flip kernel: every step of a batch walks ONE loop over its descriptors)
+  int tf_npick[2 * LMC_MAX_TABLE_FLIPS];
+  uint32_t tf_pick[2 * LMC_MAX_TABLE_FLIPS][2 * LMC_MAX_FLIPS];
   const double* lgam;      // [max_n + 2] ln(n!) table for the table-flip a-priori factor
   // speculative-batch kernel (lmc_spec.cuh): merged three-gather records + pre-differenced tables
   int spOK;                // tables built (0: model outside the limits of the speculative kernel)

@@ -78,6 +78,8 @@ struct PackedStep {
 struct TfShared {
   int table[LMC_MAX_TABLE_FLIPS][LMC_MAX_DIMS];
   int dim_sl[LMC_MAX_DIMS], dim_code[LMC_MAX_DIMS];
+  int npick[2 * LMC_MAX_TABLE_FLIPS];
+  uint32_t pick[2 * LMC_MAX_TABLE_FLIPS][2 * LMC_MAX_FLIPS];
   int sl_off[LMC_MAX_SUBLATTICES + 1], sl_nwords[LMC_MAX_SUBLATTICES], sl_plane_off[LMC_MAX_SUBLATTICES], sl_first[LMC_MAX_SUBLATTICES];
   double sl_cum[LMC_MAX_SUBLATTICES];
 };
@@ -128,6 +130,9 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
   for (int i = threadIdx.x; i < LMC_MAX_TABLE_FLIPS * LMC_MAX_DIMS; i += blockDim.x)
     ts.table[i / LMC_MAX_DIMS][i % LMC_MAX_DIMS] = m.tf_table[i / LMC_MAX_DIMS][i % LMC_MAX_DIMS];
   for (int i = threadIdx.x; i < LMC_MAX_DIMS; i += blockDim.x) { ts.dim_sl[i] = m.tf_dim_sl[i]; ts.dim_code[i] = m.tf_dim_code[i]; }
+  for (int i = threadIdx.x; i < 2 * LMC_MAX_TABLE_FLIPS * 2 * LMC_MAX_FLIPS; i += blockDim.x)
+    ts.pick[i / (2 * LMC_MAX_FLIPS)][i % (2 * LMC_MAX_FLIPS)] = m.tf_pick[i / (2 * LMC_MAX_FLIPS)][i % (2 * LMC_MAX_FLIPS)];
+  for (int i = threadIdx.x; i < 2 * LMC_MAX_TABLE_FLIPS; i += blockDim.x) ts.npick[i] = m.tf_npick[i];
   for (int i = threadIdx.x; i < LMC_MAX_SUBLATTICES; i += blockDim.x) {
     ts.sl_off[i] = m.sl_off[i]; ts.sl_nwords[i] = m.sl_nwords[i]; ts.sl_plane_off[i] = m.sl_plane_off[i];
     ts.sl_first[i] = m.sl_first[i]; ts.sl_cum[i] = m.sl_cum[i];
@@ -301,8 +306,8 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
         for (int i = 0; i < 2 * m.tfNF; ++i)
           if (tfc[2 * TF + i] > u && tfc[i] > 0.0) { tf_idx = i; break; }
         // table flip: sequential picks, one random word each (words 4.. of the step), mcusher.py:602-639
-        const int sgn = (tf_idx & 1) ? -1 : 1;
-        const int* urow = ts.table[tf_idx >> 1];
+        // one descriptor per random word, in the reference's order (DevModel::tf_pick): the groups of the warp walk the
+        // same loop whatever their direction (nested loops over dimensions and counts left them on different paths)
         int wi = 0;
         U4 rb{r1.x, r1.y, r1.z, r1.w};
         int cur_blk = 1;
@@ -313,54 +318,42 @@ __global__ void __launch_bounds__(512, 1) lmc_spec_tf_kernel(const DevModel m, c
           ++wi;
           return c == 0 ? rb.x : c == 1 ? rb.y : c == 2 ? rb.z : rb.w;
         };
-        int d0 = 0;
-        while (d0 < m.tfD) {
-          const int sl = ts.dim_sl[d0];
-          int d1 = d0 + 1;
-          while (d1 < m.tfD && ts.dim_sl[d1] == sl) ++d1;
-          if (sl >= 0) {
-            // picked sites / positions / ranks: four 16-bit fields of one register pair each (indexed by shifts; arrays
-            // indexed at run time would be local memory)
-            unsigned long long pool = 0ull, ppos = 0ull;
-            int npool = 0;
-            for (int d = d0; d < d1; ++d) {
-              const int ud = sgn * urow[d];
-              if (ud >= 0) continue;
-              unsigned long long ranks = 0ull;   // ascending
-              int nr = 0;
-              const int ndd = count_of(d);
-              for (int p = 0; p < -ud; ++p) {
-                int idx = (int)mulhi32(next_word(), (uint32_t)(ndd - p));
-                // index among the remaining sites -> rank in the original (ascending-site) list
-                int at = 0;
-                for (int q = 0; q < nr; ++q)
-                  if (idx >= (int)((ranks >> (16 * q)) & 0xffffull)) { ++idx; at = q + 1; }
-                const unsigned long long low = (1ull << (16 * at)) - 1ull;
-                ranks = (ranks & low) | ((unsigned long long)idx << (16 * at)) | ((ranks & ~low) << 16);
-                ++nr;
-                const int pp = tf_select(ts, planes, pfx, sl, ts.dim_code[d], idx, false);
-                if (npool < LMC_MAX_FLIPS) {
-                  pool |= (unsigned long long)tf_site_of_pos(m, ts, sl, pp) << (16 * npool);
-                  ppos |= (unsigned long long)pp << (16 * npool);
-                  ++npool;
-                }
-              }
+        // picked sites / positions / ranks: four 16-bit fields of one register pair each (indexed by shifts; arrays
+        // indexed at run time would be local memory)
+        unsigned long long pool = 0ull, ppos = 0ull, ranks = 0ull;
+        int npool = 0, nr = 0;
+        const int npk = ts.npick[tf_idx];
+        for (int k = 0; k < npk; ++k) {
+          const uint32_t pd = ts.pick[tf_idx][k];
+          const int sl = (int)((pd >> 1) & 7u), code = (int)((pd >> 4) & 15u), d = (int)((pd >> 8) & 15u), p = (int)((pd >> 12) & 15u);
+          const uint32_t word = next_word();
+          if (pd & 0x10000u) { pool = 0ull; ppos = 0ull; npool = 0; }   // first pick of a sublattice
+          if (!(pd & 1u)) {
+            // a site that holds `code`: index among the remaining ones -> rank in the ascending-site list
+            if (p == 0) { ranks = 0ull; nr = 0; }
+            int idx = (int)mulhi32(word, (uint32_t)(count_of(d) - p));
+            int at = 0;
+            for (int q = 0; q < nr; ++q)
+              if (idx >= (int)((ranks >> (16 * q)) & 0xffffull)) { ++idx; at = q + 1; }
+            const unsigned long long low = (1ull << (16 * at)) - 1ull;
+            ranks = (ranks & low) | ((unsigned long long)idx << (16 * at)) | ((ranks & ~low) << 16);
+            ++nr;
+            const int pp = tf_select(ts, planes, pfx, sl, code, idx, false);
+            if (npool < LMC_MAX_FLIPS) {
+              pool |= (unsigned long long)tf_site_of_pos(m, ts, sl, pp) << (16 * npool);
+              ppos |= (unsigned long long)pp << (16 * npool);
+              ++npool;
             }
-            for (int d = d0; d < d1; ++d) {
-              const int ud = sgn * urow[d];
-              if (ud <= 0) continue;
-              for (int p = 0; p < ud; ++p) {
-                const int idx = (int)mulhi32(next_word(), (uint32_t)npool);
-                const int site = (int)((pool >> (16 * idx)) & 0xffffull), pp = (int)((ppos >> (16 * idx)) & 0xffffull);
-                const unsigned long long low = (1ull << (16 * idx)) - 1ull;
-                pool = (pool & low) | ((pool >> 16) & ~low);
-                ppos = (ppos & low) | ((ppos >> 16) & ~low);
-                --npool;
-                st.push(site, occ[site], ts.dim_code[d], sl, pp);
-              }
-            }
+          } else {
+            // one of the vacated sites takes `code`
+            const int idx = (int)mulhi32(word, (uint32_t)npool);
+            const int site = (int)((pool >> (16 * idx)) & 0xffffull), pp = (int)((ppos >> (16 * idx)) & 0xffffull);
+            const unsigned long long low = (1ull << (16 * idx)) - 1ull;
+            pool = (pool & low) | ((pool >> 16) & ~low);
+            ppos = (ppos & low) | ((ppos >> 16) & ~low);
+            --npool;
+            st.push(site, occ[site], code, sl, pp);
           }
-          d0 = d1;
         }
         st.log_priori = tfc[4 * TF + tf_idx];   // compute_log_priori_factor, mcusher.py:656-711 (tabulated per direction)
       }
