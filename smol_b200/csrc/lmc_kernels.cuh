@@ -796,13 +796,13 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
       U4 r1blk{0, 0, 0, 0};
       int ms_toggled = 0;   // flips of chained swaps whose plane bits are temporarily toggled
       int tf_idx = -1;
-      int nd[LMC_MAX_DIMS];
       if (USHER == LMC_USHER_TABLEFLIP) {
         // TableFlip.propose_step, mcusher.py:553-639
         r1blk = philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), 1u, wid, k0, k1);
-        for (int d = 0; d < m.tfD; ++d)
-          nd[d] = m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
         if (!tfc_valid) {
+          int nd[LMC_MAX_DIMS];
+          for (int d = 0; d < m.tfD; ++d)
+            nd[d] = m.tf_dim_sl[d] >= 0 ? cnt[m.tf_dim_sl[d] * LMC_MAX_CODES + m.tf_dim_code[d]] : 0;
           // The direction weights (utils/math.py:832-867), their cumulative probabilities and the a-priori factor of
           // every direction (mcusher.py:656-711) depend on the species COUNTS only, which change when a table flip is
           // accepted: evaluated here once per such change (the same expressions, in the same order) and kept in the
@@ -986,22 +986,31 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
           int d1 = d0 + 1;
           while (d1 < m.tfD && m.tf_dim_sl[d1] == sl) ++d1;
           if (sl >= 0) {
-            int pool[LMC_MAX_FLIPS], ppos[LMC_MAX_FLIPS];
+            // picked sites / positions / ranks: four 16-bit fields of one register pair each, indexed by shifts (arrays
+            // indexed at run time live in local memory: every pick then waited on L1 / L2)
+            unsigned long long pool = 0ull, ppos = 0ull;
             int npool = 0;
             for (int d = d0; d < d1; ++d) {
               const int ud = sgn * urow[d];
               if (ud >= 0) continue;
-              int ranks[LMC_MAX_FLIPS];
+              unsigned long long ranks = 0ull;   // ascending
               int nr = 0;
+              const int ndd = cnt[sl * LMC_MAX_CODES + m.tf_dim_code[d]];
               for (int p = 0; p < -ud; ++p) {
-                int idx = (int)mulhi32(next_word(), (uint32_t)(nd[d] - p));
+                int idx = (int)mulhi32(next_word(), (uint32_t)(ndd - p));
                 // index among the remaining sites -> rank in the original (ascending-site) list
-                for (int q = 0; q < nr; ++q) if (idx >= ranks[q]) ++idx;
-                int q = nr;
-                while (q > 0 && ranks[q - 1] > idx) { ranks[q] = ranks[q - 1]; --q; }
-                ranks[q] = idx; ++nr;
+                int at = 0;
+                for (int q = 0; q < nr; ++q)
+                  if (idx >= (int)((ranks >> (16 * q)) & 0xffffull)) { ++idx; at = q + 1; }
+                const unsigned long long low = (1ull << (16 * at)) - 1ull;
+                ranks = (ranks & low) | ((unsigned long long)idx << (16 * at)) | ((ranks & ~low) << 16);
+                ++nr;
                 const int pp = select_pos<G>(m, planes, sl, m.tf_dim_code[d], idx, false, g, gmask);
-                if (npool < LMC_MAX_FLIPS) { pool[npool] = site_of_pos(m, sl, pp); ppos[npool] = pp; ++npool; }
+                if (npool < LMC_MAX_FLIPS) {
+                  pool |= (unsigned long long)site_of_pos(m, sl, pp) << (16 * npool);
+                  ppos |= (unsigned long long)pp << (16 * npool);
+                  ++npool;
+                }
               }
             }
             for (int d = d0; d < d1; ++d) {
@@ -1009,8 +1018,10 @@ lmc_run_kernel(const DevModel m, const RunArgs a) {
               if (ud <= 0) continue;
               for (int p = 0; p < ud; ++p) {
                 const int idx = (int)mulhi32(next_word(), (uint32_t)npool);
-                const int site = pool[idx], pp = ppos[idx];
-                for (int q = idx; q + 1 < npool; ++q) { pool[q] = pool[q + 1]; ppos[q] = ppos[q + 1]; }
+                const int site = (int)((pool >> (16 * idx)) & 0xffffull), pp = (int)((ppos >> (16 * idx)) & 0xffffull);
+                const unsigned long long low = (1ull << (16 * idx)) - 1ull;
+                pool = (pool & low) | ((pool >> 16) & ~low);
+                ppos = (ppos & low) | ((ppos >> 16) & ~low);
                 --npool;
                 push_flip(st, site, occ[site], m.tf_dim_code[d], sl, pp);
               }
