@@ -314,6 +314,15 @@ int lmc_spec_tables_host(const LmcModelDesc* desc, int32_t* info, double* dtab_o
 int lmc_spec_env_host(const LmcModelDesc* desc, int32_t* info, uint16_t* tb_out, int64_t tb_cap, uint32_t* rev_out,
                       int64_t rev_cap, uint8_t* pair_out, int64_t pair_cap);
 
+/* host-only: compact environment words (one 64-bit word per active site and walker in shared memory; the kernel the
+ * library takes for Metropolis flip / swap steps of models whose merged records fit 64 bits per site).  info[8] = {built,
+ * bits per code, records per lane, padded records per lane P, active sites A, reverse entries per site R, site classes C,
+ * bits used}; desc_out [C][4][P] u32 (table base | field shift << 16, lane order), cls_out [N] u8, rev_out [A][R] u32
+ * (gathering active site | bit << 16, 0xffffffff = none), pair_out [A][A] u64 (bits of the row site's word that hold the
+ * column site); each filled when large enough (capacities in elements) */
+int lmc_spec_c64_host(const LmcModelDesc* desc, int32_t* info, uint32_t* desc_out, int64_t desc_cap, uint8_t* cls_out,
+                      int64_t cls_cap, uint32_t* rev_out, int64_t rev_cap, uint64_t* pair_out, int64_t pair_cap);
+
 /* Distance processor state of every walker: features_dev [W][F] holds the EXTENSIVE features on entry
  * (lmc_full_features) and the distance vector on return; vector_dev [W][F] <- features / supercell size;
  * enthalpy_dev [W] <- natural_parameters . distance vector */
@@ -335,6 +344,8 @@ int lmc_ewald_site_kernel(const double* cart_dev, int num_sites, const int32_t* 
 int64_t lmc_launch_count(void);
 /* how many of them were environment-word variants of the speculative kernel (LmcRunConfig.spec_env_dev) */
 int64_t lmc_env_launch_count(void);
+/* ... and how many were launches of the compact-word kernel (lmc_spec_c64_host) */
+int64_t lmc_c64_launch_count(void);
 
 #ifdef __cplusplus
 }

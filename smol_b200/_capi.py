@@ -117,7 +117,7 @@ class LmcRunConfig(C.Structure):
 EXPORTS = (
     "lmc_version", "lmc_last_error", "lmc_row_stride", "lmc_model_create", "lmc_model_destroy",
     "lmc_model_num_features", "lmc_cast_i32_to_i8", "lmc_cast_i8_to_i32", "lmc_full_features",
-    "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_env_launch_count", "lmc_spec_tables_host", "lmc_spec_env_host", "lmc_model_info",
+    "lmc_delta_features", "lmc_run", "lmc_launch_count", "lmc_env_launch_count", "lmc_c64_launch_count", "lmc_spec_tables_host", "lmc_spec_env_host", "lmc_spec_c64_host", "lmc_model_info",
     "lmc_ewald_field", "lmc_bias_init", "lmc_ewald_site_kernel", "lmc_distance_init", "lmc_full_features_field",
 )
 
@@ -160,7 +160,10 @@ def load():
     lib.lmc_distance_init.argtypes = [_P, C.c_int, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, _P]
     lib.lmc_launch_count.restype = C.c_int64
     lib.lmc_env_launch_count.restype = C.c_int64
+    lib.lmc_c64_launch_count.restype = C.c_int64
     lib.lmc_spec_tables_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64]
+    lib.lmc_spec_c64_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64,
+                                      _P, C.c_int64, _P, C.c_int64]
     lib.lmc_spec_env_host.argtypes = [C.POINTER(LmcModelDesc), C.POINTER(C.c_int32), _P, C.c_int64, _P, C.c_int64,
                                       _P, C.c_int64]
     if lib.lmc_version() != LMC_ABI_VERSION:

@@ -32,10 +32,12 @@ def up_to_date() -> bool:
 def _deps(src):
     """files an object depends on: its source, every header, and (for the API unit only) nothing else"""
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    if "lmc_spec_inst" not in src and "lmc_spec_tf_inst" not in src:
+    if "lmc_spec_inst" not in src and "lmc_spec_tf_inst" not in src and "lmc_spec_c64_inst" not in src:
         hdrs = [h for h in hdrs if not h.endswith("lmc_spec.cuh")]
     if "lmc_spec_tf_inst" not in src:
         hdrs = [h for h in hdrs if not h.endswith("lmc_spec_tf.cuh")]
+    if "lmc_spec_c64_inst" not in src:
+        hdrs = [h for h in hdrs if not h.endswith("lmc_spec_c64.cuh")]
     if "lmc_wl_inst" not in src:
         hdrs = [h for h in hdrs if not h.endswith("lmc_wl.cuh")]
     return [src, os.path.join(HERE, "..", "include", "lmc.h"), *hdrs]
@@ -68,6 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     jobs.append((os.path.join(CSRC, "lmc_spec_inst2.cu"), os.path.join(objdir, "lmc_spec2.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_inst3.cu"), os.path.join(objdir, "lmc_spec3.o"), [], force))
     jobs.append((os.path.join(CSRC, "lmc_spec_tf_inst.cu"), os.path.join(objdir, "lmc_spec_tf.o"), [], force))
+    jobs.append((os.path.join(CSRC, "lmc_spec_c64_inst.cu"), os.path.join(objdir, "lmc_spec_c64.o"), [], force))
     log = []
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(jobs))) as ex:
         for cmd, r in ex.map(_compile, jobs):

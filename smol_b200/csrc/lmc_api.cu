@@ -20,6 +20,7 @@ using namespace lmc;
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_c64_launches{0};   // launches of the compact-word kernel
 static std::atomic<long long> g_env_launches{0};   // launches of the environment-word variants (tests / diagnostics)
 
 static int fail(const std::string& msg) {
@@ -69,6 +70,7 @@ extern "C" const char* lmc_last_error(void) { return g_err.c_str(); }
 extern "C" int lmc_row_stride(int n) { return (n + 16) & ~15; }   // always at least one zero pad byte behind the row
 extern "C" int64_t lmc_launch_count(void) { return g_launches.load(); }
 extern "C" int64_t lmc_env_launch_count(void) { return g_env_launches.load(); }
+extern "C" int64_t lmc_c64_launch_count(void) { return g_c64_launches.load(); }
 extern "C" int lmc_model_num_features(const LmcModel* m) { return m ? m->dm.F : -1; }
 
 extern "C" int lmc_model_destroy(LmcModel* m) {
@@ -472,6 +474,107 @@ static void build_env_tables(const LmcModelDesc* d, const SpecTables& sp, EnvTab
   ev.ok = 1; ev.b = b; ev.nrl = nrl; ev.nrlp = nrlp; ev.wide = wide; ev.NA = NA; ev.pair_ok = want_pair ? 1 : 0;
 }
 
+// Compact environment words of lmc_spec_c64.cuh: ONE 64-bit word per active site and walker, in shared memory.  Every
+// merged record owns a field of three codes (3 b bits) inside the word of its site; a record whose first gathered site is
+// the last one of another record starts on that record's last slot (chains of overlapping fields), which is what brings
+// the 22 records of the FCC cluster set from 66 to 64 bits.  Per record the kernel needs the table base and the shift of
+// the field: one u32 list per lane of the four-lane step group, deduplicated over sites (translation-equivalent sites
+// share theirs) and staged with the table blob.  An accepted flip of site s xors (old ^ new) into the bits that hold s in
+// the words of the sites that gather it (reverse map); the second flip of a swap sees the first through the pair mask.
+struct C64Tables {
+  int ok = 0, b = 0, nrl = 0, nrlp = 0, NA = 0, RV = 0, ncls = 0, bits = 0;
+  std::vector<uint32_t> desc;              // [ncls][4][nrlp] table base | shift << 16 of the lane's i-th record
+  std::vector<uint8_t> cls;                // [N] class of a site
+  std::vector<uint32_t> rev;               // [NA][RV] active index of the gathering site | bit << 16; ~0 = none
+  std::vector<unsigned long long> pair;    // [NA][NA] bits of the ROW site's word that hold the COLUMN site (lowest bit of each slot)
+};
+
+static void build_c64_tables(const LmcModelDesc* d, const SpecTables& sp, C64Tables& ct) {
+  ct = C64Tables();
+  if (!sp.ok || getenv("LMC_SPEC_C64_OFF")) return;
+  const int N = d->num_sites, NQ = sp.NQ, NC = sp.NC;
+  if (NC > 4) return;
+  const int b = NC <= 2 ? 1 : 2, fb = 3 * b;
+  const int nrl = NQ / 4, nrlp = (nrl + 3) & ~3;
+  const int NA = d->sl_site_off[d->num_sublattices];
+  if (NA <= 0 || NA > 65535 || (size_t)NA * NA * 8 > (size_t(64) << 20)) return;
+  std::vector<int> aidx(N, -1);
+  for (int a = 0; a < NA; ++a) {
+    const int s = d->sl_sites[a];
+    if (s < 0 || s >= N || aidx[s] >= 0) return;
+    aidx[s] = a;
+  }
+  const uint32_t* rec = reinterpret_cast<const uint32_t*>(sp.rec.data());
+  std::vector<std::vector<uint32_t>> rev(NA);
+  ct.pair.assign((size_t)NA * NA, 0ull);
+  ct.cls.assign(N, 0);
+  std::map<std::vector<uint32_t>, int> seen;
+  int maxbits = 0;
+  std::vector<int> S0(NQ), S1(NQ), S2(NQ), TB(NQ), succ(NQ), pred(NQ), pos(NQ);
+  for (int k = 0; k < N; ++k) {
+    for (int r = 0; r < NQ; ++r) {
+      const uint32_t x = rec[((size_t)k * NQ + r) * 2], y = rec[((size_t)k * NQ + r) * 2 + 1];
+      S0[r] = (int)(x & 0xffffu); S1[r] = (int)(x >> 16); S2[r] = (int)(y & 0xffffu); TB[r] = (int)(y >> 16);
+      succ[r] = pred[r] = -1; pos[r] = 0;
+    }
+    auto real = [&](int r) { return TB[r] != 0 || S0[r] < N || S1[r] < N || S2[r] < N; };
+    // chains: B starts on A's last slot when that is the site B gathers first
+    for (int a = 0; a < NQ; ++a) {
+      if (!real(a) || S2[a] >= N) continue;
+      for (int c = 0; c < NQ && succ[a] < 0; ++c) {
+        if (c == a || !real(c) || pred[c] >= 0 || S0[c] != S2[a]) continue;
+        bool cycle = false;
+        for (int w = c; w >= 0 && !cycle; w = succ[w]) cycle = w == a;
+        if (cycle) continue;
+        succ[a] = c; pred[c] = a;
+      }
+    }
+    int at = 0;
+    for (int h = 0; h < NQ; ++h) {
+      if (!real(h) || pred[h] >= 0) continue;
+      int w = h;
+      pos[w] = at;
+      while (succ[w] >= 0) { pos[succ[w]] = pos[w] + 2 * b; w = succ[w]; }
+      at = pos[w] + fb;
+    }
+    maxbits = std::max(maxbits, at);
+    if (at > 64) return;
+    std::vector<uint32_t> row((size_t)4 * nrlp, 0u);
+    for (int l = 0; l < 4; ++l)
+      for (int i = 0; i < nrl; ++i) {
+        const int r = 2 * (l + 4 * (i >> 1)) + (i & 1);
+        row[(size_t)l * nrlp + i] = (uint32_t)TB[r] | ((uint32_t)pos[r] << 16);
+      }
+    auto it = seen.find(row);
+    if (it == seen.end()) {
+      if (seen.size() >= 256 || (seen.size() + 1) * row.size() * 4 > 8 * 1024) return;
+      it = seen.emplace(row, (int)seen.size()).first;
+      ct.desc.insert(ct.desc.end(), row.begin(), row.end());
+    }
+    ct.cls[k] = (uint8_t)it->second;
+    if (aidx[k] < 0) continue;
+    for (int r = 0; r < NQ; ++r) {
+      if (!real(r)) continue;
+      const int site[3] = {S0[r], S1[r], S2[r]};
+      for (int j = 0; j < 3; ++j) {
+        const int s = site[j];
+        if (s >= N || aidx[s] < 0) continue;
+        const int bit = pos[r] + j * b;
+        unsigned long long& pm = ct.pair[(size_t)aidx[k] * NA + aidx[s]];
+        if (pm & (1ull << bit)) continue;           // the shared slot of two chained records: one entry
+        pm |= 1ull << bit;
+        rev[aidx[s]].push_back((uint32_t)aidx[k] | ((uint32_t)bit << 16));
+      }
+    }
+  }
+  size_t rv = 1;
+  for (int a = 0; a < NA; ++a) rv = std::max(rv, rev[a].size());
+  ct.RV = (int)((rv + 31) & ~size_t(31));
+  ct.rev.assign((size_t)NA * ct.RV, 0xffffffffu);
+  for (int a = 0; a < NA; ++a) std::copy(rev[a].begin(), rev[a].end(), ct.rev.begin() + (size_t)a * ct.RV);
+  ct.ok = 1; ct.b = b; ct.nrl = nrl; ct.nrlp = nrlp; ct.NA = NA; ct.ncls = (int)seen.size(); ct.bits = maxbits;
+}
+
 // host-only: build the tables of the speculative kernel for a model description (tests / diagnostics)
 // info = {ok, NC, L, NQ, nblocks, merged, table bytes, record bytes}
 extern "C" int lmc_spec_tables_host(const LmcModelDesc* d, int32_t* info, double* dtab_out, int64_t dtab_cap,
@@ -490,6 +593,28 @@ extern "C" int lmc_spec_tables_host(const LmcModelDesc* d, int32_t* info, double
   return 0;
 }
 
+// host-only: compact environment-word tables of a model description (tests / diagnostics)
+// info = {ok, bits per code, records per lane, padded records per lane, active sites, reverse entries per site, classes, bits used}
+extern "C" int lmc_spec_c64_host(const LmcModelDesc* d, int32_t* info, uint32_t* desc_out, int64_t desc_cap, uint8_t* cls_out,
+                                 int64_t cls_cap, uint32_t* rev_out, int64_t rev_cap, uint64_t* pair_out, int64_t pair_cap) {
+  if (!d || !info) return fail("null argument");
+  std::vector<OrbDev> orbs;
+  std::vector<double> tabA;
+  bool kone = true;
+  if (host_orbits(d, orbs, tabA, kone)) return -1;
+  SpecTables sp;
+  build_spec_tables(d, orbs, tabA, kone, sp);
+  C64Tables ct;
+  build_c64_tables(d, sp, ct);
+  info[0] = ct.ok; info[1] = ct.b; info[2] = ct.nrl; info[3] = ct.nrlp; info[4] = ct.NA; info[5] = ct.RV; info[6] = ct.ncls;
+  info[7] = ct.bits;
+  if (desc_out && (int64_t)ct.desc.size() <= desc_cap) memcpy(desc_out, ct.desc.data(), ct.desc.size() * 4);
+  if (cls_out && (int64_t)ct.cls.size() <= cls_cap) memcpy(cls_out, ct.cls.data(), ct.cls.size());
+  if (rev_out && (int64_t)ct.rev.size() <= rev_cap) memcpy(rev_out, ct.rev.data(), ct.rev.size() * 4);
+  if (pair_out && (int64_t)ct.pair.size() <= pair_cap) memcpy(pair_out, ct.pair.data(), ct.pair.size() * 8);
+  return 0;
+}
+
 // host-only: environment-word tables of a model description (tests / diagnostics)
 // info = {ok, bits per code, records per lane, padded records per lane, wide, active sites, reverse entries per site, pair table built}
 extern "C" int lmc_spec_env_host(const LmcModelDesc* d, int32_t* info, uint16_t* tb_out, int64_t tb_cap, uint32_t* rev_out,
@@ -503,6 +628,8 @@ extern "C" int lmc_spec_env_host(const LmcModelDesc* d, int32_t* info, uint16_t*
   build_spec_tables(d, orbs, tabA, kone, sp);
   EnvTables ev;
   build_env_tables(d, sp, ev);
+  C64Tables c64;
+  build_c64_tables(d, sp, c64);
   info[0] = ev.ok; info[1] = ev.b; info[2] = ev.nrl; info[3] = ev.nrlp; info[4] = ev.wide; info[5] = ev.NA; info[6] = ev.RV;
   info[7] = ev.pair_ok;
   if (tb_out && (int64_t)ev.tb.size() <= tb_cap) memcpy(tb_out, ev.tb.data(), ev.tb.size() * 2);
@@ -660,6 +787,8 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
   m.spOK = sp.ok; m.spNC = sp.NC; m.spL = sp.L; m.spNQ = sp.NQ; m.spSb = sp.NQ * 8;
   EnvTables ev;
   build_env_tables(d, sp, ev);
+  C64Tables c64;
+  build_c64_tables(d, sp, c64);
   // blob: cls (nCls + 1 entries, the last is the all-zero padding class) | tabA | nat | orb
   {
     const int C = m.nCls + 1;
@@ -675,6 +804,9 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     // DIFFERENT entries at once: shared memory serves that, the constant bank serialises it); filled below
     m.off_ctab = (int)off; off += 3 * LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 8;
     m.blob_bytes = (int)off;      // what every kernel but the environment-word variants stages
+    m.off_c64desc = (int)off; off += (c64.desc.size() * 4 + 15) & ~size_t(15);
+    m.off_c64cls = (int)off; off += (c64.cls.size() * (c64.ok ? 1 : 0) + 15) & ~size_t(15);
+    m.blob_c64_bytes = (int)off;
     m.off_envtb = (int)off; off += (ev.tbc.size() * 2 + 15) & ~size_t(15);
     m.off_envcls = (int)off; off += (ev.cls.size() + 15) & ~size_t(15);
     m.blob_env_bytes = (int)off;
@@ -698,6 +830,10 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     memcpy(blob.data() + m.off_orb, orbs.data(), (size_t)m.nOrb * sizeof(OrbDev));
     if (!qtab.empty()) memcpy(blob.data() + m.off_qtab, qtab.data(), qtab.size() * 8);
     if (!dtab.empty()) memcpy(blob.data() + m.off_dtab, dtab.data(), dtab.size() * 8);
+    if (c64.ok) {
+      memcpy(blob.data() + m.off_c64desc, c64.desc.data(), c64.desc.size() * 4);
+      memcpy(blob.data() + m.off_c64cls, c64.cls.data(), c64.cls.size());
+    }
     if (ev.ncls) {
       memcpy(blob.data() + m.off_envtb, ev.tbc.data(), ev.tbc.size() * 2);
       memcpy(blob.data() + m.off_envcls, ev.cls.data(), ev.cls.size());
@@ -706,6 +842,13 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
     if (m.spOK) UP(unsigned char, sprec.data(), sprec.size(), m.sp_rec);
     m.spFtab = nullptr;
     if (m.spOK && !sp.ftab.empty()) UP(double, sp.ftab.data(), sp.ftab.size(), m.spFtab);
+    m.c64OK = c64.ok; m.c64B = c64.b; m.c64NRL = c64.nrl; m.c64NRLP = c64.nrlp; m.c64NA = c64.NA; m.c64RV = c64.RV;
+    m.c64NCls = c64.ncls; m.c64Bits = c64.bits;
+    m.c64Rev = nullptr; m.c64Pair = nullptr;
+    if (c64.ok) {
+      UP(uint32_t, c64.rev.data(), c64.rev.size(), m.c64Rev);
+      UP(unsigned long long, c64.pair.data(), c64.pair.size(), m.c64Pair);
+    }
     m.envNCls = ev.ncls;
     m.envOK = ev.ok; m.envB = ev.b; m.envNRL = ev.nrl; m.envNRLP = ev.nrlp; m.envWide = ev.wide; m.envNA = ev.NA;
     m.envRV = ev.RV;
@@ -1200,17 +1343,31 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     }
   }
   if (tf_spec) G = 32;
-  const int stash_slots = tf_spec ? 1 : a.max_flips;
+  // compact environment words in shared memory (lmc_spec_c64.cuh): the default of the speculative flip / swap kernel
+  // where the model has the tables and 28 walkers per SM (seven blocks of four) still fit beside their words
+  bool spec_c64 = use_spec && m.c64OK && !field && spec_sg == 4 && !spec_lists && c->block_threads == 0 && !getenv("LMC_SPEC_WIDE") &&
+                  c->spec_env_dev == nullptr;   // (a caller that hands in the L2 workspace asks for that variant)
+  if (const char* e = getenv("LMC_SPEC_C64")) spec_c64 = spec_c64 && atoi(e) != 0;
+  if (spec_c64) {
+    const size_t slab = (size_t)m.Npad + (((size_t)m.F * 8 + 15) & ~size_t(15)) +
+                        std::max<size_t>(((size_t)m.Rstride * stash_el + 15) & ~size_t(15), 32 * 16) +
+                        LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4 + ((m.plane_words * 4 + 15) & ~15) + ((m.plane_words * 2 + 15) & ~15) +
+                        (size_t)m.c64NA * 8;
+    if (7 * ((((size_t)m.blob_c64_bytes + 15) & ~size_t(15)) + 4 * slab + 1024) > 227 * 1024) spec_c64 = false;
+  }
+  const bool one_slot = tf_spec || spec_c64;   // one stash slot (the commit evaluates and folds flip by flip) that also holds the ring(s)
+  const int stash_slots = one_slot ? 1 : a.max_flips;
   size_t stash_bytes = ((size_t)stash_slots * m.Rstride * stash_el + 15) & ~size_t(15);
   if (tf_spec) stash_bytes = std::max<size_t>(stash_bytes, 2 * 32 * 16);   // the two random-word rings live in the idle stash
+  if (spec_c64) stash_bytes = std::max<size_t>(stash_bytes, 32 * 16);
   a.off_cnt = a.off_stash + (int)stash_bytes;
   a.off_plane = a.off_cnt + LMC_MAX_SUBLATTICES * LMC_MAX_CODES * 4;
   a.off_ring = a.off_plane + ((m.plane_words * 4 + 15) & ~15);   // species bit-planes
-  a.off_eidx = a.off_ring + (tf_spec ? 0 : G * 16);                   // per-lane precomputed proposals
-  if (tf_spec) a.off_ring = a.off_stash;
+  a.off_eidx = a.off_ring + (one_slot ? 0 : G * 16);                  // per-lane precomputed proposals
+  if (one_slot) a.off_ring = a.off_stash;
   a.ew_field = field ? c->ewald_field_dev : nullptr;
   a.off_lists = a.off_eidx + ((ewald && !field) ? (((m.ewK ? 1 : 2) * m.N + 15) & ~15) : 0);  // per-site Ewald cache (u8 charge index or u16 row)
-  if (tf_spec) a.off_lists = a.off_eidx + ((m.plane_words * 2 + 15) & ~15);   // (off_eidx: prefix popcounts of the plane words, u16)
+  if (one_slot) a.off_lists = a.off_eidx + ((m.plane_words * 2 + 15) & ~15);   // (off_eidx: prefix popcounts of the plane words, u16)
   a.off_bias = a.off_lists + (spec_lists ? ((m.list_entries * 2 + 15) & ~15) : 0);   // sorted position lists
   a.off_dist = a.off_bias + (c->bias_mode != LMC_BIAS_NONE ? 16 * ((1 + LMC_MAX_BIAS_ROWS + 1) / 2) : 0);   // running bias value and table sums
   a.walker_smem = a.off_dist + (dist ? ((3 * m.F * 8 + 15) & ~15) : 0);   // distance processor: vector, delta, new distances
@@ -1225,6 +1382,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
     a.off_wl = a.walker_smem;
     a.walker_smem += (c->wl.num_bins * 16 + 15) & ~15;
   }
+  a.off_env64 = a.walker_smem;
+  if (spec_c64) a.walker_smem += (m.c64NA * 8 + 15) & ~15;
   a.dist_ngrp = c->dist_num_groups; a.dist_tol = c->dist_tol; a.dist_target = c->dist_target_dev;
   a.dist_grp_off = c->dist_group_off_dev; a.dist_grp_idx = c->dist_group_idx_dev; a.dist_grp_diam = c->dist_group_diam_dev;
   a.dist_vec = c->dist_vector_dev;
@@ -1234,7 +1393,8 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
                   (c->usher == LMC_USHER_FLIP || m.envPair != nullptr);
   if (const char* e = getenv("LMC_SPEC_ENV")) spec_env = spec_env && atoi(e) != 0;
   a.env = spec_env ? reinterpret_cast<uint32_t*>(c->spec_env_dev) : nullptr;
-  const size_t blob = ((size_t)(use_spec ? (spec_env ? m.blob_env_bytes : m.blob_bytes) : m.off_dtab) + 15) & ~size_t(15);
+  if (spec_c64) spec_env = false;
+  const size_t blob = ((size_t)(use_spec ? (spec_c64 ? m.blob_c64_bytes : (spec_env ? m.blob_env_bytes : m.blob_bytes)) : m.off_dtab) + 15) & ~size_t(15);
   size_t smem = 0;
   if (auto_threads && relaxed) {
     // shared memory limits residency here: take the block size with the most resident walkers per SM
@@ -1325,7 +1485,9 @@ extern "C" int lmc_run(const LmcModel* mdl, const LmcRunConfig* c, void* stream)
   const bool wl = c->kernel == LMC_KERNEL_WANGLANDAU;
   const int ewmode = !ewald ? 0 : (field ? 2 : 1);   // Ewald path of the classic kernels
   spec_wide = spec_wide && threads == 448;
-  if (spec_env) { rc = launch_spec_env(m, a, m.kone != 0, c->usher, field, spec_wide, lc); g_env_launches++; }
+  if (spec_c64 && threads == 128 && !spec_wide) { rc = launch_spec_c64(m, a, m.kone != 0, c->usher, lc); g_c64_launches++; }
+  else if (spec_c64) return fail("internal: the compact-word kernel was planned for blocks of four walkers");
+  else if (spec_env) { rc = launch_spec_env(m, a, m.kone != 0, c->usher, field, spec_wide, lc); g_env_launches++; }
   else if (use_spec && (field || spec_wide)) rc = launch_spec_x(m, a, m.kone != 0, c->usher, field, spec_wide, lc);
   else if (use_spec) rc = launch_spec(m, a, m.kone != 0, c->usher, spec_sg, spec_lists, lc);
   else if (dist) rc = launch_run_dist(m, a, m.kone != 0, c->usher, lc);

@@ -22,6 +22,8 @@ int launch_spec(const DevModel& m, const RunArgs& a, bool kone, int usher, int s
 int launch_spec_x(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
 // environment-word variants (RunArgs.env), four lanes per step
 int launch_spec_env(const DevModel& m, const RunArgs& a, bool kone, int usher, bool ewf, bool wide, const LaunchCfg& lc);
+// compact environment words in shared memory (lmc_spec_c64.cuh): Metropolis flip / swap, four walkers per block
+int launch_spec_c64(const DevModel& m, const RunArgs& a, bool kone, int usher, const LaunchCfg& lc);
 // speculative table-flip kernel (lmc_spec_tf.cuh): up to 16 walkers per block, ewf = Ewald through the potential cache
 int launch_spec_tf(const DevModel& m, const RunArgs& a, bool kone, bool ewf, const LaunchCfg& lc);
 // distance processors (Metropolis flip / swap, G = 32)

@@ -105,6 +105,13 @@ struct DevModel {
   int blob_env_bytes;          // blob size including them (what the environment-word variants stage)
   const uint16_t* envTb;   // [N][4][envNRLP] table base of the lane's i-th record
   const uint32_t* envRev;  // [envNA][envRV] gathering site (active index) | bit position << 16; 0xffffffff = none
+  // compact environment words (lmc_spec_c64.cuh, build_c64_tables in lmc_api.cu): one 64-bit word per active site and
+  // walker in SHARED memory
+  int c64OK, c64B, c64NRL, c64NRLP, c64NA, c64RV, c64NCls, c64Bits;
+  int off_c64desc, off_c64cls;   // blob, behind blob_bytes: [c64NCls][4][c64NRLP] u32 (table base | shift << 16), [N] u8 class of a site
+  int blob_c64_bytes;            // blob size including them (what the compact-word kernel stages)
+  const uint32_t* c64Rev;        // [c64NA][c64RV] gathering site (active index) | bit << 16; 0xffffffff = none
+  const unsigned long long* c64Pair;   // [c64NA][c64NA] bits of the row site's word that hold the column site
   const unsigned char* envPair;   // [envNA][envNA][4] x (u32 | u64 if envWide): lowest slot bits, per lane chunk, where the column
                                   // site sits among the codes the row site gathers; nullptr when not built (swaps need it)
 };
@@ -156,6 +163,7 @@ struct RunArgs {
   const uint8_t* mask;        // [W] multicell: walkers taking part in this launch (nullptr = all)
   const double* acc_off;      // [W] multicell: enthalpy offset inside the Metropolis exponent (nullptr = 0)
   uint32_t* env;      // [W][envNA][4 or 8] environment words of the walkers (ENV variants), workspace rebuilt by every launch
+  int off_env64;      // compact environment words in the walker's slab: [c64NA] x u64
   int max_flips;      // flips per step of the selected usher (stash slots)
   int seq_flips;      // debug: evaluate the flips of a step strictly one after another
 };

@@ -241,6 +241,10 @@ class LmcEngine:
     def launch_count(self) -> int:
         return int(self.lib.lmc_launch_count())
 
+    def c64_launch_count(self) -> int:
+        """launches of the speculative kernel over compact environment words (process-wide)"""
+        return int(self.lib.lmc_c64_launch_count())
+
     def env_launch_count(self) -> int:
         """launches of the speculative kernel's environment-word variants (process-wide)"""
         return int(self.lib.lmc_env_launch_count())
