@@ -78,22 +78,29 @@ __device__ __forceinline__ int c64_select_ne(const uint32_t* planes, const uint1
   return lo * 32 + spec_nth_bit(word, k - (32 * lo - (int)pfx[base + lo]));
 }
 
-// words of every active site from the occupancy row (whole warp, start of a launch)
+// words of every active site from the occupancy row (whole warp, start of a launch): four lanes per site, each with
+// the records of one lane chunk (their loads come from L2 and are independent), combined by shuffles
 __device__ __forceinline__ void c64_build(const DevModel& m, const unsigned char* smem, unsigned long long* env, const uint8_t* occ, int g) {
   const uint32_t b = (uint32_t)m.c64B;
   const uint32_t* dbase = reinterpret_cast<const uint32_t*>(smem + m.off_c64desc);
-  for (int ai = g; ai < m.c64NA; ai += 32) {
-    const int site = __ldg(m.sl_sites + ai);
-    const uint2* rp = reinterpret_cast<const uint2*>(m.sp_rec + (size_t)site * m.spSb);
-    const uint32_t* dsc = dbase + (int)smem[m.off_c64cls + site] * 4 * m.c64NRLP;
+  const int l = g & 3;
+  for (int a0 = 0; a0 < m.c64NA; a0 += 8) {   // uniform
+    const int ai = a0 + (g >> 2);
     unsigned long long e = 0ull;
-    for (int l = 0; l < 4; ++l)
+    if (ai < m.c64NA) {
+      const int site = __ldg(m.sl_sites + ai);
+      const uint2* rp = reinterpret_cast<const uint2*>(m.sp_rec + (size_t)site * m.spSb);
+      const uint32_t* dsc = dbase + ((int)smem[m.off_c64cls + site] * 4 + l) * m.c64NRLP;
+#pragma unroll 6
       for (int i = 0; i < m.c64NRL; ++i) {
         const uint2 rc = __ldg(rp + 2 * (l + 4 * (i >> 1)) + (i & 1));
         const uint32_t field = (uint32_t)occ[rc.x & 0xffffu] | ((uint32_t)occ[rc.x >> 16] << b) | ((uint32_t)occ[rc.y & 0xffffu] << (2u * b));
-        e |= (unsigned long long)field << (dsc[l * m.c64NRLP + i] >> 16);   // (overlapping fields carry the same codes)
+        e |= (unsigned long long)field << (dsc[i] >> 16);   // (overlapping fields carry the same codes)
       }
-    env[ai] = e;
+    }
+    e |= __shfl_xor_sync(0xffffffffu, e, 1);
+    e |= __shfl_xor_sync(0xffffffffu, e, 2);
+    if (ai < m.c64NA && l == 0) env[ai] = e;
   }
 }
 
