@@ -39,28 +39,21 @@ __device__ __forceinline__ void c64_pairs(const double* Dn, unsigned long long e
   }
 }
 
-template <int EB, bool P2>
-__device__ __forceinline__ double c64_flip_energy_p(const DevModel& m, const double* Dn, unsigned long long e, const uint32_t* dsc, uint32_t NC) {
-  double a0 = 0.0, a1 = 0.0;
-  switch (m.c64NRL) {   // kernel parameter: a uniform branch; straight-line code for the usual record counts
-    case 2: c64_pairs<EB, P2, 1>(Dn, e, dsc, NC, a0, a1); break;
-    case 4: c64_pairs<EB, P2, 2>(Dn, e, dsc, NC, a0, a1); break;
-    case 6: c64_pairs<EB, P2, 3>(Dn, e, dsc, NC, a0, a1); break;
-    case 8: c64_pairs<EB, P2, 4>(Dn, e, dsc, NC, a0, a1); break;
-    default:
-      for (int i0 = 0; i0 < m.c64NRL; i0 += 2) c64_pairs<EB, P2, 1>(Dn, e, dsc + i0, NC, a0, a1);
-  }
-  return a0 + a1;
-}
-
-template <int EB>
+// scaled energy change of one flip.  NPAIR > 0: that many record pairs per lane as straight-line code (the kernel is
+// instantiated for the usual count, three); NPAIR == 0: a loop over the model's count
+template <int EB, bool P2, int NPAIR>
 __device__ __forceinline__ double c64_flip_energy(const DevModel& m, const unsigned char* smem, const double* dtab,
                                                   unsigned long long e, int site, int oldc, int newc, int l) {
   const uint32_t* dsc = reinterpret_cast<const uint32_t*>(smem + m.off_c64desc) + ((int)smem[m.off_c64cls + site] * 4 + l) * m.c64NRLP;
   const double* Dn = dtab + newc * m.spL + oldc;   // the old code is the fastest index of a block
-  const uint32_t NC = (uint32_t)m.spNC;
-  if (NC == (1u << EB)) return c64_flip_energy_p<EB, true>(m, Dn, e, dsc, NC);
-  return c64_flip_energy_p<EB, false>(m, Dn, e, dsc, NC);
+  const uint32_t NC = P2 ? (1u << EB) : (uint32_t)m.spNC;
+  double a0 = 0.0, a1 = 0.0;
+  if (NPAIR > 0) {
+    c64_pairs<EB, P2, NPAIR ? NPAIR : 1>(Dn, e, dsc, NC, a0, a1);
+  } else {
+    for (int i0 = 0; i0 < m.c64NRL; i0 += 2) c64_pairs<EB, P2, 1>(Dn, e, dsc + i0, NC, a0, a1);
+  }
+  return a0 + a1;
 }
 
 // k-th (0-based) active position of a sublattice whose code differs from `code` (Swap.propose_step, mcusher.py:190-196),
@@ -116,7 +109,9 @@ __device__ __forceinline__ void c64_commit(const DevModel& m, unsigned long long
   }
 }
 
-template <bool KONE, int USHER, int EB>
+// P2: the code radix of the difference table is 2^EB (the field of a record IS its table index); NPAIR: record pairs per
+// lane known at compile time (0: read from the model)
+template <bool KONE, int USHER, int EB, bool P2, int NPAIR>
 __global__ void __launch_bounds__(128, 7) lmc_spec_c64_kernel(const DevModel m, const RunArgs a) {
   static_assert(USHER == LMC_USHER_FLIP || USHER == LMC_USHER_SWAP, "flip / swap only");
   static_assert(EB == 1 || EB == 2, "one or two bits per species code");
@@ -257,9 +252,9 @@ __global__ void __launch_bounds__(128, 7) lmc_spec_c64_kernel(const DevModel m, 
       // ------------------------------ evaluate ------------------------------------------------
       double acc = 0.0, dmu = 0.0;
       if (live && n > 0) {
-        acc = c64_flip_energy<EB>(m, smem, dtab, e1, site1, s1, s2, l);
+        acc = c64_flip_energy<EB, P2, NPAIR>(m, smem, dtab, e1, site1, s1, s2, l);
         if (USHER == LMC_USHER_SWAP)
-          acc += c64_flip_energy<EB>(m, smem, dtab, e2 ^ (pm2 * (unsigned long long)(s1 ^ s2)), site2, s2, s1, l);
+          acc += c64_flip_energy<EB, P2, NPAIR>(m, smem, dtab, e2 ^ (pm2 * (unsigned long long)(s1 ^ s2)), site2, s2, s1, l);
       }
       acc += __shfl_xor_sync(FULL, acc, 1);
       acc += __shfl_xor_sync(FULL, acc, 2);
