@@ -152,11 +152,12 @@ class Config2(Workload):
         return M.random_occupancies(self.subspace(), self.supercell(), W, seed=seed, balanced=True)
 
     def built_bytes(self, acceptance, ewald_cache=False):
-        # speculative kernel + cover merge: 22 records x 3 byte gathers per flip, 2 flips; an accepted step is
-        # re-evaluated with the classic records (213 gathers per flip) and writes 2 bytes
-        b = 2 * 66 + acceptance * (2 * 213 + 2) + (512 + 64 + 9) / 512
-        return b, ("cover-merged records: 2 x 66 int8 gathers per attempted swap + (2 x 213 gathers + 2 writes) per "
-                   "ACCEPTED swap + trace / thin_by")
+        # speculative kernel over compact environment words: per attempted swap the two sites' 64-bit words + the pair
+        # mask + the 2 occupancy bytes of the proposal; an accepted swap is re-evaluated with the classic records (213
+        # gathers per flip), writes 2 bytes and xors one bit into the words of the ~54 sites around each changed site
+        b = 2 * 8 + 8 + 2 + acceptance * (2 * 213 + 2 + 2 * 64 * 8) + (512 + 64 + 9) / 512
+        return b, ("compact environment words: 2 x 8 B site words + 8 B pair mask + 2 occupancy bytes per attempted swap + "
+                   "(2 x 213 gathers + 2 writes + 2 x 64 word updates) per ACCEPTED swap + trace / thin_by")
 
 
 class Config3(Workload):
