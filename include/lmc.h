@@ -265,7 +265,8 @@ int lmc_model_num_features(const LmcModel* model);
 /* info[0] = 1 if the Ewald matrix factorises as M[i,j] = q_i q_j K[site_i, site_j] (potential cache usable),
  * info[1] = speculative-kernel tables built, info[2] = bytes of the staged table blob, info[3] = records per site
  * of the speculative kernel, info[4] = bytes per walker of LmcRunConfig.spec_env_dev (0: environment words not
- * available for this model); entries beyond `n` are not written */
+ * available for this model), info[5] = bits per site of the compact environment words the speculative flip / swap kernel
+ * keeps in shared memory (0: the records do not fit 64 bits, occupancy gathers); entries beyond `n` are not written */
 int lmc_model_info(const LmcModel* model, int32_t* info, int n);
 
 /* int32 [W][N] <-> int8 [W][row_stride] */

@@ -1047,9 +1047,9 @@ extern "C" int lmc_model_create(const LmcModelDesc* d, LmcModel** out) {
 extern "C" int lmc_model_info(const LmcModel* mdl, int32_t* info, int n) {
   if (!mdl || !info) return fail("null argument");
   const DevModel& m = mdl->dm;
-  const int32_t v[5] = {m.E > 0 && m.ewK != nullptr, m.spOK, m.blob_bytes, m.spNQ,
-                        m.envOK ? m.envNA * (m.envWide ? 32 : 16) : 0};
-  for (int i = 0; i < n && i < 5; ++i) info[i] = v[i];
+  const int32_t v[6] = {m.E > 0 && m.ewK != nullptr, m.spOK, m.blob_bytes, m.spNQ,
+                        m.envOK ? m.envNA * (m.envWide ? 32 : 16) : 0, m.c64OK ? m.c64Bits : 0};
+  for (int i = 0; i < n && i < 6; ++i) info[i] = v[i];
   return 0;
 }
 

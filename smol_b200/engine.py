@@ -191,10 +191,11 @@ class LmcEngine:
 
     def model_info(self):
         """(Ewald matrix factorises, speculative tables built, table blob bytes, speculative records per site,
-        bytes per walker of the environment-word workspace ``LmcRunConfig.spec_env_dev`` or 0)"""
+        bytes per walker of the environment-word workspace ``LmcRunConfig.spec_env_dev`` or 0, bits per site of the
+        compact environment words or 0)"""
         if getattr(self, "_info", None) is None:
-            info = (C.c_int32 * 5)()
-            capi.check(self.lib.lmc_model_info(self.handle, info, 5))
+            info = (C.c_int32 * 6)()
+            capi.check(self.lib.lmc_model_info(self.handle, info, 6))
             self._info = tuple(int(x) for x in info)
         return self._info
 

@@ -640,16 +640,18 @@ def test_bias_rejected_where_the_reference_rejects_it(cuda_device):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["decomposition", "expansion"])
 @pytest.mark.parametrize("n,T,thin", [(2, 1000.0, 20), (4, 300.0, 7), (4, 1000.0, 64), (3, 1e5, 13)])
-@pytest.mark.parametrize("sg", ["4", "4E", "4L", "2", "1"])
+@pytest.mark.parametrize("sg", ["4", "4G", "4E", "4L", "2", "1"])
 def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypatch):
     """low / medium / near-infinite temperature (acceptance ~0 .. ~1), sampling intervals that are not
     multiples of the batch, aliased 2x2x2 cell; spec_mode=2 forces the speculative kernel, 1 the classic
     one: both must reproduce the oracle chain bit for bit.  sg = lanes per speculated step, L = swap partner
-    from sorted position lists instead of the rank select, E = environment words instead of occupancy gathers
-    (``Sampler(spec_env=True)``, where the model has the tables)."""
+    from sorted position lists instead of the rank select, E = environment words in L2 instead of occupancy gathers
+    (``Sampler(spec_env=True)``, where the model has the tables); "4" takes the compact environment words in shared memory
+    (csrc/lmc_spec_c64.cuh) where the model's records fit 64 bits per site, "4G" keeps the gathers."""
     import smol_b200 as S
     monkeypatch.setenv("LMC_SPEC_SG", sg[0])
     monkeypatch.setenv("LMC_SPEC_LISTS", "1" if sg.endswith("L") else "0")
+    monkeypatch.setenv("LMC_SPEC_C64", "0" if sg.endswith("G") else "1")
     O = _oracle()
     sub = M.fcc_subspace()
     scm = np.eye(3, dtype=int) * n
@@ -664,10 +666,14 @@ def test_speculative_swap_trajectory(cuda_device, kind, n, T, thin, sg, monkeypa
     occ0 = M.random_occupancies(sub, scm, W, seed=3, balanced=True)
     seeds = np.arange(500, 500 + W)
     nsteps = thin * 30
-    env0 = S.Sampler.from_ensemble(ens_g, T, step_type="swap", nwalkers=W, seeds=list(seeds)).engine.env_launch_count()
+    eng0 = S.Sampler.from_ensemble(ens_g, T, step_type="swap", nwalkers=W, seeds=list(seeds)).engine
+    env0, c640 = eng0.env_launch_count(), eng0.c64_launch_count()
     smp, ref, _ = _run_both(ens_g, ens_o, "swap", W, nsteps, thin, occ0, seeds, T=T,
                             usher_kwargs=dict(spec_mode=2, spec_env=sg.endswith("E")))
     _compare_traces(smp, ref)
+    # the compact-word kernel ran exactly where it is meant to: the default of the four-lane variant for these models
+    assert smp.engine.model_info()[5] > 0
+    assert (smp.engine.c64_launch_count() > c640) == (sg == "4")
     # the environment-word variant ran exactly where it is meant to (decomposition: merged records fit the lane chunks)
     took_env = smp.engine.env_launch_count() > env0
     assert took_env == (sg == "4E" and smp.engine.model_info()[4] > 0)

@@ -200,10 +200,11 @@ class Config3(Workload):
         # accepted flip re-evaluates (213 gathers), writes 1 byte, reads one row of the site kernel K (N f64) and
         # read-modify-writes the walker's potential row (2 x N f64)
         N = 1024
-        b = 66 + 8 + acceptance * (213 + 1 + 3 * 8 * N) + (N + 80 + 9) / 512
-        return b, ("66 int8 gathers + 1 cached potential (8 B) per attempted flip + (213 gathers + 1 write + K row "
-                   "8N + potential row RMW 16N) per ACCEPTED flip + trace / thin_by; the reference's two E-long "
-                   "matrix rows per flip are never read")
+        b = 66 + 8 + acceptance * (213 + 1 + 2 * 8 * N) + (N + 80 + 9) / 512
+        return b, ("66 int8 gathers + 1 cached potential (8 B) per attempted flip + (213 gathers + 1 write + potential "
+                   "row RMW 16N) per ACCEPTED flip + trace / thin_by; the rows of the site kernel K are a table shared by "
+                   "all walkers (L2 resident, not counted: SURVEY 8d accounting); the reference's two E-long matrix rows "
+                   "per flip are never read")
 
 
 class Config4(Workload):
@@ -350,10 +351,11 @@ class Config5(Workload):
             # changed site 64 merged records x 3 int8 gathers + the cached potential (8 B) + one element of K per earlier
             # flip of the step; an ACCEPTED step is re-evaluated with the classic records (~241 gathers per changed
             # site), reads one row of K per changed site and read-modify-writes the walker's potential row
-            b = 2.5 * (192 + 8 + 8 + 1) + acceptance * (2.5 * (241 + 8 * N) + 16 * N) + (N + 88 + 9) / self.thin_by
+            b = 2.5 * (192 + 8 + 8 + 1) + acceptance * (2.5 * 241 + 16 * N) + (N + 88 + 9) / self.thin_by
             return b, ("speculative table-flip kernel, potential cache: per changed site 192 int8 gathers (64 merged "
-                       "records) + 16 B of cached potential / K elements; per ACCEPTED step 2.5 x (241 gathers + one row "
-                       "of K, 8N B) + the potential row read-modify-write (16N B)")
+                       "records) + 16 B of cached potential / K elements; per ACCEPTED step 2.5 x 241 gathers + the "
+                       "walker's potential row read-modify-write (16N B); the rows of the site kernel K (2.5 x 8N B per "
+                       "accepted step) are a table shared by all walkers, L2 resident, not counted (SURVEY 8d accounting)")
         # Ewald through the factorised site kernel: per changed site ~241 gathers + ONE row of K (N f64) + the
         # walker's charge indices (N bytes); k ~ 2.5 changed sites per step
         b = 2.5 * (241 + 8 * N + N + 1) + (N + 88 + 9) / self.thin_by
