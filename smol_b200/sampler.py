@@ -618,7 +618,11 @@ class Sampler:
         # bookkeeping of chunk i overlap the kernel of chunk i+1 (double-buffered trace slots, copies
         # on a side stream).  The chains are unaffected: the RNG is counter based.
         nmax = max(1, min(S, int(max_chunk_bytes // max(per_sample, 1)))) if S else 0
-        if S >= 2 * pipeline_chunks:
+        if not block and stream_chunk == 0:
+            # non-blocking runs overlap their copies with the NEXT run's kernel: one launch per run (every launch pays
+            # the start-up of its blocks -- staging, bit-planes, environment words -- once more)
+            pass
+        elif S >= 2 * pipeline_chunks:
             nmax = min(nmax, -(-S // pipeline_chunks))
         elif S >= 2:
             nmax = min(nmax, -(-S // 2))
