@@ -718,6 +718,32 @@ def test_speculative_semigrand_flip_trajectory(cuda_device, T, sg, monkeypatch):
     assert (smp.engine.env_launch_count() > env0) == (sg == "4E")
 
 
+@pytest.mark.parametrize("kind,n", [("decomposition", 4), ("expansion", 3)])
+def test_speculative_semigrand_flip_binary_compact_words(cuda_device, kind, n):
+    """binary FCC, chemical potentials, single flips: the FLIP instantiations of the compact-word kernel
+    (csrc/lmc_spec_c64.cuh; three record pairs per lane as straight-line code on the 4x4x4 cell, the loop on 3x3x3)"""
+    import smol_b200 as S
+    O = _oracle()
+    sub = M.fcc_subspace()
+    scm = np.eye(3, dtype=int) * n
+    coefs = M.fcc_coefs(sub)
+    gpu_p, ora_p = _processors(kind, sub, scm, coefs)
+    mus = {"A": 0.0, "B": 0.15}
+    ens_g = S.Ensemble(gpu_p, chemical_potentials=mus)
+
+    def ens_o():
+        return O.Ensemble(ora_p, M.oracle_sublattices(O, ens_g.sublattices), chemical_potentials=mus)
+
+    W = 4
+    occ0 = M.random_occupancies(sub, scm, W, seed=14)
+    seeds = np.arange(210, 210 + W)
+    c640 = S.Sampler.from_ensemble(ens_g, 800.0, step_type="flip", nwalkers=W, seeds=list(seeds)).engine.c64_launch_count()
+    smp, ref, _ = _run_both(ens_g, ens_o, "flip", W, 390, 13, occ0, seeds, T=800.0, usher_kwargs=dict(spec_mode=2))
+    _compare_traces(smp, ref)
+    assert smp.engine.c64_launch_count() > c640
+    assert 0 < smp.samples.step_efficiency() < 1
+
+
 def test_speculative_two_sublattice_swap(cuda_device):
     """cation AND anion sublattices active (different record counts per site class), correlation basis"""
     import smol_b200 as S
